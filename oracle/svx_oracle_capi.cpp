@@ -1,0 +1,294 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see svx_oracle.hpp). Flat C entry points so that
+// tests/, smoke() and bench.py's CPU baseline can drive the restatement through ctypes.
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+#include "svx_oracle.hpp"
+
+using namespace svxo;
+
+// NodeStack<i32, SIZE> KAT driver (raytracing/tests.rs:817-911): ops[i] >= 0 pushes ops[i]; -1 pops; -2 reads last;
+// -3 adds 50 through last_mut. out[i] receives the popped / last value, or INT32_MIN for None. SIZE is 3 or 4.
+template <size_t SIZE>
+static void run_stack_script(const int32_t* ops, uint32_t n, int32_t* out) {
+    NodeStack<int32_t, SIZE> stack;
+    for (uint32_t i = 0; i < n; ++i) {
+        out[i] = INT32_MIN;
+        if (ops[i] >= 0) {
+            stack.push(ops[i]);
+        } else if (ops[i] == -1) {
+            int32_t v;
+            if (stack.pop(&v)) out[i] = v;
+        } else if (ops[i] == -2) {
+            if (const int32_t* l = stack.last()) out[i] = *l;
+        } else {
+            if (int32_t* l = stack.last_mut()) *l += 50;
+        }
+    }
+}
+extern "C" {
+
+struct svxo_entry {
+    uint32_t kind;  // 0 Empty, 1 Visual, 2 Informative, 3 Complex
+    uint8_t rgba[4];
+    uint32_t data;
+};
+
+struct svxo_hit {
+    uint32_t hit;
+    uint32_t palette_value;
+    svxo_entry entry;
+    float impact_point[3];
+    float normal[3];
+    float distance;  // (impact_point - ray.origin).length(), vector.rs:75-77
+    uint32_t node_iters, voxel_fetches, outer_iters, would_panic;
+};
+
+struct svxo_camera {
+    float origin[3];
+    float direction[3];
+    float glass_width, glass_height, glass_distance;
+};
+
+static Entry to_entry(const svxo_entry* e) {
+    Entry r;
+    r.kind = (EntryKind)e->kind;
+    r.albedo = Albedo{e->rgba[0], e->rgba[1], e->rgba[2], e->rgba[3]};
+    r.data = e->data;
+    return r;
+}
+static void from_entry(const Entry& e, svxo_entry* out) {
+    out->kind = (uint32_t)e.kind;
+    out->rgba[0] = e.albedo.r;
+    out->rgba[1] = e.albedo.g;
+    out->rgba[2] = e.albedo.b;
+    out->rgba[3] = e.albedo.a;
+    out->data = e.data;
+}
+
+int32_t svxo_octree_new(uint32_t size, uint32_t brick_dim, void** out) {
+    Octree* t = nullptr;
+    Status s = Octree::create(size, brick_dim, &t);
+    *out = t;
+    return s;
+}
+void svxo_octree_free(void* t) { delete (Octree*)t; }
+void svxo_octree_set_auto_simplify(void* t, int32_t v) { ((Octree*)t)->auto_simplify = v != 0; }
+uint32_t svxo_octree_size(void* t) { return ((Octree*)t)->get_size(); }
+
+int32_t svxo_octree_insert(void* t, uint32_t x, uint32_t y, uint32_t z, const svxo_entry* e) {
+    return ((Octree*)t)->insert(V3u{x, y, z}, to_entry(e));
+}
+int32_t svxo_octree_insert_at_lod(void* t, uint32_t x, uint32_t y, uint32_t z, uint32_t size, const svxo_entry* e) {
+    return ((Octree*)t)->insert_at_lod(V3u{x, y, z}, size, to_entry(e));
+}
+int32_t svxo_octree_update(void* t, uint32_t x, uint32_t y, uint32_t z, const svxo_entry* e) {
+    return ((Octree*)t)->update(V3u{x, y, z}, to_entry(e));
+}
+// Visual inserts in bulk: positions xyz[n][3], colours rgba[n][4]; optional per-voxel lod sizes (nullptr = 1)
+int32_t svxo_octree_insert_batch(void* t, const uint32_t* xyz, const uint8_t* rgba, const uint32_t* lod, uint64_t n) {
+    Octree* tree = (Octree*)t;
+    for (uint64_t i = 0; i < n; ++i) {
+        Entry e;
+        e.kind = EntryKind::Visual;
+        e.albedo = Albedo{rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2], rgba[4 * i + 3]};
+        const V3u p{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        const Status s = (lod && lod[i] > 1) ? tree->insert_at_lod(p, lod[i], e) : tree->insert(p, e);
+        if (s != OK) return s;
+    }
+    return OK;
+}
+void svxo_octree_get(void* t, uint32_t x, uint32_t y, uint32_t z, svxo_entry* out) {
+    from_entry(((Octree*)t)->get(V3u{x, y, z}), out);
+}
+// get() over a whole box, as palette-resolved (kind, rgba, data) triples: used for tree-equality sweeps
+void svxo_octree_get_sweep(void* t, uint32_t x0, uint32_t y0, uint32_t z0, uint32_t nx, uint32_t ny, uint32_t nz,
+                           svxo_entry* out) {
+    Octree* tree = (Octree*)t;
+    size_t i = 0;
+    for (uint32_t x = x0; x < x0 + nx; ++x)
+        for (uint32_t y = y0; y < y0 + ny; ++y)
+            for (uint32_t z = z0; z < z0 + nz; ++z) from_entry(tree->get(V3u{x, y, z}), &out[i++]);
+}
+uint64_t svxo_octree_structure_hash(void* t) { return ((Octree*)t)->structure_hash(); }
+uint64_t svxo_octree_node_count(void* t) { return ((Octree*)t)->nodes.len(); }
+uint64_t svxo_octree_palette_sizes(void* t, uint64_t* n_data) {
+    *n_data = ((Octree*)t)->voxel_data_palette.size();
+    return ((Octree*)t)->voxel_color_palette.size();
+}
+
+static void fill_hit(const Hit& h, const Ray& ray, const RayStats& st, svxo_hit* out) {
+    out->hit = h.hit ? 1 : 0;
+    out->palette_value = h.hit ? h.palette_value : 0xFFFFFFFFu;
+    from_entry(h.entry, &out->entry);
+    out->impact_point[0] = h.impact_point.x;
+    out->impact_point[1] = h.impact_point.y;
+    out->impact_point[2] = h.impact_point.z;
+    out->normal[0] = h.normal.x;
+    out->normal[1] = h.normal.y;
+    out->normal[2] = h.normal.z;
+    const V3f d = {h.impact_point.x - ray.origin.x, h.impact_point.y - ray.origin.y, h.impact_point.z - ray.origin.z};
+    out->distance = h.hit ? std::sqrt((d.x * d.x) + (d.y * d.y) + (d.z * d.z)) : 0.0f;
+    out->node_iters = st.node_iters;
+    out->voxel_fetches = st.voxel_fetches;
+    out->outer_iters = st.outer_iters;
+    out->would_panic = st.would_panic;
+}
+
+void svxo_octree_get_by_ray(void* t, const float origin[3], const float direction[3], svxo_hit* out) {
+    Ray ray{{origin[0], origin[1], origin[2]}, {direction[0], direction[1], direction[2]}};
+    RayStats st;
+    Hit h = ((Octree*)t)->get_by_ray(ray, &st);
+    fill_hit(h, ray, st, out);
+}
+
+// rays[n][6] = origin xyz, direction xyz
+void svxo_octree_get_by_rays(void* t, const float* rays, uint64_t n, svxo_hit* out) {
+    for (uint64_t i = 0; i < n; ++i) svxo_octree_get_by_ray(t, rays + 6 * i, rays + 6 * i + 3, &out[i]);
+}
+
+void svxo_make_pixel_ray(const svxo_camera* c, uint32_t w, uint32_t h, uint32_t x, uint32_t y, float out[6]) {
+    Camera cam{{c->origin[0], c->origin[1], c->origin[2]}, {c->direction[0], c->direction[1], c->direction[2]},
+               c->glass_width, c->glass_height, c->glass_distance};
+    Ray r = make_pixel_ray(cam, w, h, x, y);
+    out[0] = r.origin.x; out[1] = r.origin.y; out[2] = r.origin.z;
+    out[3] = r.direction.x; out[4] = r.direction.y; out[5] = r.direction.z;
+}
+
+// One frame of the caller loop of examples/cpu_render.rs:104-136. Pixel (x, y) is stored at image row h-1-y
+// (cpu_render.rs:106). Rows [row_begin, row_end) of the IMAGE are rendered (row = h-1-y), interleaved over
+// `threads` host threads. Outputs may be null. counters[4] (optional) accumulates
+// {sum node_iters, sum voxel_fetches, sum outer_iters, rays that entered the root cube}.
+// Returns wall-clock seconds spent in the pixel loop.
+double svxo_render(void* t, const svxo_camera* c, uint32_t w, uint32_t h, uint32_t row_begin, uint32_t row_end,
+                   uint32_t threads, uint32_t* hit_id, uint8_t* albedo, float* distance, float* normal,
+                   uint64_t* counters) {
+    Octree* tree = (Octree*)t;
+    Camera cam{{c->origin[0], c->origin[1], c->origin[2]}, {c->direction[0], c->direction[1], c->direction[2]},
+               c->glass_width, c->glass_height, c->glass_distance};
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<uint64_t> acc[5];
+    for (auto& a : acc) a = 0;
+    auto worker = [&](uint32_t tid) {
+        uint64_t local[5] = {0, 0, 0, 0, 0};
+        for (uint32_t row = row_begin + tid; row < row_end; row += threads) {
+            const uint32_t y = h - 1 - row;
+            for (uint32_t x = 0; x < w; ++x) {
+                const Ray ray = make_pixel_ray(cam, w, h, x, y);
+                RayStats st;
+                const Hit hit = tree->get_by_ray(ray, &st);
+                const size_t i = (size_t)row * w + x;
+                if (hit_id) hit_id[i] = hit.hit ? hit.palette_value : 0xFFFFFFFFu;
+                if (albedo) {
+                    const Albedo a = (hit.hit && (hit.entry.kind == EntryKind::Visual || hit.entry.kind == EntryKind::Complex))
+                                         ? hit.entry.albedo
+                                         : Albedo{0, 0, 0, 0};
+                    albedo[4 * i] = a.r; albedo[4 * i + 1] = a.g; albedo[4 * i + 2] = a.b; albedo[4 * i + 3] = a.a;
+                }
+                if (distance) {
+                    const V3f d = {hit.impact_point.x - ray.origin.x, hit.impact_point.y - ray.origin.y,
+                                   hit.impact_point.z - ray.origin.z};
+                    distance[i] = hit.hit ? std::sqrt((d.x * d.x) + (d.y * d.y) + (d.z * d.z)) : 0.0f;
+                }
+                if (normal) {
+                    normal[3 * i] = hit.hit ? hit.normal.x : 0.0f;
+                    normal[3 * i + 1] = hit.hit ? hit.normal.y : 0.0f;
+                    normal[3 * i + 2] = hit.hit ? hit.normal.z : 0.0f;
+                }
+                local[0] += st.node_iters;
+                local[1] += st.voxel_fetches;
+                local[2] += st.outer_iters;
+                local[3] += st.outer_iters > 0 ? 1 : 0;
+                local[4] += st.would_panic;
+            }
+        }
+        for (int k = 0; k < 5; ++k) acc[k] += local[k];
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    if (threads == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (uint32_t i = 0; i < threads; ++i) pool.emplace_back(worker, i);
+        for (auto& th : pool) th.join();
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    if (counters)
+        for (int k = 0; k < 5; ++k) counters[k] = acc[k];
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+uint32_t svxo_hardware_threads() { return std::max(1u, std::thread::hardware_concurrency()); }
+
+// ---- spatial KAT entry points -------------------------------------------------------------------
+uint32_t svxo_hash_region(float x, float y, float z, float half) { return hash_region(V3f{x, y, z}, half); }
+uint32_t svxo_hash_direction(float x, float y, float z) { return hash_direction(V3f{x, y, z}); }
+uint64_t svxo_flat_projection(uint64_t x, uint64_t y, uint64_t z, uint64_t s) { return flat_projection(x, y, z, s); }
+uint64_t svxo_position_in_bitmap_64bits(uint64_t x, uint64_t y, uint64_t z, uint64_t s) {
+    return position_in_bitmap_64bits(x, y, z, s);
+}
+uint64_t svxo_set_occupancy_in_bitmap_64bits(uint64_t x, uint64_t y, uint64_t z, uint64_t size, uint64_t dim,
+                                             int32_t occupied, uint64_t bitmap) {
+    set_occupancy_in_bitmap_64bits(x, y, z, size, dim, occupied != 0, &bitmap);
+    return bitmap;
+}
+void svxo_child_bounds_for(const float min_pos[3], float size, uint32_t octant, float out[4]) {
+    Cube c = child_bounds_for(Cube{{min_pos[0], min_pos[1], min_pos[2]}, size}, (uint8_t)octant);
+    out[0] = c.min_position.x; out[1] = c.min_position.y; out[2] = c.min_position.z; out[3] = c.size;
+}
+// returns 0 = None, 1 = Some{impact_distance: None}, 2 = Some{impact_distance: Some(d)}
+int32_t svxo_intersect_ray(const float min_pos[3], float size, const float origin[3], const float direction[3],
+                           float* d) {
+    bool has = false;
+    float dist = 0;
+    const bool hit = intersect_ray(Cube{{min_pos[0], min_pos[1], min_pos[2]}, size},
+                                   Ray{{origin[0], origin[1], origin[2]}, {direction[0], direction[1], direction[2]}}, &has,
+                                   &dist);
+    *d = dist;
+    return hit ? (has ? 2 : 1) : 0;
+}
+uint32_t svxo_step_octant(uint32_t octant, float sx, float sy, float sz) {
+    return step_octant((uint8_t)octant, V3f{sx, sy, sz});
+}
+void svxo_cube_impact_normal(const float min_pos[3], float size, const float p[3], float out[3]) {
+    V3f n = cube_impact_normal(Cube{{min_pos[0], min_pos[1], min_pos[2]}, size}, V3f{p[0], p[1], p[2]});
+    out[0] = n.x; out[1] = n.y; out[2] = n.z;
+}
+void svxo_dda_scale_factors(const float direction[3], float out[3]) {
+    V3f s = get_dda_scale_factors(Ray{{0, 0, 0}, {direction[0], direction[1], direction[2]}});
+    out[0] = s.x; out[1] = s.y; out[2] = s.z;
+}
+void svxo_normalized(const float v[3], float out[3]) {
+    const float len = std::sqrt((v[0] * v[0]) + (v[1] * v[1]) + (v[2] * v[2]));
+    out[0] = v[0] / len; out[1] = v[1] / len; out[2] = v[2] / len;
+}
+// LUT dumps: mask[8], index[64] (x*16+y*4+z order of [x][y][z]), step[27] ([x][y][z]), ray2node[512] ([pos][dir])
+void svxo_luts(uint64_t* mask, uint32_t* index, uint32_t* step, uint64_t* ray2node, float* offsets) {
+    const Luts& l = luts();
+    for (int i = 0; i < 8; ++i) mask[i] = l.bitmap_mask_for_octant[i];
+    for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 4; ++y)
+            for (int z = 0; z < 4; ++z) index[x * 16 + y * 4 + z] = l.bitmap_index[x][y][z];
+    for (int x = 0; x < 3; ++x)
+        for (int y = 0; y < 3; ++y)
+            for (int z = 0; z < 3; ++z) step[x * 9 + y * 3 + z] = l.octant_step_result[x][y][z];
+    for (int p = 0; p < 64; ++p)
+        for (int d = 0; d < 8; ++d) ray2node[p * 8 + d] = l.ray_to_node_occupancy[p][d];
+    for (int o = 0; o < 8; ++o) {
+        offsets[3 * o] = l.octant_offset[o].x;
+        offsets[3 * o + 1] = l.octant_offset[o].y;
+        offsets[3 * o + 2] = l.octant_offset[o].z;
+    }
+}
+
+void svxo_node_stack_script(uint32_t size, const int32_t* ops, uint32_t n, int32_t* out) {
+    if (size == 3)
+        run_stack_script<3>(ops, n, out);
+    else
+        run_stack_script<4>(ops, n, out);
+}
+
+}  // extern "C"
