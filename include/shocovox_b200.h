@@ -1,0 +1,200 @@
+/*
+ * shocovox_b200 — C ABI of the B200-native primary-ray path of davids91/shocovox.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types. Every entry point cites
+ * the reference (shocovox-rs 0.11.1) interface it replaces; paths are relative to the reference checkout.
+ * The reference has no FFI of its own (it is a Rust crate), so these are the symbols a `shocovox_b200-sys`
+ * style `extern "C"` block binds (INTEGRATION.md shows that block).
+ *
+ * Rules
+ *  - every call returns an svx_status (0 = OK); nothing throws or aborts across the boundary;
+ *  - handles are created by the library and released by the caller with the matching *_free;
+ *  - an octree handle allows one writer or many readers (caller-enforced, like `&mut self` / `&self`);
+ *  - a host/view handle serialises its own calls internally and owns its CUDA stream;
+ *  - ray queries run on the GPU only. There is no CPU fallback: without a CUDA device every svx_gpu_* /
+ *    svx_view_* call fails with SVX_E_CUDA.
+ */
+#ifndef SHOCOVOX_B200_H
+#define SHOCOVOX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVX_API __attribute__((visibility("default")))
+
+/* OctreeError, src/octree/types.rs:9-21 (+ device-side failures) */
+typedef enum svx_status {
+    SVX_OK = 0,
+    SVX_E_INVALID_SIZE = 1,            /* OctreeError::InvalidSize            */
+    SVX_E_INVALID_BRICK_DIMENSION = 2, /* OctreeError::InvalidBrickDimension  */
+    SVX_E_INVALID_STRUCTURE = 3,       /* OctreeError::InvalidStructure       */
+    SVX_E_INVALID_POSITION = 4,        /* OctreeError::InvalidPosition        */
+    SVX_E_INVALID_ARGUMENT = 5,        /* null handle / bad enum / zero resolution */
+    SVX_E_CUDA = -1,                   /* CUDA runtime error (svx_last_error_message has the text) */
+    SVX_E_OUT_OF_MEMORY = -2
+} svx_status;
+
+/* Albedo, src/octree/types.rs:92-97 ; Albedo::from(u32) is 0xRRGGBBAA, src/octree/detail.rs:92-105 */
+typedef struct svx_albedo {
+    uint8_t r, g, b, a;
+} svx_albedo;
+
+/* OctreeEntry<u32>, src/octree/types.rs:24-36 */
+typedef enum svx_entry_kind {
+    SVX_ENTRY_EMPTY = 0,
+    SVX_ENTRY_VISUAL = 1,
+    SVX_ENTRY_INFORMATIVE = 2,
+    SVX_ENTRY_COMPLEX = 3
+} svx_entry_kind;
+
+typedef struct svx_entry {
+    uint32_t kind; /* svx_entry_kind */
+    svx_albedo albedo;
+    uint32_t data;
+} svx_entry;
+
+/* Ray, src/spatial/raytracing/mod.rs:8-11 ; direction must be unit length (:14-16) */
+typedef struct svx_ray {
+    float origin[3];
+    float direction[3];
+} svx_ray;
+
+/* Return tuple of get_by_ray, src/raytracing/raytracing_on_cpu.rs:316 :
+ * Option<(OctreeEntry<T>, V3c<f32> impact_point, V3c<f32> normal)> plus the derived outputs of SURVEY §8 R14 */
+typedef struct svx_hit {
+    uint32_t hit;           /* 0 = None */
+    uint32_t palette_value; /* PaletteIndexValues of the voxel (colour idx | data idx << 16); 0xFFFFFFFF on a miss */
+    svx_entry entry;        /* palette-resolved entry */
+    float impact_point[3];
+    float normal[3];
+    float distance;         /* (impact_point - origin).length() */
+} svx_hit;
+
+/* Viewport, src/raytracing/bevy/types.rs:55-71 */
+typedef struct svx_viewport {
+    float origin[3];
+    float direction[3];
+    float frustum[3]; /* x: glass width, y: glass height, z: max depth */
+    float fov;
+} svx_viewport;
+
+/* The examples disagree on where the looking glass sits: `direction * fov`
+ * (examples/cpu_render.rs:92, beach.rs:180, minecraft.rs:177) or `direction * frustum.z`
+ * (examples/dot_cube.rs:209, sponza.rs:179). The view takes it as a mode. */
+typedef enum svx_glass_mode { SVX_GLASS_AT_FOV = 0, SVX_GLASS_AT_FRUSTUM_Z = 1 } svx_glass_mode;
+
+typedef struct svx_octree svx_octree;     /* Octree<u32>,    src/octree/types.rs:169-207      */
+typedef struct svx_gpu_host svx_gpu_host; /* OctreeGPUHost,  src/raytracing/bevy/types.rs:80-87 */
+typedef struct svx_view svx_view;         /* OctreeGPUView,  src/raytracing/bevy/types.rs:92-130 */
+
+/* Device-resident frame produced by svx_view_render: SoA, image order (row 0 = top, pixel (x, y) of the
+ * reference's caller loop lands in row h-1-y, examples/cpu_render.rs:106). Pointers are CUDA device pointers
+ * owned by the view and valid until the next render / set_resolution / free on that view. */
+typedef struct svx_frame {
+    uint32_t width, height;
+    uint32_t row_begin, row_end; /* rows this view renders (its shard); others are left untouched */
+    const uint32_t* hit_id;      /* [h*w] palette value of the hit voxel, 0xFFFFFFFF = miss */
+    const uint32_t* albedo;      /* [h*w] RGBA8 (r in the low byte), 0 on a miss or when the voxel has no colour */
+    const float* distance;       /* [h*w] hit distance, 0 on a miss */
+    float kernel_ms;             /* CUDA-event time of the traversal kernel for this render */
+} svx_frame;
+
+/* Counters of one serialised tree (render-data upload) */
+typedef struct svx_gpu_stats {
+    uint64_t nodes, bricks, voxel_bytes, total_bytes;
+    uint32_t tree_size, brick_dim, depth, colours;
+} svx_gpu_stats;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+SVX_API const char* svx_version(void);
+SVX_API const char* svx_last_error_message(void); /* thread-local text of the last failing call */
+SVX_API int32_t svx_cuda_device_count(void);      /* 0 when no usable CUDA device exists */
+
+/* ---- Octree: construction and point queries (host) --------------------------------------------------- */
+/* Octree::new, src/octree/mod.rs:173-205 (validation order kept: brick dimension, size, structure) */
+SVX_API int32_t svx_octree_new(uint32_t size, uint32_t brick_dim, svx_octree** out);
+SVX_API void svx_octree_free(svx_octree* tree);
+/* Octree::insert, src/octree/update/insert.rs:47-56 ; an empty entry is a no-op returning OK (:117-119) */
+SVX_API int32_t svx_octree_insert(svx_octree* tree, uint32_t x, uint32_t y, uint32_t z, const svx_entry* entry);
+/* Octree::insert_at_lod, src/octree/update/insert.rs:63-73 */
+SVX_API int32_t svx_octree_insert_at_lod(svx_octree* tree, uint32_t x, uint32_t y, uint32_t z, uint32_t insert_size,
+                                         const svx_entry* entry);
+/* Octree::update, src/octree/update/insert.rs:79-88 */
+SVX_API int32_t svx_octree_update(svx_octree* tree, uint32_t x, uint32_t y, uint32_t z, const svx_entry* entry);
+/* The per-voxel insert loop every example runs (examples/cpu_render.rs:21-43): n Visual inserts in array order.
+ * xyz is [n][3], rgba is [n][4], lod (optional) holds an insert_at_lod size per voxel (<= 1 means insert). */
+SVX_API int32_t svx_octree_insert_batch(svx_octree* tree, const uint32_t* xyz, const uint8_t* rgba, const uint32_t* lod,
+                                        uint64_t n);
+/* Octree::get, src/octree/mod.rs:209-215 */
+SVX_API int32_t svx_octree_get(const svx_octree* tree, uint32_t x, uint32_t y, uint32_t z, svx_entry* out);
+/* get() over the box [x0,x0+nx) x [y0,y0+ny) x [z0,z0+nz), x-major then y then z */
+SVX_API int32_t svx_octree_get_sweep(const svx_octree* tree, uint32_t x0, uint32_t y0, uint32_t z0, uint32_t nx,
+                                     uint32_t ny, uint32_t nz, svx_entry* out);
+/* Octree::get_size, src/octree/mod.rs:374-376 */
+SVX_API uint32_t svx_octree_size(const svx_octree* tree);
+SVX_API uint32_t svx_octree_brick_dim(const svx_octree* tree);
+/* pub auto_simplify, src/octree/types.rs:203 */
+SVX_API int32_t svx_octree_set_auto_simplify(svx_octree* tree, int32_t enabled);
+/* Key-order independent digest of the reachable tree (node kinds, occupancy bits, bricks, palettes) */
+SVX_API uint64_t svx_octree_structure_hash(const svx_octree* tree);
+SVX_API uint64_t svx_octree_node_count(const svx_octree* tree);
+
+/* ---- OctreeGPUHost: render-data upload ---------------------------------------------------------------- */
+/* OctreeGPUHost{tree}, src/raytracing/bevy/types.rs:80-87. Serialises the WHOLE tree into coalesced SoA
+ * buffers and uploads it to `device` (the reference streams nodes on demand instead, bevy/data.rs:365). The
+ * octree handle must outlive the host. */
+SVX_API int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host** out);
+SVX_API void svx_gpu_host_free(svx_gpu_host* host);
+/* Re-serialise and re-upload after the tree was edited (OctreeGPUView::reload, src/raytracing/bevy/mod.rs:56-60) */
+SVX_API int32_t svx_gpu_host_reload(svx_gpu_host* host);
+SVX_API int32_t svx_gpu_host_stats(const svx_gpu_host* host, svx_gpu_stats* out);
+/* Octree::get_by_ray (src/raytracing/raytracing_on_cpu.rs:316-318) for n rays at once, on the GPU.
+ * `rays` and `hits` are HOST arrays; n = 1 is the reference's single-ray call. */
+SVX_API int32_t svx_gpu_host_get_by_rays(svx_gpu_host* host, const svx_ray* rays, uint64_t n, svx_hit* hits);
+
+/* ---- OctreeGPUView: viewport + framebuffer -------------------------------------------------------------- */
+/* OctreeGPUHost::create_new_view, src/raytracing/bevy/data.rs:111-166. `size_hint` is the reference's node-cache
+ * capacity; the whole tree is resident here so it is ignored. resolution = [width, height]. */
+SVX_API int32_t svx_gpu_host_create_view(svx_gpu_host* host, uint32_t size_hint, const svx_viewport* viewport,
+                                         uint32_t width, uint32_t height, svx_view** out);
+SVX_API void svx_view_free(svx_view* view);
+/* OctreeSpyGlass::viewport / viewport_mut, src/raytracing/bevy/mod.rs:90-99 */
+SVX_API int32_t svx_view_get_viewport(const svx_view* view, svx_viewport* out);
+SVX_API int32_t svx_view_set_viewport(svx_view* view, const svx_viewport* viewport);
+SVX_API int32_t svx_view_set_glass_mode(svx_view* view, int32_t mode /* svx_glass_mode */);
+/* OctreeGPUView::set_resolution / resolution, src/raytracing/bevy/mod.rs:62-88 */
+SVX_API int32_t svx_view_set_resolution(svx_view* view, uint32_t width, uint32_t height);
+SVX_API int32_t svx_view_resolution(const svx_view* view, uint32_t* width, uint32_t* height);
+/* Multi-GPU sharding: this view renders image rows r with (r / rows_per_band) % world == rank. world = 1 renders
+ * everything (the default). */
+SVX_API int32_t svx_view_set_shard(svx_view* view, uint32_t rank, uint32_t world, uint32_t rows_per_band);
+/* One frame: in-kernel ray generation (examples/cpu_render.rs:78-114) + get_by_ray per pixel + framebuffer write.
+ * Asynchronous on the view's stream unless `out` is non-null, in which case the call synchronises and fills it. */
+SVX_API int32_t svx_view_render(svx_view* view, svx_frame* out);
+/* Same frame, delivered into HOST buffers (any may be null): includes the device->host copies. */
+SVX_API int32_t svx_view_render_to_host(svx_view* view, uint32_t* hit_id, uint32_t* albedo, float* distance);
+/* Batch mode: n camera poses through the same view (pose-sharded rendering). Host output arrays are
+ * [n][h*w] (any may be null). kernel_ms_total (optional) receives the summed CUDA-event kernel time. */
+SVX_API int32_t svx_view_render_batch(svx_view* view, const svx_viewport* poses, uint32_t n, uint32_t* hit_id,
+                                      uint32_t* albedo, float* distance, float* kernel_ms_total);
+/* Raw handles for interop with an existing CUDA context (torch, NCCL): the view's cudaStream_t and device id */
+SVX_API void* svx_view_cuda_stream(const svx_view* view);
+SVX_API int32_t svx_view_device(const svx_view* view);
+SVX_API int32_t svx_view_synchronize(svx_view* view);
+/* Device-side stopwatch on the view's stream: CUDA events recorded around whatever is enqueued between the two calls.
+ * svx_view_timer_stop synchronises the stream and returns the elapsed milliseconds. */
+SVX_API int32_t svx_view_timer_start(svx_view* view);
+SVX_API int32_t svx_view_timer_stop(svx_view* view, float* elapsed_ms);
+/* Evicts the L2 cache by overwriting a scratch buffer larger than L2 on the view's stream (benchmark hygiene). */
+SVX_API int32_t svx_view_flush_l2(svx_view* view);
+/* Number of kernel launches this view/host has issued since creation (bench.py's gpu_launches claim) */
+SVX_API uint64_t svx_view_launch_count(const svx_view* view);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHOCOVOX_B200_H */

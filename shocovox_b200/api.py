@@ -1,0 +1,561 @@
+"""Host-side mirror of the reference crate's API for the primary-ray path, over the C ABI (include/shocovox_b200.h).
+
+Names, argument meaning and error behaviour follow shocovox-rs 0.11.1 (paths relative to the reference checkout):
+
+    Octree.new / insert / insert_at_lod / update / get / get_size     src/octree/mod.rs, src/octree/update/insert.rs
+    Ray, Octree.get_by_ray                                            src/spatial/raytracing/mod.rs:8-11, src/raytracing/raytracing_on_cpu.rs:316
+    Viewport, OctreeGPUHost.create_new_view, OctreeGPUView            src/raytracing/bevy/types.rs:55-130, bevy/data.rs:111
+
+Ray queries run on the GPU only: there is no CPU fallback here. Without a CUDA device `OctreeGPUHost(...)` raises.
+torch is optional plumbing (wrapping the device framebuffer for NCCL gathers); the product is the shared library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+# ---- status codes (svx_status) ---------------------------------------------------------------------------------
+OK = 0
+E_INVALID_SIZE = 1
+E_INVALID_BRICK_DIMENSION = 2
+E_INVALID_STRUCTURE = 3
+E_INVALID_POSITION = 4
+E_INVALID_ARGUMENT = 5
+E_CUDA = -1
+E_OUT_OF_MEMORY = -2
+
+ENTRY_EMPTY, ENTRY_VISUAL, ENTRY_INFORMATIVE, ENTRY_COMPLEX = 0, 1, 2, 3
+GLASS_AT_FOV, GLASS_AT_FRUSTUM_Z = 0, 1
+MISS = 0xFFFFFFFF
+
+
+class OctreeError(Exception):
+    """OctreeError of the reference (src/octree/types.rs:9-21) plus device failures."""
+
+    NAMES = {
+        E_INVALID_SIZE: "InvalidSize",
+        E_INVALID_BRICK_DIMENSION: "InvalidBrickDimension",
+        E_INVALID_STRUCTURE: "InvalidStructure",
+        E_INVALID_POSITION: "InvalidPosition",
+        E_INVALID_ARGUMENT: "InvalidArgument",
+        E_CUDA: "Cuda",
+        E_OUT_OF_MEMORY: "OutOfMemory",
+    }
+
+    def __init__(self, code: int, message: str = ""):
+        self.code = code
+        super().__init__(f"{self.NAMES.get(code, code)}: {message}")
+
+
+class _Albedo(C.Structure):
+    _fields_ = [("r", C.c_uint8), ("g", C.c_uint8), ("b", C.c_uint8), ("a", C.c_uint8)]
+
+
+class _Entry(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("albedo", _Albedo), ("data", C.c_uint32)]
+
+
+class _Ray(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("direction", C.c_float * 3)]
+
+
+class _Hit(C.Structure):
+    _fields_ = [
+        ("hit", C.c_uint32),
+        ("palette_value", C.c_uint32),
+        ("entry", _Entry),
+        ("impact_point", C.c_float * 3),
+        ("normal", C.c_float * 3),
+        ("distance", C.c_float),
+    ]
+
+
+class _Viewport(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("direction", C.c_float * 3), ("frustum", C.c_float * 3), ("fov", C.c_float)]
+
+
+class _Frame(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32),
+        ("height", C.c_uint32),
+        ("row_begin", C.c_uint32),
+        ("row_end", C.c_uint32),
+        ("hit_id", C.c_void_p),
+        ("albedo", C.c_void_p),
+        ("distance", C.c_void_p),
+        ("kernel_ms", C.c_float),
+    ]
+
+
+class _GpuStats(C.Structure):
+    _fields_ = [
+        ("nodes", C.c_uint64),
+        ("bricks", C.c_uint64),
+        ("voxel_bytes", C.c_uint64),
+        ("total_bytes", C.c_uint64),
+        ("tree_size", C.c_uint32),
+        ("brick_dim", C.c_uint32),
+        ("depth", C.c_uint32),
+        ("colours", C.c_uint32),
+    ]
+
+
+HIT_DTYPE = np.dtype(
+    [
+        ("hit", "<u4"),
+        ("palette_value", "<u4"),
+        ("entry_kind", "<u4"),
+        ("rgba", "u1", (4,)),
+        ("data", "<u4"),
+        ("impact_point", "<f4", (3,)),
+        ("normal", "<f4", (3,)),
+        ("distance", "<f4"),
+    ]
+)
+ENTRY_DTYPE = np.dtype([("kind", "<u4"), ("rgba", "u1", (4,)), ("data", "<u4")])
+VIEWPORT_DTYPE = np.dtype([("origin", "<f4", (3,)), ("direction", "<f4", (3,)), ("frustum", "<f4", (3,)), ("fov", "<f4")])
+assert HIT_DTYPE.itemsize == C.sizeof(_Hit) and ENTRY_DTYPE.itemsize == C.sizeof(_Entry)
+assert VIEWPORT_DTYPE.itemsize == C.sizeof(_Viewport)
+
+# every symbol include/shocovox_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "svx_version", "svx_last_error_message", "svx_cuda_device_count",
+    "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
+    "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
+    "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count",
+    "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
+    "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
+    "svx_view_set_glass_mode", "svx_view_set_resolution", "svx_view_resolution", "svx_view_set_shard",
+    "svx_view_render", "svx_view_render_to_host", "svx_view_render_batch", "svx_view_cuda_stream", "svx_view_device",
+    "svx_view_synchronize", "svx_view_timer_start", "svx_view_timer_stop", "svx_view_flush_l2", "svx_view_launch_count",
+]
+
+_lib: Optional[C.CDLL] = None
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+def lib() -> C.CDLL:
+    """Loads (building first if the sources are newer) the product's shared library. Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    if not path.exists():
+        raise OctreeError(E_CUDA, f"{path} is missing: build it with `python -m shocovox_b200.build`")
+    L = C.CDLL(str(path))
+    u32, u64, i32, vp = C.c_uint32, C.c_uint64, C.c_int32, C.c_void_p
+    L.svx_version.restype = C.c_char_p
+    L.svx_last_error_message.restype = C.c_char_p
+    L.svx_cuda_device_count.restype = i32
+    L.svx_octree_new.argtypes = [u32, u32, C.POINTER(vp)]
+    L.svx_octree_free.argtypes = [vp]
+    L.svx_octree_free.restype = None
+    L.svx_octree_insert.argtypes = [vp, u32, u32, u32, C.POINTER(_Entry)]
+    L.svx_octree_insert_at_lod.argtypes = [vp, u32, u32, u32, u32, C.POINTER(_Entry)]
+    L.svx_octree_update.argtypes = [vp, u32, u32, u32, C.POINTER(_Entry)]
+    L.svx_octree_insert_batch.argtypes = [vp, vp, vp, vp, u64]
+    L.svx_octree_get.argtypes = [vp, u32, u32, u32, C.POINTER(_Entry)]
+    L.svx_octree_get_sweep.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp]
+    L.svx_octree_size.argtypes = [vp]
+    L.svx_octree_size.restype = u32
+    L.svx_octree_brick_dim.argtypes = [vp]
+    L.svx_octree_brick_dim.restype = u32
+    L.svx_octree_set_auto_simplify.argtypes = [vp, i32]
+    L.svx_octree_structure_hash.argtypes = [vp]
+    L.svx_octree_structure_hash.restype = u64
+    L.svx_octree_node_count.argtypes = [vp]
+    L.svx_octree_node_count.restype = u64
+    L.svx_gpu_host_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.svx_gpu_host_free.argtypes = [vp]
+    L.svx_gpu_host_free.restype = None
+    L.svx_gpu_host_reload.argtypes = [vp]
+    L.svx_gpu_host_stats.argtypes = [vp, C.POINTER(_GpuStats)]
+    L.svx_gpu_host_get_by_rays.argtypes = [vp, vp, u64, vp]
+    L.svx_gpu_host_create_view.argtypes = [vp, u32, C.POINTER(_Viewport), u32, u32, C.POINTER(vp)]
+    L.svx_view_free.argtypes = [vp]
+    L.svx_view_free.restype = None
+    L.svx_view_get_viewport.argtypes = [vp, C.POINTER(_Viewport)]
+    L.svx_view_set_viewport.argtypes = [vp, C.POINTER(_Viewport)]
+    L.svx_view_set_glass_mode.argtypes = [vp, i32]
+    L.svx_view_set_resolution.argtypes = [vp, u32, u32]
+    L.svx_view_resolution.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    L.svx_view_set_shard.argtypes = [vp, u32, u32, u32]
+    L.svx_view_render.argtypes = [vp, C.POINTER(_Frame)]
+    L.svx_view_render_to_host.argtypes = [vp, vp, vp, vp]
+    L.svx_view_render_batch.argtypes = [vp, vp, u32, vp, vp, vp, C.POINTER(C.c_float)]
+    L.svx_view_cuda_stream.argtypes = [vp]
+    L.svx_view_cuda_stream.restype = vp
+    L.svx_view_device.argtypes = [vp]
+    L.svx_view_synchronize.argtypes = [vp]
+    L.svx_view_timer_start.argtypes = [vp]
+    L.svx_view_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.svx_view_flush_l2.argtypes = [vp]
+    L.svx_view_launch_count.argtypes = [vp]
+    L.svx_view_launch_count.restype = u64
+    _lib = L
+    return L
+
+
+def _check(status: int):
+    if status != OK:
+        raise OctreeError(status, lib().svx_last_error_message().decode(errors="replace"))
+
+
+def cuda_device_count() -> int:
+    return int(lib().svx_cuda_device_count())
+
+
+# ---- value types ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Albedo:
+    """Albedo{r,g,b,a} (src/octree/types.rs:92-97)."""
+
+    r: int = 0
+    g: int = 0
+    b: int = 0
+    a: int = 0
+
+    @staticmethod
+    def from_u32(value: int) -> "Albedo":
+        """`Albedo::from(u32)` = 0xRRGGBBAA (src/octree/detail.rs:92-105)."""
+        return Albedo((value >> 24) & 0xFF, (value >> 16) & 0xFF, (value >> 8) & 0xFF, value & 0xFF)
+
+    def is_transparent(self) -> bool:
+        return self.a == 0
+
+
+def _as_albedo(v) -> Optional[Albedo]:
+    if v is None or isinstance(v, Albedo):
+        return v
+    if isinstance(v, (tuple, list)):
+        return Albedo(*[int(c) for c in v])
+    return Albedo.from_u32(int(v))
+
+
+@dataclass(frozen=True)
+class OctreeEntry:
+    """OctreeEntry<u32> (src/octree/types.rs:24-36): Empty | Visual(albedo) | Informative(data) | Complex(albedo, data)."""
+
+    albedo: Optional[Albedo] = None
+    data: Optional[int] = None
+
+    @property
+    def kind(self) -> int:
+        if self.albedo is not None and self.data is not None:
+            return ENTRY_COMPLEX
+        if self.albedo is not None:
+            return ENTRY_VISUAL
+        if self.data is not None:
+            return ENTRY_INFORMATIVE
+        return ENTRY_EMPTY
+
+    def is_none(self) -> bool:  # src/octree/mod.rs:102-109
+        return (self.albedo is None or self.albedo.is_transparent()) and (self.data is None or self.data == 0)
+
+    def is_some(self) -> bool:
+        return not self.is_none()
+
+    def _c(self) -> _Entry:
+        e = _Entry()
+        e.kind = self.kind
+        if self.albedo is not None:
+            e.albedo = _Albedo(self.albedo.r, self.albedo.g, self.albedo.b, self.albedo.a)
+        if self.data is not None:
+            e.data = int(self.data)
+        return e
+
+    @staticmethod
+    def _from_c(e: _Entry) -> "OctreeEntry":
+        alb = Albedo(e.albedo.r, e.albedo.g, e.albedo.b, e.albedo.a) if e.kind in (ENTRY_VISUAL, ENTRY_COMPLEX) else None
+        dat = int(e.data) if e.kind in (ENTRY_INFORMATIVE, ENTRY_COMPLEX) else None
+        return OctreeEntry(alb, dat)
+
+
+def entry(albedo=None, data=None) -> OctreeEntry:
+    return OctreeEntry(_as_albedo(albedo), None if data is None else int(data))
+
+
+@dataclass
+class Ray:
+    """Ray{origin, direction} (src/spatial/raytracing/mod.rs:8-11); direction must be unit length."""
+
+    origin: Sequence[float]
+    direction: Sequence[float]
+
+
+@dataclass
+class Viewport:
+    """Viewport{origin, direction, frustum, fov} (src/raytracing/bevy/types.rs:55-71)."""
+
+    origin: Sequence[float]
+    direction: Sequence[float]
+    frustum: Sequence[float] = (4.0, 4.0, 3.0)
+    fov: float = 3.0
+
+    def _c(self) -> _Viewport:
+        v = _Viewport()
+        v.origin[:] = [float(np.float32(x)) for x in self.origin]
+        v.direction[:] = [float(np.float32(x)) for x in self.direction]
+        v.frustum[:] = [float(np.float32(x)) for x in self.frustum]
+        v.fov = float(self.fov)
+        return v
+
+
+@dataclass
+class RayHit:
+    """The Some((entry, impact_point, normal)) of get_by_ray, plus the palette value and the hit distance."""
+
+    entry: OctreeEntry
+    impact_point: tuple
+    normal: tuple
+    palette_value: int
+    distance: float
+
+
+def normalized(v) -> np.ndarray:
+    """V3c::normalized (src/spatial/math/vector.rs:75-81) in f32: v / sqrt((x*x + y*y) + z*z)."""
+    v = np.asarray(v, dtype=np.float32)
+    ln = np.sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2], dtype=np.float32)
+    return (v / ln).astype(np.float32)
+
+
+# ---- Octree -------------------------------------------------------------------------------------------------------
+class Octree:
+    """`Octree<u32>`: construction and point queries on the host; ray queries through an OctreeGPUHost."""
+
+    def __init__(self, size: int, brick_dimension: int):
+        self._h = C.c_void_p()
+        _check(lib().svx_octree_new(size, brick_dimension, C.byref(self._h)))
+
+    @staticmethod
+    def new(size: int, brick_dimension: int) -> "Octree":
+        return Octree(size, brick_dimension)
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
+            _lib.svx_octree_free(self._h)
+            self._h = C.c_void_p()
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    @property
+    def auto_simplify(self):
+        raise AttributeError("write-only mirror of the pub field; use set_auto_simplify")
+
+    def set_auto_simplify(self, enabled: bool):
+        _check(lib().svx_octree_set_auto_simplify(self._h, int(enabled)))
+
+    def insert(self, position, albedo=None, data=None):
+        _check(lib().svx_octree_insert(self._h, *[int(c) for c in position], C.byref(entry(albedo, data)._c())))
+
+    def insert_at_lod(self, position, insert_size: int, albedo=None, data=None):
+        _check(lib().svx_octree_insert_at_lod(self._h, *[int(c) for c in position], int(insert_size),
+                                              C.byref(entry(albedo, data)._c())))
+
+    def update(self, position, albedo=None, data=None):
+        _check(lib().svx_octree_update(self._h, *[int(c) for c in position], C.byref(entry(albedo, data)._c())))
+
+    def insert_batch(self, xyz: np.ndarray, rgba: np.ndarray, lod: Optional[np.ndarray] = None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.uint32)
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        if xyz.ndim != 2 or xyz.shape[1] != 3 or rgba.shape != (xyz.shape[0], 4):
+            raise OctreeError(E_INVALID_ARGUMENT, "xyz must be [n,3] and rgba [n,4]")
+        lod_p = None
+        if lod is not None:
+            lod = np.ascontiguousarray(lod, dtype=np.uint32)
+            lod_p = lod.ctypes.data
+        _check(lib().svx_octree_insert_batch(self._h, xyz.ctypes.data, rgba.ctypes.data, lod_p, xyz.shape[0]))
+
+    def get(self, position) -> OctreeEntry:
+        e = _Entry()
+        _check(lib().svx_octree_get(self._h, *[int(c) for c in position], C.byref(e)))
+        return OctreeEntry._from_c(e)
+
+    def get_sweep(self, origin, extent) -> np.ndarray:
+        out = np.zeros(int(extent[0]) * int(extent[1]) * int(extent[2]), dtype=ENTRY_DTYPE)
+        _check(lib().svx_octree_get_sweep(self._h, *[int(c) for c in origin], *[int(c) for c in extent], out.ctypes.data))
+        return out.reshape(tuple(int(c) for c in extent))
+
+    def get_size(self) -> int:
+        return int(lib().svx_octree_size(self._h))
+
+    def brick_dim(self) -> int:
+        return int(lib().svx_octree_brick_dim(self._h))
+
+    def structure_hash(self) -> int:
+        return int(lib().svx_octree_structure_hash(self._h))
+
+    def node_count(self) -> int:
+        return int(lib().svx_octree_node_count(self._h))
+
+    # `Octree::get_by_ray(&Ray)`: one ray, on the GPU (a host is created on first use and reloaded after edits)
+    def get_by_ray(self, ray: Ray, device: int = 0) -> Optional[RayHit]:
+        host = getattr(self, "_ray_host", None)
+        if host is None or host.device != device:
+            host = OctreeGPUHost(self, device)
+            self._ray_host = host
+        else:
+            host.reload()
+        return host.get_by_ray(ray)
+
+
+# ---- OctreeGPUHost / OctreeGPUView ----------------------------------------------------------------------------------
+class OctreeGPUHost:
+    """OctreeGPUHost{tree} (src/raytracing/bevy/types.rs:80-87): owns the device copy of the whole tree."""
+
+    def __init__(self, tree: Octree, device: int = 0):
+        self.tree = tree
+        self.device = int(device)
+        self._h = C.c_void_p()
+        _check(lib().svx_gpu_host_create(tree.handle, self.device, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
+            _lib.svx_gpu_host_free(self._h)
+            self._h = C.c_void_p()
+
+    def reload(self):
+        _check(lib().svx_gpu_host_reload(self._h))
+
+    def stats(self) -> dict:
+        s = _GpuStats()
+        _check(lib().svx_gpu_host_stats(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in _GpuStats._fields_}
+
+    def get_by_rays(self, rays: np.ndarray) -> np.ndarray:
+        """rays: [n,6] f32 (origin xyz, direction xyz) -> structured array (HIT_DTYPE)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        out = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        _check(lib().svx_gpu_host_get_by_rays(self._h, rays.ctypes.data, rays.shape[0], out.ctypes.data))
+        return out
+
+    def get_by_ray(self, ray: Ray) -> Optional[RayHit]:
+        r = np.concatenate([np.asarray(ray.origin, dtype=np.float32), np.asarray(ray.direction, dtype=np.float32)])
+        h = self.get_by_rays(r[None, :])[0]
+        if not h["hit"]:
+            return None
+        kind = int(h["entry_kind"])
+        alb = Albedo(*[int(c) for c in h["rgba"]]) if kind in (ENTRY_VISUAL, ENTRY_COMPLEX) else None
+        dat = int(h["data"]) if kind in (ENTRY_INFORMATIVE, ENTRY_COMPLEX) else None
+        return RayHit(OctreeEntry(alb, dat), tuple(float(v) for v in h["impact_point"]),
+                      tuple(float(v) for v in h["normal"]), int(h["palette_value"]), float(h["distance"]))
+
+    def create_new_view(self, size: int, viewport: Viewport, resolution: Sequence[int]) -> "OctreeGPUView":
+        """OctreeGPUHost::create_new_view (src/raytracing/bevy/data.rs:111-166). `size` (node-cache capacity in the
+        reference) is accepted and ignored: the whole tree is resident."""
+        return OctreeGPUView(self, size, viewport, resolution)
+
+
+class OctreeGPUView:
+    """OctreeGPUView + OctreeSpyGlass (src/raytracing/bevy/types.rs:92-130, bevy/mod.rs:56-99)."""
+
+    def __init__(self, host: OctreeGPUHost, size: int, viewport: Viewport, resolution: Sequence[int]):
+        self.host = host
+        self._h = C.c_void_p()
+        vp = viewport._c()
+        _check(lib().svx_gpu_host_create_view(host._h, int(size), C.byref(vp), int(resolution[0]), int(resolution[1]),
+                                              C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
+            _lib.svx_view_free(self._h)
+            self._h = C.c_void_p()
+
+    def reload(self):
+        self.host.reload()
+
+    def viewport(self) -> Viewport:
+        v = _Viewport()
+        _check(lib().svx_view_get_viewport(self._h, C.byref(v)))
+        return Viewport(tuple(v.origin), tuple(v.direction), tuple(v.frustum), float(v.fov))
+
+    def set_viewport(self, viewport: Viewport):
+        vp = viewport._c()
+        _check(lib().svx_view_set_viewport(self._h, C.byref(vp)))
+
+    def set_glass_mode(self, mode: int):
+        _check(lib().svx_view_set_glass_mode(self._h, int(mode)))
+
+    def set_resolution(self, resolution: Sequence[int]):
+        _check(lib().svx_view_set_resolution(self._h, int(resolution[0]), int(resolution[1])))
+
+    def resolution(self):
+        w, h = C.c_uint32(), C.c_uint32()
+        _check(lib().svx_view_resolution(self._h, C.byref(w), C.byref(h)))
+        return [int(w.value), int(h.value)]
+
+    def set_shard(self, rank: int, world: int, rows_per_band: int = 8):
+        _check(lib().svx_view_set_shard(self._h, int(rank), int(world), int(rows_per_band)))
+
+    def render(self, sync: bool = True) -> Optional[dict]:
+        """Renders one frame on the device. With sync, returns device pointers and the kernel's CUDA-event time."""
+        if not sync:
+            _check(lib().svx_view_render(self._h, None))
+            return None
+        f = _Frame()
+        _check(lib().svx_view_render(self._h, C.byref(f)))
+        return {"width": f.width, "height": f.height, "hit_id": f.hit_id, "albedo": f.albedo, "distance": f.distance,
+                "kernel_ms": float(f.kernel_ms)}
+
+    def render_to_host(self, hit_id: Optional[np.ndarray] = None, albedo: Optional[np.ndarray] = None,
+                       distance: Optional[np.ndarray] = None, want=("hit_id", "albedo", "distance")) -> dict:
+        """Renders and copies the frame into host arrays (allocated here unless given, e.g. pinned buffers)."""
+        w, h = self.resolution()
+        if hit_id is None and "hit_id" in want:
+            hit_id = np.empty((h, w), dtype=np.uint32)
+        if albedo is None and "albedo" in want:
+            albedo = np.empty((h, w), dtype=np.uint32)
+        if distance is None and "distance" in want:
+            distance = np.empty((h, w), dtype=np.float32)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        _check(lib().svx_view_render_to_host(self._h, ptr(hit_id), ptr(albedo), ptr(distance)))
+        return {"hit_id": hit_id, "albedo": albedo, "distance": distance}
+
+    def render_to_host_ptr(self, hit_id_ptr: int, albedo_ptr: int, distance_ptr: int):
+        """Same, into raw host pointers (0 = skip), e.g. torch pinned tensors' data_ptr()."""
+        _check(lib().svx_view_render_to_host(self._h, hit_id_ptr or None, albedo_ptr or None, distance_ptr or None))
+
+    def render_batch(self, poses: Sequence[Viewport], want=("hit_id", "albedo", "distance")) -> dict:
+        w, h = self.resolution()
+        n = len(poses)
+        arr = np.zeros(n, dtype=VIEWPORT_DTYPE)
+        for i, p in enumerate(poses):
+            arr[i] = (tuple(np.float32(p.origin)), tuple(np.float32(p.direction)), tuple(np.float32(p.frustum)), p.fov)
+        hit_id = np.empty((n, h, w), dtype=np.uint32) if "hit_id" in want else None
+        albedo = np.empty((n, h, w), dtype=np.uint32) if "albedo" in want else None
+        distance = np.empty((n, h, w), dtype=np.float32) if "distance" in want else None
+        ms = C.c_float()
+        ptr = lambda a: None if a is None else a.ctypes.data
+        _check(lib().svx_view_render_batch(self._h, arr.ctypes.data, n, ptr(hit_id), ptr(albedo), ptr(distance), C.byref(ms)))
+        return {"hit_id": hit_id, "albedo": albedo, "distance": distance, "kernel_ms": float(ms.value)}
+
+    def synchronize(self):
+        _check(lib().svx_view_synchronize(self._h))
+
+    def timer_start(self):
+        _check(lib().svx_view_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _check(lib().svx_view_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        _check(lib().svx_view_flush_l2(self._h))
+
+    def cuda_stream(self) -> int:
+        return int(lib().svx_view_cuda_stream(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(lib().svx_view_launch_count(self._h))

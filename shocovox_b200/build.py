@@ -1,0 +1,63 @@
+"""Builds libshocovox_b200.so (CUDA kernels + C ABI) for sm_100a, in-tree.
+
+nvcc cross-compiles without a GPU. Flags that matter for parity with the reference's f32 arithmetic:
+  -fmad=false                      Rust never contracts a*b+c into an FMA
+  -prec-div=true -prec-sqrt=true   IEEE-rounded division and sqrt (nvcc defaults, stated explicitly)
+  -ftz=false                       denormals kept (default)
+  -Xcompiler -ffp-contract=off     the host code that derives the per-frame camera constants follows the same rule
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libshocovox_b200.so"
+SOURCES = ["host_octree.cpp", "gpu_tree.cpp", "kernels.cu", "capi.cu"]
+HEADERS = ["host_octree.hpp", "gpu_tree.hpp", "kernels.cuh", "traverse.cuh", "../../include/shocovox_b200.h"]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def is_stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES + HEADERS] + [Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not is_stale():
+        return LIB
+    cmd = [
+        nvcc_path(), "-shared", "-o", str(LIB),
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-O3", "-std=c++17", "-lineinfo",
+        "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+        "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden,-Wall",
+        "-Xptxas", "-v",
+        "-cudart", "static",
+        "-x", "cu",
+    ] + [str(CSRC / s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
+    (PKG / "build_ptxas.log").write_text(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(LIB)

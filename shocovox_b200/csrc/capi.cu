@@ -1,0 +1,651 @@
+// C ABI of shocovox_b200 (include/shocovox_b200.h): octree construction on the host, render-data upload,
+// viewport rendering and batched ray queries on the GPU. There is no CPU ray path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/shocovox_b200.h"
+#include "gpu_tree.hpp"
+#include "host_octree.hpp"
+#include "kernels.cuh"
+
+using namespace svx;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int32_t fail(int32_t code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int32_t cuda_fail(cudaError_t e, const char* what) {
+    return fail(SVX_E_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CUDA_TRY(expr)                                        \
+    do {                                                      \
+        cudaError_t e__ = (expr);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+    } while (0)
+
+// ---- the reference's tables, regenerated from their generator logic (reference src/spatial/lut.rs:12-152), used
+// ---- ONLY to validate the device closed forms once per process
+void host_tables(uint64_t* ray2node /*512*/, uint64_t* octmask /*8*/, uint32_t* step /*216*/) {
+    auto offs = [](int o, int axis) { return axis == 0 ? (o & 1) : (axis == 1 ? ((o >> 2) & 1) : ((o >> 1) & 1)); };
+    for (int o = 0; o < 8; ++o) {
+        uint64_t m = 0;
+        for (int x = 2 * offs(o, 0); x < 2 * offs(o, 0) + 2; ++x)
+            for (int y = 2 * offs(o, 1); y < 2 * offs(o, 1) + 2; ++y)
+                for (int z = 2 * offs(o, 2); z < 2 * offs(o, 2) + 2; ++z) m |= occupancy_box(x, y, z, 1, 4);
+        octmask[o] = m;
+    }
+    for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 4; ++y)
+            for (int z = 0; z < 4; ++z)
+                for (int dx = -1; dx <= 1; dx += 2)
+                    for (int dy = -1; dy <= 1; dy += 2)
+                        for (int dz = -1; dz <= 1; dz += 2) {
+                            const int dir = ((1.0f + (float)dx) >= 1.0f) + 2 * ((1.0f + (float)dz) >= 1.0f) +
+                                            4 * ((1.0f + (float)dy) >= 1.0f);
+                            const int mx = std::clamp(x + dx * 4, 0, 3), my = std::clamp(y + dy * 4, 0, 3),
+                                      mz = std::clamp(z + dz * 4, 0, 3);
+                            uint64_t m = 0;
+                            for (int bx = std::min(mx, x); bx <= std::max(mx, x); ++bx)
+                                for (int by = std::min(my, y); by <= std::max(my, y); ++by)
+                                    for (int bz = std::min(mz, z); bz <= std::max(mz, z); ++bz)
+                                        m |= occupancy_box(bx, by, bz, 1, 4);
+                            ray2node[(x + 4 * y + 16 * z) * 8 + dir] = m;
+                        }
+    for (int o = 0; o < 8; ++o)
+        for (int sx = -1; sx <= 1; ++sx)
+            for (int sy = -1; sy <= 1; ++sy)
+                for (int sz = -1; sz <= 1; ++sz) {
+                    const float c[3] = {3.0f + offs(o, 0) * 6.0f + sx * 6.0f, 3.0f + offs(o, 1) * 6.0f + sy * 6.0f,
+                                        3.0f + offs(o, 2) * 6.0f + sz * 6.0f};
+                    uint32_t res;
+                    if (c[0] < 0 || c[0] > 12 || c[1] < 0 || c[1] > 12 || c[2] < 0 || c[2] > 12)
+                        res = 8;
+                    else
+                        res = (c[0] >= 6.0f) + 2 * (c[2] >= 6.0f) + 4 * (c[1] >= 6.0f);
+                    step[((sx + 1) * 9 + (sy + 1) * 3 + (sz + 1)) * 8 + o] = res;
+                }
+}
+
+std::once_flag g_selftest_once;
+int32_t g_selftest_status = SVX_OK;
+std::string g_selftest_error;
+
+void run_selftest(cudaStream_t stream) {
+    uint64_t* dev = nullptr;
+    std::vector<uint64_t> got(736);
+    cudaError_t e = cudaMalloc(&dev, got.size() * 8);
+    if (e == cudaSuccess) e = launch_lut_selftest(dev, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(got.data(), dev, got.size() * 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (dev) cudaFree(dev);
+    if (e != cudaSuccess) {
+        g_selftest_status = SVX_E_CUDA;
+        g_selftest_error = std::string("LUT self-test launch failed: ") + cudaGetErrorString(e);
+        return;
+    }
+    uint64_t r2n[512], om[8];
+    uint32_t st[216];
+    host_tables(r2n, om, st);
+    for (int i = 0; i < 512; ++i)
+        if (got[i] != r2n[i]) g_selftest_status = SVX_E_CUDA;
+    for (int i = 0; i < 8; ++i)
+        if (got[512 + i] != om[i]) g_selftest_status = SVX_E_CUDA;
+    for (int i = 0; i < 216; ++i)
+        if (got[520 + i] != st[i]) g_selftest_status = SVX_E_CUDA;
+    if (g_selftest_status != SVX_OK) g_selftest_error = "device closed forms disagree with the reference look-up tables";
+}
+
+struct Vec3 {
+    float x, y, z;
+};
+inline Vec3 operator+(Vec3 a, Vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Vec3 operator*(Vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline Vec3 operator/(Vec3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+
+}  // namespace
+
+struct svx_octree {
+    HostOctree* tree = nullptr;
+};
+
+struct svx_gpu_host {
+    const svx_octree* octree = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    SerialisedTree host_copy;  // kept only for stats (vectors are released after upload)
+    svx_gpu_stats stats{};
+    DeviceTree dev{};
+    void* d_node_head = nullptr;
+    void* d_node_slot = nullptr;
+    void* d_voxels = nullptr;
+    void* d_brick_bits = nullptr;
+    void* d_palette = nullptr;
+    LaunchConfig cfg;
+    uint64_t launches = 0;
+    uint64_t uploaded_revision = ~0ull;
+    // scratch for get_by_rays
+    float* d_rays = nullptr;
+    RayHitRecord* d_hits = nullptr;
+    uint64_t ray_capacity = 0;
+};
+
+struct svx_view {
+    svx_gpu_host* host = nullptr;
+    svx_viewport viewport{};
+    int32_t glass_mode = SVX_GLASS_AT_FOV;
+    uint32_t width = 0, height = 0;
+    uint32_t rank = 0, world = 1, band_rows = 8;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t tm_start = nullptr, tm_stop = nullptr;
+    void* d_flush = nullptr;
+    size_t flush_bytes = 0;
+    uint32_t* d_hit_id = nullptr;
+    uint32_t* d_albedo = nullptr;
+    float* d_distance = nullptr;
+    uint64_t launches = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+void free_device_tree(svx_gpu_host* h) {
+    cudaFree(h->d_node_head);
+    cudaFree(h->d_node_slot);
+    cudaFree(h->d_voxels);
+    cudaFree(h->d_brick_bits);
+    cudaFree(h->d_palette);
+    h->d_node_head = h->d_node_slot = h->d_voxels = h->d_brick_bits = h->d_palette = nullptr;
+}
+
+int32_t upload(svx_gpu_host* h) {
+    SerialisedTree s;
+    serialise(*h->octree->tree, &s);
+    free_device_tree(h);
+    auto put = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+    };
+    CUDA_TRY(put(&h->d_node_head, s.node_head.data(), s.node_head.size() * sizeof(NodeHead)));
+    CUDA_TRY(put(&h->d_node_slot, s.node_slot.data(), s.node_slot.size() * 4));
+    CUDA_TRY(put(&h->d_voxels, s.voxels.data(), s.voxels.size() * 4));
+    CUDA_TRY(put(&h->d_brick_bits, s.brick_bits.data(), s.brick_bits.size() * 4));
+    CUDA_TRY(put(&h->d_palette, s.palette.data(), s.palette.size() * 4));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const uint32_t vol = s.brick_dim * s.brick_dim * s.brick_dim;
+    DeviceTree& d = h->dev;
+    d.node_head = (const NodeHead*)h->d_node_head;
+    d.node_slot = (const uint32_t*)h->d_node_slot;
+    d.voxels = (const uint32_t*)h->d_voxels;
+    d.brick_bits = (const uint32_t*)h->d_brick_bits;
+    d.palette = (const uint32_t*)h->d_palette;
+    d.n_nodes = (uint32_t)s.node_head.size();
+    d.n_bricks = (uint32_t)(s.voxels.size() / vol);
+    d.tree_size = s.tree_size;
+    d.brick_dim = s.brick_dim;
+    d.brick_shift = s.brick_shift;
+    d.bit_words = s.bit_words;
+    d.n_colors = (uint32_t)h->octree->tree->color_palette().size();
+    d.inv_tree_size = 1.0f / (float)s.tree_size;
+    d.inv_brick_dim = 1.0f / (float)s.brick_dim;
+    h->stats.nodes = s.node_head.size();
+    h->stats.bricks = d.n_bricks;
+    h->stats.voxel_bytes = s.voxels.size() * 4;
+    h->stats.total_bytes = s.total_bytes();
+    h->stats.tree_size = s.tree_size;
+    h->stats.brick_dim = s.brick_dim;
+    h->stats.depth = s.depth;
+    h->stats.colours = d.n_colors;
+    h->uploaded_revision = s.revision;
+    return SVX_OK;
+}
+
+// Camera constants of reference examples/cpu_render.rs:78-103 in its f32 operation order
+void make_frame_constants(const svx_view* v, FrameParams* f) {
+    const svx_viewport& vp = v->viewport;
+    const Vec3 origin{vp.origin[0], vp.origin[1], vp.origin[2]};
+    const Vec3 dir{vp.direction[0], vp.direction[1], vp.direction[2]};
+    const Vec3 up{0.0f, 1.0f, 0.0f};
+    // viewport_up_direction.cross(viewport_ray.direction).normalized()  (vector.rs:186-192, :79-81)
+    const Vec3 c{up.y * dir.z - up.z * dir.y, up.z * dir.x - up.x * dir.z, up.x * dir.y - up.y * dir.x};
+    const float clen = std::sqrt((c.x * c.x) + (c.y * c.y) + (c.z * c.z));
+    const Vec3 right = c / clen;
+    const float glass_w = vp.frustum[0], glass_h = vp.frustum[1];
+    const float glass_d = v->glass_mode == SVX_GLASS_AT_FRUSTUM_Z ? vp.frustum[2] : vp.fov;
+    const Vec3 bl = origin + (dir * glass_d) - (up * (glass_h / 2.0f)) - (right * (glass_w / 2.0f));
+    f->ox = origin.x; f->oy = origin.y; f->oz = origin.z;
+    f->blx = bl.x; f->bly = bl.y; f->blz = bl.z;
+    f->rx = right.x; f->ry = right.y; f->rz = right.z;
+    f->ux = up.x; f->uy = up.y; f->uz = up.z;
+    f->pixel_width = glass_w / (float)v->width;
+    f->pixel_height = glass_h / (float)v->height;
+    f->width = v->width;
+    f->height = v->height;
+    f->rank = v->rank;
+    f->world = v->world;
+    f->band_rows = v->band_rows;
+    // rows owned by this shard
+    uint32_t rows = 0;
+    const uint32_t bands = (v->height + v->band_rows - 1) / v->band_rows;
+    for (uint32_t b = v->rank; b < bands; b += v->world) rows += std::min(v->band_rows, v->height - b * v->band_rows);
+    // the kernel maps local rows band by band, so a partial last band must stay addressable
+    uint32_t owned_bands = 0;
+    for (uint32_t b = v->rank; b < bands; b += v->world) ++owned_bands;
+    f->rows_local = owned_bands * v->band_rows;
+    (void)rows;
+    f->hit_id = v->d_hit_id;
+    f->albedo = v->d_albedo;
+    f->distance = v->d_distance;
+}
+
+int32_t alloc_frame(svx_view* v) {
+    cudaFree(v->d_hit_id);
+    cudaFree(v->d_albedo);
+    cudaFree(v->d_distance);
+    v->d_hit_id = v->d_albedo = nullptr;
+    v->d_distance = nullptr;
+    const size_t n = (size_t)v->width * v->height;
+    CUDA_TRY(cudaMalloc((void**)&v->d_hit_id, n * 4));
+    CUDA_TRY(cudaMalloc((void**)&v->d_albedo, n * 4));
+    CUDA_TRY(cudaMalloc((void**)&v->d_distance, n * 4));
+    CUDA_TRY(cudaMemsetAsync(v->d_hit_id, 0xFF, n * 4, v->stream));
+    CUDA_TRY(cudaMemsetAsync(v->d_albedo, 0, n * 4, v->stream));
+    CUDA_TRY(cudaMemsetAsync(v->d_distance, 0, n * 4, v->stream));
+    return SVX_OK;
+}
+
+int32_t render_locked(svx_view* v) {
+    FrameParams f;
+    make_frame_constants(v, &f);
+    CUDA_TRY(cudaEventRecord(v->ev_start, v->stream));
+    CUDA_TRY(launch_render(v->host->dev, f, v->host->cfg, v->stream));
+    CUDA_TRY(cudaEventRecord(v->ev_stop, v->stream));
+    v->launches += 1;
+    return SVX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* svx_version(void) { return "shocovox_b200 0.1.0 (sm_100a)"; }
+const char* svx_last_error_message(void) { return g_last_error.c_str(); }
+int32_t svx_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---- octree ---------------------------------------------------------------------------------------------------
+int32_t svx_octree_new(uint32_t size, uint32_t brick_dim, svx_octree** out) {
+    if (!out) return fail(SVX_E_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    HostOctree* t = nullptr;
+    const int32_t s = HostOctree::create(size, brick_dim, &t);
+    if (s != SVX_OK) return fail(s, "Octree::new rejected (size, brick_dim)");
+    *out = new (std::nothrow) svx_octree();
+    if (!*out) {
+        delete t;
+        return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
+    }
+    (*out)->tree = t;
+    return SVX_OK;
+}
+void svx_octree_free(svx_octree* tree) {
+    if (!tree) return;
+    delete tree->tree;
+    delete tree;
+}
+int32_t svx_octree_insert(svx_octree* t, uint32_t x, uint32_t y, uint32_t z, const svx_entry* e) {
+    if (!t || !e) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    return t->tree->insert_at_lod_internal(true, x, y, z, 1, *e);
+}
+int32_t svx_octree_insert_at_lod(svx_octree* t, uint32_t x, uint32_t y, uint32_t z, uint32_t insert_size,
+                                 const svx_entry* e) {
+    if (!t || !e) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    return t->tree->insert_at_lod_internal(true, x, y, z, insert_size, *e);
+}
+int32_t svx_octree_update(svx_octree* t, uint32_t x, uint32_t y, uint32_t z, const svx_entry* e) {
+    if (!t || !e) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    return t->tree->insert_at_lod_internal(false, x, y, z, 1, *e);
+}
+int32_t svx_octree_insert_batch(svx_octree* t, const uint32_t* xyz, const uint8_t* rgba, const uint32_t* lod, uint64_t n) {
+    if (!t || (n && (!xyz || !rgba))) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    for (uint64_t i = 0; i < n; ++i) {
+        svx_entry e{};
+        e.kind = SVX_ENTRY_VISUAL;
+        e.albedo = svx_albedo{rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2], rgba[4 * i + 3]};
+        const uint32_t sz = (lod && lod[i] > 1) ? lod[i] : 1;
+        const int32_t s = t->tree->insert_at_lod_internal(true, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], sz, e);
+        if (s != SVX_OK) return fail(s, "insert failed in batch");
+    }
+    return SVX_OK;
+}
+int32_t svx_octree_get(const svx_octree* t, uint32_t x, uint32_t y, uint32_t z, svx_entry* out) {
+    if (!t || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = t->tree->get(x, y, z);
+    return SVX_OK;
+}
+int32_t svx_octree_get_sweep(const svx_octree* t, uint32_t x0, uint32_t y0, uint32_t z0, uint32_t nx, uint32_t ny,
+                             uint32_t nz, svx_entry* out) {
+    if (!t || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    size_t i = 0;
+    for (uint32_t x = x0; x < x0 + nx; ++x)
+        for (uint32_t y = y0; y < y0 + ny; ++y)
+            for (uint32_t z = z0; z < z0 + nz; ++z) out[i++] = t->tree->get(x, y, z);
+    return SVX_OK;
+}
+uint32_t svx_octree_size(const svx_octree* t) { return t ? t->tree->size() : 0; }
+uint32_t svx_octree_brick_dim(const svx_octree* t) { return t ? t->tree->brick_dim() : 0; }
+int32_t svx_octree_set_auto_simplify(svx_octree* t, int32_t enabled) {
+    if (!t) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    t->tree->auto_simplify = enabled != 0;
+    return SVX_OK;
+}
+uint64_t svx_octree_structure_hash(const svx_octree* t) { return t ? t->tree->structure_hash() : 0; }
+uint64_t svx_octree_node_count(const svx_octree* t) { return t ? t->tree->nodes().size() : 0; }
+
+// ---- gpu host -------------------------------------------------------------------------------------------------
+int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host** out) {
+    if (!tree || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SVX_E_CUDA, "no CUDA device available: the ray path has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(SVX_E_INVALID_ARGUMENT, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    svx_gpu_host* h = new (std::nothrow) svx_gpu_host();
+    if (!h) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
+    h->octree = tree;
+    h->device = device;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->cfg.sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaStreamCreate");
+    }
+    std::call_once(g_selftest_once, run_selftest, h->stream);
+    if (g_selftest_status != SVX_OK) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return fail(g_selftest_status, g_selftest_error);
+    }
+    const int32_t s = upload(h);
+    if (s != SVX_OK) {
+        free_device_tree(h);
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return s;
+    }
+    *out = h;
+    return SVX_OK;
+}
+
+void svx_gpu_host_free(svx_gpu_host* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_device_tree(h);
+    cudaFree(h->d_rays);
+    cudaFree(h->d_hits);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int32_t svx_gpu_host_reload(svx_gpu_host* h) {
+    if (!h) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return upload(h);
+}
+
+int32_t svx_gpu_host_stats(const svx_gpu_host* h, svx_gpu_stats* out) {
+    if (!h || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = h->stats;
+    return SVX_OK;
+}
+
+int32_t svx_gpu_host_get_by_rays(svx_gpu_host* h, const svx_ray* rays, uint64_t n, svx_hit* hits) {
+    if (!h || (n && (!rays || !hits))) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return SVX_OK;
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (n > h->ray_capacity) {
+        cudaFree(h->d_rays);
+        cudaFree(h->d_hits);
+        h->d_rays = nullptr;
+        h->d_hits = nullptr;
+        h->ray_capacity = 0;
+        CUDA_TRY(cudaMalloc((void**)&h->d_rays, n * sizeof(svx_ray)));
+        CUDA_TRY(cudaMalloc((void**)&h->d_hits, n * sizeof(RayHitRecord)));
+        h->ray_capacity = n;
+    }
+    static_assert(sizeof(svx_ray) == 24, "svx_ray is six packed floats");
+    CUDA_TRY(cudaMemcpyAsync(h->d_rays, rays, n * sizeof(svx_ray), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(launch_rays(h->dev, h->d_rays, n, h->d_hits, h->cfg, h->stream));
+    h->launches += 1;
+    std::vector<RayHitRecord> rec(n);
+    CUDA_TRY(cudaMemcpyAsync(rec.data(), h->d_hits, n * sizeof(RayHitRecord), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const HostOctree& tree = *h->octree->tree;
+    for (uint64_t i = 0; i < n; ++i) {
+        svx_hit& o = hits[i];
+        std::memset(&o, 0, sizeof(o));
+        o.palette_value = rec[i].palette_value;
+        o.hit = rec[i].hit;
+        if (o.hit) {
+            o.entry = tree.resolve(rec[i].palette_value);  // palette lookup of the returned voxel (node.rs:429-467)
+            std::memcpy(o.impact_point, rec[i].impact, 12);
+            std::memcpy(o.normal, rec[i].normal, 12);
+            o.distance = rec[i].distance;
+        } else {
+            o.palette_value = NIL;
+        }
+    }
+    return SVX_OK;
+}
+
+// ---- views ----------------------------------------------------------------------------------------------------
+int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* vp, uint32_t width, uint32_t height,
+                                 svx_view** out) {
+    if (!h || !vp || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (width == 0 || height == 0) return fail(SVX_E_INVALID_ARGUMENT, "zero resolution");
+    CUDA_TRY(cudaSetDevice(h->device));
+    svx_view* v = new (std::nothrow) svx_view();
+    if (!v) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
+    v->host = h;
+    v->viewport = *vp;
+    v->width = width;
+    v->height = height;
+    cudaError_t e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&v->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&v->ev_stop);
+    if (e == cudaSuccess) e = cudaEventCreate(&v->tm_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&v->tm_stop);
+    if (e != cudaSuccess) {
+        svx_view_free(v);
+        return cuda_fail(e, "view stream/event creation");
+    }
+    const int32_t s = alloc_frame(v);
+    if (s != SVX_OK) {
+        svx_view_free(v);
+        return s;
+    }
+    *out = v;
+    return SVX_OK;
+}
+
+void svx_view_free(svx_view* v) {
+    if (!v) return;
+    cudaSetDevice(v->host->device);
+    if (v->stream) cudaStreamSynchronize(v->stream);
+    cudaFree(v->d_hit_id);
+    cudaFree(v->d_albedo);
+    cudaFree(v->d_distance);
+    if (v->ev_start) cudaEventDestroy(v->ev_start);
+    if (v->ev_stop) cudaEventDestroy(v->ev_stop);
+    if (v->tm_start) cudaEventDestroy(v->tm_start);
+    if (v->tm_stop) cudaEventDestroy(v->tm_stop);
+    cudaFree(v->d_flush);
+    if (v->stream) cudaStreamDestroy(v->stream);
+    delete v;
+}
+
+int32_t svx_view_get_viewport(const svx_view* v, svx_viewport* out) {
+    if (!v || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = v->viewport;
+    return SVX_OK;
+}
+int32_t svx_view_set_viewport(svx_view* v, const svx_viewport* vp) {
+    if (!v || !vp) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    v->viewport = *vp;
+    return SVX_OK;
+}
+int32_t svx_view_set_glass_mode(svx_view* v, int32_t mode) {
+    if (!v || (mode != SVX_GLASS_AT_FOV && mode != SVX_GLASS_AT_FRUSTUM_Z)) return fail(SVX_E_INVALID_ARGUMENT, "bad mode");
+    std::lock_guard<std::mutex> lock(v->mu);
+    v->glass_mode = mode;
+    return SVX_OK;
+}
+int32_t svx_view_set_resolution(svx_view* v, uint32_t width, uint32_t height) {
+    if (!v || width == 0 || height == 0) return fail(SVX_E_INVALID_ARGUMENT, "bad resolution");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    v->width = width;
+    v->height = height;
+    return alloc_frame(v);
+}
+int32_t svx_view_resolution(const svx_view* v, uint32_t* width, uint32_t* height) {
+    if (!v || !width || !height) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *width = v->width;
+    *height = v->height;
+    return SVX_OK;
+}
+int32_t svx_view_set_shard(svx_view* v, uint32_t rank, uint32_t world, uint32_t rows_per_band) {
+    if (!v || world == 0 || rank >= world || rows_per_band == 0) return fail(SVX_E_INVALID_ARGUMENT, "bad shard");
+    std::lock_guard<std::mutex> lock(v->mu);
+    v->rank = rank;
+    v->world = world;
+    v->band_rows = rows_per_band;
+    return SVX_OK;
+}
+
+int32_t svx_view_render(svx_view* v, svx_frame* out) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    const int32_t s = render_locked(v);
+    if (s != SVX_OK) return s;
+    if (out) {
+        CUDA_TRY(cudaStreamSynchronize(v->stream));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, v->ev_start, v->ev_stop));
+        out->width = v->width;
+        out->height = v->height;
+        out->row_begin = 0;
+        out->row_end = v->height;
+        out->hit_id = v->d_hit_id;
+        out->albedo = v->d_albedo;
+        out->distance = v->d_distance;
+        out->kernel_ms = ms;
+    }
+    return SVX_OK;
+}
+
+int32_t svx_view_render_to_host(svx_view* v, uint32_t* hit_id, uint32_t* albedo, float* distance) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    const int32_t s = render_locked(v);
+    if (s != SVX_OK) return s;
+    const size_t bytes = (size_t)v->width * v->height * 4;
+    if (hit_id) CUDA_TRY(cudaMemcpyAsync(hit_id, v->d_hit_id, bytes, cudaMemcpyDeviceToHost, v->stream));
+    if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo, v->d_albedo, bytes, cudaMemcpyDeviceToHost, v->stream));
+    if (distance) CUDA_TRY(cudaMemcpyAsync(distance, v->d_distance, bytes, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    return SVX_OK;
+}
+
+int32_t svx_view_render_batch(svx_view* v, const svx_viewport* poses, uint32_t n, uint32_t* hit_id, uint32_t* albedo,
+                              float* distance, float* kernel_ms_total) {
+    if (!v || (n && !poses)) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    const size_t px = (size_t)v->width * v->height;
+    float total = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        v->viewport = poses[i];
+        const int32_t s = render_locked(v);
+        if (s != SVX_OK) return s;
+        if (hit_id) CUDA_TRY(cudaMemcpyAsync(hit_id + i * px, v->d_hit_id, px * 4, cudaMemcpyDeviceToHost, v->stream));
+        if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo + i * px, v->d_albedo, px * 4, cudaMemcpyDeviceToHost, v->stream));
+        if (distance) CUDA_TRY(cudaMemcpyAsync(distance + i * px, v->d_distance, px * 4, cudaMemcpyDeviceToHost, v->stream));
+        CUDA_TRY(cudaStreamSynchronize(v->stream));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, v->ev_start, v->ev_stop));
+        total += ms;
+    }
+    if (kernel_ms_total) *kernel_ms_total = total;
+    return SVX_OK;
+}
+
+void* svx_view_cuda_stream(const svx_view* v) { return v ? (void*)v->stream : nullptr; }
+int32_t svx_view_device(const svx_view* v) { return v ? v->host->device : -1; }
+int32_t svx_view_synchronize(svx_view* v) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    return SVX_OK;
+}
+int32_t svx_view_timer_start(svx_view* v) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    CUDA_TRY(cudaEventRecord(v->tm_start, v->stream));
+    return SVX_OK;
+}
+int32_t svx_view_timer_stop(svx_view* v, float* elapsed_ms) {
+    if (!v || !elapsed_ms) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    CUDA_TRY(cudaEventRecord(v->tm_stop, v->stream));
+    CUDA_TRY(cudaEventSynchronize(v->tm_stop));
+    CUDA_TRY(cudaEventElapsedTime(elapsed_ms, v->tm_start, v->tm_stop));
+    return SVX_OK;
+}
+int32_t svx_view_flush_l2(svx_view* v) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    if (!v->d_flush) {
+        v->flush_bytes = (size_t)384 << 20;  // 3x the 126 MB L2
+        CUDA_TRY(cudaMalloc(&v->d_flush, v->flush_bytes));
+    }
+    CUDA_TRY(cudaMemsetAsync(v->d_flush, (int)(v->launches & 0xFF), v->flush_bytes, v->stream));
+    return SVX_OK;
+}
+uint64_t svx_view_launch_count(const svx_view* v) { return v ? v->launches + v->host->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Breadth-first serialisation of the host octree into the device layout (see gpu_tree.hpp).
+#include "gpu_tree.hpp"
+
+#include <cstring>
+
+namespace svx {
+
+void serialise(const HostOctree& tree, SerialisedTree* out) {
+    SerialisedTree& s = *out;
+    s = SerialisedTree();
+    s.tree_size = tree.size();
+    s.brick_dim = tree.brick_dim();
+    s.brick_shift = 0;
+    while ((1u << s.brick_shift) < s.brick_dim) ++s.brick_shift;
+    const uint32_t vol = tree.brick_volume();
+    s.bit_words = (vol + 31) / 32;
+    s.revision = tree.revision();
+
+    const std::vector<NodeRec>& nodes = tree.nodes();
+    // breadth-first order over reachable nodes; `order[i]` = host key of device node i
+    std::vector<uint32_t> order;
+    std::vector<uint32_t> level_end;
+    order.push_back(0);
+    for (size_t i = 0; i < order.size(); ++i) {
+        const NodeRec& n = nodes[order[i]];
+        if (n.kind != NK_INTERNAL || n.link != LK_CHILDREN) continue;
+        for (int o = 0; o < 8; ++o)
+            if (tree.key_is_valid(n.child[o])) order.push_back(n.child[o]);
+    }
+    std::vector<uint32_t> remap(nodes.size(), NIL);
+    for (size_t i = 0; i < order.size(); ++i) remap[order[i]] = (uint32_t)i;
+
+    s.node_head.resize(order.size());
+    s.node_slot.assign(order.size() * 8, NIL);
+    uint32_t n_bricks = 0;
+    auto add_brick = [&](uint32_t handle) {
+        const uint32_t idx = n_bricks++;
+        s.voxels.resize((size_t)n_bricks * vol);
+        s.brick_bits.resize((size_t)n_bricks * s.bit_words, 0u);
+        const uint32_t* src = tree.brick_data(handle);
+        std::memcpy(s.voxels.data() + (size_t)idx * vol, src, (size_t)vol * 4);
+        uint32_t* bits = s.brick_bits.data() + (size_t)idx * s.bit_words;
+        for (uint32_t i = 0; i < vol; ++i)
+            if (!tree.value_is_empty(src[i])) bits[i >> 5] |= 1u << (i & 31);
+        return idx;
+    };
+    auto slot_of = [&](const BrickRef& b) -> uint32_t {
+        if (b.kind == BK_SOLID) return b.value;
+        if (b.kind == BK_PARTED) return add_brick(b.value);
+        return NIL;
+    };
+
+    for (size_t i = 0; i < order.size(); ++i) {
+        const uint32_t key = order[i];
+        const NodeRec& n = nodes[key];
+        const uint64_t oc = tree.stored_occupied_bits(key);
+        NodeHead h{(uint32_t)oc, (uint32_t)(oc >> 32), n.kind, NIL};
+        uint32_t* slot = s.node_slot.data() + i * 8;
+        if (n.kind == NK_INTERNAL) {
+            if (n.link == LK_CHILDREN)
+                for (int o = 0; o < 8; ++o) slot[o] = tree.key_is_valid(n.child[o]) ? remap[n.child[o]] : NIL;
+        } else if (n.kind == NK_LEAF) {
+            for (int o = 0; o < 8; ++o) {
+                h.meta |= (uint32_t)n.brick[o].kind << (2 + 2 * o);
+                slot[o] = slot_of(n.brick[o]);
+            }
+        } else if (n.kind == NK_UNIFORM) {
+            h.meta |= (uint32_t)n.brick[0].kind << 2;
+            h.aux = slot_of(n.brick[0]);
+        }
+        s.node_head[i] = h;
+    }
+    // depth of the deepest node (root = 1): bounds the ring-stack overflow behaviour, reported in stats
+    {
+        std::vector<uint32_t> d(order.size(), 1);
+        uint32_t deepest = 1;
+        for (size_t i = 0; i < order.size(); ++i) {
+            if ((s.node_head[i].meta & 3u) != NK_INTERNAL) continue;
+            for (int o = 0; o < 8; ++o) {
+                const uint32_t c = s.node_slot[i * 8 + o];
+                if (c != NIL) {
+                    d[c] = d[i] + 1;
+                    deepest = d[c] > deepest ? d[c] : deepest;
+                }
+            }
+        }
+        s.depth = deepest;
+    }
+    const std::vector<svx_albedo>& pal = tree.color_palette();
+    s.palette.resize(pal.size() ? pal.size() : 1, 0u);
+    for (size_t i = 0; i < pal.size(); ++i)
+        s.palette[i] = (uint32_t)pal[i].r | ((uint32_t)pal[i].g << 8) | ((uint32_t)pal[i].b << 16) | ((uint32_t)pal[i].a << 24);
+    if (s.voxels.empty()) {  // keep device pointers non-null
+        s.voxels.assign(1, NIL);
+        s.brick_bits.assign(1, 0u);
+    }
+}
+
+}  // namespace svx

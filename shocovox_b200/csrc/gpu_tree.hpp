@@ -1,0 +1,66 @@
+// Device layout of the octree ("render data") and its breadth-first serialiser.
+//
+// The reference uploads 4-byte granular arrays on demand (metadata / node_children / node_ocbits / voxels,
+// reference src/raytracing/bevy/types.rs:216-279, bevy/cache.rs:413-539). Here the whole tree is resident and a
+// node visit is ONE 16-byte load:
+//
+//   node_head[i] : uint4 { ocbits.lo, ocbits.hi, meta, aux }
+//        ocbits = stored_occupied_bits(node)   (reference src/octree/detail.rs:524-544, resolved on the host)
+//        meta   = kind[1:0] | brick kind of octant o at [2+2o+1 : 2+2o]   (0 empty, 1 parted, 2 solid)
+//                 kind: 0 Nothing, 1 Internal, 2 Leaf, 3 UniformLeaf (its brick kind sits in octant 0's field)
+//        aux    = UniformLeaf: the brick slot (below); otherwise NIL
+//   node_slot[8i + o] : u32   Internal: child node index or NIL (validity resolved on the host)
+//                             Leaf: brick slot of octant o
+//        brick slot = palette value (Solid) | brick index (Parted) | NIL (Empty)
+//   voxels[brick * dim^3 + x + y*dim + z*dim^2] : u32 palette values (reference flat_projection order)
+//   brick_bits[brick * words + ...] : 1 bit per voxel, set when the voxel is NOT empty (pix_points_to_empty false);
+//        the DDA walks these bits and fetches the 4-byte voxel only for the hit
+//   palette[c] : RGBA8, r in the low byte
+//
+// Nodes are numbered breadth-first from the root (index 0), so the top levels share cache lines.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "host_octree.hpp"
+
+namespace svx {
+
+struct NodeHead {
+    uint32_t oc_lo, oc_hi, meta, aux;
+};
+
+// POD handed to kernels by value
+struct DeviceTree {
+    const NodeHead* node_head;
+    const uint32_t* node_slot;
+    const uint32_t* voxels;
+    const uint32_t* brick_bits;
+    const uint32_t* palette;
+    uint32_t n_nodes;
+    uint32_t n_bricks;
+    uint32_t tree_size;
+    uint32_t brick_dim;
+    uint32_t brick_shift;       // log2(brick_dim)
+    uint32_t bit_words;         // u32 words of brick_bits per brick
+    uint32_t n_colors;
+    float inv_tree_size;        // 1 / tree_size (exact, power of two)
+    float inv_brick_dim;        // 1 / brick_dim (exact, power of two)
+};
+
+struct SerialisedTree {
+    std::vector<NodeHead> node_head;
+    std::vector<uint32_t> node_slot;
+    std::vector<uint32_t> voxels;
+    std::vector<uint32_t> brick_bits;
+    std::vector<uint32_t> palette;
+    uint32_t tree_size = 0, brick_dim = 0, brick_shift = 0, bit_words = 0, depth = 0;
+    uint64_t revision = 0;
+    size_t total_bytes() const {
+        return node_head.size() * sizeof(NodeHead) + (node_slot.size() + voxels.size() + brick_bits.size() + palette.size()) * 4;
+    }
+};
+
+void serialise(const HostOctree& tree, SerialisedTree* out);
+
+}  // namespace svx

@@ -1,0 +1,121 @@
+// Host-side brick-leaf sparse voxel octree of the product: the construction API the reference keeps on the CPU
+// (Octree::new / insert / insert_at_lod / update / get, reference src/octree/**), stored the way the GPU wants it.
+//
+// Layout: fixed-size node records in one arena plus ONE pooled voxel array for all parted bricks (a brick is a
+// handle into the pool, not an owned Vec as in the reference's BrickData::Parted, src/octree/types.rs:40-52).
+// A node record already carries what the device record needs (occupancy bits, brick kinds, 8 slots), so the
+// render-data upload (gpu_tree.cpp) is a breadth-first compaction, not a re-encoding.
+//
+// The tree *shape* decides which f32 path a ray takes, so every mutation follows the reference's
+// rules exactly; tests/test_host_octree.py checks shape equality against the oracle with a structural hash.
+// All `file:line` citations are relative to the reference checkout.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/shocovox_b200.h"
+
+namespace svx {
+
+constexpr uint32_t NIL = 0xFFFFFFFFu;  // empty_marker::<u32>(), src/object_pool.rs:14-16
+
+enum NodeKind : uint8_t { NK_NOTHING = 0, NK_INTERNAL = 1, NK_LEAF = 2, NK_UNIFORM = 3 };  // NodeContent, types.rs:56-72
+enum LinkKind : uint8_t { LK_NONE = 0, LK_CHILDREN = 1, LK_BITMAP = 2 };                  // NodeChildren, types.rs:76-81
+enum BrickKind : uint8_t { BK_EMPTY = 0, BK_PARTED = 1, BK_SOLID = 2 };                   // BrickData, types.rs:40-52
+
+// A brick reference: Solid carries the palette value itself, Parted a handle into the voxel pool.
+struct BrickRef {
+    uint8_t kind = BK_EMPTY;
+    uint32_t value = NIL;
+};
+
+struct NodeRec {
+    uint64_t ocbits = 0;     // NodeContent::Internal(u64)
+    uint64_t leaf_bits = 0;  // NodeChildren::OccupancyBitmap(u64)
+    uint32_t child[8] = {NIL, NIL, NIL, NIL, NIL, NIL, NIL, NIL};  // NodeChildren::Children
+    BrickRef brick[8];       // Leaf: one per octant ; UniformLeaf: brick[0]
+    uint8_t kind = NK_NOTHING;
+    uint8_t link = LK_NONE;
+    uint8_t reserved = 0;    // ObjectPool's `reserved` flag, src/object_pool.rs:9-12
+};
+
+struct BoundsF {  // Cube, src/spatial/mod.rs:18-21
+    float x, y, z, size;
+};
+
+class HostOctree {
+   public:
+    static int32_t create(uint32_t size, uint32_t brick_dim, HostOctree** out);
+
+    int32_t insert_at_lod_internal(bool overwrite_if_empty, uint32_t x, uint32_t y, uint32_t z, uint32_t insert_size,
+                                   const svx_entry& e);
+    svx_entry get(uint32_t x, uint32_t y, uint32_t z) const;
+    uint64_t structure_hash() const;
+
+    uint32_t size() const { return size_; }
+    uint32_t brick_dim() const { return dim_; }
+    uint32_t brick_volume() const { return vol_; }
+    uint64_t revision() const { return revision_; }
+    bool auto_simplify = true;
+
+    // read access for the serialiser
+    const std::vector<NodeRec>& nodes() const { return nodes_; }
+    const uint32_t* brick_data(uint32_t handle) const { return voxels_.data() + (size_t)handle * vol_; }
+    const std::vector<svx_albedo>& color_palette() const { return colors_; }
+    const std::vector<uint32_t>& data_palette() const { return datas_; }
+    bool key_is_valid(size_t key) const { return key < nodes_.size() && nodes_[key].reserved; }
+    uint64_t stored_occupied_bits(size_t key) const;
+    bool value_is_empty(uint32_t v) const;  // pix_points_to_empty, src/octree/node.rs:405-427
+    svx_entry resolve(uint32_t v) const;    // pix_get_ref, src/octree/node.rs:429-467
+
+   private:
+    // ---- arena (ObjectPool semantics, src/object_pool.rs:153-241) ----
+    size_t pool_push();
+    void pool_free(size_t key);
+    bool next_available() const;
+    // ---- brick pool ----
+    uint32_t brick_alloc(uint32_t fill);
+    uint32_t brick_clone(uint32_t handle);
+    void brick_release(BrickRef& b);
+    uint32_t* brick_mut(uint32_t handle) { return voxels_.data() + (size_t)handle * vol_; }
+    BrickRef brick_copy(const BrickRef& b);
+    bool brick_equal(const BrickRef& a, const BrickRef& b) const;
+    bool brick_homogeneous(const BrickRef& b, uint32_t* v) const;
+    bool brick_simplify(BrickRef& b);
+    uint64_t brick_bits(const uint32_t* vox) const;
+    uint64_t brick_ref_bits(const BrickRef& b) const;
+    void clear_content(size_t key);  // drops bricks, kind = Nothing
+    // ---- reference algorithms ----
+    uint32_t add_to_palette(const svx_entry& e);
+    size_t leaf_update(bool overwrite, size_t key, const BoundsF& node_b, const BoundsF& target_b, size_t octant,
+                       uint32_t x, uint32_t y, uint32_t z, uint32_t size, uint32_t content);
+    size_t update_brick(bool overwrite, uint32_t* brick, const BoundsF& b, uint32_t x, uint32_t y, uint32_t z,
+                        uint32_t size, uint32_t data) const;
+    void subdivide_leaf_to_nodes(size_t key, size_t target_octant);
+    void deallocate_children_of(size_t key);
+    void store_occupied_bits(size_t key, uint64_t bits);
+    bool simplify(size_t key);
+    bool node_is_all(const NodeRec& n, uint32_t v) const;
+    bool node_compare(const NodeRec& a, const NodeRec& b) const;
+    BrickRef try_brick_from_node(size_t key);
+    void dilute(const uint32_t* src, uint32_t out_handles[8]);
+    uint64_t hash_node(size_t key) const;
+    uint64_t hash_brick(const BrickRef& b) const;
+
+    uint32_t size_ = 0, dim_ = 0, vol_ = 0;
+    std::vector<NodeRec> nodes_;
+    size_t first_available_ = 0;
+    std::vector<uint32_t> voxels_;
+    std::vector<uint32_t> free_bricks_;
+    std::vector<svx_albedo> colors_;
+    std::vector<uint32_t> datas_;
+    std::unordered_map<uint32_t, uint32_t> color_index_, data_index_;
+    uint64_t revision_ = 0;
+};
+
+// Spatial helpers shared by host code (reference src/spatial/math/mod.rs)
+uint64_t occupancy_box(uint32_t px, uint32_t py, uint32_t pz, uint32_t size, uint32_t dim);  // bits set_occupancy_in_bitmap_64bits would set
+
+}  // namespace svx

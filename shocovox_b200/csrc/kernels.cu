@@ -1,0 +1,140 @@
+// sm_100a kernels of the primary-ray path: the viewport kernel (ray generation + traversal + framebuffer) and the
+// batched get_by_ray kernel. Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see build.py).
+#include "kernels.cuh"
+#include "traverse.cuh"
+
+namespace svx {
+
+// One warp renders an 8x4 pixel tile (coherent rays, 32-byte framebuffer segments per row and plane);
+// a 256-thread block covers 32x8 pixels.
+constexpr int TILE_W = 32;
+constexpr int TILE_H = 8;
+constexpr int BLOCK_THREADS = 256;
+
+__device__ __forceinline__ void pixel_of_thread(int& tx, int& ty) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    tx = ((warp & 3) << 3) + (lane & 7);
+    ty = ((warp >> 2) << 2) + (lane >> 3);
+}
+
+// Ray generation of the caller loop, reference examples/cpu_render.rs:104-114, in its f32 operation order:
+//   glass_point = (bottom_left + (right * x as f32) * pixel_width) + (up * y as f32) * pixel_height
+//   direction   = (glass_point - origin).normalized()          (three divisions, vector.rs:79-81)
+__device__ __forceinline__ void make_ray(const FrameParams& f, uint32_t x, uint32_t y, RayConst& r) {
+    const float xf = (float)x, yf = (float)y;
+    const float gx = (f.blx + (f.rx * xf) * f.pixel_width) + (f.ux * yf) * f.pixel_height;
+    const float gy = (f.bly + (f.ry * xf) * f.pixel_width) + (f.uy * yf) * f.pixel_height;
+    const float gz = (f.blz + (f.rz * xf) * f.pixel_width) + (f.uz * yf) * f.pixel_height;
+    const float vx = gx - f.ox, vy = gy - f.oy, vz = gz - f.oz;
+    const float len = sqrtf((vx * vx) + (vy * vy) + (vz * vz));
+    r.ox = f.ox; r.oy = f.oy; r.oz = f.oz;
+    r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const DeviceTree tree, const FrameParams f) {
+    int tx, ty;
+    pixel_of_thread(tx, ty);
+    const uint32_t x = blockIdx.x * TILE_W + tx;
+    const uint32_t lr = blockIdx.y * TILE_H + ty;  // row index inside this shard
+    if (x >= f.width || lr >= f.rows_local) return;
+    // shard-local row -> image row (interleaved bands)
+    const uint32_t band = lr / f.band_rows, within = lr - band * f.band_rows;
+    const uint32_t row = (band * f.world + f.rank) * f.band_rows + within;
+    if (row >= f.height) return;
+    const uint32_t y = f.height - 1u - row;  // pixel (x, y) lands in image row h-1-y (cpu_render.rs:106)
+
+    RayConst r;
+    make_ray(f, x, y, r);
+    ray_setup(r);
+    TraceResult res;
+    const bool hit = trace_ray(tree, r, res);
+
+    const size_t i = (size_t)row * f.width + x;
+    uint32_t rgba = 0u;
+    float dist = 0.0f;
+    if (hit) {
+        const uint32_t ci = res.palette_value & 0xFFFFu;
+        if (ci < 0xFFFFu && ci < tree.n_colors) rgba = __ldg(tree.palette + ci);
+        const float vx = res.px - r.ox, vy = res.py - r.oy, vz = res.pz - r.oz;
+        dist = sqrtf((vx * vx) + (vy * vy) + (vz * vz));  // V3c::length, vector.rs:75-77
+    }
+    f.hit_id[i] = hit ? res.palette_value : NIL;
+    f.albedo[i] = rgba;
+    f.distance[i] = dist;
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS) rays_kernel(const DeviceTree tree, const float* __restrict__ rays,
+                                                             uint64_t n, RayHitRecord* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayConst r;
+    r.ox = rays[6 * i + 0]; r.oy = rays[6 * i + 1]; r.oz = rays[6 * i + 2];
+    r.dx = rays[6 * i + 3]; r.dy = rays[6 * i + 4]; r.dz = rays[6 * i + 5];
+    ray_setup(r);
+    TraceResult res;
+    const bool hit = trace_ray(tree, r, res);
+    RayHitRecord h;
+    h.hit = hit ? 1u : 0u;
+    h.palette_value = hit ? res.palette_value : NIL;
+    h.impact[0] = h.impact[1] = h.impact[2] = 0.0f;
+    h.normal[0] = h.normal[1] = h.normal[2] = 0.0f;
+    h.distance = 0.0f;
+    if (hit) {
+        h.impact[0] = res.px; h.impact[1] = res.py; h.impact[2] = res.pz;
+        impact_normal(res, h.normal[0], h.normal[1], h.normal[2]);
+        const float vx = res.px - r.ox, vy = res.py - r.oy, vz = res.pz - r.oz;
+        h.distance = sqrtf((vx * vx) + (vy * vy) + (vz * vz));
+    }
+    out[i] = h;
+}
+
+// Evaluates the closed forms that replace the reference's tables, for every table index.
+__global__ void lut_selftest_kernel(uint64_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 512u) {
+        // RAY_TO_NODE_OCCUPANCY_BITMASK_LUT[cell][dir]: recover the mask bit by bit from the predicate
+        const uint32_t cell = i >> 3, dir = i & 7u;
+        const uint32_t cx = cell & 3u, cy = (cell >> 2) & 3u, cz = cell >> 4;
+        uint64_t m = 0;
+        for (uint32_t b = 0; b < 64u; ++b) {
+            const uint64_t one = 1ull << b;
+            if (ray_may_hit((uint32_t)one, (uint32_t)(one >> 32), cx, cy, cz, dir)) m |= one;
+        }
+        out[i] = m;
+    } else if (i < 520u) {
+        const uint32_t o = i - 512u;
+        uint64_t m = 0;
+        for (uint32_t b = 0; b < 64u; ++b) {
+            const uint64_t one = 1ull << b;
+            if (octant_occupied((uint32_t)one, (uint32_t)(one >> 32), o)) m |= one;
+        }
+        out[i] = m;
+    } else if (i < 520u + 216u) {
+        const uint32_t k = i - 520u;
+        const uint32_t o = k & 7u, s = k >> 3;  // s = (x+1)*9 + (y+1)*3 + (z+1)
+        const float sx = (float)((int)(s / 9u) - 1), sy = (float)((int)((s / 3u) % 3u) - 1), sz = (float)((int)(s % 3u) - 1);
+        out[i] = step_octant(o, sx, sy, sz);
+    }
+}
+
+cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig&, cudaStream_t stream) {
+    if (frame.rows_local == 0 || frame.width == 0) return cudaSuccess;
+    dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
+    render_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rays(const DeviceTree& tree, const float* rays, uint64_t n, RayHitRecord* out, const LaunchConfig&,
+                        cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + BLOCK_THREADS - 1) / BLOCK_THREADS);
+    rays_kernel<<<blocks, BLOCK_THREADS, 0, stream>>>(tree, rays, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lut_selftest(uint64_t* out, cudaStream_t stream) {
+    lut_selftest_kernel<<<(736 + 127) / 128, 128, 0, stream>>>(out);
+    return cudaGetLastError();
+}
+
+}  // namespace svx

@@ -1,0 +1,47 @@
+// Kernel entry points of the primary-ray path (launch wrappers are in kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "gpu_tree.hpp"
+
+namespace svx {
+
+// Per-frame camera constants of the caller loop in reference examples/cpu_render.rs:78-103, computed once on the
+// host in the reference's f32 operation order (capi.cu: make_frame_constants).
+struct FrameParams {
+    float ox, oy, oz;      // viewport_ray.origin
+    float blx, bly, blz;   // viewport_bottom_left
+    float rx, ry, rz;      // viewport_right_direction
+    float ux, uy, uz;      // viewport_up_direction = (0, 1, 0)
+    float pixel_width, pixel_height;
+    uint32_t width, height;
+    // sharding: this launch renders image rows r with (r / band_rows) % world == rank
+    uint32_t rank, world, band_rows;
+    uint32_t rows_local;   // number of image rows this shard owns
+    uint32_t* hit_id;      // [h*w]
+    uint32_t* albedo;      // [h*w]
+    float* distance;       // [h*w]
+};
+
+// Output record of the batched get_by_ray query
+struct RayHitRecord {
+    uint32_t hit;
+    uint32_t palette_value;
+    float impact[3];
+    float normal[3];
+    float distance;
+};
+
+struct LaunchConfig {
+    int sm_count = 148;
+};
+
+cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig& cfg, cudaStream_t stream);
+cudaError_t launch_rays(const DeviceTree& tree, const float* rays /* [n][6] */, uint64_t n, RayHitRecord* out,
+                        const LaunchConfig& cfg, cudaStream_t stream);
+// Fills out[0..512) with RAY_TO_NODE mask words, out[512..520) octant masks, then 27*8 step results, evaluated by
+// the device closed forms; the host compares them with tables regenerated from the reference's generator logic.
+cudaError_t launch_lut_selftest(uint64_t* out /* device, 512 + 8 + 216 entries */, cudaStream_t stream);
+
+}  // namespace svx

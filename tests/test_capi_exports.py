@@ -1,0 +1,74 @@
+"""The C-ABI library loads and exports every symbol include/shocovox_b200.h declares (no GPU needed)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+import shocovox_b200 as S
+from shocovox_b200 import api
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "shocovox_b200.h").read_text()
+
+
+def declared_symbols():
+    return re.findall(r"SVX_API\s+[\w\s\*]+?\b(svx_\w+)\s*\(", HEADER)
+
+
+def test_header_declares_what_the_binding_lists():
+    assert sorted(declared_symbols()) == sorted(api.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = S.lib()
+    for name in declared_symbols():
+        assert hasattr(L, name), name
+
+
+def test_version_and_error_text():
+    L = S.lib()
+    assert b"sm_100a" in L.svx_version()
+    assert isinstance(L.svx_last_error_message(), bytes)
+
+
+def test_octree_errors_follow_the_reference_order():
+    # src/octree/mod.rs:174-187
+    for size, dim, code in [(0, 8, api.E_INVALID_BRICK_DIMENSION), (64, 3, api.E_INVALID_BRICK_DIMENSION),
+                            (4, 8, api.E_INVALID_SIZE), (24, 8, api.E_INVALID_SIZE), (8, 8, api.E_INVALID_STRUCTURE)]:
+        with pytest.raises(S.OctreeError) as e:
+            S.Octree(size, dim)
+        assert e.value.code == code
+    t = S.Octree(4, 1)
+    with pytest.raises(S.OctreeError) as e:
+        t.insert((4, 0, 0), 0xFF0000FF)
+    assert e.value.code == api.E_INVALID_POSITION
+    assert t.get_size() == 4 and t.brick_dim() == 1
+
+
+def test_null_arguments_are_rejected_not_crashed():
+    L = S.lib()
+    assert L.svx_octree_new(4, 1, None) == api.E_INVALID_ARGUMENT
+    assert L.svx_gpu_host_create(None, 0, None) == api.E_INVALID_ARGUMENT
+    assert L.svx_view_render(None, None) == api.E_INVALID_ARGUMENT
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """Without a CUDA device the ray path must fail loudly, never fall back to host code."""
+    if S.cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    t = S.Octree(4, 1)
+    t.insert((1, 1, 1), 0xFF0000FF)
+    with pytest.raises(S.OctreeError) as e:
+        S.OctreeGPUHost(t)
+    assert e.value.code == api.E_CUDA
+    with pytest.raises(S.OctreeError):
+        t.get_by_ray(S.Ray((5, 5, 5), tuple(S.normalized((-1, -1, -1)))))
+
+
+def test_product_does_not_reference_the_oracle():
+    """The shipped package must not import, link or call anything under oracle/."""
+    pkg = ROOT / "shocovox_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.hpp")) + list(pkg.rglob("*.cuh")):
+        text = p.read_text()
+        assert "svxo_" not in text and "oracle_lib" not in text and "libsvx_oracle" not in text, p

@@ -1,0 +1,274 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: hit voxel id and albedo bit-exact, hit distance
+within 1e-4 relative (BASELINE.json north star) - and, stricter, bit-exact impact points / normals / distances.
+
+All tests here need a B200 (`-m gpu`). Nothing reads /root/reference at run time.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import shocovox_b200 as S
+from product_adapter import ProductOctree
+from ray_cases import CASES, check_expectation
+from shocovox_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+DIST_RTOL = 1e-4  # tolerance stated by BASELINE.json's north star
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def oracle_camera(c):
+    return O.make_camera(c.origin, c.direction, c.frustum[0], c.frustum[1], c.glass_distance)
+
+
+def viewport(c):
+    return S.Viewport(c.origin, c.direction, c.frustum, c.fov)
+
+
+def both_trees(scene):
+    return scenes.build_tree(scene, S.Octree), scenes.build_tree(scene, O.OracleOctree)
+
+
+def assert_frames_equal(gpu, ora, strict=True):
+    assert np.array_equal(gpu["hit_id"], ora["hit_id"]), "hit voxel ids differ"
+    ora_rgba = ora["albedo"].reshape(ora["albedo"].shape[0], ora["albedo"].shape[1], 4).copy().view(np.uint32)[..., 0]
+    assert np.array_equal(gpu["albedo"], ora_rgba), "albedo differs"
+    d_gpu, d_ora = gpu["distance"].astype(np.float64), ora["distance"].astype(np.float64)
+    rel = np.abs(d_gpu - d_ora) / np.maximum(np.abs(d_ora), 1e-30)
+    rel[d_ora == 0] = np.abs(d_gpu[d_ora == 0])
+    assert rel.max() <= DIST_RTOL, f"distance rel err {rel.max()}"
+    if strict:
+        assert np.array_equal(bits(gpu["distance"]), bits(ora["distance"])), "distance bits differ"
+
+
+def render_pair(scene, cam, res):
+    tree, otree = both_trees(scene)
+    assert tree.structure_hash() == otree.structure_hash()
+    host = S.OctreeGPUHost(tree)
+    view = host.create_new_view(64, viewport(cam), res)
+    if cam.glass_at_frustum_z:
+        view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+    gpu = view.render_to_host()
+    ora = otree.render(oracle_camera(cam), res[0], res[1])
+    assert ora["would_panic"] == 0
+    return gpu, ora, view, host, tree, otree
+
+
+# ---- the reference's deterministic edge-case rays, on the GPU (src/raytracing/tests.rs:253-813) ------------------
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_edge_case_rays_on_gpu(case):
+    p, o = ProductOctree(case["size"], case["dim"]), O.OracleOctree(case["size"], case["dim"])
+    case["build"](p)
+    case["build"](o)
+    ray = np.concatenate([np.asarray(case["origin"], np.float32), np.asarray(case["direction"], np.float32)])
+    host = S.OctreeGPUHost(p.tree)
+    g = host.get_by_rays(ray[None])[0]
+    h = o.get_by_ray(case["origin"], case["direction"])
+    check_expectation(case, bool(g["hit"]), int(g["entry_kind"]), tuple(int(c) for c in g["rgba"]), int(g["data"]),
+                      tuple(g["normal"]))
+    assert bool(g["hit"]) == bool(h.hit)
+    if h.hit:
+        assert int(g["palette_value"]) == h.palette_value
+        assert np.array_equal(bits(g["impact_point"]), bits(np.array(h.impact_point[:], np.float32)))
+        assert np.array_equal(bits(g["normal"]), bits(np.array(h.normal[:], np.float32)))
+        assert bits(g["distance"]) == bits(np.float32(h.distance))
+
+
+def test_single_ray_api_matches_reference_semantics():
+    """`Octree::get_by_ray(&Ray)` through the mirror API (one ray, GPU)."""
+    case = next(c for c in CASES if c["name"] == "detailed_brick_z_edge_error")
+    p = ProductOctree(case["size"], case["dim"])
+    case["build"](p)
+    hit = p.tree.get_by_ray(S.Ray(case["origin"], case["direction"]))
+    assert hit is not None and hit.entry == S.entry(1) and hit.normal == (0.0, 0.0, -1.0)
+    miss = p.tree.get_by_ray(S.Ray((100.0, 100.0, 100.0), tuple(S.normalized((1, 1, 1)))))
+    assert miss is None
+
+
+# ---- random rays: every output field bit-exact --------------------------------------------------------------------
+def random_rays(size, n, seed):
+    rng = np.random.default_rng(seed)
+    origin = rng.uniform(-1.0 * size, 2.0 * size, (n, 3)).astype(np.float32)
+    inside = rng.random(n) < 0.25
+    origin[inside] = rng.uniform(0, size, (int(inside.sum()), 3)).astype(np.float32)
+    target = rng.uniform(0, size, (n, 3)).astype(np.float32)
+    d = target - origin
+    ln = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2], dtype=np.float32)
+    d = (d / ln[:, None]).astype(np.float32)
+    # a share of axis-parallel and grazing rays (infinite / NaN scale factors)
+    k = n // 16
+    d[:k] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, k)] * rng.choice([-1.0, 1.0], k)[:, None].astype(np.float32)
+    origin[:k] = np.round(origin[:k])
+    return np.concatenate([origin, d], axis=1)
+
+
+SCENES_FOR_RAYS = {
+    "cpu_render_64_8": lambda: scenes.cpu_render_scene(64, 8),
+    "cpu_render_32_1": lambda: scenes.cpu_render_scene(32, 1),
+    "cpu_render_32_2": lambda: scenes.cpu_render_scene(32, 2),
+    "cpu_render_64_4": lambda: scenes.cpu_render_scene(64, 4),
+    "dot_cube_128_32": lambda: scenes.dot_cube_scene(128, 32),
+    "criterion_128_8": lambda: scenes.criterion_scene(128, 8, 48),
+    "colonnade_256_8": scenes.colonnade_scene,
+    "terrain_blocky_128_8": lambda: scenes.terrain_scene(128, 8, 1234, 4),
+    "terrain_256_8_shell": lambda: scenes.terrain_scene(256, 8, 4321, 1, shell=3),
+}
+
+
+@pytest.mark.parametrize("name", list(SCENES_FOR_RAYS))
+def test_random_rays_bit_exact(name):
+    scene = SCENES_FOR_RAYS[name]()
+    tree, otree = both_trees(scene)
+    assert tree.structure_hash() == otree.structure_hash()
+    rays = random_rays(scene.tree_size, 60000, zlib.crc32(name.encode()) % 1000)
+    g = S.OctreeGPUHost(tree).get_by_rays(rays)
+    o = otree.get_by_rays(rays)
+    assert int(o["would_panic"].sum()) == 0
+    assert np.array_equal(g["hit"], o["hit"])
+    assert np.array_equal(g["palette_value"], o["palette_value"])
+    assert np.array_equal(g["entry_kind"], o["entry_kind"])
+    assert np.array_equal(g["rgba"], o["rgba"]) and np.array_equal(g["data"], o["data"])
+    assert np.array_equal(bits(g["impact_point"]), bits(o["impact_point"]))
+    assert np.array_equal(bits(g["normal"]), bits(o["normal"]))
+    assert np.array_equal(bits(g["distance"]), bits(o["distance"]))
+    assert o["hit"].sum() > 1000  # the test actually exercises hits
+
+
+# ---- frames: the BASELINE configs --------------------------------------------------------------------------------------
+def test_c1_cpu_render_150x150_sequence():
+    """BASELINE config 1: examples/cpu_render.rs scene at 150x150, fixed camera sequence angle_k = 40 + 0.005 k."""
+    scene = scenes.cpu_render_scene()
+    tree, otree = both_trees(scene)
+    host = S.OctreeGPUHost(tree)
+    cams = [scenes.cpu_render_camera(64, k) for k in range(0, 64, 7)]
+    view = host.create_new_view(64, viewport(cams[0]), (150, 150))
+    batch = view.render_batch([viewport(c) for c in cams])
+    for i, c in enumerate(cams):
+        ora = otree.render(oracle_camera(c), 150, 150)
+        assert_frames_equal({k: batch[k][i] for k in ("hit_id", "albedo", "distance")}, ora)
+        assert (ora["hit_id"] != S.MISS).sum() > 1000
+
+
+def test_c1_cpu_render_1080p():
+    gpu, ora, *_ = render_pair(scenes.cpu_render_scene(), scenes.cpu_render_camera(), (1920, 1080))
+    assert_frames_equal(gpu, ora)
+
+
+@pytest.mark.parametrize("zoom", [False, True], ids=["glass_at_fov", "glass_at_frustum_z"])
+def test_c2_dot_cube_1080p(zoom):
+    """BASELINE config 2: examples/dot_cube.rs tree (256 / 32) at 1920x1080, both looking-glass placements."""
+    gpu, ora, *_ = render_pair(scenes.dot_cube_scene(), scenes.dot_cube_camera(zoom=zoom), (1920, 1080))
+    assert_frames_equal(gpu, ora)
+    assert (ora["hit_id"] != S.MISS).sum() > 10000
+
+
+def test_c3_blocky_terrain_reduced():
+    """BASELINE config 3 at a size the oracle finishes in seconds (256^3 / 32, 1280x720)."""
+    gpu, ora, *_ = render_pair(scenes.terrain_scene(256, 32, 1234, 4, name="minecraft"), scenes.terrain_camera(256), (1280, 720))
+    assert_frames_equal(gpu, ora)
+    assert (ora["hit_id"] != S.MISS).sum() > 100000
+
+
+def test_c4_mixed_resolution_bricks():
+    """BASELINE config 4's tree family: insert_at_lod slabs (Solid bricks, UniformLeaf nodes) + per-voxel detail."""
+    gpu, ora, *_ = render_pair(scenes.colonnade_scene(), scenes.colonnade_camera(), (1280, 720))
+    assert_frames_equal(gpu, ora)
+    assert (ora["hit_id"] != S.MISS).sum() > 100000
+
+
+def test_c5_deep_tree_poses():
+    """BASELINE config 5's tree family (brick 8, deeper than the 4-entry ring stack) over orbiting poses."""
+    scene = scenes.terrain_scene(256, 8, 4321, 1, shell=4)
+    tree, otree = both_trees(scene)
+    host = S.OctreeGPUHost(tree)
+    assert host.stats()["depth"] > 4
+    cams = scenes.orbit_cameras(256, 8)
+    view = host.create_new_view(64, viewport(cams[0]), (640, 360))
+    batch = view.render_batch([viewport(c) for c in cams])
+    for i, c in enumerate(cams):
+        ora = otree.render(oracle_camera(c), 640, 360)
+        assert_frames_equal({k: batch[k][i] for k in ("hit_id", "albedo", "distance")}, ora)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------------
+def test_empty_tree_renders_all_misses():
+    t = S.Octree(64, 8)
+    view = S.OctreeGPUHost(t).create_new_view(1, viewport(scenes.cpu_render_camera()), (64, 48))
+    f = view.render_to_host()
+    assert (f["hit_id"] == S.MISS).all() and (f["albedo"] == 0).all() and (f["distance"] == 0).all()
+
+
+def test_ragged_resolutions_and_resize():
+    """Resolutions that are not multiples of the 32x8 tile, and set_resolution."""
+    scene = scenes.cpu_render_scene()
+    tree, otree = both_trees(scene)
+    cam = scenes.cpu_render_camera()
+    view = S.OctreeGPUHost(tree).create_new_view(1, viewport(cam), (33, 7))
+    for res in [(33, 7), (1, 1), (150, 150), (257, 129)]:
+        view.set_resolution(res)
+        assert view.resolution() == list(res)
+        assert_frames_equal(view.render_to_host(), otree.render(oracle_camera(cam), res[0], res[1]))
+
+
+def test_camera_inside_the_tree():
+    scene = scenes.cpu_render_scene()
+    tree, otree = both_trees(scene)
+    cam = scenes.CameraSpec((20.0, 40.0, 20.0), tuple(float(v) for v in S.normalized((1.0, -0.3, 0.9))), (4.0, 4.0, 3.0), 3.0)
+    view = S.OctreeGPUHost(tree).create_new_view(1, viewport(cam), (320, 240))
+    assert_frames_equal(view.render_to_host(), otree.render(oracle_camera(cam), 320, 240))
+
+
+def test_reload_after_edit():
+    scene = scenes.cpu_render_scene()
+    tree, otree = both_trees(scene)
+    cam = scenes.cpu_render_camera()
+    host = S.OctreeGPUHost(tree)
+    view = host.create_new_view(1, viewport(cam), (150, 150))
+    before = view.render_to_host()
+    for t in (tree, otree):
+        t.insert_at_lod((0, 48, 0), 16, 0x11FF22FF)
+    view.reload()
+    after = view.render_to_host()
+    assert not np.array_equal(before["hit_id"], after["hit_id"])
+    assert_frames_equal(after, otree.render(oracle_camera(cam), 150, 150))
+
+
+def test_row_band_shards_compose_the_full_frame():
+    """Screen sharding used for multi-GPU: the union of the shards equals the unsharded frame byte for byte."""
+    scene = scenes.cpu_render_scene()
+    tree = scenes.build_tree(scene, S.Octree)
+    cam = scenes.cpu_render_camera()
+    host = S.OctreeGPUHost(tree)
+    full = host.create_new_view(1, viewport(cam), (300, 203)).render_to_host()
+    for world, band in [(2, 8), (3, 16), (8, 8)]:
+        acc = {k: np.zeros_like(v) for k, v in full.items()}
+        rows = np.arange(203)
+        for rank in range(world):
+            v = host.create_new_view(1, viewport(cam), (300, 203))
+            v.set_shard(rank, world, band)
+            part = v.render_to_host()
+            mine = (rows // band) % world == rank
+            for k in acc:
+                acc[k][mine] = part[k][mine]
+        for k in full:
+            assert np.array_equal(acc[k], full[k]), (world, band, k)
+
+
+def test_render_is_deterministic_and_counts_launches():
+    scene = scenes.cpu_render_scene()
+    tree = scenes.build_tree(scene, S.Octree)
+    view = S.OctreeGPUHost(tree).create_new_view(1, viewport(scenes.cpu_render_camera()), (640, 360))
+    a = view.render_to_host()
+    n0 = view.launch_count()
+    b = view.render_to_host()
+    assert view.launch_count() == n0 + 1
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    f = view.render()
+    assert f["kernel_ms"] > 0 and f["hit_id"]

@@ -1,5 +1,5 @@
 """Black-box construction tests of the reference (src/octree/update/tests.rs, src/octree/mod.rs:173-205),
-restated against the CPU oracle. Paths relative to /root/reference/."""
+restated against the CPU oracle AND the product's host octree. Paths relative to /root/reference/."""
 import itertools
 
 import numpy as np
@@ -7,6 +7,7 @@ import pytest
 
 import oracle_lib as O
 from oracle_lib import OracleOctree, entry_key as K
+from product_adapter import ProductOctree
 
 RED, GREEN, BLUE = 0xFF0000FF, 0x00FF00FF, 0x0000FFFF
 OFFS = [(0, 0, 0), (1, 0, 0), (0, 0, 1), (1, 0, 1), (0, 1, 0), (1, 1, 0), (0, 1, 1), (1, 1, 1)]  # lut.rs:156-197
@@ -19,9 +20,10 @@ def make_tree(cls, size, dim, simplify=True):
     return t
 
 
-@pytest.fixture(params=["oracle"])
+@pytest.fixture(params=["oracle", "product"])
 def Tree(request):
-    return OracleOctree
+    """Every construction test runs against the CPU oracle and against the product's host octree (C ABI)."""
+    return OracleOctree if request.param == "oracle" else ProductOctree
 
 
 # src/octree/mod.rs:173-187 (validation order)
