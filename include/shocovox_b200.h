@@ -170,7 +170,7 @@ SVX_API int32_t svx_view_set_glass_mode(svx_view* view, int32_t mode /* svx_glas
 SVX_API int32_t svx_view_set_resolution(svx_view* view, uint32_t width, uint32_t height);
 SVX_API int32_t svx_view_resolution(const svx_view* view, uint32_t* width, uint32_t* height);
 /* Multi-GPU sharding: this view renders image rows r with (r / rows_per_band) % world == rank. world = 1 renders
- * everything (the default). */
+ * everything (the default). rows_per_band must be a power of two. */
 SVX_API int32_t svx_view_set_shard(svx_view* view, uint32_t rank, uint32_t world, uint32_t rows_per_band);
 /* One frame: in-kernel ray generation (examples/cpu_render.rs:78-114) + get_by_ray per pixel + framebuffer write.
  * Asynchronous on the view's stream unless `out` is non-null, in which case the call synchronises and fills it. */

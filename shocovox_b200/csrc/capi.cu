@@ -237,7 +237,8 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     f->height = v->height;
     f->rank = v->rank;
     f->world = v->world;
-    f->band_rows = v->band_rows;
+    f->band_shift = 0;
+    while ((1u << f->band_shift) < v->band_rows) ++f->band_shift;
     // rows owned by this shard
     uint32_t rows = 0;
     const uint32_t bands = (v->height + v->band_rows - 1) / v->band_rows;
@@ -547,7 +548,8 @@ int32_t svx_view_resolution(const svx_view* v, uint32_t* width, uint32_t* height
     return SVX_OK;
 }
 int32_t svx_view_set_shard(svx_view* v, uint32_t rank, uint32_t world, uint32_t rows_per_band) {
-    if (!v || world == 0 || rank >= world || rows_per_band == 0) return fail(SVX_E_INVALID_ARGUMENT, "bad shard");
+    if (!v || world == 0 || rank >= world || rows_per_band == 0 || (rows_per_band & (rows_per_band - 1)) != 0)
+        return fail(SVX_E_INVALID_ARGUMENT, "bad shard (rows_per_band must be a power of two)");
     std::lock_guard<std::mutex> lock(v->mu);
     v->rank = rank;
     v->world = world;

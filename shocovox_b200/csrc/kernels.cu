@@ -20,15 +20,15 @@ __device__ __forceinline__ void pixel_of_thread(int& tx, int& ty) {
 // Ray generation of the caller loop, reference examples/cpu_render.rs:104-114, in its f32 operation order:
 //   glass_point = (bottom_left + (right * x as f32) * pixel_width) + (up * y as f32) * pixel_height
 //   direction   = (glass_point - origin).normalized()          (three divisions, vector.rs:79-81)
-__device__ __forceinline__ void make_ray(const FrameParams& f, uint32_t x, uint32_t y, RayConst& r) {
+// Returns the un-normalised vector glass_point - origin; the exact normalisation happens only for rays that may hit.
+__device__ __forceinline__ void glass_vector(const FrameParams& f, uint32_t x, uint32_t y, float& vx, float& vy, float& vz) {
     const float xf = (float)x, yf = (float)y;
     const float gx = (f.blx + (f.rx * xf) * f.pixel_width) + (f.ux * yf) * f.pixel_height;
     const float gy = (f.bly + (f.ry * xf) * f.pixel_width) + (f.uy * yf) * f.pixel_height;
     const float gz = (f.blz + (f.rz * xf) * f.pixel_width) + (f.uz * yf) * f.pixel_height;
-    const float vx = gx - f.ox, vy = gy - f.oy, vz = gz - f.oz;
-    const float len = sqrtf((vx * vx) + (vy * vy) + (vz * vz));
-    r.ox = f.ox; r.oy = f.oy; r.oz = f.oz;
-    r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
+    vx = gx - f.ox;
+    vy = gy - f.oy;
+    vz = gz - f.oz;
 }
 
 __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const DeviceTree tree, const FrameParams f) {
@@ -37,28 +37,41 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const DeviceTree 
     const uint32_t x = blockIdx.x * TILE_W + tx;
     const uint32_t lr = blockIdx.y * TILE_H + ty;  // row index inside this shard
     if (x >= f.width || lr >= f.rows_local) return;
-    // shard-local row -> image row (interleaved bands)
-    const uint32_t band = lr / f.band_rows, within = lr - band * f.band_rows;
-    const uint32_t row = (band * f.world + f.rank) * f.band_rows + within;
+    // shard-local row -> image row (interleaved bands of 2^band_shift rows)
+    const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
+    const uint32_t row = ((band * f.world + f.rank) << f.band_shift) + within;
     if (row >= f.height) return;
     const uint32_t y = f.height - 1u - row;  // pixel (x, y) lands in image row h-1-y (cpu_render.rs:106)
-
-    RayConst r;
-    make_ray(f, x, y, r);
-    ray_setup(r);
-    TraceResult res;
-    const bool hit = trace_ray(tree, r, res);
-
     const size_t i = (size_t)row * f.width + x;
-    uint32_t rgba = 0u;
+
+    float vx, vy, vz;
+    glass_vector(f, x, y, vx, vy, vz);
+    const float tree_size = (float)tree.tree_size;
+    uint32_t hit_id = NIL, rgba = 0u;
     float dist = 0.0f;
-    if (hit) {
-        const uint32_t ci = res.palette_value & 0xFFFFu;
-        if (ci < 0xFFFFu && ci < tree.n_colors) rgba = __ldg(tree.palette + ci);
-        const float vx = res.px - r.ox, vy = res.py - r.oy, vz = res.pz - r.oz;
-        dist = sqrtf((vx * vx) + (vy * vy) + (vz * vz));  // V3c::length, vector.rs:75-77
+    // 1) cheap conservative rejection with an approximately normalised direction (see certain_root_miss)
+    const float rl = rsqrtf((vx * vx) + (vy * vy) + (vz * vz));
+    if (!certain_root_miss(f.ox, f.oy, f.oz, vx * rl, vy * rl, vz * rl, tree_size)) {
+        // 2) the reference's exact arithmetic for everything that may hit
+        RayConst r;
+        const float len = sqrtf((vx * vx) + (vy * vy) + (vz * vz));
+        r.ox = f.ox; r.oy = f.oy; r.oz = f.oz;
+        r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
+        float px, py, pz;
+        uint32_t target_octant;
+        if (root_entry(r, tree_size, px, py, pz, target_octant)) {
+            ray_setup(r);
+            TraceResult res;
+            if (traverse(tree, r, px, py, pz, target_octant, res)) {
+                hit_id = res.palette_value;
+                const uint32_t ci = res.palette_value & 0xFFFFu;
+                if (ci < 0xFFFFu && ci < tree.n_colors) rgba = __ldg(tree.palette + ci);
+                const float wx = res.px - r.ox, wy = res.py - r.oy, wz = res.pz - r.oz;
+                dist = sqrtf((wx * wx) + (wy * wy) + (wz * wz));  // V3c::length, vector.rs:75-77
+            }
+        }
     }
-    f.hit_id[i] = hit ? res.palette_value : NIL;
+    f.hit_id[i] = hit_id;
     f.albedo[i] = rgba;
     f.distance[i] = dist;
 }
@@ -112,8 +125,8 @@ __global__ void lut_selftest_kernel(uint64_t* out) {
     } else if (i < 520u + 216u) {
         const uint32_t k = i - 520u;
         const uint32_t o = k & 7u, s = k >> 3;  // s = (x+1)*9 + (y+1)*3 + (z+1)
-        const float sx = (float)((int)(s / 9u) - 1), sy = (float)((int)((s / 3u) % 3u) - 1), sz = (float)((int)(s % 3u) - 1);
-        out[i] = step_octant(o, sx, sy, sz);
+        const int sx = (int)(s / 9u) - 1, sy = (int)((s / 3u) % 3u) - 1, sz = (int)(s % 3u) - 1;
+        out[i] = step_octant(o, sx != 0, sy != 0, sz != 0, sx, sy, sz);
     }
 }
 

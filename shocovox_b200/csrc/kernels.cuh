@@ -17,7 +17,7 @@ struct FrameParams {
     float pixel_width, pixel_height;
     uint32_t width, height;
     // sharding: this launch renders image rows r with (r / band_rows) % world == rank
-    uint32_t rank, world, band_rows;
+    uint32_t rank, world, band_shift;  // bands of 2^band_shift rows
     uint32_t rows_local;   // number of image rows this shard owns
     uint32_t* hit_id;      // [h*w]
     uint32_t* albedo;      // [h*w]

@@ -66,12 +66,13 @@ __device__ __forceinline__ bool ray_may_hit(uint32_t oc_lo, uint32_t oc_hi, uint
 }
 
 // step_octant, spatial/raytracing/mod.rs:68-80 with OCTANT_STEP_RESULT_LUT (generate_octant_step_result_lut,
-// lut.rs:91-137): move one octant along each stepped axis, OOB when leaving the 2x2x2 block.
-// `step` components are `(v as i32).signum()` of a +-1.0 / 0.0 / NaN float.
-__device__ __forceinline__ uint32_t step_octant(uint32_t octant, float sx, float sy, float sz) {
-    const int ix = (int)(octant & 1u) + (sx > 0.5f) - (sx < -0.5f);
-    const int iz = (int)((octant >> 1) & 1u) + (sz > 0.5f) - (sz < -0.5f);
-    const int iy = (int)((octant >> 2) & 1u) + (sy > 0.5f) - (sy < -0.5f);
+// lut.rs:91-137): move one octant along each stepped axis, OOB when leaving the 2x2x2 block. The step arrives as
+// three "this axis stepped" predicates plus the ray's per-axis direction (+1 / -1), which is what
+// `(step as i32).signum()` of dda_step_to_next_sibling's +-1.0 / 0.0 result is.
+__device__ __forceinline__ uint32_t step_octant(uint32_t octant, bool sx, bool sy, bool sz, int isx, int isy, int isz) {
+    const int ix = (int)(octant & 1u) + (sx ? isx : 0);
+    const int iz = (int)((octant >> 1) & 1u) + (sz ? isz : 0);
+    const int iy = (int)((octant >> 2) & 1u) + (sy ? isy : 0);
     if (((ix | iy | iz) & ~1) != 0) return OOB_OCTANT;
     return (uint32_t)(ix | (iz << 1) | (iy << 2));
 }
@@ -80,18 +81,22 @@ struct RayConst {
     float ox, oy, oz;      // origin
     float dx, dy, dz;      // direction
     float sfx, sfy, sfz;   // get_dda_scale_factors, raytracing_on_cpu.rs:99-112
-    float sgx, sgy, sgz;   // signum(direction)
-    float s0x, s0y, s0z;   // signum.max(0.)
-    uint32_t dirbits;      // hash_direction
+    bool negx, negy, negz; // sign bit of the direction: f32::signum is -1.0 (also for -0.0), else +1.0
+    int isx, isy, isz;     // the same as integers
+    uint32_t dirbits;      // hash_direction, spatial/math/mod.rs:22-26
 };
 
-// dda_step_to_next_sibling, raytracing_on_cpu.rs:124-152
+// dda_step_to_next_sibling, raytracing_on_cpu.rs:124-152.
+//   steps_needed = size * signum.max(0.) - signum * (p - min)      (signum = +-1.0)
+// is `size - (p - min)` for signum +1 (x*1 and 1*x are exact) and `0 - (-(p - min))` = p - min for signum -1; the
+// only bit that can differ is the sign of a zero, which the following `.abs()` removes. A NaN direction component
+// makes its scale factor NaN, hence d NaN, in both forms. Outputs: which axes stepped (min_step == d_axis).
 __device__ __forceinline__ void dda_step(const RayConst& r, float& px, float& py, float& pz, float bx, float by,
-                                         float bz, float bsize, float& stx, float& sty, float& stz) {
+                                         float bz, float bsize, bool& sx, bool& sy, bool& sz) {
     const float dfx = px - bx, dfy = py - by, dfz = pz - bz;
-    const float nx = bsize * r.s0x - r.sgx * dfx;
-    const float ny = bsize * r.s0y - r.sgy * dfy;
-    const float nz = bsize * r.s0z - r.sgz * dfz;
+    const float nx = r.negx ? dfx : (bsize - dfx);
+    const float ny = r.negy ? dfy : (bsize - dfy);
+    const float nz = r.negz ? dfz : (bsize - dfz);
     const float d_x = fabsf(nx * r.sfx);
     const float d_y = fabsf(ny * r.sfy);
     const float d_z = fabsf(nz * r.sfz);
@@ -99,22 +104,23 @@ __device__ __forceinline__ void dda_step(const RayConst& r, float& px, float& py
     px = px + r.dx * m;
     py = py + r.dy * m;
     pz = pz + r.dz * m;
-    stx = (m == d_x) ? r.sgx : 0.0f;
-    sty = (m == d_y) ? r.sgy : 0.0f;
-    stz = (m == d_z) ? r.sgz : 0.0f;
+    sx = (m == d_x);
+    sy = (m == d_y);
+    sz = (m == d_z);
 }
 
+// Everything get_by_ray derives from the direction before the loop (raytracing_on_cpu.rs:331-332)
 __device__ __forceinline__ void ray_setup(RayConst& r) {
     auto sq = [](float v) { return v * v; };  // `.powf(2.)` == x*x
     r.sfx = sqrtf(1.0f + sq(r.dz / r.dx) + sq(r.dy / r.dx));
     r.sfy = sqrtf(sq(r.dx / r.dy) + 1.0f + sq(r.dz / r.dy));
     r.sfz = sqrtf((sq(r.dx / r.dz) + 1.0f) + sq(r.dy / r.dz));
-    r.sgx = rust_signum(r.dx);
-    r.sgy = rust_signum(r.dy);
-    r.sgz = rust_signum(r.dz);
-    r.s0x = fmaxf(r.sgx, 0.0f);
-    r.s0y = fmaxf(r.sgy, 0.0f);
-    r.s0z = fmaxf(r.sgz, 0.0f);
+    r.negx = signbit(r.dx);
+    r.negy = signbit(r.dy);
+    r.negz = signbit(r.dz);
+    r.isx = r.negx ? -1 : 1;
+    r.isy = r.negy ? -1 : 1;
+    r.isz = r.negz ? -1 : 1;
     r.dirbits = hash_region(1.0f + r.dx, 1.0f + r.dy, 1.0f + r.dz, 1.0f);
 }
 
@@ -123,8 +129,8 @@ __device__ __forceinline__ int clamp_index(float v, int dim) { return min(max(__
 // `v.floor() as usize` for the 4x4x4 bitmap position; the reference bounds-panics above 3, we clamp
 __device__ __forceinline__ uint32_t bitmap_coord(float v) { return (uint32_t)min(max(__float2int_rd(v), 0), 3); }
 
-// traverse_brick, raytracing_on_cpu.rs:156-252. Walks the occupancy bit-brick; returns the flat index of the first
-// non-empty voxel or -1.
+// traverse_brick, raytracing_on_cpu.rs:156-252. Walks the occupancy bit-brick (1 bit per voxel, set = not empty) and
+// returns the flat index of the first non-empty voxel or -1. The current 32-voxel word stays in a register.
 __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayConst& r, float& px, float& py, float& pz,
                                               uint32_t brick, float bx, float by, float bz, float bsize,
                                               float inv_size, int& hx, int& hy, int& hz) {
@@ -135,23 +141,28 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     int iz = clamp_index((pz - bz) * fdim * inv_size, dim);
     const float unit = bsize * t.inv_brick_dim;  // size / dim, exact: both powers of two
     float cx = bx + (float)ix * unit, cy = by + (float)iy * unit, cz = bz + (float)iz * unit;
+    // `current_bounds.min_position += step * brick_unit`: step is +-1.0 or 0.0, so the addend is +-unit or +0
+    const float ux = r.negx ? -unit : unit, uy = r.negy ? -unit : unit, uz = r.negz ? -unit : unit;
     const uint32_t* bits = t.brick_bits + (size_t)brick * t.bit_words;
     const uint32_t sh = t.brick_shift;
+    int word_index = -1;
+    uint32_t word = 0u;
     for (;;) {
         if (((ix | iy | iz) < 0) || ix >= dim || iy >= dim || iz >= dim) return -1;
         const int flat = ix + (iy << sh) + (iz << (2 * sh));
-        if ((__ldg(bits + (flat >> 5)) >> (flat & 31)) & 1u) {
+        if ((flat >> 5) != word_index) {
+            word_index = flat >> 5;
+            word = __ldg(bits + word_index);
+        }
+        if ((word >> (flat & 31)) & 1u) {
             hx = ix; hy = iy; hz = iz;
             return flat;
         }
-        float stx, sty, stz;
-        dda_step(r, px, py, pz, cx, cy, cz, unit, stx, sty, stz);
-        cx = cx + stx * unit;
-        cy = cy + sty * unit;
-        cz = cz + stz * unit;
-        ix += __float2int_rn(stx);  // V3c::<i32>::from(step) rounds (vector.rs:354-364); NaN -> 0
-        iy += __float2int_rn(sty);
-        iz += __float2int_rn(stz);
+        bool sx, sy, sz;
+        dda_step(r, px, py, pz, cx, cy, cz, unit, sx, sy, sz);
+        if (sx) { cx = cx + ux; ix += r.isx; }
+        if (sy) { cy = cy + uy; iy += r.isy; }
+        if (sz) { cz = cz + uz; iz += r.isz; }
     }
 }
 
@@ -180,29 +191,52 @@ __device__ __forceinline__ bool probe_brick(const DeviceTree& t, const RayConst&
     return true;
 }
 
-// Octree::get_by_ray -> get_by_ray_at_lod(ray, f32::MAX), raytracing_on_cpu.rs:316-565 (MIP maps off: :369-386 dead)
-__device__ __forceinline__ bool trace_ray(const DeviceTree& t, const RayConst& r, TraceResult& out) {
+// Conservative "this ray certainly misses the root cube" test on APPROXIMATE arithmetic (MUFU reciprocals, no IEEE
+// division). `dx,dy,dz` may be any direction within a few ulp of the exactly normalised one. With a_i the exact
+// numerators (bound - origin, the same single subtraction the exact path performs), every approximate t_i is within
+// 2^-19 relative of the t_i the exact slab test (root_entry) computes; min/max are 1-Lipschitz, so tmin/tmax are
+// within 2^-19 * M, M = max|t_i|. The test only answers "miss" with a 2^-14 * M margin (32x slack) and answers
+// "don't know" for anything non-finite or nearly axis-parallel; those rays take the exact path. It can therefore
+// never change a result, only skip work.
+__device__ __forceinline__ bool certain_root_miss(float ox, float oy, float oz, float dx, float dy, float dz, float size) {
+    const float dmin = fminf(fminf(fabsf(dx), fabsf(dy)), fabsf(dz));
+    if (!(dmin > 1e-20f)) return false;
+    const float rx = __fdividef(1.0f, dx), ry = __fdividef(1.0f, dy), rz = __fdividef(1.0f, dz);
+    const float t1 = (0.0f - ox) * rx, t2 = (size - ox) * rx;
+    const float t3 = (0.0f - oy) * ry, t4 = (size - oy) * ry;
+    const float t5 = (0.0f - oz) * rz, t6 = (size - oz) * rz;
+    const float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+    const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(t1), fabsf(t2)), fmaxf(fabsf(t3), fabsf(t4))), fmaxf(fabsf(t5), fabsf(t6)));
+    if (!(m < 1e30f)) return false;
+    const float e = m * 6.103515625e-5f;  // 2^-14
+    return (tmax < -e) || ((tmin - tmax) > 2.0f * e);
+}
+
+// Cube::intersect_ray on the root cube + the entry point and octant (spatial/raytracing/mod.rs:32-61,
+// raytracing_on_cpu.rs:335-348). Needs only origin and direction of `r`. Returns false when the ray misses.
+__device__ __forceinline__ bool root_entry(const RayConst& r, float tree_size, float& px, float& py, float& pz,
+                                           uint32_t& target_octant) {
+    const float t1 = (0.0f - r.ox) / r.dx, t2 = (tree_size - r.ox) / r.dx;
+    const float t3 = (0.0f - r.oy) / r.dy, t4 = (tree_size - r.oy) / r.dy;
+    const float t5 = (0.0f - r.oz) / r.dz, t6 = (tree_size - r.oz) / r.dz;
+    const float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+    const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+    if (tmax < 0.0f || tmin > tmax) return false;
+    const float d = (tmin < 0.0f) ? 0.0f : tmin;  // impact_distance.unwrap_or(0.)
+    px = r.ox + r.dx * d;
+    py = r.oy + r.dy * d;
+    pz = r.oz + r.dz * d;
+    target_octant = hash_region(px, py, pz, tree_size * 0.5f);
+    return true;
+}
+
+// The loops of get_by_ray_at_lod(ray, f32::MAX), raytracing_on_cpu.rs:349-565 (MIP maps off: :369-386 is dead code),
+// entered with the point / octant root_entry produced and a fully set-up RayConst.
+__device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r, float px, float py, float pz,
+                                         uint32_t target_octant, TraceResult& out) {
     const float tree_size = (float)t.tree_size;
-    float px, py, pz;
-    uint32_t target_octant;
-    {
-        // Cube::intersect_ray on the root cube, spatial/raytracing/mod.rs:32-61
-        const float t1 = (0.0f - r.ox) / r.dx, t2 = (tree_size - r.ox) / r.dx;
-        const float t3 = (0.0f - r.oy) / r.dy, t4 = (tree_size - r.oy) / r.dy;
-        const float t5 = (0.0f - r.oz) / r.dz, t6 = (tree_size - r.oz) / r.dz;
-        const float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
-        const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
-        if (tmax < 0.0f || tmin > tmax) {
-            out.palette_value = NIL;
-            return false;
-        }
-        const float d = (tmin < 0.0f) ? 0.0f : tmin;
-        px = r.ox + r.dx * d;
-        py = r.oy + r.dy * d;
-        pz = r.oz + r.dz * d;
-        target_octant = hash_region(px, py, pz, tree_size * 0.5f);
-    }
-    // NodeStack<u32, 4>, raytracing_on_cpu.rs:20-82: a ring buffer that overwrites its oldest entry
+    // NodeStack<u32, 4>, raytracing_on_cpu.rs:20-82: a ring buffer that overwrites its oldest entry.
     // Held as a 4-deep shift register (s0 = newest): pushing drops the oldest entry, popping removes the newest,
     // which is exactly what the ring buffer does; entries beyond `count` are never read.
     uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
@@ -219,11 +253,10 @@ __device__ __forceinline__ bool trace_ray(const DeviceTree& t, const RayConst& r
         s3 = s2; s2 = s1; s1 = s0; s0 = 0u;
         count = min(count + 1u, 4u);
         while (count != 0u) {
-            // cur == stack[head] at this point: one 16-byte load serves occupancy bits and node kind
+            // cur == top of the stack here: one 16-byte load serves occupancy bits and node kind
             const uint4 hd = __ldg(reinterpret_cast<const uint4*>(t.node_head) + cur);
             const uint32_t oc_lo = hd.x, oc_hi = hd.y, meta = hd.z;
             const uint32_t kind = meta & 3u;
-            bool backtrack = (kind == NK_UNIFORM);
             if (target_octant != OOB_OCTANT) {
                 if (kind == NK_UNIFORM) {
                     if (probe_brick(t, r, px, py, pz, (meta >> 2) & 3u, hd.w, bx, by, bz, bsize, binv, out)) return true;
@@ -243,7 +276,7 @@ __device__ __forceinline__ bool trace_ray(const DeviceTree& t, const RayConst& r
             float bpx = rust_clamp(((px - bx) * 4.0f) * binv, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
             float bpy = rust_clamp(((py - by) * 4.0f) * binv, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
             float bpz = rust_clamp(((pz - bz) * 4.0f) * binv, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
-            if (backtrack || target_octant == OOB_OCTANT || (oc_lo | oc_hi) == 0u ||
+            if (kind == NK_UNIFORM || target_octant == OOB_OCTANT || (oc_lo | oc_hi) == 0u ||
                 !ray_may_hit(oc_lo, oc_hi, bitmap_coord(bpx), bitmap_coord(bpy), bitmap_coord(bpz), r.dirbits)) {
                 // POP (:445-474)
                 count -= 1u;
@@ -258,9 +291,9 @@ __device__ __forceinline__ bool trace_ray(const DeviceTree& t, const RayConst& r
                                 pbz = floorf(bz * inv_twice) * twice;
                     const float half = bsize * 0.5f;
                     const uint32_t from = hash_region((bx + half) - pbx, (by + half) - pby, (bz + half) - pbz, bsize);
-                    float stx, sty, stz;
-                    dda_step(r, px, py, pz, bx, by, bz, bsize, stx, sty, stz);
-                    target_octant = step_octant(from, stx, sty, stz);
+                    bool sx, sy, sz;
+                    dda_step(r, px, py, pz, bx, by, bz, bsize, sx, sy, sz);
+                    target_octant = step_octant(from, sx, sy, sz, r.isx, r.isy, r.isz);
                     bsize = twice;
                     binv = inv_twice;
                     bx = pbx; by = pby; bz = pbz;
@@ -284,18 +317,19 @@ __device__ __forceinline__ bool trace_ray(const DeviceTree& t, const RayConst& r
                 count = min(count + 1u, 4u);
             } else {
                 // ADVANCE (:497-544)
+                const float q = 4.0f * binv;  // `step * 4. / size` is +-q or +0 (sic: 4/size cells)
+                const float qx = r.negx ? -q : q, qy = r.negy ? -q : q, qz = r.negz ? -q : q;
                 for (;;) {
-                    float stx, sty, stz;
-                    dda_step(r, px, py, pz, tbx, tby, tbz, hs, stx, sty, stz);
-                    target_octant = step_octant(target_octant, stx, sty, stz);
+                    bool sx, sy, sz;
+                    dda_step(r, px, py, pz, tbx, tby, tbz, hs, sx, sy, sz);
+                    target_octant = step_octant(target_octant, sx, sy, sz, r.isx, r.isy, r.isz);
                     if (target_octant == OOB_OCTANT) break;
                     tbx = bx + (float)(target_octant & 1u) * hs;
                     tby = by + (float)((target_octant >> 2) & 1u) * hs;
                     tbz = bz + (float)((target_octant >> 1) & 1u) * hs;
-                    // (sic) 4/size cells per sibling step, not 2
-                    bpx = bpx + (stx * 4.0f) * binv;
-                    bpy = bpy + (sty * 4.0f) * binv;
-                    bpz = bpz + (stz * 4.0f) * binv;
+                    if (sx) bpx = bpx + qx;
+                    if (sy) bpy = bpy + qy;
+                    if (sz) bpz = bpz + qz;
                     if (kind == NK_INTERNAL) {
                         child = __ldg(t.node_slot + (size_t)cur * 8u + target_octant);
                         if (child != NIL && octant_occupied(oc_lo, oc_hi, target_octant) &&
@@ -318,6 +352,17 @@ __device__ __forceinline__ bool trace_ray(const DeviceTree& t, const RayConst& r
     }
     out.palette_value = NIL;
     return false;
+}
+
+// Octree::get_by_ray (raytracing_on_cpu.rs:316-318) for a ray whose origin / direction are set in `r`
+__device__ __forceinline__ bool trace_ray(const DeviceTree& t, RayConst& r, TraceResult& out) {
+    float px, py, pz;
+    uint32_t target_octant;
+    out.palette_value = NIL;
+    if (certain_root_miss(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, (float)t.tree_size)) return false;
+    if (!root_entry(r, (float)t.tree_size, px, py, pz, target_octant)) return false;
+    ray_setup(r);
+    return traverse(t, r, px, py, pz, target_octant, out);
 }
 
 // cube_impact_normal, spatial/raytracing/mod.rs:106-134
