@@ -231,6 +231,69 @@ __device__ __forceinline__ bool root_entry(const RayConst& r, float tree_size, f
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Exact fast-forward of the reference's "0.1 nudge" crawl (raytracing_on_cpu.rs:548-562).
+//
+// When the root's occupancy test fails (:438-443) the root is popped, the stack is empty, and the outer loop only does
+//     p += direction * 0.1 ; bounds check ; re-hash the root octant
+// once per iteration until the 4x4x4 bitmap cell of p changes (the test depends on nothing else) or p leaves the cube.
+// A ray looking over a 1024^3 terrain repeats this ~10^4 times. The additions are f32 and must be reproduced bit for
+// bit, but they have a closed form: for x in one binade [2^e, 2^(e+1)), ulp u = 2^(e-23), x = X*u with integer X, and
+// c = t*u with real t, RN(x + c) = (X + rint(t))*u whenever t is not a tie (frac(t) != 0.5) and the sum stays in the
+// binade - independent of X. So n consecutive additions give (X + n*q)*u exactly, q = rint(t). crawl_limit() returns
+// how many additions one axis can take before it would leave its binade or cross the next cell / cube boundary
+// (multiples of size/4); the minimum over the axes is applied in one step. Anything irregular (tie, denormal,
+// |c| >= 2^e) returns 0 and the caller falls back to stepping one addition at a time, which is always valid.
+struct CrawlAxis {
+    uint32_t limit;  // additions that are certainly "same binade, same cell, in bounds"
+    int q;           // mantissa increment per addition
+};
+
+__device__ __forceinline__ CrawlAxis crawl_limit(float x, float c, float quarter, float inv_quarter) {
+    CrawlAxis a;
+    a.limit = 0u;
+    a.q = 0;
+    const uint32_t bits = __float_as_uint(x);
+    const uint32_t ef = bits >> 23;            // sign is 0: x > 0 inside the cube
+    if (ef < 24u || ef > 200u) return a;       // denormal / tiny / huge: step explicitly
+    const uint32_t X = (bits & 0x7FFFFFu) | 0x800000u;
+    const float to_ulps = __uint_as_float((277u - ef) << 23);  // 2^(23 - e), exact
+    const float t = c * to_ulps;               // exact scaling
+    if (!(fabsf(t) < 8388608.0f)) return a;    // |c| >= 2^e (or NaN): leaves the binade at once
+    const int q = __float2int_rn(t);
+    if (fabsf(t - (float)q) == 0.5f) return a; // tie: rounding would depend on the parity of X
+    a.q = q;
+    if (q == 0) {                              // x + c rounds back to x: this axis never moves
+        a.limit = 0xFFFFFFFFu;
+        return a;
+    }
+    const float cell = floorf(x * inv_quarter);  // bitmap cell along this axis (x * 4 / size, exact scaling)
+    if (q > 0) {
+        const uint32_t lim_binade = (0xFFFFFFu - X) / (uint32_t)q;
+        // stays in the cell (and, for the last cell, inside the cube) while x_n < (cell + 1) * size/4
+        const float bu = ((cell + 1.0f) * quarter) * to_ulps;  // boundary in ulps: an exact integer, maybe > 2^24
+        const uint32_t b = bu >= 16777216.0f ? 16777216u : (uint32_t)bu;
+        const uint32_t lim_cell = (b - 1u >= X) ? (b - 1u - X) / (uint32_t)q : 0u;
+        a.limit = min(lim_binade, lim_cell);
+    } else {
+        const uint32_t nq = (uint32_t)(-q);
+        const uint32_t lim_binade = (X - 0x800000u) / nq;
+        // stays in the cell while x_n >= cell * size/4 (x_n > 0 is implied by staying in the binade)
+        const uint32_t b = (uint32_t)((cell * quarter) * to_ulps);
+        const uint32_t lim_cell = (X >= b) ? (X - b) / nq : 0u;
+        a.limit = min(lim_binade, lim_cell);
+    }
+    return a;
+}
+
+__device__ __forceinline__ float crawl_apply(float x, int q, uint32_t n) {
+    if (q == 0) return x;
+    const uint32_t bits = __float_as_uint(x);
+    const uint32_t X = (bits & 0x7FFFFFu) | 0x800000u;
+    const uint32_t Xn = (uint32_t)((int)X + q * (int)n);  // stays within [2^23, 2^24) by construction
+    return __uint_as_float((bits & 0x7F800000u) | (Xn & 0x7FFFFFu));
+}
+
 // The loops of get_by_ray_at_lod(ray, f32::MAX), raytracing_on_cpu.rs:349-565 (MIP maps off: :369-386 is dead code),
 // entered with the point / octant root_entry produced and a fully set-up RayConst.
 __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r, float px, float py, float pz,
@@ -245,7 +308,46 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
     float bx = 0.0f, by = 0.0f, bz = 0.0f, bsize = tree_size;
     float binv = t.inv_tree_size;  // 1 / bsize, exact (powers of two), tracked alongside bsize
 
+    // the root record is needed on every restart; Internal / Nothing roots can crawl (a leaf root probes bricks)
+    const uint4 root_hd = __ldg(reinterpret_cast<const uint4*>(t.node_head));
+    const bool root_can_crawl = (root_hd.z & 3u) == NK_INTERNAL || (root_hd.z & 3u) == NK_NOTHING;
+    const float cwx = r.dx * 0.1f, cwy = r.dy * 0.1f, cwz = r.dz * 0.1f;  // `ray.direction * 0.1` (:551)
+    const float quarter = tree_size * 0.25f, inv_quarter = t.inv_tree_size * 4.0f;
+
     while (target_octant != OOB_OCTANT) {
+        if (root_can_crawl) {
+            // Outer iterations in which the root is popped right away, without touching the stack or the tree:
+            // test the root's occupancy for the cell of p; on failure nudge p, check the bounds, repeat.
+            uint32_t fails = 0u;
+            for (;;) {
+                const float cpx = rust_clamp((px * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+                const float cpy = rust_clamp((py * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+                const float cpz = rust_clamp((pz * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+                if ((root_hd.x | root_hd.y) != 0u &&
+                    ray_may_hit(root_hd.x, root_hd.y, bitmap_coord(cpx), bitmap_coord(cpy), bitmap_coord(cpz), r.dirbits))
+                    break;  // the root survives its test: run the node loop below
+                if (++fails >= 2u) {
+                    // a run of failing iterations: apply as many nudges as provably change nothing, at once
+                    const CrawlAxis ax = crawl_limit(px, cwx, quarter, inv_quarter);
+                    const CrawlAxis ay = crawl_limit(py, cwy, quarter, inv_quarter);
+                    const CrawlAxis az = crawl_limit(pz, cwz, quarter, inv_quarter);
+                    const uint32_t n = min(min(ax.limit, ay.limit), az.limit);
+                    if (n != 0u && n != 0xFFFFFFFFu) {
+                        px = crawl_apply(px, ax.q, n);
+                        py = crawl_apply(py, ay.q, n);
+                        pz = crawl_apply(pz, az.q, n);
+                    }
+                }
+                px = px + cwx;
+                py = py + cwy;
+                pz = pz + cwz;
+                if (!(px < tree_size && py < tree_size && pz < tree_size && px > 0.0f && py > 0.0f && pz > 0.0f)) {
+                    out.palette_value = NIL;
+                    return false;
+                }
+            }
+            target_octant = hash_region(px, py, pz, tree_size * 0.5f);
+        }
         cur = 0;
         bx = by = bz = 0.0f;
         bsize = tree_size;
@@ -342,9 +444,9 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             }
         }
         // restart from the root after a 0.1 nudge (:548-562)
-        px = px + r.dx * 0.1f;
-        py = py + r.dy * 0.1f;
-        pz = pz + r.dz * 0.1f;
+        px = px + cwx;
+        py = py + cwy;
+        pz = pz + cwz;
         if (px < tree_size && py < tree_size && pz < tree_size && px > 0.0f && py > 0.0f && pz > 0.0f)
             target_octant = hash_region(px, py, pz, tree_size * 0.5f);
         else

@@ -272,3 +272,31 @@ def test_render_is_deterministic_and_counts_launches():
         assert np.array_equal(a[k], b[k])
     f = view.render()
     assert f["kernel_ms"] > 0 and f["hit_id"]
+
+
+def test_crawl_fast_forward_is_exact_on_a_large_tree():
+    """rays that skim over a 512^3 terrain take thousands of 0.1-nudge restarts; the kernel fast-forwards
+    them in closed form and must still land on the oracle's bits."""
+    scene = scenes.terrain_scene(512, 8, 4321, 1, shell=4)
+    tree, otree = both_trees(scene)
+    cam = scenes.terrain_camera(512)
+    ocam = oracle_camera(cam)
+    rays = np.stack([O.pixel_ray(ocam, 320, 180, x, y) for y in range(0, 180, 3) for x in range(0, 320, 3)])
+    g = S.OctreeGPUHost(tree).get_by_rays(rays)
+    o = otree.get_by_rays(rays)
+    assert int(o["outer_iters"].max()) > 2000  # the crawl really happens
+    assert np.array_equal(g["hit"], o["hit"]) and np.array_equal(g["palette_value"], o["palette_value"])
+    assert np.array_equal(bits(g["impact_point"]), bits(o["impact_point"]))
+    assert np.array_equal(bits(g["distance"]), bits(o["distance"]))
+    # rays from inside the tree, in every direction octant (negative steps, all binades down to the origin corner)
+    rng = np.random.default_rng(5)
+    origin = rng.uniform(1, 511, (3000, 3)).astype(np.float32)
+    origin[:, 1] = rng.uniform(200, 511, 3000).astype(np.float32)
+    d = rng.normal(size=(3000, 3)).astype(np.float32)
+    d[:, 1] = np.abs(d[:, 1]) * 0.2
+    ln = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2], dtype=np.float32)
+    rays = np.concatenate([origin, (d / ln[:, None]).astype(np.float32)], axis=1)
+    g = S.OctreeGPUHost(tree).get_by_rays(rays)
+    o = otree.get_by_rays(rays)
+    assert np.array_equal(g["hit"], o["hit"]) and np.array_equal(g["palette_value"], o["palette_value"])
+    assert np.array_equal(bits(g["impact_point"]), bits(o["impact_point"]))
