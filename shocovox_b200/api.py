@@ -148,7 +148,10 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    import os
+
+    override = os.environ.get("SVX_LIB")  # a tuning variant built with build.build(out=..., defines=...)
+    path = Path(override) if override else _build.build()
     if not path.exists():
         raise OctreeError(E_CUDA, f"{path} is missing: build it with `python -m shocovox_b200.build`")
     L = C.CDLL(str(path))

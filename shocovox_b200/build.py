@@ -36,11 +36,12 @@ def is_stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: Path = LIB, defines=()) -> Path:
+    """Builds the library. `out` / `defines` produce tuning variants (e.g. -DSVX_MIN_BLOCKS=4) next to the default."""
+    if not force and out == LIB and not is_stale():
         return LIB
     cmd = [
-        nvcc_path(), "-shared", "-o", str(LIB),
+        nvcc_path(), "-shared", "-o", str(out), *[f"-D{d}" for d in defines],
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-std=c++17", "-lineinfo",
         "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
@@ -54,8 +55,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
-    (PKG / "build_ptxas.log").write_text(res.stderr)
-    return LIB
+    (PKG / ("build_ptxas.log" if out == LIB else out.name + ".ptxas.log")).write_text(res.stderr)
+    return out
 
 
 if __name__ == "__main__":

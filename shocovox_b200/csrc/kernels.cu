@@ -10,6 +10,9 @@ namespace svx {
 constexpr int TILE_W = 32;
 constexpr int TILE_H = 8;
 constexpr int BLOCK_THREADS = 256;
+#ifndef SVX_MIN_BLOCKS
+#define SVX_MIN_BLOCKS 4
+#endif
 
 __device__ __forceinline__ void pixel_of_thread(int& tx, int& ty) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -31,7 +34,7 @@ __device__ __forceinline__ void glass_vector(const FrameParams& f, uint32_t x, u
     vz = gz - f.oz;
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const DeviceTree tree, const FrameParams f) {
+__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
     const uint32_t x = blockIdx.x * TILE_W + tx;

@@ -249,6 +249,13 @@ struct CrawlAxis {
     int q;           // mantissa increment per addition
 };
 
+// floor(gap / q) from below without an integer division: the approximate quotient is at most 2 ulp high, the
+// (1 - 2^-20) factor pulls it under the real quotient, and truncation then never exceeds floor(gap / q). A smaller
+// count is always valid (fewer additions are fast-forwarded). gap < 2^24 and q < 2^23 are exact in f32.
+__device__ __forceinline__ uint32_t floor_div_below(uint32_t gap, uint32_t q) {
+    return (uint32_t)(__fdividef((float)gap, (float)q) * 0.99999904632568359375f);
+}
+
 __device__ __forceinline__ CrawlAxis crawl_limit(float x, float c, float quarter, float inv_quarter) {
     CrawlAxis a;
     a.limit = 0u;
@@ -269,19 +276,16 @@ __device__ __forceinline__ CrawlAxis crawl_limit(float x, float c, float quarter
     }
     const float cell = floorf(x * inv_quarter);  // bitmap cell along this axis (x * 4 / size, exact scaling)
     if (q > 0) {
-        const uint32_t lim_binade = (0xFFFFFFu - X) / (uint32_t)q;
-        // stays in the cell (and, for the last cell, inside the cube) while x_n < (cell + 1) * size/4
-        const float bu = ((cell + 1.0f) * quarter) * to_ulps;  // boundary in ulps: an exact integer, maybe > 2^24
-        const uint32_t b = bu >= 16777216.0f ? 16777216u : (uint32_t)bu;
-        const uint32_t lim_cell = (b - 1u >= X) ? (b - 1u - X) / (uint32_t)q : 0u;
-        a.limit = min(lim_binade, lim_cell);
+        // stays in the binade while X_n <= 2^24 - 1, and in the cell (for the last cell: inside the cube) while
+        // x_n < (cell + 1) * size/4. The boundary in ulps is an exact integer, possibly beyond the binade.
+        const float bu = ((cell + 1.0f) * quarter) * to_ulps;
+        const uint32_t top = bu >= 16777216.0f ? 16777216u : (uint32_t)bu;
+        a.limit = (top - 1u >= X) ? floor_div_below(top - 1u - X, (uint32_t)q) : 0u;
     } else {
-        const uint32_t nq = (uint32_t)(-q);
-        const uint32_t lim_binade = (X - 0x800000u) / nq;
-        // stays in the cell while x_n >= cell * size/4 (x_n > 0 is implied by staying in the binade)
+        // stays in the binade while X_n >= 2^23 and in the cell while x_n >= cell * size/4 (x_n > 0 is implied)
         const uint32_t b = (uint32_t)((cell * quarter) * to_ulps);
-        const uint32_t lim_cell = (X >= b) ? (X - b) / nq : 0u;
-        a.limit = min(lim_binade, lim_cell);
+        const uint32_t bottom = max(b, 0x800000u);
+        a.limit = (X >= bottom) ? floor_div_below(X - bottom, (uint32_t)(-q)) : 0u;
     }
     return a;
 }
