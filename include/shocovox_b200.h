@@ -172,6 +172,16 @@ SVX_API int32_t svx_view_resolution(const svx_view* view, uint32_t* width, uint3
 /* Multi-GPU sharding: this view renders image rows r with (r / rows_per_band) % world == rank. world = 1 renders
  * everything (the default). rows_per_band must be a power of two. */
 SVX_API int32_t svx_view_set_shard(svx_view* view, uint32_t rank, uint32_t world, uint32_t rows_per_band);
+/* With compact rows the shard's rows are stored back to back ([rows_local][width], band-major) instead of at their image
+ * rows: the layout a collective gather wants. */
+SVX_API int32_t svx_view_set_compact_rows(svx_view* view, int32_t enabled);
+/* Device pointers of the view's framebuffer planes (valid until set_resolution / free) */
+SVX_API int32_t svx_view_frame_pointers(const svx_view* view, void** hit_id, void** albedo, void** distance);
+/* Fused gather over NVLink: export this view's framebuffer planes as three 64-byte CUDA IPC handles, and make another
+ * view (in another process, on another GPU) store its shard straight into them from inside the traversal kernel.
+ * Passing null detaches. The exporting view must outlive every importer. */
+SVX_API int32_t svx_view_export_frame_ipc(const svx_view* view, uint8_t* handles_3x64);
+SVX_API int32_t svx_view_set_peer_frame_ipc(svx_view* view, const uint8_t* handles_3x64);
 /* One frame: in-kernel ray generation (examples/cpu_render.rs:78-114) + get_by_ray per pixel + framebuffer write.
  * Asynchronous on the view's stream unless `out` is non-null, in which case the call synchronises and fills it. */
 SVX_API int32_t svx_view_render(svx_view* view, svx_frame* out);

@@ -147,7 +147,10 @@ struct svx_view {
     svx_viewport viewport{};
     int32_t glass_mode = SVX_GLASS_AT_FOV;
     uint32_t width = 0, height = 0;
-    uint32_t rank = 0, world = 1, band_rows = 8;
+    uint32_t rank = 0, world = 1, band_rows = 8, compact = 0;
+    // peer framebuffers opened from CUDA IPC handles (fused gather: the kernel stores straight into another GPU)
+    void* peer_base[3] = {nullptr, nullptr, nullptr};
+    bool use_peer = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t tm_start = nullptr, tm_stop = nullptr;
@@ -248,9 +251,10 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     for (uint32_t b = v->rank; b < bands; b += v->world) ++owned_bands;
     f->rows_local = owned_bands * v->band_rows;
     (void)rows;
-    f->hit_id = v->d_hit_id;
-    f->albedo = v->d_albedo;
-    f->distance = v->d_distance;
+    f->compact = v->compact;
+    f->hit_id = v->use_peer ? (uint32_t*)v->peer_base[0] : v->d_hit_id;
+    f->albedo = v->use_peer ? (uint32_t*)v->peer_base[1] : v->d_albedo;
+    f->distance = v->use_peer ? (float*)v->peer_base[2] : v->d_distance;
 }
 
 int32_t alloc_frame(svx_view* v) {
@@ -510,6 +514,8 @@ void svx_view_free(svx_view* v) {
     if (v->ev_stop) cudaEventDestroy(v->ev_stop);
     if (v->tm_start) cudaEventDestroy(v->tm_start);
     if (v->tm_stop) cudaEventDestroy(v->tm_stop);
+    for (int i = 0; i < 3; ++i)
+        if (v->peer_base[i]) cudaIpcCloseMemHandle(v->peer_base[i]);
     cudaFree(v->d_flush);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
@@ -554,6 +560,54 @@ int32_t svx_view_set_shard(svx_view* v, uint32_t rank, uint32_t world, uint32_t 
     v->rank = rank;
     v->world = world;
     v->band_rows = rows_per_band;
+    return SVX_OK;
+}
+
+int32_t svx_view_set_compact_rows(svx_view* v, int32_t enabled) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    v->compact = enabled ? 1u : 0u;
+    return SVX_OK;
+}
+
+int32_t svx_view_frame_pointers(const svx_view* v, void** hit_id, void** albedo, void** distance) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    if (hit_id) *hit_id = v->d_hit_id;
+    if (albedo) *albedo = v->d_albedo;
+    if (distance) *distance = v->d_distance;
+    return SVX_OK;
+}
+
+int32_t svx_view_export_frame_ipc(const svx_view* v, uint8_t* handles /* 3 x 64 bytes */) {
+    if (!v || !handles) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    void* ptrs[3] = {v->d_hit_id, v->d_albedo, v->d_distance};
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h, ptrs[i]));
+        std::memcpy(handles + 64 * i, &h, 64);
+    }
+    return SVX_OK;
+}
+
+int32_t svx_view_set_peer_frame_ipc(svx_view* v, const uint8_t* handles /* 3 x 64 bytes, or null to detach */) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    for (int i = 0; i < 3; ++i) {
+        if (v->peer_base[i]) cudaIpcCloseMemHandle(v->peer_base[i]);
+        v->peer_base[i] = nullptr;
+    }
+    v->use_peer = false;
+    if (!handles) return SVX_OK;
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * i, 64);
+        CUDA_TRY(cudaIpcOpenMemHandle(&v->peer_base[i], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    v->use_peer = true;
     return SVX_OK;
 }
 

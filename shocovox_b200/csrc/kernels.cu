@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(c
     const uint32_t row = ((band * f.world + f.rank) << f.band_shift) + within;
     if (row >= f.height) return;
     const uint32_t y = f.height - 1u - row;  // pixel (x, y) lands in image row h-1-y (cpu_render.rs:106)
-    const size_t i = (size_t)row * f.width + x;
+    const size_t i = (size_t)(f.compact ? lr : row) * f.width + x;
 
     float vx, vy, vz;
     glass_vector(f, x, y, vx, vy, vz);
