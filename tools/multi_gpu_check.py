@@ -57,10 +57,7 @@ def main():
 
     # (a) compact bands + NCCL all-gather
     lr = D.padded_local_rows(h, world, args.band)
-    va = host.create_new_view(64, vp, (w, lr))  # a compact buffer of local rows
-    va.set_resolution((w, h))                   # framebuffer is (h, w); only the first `lr` rows are used when compact
-    if cam.glass_at_frustum_z:
-        va.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+    va = new_view()  # framebuffer is (h, w); only the first `lr` rows are used when compact
     va.set_shard(rank, world, args.band)
     va.set_compact_rows(True)
     ptrs = va.frame_pointers()
