@@ -322,7 +322,11 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
         if (root_can_crawl) {
             // Outer iterations in which the root is popped right away, without touching the stack or the tree:
             // test the root's occupancy for the cell of p; on failure nudge p, check the bounds, repeat.
+            // Per-axis fast-forward state: q = mantissa increment per nudge, rem = further nudges that provably keep the
+            // axis in its binade, bitmap cell and the cube. An axis is re-analysed only after its own budget ran out.
             uint32_t fails = 0u;
+            int qx = 0, qy = 0, qz = 0;
+            uint32_t remx = 0u, remy = 0u, remz = 0u;
             for (;;) {
                 const float cpx = rust_clamp((px * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
                 const float cpy = rust_clamp((py * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
@@ -332,15 +336,22 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                     break;  // the root survives its test: run the node loop below
                 if (++fails >= 2u) {
                     // a run of failing iterations: apply as many nudges as provably change nothing, at once
-                    const CrawlAxis ax = crawl_limit(px, cwx, quarter, inv_quarter);
-                    const CrawlAxis ay = crawl_limit(py, cwy, quarter, inv_quarter);
-                    const CrawlAxis az = crawl_limit(pz, cwz, quarter, inv_quarter);
-                    const uint32_t n = min(min(ax.limit, ay.limit), az.limit);
+                    if (remx == 0u) { const CrawlAxis a = crawl_limit(px, cwx, quarter, inv_quarter); qx = a.q; remx = a.limit; }
+                    if (remy == 0u) { const CrawlAxis a = crawl_limit(py, cwy, quarter, inv_quarter); qy = a.q; remy = a.limit; }
+                    if (remz == 0u) { const CrawlAxis a = crawl_limit(pz, cwz, quarter, inv_quarter); qz = a.q; remz = a.limit; }
+                    const uint32_t n = min(min(remx, remy), remz);
                     if (n != 0u && n != 0xFFFFFFFFu) {
-                        px = crawl_apply(px, ax.q, n);
-                        py = crawl_apply(py, ay.q, n);
-                        pz = crawl_apply(pz, az.q, n);
+                        px = crawl_apply(px, qx, n);
+                        py = crawl_apply(py, qy, n);
+                        pz = crawl_apply(pz, qz, n);
+                        if (remx != 0xFFFFFFFFu) remx -= n;
+                        if (remy != 0xFFFFFFFFu) remy -= n;
+                        if (remz != 0xFFFFFFFFu) remz -= n;
                     }
+                    // the explicit nudge below consumes one more regular step of every axis that still has budget
+                    if (remx != 0u && remx != 0xFFFFFFFFu) remx -= 1u;
+                    if (remy != 0u && remy != 0xFFFFFFFFu) remy -= 1u;
+                    if (remz != 0u && remz != 0xFFFFFFFFu) remz -= 1u;
                 }
                 px = px + cwx;
                 py = py + cwy;
