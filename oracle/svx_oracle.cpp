@@ -367,8 +367,15 @@ static const uint32_t* get_homogeneous_data(const Brick& b) {
         case BrickKind::Empty: return nullptr;
         case BrickKind::Solid: return &b.solid;
         case BrickKind::Parted:
-            for (uint32_t v : b.data)
-                if (v != b.data[0]) return nullptr;
+            // same answer as the reference's linear scan; `witness` remembers an index that differed last time so
+            // that repeated calls on a growing brick stay O(1) (build-time only, no effect on results)
+            if (b.witness != 0 && b.witness < b.data.size() && b.data[b.witness] != b.data[0]) return nullptr;
+            for (size_t i = 1; i < b.data.size(); ++i)
+                if (b.data[i] != b.data[0]) {
+                    b.witness = (uint32_t)i;
+                    return nullptr;
+                }
+            b.witness = 0;
             return &b.data[0];
     }
     return nullptr;
@@ -989,46 +996,55 @@ bool Octree::simplify(size_t node_key) {
                 nodes.item[node_key] = std::move(u);
                 return true;
             }
-            std::vector<uint32_t> unified(d * d * d, EMPTY_MARKER_U32);
+            // update/mod.rs:860-997. The reference fills the unified brick while it checks; the check is done first here
+            // (same predicate, same early exits) so that the dim^3 buffer is only built when it is going to be used.
             bool is_leaf_uniform = true;
             const Luts& l = luts();
-            for (int octant = 0; octant < 8; ++octant) {
-                const size_t brick_half = d / 2;
-                const V3s octant_offset = to_usize(l.octant_offset[octant] * (float)brick_half);
+            const size_t brick_half = d / 2;
+            for (int octant = 0; octant < 8 && is_leaf_uniform; ++octant) {
                 const Brick& b = node.bricks[octant];
-                switch (b.kind) {
-                    case BrickKind::Empty: is_leaf_uniform &= (b == node.bricks[0]); break;
-                    case BrickKind::Solid:
-                        is_leaf_uniform &= (b == node.bricks[0]);
-                        for (size_t x = octant_offset.x; x < octant_offset.x + brick_half; ++x)
-                            for (size_t y = octant_offset.y; y < octant_offset.y + brick_half; ++y)
-                                for (size_t z = octant_offset.z; z < octant_offset.z + brick_half; ++z)
-                                    unified[flat_projection(x, y, z, d)] = b.solid;
-                        break;
-                    case BrickKind::Parted:
-                        for (size_t x = 0; x < brick_half; ++x)
-                            for (size_t y = 0; y < brick_half; ++y)
-                                for (size_t z = 0; z < brick_half; ++z) {
-                                    if (!is_leaf_uniform) break;
-                                    const uint32_t v0 = b.data[flat_projection(x * 2, y * 2, z * 2, d)];
-                                    if (v0 == b.data[flat_projection(x * 2 + 1, y * 2, z * 2, d)] &&
-                                        v0 == b.data[flat_projection(x * 2, y * 2 + 1, z * 2, d)] &&
-                                        v0 == b.data[flat_projection(x * 2, y * 2, z * 2 + 1, d)] &&
-                                        v0 == b.data[flat_projection(x * 2 + 1, y * 2 + 1, z * 2, d)] &&
-                                        v0 == b.data[flat_projection(x * 2, y * 2 + 1, z * 2 + 1, d)] &&
-                                        v0 == b.data[flat_projection(x * 2 + 1, y * 2, z * 2 + 1, d)] &&
-                                        v0 == b.data[flat_projection(x * 2 + 1, y * 2 + 1, z * 2 + 1, d)]) {
-                                        unified[flat_projection(octant_offset.x + x, octant_offset.y + y,
-                                                                octant_offset.z + z, d)] = v0;
-                                    } else {
-                                        is_leaf_uniform = false;
-                                    }
-                                }
-                        break;
+                if (b.kind != BrickKind::Parted) {
+                    is_leaf_uniform &= (b == node.bricks[0]);
+                    continue;
                 }
-                if (!is_leaf_uniform) break;
+                auto block_uniform = [&](size_t x, size_t y, size_t z) {
+                    const uint32_t v0 = b.data[flat_projection(x * 2, y * 2, z * 2, d)];
+                    return v0 == b.data[flat_projection(x * 2 + 1, y * 2, z * 2, d)] &&
+                           v0 == b.data[flat_projection(x * 2, y * 2 + 1, z * 2, d)] &&
+                           v0 == b.data[flat_projection(x * 2, y * 2, z * 2 + 1, d)] &&
+                           v0 == b.data[flat_projection(x * 2 + 1, y * 2 + 1, z * 2, d)] &&
+                           v0 == b.data[flat_projection(x * 2, y * 2 + 1, z * 2 + 1, d)] &&
+                           v0 == b.data[flat_projection(x * 2 + 1, y * 2, z * 2 + 1, d)] &&
+                           v0 == b.data[flat_projection(x * 2 + 1, y * 2 + 1, z * 2 + 1, d)];
+                };
+                if (b.witness2 != 0xFFFFFFFFu && brick_half > 0) {
+                    const size_t w = b.witness2;
+                    if (!block_uniform(w % brick_half, (w / brick_half) % brick_half, w / (brick_half * brick_half))) {
+                        is_leaf_uniform = false;
+                        break;
+                    }
+                }
+                b.witness2 = 0xFFFFFFFFu;
+                for (size_t x = 0; x < brick_half && is_leaf_uniform; ++x)
+                    for (size_t y = 0; y < brick_half && is_leaf_uniform; ++y)
+                        for (size_t z = 0; z < brick_half && is_leaf_uniform; ++z)
+                            if (!block_uniform(x, y, z)) {
+                                b.witness2 = (uint32_t)(x + y * brick_half + z * brick_half * brick_half);
+                                is_leaf_uniform = false;
+                            }
             }
             if (is_leaf_uniform) {
+                std::vector<uint32_t> unified(d * d * d, EMPTY_MARKER_U32);
+                for (int octant = 0; octant < 8; ++octant) {
+                    const V3s octant_offset = to_usize(l.octant_offset[octant] * (float)brick_half);
+                    const Brick& b = node.bricks[octant];
+                    if (b.kind == BrickKind::Empty) continue;
+                    for (size_t x = 0; x < brick_half; ++x)
+                        for (size_t y = 0; y < brick_half; ++y)
+                            for (size_t z = 0; z < brick_half; ++z)
+                                unified[flat_projection(octant_offset.x + x, octant_offset.y + y, octant_offset.z + z, d)] =
+                                    b.kind == BrickKind::Solid ? b.solid : b.data[flat_projection(x * 2, y * 2, z * 2, d)];
+                }
                 Node u;
                 u.kind = NodeKind::UniformLeaf;
                 u.ubrick.kind = BrickKind::Parted;

@@ -47,6 +47,10 @@ struct Brick {
     BrickKind kind = BrickKind::Empty;
     uint32_t solid = 0;           // valid when kind == Solid
     std::vector<uint32_t> data;   // valid when kind == Parted (dim^3, x fastest)
+    // build-time hints only (always re-verified, never change a result): an index that differed from data[0] /
+    // a 2x2x2 block that was non-uniform the last time the brick was scanned
+    mutable uint32_t witness = 0;
+    mutable uint32_t witness2 = 0xFFFFFFFFu;
     bool operator==(const Brick& o) const;
 };
 

@@ -147,8 +147,12 @@ uint32_t HostOctree::brick_alloc(uint32_t fill) {
     } else {
         h = (uint32_t)(voxels_.size() / vol_);
         voxels_.resize(voxels_.size() + vol_);
+        witness_.push_back(0u);
+        witness2_.push_back(0xFFFFFFFFu);
     }
     std::fill_n(brick_mut(h), vol_, fill);
+    witness_[h] = 0u;
+    witness2_[h] = 0xFFFFFFFFu;
     return h;
 }
 
@@ -184,10 +188,46 @@ bool HostOctree::brick_homogeneous(const BrickRef& b, uint32_t* v) const {
         *v = b.value;
         return true;
     }
+    // Same answer as the reference's linear scan, amortised: remember one position that differed from d[0] last
+    // time (a "witness"); while it still differs the brick cannot be homogeneous.
     const uint32_t* d = brick_data(b.value);
+    uint32_t& w = witness_[b.value];
+    if (w != 0u && d[w] != d[0]) return false;
     for (uint32_t i = 1; i < vol_; ++i)
-        if (d[i] != d[0]) return false;
+        if (d[i] != d[0]) {
+            w = i;
+            return false;
+        }
+    w = 0u;
     *v = d[0];
+    return true;
+}
+
+// Is every aligned 2x2x2 block of the brick one value? (the test update/mod.rs:884-980 applies to Parted bricks when it
+// tries to express 8 bricks as one brick of half the resolution). Same answer as the reference's scan, amortised with
+// a witness: the flat index of a block corner that was found non-uniform last time.
+bool HostOctree::brick_blockwise_uniform(uint32_t handle) const {
+    const uint32_t* d = brick_data(handle);
+    const size_t half = dim_ / 2;
+    auto block_uniform = [&](size_t x, size_t y, size_t z) {
+        const uint32_t v = d[flat(2 * x, 2 * y, 2 * z, dim_)];
+        for (size_t c = 1; c < 8; ++c)
+            if (d[flat(2 * x + (c & 1), 2 * y + ((c >> 1) & 1), 2 * z + (c >> 2), dim_)] != v) return false;
+        return true;
+    };
+    uint32_t& w = witness2_[handle];
+    if (w != 0xFFFFFFFFu) {
+        const size_t x = w % half, y = (w / half) % half, z = w / (half * half);
+        if (!block_uniform(x, y, z)) return false;
+    }
+    for (size_t x = 0; x < half; ++x)
+        for (size_t y = 0; y < half; ++y)
+            for (size_t z = 0; z < half; ++z)
+                if (!block_uniform(x, y, z)) {
+                    w = (uint32_t)(x + y * half + z * half * half);
+                    return false;
+                }
+    w = 0xFFFFFFFFu;
     return true;
 }
 
@@ -648,17 +688,7 @@ bool HostOctree::simplify(size_t key) {
                     uniform = brick_equal(b, n.brick[0]);
                     continue;
                 }
-                const uint32_t* d = brick_data(b.value);
-                for (size_t x = 0; x < half && uniform; ++x)
-                    for (size_t y = 0; y < half && uniform; ++y)
-                        for (size_t z = 0; z < half && uniform; ++z) {
-                            const uint32_t v = d[flat(2 * x, 2 * y, 2 * z, dim_)];
-                            for (size_t c = 1; c < 8; ++c)
-                                if (d[flat(2 * x + (c & 1), 2 * y + ((c >> 1) & 1), 2 * z + (c >> 2), dim_)] != v) {
-                                    uniform = false;
-                                    break;
-                                }
-                        }
+                uniform = brick_blockwise_uniform(b.value);
             }
             if (!uniform) return simplified;
             const uint32_t h = brick_alloc(NIL);

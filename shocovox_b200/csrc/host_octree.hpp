@@ -84,6 +84,7 @@ class HostOctree {
     bool brick_equal(const BrickRef& a, const BrickRef& b) const;
     bool brick_homogeneous(const BrickRef& b, uint32_t* v) const;
     bool brick_simplify(BrickRef& b);
+    bool brick_blockwise_uniform(uint32_t handle) const;
     uint64_t brick_bits(const uint32_t* vox) const;
     uint64_t brick_ref_bits(const BrickRef& b) const;
     void clear_content(size_t key);  // drops bricks, kind = Nothing
@@ -109,6 +110,8 @@ class HostOctree {
     size_t first_available_ = 0;
     std::vector<uint32_t> voxels_;
     std::vector<uint32_t> free_bricks_;
+    mutable std::vector<uint32_t> witness2_;  // per brick: a 2x2x2 block known to be non-uniform (NIL = none known)
+    mutable std::vector<uint32_t> witness_;  // per brick: a voxel index known to differ from voxel 0 (0 = none known)
     std::vector<svx_albedo> colors_;
     std::vector<uint32_t> datas_;
     std::unordered_map<uint32_t, uint32_t> color_index_, data_index_;
