@@ -158,25 +158,32 @@ void svxo_make_pixel_ray(const svxo_camera* c, uint32_t w, uint32_t h, uint32_t 
     out[3] = r.direction.x; out[4] = r.direction.y; out[5] = r.direction.z;
 }
 
-// One frame of the caller loop of examples/cpu_render.rs:104-136. Pixel (x, y) is stored at image row h-1-y
-// (cpu_render.rs:106). Rows [row_begin, row_end) of the IMAGE are rendered (row = h-1-y), interleaved over
-// `threads` host threads. Outputs may be null. counters[4] (optional) accumulates
-// {sum node_iters, sum voxel_fetches, sum outer_iters, rays that entered the root cube}.
+// The caller loop of examples/cpu_render.rs:104-136 over an explicit list of IMAGE rows (row = h-1-y, cpu_render.rs:106).
+// Work is handed out in 64-pixel chunks from an atomic counter to `threads` host threads (0 = all hardware threads).
+// Outputs (any may be null) are full [h*w] planes; only the listed rows are written. counters[5] (optional) receives
+// {sum node_iters, sum voxel_fetches, sum outer_iters, rays that entered the root cube, would_panic}.
 // Returns wall-clock seconds spent in the pixel loop.
-double svxo_render(void* t, const svxo_camera* c, uint32_t w, uint32_t h, uint32_t row_begin, uint32_t row_end,
-                   uint32_t threads, uint32_t* hit_id, uint8_t* albedo, float* distance, float* normal,
-                   uint64_t* counters) {
+double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
+                        uint32_t threads, uint32_t* hit_id, uint8_t* albedo, float* distance, float* normal,
+                        uint64_t* counters) {
     Octree* tree = (Octree*)t;
     Camera cam{{c->origin[0], c->origin[1], c->origin[2]}, {c->direction[0], c->direction[1], c->direction[2]},
                c->glass_width, c->glass_height, c->glass_distance};
     if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
     std::atomic<uint64_t> acc[5];
     for (auto& a : acc) a = 0;
-    auto worker = [&](uint32_t tid) {
+    constexpr uint64_t CHUNK = 64;
+    const uint64_t total = (uint64_t)n_rows * w;
+    std::atomic<uint64_t> next{0};
+    auto worker = [&]() {
         uint64_t local[5] = {0, 0, 0, 0, 0};
-        for (uint32_t row = row_begin + tid; row < row_end; row += threads) {
-            const uint32_t y = h - 1 - row;
-            for (uint32_t x = 0; x < w; ++x) {
+        for (;;) {
+            const uint64_t begin = next.fetch_add(CHUNK);
+            if (begin >= total) break;
+            const uint64_t end = std::min(begin + CHUNK, total);
+            for (uint64_t k = begin; k < end; ++k) {
+                const uint32_t row = rows[k / w], x = (uint32_t)(k % w);
+                const uint32_t y = h - 1 - row;
                 const Ray ray = make_pixel_ray(cam, w, h, x, y);
                 RayStats st;
                 const Hit hit = tree->get_by_ray(ray, &st);
@@ -209,16 +216,26 @@ double svxo_render(void* t, const svxo_camera* c, uint32_t w, uint32_t h, uint32
     };
     const auto t0 = std::chrono::steady_clock::now();
     if (threads == 1) {
-        worker(0);
+        worker();
     } else {
         std::vector<std::thread> pool;
-        for (uint32_t i = 0; i < threads; ++i) pool.emplace_back(worker, i);
+        for (uint32_t i = 0; i < threads; ++i) pool.emplace_back(worker);
         for (auto& th : pool) th.join();
     }
     const auto t1 = std::chrono::steady_clock::now();
     if (counters)
         for (int k = 0; k < 5; ++k) counters[k] = acc[k];
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Rows [row_begin, row_end) of one frame
+double svxo_render(void* t, const svxo_camera* c, uint32_t w, uint32_t h, uint32_t row_begin, uint32_t row_end,
+                   uint32_t threads, uint32_t* hit_id, uint8_t* albedo, float* distance, float* normal,
+                   uint64_t* counters) {
+    std::vector<uint32_t> rows;
+    for (uint32_t r = row_begin; r < row_end; ++r) rows.push_back(r);
+    return svxo_render_rows(t, c, w, h, rows.data(), (uint32_t)rows.size(), threads, hit_id, albedo, distance, normal,
+                            counters);
 }
 
 uint32_t svxo_hardware_threads() { return std::max(1u, std::thread::hardware_concurrency()); }

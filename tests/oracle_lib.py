@@ -125,6 +125,8 @@ def lib() -> C.CDLL:
     L.svxo_make_pixel_ray.argtypes = [C.POINTER(Camera), u32, u32, u32, u32, f3]
     L.svxo_render.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, vp, vp, vp, vp, vp]
     L.svxo_render.restype = C.c_double
+    L.svxo_render_rows.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, u32, u32, vp, vp, vp, vp, vp]
+    L.svxo_render_rows.restype = C.c_double
     L.svxo_hardware_threads.restype = u32
     L.svxo_hash_region.argtypes = [f32, f32, f32, f32]
     L.svxo_hash_region.restype = u32
@@ -256,20 +258,24 @@ class OracleOctree:
         lib().svxo_octree_get_by_rays(self._h, rays.ctypes.data, rays.shape[0], out.ctypes.data)
         return out
 
-    def render(self, cam: Camera, w: int, h: int, threads: int = 0, rows=None, want_normal=False):
-        """Returns dict(hit_id u32[h,w], albedo u8[h,w,4], distance f32[h,w], seconds, counters)."""
+    def render(self, cam: Camera, w: int, h: int, threads: int = 0, rows=None, want_normal=False, row_list=None):
+        """Returns dict(hit_id u32[h,w], albedo u8[h,w,4], distance f32[h,w], seconds, counters).
+        rows=(r0, r1) renders a contiguous range, row_list an explicit list of image rows (others stay untouched)."""
         r0, r1 = rows if rows is not None else (0, h)
+        if row_list is None:
+            row_list = np.arange(r0, r1, dtype=np.uint32)
+        row_list = np.ascontiguousarray(row_list, dtype=np.uint32)
         hit_id = np.full((h, w), 0xFFFFFFFF, dtype=np.uint32)
         albedo = np.zeros((h, w, 4), dtype=np.uint8)
         dist = np.zeros((h, w), dtype=np.float32)
         normal = np.zeros((h, w, 3), dtype=np.float32) if want_normal else None
         counters = np.zeros(5, dtype=np.uint64)
-        secs = lib().svxo_render(
-            self._h, C.byref(cam), w, h, r0, r1, threads, hit_id.ctypes.data, albedo.ctypes.data, dist.ctypes.data,
-            normal.ctypes.data if want_normal else None, counters.ctypes.data,
+        secs = lib().svxo_render_rows(
+            self._h, C.byref(cam), w, h, row_list.ctypes.data, len(row_list), threads, hit_id.ctypes.data,
+            albedo.ctypes.data, dist.ctypes.data, normal.ctypes.data if want_normal else None, counters.ctypes.data,
         )
         return {
-            "hit_id": hit_id, "albedo": albedo, "distance": dist, "normal": normal, "seconds": secs,
+            "hit_id": hit_id, "albedo": albedo, "distance": dist, "normal": normal, "seconds": secs, "rows": row_list,
             "node_iters": int(counters[0]), "voxel_fetches": int(counters[1]), "outer_iters": int(counters[2]),
             "rays_in_root": int(counters[3]), "would_panic": int(counters[4]),
         }

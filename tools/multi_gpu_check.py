@@ -33,7 +33,8 @@ def main():
     rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    scene, cam, res, _ = bench.make_workload(args.workload)
+    scene, cams, res, _ = bench.make_workload(args.workload)
+    cam = cams[0]
     w, h = res
     tree = scenes.build_tree(scene, S.Octree)
     host = S.OctreeGPUHost(tree, local_rank)
