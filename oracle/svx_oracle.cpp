@@ -1416,6 +1416,7 @@ Hit Octree::get_by_ray(const Ray& ray, RayStats* st) const {
 
     while (target_octant != OOB_OCTANT) {
         if (st) st->outer_iters++;
+        const uint32_t node_iters_before = st ? st->node_iters : 0;
         current_node_key = 0;
         current_bounds = Cube{unit(0.0f), (float)octree_size};
         node_stack.push(0);
@@ -1499,6 +1500,7 @@ Hit Octree::get_by_ray(const Ray& ray, RayStats* st) const {
                 }
             }
         }
+        if (st && st->node_iters - node_iters_before == 1) st->crawl_iters++;
         // :548-562 restart from the root after nudging the point forward
         ray_current_point = ray_current_point + ray.direction * 0.1f;
         const float sz = (float)octree_size;

@@ -142,6 +142,7 @@ struct RayStats {
     uint32_t voxel_fetches = 0; // brick voxel reads in traverse_brick (raytracing_on_cpu.rs:218)
     uint32_t outer_iters = 0;   // iterations of `while target_octant != OOB_OCTANT` (raytracing_on_cpu.rs:352)
     uint32_t would_panic = 0;   // an index the Rust code would have bounds-panicked on
+    uint32_t crawl_iters = 0;   // outer iterations whose node loop ran once: the root failed its occupancy test and was popped
 };
 
 struct Hit {

@@ -44,7 +44,7 @@ struct svxo_hit {
     float impact_point[3];
     float normal[3];
     float distance;  // (impact_point - ray.origin).length(), vector.rs:75-77
-    uint32_t node_iters, voxel_fetches, outer_iters, would_panic;
+    uint32_t node_iters, voxel_fetches, outer_iters, would_panic, crawl_iters;
 };
 
 struct svxo_camera {
@@ -136,6 +136,7 @@ static void fill_hit(const Hit& h, const Ray& ray, const RayStats& st, svxo_hit*
     out->voxel_fetches = st.voxel_fetches;
     out->outer_iters = st.outer_iters;
     out->would_panic = st.would_panic;
+    out->crawl_iters = st.crawl_iters;
 }
 
 void svxo_octree_get_by_ray(void* t, const float origin[3], const float direction[3], svxo_hit* out) {
@@ -160,8 +161,8 @@ void svxo_make_pixel_ray(const svxo_camera* c, uint32_t w, uint32_t h, uint32_t 
 
 // The caller loop of examples/cpu_render.rs:104-136 over an explicit list of IMAGE rows (row = h-1-y, cpu_render.rs:106).
 // Work is handed out in 64-pixel chunks from an atomic counter to `threads` host threads (0 = all hardware threads).
-// Outputs (any may be null) are full [h*w] planes; only the listed rows are written. counters[5] (optional) receives
-// {sum node_iters, sum voxel_fetches, sum outer_iters, rays that entered the root cube, would_panic}.
+// Outputs (any may be null) are full [h*w] planes; only the listed rows are written. counters[6] (optional) receives
+// {sum node_iters, sum voxel_fetches, sum outer_iters, rays that entered the root cube, would_panic, sum crawl_iters}.
 // Returns wall-clock seconds spent in the pixel loop.
 double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
                         uint32_t threads, uint32_t* hit_id, uint8_t* albedo, float* distance, float* normal,
@@ -170,13 +171,13 @@ double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, c
     Camera cam{{c->origin[0], c->origin[1], c->origin[2]}, {c->direction[0], c->direction[1], c->direction[2]},
                c->glass_width, c->glass_height, c->glass_distance};
     if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
-    std::atomic<uint64_t> acc[5];
+    std::atomic<uint64_t> acc[6];
     for (auto& a : acc) a = 0;
     constexpr uint64_t CHUNK = 64;
     const uint64_t total = (uint64_t)n_rows * w;
     std::atomic<uint64_t> next{0};
     auto worker = [&]() {
-        uint64_t local[5] = {0, 0, 0, 0, 0};
+        uint64_t local[6] = {0, 0, 0, 0, 0, 0};
         for (;;) {
             const uint64_t begin = next.fetch_add(CHUNK);
             if (begin >= total) break;
@@ -210,9 +211,10 @@ double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, c
                 local[2] += st.outer_iters;
                 local[3] += st.outer_iters > 0 ? 1 : 0;
                 local[4] += st.would_panic;
+                local[5] += st.crawl_iters;
             }
         }
-        for (int k = 0; k < 5; ++k) acc[k] += local[k];
+        for (int k = 0; k < 6; ++k) acc[k] += local[k];
     };
     const auto t0 = std::chrono::steady_clock::now();
     if (threads == 1) {
@@ -224,7 +226,7 @@ double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, c
     }
     const auto t1 = std::chrono::steady_clock::now();
     if (counters)
-        for (int k = 0; k < 5; ++k) counters[k] = acc[k];
+        for (int k = 0; k < 6; ++k) counters[k] = acc[k];
     return std::chrono::duration<double>(t1 - t0).count();
 }
 

@@ -239,11 +239,11 @@ __device__ __forceinline__ bool root_entry(const RayConst& r, float tree_size, f
 // once per iteration until the 4x4x4 bitmap cell of p changes (the test depends on nothing else) or p leaves the cube.
 // A ray looking over a 1024^3 terrain repeats this ~10^4 times. The additions are f32 and must be reproduced bit for
 // bit, but they have a closed form: for x in one binade [2^e, 2^(e+1)), ulp u = 2^(e-23), x = X*u with integer X, and
-// c = t*u with real t, RN(x + c) = (X + rint(t))*u whenever t is not a tie (frac(t) != 0.5) and the sum stays in the
-// binade - independent of X. So n consecutive additions give (X + n*q)*u exactly, q = rint(t). crawl_limit() returns
+// c = t*u with real t, RN(x + c) = (X + rint(t))*u whenever t is not a tie (frac(t) != 0.5; ties are regular too once
+// X is even, see crawl_limit) and the sum stays in the binade - independent of X. So n consecutive additions give (X + n*q)*u exactly, q = rint(t). crawl_limit() returns
 // how many additions one axis can take before it would leave its binade or cross the next cell / cube boundary
-// (multiples of size/4); the minimum over the axes is applied in one step. Anything irregular (tie, denormal,
-// |c| >= 2^e) returns 0 and the caller falls back to stepping one addition at a time, which is always valid.
+// (multiples of size/4); the minimum over the axes is applied in one step. Anything irregular (a tie on an odd
+// mantissa, denormals, |c| >= 2^e) returns 0 and the caller falls back to one explicit addition, which is always valid.
 struct CrawlAxis {
     uint32_t limit;  // additions that are certainly "same binade, same cell, in bounds"
     int q;           // mantissa increment per addition
@@ -267,8 +267,11 @@ __device__ __forceinline__ CrawlAxis crawl_limit(float x, float c, float quarter
     const float to_ulps = __uint_as_float((277u - ef) << 23);  // 2^(23 - e), exact
     const float t = c * to_ulps;               // exact scaling
     if (!(fabsf(t) < 8388608.0f)) return a;    // |c| >= 2^e (or NaN): leaves the binade at once
+    // q = rint(t), ties to even. If t is an exact tie (frac = 0.5) the sum (X + t)*u rounds to the EVEN mantissa of
+    // X + floor(t), X + ceil(t). With X even that is X + q (q is the even candidate), and X stays even afterwards, so
+    // the recurrence is regular again; with X odd one explicit addition makes it even first.
     const int q = __float2int_rn(t);
-    if (fabsf(t - (float)q) == 0.5f) return a; // tie: rounding would depend on the parity of X
+    if (fabsf(t - (float)q) == 0.5f && (X & 1u)) return a;
     a.q = q;
     if (q == 0) {                              // x + c rounds back to x: this axis never moves
         a.limit = 0xFFFFFFFFu;

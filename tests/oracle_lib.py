@@ -45,6 +45,7 @@ class Hit(C.Structure):
         ("voxel_fetches", C.c_uint32),
         ("outer_iters", C.c_uint32),
         ("would_panic", C.c_uint32),
+        ("crawl_iters", C.c_uint32),
     ]
 
 
@@ -72,6 +73,7 @@ HIT_DTYPE = np.dtype(
         ("voxel_fetches", "<u4"),
         ("outer_iters", "<u4"),
         ("would_panic", "<u4"),
+        ("crawl_iters", "<u4"),
     ]
 )
 assert HIT_DTYPE.itemsize == C.sizeof(Hit)
@@ -269,7 +271,7 @@ class OracleOctree:
         albedo = np.zeros((h, w, 4), dtype=np.uint8)
         dist = np.zeros((h, w), dtype=np.float32)
         normal = np.zeros((h, w, 3), dtype=np.float32) if want_normal else None
-        counters = np.zeros(5, dtype=np.uint64)
+        counters = np.zeros(6, dtype=np.uint64)
         secs = lib().svxo_render_rows(
             self._h, C.byref(cam), w, h, row_list.ctypes.data, len(row_list), threads, hit_id.ctypes.data,
             albedo.ctypes.data, dist.ctypes.data, normal.ctypes.data if want_normal else None, counters.ctypes.data,
@@ -277,7 +279,7 @@ class OracleOctree:
         return {
             "hit_id": hit_id, "albedo": albedo, "distance": dist, "normal": normal, "seconds": secs, "rows": row_list,
             "node_iters": int(counters[0]), "voxel_fetches": int(counters[1]), "outer_iters": int(counters[2]),
-            "rays_in_root": int(counters[3]), "would_panic": int(counters[4]),
+            "rays_in_root": int(counters[3]), "would_panic": int(counters[4]), "crawl_iters": int(counters[5]),
         }
 
 
