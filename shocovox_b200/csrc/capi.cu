@@ -251,6 +251,54 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     for (uint32_t b = v->rank; b < bands; b += v->world) ++owned_bands;
     f->rows_local = owned_bands * v->band_rows;
     (void)rows;
+    // Conservative screen rectangle of the root cube. The looking glass is the parallelogram
+    //   origin + dir*glass_d + a*right + b*up,  a in [-w/2, w/2], b in [-h/2, h/2]   (right is perpendicular to up),
+    // pixel (x, y) looks through a = -w/2 + x*pw, b = -h/2 + y*ph. A cube corner P in front of the glass plane projects
+    // to the (a, b) where the line origin->P crosses that plane; rays that hit the (convex) cube pass through the convex
+    // hull of the 8 projections, hence through their bounding rectangle. Done in double, padded by 2 pixels; any corner
+    // not safely in front of the eye (camera inside or beside the cube) disables the cull.
+    f->cull_x0 = 0; f->cull_x1 = v->width - 1; f->cull_row0 = 0; f->cull_row1 = v->height - 1;
+    {
+        const double S = (double)v->host->dev.tree_size;
+        const double o[3] = {origin.x, origin.y, origin.z}, d[3] = {dir.x, dir.y, dir.z};
+        const double rt[3] = {right.x, right.y, right.z}, u[3] = {up.x, up.y, up.z};
+        const double n[3] = {rt[1] * u[2] - rt[2] * u[1], rt[2] * u[0] - rt[0] * u[2], rt[0] * u[1] - rt[1] * u[0]};
+        const double dn = d[0] * n[0] + d[1] * n[1] + d[2] * n[2];
+        const double rr = rt[0] * rt[0] + rt[1] * rt[1] + rt[2] * rt[2];
+        double ax0 = 1e300, ax1 = -1e300, by0 = 1e300, by1 = -1e300;
+        bool ok = std::isfinite(dn) && std::fabs(dn) > 1e-9 && glass_d > 0.0f && rr > 1e-12;
+        for (int c = 0; c < 8 && ok; ++c) {
+            const double P[3] = {(c & 1) ? S : 0.0, (c & 2) ? S : 0.0, (c & 4) ? S : 0.0};
+            const double wv[3] = {P[0] - o[0], P[1] - o[1], P[2] - o[2]};
+            const double wn = wv[0] * n[0] + wv[1] * n[1] + wv[2] * n[2];
+            const double s = (double)glass_d * dn / wn;  // origin + s*w lies in the glass plane
+            const double wl = std::sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
+            if (!(wn * dn > 1e-6 * wl * std::fabs(dn)) || !std::isfinite(s) || s <= 0.0) {
+                ok = false;  // corner behind / beside the eye plane
+                break;
+            }
+            const double q[3] = {s * wv[0] - glass_d * d[0], s * wv[1] - glass_d * d[1], s * wv[2] - glass_d * d[2]};
+            const double a = (q[0] * rt[0] + q[1] * rt[1] + q[2] * rt[2]) / rr;
+            const double b = q[0] * u[0] + q[1] * u[1] + q[2] * u[2];
+            ax0 = std::min(ax0, a); ax1 = std::max(ax1, a);
+            by0 = std::min(by0, b); by1 = std::max(by1, b);
+        }
+        if (ok) {
+            const double pw = (double)f->pixel_width, ph = (double)f->pixel_height;
+            const double x0 = std::floor((ax0 + glass_w / 2.0) / pw) - 2.0, x1 = std::ceil((ax1 + glass_w / 2.0) / pw) + 2.0;
+            const double y0 = std::floor((by0 + glass_h / 2.0) / ph) - 2.0, y1 = std::ceil((by1 + glass_h / 2.0) / ph) + 2.0;
+            const double W = v->width, H = v->height;
+            if (x1 < 0 || y1 < 0 || x0 > W - 1 || y0 > H - 1) {  // nothing of the cube on screen
+                f->cull_x0 = 1; f->cull_x1 = 0; f->cull_row0 = 1; f->cull_row1 = 0;
+            } else {
+                f->cull_x0 = (uint32_t)std::max(0.0, x0);
+                f->cull_x1 = (uint32_t)std::min(W - 1, x1);
+                // pixel row y lands in image row H-1-y
+                f->cull_row0 = (uint32_t)(H - 1 - std::min(H - 1, y1));
+                f->cull_row1 = (uint32_t)(H - 1 - std::max(0.0, y0));
+            }
+        }
+    }
     f->compact = v->compact;
     f->hit_id = v->use_peer ? (uint32_t*)v->peer_base[0] : v->d_hit_id;
     f->albedo = v->use_peer ? (uint32_t*)v->peer_base[1] : v->d_albedo;

@@ -47,11 +47,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(c
     const uint32_t y = f.height - 1u - row;  // pixel (x, y) lands in image row h-1-y (cpu_render.rs:106)
     const size_t i = (size_t)(f.compact ? lr : row) * f.width + x;
 
+    uint32_t hit_id = NIL, rgba = 0u;
+    float dist = 0.0f;
+    // 0) pixels outside the projected bounding rectangle of the root cube are sky (host-computed, conservative)
+    if (x < f.cull_x0 || x > f.cull_x1 || row < f.cull_row0 || row > f.cull_row1) {
+        f.hit_id[i] = NIL;
+        f.albedo[i] = 0u;
+        f.distance[i] = 0.0f;
+        return;
+    }
     float vx, vy, vz;
     glass_vector(f, x, y, vx, vy, vz);
     const float tree_size = (float)tree.tree_size;
-    uint32_t hit_id = NIL, rgba = 0u;
-    float dist = 0.0f;
     // 1) cheap conservative rejection with an approximately normalised direction (see certain_root_miss)
     const float rl = rsqrtf((vx * vx) + (vy * vy) + (vz * vz));
     if (!certain_root_miss(f.ox, f.oy, f.oz, vx * rl, vy * rl, vz * rl, tree_size)) {

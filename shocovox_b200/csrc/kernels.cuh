@@ -19,6 +19,9 @@ struct FrameParams {
     // sharding: this launch renders image rows r with (r / band_rows) % world == rank
     uint32_t rank, world, band_shift;  // bands of 2^band_shift rows
     uint32_t rows_local;   // number of image rows this shard owns
+    // pixels outside [cull_x0, cull_x1] x [cull_row0, cull_row1] (image coordinates, inclusive) certainly miss the root
+    // cube: a conservative screen-space bound of the cube's projection computed on the host (capi.cu)
+    uint32_t cull_x0, cull_x1, cull_row0, cull_row1;
     uint32_t compact;      // 1: store shard-local row lr at output row lr (band-major compact buffer for gathers)
     uint32_t* hit_id;      // [h*w]
     uint32_t* albedo;      // [h*w]

@@ -145,11 +145,15 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     const float ux = r.negx ? -unit : unit, uy = r.negy ? -unit : unit, uz = r.negz ? -unit : unit;
     const uint32_t* bits = t.brick_bits + (size_t)brick * t.bit_words;
     const uint32_t sh = t.brick_shift;
+    // flat_projection(ix, iy, iz) kept incrementally, like the reference's current_flat_index (:205-207)
+    int flat = ix + (iy << sh) + (iz << (2 * sh));
+    const int fsx = r.isx, fsy = r.isy * (1 << sh), fsz = r.isz * (1 << (2 * sh));
     int word_index = -1;
     uint32_t word = 0u;
     for (;;) {
-        if (((ix | iy | iz) < 0) || ix >= dim || iy >= dim || iz >= dim) return -1;
-        const int flat = ix + (iy << sh) + (iz << (2 * sh));
+        // index out of the brick on any axis: dim is a power of two, so OR-ing the three indices keeps a set sign bit
+        // (negative) or a set bit >= dim (one index reached dim) visible in a single unsigned compare
+        if ((uint32_t)(ix | iy | iz) >= (uint32_t)dim) return -1;
         if ((flat >> 5) != word_index) {
             word_index = flat >> 5;
             word = __ldg(bits + word_index);
@@ -160,9 +164,9 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
         }
         bool sx, sy, sz;
         dda_step(r, px, py, pz, cx, cy, cz, unit, sx, sy, sz);
-        if (sx) { cx = cx + ux; ix += r.isx; }
-        if (sy) { cy = cy + uy; iy += r.isy; }
-        if (sz) { cz = cz + uz; iz += r.isz; }
+        if (sx) { cx = cx + ux; ix += r.isx; flat += fsx; }
+        if (sy) { cy = cy + uy; iy += r.isy; flat += fsy; }
+        if (sz) { cz = cz + uz; iz += r.isz; flat += fsz; }
     }
 }
 

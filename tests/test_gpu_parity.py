@@ -300,3 +300,36 @@ def test_crawl_fast_forward_is_exact_on_a_large_tree():
     o = otree.get_by_rays(rays)
     assert np.array_equal(g["hit"], o["hit"]) and np.array_equal(g["palette_value"], o["palette_value"])
     assert np.array_equal(bits(g["impact_point"]), bits(o["impact_point"]))
+
+
+def test_random_cameras_exercise_cull_rectangle_and_prefilter():
+    """Cameras at random places around (and inside, and hugging the faces of) the tree, random glass sizes and both
+    glass modes: the host-side cull rectangle and the approximate root-miss prefilter must never change a pixel."""
+    scene = scenes.cpu_render_scene()
+    tree, otree = both_trees(scene)
+    host = S.OctreeGPUHost(tree)
+    rng = np.random.default_rng(2024)
+    view = host.create_new_view(1, viewport(scenes.cpu_render_camera()), (96, 64))
+    hits = 0
+    for k in range(60):
+        kind = k % 4
+        if kind == 0:    # far away, cube small on screen
+            origin = rng.uniform(-400, 400, 3)
+        elif kind == 1:  # close to a face, cube partly off screen
+            origin = rng.uniform(-20, 84, 3)
+            origin[rng.integers(0, 3)] = rng.choice([-3.0, 67.0])
+        elif kind == 2:  # inside the tree
+            origin = rng.uniform(1, 63, 3)
+        else:            # looking away / grazing
+            origin = rng.uniform(-100, 164, 3)
+        target = rng.uniform(-16, 80, 3) if kind != 3 else origin + rng.normal(size=3) * 50
+        d = S.normalized((target - origin).astype(np.float32))
+        cam = scenes.CameraSpec(tuple(float(v) for v in origin.astype(np.float32)), tuple(float(v) for v in d),
+                                (float(rng.uniform(1, 8)), float(rng.uniform(1, 8)), float(rng.uniform(2, 300))),
+                                float(rng.uniform(0.5, 6)), glass_at_frustum_z=bool(k % 2))
+        view.set_viewport(viewport(cam))
+        view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z if cam.glass_at_frustum_z else S.GLASS_AT_FOV)
+        ora = otree.render(oracle_camera(cam), 96, 64)
+        assert_frames_equal(view.render_to_host(), ora)
+        hits += int((ora["hit_id"] != S.MISS).sum())
+    assert hits > 20000
