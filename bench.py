@@ -237,6 +237,17 @@ def main() -> int:
         return 1
     dist = torch = None
     if world > 1:
+        # keep this rank's host threads and first-touch pinned pages on the CPU cores NVML reports as local to its GPU
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank), (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+            if cpus:
+                os.sched_setaffinity(0, cpus & set(range(os.cpu_count())) or cpus)
+        except Exception:
+            pass
         import torch
         import torch.distributed as dist
 
