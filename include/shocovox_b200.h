@@ -125,6 +125,9 @@ SVX_API int32_t svx_octree_insert_at_lod(svx_octree* tree, uint32_t x, uint32_t 
                                          const svx_entry* entry);
 /* Octree::update, src/octree/update/insert.rs:79-88 */
 SVX_API int32_t svx_octree_update(svx_octree* tree, uint32_t x, uint32_t y, uint32_t z, const svx_entry* entry);
+/* Octree::clear / clear_at_lod, src/octree/update/clear.rs:48-78 */
+SVX_API int32_t svx_octree_clear(svx_octree* tree, uint32_t x, uint32_t y, uint32_t z);
+SVX_API int32_t svx_octree_clear_at_lod(svx_octree* tree, uint32_t x, uint32_t y, uint32_t z, uint32_t clear_size);
 /* The per-voxel insert loop every example runs (examples/cpu_render.rs:21-43): n Visual inserts in array order.
  * xyz is [n][3], rgba is [n][4], lod (optional) holds an insert_at_lod size per voxel (<= 1 means insert). */
 SVX_API int32_t svx_octree_insert_batch(svx_octree* tree, const uint32_t* xyz, const uint8_t* rgba, const uint32_t* lod,

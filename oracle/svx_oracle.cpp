@@ -1240,6 +1240,255 @@ Status Octree::insert_at_lod_internal(bool overwrite_if_empty, V3u position_u, u
 }
 
 // ---------------------------------------------------------------------------------------------
+// octree/update/clear.rs and the emptiness helpers it needs (node.rs:107-241, :470-515, detail.rs:181-316)
+// ---------------------------------------------------------------------------------------------
+// BrickData::is_empty_throughout, node.rs:107-178
+bool Octree::brick_is_empty_throughout(const Brick& b, uint8_t octant) const {
+    const size_t d = brick_dim;
+    switch (b.kind) {
+        case BrickKind::Empty: return true;
+        case BrickKind::Solid: return pix_points_to_empty(b.solid);
+        case BrickKind::Parted: {
+            if (1 == d) return pix_points_to_empty(b.data[0]);
+            const V3s off = to_usize(luts().octant_offset[octant]);
+            if (2 == d) return pix_points_to_empty(b.data[flat_projection(off.x, off.y, off.z, 2)]);
+            const size_t extent = d / 2;
+            for (size_t x = off.x * extent; x < off.x * extent + extent; ++x)
+                for (size_t y = off.y * extent; y < off.y * extent + extent; ++y)
+                    for (size_t z = off.z * extent; z < off.z * extent + extent; ++z)
+                        if (!pix_points_to_empty(b.data[flat_projection(x, y, z, d)])) return false;
+            return true;
+        }
+    }
+    return true;
+}
+
+// BrickData::is_part_empty_throughout, node.rs:184-241
+bool Octree::brick_is_part_empty_throughout(const Brick& b, uint8_t part_octant, uint8_t target_octant) const {
+    const size_t d = brick_dim;
+    switch (b.kind) {
+        case BrickKind::Empty: return true;
+        case BrickKind::Solid: return pix_points_to_empty(b.solid);
+        case BrickKind::Parted: {
+            if (1 == d) return pix_points_to_empty(b.data[0]);
+            if (2 == d) {
+                const V3s off = to_usize(luts().octant_offset[part_octant]);
+                return pix_points_to_empty(b.data[flat_projection(off.x, off.y, off.z, 2)]);
+            }
+            const float outer_extent = (float)d / 2.0f, inner_extent = (float)d / 4.0f;
+            const V3s off =
+                to_usize(luts().octant_offset[part_octant] * outer_extent + luts().octant_offset[target_octant] * inner_extent);
+            const size_t n = f2usize(inner_extent);
+            for (size_t x = 0; x < n; ++x)
+                for (size_t y = 0; y < n; ++y)
+                    for (size_t z = 0; z < n; ++z)
+                        if (!pix_points_to_empty(b.data[flat_projection(off.x + x, off.y + y, off.z + z, d)])) return false;
+            return true;
+        }
+    }
+    return true;
+}
+
+// NodeContent::is_empty, node.rs:470-515
+bool Octree::node_is_empty(const Node& n) const {
+    auto brick_empty = [&](const Brick& b) {
+        if (b.kind == BrickKind::Empty) return true;
+        if (b.kind == BrickKind::Solid) return pix_points_to_empty(b.solid);
+        for (uint32_t v : b.data)
+            if (!pix_points_to_empty(v)) return false;
+        return true;
+    };
+    switch (n.kind) {
+        case NodeKind::UniformLeaf: return brick_empty(n.ubrick);
+        case NodeKind::Leaf:
+            for (int o = 0; o < 8; ++o)
+                if (!brick_empty(n.bricks[o])) return false;
+            return true;
+        case NodeKind::Internal: return false;
+        case NodeKind::Nothing: return true;
+    }
+    return true;
+}
+
+// node_empty_at, detail.rs:255-316
+bool Octree::node_empty_at(size_t node_key, uint8_t target_octant) const {
+    const Node& n = nodes.item[node_key];
+    auto brick_empty = [&](const Brick& b) {
+        if (b.kind == BrickKind::Empty) return true;
+        if (b.kind == BrickKind::Solid) return pix_points_to_empty(b.solid);
+        const uint32_t* h = get_homogeneous_data(b);
+        return h ? pix_points_to_empty(*h) : false;
+    };
+    switch (n.kind) {
+        case NodeKind::Nothing: return true;
+        case NodeKind::Leaf: return brick_empty(n.bricks[target_octant]);
+        case NodeKind::UniformLeaf: return brick_empty(n.ubrick);
+        case NodeKind::Internal:
+            for (uint8_t child_octant = 0; child_octant < 8; ++child_octant) {
+                const size_t child_key = child_of(node_children[node_key], target_octant);
+                if (nodes.key_is_valid(child_key) && !node_empty_at(child_key, child_octant)) return false;
+            }
+            return true;
+    }
+    return true;
+}
+
+// should_bitmap_be_empty_at_bitmap_index -> ..._at_octants, detail.rs:181-252
+bool Octree::should_bitmap_be_empty_at_bitmap_index(size_t node_key, size_t x, size_t y, size_t z) const {
+    const V3f position = V3f{0.5f, 0.5f, 0.5f} + V3f{(float)x, (float)y, (float)z};
+    const uint8_t target_octant = hash_region(position, (float)BITMAP_DIMENSION / 2.0f);
+    const uint8_t target_octant_for_child =
+        hash_region(position - (luts().octant_offset[target_octant] * (float)BITMAP_DIMENSION / 2.0f), (float)BITMAP_DIMENSION / 4.0f);
+    const Node& n = nodes.item[node_key];
+    switch (n.kind) {
+        case NodeKind::Nothing: return true;
+        case NodeKind::Internal: {
+            const size_t child_key = child_of(node_children[node_key], target_octant);
+            return nodes.key_is_valid(child_key) ? node_empty_at(child_key, target_octant_for_child) : true;
+        }
+        case NodeKind::UniformLeaf: return brick_is_part_empty_throughout(n.ubrick, target_octant, target_octant_for_child);
+        case NodeKind::Leaf: return brick_is_empty_throughout(n.bricks[target_octant], target_octant_for_child);
+    }
+    return true;
+}
+
+// clear_at_lod, clear.rs:55-348
+Status Octree::clear_at_lod(V3u position_u, uint32_t clear_size) {
+    const Cube root_bounds{unit(0.0f), (float)octree_size};
+    const V3f position = to_f32(position_u);
+    if (!bound_contains(root_bounds, position)) return E_INVALID_POSITION;
+
+    struct StackItem {
+        uint32_t key;
+        Cube bounds;
+    };
+    std::vector<StackItem> node_stack;
+    node_stack.push_back({0u, root_bounds});
+    size_t actual_update_size = 0;
+    const Luts& l = luts();
+    auto to_u32 = [](float v) { return (uint32_t)f2usize(std::round(v)); };  // From<V3c<f32>> for V3c<u32>, vector.rs:326-336
+
+    for (;;) {
+        const size_t current_node_key = node_stack.back().key;
+        const Cube current_bounds = node_stack.back().bounds;
+        const uint8_t target_child_octant = child_octant_for(current_bounds, position);
+        const Cube target_bounds{
+            current_bounds.min_position + l.octant_offset[target_child_octant] * current_bounds.size / 2.0f,
+            current_bounds.size / 2.0f};
+        const size_t target_child_key = child_of(node_children[current_node_key], target_child_octant);
+        // `*position <= target_bounds.min_position.into()` : lexicographic compare of V3c<u32>
+        const uint32_t mx = to_u32(target_bounds.min_position.x), my = to_u32(target_bounds.min_position.y),
+                       mz = to_u32(target_bounds.min_position.z);
+        const bool pos_le_min = position_u.x != mx ? position_u.x < mx : (position_u.y != my ? position_u.y < my : position_u.z <= mz);
+        if (clear_size > 1 && target_bounds.size <= (float)clear_size && pos_le_min && nodes.key_is_valid(target_child_key)) {
+            deallocate_children_of(target_child_key);
+            nodes.item[target_child_key] = Node();
+            node_children[target_child_key] = Children();
+            actual_update_size = f2usize(target_bounds.size);
+            node_stack.push_back({(uint32_t)child_of(node_children[current_node_key], target_child_octant), target_bounds});
+            break;
+        }
+
+        if (target_bounds.size > (float)std::max(clear_size, brick_dim) || nodes.key_is_valid(target_child_key)) {
+            if (nodes.key_is_valid(target_child_key)) {
+                node_stack.push_back({(uint32_t)child_of(node_children[current_node_key], target_child_octant), target_bounds});
+            } else {
+                const Node& cn = nodes.item[current_node_key];
+                if (cn.kind == NodeKind::Leaf || cn.kind == NodeKind::UniformLeaf) {
+                    const Brick& b = cn.kind == NodeKind::UniformLeaf ? cn.ubrick : cn.bricks[target_child_octant];
+                    bool target_match;
+                    if (b.kind == BrickKind::Empty) {
+                        target_match = true;
+                    } else if (b.kind == BrickKind::Solid) {
+                        target_match = pix_points_to_empty(b.solid);
+                    } else {
+                        // (sic) indexes the brick with position - current_bounds.min, unscaled (clear.rs:139-146, :164-171);
+                        // the reference bounds-panics when that leaves the brick
+                        const size_t ix = position_u.x - to_u32(current_bounds.min_position.x),
+                                     iy = position_u.y - to_u32(current_bounds.min_position.y),
+                                     iz = position_u.z - to_u32(current_bounds.min_position.z);
+                        const size_t fi = flat_projection(ix, iy, iz, brick_dim);
+                        if (fi >= b.data.size()) return E_INVALID_STRUCTURE;
+                        target_match = pix_points_to_empty(b.data[fi]);
+                    }
+                    if (target_match || node_is_empty(cn)) break;
+                    subdivide_leaf_to_nodes(current_node_key, target_child_octant);
+                    node_stack.push_back({(uint32_t)child_of(node_children[current_node_key], target_child_octant), target_bounds});
+                } else {
+                    break;  // no child at the requested position: nothing to clear
+                }
+            }
+        } else {
+            actual_update_size = leaf_update(true, current_node_key, current_bounds, target_bounds, target_child_octant, position_u,
+                                             clear_size, EMPTY_MARKER_U32);
+            break;
+        }
+    }
+
+    // post-processing (clear.rs:224-346)
+    bool have_removed = false;
+    StackItem removed{0, Cube{}};
+    {
+        const StackItem last = node_stack.back();
+        node_stack.pop_back();
+        if (f2usize(last.bounds.size) <= actual_update_size) {
+            have_removed = true;
+            removed = last;
+        }
+    }
+    bool simplifyable = auto_simplify;
+    for (size_t i = node_stack.size(); i-- > 0;) {
+        const size_t node_key = node_stack[i].key;
+        const Cube node_bounds = node_stack[i].bounds;
+        if (have_removed) {
+            const uint8_t child_octant = hash_region(
+                (removed.bounds.min_position - node_bounds.min_position) + unit(removed.bounds.size / 2.0f), node_bounds.size / 2.0f);
+            Children& c = node_children[node_key];
+            if (c.kind == ChildrenKind::Children) {  // NodeChildren::clear, node.rs:75-83
+                c.child[child_octant] = EMPTY_MARKER_U32;
+                bool all_empty = true;
+                for (int k = 0; k < 8; ++k) all_empty &= (c.child[k] == EMPTY_MARKER_U32);
+                if (all_empty) c = Children();
+            }
+            nodes.free_key(removed.key);
+            have_removed = false;
+        }
+        const uint64_t previous_occupied_bits = stored_occupied_bits(node_key);
+        uint64_t new_occupied_bits = node_children[node_key].kind == ChildrenKind::NoChildren ? 0 : previous_occupied_bits;
+        if (f2usize(node_bounds.size) == actual_update_size) {
+            new_occupied_bits = 0;
+        } else {
+            const V3s start = matrix_index_for(node_bounds, position_u, (uint32_t)BITMAP_DIMENSION);
+            const size_t n = f2usize(std::ceil((float)actual_update_size * (float)BITMAP_DIMENSION / node_bounds.size));
+            for (size_t x = start.x; x < std::min(start.x + n, BITMAP_DIMENSION); ++x)
+                for (size_t y = start.y; y < std::min(start.y + n, BITMAP_DIMENSION); ++y)
+                    for (size_t z = start.z; z < std::min(start.z + n, BITMAP_DIMENSION); ++z)
+                        if (should_bitmap_be_empty_at_bitmap_index(node_key, x, y, z))
+                            set_occupancy_in_bitmap_64bits(x, y, z, 1, BITMAP_DIMENSION, false, &new_occupied_bits);
+        }
+        if (0 != new_occupied_bits && node_children[node_key].kind == ChildrenKind::Children) {
+            Node in;
+            in.kind = NodeKind::Internal;
+            in.occupied_bits = new_occupied_bits;
+            nodes.item[node_key] = std::move(in);
+        } else {
+            deallocate_children_of(node_key);
+            node_children[node_key] = Children();
+            have_removed = true;
+            removed = node_stack[i];
+            nodes.item[node_key] = Node();
+        }
+        if (0 == new_occupied_bits)
+            node_children[node_key] = Children();
+        else
+            store_occupied_bits(node_key, new_occupied_bits);
+        if (simplifyable) simplifyable = simplify(node_key);
+        if (previous_occupied_bits == new_occupied_bits) break;
+    }
+    return OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // structure hash: key-order independent digest of everything get_by_ray can observe
 // ---------------------------------------------------------------------------------------------
 static inline uint64_t mix64(uint64_t h, uint64_t v) {

@@ -161,6 +161,8 @@ class Octree {
     Status insert(V3u position, const Entry& e) { return insert_at_lod_internal(true, position, 1, e); }
     Status insert_at_lod(V3u position, uint32_t size, const Entry& e) { return insert_at_lod_internal(true, position, size, e); }
     Status update(V3u position, const Entry& e) { return insert_at_lod_internal(false, position, 1, e); }
+    Status clear(V3u position) { return clear_at_lod(position, 1); }   // src/octree/update/clear.rs:48-50
+    Status clear_at_lod(V3u position, uint32_t clear_size);           // src/octree/update/clear.rs:55-348
     Entry get(V3u position) const;
     uint32_t get_size() const { return octree_size; }
     Hit get_by_ray(const Ray& ray, RayStats* stats = nullptr) const;
@@ -197,6 +199,11 @@ class Octree {
     uint64_t calculate_occupied_bits(const Brick& b) const;
     bool brick_simplify(Brick& b) const;
     bool node_is_all(const Node& n, uint32_t data) const;
+    bool node_is_empty(const Node& n) const;
+    bool node_empty_at(size_t node_key, uint8_t target_octant) const;
+    bool should_bitmap_be_empty_at_bitmap_index(size_t node_key, size_t x, size_t y, size_t z) const;
+    bool brick_is_empty_throughout(const Brick& b, uint8_t octant) const;
+    bool brick_is_part_empty_throughout(const Brick& b, uint8_t part_octant, uint8_t target_octant) const;
     uint64_t hash_node(size_t key) const;
 
     // ray helpers

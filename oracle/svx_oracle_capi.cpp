@@ -3,7 +3,9 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <thread>
 
 #include "svx_oracle.hpp"
@@ -88,6 +90,10 @@ int32_t svxo_octree_insert_at_lod(void* t, uint32_t x, uint32_t y, uint32_t z, u
 int32_t svxo_octree_update(void* t, uint32_t x, uint32_t y, uint32_t z, const svxo_entry* e) {
     return ((Octree*)t)->update(V3u{x, y, z}, to_entry(e));
 }
+int32_t svxo_octree_clear(void* t, uint32_t x, uint32_t y, uint32_t z) { return ((Octree*)t)->clear(V3u{x, y, z}); }
+int32_t svxo_octree_clear_at_lod(void* t, uint32_t x, uint32_t y, uint32_t z, uint32_t size) {
+    return ((Octree*)t)->clear_at_lod(V3u{x, y, z}, size);
+}
 // Visual inserts in bulk: positions xyz[n][3], colours rgba[n][4]; optional per-voxel lod sizes (nullptr = 1)
 int32_t svxo_octree_insert_batch(void* t, const uint32_t* xyz, const uint8_t* rgba, const uint32_t* lod, uint64_t n) {
     Octree* tree = (Octree*)t;
@@ -112,6 +118,42 @@ void svxo_octree_get_sweep(void* t, uint32_t x0, uint32_t y0, uint32_t z0, uint3
     for (uint32_t x = x0; x < x0 + nx; ++x)
         for (uint32_t y = y0; y < y0 + ny; ++y)
             for (uint32_t z = z0; z < z0 + nz; ++z) from_entry(tree->get(V3u{x, y, z}), &out[i++]);
+}
+// debug aid for tests: node kinds, occupancy bits and brick kinds on the path from the root to a position
+int32_t svxo_octree_describe_path(void* tp, uint32_t x, uint32_t y, uint32_t z, char* out, uint32_t cap) {
+    Octree* t = (Octree*)tp;
+    std::string s;
+    size_t key = 0;
+    float bx = 0, by = 0, bz = 0, size = (float)t->octree_size;
+    for (int depth = 0; depth < 40; ++depth) {
+        const Node& n = t->nodes.item[key];
+        const Children& c = t->node_children[key];
+        char buf[256];
+        snprintf(buf, sizeof buf, "[key %zu size %g kind %d link %d ocbits %016llx]", key, size, (int)n.kind, (int)c.kind,
+                 (unsigned long long)t->stored_occupied_bits(key));
+        s += buf;
+        const float half = size / 2;
+        const int oct = ((float)x - bx >= half) + 2 * ((float)z - bz >= half) + 4 * ((float)y - by >= half);
+        if (n.kind == NodeKind::Leaf) {
+            s += " bricks:";
+            for (int o = 0; o < 8; ++o) s += " " + std::to_string((int)n.bricks[o].kind);
+            s += " target " + std::to_string(oct);
+            break;
+        }
+        if (n.kind == NodeKind::UniformLeaf) {
+            s += " ubrick " + std::to_string((int)n.ubrick.kind);
+            break;
+        }
+        if (n.kind != NodeKind::Internal || c.kind != ChildrenKind::Children) break;
+        const uint32_t ck = c.child[oct];
+        s += " -> oct " + std::to_string(oct) + " child " + std::to_string(ck) + (t->nodes.key_is_valid(ck) ? "" : " (invalid)") + "\n";
+        if (!t->nodes.key_is_valid(ck)) break;
+        key = ck;
+        bx += (oct & 1) * half; by += ((oct >> 2) & 1) * half; bz += ((oct >> 1) & 1) * half;
+        size = half;
+    }
+    snprintf(out, cap, "%s", s.c_str());
+    return (int32_t)s.size();
 }
 uint64_t svxo_octree_structure_hash(void* t) { return ((Octree*)t)->structure_hash(); }
 uint64_t svxo_octree_node_count(void* t) { return ((Octree*)t)->nodes.len(); }

@@ -127,7 +127,7 @@ assert VIEWPORT_DTYPE.itemsize == C.sizeof(_Viewport)
 EXPORTS = [
     "svx_version", "svx_last_error_message", "svx_cuda_device_count",
     "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
-    "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
+    "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
     "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count",
     "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
@@ -166,6 +166,8 @@ def lib() -> C.CDLL:
     L.svx_octree_insert.argtypes = [vp, u32, u32, u32, C.POINTER(_Entry)]
     L.svx_octree_insert_at_lod.argtypes = [vp, u32, u32, u32, u32, C.POINTER(_Entry)]
     L.svx_octree_update.argtypes = [vp, u32, u32, u32, C.POINTER(_Entry)]
+    L.svx_octree_clear.argtypes = [vp, u32, u32, u32]
+    L.svx_octree_clear_at_lod.argtypes = [vp, u32, u32, u32, u32]
     L.svx_octree_insert_batch.argtypes = [vp, vp, vp, vp, u64]
     L.svx_octree_get.argtypes = [vp, u32, u32, u32, C.POINTER(_Entry)]
     L.svx_octree_get_sweep.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp]
@@ -373,6 +375,12 @@ class Octree:
 
     def update(self, position, albedo=None, data=None):
         _check(lib().svx_octree_update(self._h, *[int(c) for c in position], C.byref(entry(albedo, data)._c())))
+
+    def clear(self, position):
+        _check(lib().svx_octree_clear(self._h, *[int(c) for c in position]))
+
+    def clear_at_lod(self, position, clear_size: int):
+        _check(lib().svx_octree_clear_at_lod(self._h, *[int(c) for c in position], int(clear_size)))
 
     def insert_batch(self, xyz: np.ndarray, rgba: np.ndarray, lod: Optional[np.ndarray] = None):
         xyz = np.ascontiguousarray(xyz, dtype=np.uint32)

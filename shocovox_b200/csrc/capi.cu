@@ -379,6 +379,14 @@ int32_t svx_octree_update(svx_octree* t, uint32_t x, uint32_t y, uint32_t z, con
     if (!t || !e) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     return t->tree->insert_at_lod_internal(false, x, y, z, 1, *e);
 }
+int32_t svx_octree_clear(svx_octree* t, uint32_t x, uint32_t y, uint32_t z) {
+    if (!t) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    return t->tree->clear_at_lod(x, y, z, 1);
+}
+int32_t svx_octree_clear_at_lod(svx_octree* t, uint32_t x, uint32_t y, uint32_t z, uint32_t clear_size) {
+    if (!t) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    return t->tree->clear_at_lod(x, y, z, clear_size);
+}
 int32_t svx_octree_insert_batch(svx_octree* t, const uint32_t* xyz, const uint8_t* rgba, const uint32_t* lod, uint64_t n) {
     if (!t || (n && (!xyz || !rgba))) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     for (uint64_t i = 0; i < n; ++i) {

@@ -884,6 +884,232 @@ int32_t HostOctree::insert_at_lod_internal(bool overwrite, uint32_t x, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// clear / clear_at_lod, src/octree/update/clear.rs:48-348, with the emptiness predicates of node.rs / detail.rs
+// ------------------------------------------------------------------------------------------------------------
+// BrickData::is_empty_throughout, node.rs:107-178: is one octant of the brick empty?
+bool HostOctree::brick_octant_empty(const BrickRef& b, uint8_t octant) const {
+    if (b.kind == BK_EMPTY) return true;
+    if (b.kind == BK_SOLID) return value_is_empty(b.value);
+    const uint32_t* d = brick_data(b.value);
+    if (dim_ == 1) return value_is_empty(d[0]);
+    const size_t ox = octant & 1, oy = (octant >> 2) & 1, oz = (octant >> 1) & 1;
+    if (dim_ == 2) return value_is_empty(d[flat(ox, oy, oz, 2)]);
+    const size_t e = dim_ / 2;
+    for (size_t x = ox * e; x < ox * e + e; ++x)
+        for (size_t y = oy * e; y < oy * e + e; ++y)
+            for (size_t z = oz * e; z < oz * e + e; ++z)
+                if (!value_is_empty(d[flat(x, y, z, dim_)])) return false;
+    return true;
+}
+
+// BrickData::is_part_empty_throughout, node.rs:184-241: is sub-octant `target` of octant `part` empty?
+bool HostOctree::brick_part_empty(const BrickRef& b, uint8_t part, uint8_t target) const {
+    if (b.kind == BK_EMPTY) return true;
+    if (b.kind == BK_SOLID) return value_is_empty(b.value);
+    const uint32_t* d = brick_data(b.value);
+    if (dim_ == 1) return value_is_empty(d[0]);
+    if (dim_ == 2) return value_is_empty(d[flat(part & 1, (part >> 2) & 1, (part >> 1) & 1, 2)]);
+    const float outer = (float)dim_ / 2.0f, inner = (float)dim_ / 4.0f;
+    const size_t bx = round_index(off_x(part) * outer + off_x(target) * inner), by = round_index(off_y(part) * outer + off_y(target) * inner),
+                 bz = round_index(off_z(part) * outer + off_z(target) * inner);
+    const size_t n = to_index(inner);
+    for (size_t x = 0; x < n; ++x)
+        for (size_t y = 0; y < n; ++y)
+            for (size_t z = 0; z < n; ++z)
+                if (!value_is_empty(d[flat(bx + x, by + y, bz + z, dim_)])) return false;
+    return true;
+}
+
+// NodeContent::is_empty, node.rs:470-515
+bool HostOctree::node_is_empty(const NodeRec& n) const {
+    auto empty = [&](const BrickRef& b) {
+        if (b.kind == BK_EMPTY) return true;
+        if (b.kind == BK_SOLID) return value_is_empty(b.value);
+        const uint32_t* d = brick_data(b.value);
+        for (uint32_t i = 0; i < vol_; ++i)
+            if (!value_is_empty(d[i])) return false;
+        return true;
+    };
+    if (n.kind == NK_NOTHING) return true;
+    if (n.kind == NK_INTERNAL) return false;
+    if (n.kind == NK_UNIFORM) return empty(n.brick[0]);
+    for (int o = 0; o < 8; ++o)
+        if (!empty(n.brick[o])) return false;
+    return true;
+}
+
+// node_empty_at, detail.rs:255-316
+bool HostOctree::node_empty_at(size_t key, uint8_t octant) const {
+    const NodeRec& n = nodes_[key];
+    auto empty = [&](const BrickRef& b) {
+        if (b.kind == BK_EMPTY) return true;
+        uint32_t v;
+        return brick_homogeneous(b, &v) ? value_is_empty(v) : false;
+    };
+    switch (n.kind) {
+        case NK_NOTHING: return true;
+        case NK_LEAF: return empty(n.brick[octant]);
+        case NK_UNIFORM: return empty(n.brick[0]);
+        default: {
+            // (sic) looks at the child under `octant` and asks it about each of ITS octants (detail.rs:305-313)
+            const uint32_t c = n.link == LK_CHILDREN ? n.child[octant] : NIL;
+            if (!key_is_valid(c)) return true;
+            for (uint8_t o = 0; o < 8; ++o)
+                if (!node_empty_at(c, o)) return false;
+            return true;
+        }
+    }
+}
+
+// should_bitmap_be_empty_at_bitmap_index, detail.rs:181-252
+bool HostOctree::bitmap_cell_should_be_empty(size_t key, size_t x, size_t y, size_t z) const {
+    const float px = 0.5f + (float)x, py = 0.5f + (float)y, pz = 0.5f + (float)z;
+    const uint8_t oct = octant_of(px, py, pz, 2.0f);
+    const uint8_t sub = octant_of(px - off_x(oct) * 4.0f / 2.0f, py - off_y(oct) * 4.0f / 2.0f, pz - off_z(oct) * 4.0f / 2.0f, 1.0f);
+    const NodeRec& n = nodes_[key];
+    switch (n.kind) {
+        case NK_NOTHING: return true;
+        case NK_INTERNAL: {
+            const uint32_t c = n.link == LK_CHILDREN ? n.child[oct] : NIL;
+            return key_is_valid(c) ? node_empty_at(c, sub) : true;
+        }
+        case NK_UNIFORM: return brick_part_empty(n.brick[0], oct, sub);
+        default: return brick_octant_empty(n.brick[oct], sub);
+    }
+}
+
+int32_t HostOctree::clear_at_lod(uint32_t x, uint32_t y, uint32_t z, uint32_t clear_size) {
+    const BoundsF root{0, 0, 0, (float)size_};
+    const float px = (float)x, py = (float)y, pz = (float)z;
+    if (!contains(root, px, py, pz)) return SVX_E_INVALID_POSITION;
+    ++revision_;
+    struct Visit {
+        uint32_t key;
+        BoundsF b;
+    };
+    Visit path[64];
+    int depth = 0;
+    path[depth++] = {0u, root};
+    size_t actual_update_size = 0;
+    auto as_u32 = [](float v) { return (uint32_t)round_index(v); };
+
+    for (;;) {
+        const size_t cur = path[depth - 1].key;
+        const BoundsF cb = path[depth - 1].b;
+        const uint8_t oct = octant_of(px - cb.x, py - cb.y, pz - cb.z, cb.size / 2.0f);
+        const BoundsF tb{cb.x + off_x(oct) * cb.size / 2.0f, cb.y + off_y(oct) * cb.size / 2.0f,
+                         cb.z + off_z(oct) * cb.size / 2.0f, cb.size / 2.0f};
+        const uint32_t child = nodes_[cur].link == LK_CHILDREN ? nodes_[cur].child[oct] : NIL;
+        const uint32_t mx = as_u32(tb.x), my = as_u32(tb.y), mz = as_u32(tb.z);
+        const bool pos_le_min = x != mx ? x < mx : (y != my ? y < my : z <= mz);  // V3c<u32> lexicographic <=
+        if (clear_size > 1 && tb.size <= (float)clear_size && pos_le_min && key_is_valid(child)) {
+            // the whole child node is erased; the parents' occupancy is repaired below
+            deallocate_children_of(child);
+            clear_content(child);
+            NodeRec& c = nodes_[child];
+            c.link = LK_NONE;
+            c.leaf_bits = 0;
+            for (auto& k : c.child) k = NIL;
+            actual_update_size = to_index(tb.size);
+            path[depth++] = {child, tb};
+            break;
+        }
+        if (tb.size > (float)std::max(clear_size, dim_) || key_is_valid(child)) {
+            if (key_is_valid(child)) {
+                path[depth++] = {child, tb};
+                continue;
+            }
+            const NodeRec& n = nodes_[cur];
+            if (n.kind != NK_LEAF && n.kind != NK_UNIFORM) break;  // nothing stored here
+            const BrickRef& br = n.kind == NK_UNIFORM ? n.brick[0] : n.brick[oct];
+            bool match;
+            if (br.kind == BK_EMPTY) {
+                match = true;
+            } else if (br.kind == BK_SOLID) {
+                match = value_is_empty(br.value);
+            } else {
+                // (sic) unscaled `position - current_bounds.min` as brick index (clear.rs:139-146); the reference
+                // bounds-panics when it leaves the brick
+                const size_t fi = flat(x - as_u32(cb.x), y - as_u32(cb.y), z - as_u32(cb.z), dim_);
+                if (fi >= vol_) return SVX_E_INVALID_STRUCTURE;
+                match = value_is_empty(brick_data(br.value)[fi]);
+            }
+            if (match || node_is_empty(n)) break;
+            subdivide_leaf_to_nodes(cur, oct);
+            path[depth++] = {nodes_[cur].link == LK_CHILDREN ? nodes_[cur].child[oct] : NIL, tb};
+        } else {
+            actual_update_size = leaf_update(true, cur, cb, tb, oct, x, y, z, clear_size, NIL);
+            break;
+        }
+    }
+
+    // post-processing, clear.rs:224-346: free removed nodes, recompute the occupancy bits of the ancestors
+    bool have_removed = false;
+    Visit removed = path[depth - 1];
+    --depth;
+    if (to_index(removed.b.size) <= actual_update_size) have_removed = true;
+    bool simplifyable = auto_simplify;
+    for (int i = depth - 1; i >= 0; --i) {
+        const size_t key = path[i].key;
+        const BoundsF nb = path[i].b;
+        if (have_removed) {
+            const uint8_t co = octant_of((removed.b.x - nb.x) + removed.b.size / 2.0f, (removed.b.y - nb.y) + removed.b.size / 2.0f,
+                                         (removed.b.z - nb.z) + removed.b.size / 2.0f, nb.size / 2.0f);
+            NodeRec& n = nodes_[key];
+            if (n.link == LK_CHILDREN) {  // NodeChildren::clear, node.rs:75-83
+                n.child[co] = NIL;
+                bool none = true;
+                for (int k = 0; k < 8; ++k) none &= n.child[k] == NIL;
+                if (none) {
+                    n.link = LK_NONE;
+                    n.leaf_bits = 0;
+                }
+            }
+            pool_free(removed.key);
+            have_removed = false;
+        }
+        const uint64_t previous = stored_occupied_bits(key);
+        uint64_t bits = nodes_[key].link == LK_NONE ? 0 : previous;
+        if (to_index(nb.size) == actual_update_size) {
+            bits = 0;
+        } else {
+            size_t s[3];
+            matrix_index(nb, x, y, z, 4, s);
+            const size_t n = to_index(std::ceil((float)actual_update_size * 4.0f / nb.size));
+            for (size_t cx = s[0]; cx < std::min<size_t>(s[0] + n, 4); ++cx)
+                for (size_t cy = s[1]; cy < std::min<size_t>(s[1] + n, 4); ++cy)
+                    for (size_t cz = s[2]; cz < std::min<size_t>(s[2] + n, 4); ++cz)
+                        if (bitmap_cell_should_be_empty(key, cx, cy, cz)) bits &= ~(1ull << (cx + 4 * cy + 16 * cz));
+        }
+        if (bits != 0 && nodes_[key].link == LK_CHILDREN) {
+            clear_content(key);
+            nodes_[key].kind = NK_INTERNAL;
+            nodes_[key].ocbits = bits;
+        } else {
+            deallocate_children_of(key);
+            NodeRec& n = nodes_[key];
+            n.link = LK_NONE;
+            n.leaf_bits = 0;
+            for (auto& k : n.child) k = NIL;
+            have_removed = true;
+            removed = path[i];
+            clear_content(key);
+        }
+        if (bits == 0) {
+            NodeRec& n = nodes_[key];
+            n.link = LK_NONE;
+            n.leaf_bits = 0;
+            for (auto& k : n.child) k = NIL;
+        } else {
+            store_occupied_bits(key, bits);
+        }
+        if (simplifyable) simplifyable = simplify(key);
+        if (previous == bits) break;
+    }
+    return SVX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // structure hash (same definition as the oracle's: what a ray can observe, independent of key numbering)
 // ------------------------------------------------------------------------------------------------------------
 uint64_t HostOctree::hash_brick(const BrickRef& b) const {

@@ -51,6 +51,7 @@ class HostOctree {
 
     int32_t insert_at_lod_internal(bool overwrite_if_empty, uint32_t x, uint32_t y, uint32_t z, uint32_t insert_size,
                                    const svx_entry& e);
+    int32_t clear_at_lod(uint32_t x, uint32_t y, uint32_t z, uint32_t clear_size);  // src/octree/update/clear.rs:55-348
     svx_entry get(uint32_t x, uint32_t y, uint32_t z) const;
     uint64_t structure_hash() const;
 
@@ -100,6 +101,11 @@ class HostOctree {
     bool simplify(size_t key);
     bool node_is_all(const NodeRec& n, uint32_t v) const;
     bool node_compare(const NodeRec& a, const NodeRec& b) const;
+    bool node_is_empty(const NodeRec& n) const;
+    bool node_empty_at(size_t key, uint8_t octant) const;
+    bool bitmap_cell_should_be_empty(size_t key, size_t x, size_t y, size_t z) const;
+    bool brick_octant_empty(const BrickRef& b, uint8_t octant) const;
+    bool brick_part_empty(const BrickRef& b, uint8_t part_octant, uint8_t target_octant) const;
     BrickRef try_brick_from_node(size_t key);
     void dilute(const uint32_t* src, uint32_t out_handles[8]);
     uint64_t hash_node(size_t key) const;

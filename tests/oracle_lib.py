@@ -112,6 +112,10 @@ def lib() -> C.CDLL:
         getattr(L, name).restype = i32
     L.svxo_octree_insert_at_lod.argtypes = [vp, u32, u32, u32, u32, C.POINTER(Entry)]
     L.svxo_octree_insert_at_lod.restype = i32
+    L.svxo_octree_clear.argtypes = [vp, u32, u32, u32]
+    L.svxo_octree_clear.restype = i32
+    L.svxo_octree_clear_at_lod.argtypes = [vp, u32, u32, u32, u32]
+    L.svxo_octree_clear_at_lod.restype = i32
     L.svxo_octree_insert_batch.argtypes = [vp, vp, vp, vp, u64]
     L.svxo_octree_insert_batch.restype = i32
     L.svxo_octree_get.argtypes = [vp, u32, u32, u32, C.POINTER(Entry)]
@@ -222,6 +226,12 @@ class OracleOctree:
 
     def insert_at_lod(self, pos, size, albedo=None, data=None) -> int:
         return lib().svxo_octree_insert_at_lod(self._h, *pos, size, C.byref(make_entry(albedo, data)))
+
+    def clear(self, pos) -> int:
+        return lib().svxo_octree_clear(self._h, *pos)
+
+    def clear_at_lod(self, pos, size) -> int:
+        return lib().svxo_octree_clear_at_lod(self._h, *pos, size)
 
     def insert_batch(self, xyz: np.ndarray, rgba: np.ndarray, lod: np.ndarray | None = None) -> int:
         xyz = np.ascontiguousarray(xyz, dtype=np.uint32)

@@ -32,6 +32,12 @@ class ProductOctree:
     def insert_at_lod(self, pos, size, albedo=None, data=None):
         return self._call(self.tree.insert_at_lod, pos, size, albedo, data)
 
+    def clear(self, pos):
+        return self._call(self.tree.clear, pos)
+
+    def clear_at_lod(self, pos, size):
+        return self._call(self.tree.clear_at_lod, pos, size)
+
     def insert_batch(self, xyz, rgba, lod=None):
         return self._call(self.tree.insert_batch, xyz, rgba, lod)
 

@@ -333,3 +333,26 @@ def test_random_cameras_exercise_cull_rectangle_and_prefilter():
         assert_frames_equal(view.render_to_host(), ora)
         hits += int((ora["hit_id"] != S.MISS).sum())
     assert hits > 20000
+
+
+def test_clear_then_reload_matches_oracle():
+    """§8(f) rank 1: Octree::clear / clear_at_lod edits followed by a re-upload (OctreeGPUView::reload)."""
+    scene = scenes.cpu_render_scene()
+    tree, otree = both_trees(scene)
+    cam = scenes.cpu_render_camera()
+    host = S.OctreeGPUHost(tree)
+    view = host.create_new_view(1, viewport(cam), (320, 240))
+    before = view.render_to_host()
+    rng = np.random.default_rng(11)
+    for t in (tree, otree):
+        t.clear_at_lod((32, 32, 32), 16)       # carve a block out of the dense corner
+        t.clear_at_lod((48, 48, 32), 8)
+    for _ in range(300):                         # and single voxels out of the lattice and the corner
+        p = tuple(int(v) for v in rng.integers(0, 64, 3))
+        tree.clear(p)
+        otree.clear(p)
+    assert tree.structure_hash() == otree.structure_hash()
+    view.reload()
+    after = view.render_to_host()
+    assert not np.array_equal(before["hit_id"], after["hit_id"])
+    assert_frames_equal(after, otree.render(oracle_camera(cam), 320, 240))

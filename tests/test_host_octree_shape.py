@@ -44,8 +44,8 @@ def test_scene_trees_have_identical_shape(scene_fn):
 
 @pytest.mark.parametrize("size,dim,seed", [(8, 1, 0), (8, 2, 1), (16, 2, 2), (16, 4, 3), (32, 4, 4), (32, 8, 5), (64, 8, 6)])
 def test_random_edit_sequences_have_identical_shape(size, dim, seed):
-    """Random interleaving of insert / insert_at_lod / update with few colours, so that simplification, uniform-leaf
-    splitting and whole-node overwrites all trigger (seeded)."""
+    """Random interleaving of insert / insert_at_lod / update / clear / clear_at_lod with few colours, so that
+    simplification, uniform-leaf splitting, whole-node overwrites and node removal all trigger (seeded)."""
     rng = np.random.default_rng(seed)
     a, b = O.OracleOctree(size, dim), ProductOctree(size, dim)
     colors = [0xFF0000FF, 0x00FF00FF, 0x0000FFFF]
@@ -55,10 +55,17 @@ def test_random_edit_sequences_have_identical_shape(size, dim, seed):
         c = colors[int(rng.integers(0, len(colors)))]
         if op < 6:
             ra, rb = a.insert(p, c), b.insert(p, c)
-        elif op < 8:
+        elif op < 7:
             lod = int(2 ** rng.integers(1, 4))
             q = tuple((v // lod) * lod for v in p) if rng.integers(0, 2) else p
             ra, rb = a.insert_at_lod(q, lod, c), b.insert_at_lod(q, lod, c)
+        elif op < 8:
+            if rng.integers(0, 3) == 0:
+                lod = int(2 ** rng.integers(1, 4))
+                q = tuple((v // lod) * lod for v in p) if rng.integers(0, 2) else p
+                ra, rb = a.clear_at_lod(q, lod), b.clear_at_lod(q, lod)
+            else:
+                ra, rb = a.clear(p), b.clear(p)
         elif op < 9:
             d = int(rng.integers(1, 4))
             ra, rb = a.update(p, None, d), b.update(p, None, d)

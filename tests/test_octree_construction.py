@@ -319,3 +319,226 @@ def test_random_inserts_match_model(Tree, size, dim):
         model[p] = c
     for p in itertools.product(range(size), repeat=3):
         assert t.get(p) == (K(model[p]) if p in model else K()), p
+
+
+# ---- clear / clear_at_lod (src/octree/update/clear.rs), tests of src/octree/update/tests.rs -------------------------
+def fill(t, size, color):
+    for p in itertools.product(range(size), repeat=3):
+        t.insert(p, color)
+
+
+# update/tests.rs:245-358
+@pytest.mark.parametrize("dim", [1, 2, 4])
+def test_case_simplified_insert_separated_by_clear(Tree, dim):
+    t = make_tree(Tree, 8, dim)
+    fill(t, 8, RED)
+    assert t.get((3, 3, 3)) == K(RED)
+    assert t.clear((3, 3, 3)) == O.OK
+    assert t.get((3, 3, 3)) == K()
+    assert count_hits(t, 8, RED) == 511
+
+
+# update/tests.rs:404-429
+def test_uniform_solid_leaf_separated_by_clear_where_dim_is_1(Tree):
+    t = make_tree(Tree, 2, 1)
+    for o in OFFS:
+        t.insert(o, 0xFFFF00FF)
+    t.clear((0, 0, 0))
+    assert t.get((0, 0, 0)) == K()
+    for o in OFFS[1:]:
+        assert t.get(o) == K(0xFFFF00FF)
+
+
+# update/tests.rs:463-512
+def test_uniform_solid_leaf_separated_by_clear_where_dim_is_4(Tree):
+    D = 4
+    t = make_tree(Tree, 8, D)
+    base = 0xFFFF00AA
+    for octant, o in enumerate(OFFS):
+        start = [c * (D // 2) for c in o]
+        for d in itertools.product(range(D // 2), repeat=3):
+            t.insert(tuple(s + e for s, e in zip(start, d)), base + octant)
+    assert t.get((0, 0, 0)) == K(base)
+    t.clear((0, 0, 0))
+    assert t.get((0, 0, 0)) == K()
+    for octant, o in enumerate(OFFS):
+        start = [c * (D // 2) for c in o]
+        for d in itertools.product(range(D // 2), repeat=3):
+            if d == (0, 0, 0) and octant == 0:
+                continue
+            assert t.get(tuple(s + e for s, e in zip(start, d))) == K(base + octant)
+
+
+# update/tests.rs:570-640
+def test_uniform_parted_brick_leaf_separated_by_clear_where_dim_is_4(Tree):
+    D = 4
+    t = make_tree(Tree, 8, D)
+
+    def color(x, y, z):
+        return (x - x % (D // 2), y - y % (D // 2), z - z % (D // 2), 255)
+
+    for o in OFFS:
+        for x, y, z in itertools.product(range(D), repeat=3):
+            t.insert((o[0] * D + x, o[1] * D + y, o[2] * D + z), color(x, y, z))
+    assert t.get((0, 0, 0)) == K(0x000000FF)
+    t.clear((1, 1, 1))
+    assert t.get((1, 1, 1)) == K()
+    for octant, o in enumerate(OFFS):
+        for x, y, z in itertools.product(range(D), repeat=3):
+            p = (o[0] * D + x, o[1] * D + y, o[2] * D + z)
+            if (x, y, z) == (1, 1, 1) and octant == 0:
+                assert t.get(p) == K()
+            else:
+                assert t.get(p) == K(color(x, y, z)), p
+
+
+# update/tests.rs:1030-1069
+@pytest.mark.parametrize("size,dim", [(2, 1), (4, 2)])
+def test_simple_clear(Tree, size, dim):
+    t = make_tree(Tree, size, dim, False)
+    t.insert((1, 0, 0), RED); t.insert((0, 1, 0), GREEN); t.insert((0, 0, 1), BLUE)
+    t.clear((0, 0, 1))
+    assert t.get((1, 0, 0)) == K(RED) and t.get((0, 1, 0)) == K(GREEN)
+    assert t.get((0, 0, 1)) == K() and t.get((1, 1, 1)) == K()
+
+
+# update/tests.rs:1072-1118
+def test_clear_small_parts_of_large_nodes(Tree):
+    t = make_tree(Tree, 64, 8)
+    t.insert((0, 1, 1), RED); t.insert((1, 0, 0), RED)
+    t.clear((1, 0, 0))
+    assert t.get((1, 0, 0)) == K() and t.get((0, 1, 1)) == K(RED)
+    t = make_tree(Tree, 64, 8)
+    t.insert_at_lod((33, 33, 33), 2, RED)
+    assert t.get((33, 33, 33)) == K(RED)
+    t.clear((33, 33, 33))
+    assert t.get((33, 33, 33)) == K()
+    t = make_tree(Tree, 64, 8)
+    t.insert((31, 31, 31), RED)
+    t.clear((31, 31, 31))
+    assert t.get((31, 31, 31)) == K()
+
+
+# update/tests.rs:1121-1136
+def test_double_clear(Tree):
+    t = make_tree(Tree, 2, 1, False)
+    t.insert((1, 0, 0), 0x000000FF); t.insert((0, 1, 0), 0xFFFFFFFF); t.insert((0, 0, 1), 0xFFFFFFFF)
+    t.clear((0, 0, 1)); t.clear((0, 0, 1))
+    assert t.get((1, 0, 0)) == K(0x000000FF) and t.get((0, 1, 0)) == K(0xFFFFFFFF) and t.get((0, 0, 1)) == K()
+
+
+# update/tests.rs:1139-1196
+@pytest.mark.parametrize("size,dim", [(2, 1), (4, 2)])
+def test_simplifyable_clear(Tree, size, dim):
+    t = make_tree(Tree, size, dim)
+    fill(t, size, 0xFFAAEEFF)
+    t.clear((0, 0, 0))
+    assert t.get((0, 0, 0)) == K()
+    for p in itertools.product(range(1, size), repeat=3):
+        assert t.get(p) == K(0xFFAAEEFF)
+
+
+# update/tests.rs:1199-1226
+def test_clear_to_nothing(Tree):
+    t = make_tree(Tree, 4, 1)
+    for p in itertools.product(range(2), repeat=3):
+        t.insert(p, 0xFFAAEEFF)
+    t.clear_at_lod((0, 0, 0), 2)
+    for p in itertools.product(range(2), repeat=3):
+        assert t.get(p) == K()
+
+
+# update/tests.rs:1229-1278
+def test_clear_edge_case(Tree):
+    t = make_tree(Tree, 64, 16)
+    t.update((1, 0, 0), None, 0xFACEFEED)
+    t.insert_at_lod((0, 0, 0), 32, RED)
+    t.clear_at_lod((5, 5, 5), 8)
+    for p in itertools.product(range(5, 8), repeat=3):
+        assert t.get(p) == K()
+    for p in itertools.product(range(5), repeat=3):
+        assert t.get(p) == K(RED), p
+    t.clear_at_lod((0, 0, 0), 32)
+    for p in itertools.product(range(0, 32, 3), repeat=3):
+        assert t.get(p) == K(), p
+
+
+# update/tests.rs:1281-1350
+@pytest.mark.parametrize("dim", [1, 2])
+def test_clear_at_lod(Tree, dim):
+    t = make_tree(Tree, 8, dim)
+    t.insert_at_lod((0, 0, 0), 4, 0xFFAAEEFF)
+    t.clear_at_lod((0, 0, 0), 2)
+    assert count_hits(t, 4, 0xFFAAEEFF) == 64 - 8
+
+
+# update/tests.rs:1353-1405
+def test_clear_at_lod_with_unaligned_position(Tree):
+    t = make_tree(Tree, 8, 1)
+    t.insert_at_lod((0, 0, 0), 4, 0xFFAAEEFF)
+    t.clear_at_lod((1, 1, 1), 2)
+    for p in itertools.product(range(2), repeat=3):
+        assert t.get(p) == K()
+    for p in [(0, 0, 2), (0, 2, 0), (0, 2, 2), (2, 0, 0), (2, 0, 2), (2, 2, 0), (2, 2, 2)]:
+        assert t.get(p) != K()
+    assert count_hits(t, 4, 0xFFAAEEFF) == 64 - 8
+
+
+# update/tests.rs:1408-1463
+def test_clear_at_lod_with_unaligned_position_where_dim_is_4(Tree):
+    t = make_tree(Tree, 16, 4)
+    t.insert_at_lod((0, 0, 0), 8, 0xFFAAEEFF)
+    assert count_hits(t, 8, 0xFFAAEEFF) == 512
+    t.clear_at_lod((1, 1, 1), 4)
+    assert count_hits(t, 8, 0xFFAAEEFF) == 512 - 27
+
+
+# update/tests.rs:1466-1547
+def test_clear_at_lod_with_unaligned_size(Tree):
+    t = make_tree(Tree, 8, 1)
+    t.insert_at_lod((0, 0, 0), 4, 0xFFAAEEFF)
+    t.clear_at_lod((0, 0, 0), 3)
+    assert count_hits(t, 4, 0xFFAAEEFF) == 64 - 8
+    t = make_tree(Tree, 8, 4)
+    t.insert_at_lod((0, 0, 0), 4, 0xFFAAEEFF)
+    assert count_hits(t, 8, 0xFFAAEEFF) == 64
+    t.clear_at_lod((0, 0, 0), 3)
+    assert count_hits(t, 8, 0xFFAAEEFF) == 64 - 27
+
+
+# update/tests.rs:1550-1598
+def test_clear_whole_nodes_where_dim_is_4(Tree):
+    t = make_tree(Tree, 16, 4)
+    t.insert_at_lod((0, 0, 0), 8, 0xFFAAEEFF)
+    assert count_hits(t, 8, 0xFFAAEEFF) == 512
+    t.clear_at_lod((0, 0, 0), 5)
+    assert count_hits(t, 8, 0xFFAAEEFF) == 512 - 64
+
+
+def test_clear_out_of_bounds(Tree):
+    t = make_tree(Tree, 4, 1)
+    assert t.clear((0, 4, 0)) == O.E_INVALID_POSITION
+
+
+@pytest.mark.parametrize("size,dim", [(8, 2), (16, 4), (32, 8)])
+def test_random_inserts_and_clears_match_model(Tree, size, dim):
+    """Random inserts and clears against a dict model. brick_dim 1 is left out on purpose: there the reference turns
+    Internal nodes of size 2 back into leaves and drops their children (update/mod.rs:497-521, "might induce data loss -
+    see #69"), which both implementations reproduce (tests/test_host_octree_shape.py checks they agree)."""
+    rng = np.random.default_rng(size * 1000 + dim)
+    t = make_tree(Tree, size, dim)
+    model = {}
+    colors = [0xFF0000FF, 0x00FF00FF, 0x0000FFFF]
+    for step in range(900):
+        p = tuple(int(v) for v in rng.integers(0, size, 3))
+        if rng.integers(0, 3) == 0 and model:
+            if rng.integers(0, 2):
+                p = list(model)[int(rng.integers(0, len(model)))]
+            assert t.clear(p) == O.OK
+            model.pop(p, None)
+        else:
+            c = colors[int(rng.integers(0, len(colors)))]
+            assert t.insert(p, c) == O.OK
+            model[p] = c
+    for p in itertools.product(range(size), repeat=3):
+        assert t.get(p) == (K(model[p]) if p in model else K()), p
