@@ -1,0 +1,77 @@
+"""MagicaVoxel import (shocovox_b200/vox.py; reference src/convert/magicavoxel.rs). Parity is unpinned (see the module
+docstring); these tests cover the format round trip, the reference's rotation KAT and its own small assets."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import shocovox_b200 as S
+from product_adapter import ProductOctree
+from shocovox_b200 import vox
+
+ASSETS = Path("/root/reference/assets/models")
+
+
+# src/convert/magicavoxel.rs:392-413
+def test_matrix_parse():
+    assert np.array_equal(vox.parse_rotation_matrix(4), np.eye(3, dtype=np.int64))
+    m = vox.parse_rotation_matrix((1 << 0) | (2 << 2) | (0 << 4) | (1 << 5) | (1 << 6))
+    assert np.array_equal(m, np.array([[0, 1, 0], [0, 0, -1], [-1, 0, 0]]))
+
+
+def _model(seed, size):
+    rng = np.random.default_rng(seed)
+    n = 200
+    pts = np.unique(rng.integers(0, size, (n, 3)), axis=0)
+    idx = rng.integers(0, 255, (len(pts), 1))
+    return (size, size, size), np.concatenate([pts, idx], axis=1)
+
+
+def test_round_trip_single_model_without_scene_graph():
+    size, v = _model(1, 16)
+    pal = np.random.default_rng(2).integers(1, 256, (256, 4)).astype(np.uint8)
+    blob = vox.write_vox([(size, v)], palette=pal)
+    tree_size, xyz, rgba = vox.load_vox(blob, brick_dimension=4)
+    assert tree_size == 16  # translation 0 +- half size 8 -> extent 16
+    # Rzup -> Lyup swaps y and z; the model is centred on the origin and shifted by the minimum corner
+    want = np.stack([v[:, 0], v[:, 2], v[:, 1]], axis=1)
+    assert np.array_equal(xyz.astype(np.int64), want)
+    assert np.array_equal(rgba, pal[v[:, 3]])
+
+
+def test_scene_graph_translation_and_rotation():
+    size, v = _model(3, 8)
+    pal = np.random.default_rng(4).integers(1, 256, (256, 4)).astype(np.uint8)
+    rot = (1 << 0) | (0 << 2) | (1 << 4)  # rows: (0,-1,0), (1,0,0), (0,0,1): a quarter turn about z
+    blob = vox.write_vox([(size, v), (size, v)], palette=pal, placements=[((0, 0, 0), None), ((20, 0, 0), rot)])
+    tree_size, xyz, rgba = vox.load_vox(blob, brick_dimension=4)
+    assert tree_size == 32 and len(xyz) == 2 * len(v)
+    assert xyz.max() < tree_size
+    # the first model keeps its shape (up to the axis swap); the second is the rotated copy 20 units along x
+    a = xyz[: len(v)].astype(np.int64)
+    assert np.array_equal(a - a.min(axis=0), np.stack([v[:, 0], v[:, 2], v[:, 1]], axis=1) - np.stack([v[:, 0], v[:, 2], v[:, 1]], axis=1).min(axis=0))
+    assert len(np.unique(xyz, axis=0)) == 2 * len(v)  # the copies do not overlap
+    t = S.Octree(tree_size, 4)
+    t.insert_batch(xyz, rgba)
+    for p, c in list(zip(xyz, rgba))[:50]:
+        e = t.get(tuple(int(q) for q in p))
+        assert e.albedo is not None and (e.albedo.r, e.albedo.g, e.albedo.b, e.albedo.a) == tuple(int(q) for q in c)
+
+
+@pytest.mark.parametrize("name", ["navigate.vox", "navigate_x.vox", "navigate_y.vox", "navigate_z.vox"])
+def test_reference_assets_when_present(name):
+    """The reference's own small models (assets/models): every voxel lands inside the tree, and the product's host
+    octree and the oracle build the same tree from them."""
+    path = ASSETS / name
+    if not path.exists():
+        pytest.skip("reference assets are not present on this box")
+    tree_size, xyz, rgba = vox.load_vox(path, brick_dimension=8)
+    assert 300 <= len(xyz) <= 100000 and tree_size in (64, 128, 256, 512)
+    assert int(xyz.max()) < tree_size and int(xyz.max()) >= tree_size // 2  # the model fills more than half the extent
+    a, b = O.OracleOctree(tree_size, 8), ProductOctree(tree_size, 8)
+    a.insert_batch(xyz, rgba)
+    b.insert_batch(xyz, rgba)
+    assert a.structure_hash() == b.structure_hash()
+    hits = sum(1 for p in xyz[:200] if b.get(tuple(int(q) for q in p)) != (O.EMPTY,))
+    assert hits == min(200, len(xyz))
