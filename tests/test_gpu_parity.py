@@ -20,7 +20,10 @@ DIST_RTOL = 1e-4  # tolerance stated by BASELINE.json's north star
 
 
 def bits(a):
-    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    """f32 bit patterns, with every NaN mapped to one canonical pattern (0/0 gives 0xFFC00000 on x86 and 0x7FFFFFFF
+    on the GPU; a NaN's sign and payload carry no meaning - the reference's normal of a hit at the exact cell centre)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return np.where(np.isnan(a), np.uint32(0x7FC00000), a.view(np.uint32))
 
 
 def oracle_camera(c):

@@ -1,0 +1,146 @@
+#!/usr/bin/env python3
+"""Randomised GPU-vs-oracle parity soak (GPU box): random trees (sizes, brick dims, edit mixes incl. insert_at_lod and
+clear), random rays (outside / inside / axis-parallel / grazing), every output field compared bit for bit.
+
+    python tools/fuzz_parity.py [--seconds 120] [--seed 0]
+Writes gpurun_out/fuzz_parity.json. Exit code 1 on the first mismatch (the failing case is printed).
+"""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    sys.path.insert(0, p)
+import oracle_lib as O  # noqa: E402
+import shocovox_b200 as S  # noqa: E402
+from product_adapter import ProductOctree  # noqa: E402
+
+
+def random_tree_ops(rng, size, dim):
+    ops = []
+    n = int(rng.integers(20, 1500))
+    colors = [int(c) for c in rng.integers(1, 2 ** 32 - 1, int(rng.integers(1, 6)), dtype=np.uint64) | 0xFF]
+    style = int(rng.integers(0, 4))
+    for _ in range(n):
+        if style == 0:      # scattered voxels
+            p = rng.integers(0, size, 3)
+        elif style == 1:    # a slab / floor
+            p = np.array([rng.integers(0, size), rng.integers(0, max(size // 8, 1)), rng.integers(0, size)])
+        elif style == 2:    # clustered blob
+            p = np.clip(rng.normal(size / 2, size / 8, 3), 0, size - 1).astype(np.int64)
+        else:               # mix with lod inserts and clears
+            p = rng.integers(0, size, 3)
+        p = tuple(int(v) for v in p)
+        k = int(rng.integers(0, 12))
+        c = colors[int(rng.integers(0, len(colors)))]
+        if style == 3 and k < 2:
+            lod = int(2 ** rng.integers(1, max(2, int(np.log2(size)) - 1)))
+            ops.append(("insert_at_lod", tuple((v // lod) * lod for v in p), lod, c))
+        elif style == 3 and k < 4:
+            ops.append(("clear", p))
+        elif k == 11:
+            ops.append(("insert_data", p, int(rng.integers(1, 5))))
+        else:
+            ops.append(("insert", p, c))
+    return ops
+
+
+def apply(t, ops):
+    for op in ops:
+        if op[0] == "insert":
+            t.insert(op[1], op[2])
+        elif op[0] == "insert_data":
+            t.insert(op[1], None, op[2])
+        elif op[0] == "insert_at_lod":
+            t.insert_at_lod(op[1], op[2], op[3])
+        else:
+            t.clear(op[1])
+
+
+def random_rays(rng, size, n):
+    origin = rng.uniform(-1.5 * size, 2.5 * size, (n, 3)).astype(np.float32)
+    inside = rng.random(n) < 0.3
+    origin[inside] = rng.uniform(0, size, (int(inside.sum()), 3)).astype(np.float32)
+    target = rng.uniform(-0.1 * size, 1.1 * size, (n, 3)).astype(np.float32)
+    d = target - origin
+    ln = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2], dtype=np.float32)
+    d = (d / ln[:, None]).astype(np.float32)
+    k = n // 10
+    d[:k] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, k)] * rng.choice([-1.0, 1.0], k)[:, None].astype(np.float32)
+    origin[:k] = np.round(origin[:k])
+    j = n // 10  # grazing: along a face / grid plane
+    origin[k:k + j, 1] = rng.integers(0, size + 1, j).astype(np.float32)
+    d[k:k + j, 1] = 0.0
+    ln = np.sqrt((d[k:k + j, 0] ** 2 + d[k:k + j, 1] ** 2) + d[k:k + j, 2] ** 2, dtype=np.float32)
+    d[k:k + j] = (d[k:k + j] / np.maximum(ln, 1e-12)[:, None]).astype(np.float32)
+    return np.concatenate([origin, d], axis=1)
+
+
+def bits(a):
+    """f32 bit patterns, with every NaN mapped to one canonical pattern (0/0 gives 0xFFC00000 on x86 and 0x7FFFFFFF
+    on the GPU; a NaN's sign and payload carry no meaning - the reference's normal of a hit at the exact cell centre)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return np.where(np.isnan(a), np.uint32(0x7FC00000), a.view(np.uint32))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--rays", type=int, default=20000)
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    t0 = time.time()
+    cases = rays_total = hits_total = 0
+    configs = [(4, 1), (8, 1), (8, 2), (16, 2), (16, 4), (32, 4), (32, 8), (64, 8), (64, 16), (128, 8), (128, 32), (256, 8), (512, 8), (1024, 16), (32, 1)]
+    while time.time() - t0 < args.seconds:
+        size, dim = configs[int(rng.integers(0, len(configs)))]
+        ops = random_tree_ops(rng, size, dim)
+        a, b = O.OracleOctree(size, dim), ProductOctree(size, dim)
+        apply(a, ops)
+        apply(b, ops)
+        if a.structure_hash() != b.structure_hash():
+            print("TREE SHAPE MISMATCH", size, dim, ops[:20])
+            return 1
+        rays = random_rays(rng, size, args.rays)
+        g = S.OctreeGPUHost(b.tree).get_by_rays(rays)
+        o = a.get_by_rays(rays)
+        ok = (np.array_equal(g["hit"], o["hit"]) and np.array_equal(g["palette_value"], o["palette_value"])
+              and np.array_equal(g["rgba"], o["rgba"]) and np.array_equal(g["data"], o["data"])
+              and np.array_equal(bits(g["impact_point"]), bits(o["impact_point"]))
+              and np.array_equal(bits(g["normal"]), bits(o["normal"])) and np.array_equal(bits(g["distance"]), bits(o["distance"])))
+        if not ok:
+            fields = {
+                "hit": g["hit"] != o["hit"], "palette_value": g["palette_value"] != o["palette_value"],
+                "entry_kind": g["entry_kind"] != o["entry_kind"],
+                "rgba": (g["rgba"] != o["rgba"]).any(axis=1), "data": g["data"] != o["data"],
+                "impact_point": (bits(g["impact_point"]) != bits(o["impact_point"])).any(axis=1),
+                "normal": (bits(g["normal"]) != bits(o["normal"])).any(axis=1),
+                "distance": bits(g["distance"]) != bits(o["distance"]),
+            }
+            print("RAY MISMATCH size", size, "dim", dim, "case", cases, {k: int(v.sum()) for k, v in fields.items()})
+            for k, v in fields.items():
+                idx = np.nonzero(v)[0][:3]
+                for i in idx:
+                    print(" ", k, "ray", rays[i].tolist(), "gpu", g[i], "oracle", {n: o[i][n] for n in g.dtype.names})
+            return 1
+        if int(o["would_panic"].sum()):
+            print("note: reference would have panicked on", int(o["would_panic"].sum()), "rays in case", cases)
+        cases += 1
+        rays_total += len(rays)
+        hits_total += int(o["hit"].sum())
+    out = {"seed": args.seed, "seconds": round(time.time() - t0, 1), "random_trees": cases, "rays": rays_total, "hits": hits_total,
+           "result": "every field bit-identical to the CPU oracle"}
+    Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / f"fuzz_parity_seed{args.seed}.json").write_text(json.dumps(out))
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
