@@ -132,7 +132,7 @@ EXPORTS = [
     "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
     "svx_view_set_glass_mode", "svx_view_set_resolution", "svx_view_resolution", "svx_view_set_shard",
-    "svx_view_set_compact_rows", "svx_view_frame_pointers", "svx_view_export_frame_ipc", "svx_view_set_peer_frame_ipc",
+    "svx_view_set_schedule", "svx_view_set_compact_rows", "svx_view_frame_pointers", "svx_view_export_frame_ipc", "svx_view_set_peer_frame_ipc",
     "svx_view_render", "svx_view_render_to_host", "svx_view_render_batch", "svx_view_cuda_stream", "svx_view_device",
     "svx_view_synchronize", "svx_view_timer_start", "svx_view_timer_stop", "svx_view_flush_l2", "svx_view_launch_count",
 ]
@@ -195,6 +195,7 @@ def lib() -> C.CDLL:
     L.svx_view_set_resolution.argtypes = [vp, u32, u32]
     L.svx_view_resolution.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.svx_view_set_shard.argtypes = [vp, u32, u32, u32]
+    L.svx_view_set_schedule.argtypes = [vp, i32]
     L.svx_view_set_compact_rows.argtypes = [vp, i32]
     L.svx_view_frame_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.svx_view_export_frame_ipc.argtypes = [vp, vp]
@@ -513,6 +514,9 @@ class OctreeGPUView:
 
     def set_shard(self, rank: int, world: int, rows_per_band: int = 8):
         _check(lib().svx_view_set_shard(self._h, int(rank), int(world), int(rows_per_band)))
+
+    def set_schedule(self, persistent: bool):
+        _check(lib().svx_view_set_schedule(self._h, int(persistent)))
 
     def set_compact_rows(self, enabled: bool):
         _check(lib().svx_view_set_compact_rows(self._h, int(enabled)))

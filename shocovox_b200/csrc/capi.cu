@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -16,6 +17,10 @@
 #include "kernels.cuh"
 
 using namespace svx;
+
+#ifndef SVX_DEFAULT_PERSISTENT
+#define SVX_DEFAULT_PERSISTENT false
+#endif
 
 namespace {
 
@@ -154,6 +159,9 @@ struct svx_view {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t tm_start = nullptr, tm_stop = nullptr;
+    uint32_t* d_counters = nullptr;  // two ticket counters of the persistent schedule (ping-pong across launches)
+    uint32_t counter_slot = 0;
+    bool persistent = false;
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     uint32_t* d_hit_id = nullptr;
@@ -324,8 +332,13 @@ int32_t alloc_frame(svx_view* v) {
 int32_t render_locked(svx_view* v) {
     FrameParams f;
     make_frame_constants(v, &f);
+    LaunchConfig cfg = v->host->cfg;
+    cfg.persistent = v->persistent;
+    cfg.tile_counters = v->d_counters;
+    f.counter_slot = v->counter_slot;
+    if (v->persistent) v->counter_slot ^= 1u;
     CUDA_TRY(cudaEventRecord(v->ev_start, v->stream));
-    CUDA_TRY(launch_render(v->host->dev, f, v->host->cfg, v->stream));
+    CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
     CUDA_TRY(cudaEventRecord(v->ev_stop, v->stream));
     v->launches += 1;
     return SVX_OK;
@@ -555,6 +568,14 @@ int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* 
         svx_view_free(v);
         return s;
     }
+    e = cudaMalloc((void**)&v->d_counters, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(v->d_counters, 0, 2 * sizeof(uint32_t), v->stream);
+    if (e != cudaSuccess) {
+        svx_view_free(v);
+        return cuda_fail(e, "tile counters");
+    }
+    const char* env = std::getenv("SVX_SCHEDULE");  // "persistent" | "static" (tuning override)
+    v->persistent = env ? std::strcmp(env, "persistent") == 0 : SVX_DEFAULT_PERSISTENT;
     *out = v;
     return SVX_OK;
 }
@@ -573,6 +594,7 @@ void svx_view_free(svx_view* v) {
     for (int i = 0; i < 3; ++i)
         if (v->peer_base[i]) cudaIpcCloseMemHandle(v->peer_base[i]);
     cudaFree(v->d_flush);
+    cudaFree(v->d_counters);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
 }
@@ -616,6 +638,17 @@ int32_t svx_view_set_shard(svx_view* v, uint32_t rank, uint32_t world, uint32_t 
     v->rank = rank;
     v->world = world;
     v->band_rows = rows_per_band;
+    return SVX_OK;
+}
+
+int32_t svx_view_set_schedule(svx_view* v, int32_t persistent) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    CUDA_TRY(cudaMemsetAsync(v->d_counters, 0, 2 * sizeof(uint32_t), v->stream));
+    v->counter_slot = 0;
+    v->persistent = persistent != 0;
     return SVX_OK;
 }
 

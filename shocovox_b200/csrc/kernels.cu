@@ -5,19 +5,27 @@
 
 namespace svx {
 
-// One warp renders an 8x4 pixel tile (coherent rays, 32-byte framebuffer segments per row and plane);
-// a 256-thread block covers 32x8 pixels.
-constexpr int TILE_W = 32;
-constexpr int TILE_H = 8;
-constexpr int BLOCK_THREADS = 256;
-#ifndef SVX_MIN_BLOCKS
-#define SVX_MIN_BLOCKS 4
+// One warp renders an 8x4 pixel tile (coherent rays, 32-byte framebuffer segments per row and plane).
+// CTA shape: SVX_BLOCK_WARPS_X x SVX_BLOCK_WARPS_Y warps, each warp an 8x4 pixel tile. Small CTAs retire as soon as
+// their slowest warp is done, which matters because neighbouring rays can differ a lot in length (measured on B200:
+// 128-thread CTAs of 2x2 or 4x1 warps beat 4x2 and 4x4 by 2-5 % on every scene; 64- and 32-thread CTAs lose again).
+#ifndef SVX_BLOCK_WARPS_X
+#define SVX_BLOCK_WARPS_X 2
 #endif
+#ifndef SVX_BLOCK_WARPS_Y
+#define SVX_BLOCK_WARPS_Y 2
+#endif
+#ifndef SVX_MIN_BLOCKS
+#define SVX_MIN_BLOCKS (32 / (SVX_BLOCK_WARPS_X * SVX_BLOCK_WARPS_Y))  // 1024 threads (64 registers each) per SM
+#endif
+constexpr int TILE_W = 8 * SVX_BLOCK_WARPS_X;
+constexpr int TILE_H = 4 * SVX_BLOCK_WARPS_Y;
+constexpr int BLOCK_THREADS = 32 * SVX_BLOCK_WARPS_X * SVX_BLOCK_WARPS_Y;
 
 __device__ __forceinline__ void pixel_of_thread(int& tx, int& ty) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tx = ((warp & 3) << 3) + (lane & 7);
-    ty = ((warp >> 2) << 2) + (lane >> 3);
+    tx = ((warp % SVX_BLOCK_WARPS_X) << 3) + (lane & 7);
+    ty = ((warp / SVX_BLOCK_WARPS_X) << 2) + (lane >> 3);
 }
 
 // Ray generation of the caller loop, reference examples/cpu_render.rs:104-114, in its f32 operation order:
@@ -34,11 +42,9 @@ __device__ __forceinline__ void glass_vector(const FrameParams& f, uint32_t x, u
     vz = gz - f.oz;
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(const DeviceTree tree, const FrameParams f) {
-    int tx, ty;
-    pixel_of_thread(tx, ty);
-    const uint32_t x = blockIdx.x * TILE_W + tx;
-    const uint32_t lr = blockIdx.y * TILE_H + ty;  // row index inside this shard
+// One pixel of the frame: ray generation, rejection tests, get_by_ray, framebuffer stores.
+// (x, lr) = column and shard-local row.
+__device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr) {
     if (x >= f.width || lr >= f.rows_local) return;
     // shard-local row -> image row (interleaved bands of 2^band_shift rows)
     const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
@@ -84,6 +90,38 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(c
     f.hit_id[i] = hit_id;
     f.albedo[i] = rgba;
     f.distance[i] = dist;
+}
+
+// Static schedule: one CTA per 32x8 pixel block of the frame.
+__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(const DeviceTree tree, const FrameParams f) {
+    int tx, ty;
+    pixel_of_thread(tx, ty);
+    shade_pixel(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+}
+
+// Persistent schedule: the grid is sized to the machine (SMs x resident CTAs) and every WARP pulls 8x4 pixel tiles from a
+// global counter until the frame is done, so a long ray delays one warp, not the seven that share its CTA, and the SMs
+// stay busy to the end of the frame. `counters[f.counter_slot]` is this launch's ticket counter; the other slot is
+// zeroed for the next launch (launches of one view are ordered on one stream).
+__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel_persistent(const DeviceTree tree, const FrameParams f,
+                                                                                          uint32_t* __restrict__ counters) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[f.counter_slot ^ 1u] = 0u;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tiles_x = (f.width + 7u) >> 3, tiles_y = (f.rows_local + 3u) >> 2;
+    const uint32_t blocks_x = (tiles_x + 3u) >> 2, blocks_y = (tiles_y + 1u) >> 1;
+    const uint32_t n_tickets = blocks_x * blocks_y * 8u;
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&counters[f.counter_slot], 1u);
+        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+        if (tile >= n_tickets) return;
+        // tickets are numbered so that 8 consecutive ones form the same 32x8 pixel block a CTA of the static schedule
+        // covers (neighbouring warps share tree nodes and framebuffer sectors)
+        const uint32_t blk = tile >> 3, sub = tile & 7u;
+        const uint32_t bx = blk % blocks_x, by = blk / blocks_x;
+        const uint32_t ttx = (bx << 2) + (sub & 3u), tty = (by << 1) + (sub >> 2);
+        if (ttx < tiles_x && tty < tiles_y) shade_pixel(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
+    }
 }
 
 __global__ void __launch_bounds__(BLOCK_THREADS) rays_kernel(const DeviceTree tree, const float* __restrict__ rays,
@@ -140,8 +178,14 @@ __global__ void lut_selftest_kernel(uint64_t* out) {
     }
 }
 
-cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig&, cudaStream_t stream) {
+cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig& cfg, cudaStream_t stream) {
     if (frame.rows_local == 0 || frame.width == 0) return cudaSuccess;
+    if (cfg.persistent && cfg.tile_counters) {
+        // blocks_x * blocks_y * 8 tickets cover the frame in 32x8 blocks; ragged edges are skipped inside the kernel
+        const unsigned grid = (unsigned)(cfg.sm_count * SVX_MIN_BLOCKS);
+        render_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+        return cudaGetLastError();
+    }
     dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
     render_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
     return cudaGetLastError();

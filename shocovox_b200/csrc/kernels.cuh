@@ -22,6 +22,7 @@ struct FrameParams {
     // pixels outside [cull_x0, cull_x1] x [cull_row0, cull_row1] (image coordinates, inclusive) certainly miss the root
     // cube: a conservative screen-space bound of the cube's projection computed on the host (capi.cu)
     uint32_t cull_x0, cull_x1, cull_row0, cull_row1;
+    uint32_t counter_slot; // persistent schedule: which of the two ticket counters this launch consumes
     uint32_t compact;      // 1: store shard-local row lr at output row lr (band-major compact buffer for gathers)
     uint32_t* hit_id;      // [h*w]
     uint32_t* albedo;      // [h*w]
@@ -39,6 +40,8 @@ struct RayHitRecord {
 
 struct LaunchConfig {
     int sm_count = 148;
+    bool persistent = false;          // warp-granular dynamic tile schedule instead of one CTA per 32x8 block
+    uint32_t* tile_counters = nullptr;  // device, two u32 ticket counters (ping-pong across launches)
 };
 
 cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig& cfg, cudaStream_t stream);
