@@ -152,7 +152,8 @@ SVX_API uint64_t svx_octree_node_count(const svx_octree* tree);
  * octree handle must outlive the host. */
 SVX_API int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host** out);
 SVX_API void svx_gpu_host_free(svx_gpu_host* host);
-/* Re-serialise and re-upload after the tree was edited (OctreeGPUView::reload, src/raytracing/bevy/mod.rs:56-60) */
+/* Re-serialise and re-upload after the tree was edited (OctreeGPUView::reload, src/raytracing/bevy/mod.rs:56-60).
+ * A no-op when the tree has not been modified since the last upload. */
 SVX_API int32_t svx_gpu_host_reload(svx_gpu_host* host);
 SVX_API int32_t svx_gpu_host_stats(const svx_gpu_host* host, svx_gpu_stats* out);
 /* Octree::get_by_ray (src/raytracing/raytracing_on_cpu.rs:316-318) for n rays at once, on the GPU.

@@ -490,6 +490,7 @@ void svx_gpu_host_free(svx_gpu_host* h) {
 int32_t svx_gpu_host_reload(svx_gpu_host* h) {
     if (!h) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(h->mu);
+    if (h->uploaded_revision == h->octree->tree->revision()) return SVX_OK;  // nothing was edited since the last upload
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
     return upload(h);

@@ -18,6 +18,9 @@ namespace svx {
 #ifndef SVX_MIN_BLOCKS
 #define SVX_MIN_BLOCKS (32 / (SVX_BLOCK_WARPS_X * SVX_BLOCK_WARPS_Y))  // 1024 threads (64 registers each) per SM
 #endif
+#ifndef SVX_TICKET_TILES
+#define SVX_TICKET_TILES 1u   // tiles per ticket of the persistent schedule (1, 2, 4 or 8); measured: 1 is best, larger tickets lengthen the tail
+#endif
 constexpr int TILE_W = 8 * SVX_BLOCK_WARPS_X;
 constexpr int TILE_H = 4 * SVX_BLOCK_WARPS_Y;
 constexpr int BLOCK_THREADS = 32 * SVX_BLOCK_WARPS_X * SVX_BLOCK_WARPS_Y;
@@ -109,18 +112,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel_p
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (f.width + 7u) >> 3, tiles_y = (f.rows_local + 3u) >> 2;
     const uint32_t blocks_x = (tiles_x + 3u) >> 2, blocks_y = (tiles_y + 1u) >> 1;
-    const uint32_t n_tickets = blocks_x * blocks_y * 8u;
+    // one ticket = SVX_TICKET_TILES consecutive tiles of a 32x8 pixel block (8 tiles): fewer atomics on the single
+    // counter (64 800 tiles at 1080p would serialise in L2), still much finer than a CTA of the static schedule
+    const uint32_t n_tickets = blocks_x * blocks_y * (8u / SVX_TICKET_TILES);
     for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&counters[f.counter_slot], 1u);
-        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-        if (tile >= n_tickets) return;
-        // tickets are numbered so that 8 consecutive ones form the same 32x8 pixel block a CTA of the static schedule
-        // covers (neighbouring warps share tree nodes and framebuffer sectors)
-        const uint32_t blk = tile >> 3, sub = tile & 7u;
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&counters[f.counter_slot], 1u);
+        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+        if (ticket >= n_tickets) return;
+        const uint32_t first = ticket * SVX_TICKET_TILES;
+        const uint32_t blk = first >> 3;
         const uint32_t bx = blk % blocks_x, by = blk / blocks_x;
-        const uint32_t ttx = (bx << 2) + (sub & 3u), tty = (by << 1) + (sub >> 2);
-        if (ttx < tiles_x && tty < tiles_y) shade_pixel(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
+#pragma unroll 1
+        for (uint32_t k = 0; k < SVX_TICKET_TILES; ++k) {
+            const uint32_t sub = (first & 7u) + k;
+            const uint32_t ttx = (bx << 2) + (sub & 3u), tty = (by << 1) + (sub >> 2);
+            if (ttx < tiles_x && tty < tiles_y) shade_pixel(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
+        }
     }
 }
 
