@@ -1,0 +1,109 @@
+// Host-side (no GPU) tests of the C++ mirror, written like the reference's own tests
+// (src/octree/update/tests.rs, src/octree/mod.rs). Build: see tests/test_cpp_mirror.py.
+#include <cstdio>
+#include <cstdlib>
+
+#include "shocovox_b200.hpp"
+
+using namespace svx;
+
+#define EXPECT(cond)                                                     \
+    do {                                                                 \
+        if (!(cond)) {                                                   \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            std::exit(1);                                                \
+        }                                                                \
+    } while (0)
+
+template <typename F>
+static svx_status error_of(F&& f) {
+    try {
+        f();
+    } catch (const OctreeError& e) {
+        return e.code;
+    }
+    return SVX_OK;
+}
+
+// update/tests.rs:20-46
+static void test_simple_insert_and_get() {
+    const Albedo red = Albedo::from(0xFF0000FF), green = Albedo::from(0x00FF00FF), blue = Albedo::from(0x0000FFFF);
+    Octree tree = Octree::create(2, 1);
+    tree.set_auto_simplify(false);
+    tree.insert({1, 0, 0}, red);
+    tree.insert({0, 1, 0}, green);
+    tree.insert({0, 0, 1}, blue);
+    EXPECT(tree.get({1, 0, 0}) == OctreeEntry::Visual(red));
+    EXPECT(tree.get({0, 1, 0}) == OctreeEntry::Visual(green));
+    EXPECT(tree.get({0, 0, 1}) == OctreeEntry::Visual(blue));
+    EXPECT(tree.get({1, 1, 1}) == OctreeEntry::Empty());
+    tree.insert({1, 0, 0}, green);
+    EXPECT(tree.get({1, 0, 0}) == OctreeEntry::Visual(green));
+}
+
+// update/tests.rs:57-110
+static void test_complex_insert_and_get() {
+    const Albedo red = Albedo::from(0xFF0000FF), green = Albedo::from(0x00FF00FF);
+    Octree tree = Octree::create(2, 1);
+    tree.set_auto_simplify(false);
+    tree.insert({1, 0, 0}, OctreeEntry::Complex(red, 3));
+    tree.insert({0, 1, 0}, OctreeEntry::Complex(green, 1));
+    tree.insert({0, 0, 1}, OctreeEntry::Informative(2));
+    EXPECT(tree.get({1, 0, 0}) == OctreeEntry::Complex(red, 3));
+    EXPECT(tree.get({0, 1, 0}) == OctreeEntry::Complex(green, 1));
+    EXPECT(tree.get({0, 0, 1}) == OctreeEntry::Informative(2));
+    tree.update({1, 0, 0}, OctreeEntry::Informative(4));  // update/tests.rs:376-388
+    EXPECT(tree.get({1, 0, 0}) == OctreeEntry::Complex(red, 4));
+}
+
+// update/tests.rs:143-191 and :1281-1315
+static void test_insert_and_clear_at_lod() {
+    const Albedo c = Albedo::from(0xFFAAEEFF);
+    Octree tree = Octree::create(8, 1);
+    tree.insert_at_lod({0, 0, 0}, 4, OctreeEntry::Visual(c));
+    tree.clear_at_lod({0, 0, 0}, 2);
+    int hits = 0;
+    for (uint32_t x = 0; x < 4; ++x)
+        for (uint32_t y = 0; y < 4; ++y)
+            for (uint32_t z = 0; z < 4; ++z) {
+                const OctreeEntry e = tree.get({x, y, z});
+                if (e.is_some()) {
+                    EXPECT(e == OctreeEntry::Visual(c));
+                    ++hits;
+                }
+            }
+    EXPECT(hits == 64 - 8);
+    tree.clear({3, 3, 3});
+    EXPECT(tree.get({3, 3, 3}).is_none());
+}
+
+// src/octree/mod.rs:173-187 (validation order), insert.rs:108-114
+static void test_errors() {
+    EXPECT(error_of([] { Octree::create(0, 8); }) == SVX_E_INVALID_BRICK_DIMENSION);
+    EXPECT(error_of([] { Octree::create(64, 3); }) == SVX_E_INVALID_BRICK_DIMENSION);
+    EXPECT(error_of([] { Octree::create(4, 8); }) == SVX_E_INVALID_SIZE);
+    EXPECT(error_of([] { Octree::create(8, 8); }) == SVX_E_INVALID_STRUCTURE);
+    Octree tree = Octree::create(4, 1);
+    EXPECT(error_of([&] { tree.insert({4, 0, 0}, Albedo::from(0xFF0000FF)); }) == SVX_E_INVALID_POSITION);
+    tree.insert({3, 0, 0}, Albedo{});  // an empty entry is a no-op Ok (insert.rs:117-119)
+    EXPECT(tree.get({3, 0, 0}).is_none());
+    EXPECT(tree.get_size() == 4);
+}
+
+// without a CUDA device the ray path must throw, never fall back to the CPU
+static void test_no_cpu_fallback() {
+    if (svx_cuda_device_count() > 0) return;
+    Octree tree = Octree::create(4, 1);
+    tree.insert({1, 1, 1}, Albedo::from(0xFF0000FF));
+    EXPECT(error_of([&] { OctreeGPUHost host(tree); }) == SVX_E_CUDA);
+}
+
+int main() {
+    test_simple_insert_and_get();
+    test_complex_insert_and_get();
+    test_insert_and_clear_at_lod();
+    test_errors();
+    test_no_cpu_fallback();
+    std::puts("octree_api_test: ok");
+    return 0;
+}
