@@ -185,6 +185,9 @@ void free_device_tree(svx_gpu_host* h) {
 int32_t upload(svx_gpu_host* h) {
     SerialisedTree s;
     serialise(*h->octree->tree, &s);
+    // the brick DDA addresses brick_bits with a 32-bit word offset (traverse.cuh: traverse_brick); 2^32 words are
+    // 2^37 voxels, far beyond what the u32 voxel array of the same tree could hold in 180 GB
+    if (s.brick_bits.size() > 0xFFFFFFFFull) return SVX_E_CUDA;
     free_device_tree(h);
     auto put = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));

@@ -130,43 +130,44 @@ __device__ __forceinline__ int clamp_index(float v, int dim) { return min(max(__
 __device__ __forceinline__ uint32_t bitmap_coord(float v) { return (uint32_t)min(max(__float2int_rd(v), 0), 3); }
 
 // traverse_brick, raytracing_on_cpu.rs:156-252. Walks the occupancy bit-brick (1 bit per voxel, set = not empty) and
-// returns the flat index of the first non-empty voxel or -1. The current 32-voxel word stays in a register.
+// returns the flat index (flat_projection, math/mod.rs:35-37) of the first non-empty voxel or -1.
+// The loop carries only what a step needs: the flat index (it addresses the bit and, on a hit, gives the voxel index
+// back), the current 32-voxel word in a register, and the min corner of the current cell. The reference's bounds check
+// on the integer index (:193-203) is done on that corner instead: corners are exact multiples of `unit` (integers),
+// every step moves a stepped axis by exactly one cell, so the walk has left the brick exactly when a corner equals
+// the first corner outside (min - unit going down, min + size going up).
 __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayConst& r, float& px, float& py, float& pz,
-                                              uint32_t brick, float bx, float by, float bz, float bsize,
-                                              float inv_size, int& hx, int& hy, int& hz) {
+                                              uint32_t brick, float bx, float by, float bz, float bsize, float inv_size) {
     const int dim = (int)t.brick_dim;
     const float fdim = (float)dim;
-    int ix = clamp_index((px - bx) * fdim * inv_size, dim);
-    int iy = clamp_index((py - by) * fdim * inv_size, dim);
-    int iz = clamp_index((pz - bz) * fdim * inv_size, dim);
+    const int ix = clamp_index((px - bx) * fdim * inv_size, dim);
+    const int iy = clamp_index((py - by) * fdim * inv_size, dim);
+    const int iz = clamp_index((pz - bz) * fdim * inv_size, dim);
     const float unit = bsize * t.inv_brick_dim;  // size / dim, exact: both powers of two
     float cx = bx + (float)ix * unit, cy = by + (float)iy * unit, cz = bz + (float)iz * unit;
     // `current_bounds.min_position += step * brick_unit`: step is +-1.0 or 0.0, so the addend is +-unit or +0
     const float ux = r.negx ? -unit : unit, uy = r.negy ? -unit : unit, uz = r.negz ? -unit : unit;
-    const uint32_t* bits = t.brick_bits + (size_t)brick * t.bit_words;
+    const float ex = r.negx ? bx - unit : bx + bsize, ey = r.negy ? by - unit : by + bsize, ez = r.negz ? bz - unit : bz + bsize;
     const uint32_t sh = t.brick_shift;
     // flat_projection(ix, iy, iz) kept incrementally, like the reference's current_flat_index (:205-207)
-    int flat = ix + (iy << sh) + (iz << (2 * sh));
-    const int fsx = r.isx, fsy = r.isy * (1 << sh), fsz = r.isz * (1 << (2 * sh));
-    int word_index = -1;
+    uint32_t flat = (uint32_t)ix + ((uint32_t)iy << sh) + ((uint32_t)iz << (2 * sh));
+    const uint32_t fsx = (uint32_t)r.isx, fsy = (uint32_t)(r.isy << sh), fsz = (uint32_t)(r.isz << (2 * sh));
+    const uint32_t base = brick * t.bit_words;  // word offset of this brick's bits; all bit words fit 32 bits (gpu_tree.cpp)
+    uint32_t word_index = 0xFFFFFFFFu;
     uint32_t word = 0u;
     for (;;) {
-        // index out of the brick on any axis: dim is a power of two, so OR-ing the three indices keeps a set sign bit
-        // (negative) or a set bit >= dim (one index reached dim) visible in a single unsigned compare
-        if ((uint32_t)(ix | iy | iz) >= (uint32_t)dim) return -1;
         if ((flat >> 5) != word_index) {
             word_index = flat >> 5;
-            word = __ldg(bits + word_index);
+            word = __ldg(t.brick_bits + (base + word_index));
         }
-        if ((word >> (flat & 31)) & 1u) {
-            hx = ix; hy = iy; hz = iz;
-            return flat;
-        }
+        if ((word >> (flat & 31u)) & 1u) return (int)flat;
         bool sx, sy, sz;
         dda_step(r, px, py, pz, cx, cy, cz, unit, sx, sy, sz);
-        if (sx) { cx = cx + ux; ix += r.isx; flat += fsx; }
-        if (sy) { cy = cy + uy; iy += r.isy; flat += fsy; }
-        if (sz) { cz = cz + uz; iz += r.isz; flat += fsz; }
+        flat += (sx ? fsx : 0u) + (sy ? fsy : 0u) + (sz ? fsz : 0u);
+        if (sx) cx = cx + ux;
+        if (sy) cy = cy + uy;
+        if (sz) cz = cz + uz;
+        if (cx == ex || cy == ey || cz == ez) return -1;
     }
 }
 
@@ -181,9 +182,10 @@ __device__ __forceinline__ bool probe_brick(const DeviceTree& t, const RayConst&
         out.bx = bx; out.by = by; out.bz = bz; out.bsize = bsize;
         return true;
     }
-    int hx, hy, hz;
-    const int flat = traverse_brick(t, r, px, py, pz, slot, bx, by, bz, bsize, inv_size, hx, hy, hz);
+    const int flat = traverse_brick(t, r, px, py, pz, slot, bx, by, bz, bsize, inv_size);
     if (flat < 0) return false;
+    const uint32_t dmask = t.brick_dim - 1u, sh = t.brick_shift;
+    const int hx = (int)((uint32_t)flat & dmask), hy = (int)(((uint32_t)flat >> sh) & dmask), hz = (int)((uint32_t)flat >> (2u * sh));
     out.palette_value = __ldg(t.voxels + ((size_t)slot << (3 * t.brick_shift)) + flat);
     out.px = px; out.py = py; out.pz = pz;
     // hit_bounds: min + idx * size / dim (the division is by a power of two), size / dim

@@ -22,6 +22,7 @@ CASES = {
     "terrain_512_8_4k": (lambda: scenes.terrain_scene(512, 8, 4321, 1, shell=4), lambda: scenes.terrain_camera(512), (3840, 2160)),
     "terrain_1024_8_1080p": (lambda: scenes.terrain_scene(1024, 8, 4321, 1, shell=4), lambda: scenes.orbit_cameras(1024, 256)[0], (1920, 1080)),
     "sponza_2048_32_4k": (lambda: scenes.colonnade_scene(2048, 32), lambda: scenes.colonnade_camera(2048), (3840, 2160)),
+    "minecraft_1024_32_4k": (lambda: scenes.terrain_scene(1024, 32, 1234, 4, shell=8, name="minecraft"), lambda: scenes.terrain_camera(1024), (3840, 2160)),
     "minecraft_256_32_4k": (lambda: scenes.terrain_scene(256, 32, 1234, 4, shell=8, name="minecraft"), lambda: scenes.terrain_camera(256), (3840, 2160)),
 }
 
