@@ -346,12 +346,13 @@ def main() -> int:
     try:
         import torch as _t  # plumbing only: pinned host buffers
 
-        bufs = [_t.empty(n_px, dtype=_t.int32).pin_memory(), _t.empty(n_px, dtype=_t.int32).pin_memory(),
-                _t.empty(n_px, dtype=_t.float32).pin_memory()]
-        ptrs = [b.data_ptr() for b in bufs]
+        bufs = [[_t.empty(n_px, dtype=_t.int32).pin_memory(), _t.empty(n_px, dtype=_t.int32).pin_memory(),
+                 _t.empty(n_px, dtype=_t.float32).pin_memory()] for _ in range(2)]
+        ptr_sets = [[b.data_ptr() for b in bs] for bs in bufs]
     except Exception:
-        bufs = [np.empty(n_px, dtype=np.uint32), np.empty(n_px, dtype=np.uint32), np.empty(n_px, dtype=np.float32)]
-        ptrs = [a.ctypes.data for a in bufs]
+        bufs = [[np.empty(n_px, dtype=np.uint32), np.empty(n_px, dtype=np.uint32), np.empty(n_px, dtype=np.float32)] for _ in range(2)]
+        ptr_sets = [[a.ctypes.data for a in bs] for bs in bufs]
+    ptrs = ptr_sets[0]
     e2e_view = view
     if tiles:  # end to end is measured on whole frames per rank (the public single-GPU call), not on shards
         e2e_view = host.create_new_view(64, vps[0], res)
@@ -369,13 +370,32 @@ def main() -> int:
     e1 = time.perf_counter()
     sampler.window(False)
     barrier()
+    e2e_sync_ms_total = (e1 - e0) * 1e3
+    # pipelined hand-over (svx_view_render_to_host_async): two pinned buffer sets, frame i's copies overlap frame i+1's
+    # kernel; every step still ends with the PREVIOUS step's frame complete in host memory, the last one after the loop
+    for i in range(3):
+        e2e_view.set_viewport(vps[pose_index(i)])
+        e2e_view.render_to_host_async_ptr(*ptr_sets[i & 1])
+        e2e_view.wait_host(1)
+    e2e_view.wait_host(0)
+    barrier()
+    sampler.window(True)
+    e0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_view.set_viewport(vps[pose_index(i)])
+        e2e_view.render_to_host_async_ptr(*ptr_sets[i & 1])
+        e2e_view.wait_host(1)
+    e2e_view.wait_host(0)
+    e1 = time.perf_counter()
+    sampler.window(False)
+    barrier()
     e2e_ms_total = (e1 - e0) * 1e3
     clocks = sampler.stop()
 
     if dist is not None:  # max over ranks
-        t = torch.tensor([dev_ms_total, warm_ms_total, e2e_ms_total], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([dev_ms_total, warm_ms_total, e2e_ms_total, e2e_sync_ms_total], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms_total, warm_ms_total, e2e_ms_total = [float(v) for v in t.tolist()]
+        dev_ms_total, warm_ms_total, e2e_ms_total, e2e_sync_ms_total = [float(v) for v in t.tolist()]
 
     frames_per_step = 1 if tiles else world
     total_rays = rays_per_frame * frames_per_step * args.steps
@@ -401,7 +421,11 @@ def main() -> int:
         "wall_ms_per_step_incl_flush": (wall1 - wall0) * 1e3 / args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 40, "d2h_bytes_per_step": 12 * n_px,
                 "ms_per_step": e2e_ms_total / args.steps,
-                "note": "view.set_viewport(pose) + view.render_to_host(pinned hit_id, albedo, distance); wall clock, synchronised every step"},
+                "synchronised_ms_per_step": e2e_sync_ms_total / args.steps,
+                "synchronised_value": rays_per_frame * world * args.steps / (e2e_sync_ms_total * 1e-3) / 1e6,
+                "note": "per step: view.set_viewport(pose) + view.render_to_host_async(pinned hit_id, albedo, distance) + wait for the "
+                        "previous frame; two pinned buffer sets, copies on a second stream overlap the next kernel; wall clock over all "
+                        "steps incl. the final drain. synchronised_* = the same with render_to_host and a stream sync every step"},
         "gpu_launches": int(args.steps),
         "gpu_launches_total_incl_warmup_and_e2e": int(view.launch_count() + (e2e_view.launch_count() if e2e_view is not view else 0)),
         "clocks": clocks,

@@ -194,6 +194,15 @@ SVX_API int32_t svx_view_set_peer_frame_ipc(svx_view* view, const uint8_t* handl
 SVX_API int32_t svx_view_render(svx_view* view, svx_frame* out);
 /* Same frame, delivered into HOST buffers (any may be null): includes the device->host copies. */
 SVX_API int32_t svx_view_render_to_host(svx_view* view, uint32_t* hit_id, uint32_t* albedo, float* distance);
+/* Pipelined variant: returns as soon as the kernel and the copies are queued. Frames alternate between two framebuffer
+ * slots; the copies run on a second stream, so frame i's device->host copy overlaps frame i+1's kernel. At most two
+ * frames are in flight (a third submission first waits for the oldest). The host buffers must stay valid, and are not
+ * complete, until svx_view_wait_host() has retired the frame. Replaces the frame hand-over of
+ * OctreeGPUView::output_texture (src/raytracing/bevy/mod.rs:84-88), which the reference leaves to Bevy's render graph. */
+SVX_API int32_t svx_view_render_to_host_async(svx_view* view, uint32_t* hit_id, uint32_t* albedo, float* distance);
+/* Blocks until at most `keep_in_flight` (0, 1) pipelined frames are outstanding, oldest first. kernel_ms_total
+ * (optional) receives and resets the summed CUDA-event kernel time of the frames retired since the last query. */
+SVX_API int32_t svx_view_wait_host(svx_view* view, uint32_t keep_in_flight, float* kernel_ms_total);
 /* Batch mode: n camera poses through the same view (pose-sharded rendering). Host output arrays are
  * [n][h*w] (any may be null). kernel_ms_total (optional) receives the summed CUDA-event kernel time. */
 SVX_API int32_t svx_view_render_batch(svx_view* view, const svx_viewport* poses, uint32_t n, uint32_t* hit_id,

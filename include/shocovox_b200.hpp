@@ -258,6 +258,15 @@ class OctreeGPUView {
         check(svx_view_render_to_host(h_, f.hit_id.data(), f.albedo.data(), f.distance.data()));
         return f;
     }
+    // pipelined frame into caller-owned (pinned) host planes; complete after wait_host() retired it
+    void render_to_host_async(uint32_t* hit_id, uint32_t* albedo, float* distance) {
+        check(svx_view_render_to_host_async(h_, hit_id, albedo, distance));
+    }
+    float wait_host(uint32_t keep_in_flight = 0) {
+        float ms = 0.0f;
+        check(svx_view_wait_host(h_, keep_in_flight, &ms));
+        return ms;
+    }
     svx_view* handle() const { return h_; }
 
    private:

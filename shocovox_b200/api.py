@@ -133,7 +133,7 @@ EXPORTS = [
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
     "svx_view_set_glass_mode", "svx_view_set_resolution", "svx_view_resolution", "svx_view_set_shard",
     "svx_view_set_schedule", "svx_view_set_compact_rows", "svx_view_frame_pointers", "svx_view_export_frame_ipc", "svx_view_set_peer_frame_ipc",
-    "svx_view_render", "svx_view_render_to_host", "svx_view_render_batch", "svx_view_cuda_stream", "svx_view_device",
+    "svx_view_render", "svx_view_render_to_host", "svx_view_render_to_host_async", "svx_view_wait_host", "svx_view_render_batch", "svx_view_cuda_stream", "svx_view_device",
     "svx_view_synchronize", "svx_view_timer_start", "svx_view_timer_stop", "svx_view_flush_l2", "svx_view_launch_count",
 ]
 
@@ -202,6 +202,8 @@ def lib() -> C.CDLL:
     L.svx_view_set_peer_frame_ipc.argtypes = [vp, vp]
     L.svx_view_render.argtypes = [vp, C.POINTER(_Frame)]
     L.svx_view_render_to_host.argtypes = [vp, vp, vp, vp]
+    L.svx_view_render_to_host_async.argtypes = [vp, vp, vp, vp]
+    L.svx_view_wait_host.argtypes = [vp, u32, C.POINTER(C.c_float)]
     L.svx_view_render_batch.argtypes = [vp, vp, u32, vp, vp, vp, C.POINTER(C.c_float)]
     L.svx_view_cuda_stream.argtypes = [vp]
     L.svx_view_cuda_stream.restype = vp
@@ -565,6 +567,18 @@ class OctreeGPUView:
     def render_to_host_ptr(self, hit_id_ptr: int, albedo_ptr: int, distance_ptr: int):
         """Same, into raw host pointers (0 = skip), e.g. torch pinned tensors' data_ptr()."""
         _check(lib().svx_view_render_to_host(self._h, hit_id_ptr or None, albedo_ptr or None, distance_ptr or None))
+
+    def render_to_host_async_ptr(self, hit_id_ptr: int, albedo_ptr: int, distance_ptr: int):
+        """Pipelined frame into raw (pinned) host pointers: returns once kernel and copies are queued. The buffers are
+        complete only after `wait_host` has retired the frame; at most two frames are in flight."""
+        _check(lib().svx_view_render_to_host_async(self._h, hit_id_ptr or None, albedo_ptr or None, distance_ptr or None))
+
+    def wait_host(self, keep_in_flight: int = 0) -> float:
+        """Blocks until at most `keep_in_flight` pipelined frames are outstanding; returns (and resets) the summed
+        kernel milliseconds of the frames retired since the last call."""
+        ms = C.c_float()
+        _check(lib().svx_view_wait_host(self._h, keep_in_flight, C.byref(ms)))
+        return float(ms.value)
 
     def render_batch(self, poses: Sequence[Viewport], want=("hit_id", "albedo", "distance")) -> dict:
         w, h = self.resolution()

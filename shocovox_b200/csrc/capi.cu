@@ -168,6 +168,17 @@ struct svx_view {
     uint32_t* d_albedo = nullptr;
     float* d_distance = nullptr;
     uint64_t launches = 0;
+    // Pipelined read-back (svx_view_render_to_host_async): two framebuffer slots (slot 0 = the planes above, slot 1 =
+    // alt_*), kernels on `stream`, device->host copies on `copy_stream`, so frame i's copy overlaps frame i+1's kernel.
+    cudaStream_t copy_stream = nullptr;
+    uint32_t* alt_hit_id = nullptr;
+    uint32_t* alt_albedo = nullptr;
+    float* alt_distance = nullptr;
+    cudaEvent_t slot_start[2] = {nullptr, nullptr}, slot_rendered[2] = {nullptr, nullptr}, slot_copied[2] = {nullptr, nullptr};
+    bool slot_busy[2] = {false, false};
+    uint64_t async_frames = 0;   // frames submitted through the pipelined path
+    float async_kernel_ms = 0.0f;  // summed kernel time of the pipelined frames retired so far
+    uint32_t target_slot = 0;    // which slot make_frame_constants points the kernel at
     std::mutex mu;
 };
 
@@ -311,17 +322,21 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
         }
     }
     f->compact = v->compact;
-    f->hit_id = v->use_peer ? (uint32_t*)v->peer_base[0] : v->d_hit_id;
-    f->albedo = v->use_peer ? (uint32_t*)v->peer_base[1] : v->d_albedo;
-    f->distance = v->use_peer ? (float*)v->peer_base[2] : v->d_distance;
+    const bool alt = v->target_slot == 1;
+    f->hit_id = v->use_peer ? (uint32_t*)v->peer_base[0] : (alt ? v->alt_hit_id : v->d_hit_id);
+    f->albedo = v->use_peer ? (uint32_t*)v->peer_base[1] : (alt ? v->alt_albedo : v->d_albedo);
+    f->distance = v->use_peer ? (float*)v->peer_base[2] : (alt ? v->alt_distance : v->d_distance);
 }
 
 int32_t alloc_frame(svx_view* v) {
     cudaFree(v->d_hit_id);
     cudaFree(v->d_albedo);
     cudaFree(v->d_distance);
-    v->d_hit_id = v->d_albedo = nullptr;
-    v->d_distance = nullptr;
+    cudaFree(v->alt_hit_id);
+    cudaFree(v->alt_albedo);
+    cudaFree(v->alt_distance);
+    v->d_hit_id = v->d_albedo = v->alt_hit_id = v->alt_albedo = nullptr;
+    v->d_distance = v->alt_distance = nullptr;
     const size_t n = (size_t)v->width * v->height;
     CUDA_TRY(cudaMalloc((void**)&v->d_hit_id, n * 4));
     CUDA_TRY(cudaMalloc((void**)&v->d_albedo, n * 4));
@@ -344,6 +359,79 @@ int32_t render_locked(svx_view* v) {
     CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
     CUDA_TRY(cudaEventRecord(v->ev_stop, v->stream));
     v->launches += 1;
+    return SVX_OK;
+}
+
+// Retires pipelined frames until at most `keep` are in flight (oldest first): blocks on the slot's copy-done event and
+// adds its kernel time to async_kernel_ms.
+int32_t retire_locked(svx_view* v, uint32_t keep) {
+    uint32_t busy = (v->slot_busy[0] ? 1u : 0u) + (v->slot_busy[1] ? 1u : 0u);
+    // submission order alternates slots; the older of two busy frames sits in the slot the NEXT submission would use
+    uint32_t k = (uint32_t)(v->async_frames & 1u);
+    for (int n = 0; n < 2 && busy > keep; ++n, k ^= 1u) {
+        if (!v->slot_busy[k]) continue;
+        CUDA_TRY(cudaEventSynchronize(v->slot_copied[k]));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, v->slot_start[k], v->slot_rendered[k]));
+        v->async_kernel_ms += ms;
+        v->slot_busy[k] = false;
+        --busy;
+    }
+    return SVX_OK;
+}
+
+int32_t ensure_pipeline(svx_view* v) {
+    if (!v->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CUDA_TRY(cudaEventCreate(&v->slot_start[k]));
+            CUDA_TRY(cudaEventCreate(&v->slot_rendered[k]));
+            CUDA_TRY(cudaEventCreateWithFlags(&v->slot_copied[k], cudaEventDisableTiming));
+        }
+    }
+    if (!v->alt_hit_id) {
+        const size_t n = (size_t)v->width * v->height;
+        CUDA_TRY(cudaMalloc((void**)&v->alt_hit_id, n * 4));
+        CUDA_TRY(cudaMalloc((void**)&v->alt_albedo, n * 4));
+        CUDA_TRY(cudaMalloc((void**)&v->alt_distance, n * 4));
+    }
+    return SVX_OK;
+}
+
+// One pipelined frame: kernel into the next slot on the render stream, copies of that slot on the copy stream.
+int32_t submit_async_locked(svx_view* v, uint32_t* hit_id, uint32_t* albedo, float* distance) {
+    if (v->use_peer) return fail(SVX_E_INVALID_ARGUMENT, "a view that stores into a peer framebuffer has no local frame to read back");
+    int32_t s = ensure_pipeline(v);
+    if (s != SVX_OK) return s;
+    const uint32_t k = (uint32_t)(v->async_frames & 1u);
+    if (v->slot_busy[k]) {  // the slot's previous frame must be on the host before the kernel overwrites it
+        s = retire_locked(v, 1);
+        if (s != SVX_OK) return s;
+    }
+    v->target_slot = k;
+    FrameParams f;
+    make_frame_constants(v, &f);
+    v->target_slot = 0;
+    LaunchConfig cfg = v->host->cfg;
+    cfg.persistent = v->persistent;
+    cfg.tile_counters = v->d_counters;
+    f.counter_slot = v->counter_slot;
+    if (v->persistent) v->counter_slot ^= 1u;
+    CUDA_TRY(cudaEventRecord(v->slot_start[k], v->stream));
+    CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
+    CUDA_TRY(cudaEventRecord(v->slot_rendered[k], v->stream));
+    v->launches += 1;
+    CUDA_TRY(cudaStreamWaitEvent(v->copy_stream, v->slot_rendered[k], 0));
+    const size_t bytes = (size_t)v->width * v->height * 4;
+    const uint32_t* src_hit = k ? v->alt_hit_id : v->d_hit_id;
+    const uint32_t* src_alb = k ? v->alt_albedo : v->d_albedo;
+    const float* src_dist = k ? v->alt_distance : v->d_distance;
+    if (hit_id) CUDA_TRY(cudaMemcpyAsync(hit_id, src_hit, bytes, cudaMemcpyDeviceToHost, v->copy_stream));
+    if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo, src_alb, bytes, cudaMemcpyDeviceToHost, v->copy_stream));
+    if (distance) CUDA_TRY(cudaMemcpyAsync(distance, src_dist, bytes, cudaMemcpyDeviceToHost, v->copy_stream));
+    CUDA_TRY(cudaEventRecord(v->slot_copied[k], v->copy_stream));
+    v->slot_busy[k] = true;
+    v->async_frames += 1;
     return SVX_OK;
 }
 
@@ -591,6 +679,16 @@ void svx_view_free(svx_view* v) {
     cudaFree(v->d_hit_id);
     cudaFree(v->d_albedo);
     cudaFree(v->d_distance);
+    if (v->copy_stream) cudaStreamSynchronize(v->copy_stream);
+    cudaFree(v->alt_hit_id);
+    cudaFree(v->alt_albedo);
+    cudaFree(v->alt_distance);
+    for (int k = 0; k < 2; ++k) {
+        if (v->slot_start[k]) cudaEventDestroy(v->slot_start[k]);
+        if (v->slot_rendered[k]) cudaEventDestroy(v->slot_rendered[k]);
+        if (v->slot_copied[k]) cudaEventDestroy(v->slot_copied[k]);
+    }
+    if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
     if (v->ev_start) cudaEventDestroy(v->ev_start);
     if (v->ev_stop) cudaEventDestroy(v->ev_stop);
     if (v->tm_start) cudaEventDestroy(v->tm_start);
@@ -624,6 +722,8 @@ int32_t svx_view_set_resolution(svx_view* v, uint32_t width, uint32_t height) {
     if (!v || width == 0 || height == 0) return fail(SVX_E_INVALID_ARGUMENT, "bad resolution");
     std::lock_guard<std::mutex> lock(v->mu);
     CUDA_TRY(cudaSetDevice(v->host->device));
+    const int32_t drained = retire_locked(v, 0);
+    if (drained != SVX_OK) return drained;
     CUDA_TRY(cudaStreamSynchronize(v->stream));
     v->width = width;
     v->height = height;
@@ -708,6 +808,8 @@ int32_t svx_view_render(svx_view* v, svx_frame* out) {
     if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(v->mu);
     CUDA_TRY(cudaSetDevice(v->host->device));
+    const int32_t drained = retire_locked(v, 0);
+    if (drained != SVX_OK) return drained;
     const int32_t s = render_locked(v);
     if (s != SVX_OK) return s;
     if (out) {
@@ -730,6 +832,8 @@ int32_t svx_view_render_to_host(svx_view* v, uint32_t* hit_id, uint32_t* albedo,
     if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(v->mu);
     CUDA_TRY(cudaSetDevice(v->host->device));
+    const int32_t drained = retire_locked(v, 0);
+    if (drained != SVX_OK) return drained;
     const int32_t s = render_locked(v);
     if (s != SVX_OK) return s;
     const size_t bytes = (size_t)v->width * v->height * 4;
@@ -740,26 +844,46 @@ int32_t svx_view_render_to_host(svx_view* v, uint32_t* hit_id, uint32_t* albedo,
     return SVX_OK;
 }
 
+int32_t svx_view_render_to_host_async(svx_view* v, uint32_t* hit_id, uint32_t* albedo, float* distance) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    return submit_async_locked(v, hit_id, albedo, distance);
+}
+
+int32_t svx_view_wait_host(svx_view* v, uint32_t keep_in_flight, float* kernel_ms_total) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    const int32_t s = retire_locked(v, keep_in_flight);
+    if (s != SVX_OK) return s;
+    if (kernel_ms_total) {
+        *kernel_ms_total = v->async_kernel_ms;
+        v->async_kernel_ms = 0.0f;
+    }
+    return SVX_OK;
+}
+
 int32_t svx_view_render_batch(svx_view* v, const svx_viewport* poses, uint32_t n, uint32_t* hit_id, uint32_t* albedo,
                               float* distance, float* kernel_ms_total) {
     if (!v || (n && !poses)) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(v->mu);
     CUDA_TRY(cudaSetDevice(v->host->device));
+    int32_t s = retire_locked(v, 0);
+    if (s != SVX_OK) return s;
+    v->async_kernel_ms = 0.0f;
     const size_t px = (size_t)v->width * v->height;
-    float total = 0.0f;
+    // pose i's device->host copies overlap pose i+1's kernel (two framebuffer slots)
     for (uint32_t i = 0; i < n; ++i) {
         v->viewport = poses[i];
-        const int32_t s = render_locked(v);
+        s = submit_async_locked(v, hit_id ? hit_id + i * px : nullptr, albedo ? albedo + i * px : nullptr,
+                                distance ? distance + i * px : nullptr);
         if (s != SVX_OK) return s;
-        if (hit_id) CUDA_TRY(cudaMemcpyAsync(hit_id + i * px, v->d_hit_id, px * 4, cudaMemcpyDeviceToHost, v->stream));
-        if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo + i * px, v->d_albedo, px * 4, cudaMemcpyDeviceToHost, v->stream));
-        if (distance) CUDA_TRY(cudaMemcpyAsync(distance + i * px, v->d_distance, px * 4, cudaMemcpyDeviceToHost, v->stream));
-        CUDA_TRY(cudaStreamSynchronize(v->stream));
-        float ms = 0.0f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, v->ev_start, v->ev_stop));
-        total += ms;
     }
-    if (kernel_ms_total) *kernel_ms_total = total;
+    s = retire_locked(v, 0);
+    if (s != SVX_OK) return s;
+    if (kernel_ms_total) *kernel_ms_total = v->async_kernel_ms;
+    v->async_kernel_ms = 0.0f;
     return SVX_OK;
 }
 

@@ -277,6 +277,56 @@ def test_render_is_deterministic_and_counts_launches():
     assert f["kernel_ms"] > 0 and f["hit_id"]
 
 
+def test_pipelined_read_back_delivers_the_same_frames():
+    """svx_view_render_to_host_async / svx_view_wait_host: frames alternate between two framebuffer slots and their
+    copies overlap the next kernel; every frame must equal the synchronous render of the same pose, also when
+    synchronous calls, a resize and the batch call are interleaved."""
+    import torch
+
+    scene = scenes.cpu_render_scene()
+    tree = scenes.build_tree(scene, S.Octree)
+    host = S.OctreeGPUHost(tree)
+    cams = [scenes.cpu_render_camera(k=k) for k in range(7)]
+    for res in ((320, 200), (157, 93)):
+        w, h = res
+        view = host.create_new_view(1, viewport(cams[0]), (64, 64))
+        view.set_resolution((w, h))
+        want = []
+        for c in cams:
+            view.set_viewport(viewport(c))
+            want.append({k: v.copy() for k, v in view.render_to_host().items()})
+        sets = [[torch.empty(w * h, dtype=torch.int32).pin_memory(), torch.empty(w * h, dtype=torch.int32).pin_memory(),
+                 torch.empty(w * h, dtype=torch.float32).pin_memory()] for _ in range(2)]
+        n0 = view.launch_count()
+        got = []
+        for i, c in enumerate(cams):
+            view.set_viewport(viewport(c))
+            view.render_to_host_async_ptr(*[b.data_ptr() for b in sets[i & 1]])
+            view.wait_host(1)  # frame i-1 is complete now
+            if i >= 1:
+                got.append([b.numpy().copy() for b in sets[(i - 1) & 1]])
+        assert view.wait_host(0) >= 0.0
+        got.append([b.numpy().copy() for b in sets[(len(cams) - 1) & 1]])
+        assert view.launch_count() == n0 + len(cams)
+        for i, (g, wnt) in enumerate(zip(got, want)):
+            assert np.array_equal(g[0].view(np.uint32).reshape(h, w), wnt["hit_id"]), (res, i)
+            assert np.array_equal(g[1].view(np.uint32).reshape(h, w), wnt["albedo"]), (res, i)
+            assert np.array_equal(bits(g[2].reshape(h, w)), bits(wnt["distance"])), (res, i)
+        # a synchronous call right after queued frames drains them first and still sees its own pose
+        view.set_viewport(viewport(cams[3]))
+        view.render_to_host_async_ptr(*[b.data_ptr() for b in sets[0]])
+        view.set_viewport(viewport(cams[5]))
+        sync = view.render_to_host()
+        assert np.array_equal(sync["hit_id"], want[5]["hit_id"])
+        assert np.array_equal(sets[0][0].numpy().view(np.uint32).reshape(h, w), want[3]["hit_id"])
+        # the batch call rides on the same pipeline
+        batch = view.render_batch([viewport(c) for c in cams])
+        for i, wnt in enumerate(want):
+            assert np.array_equal(batch["hit_id"][i], wnt["hit_id"]), (res, i)
+            assert np.array_equal(bits(batch["distance"][i]), bits(wnt["distance"])), (res, i)
+        assert batch["kernel_ms"] > 0
+
+
 def test_crawl_fast_forward_is_exact_on_a_large_tree():
     """rays that skim over a 512^3 terrain take thousands of 0.1-nudge restarts; the kernel fast-forwards
     them in closed form and must still land on the oracle's bits."""
