@@ -90,6 +90,30 @@ static void test_errors() {
     EXPECT(tree.get_size() == 4);
 }
 
+// src/convert/bytecode_tests.rs:182-222 (test_octree_file_io) through the C++ mirror, plus the error paths
+static void test_save_load() {
+    const Albedo red = Albedo::from(0xFF0000FF);
+    Octree tree = Octree::create(8, 1);
+    tree.insert_at_lod({0, 0, 0}, 4, OctreeEntry::Visual(red));
+    tree.clear_at_lod({0, 0, 0}, 2);
+    tree.save("test_junk_octree_cpp");
+    Octree copy = Octree::load("test_junk_octree_cpp");
+    std::remove("test_junk_octree_cpp");
+    int hits = 0;
+    for (uint32_t x = 0; x < 4; ++x)
+        for (uint32_t y = 0; y < 4; ++y)
+            for (uint32_t z = 0; z < 4; ++z) {
+                EXPECT(tree.get({x, y, z}) == copy.get({x, y, z}));
+                if (copy.get({x, y, z}).is_some()) ++hits;
+            }
+    EXPECT(hits == 64 - 8);
+    EXPECT(copy.structure_hash() == tree.structure_hash());
+    const std::vector<uint8_t> bytes = tree.to_bytes();
+    EXPECT(Octree::from_bytes(bytes).to_bytes() == bytes);
+    EXPECT(error_of([] { Octree::load("no/such/file"); }) == SVX_E_IO);
+    EXPECT(error_of([&] { Octree::from_bytes(std::vector<uint8_t>(bytes.begin(), bytes.end() - 3)); }) == SVX_E_DECODE);
+}
+
 // without a CUDA device the ray path must throw, never fall back to the CPU
 static void test_no_cpu_fallback() {
     if (svx_cuda_device_count() > 0) return;
@@ -103,6 +127,7 @@ int main() {
     test_complex_insert_and_get();
     test_insert_and_clear_at_lod();
     test_errors();
+    test_save_load();
     test_no_cpu_fallback();
     std::puts("octree_api_test: ok");
     return 0;

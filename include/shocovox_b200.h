@@ -34,6 +34,8 @@ typedef enum svx_status {
     SVX_E_INVALID_STRUCTURE = 3,       /* OctreeError::InvalidStructure       */
     SVX_E_INVALID_POSITION = 4,        /* OctreeError::InvalidPosition        */
     SVX_E_INVALID_ARGUMENT = 5,        /* null handle / bad enum / zero resolution */
+    SVX_E_DECODE = 6,                  /* from_bytes / load: not a bencoded Octree (the reference panics, octree/mod.rs:147) */
+    SVX_E_IO = 7,                      /* save / load: std::io::Error */
     SVX_E_CUDA = -1,                   /* CUDA runtime error (svx_last_error_message has the text) */
     SVX_E_OUT_OF_MEMORY = -2
 } svx_status;
@@ -145,6 +147,16 @@ SVX_API int32_t svx_octree_set_auto_simplify(svx_octree* tree, int32_t enabled);
 /* Key-order independent digest of the reachable tree (node kinds, occupancy bits, bricks, palettes) */
 SVX_API uint64_t svx_octree_structure_hash(const svx_octree* tree);
 SVX_API uint64_t svx_octree_node_count(const svx_octree* tree);
+/* Octree::to_bytes / from_bytes / save / load, src/octree/mod.rs:138-168: the bencode byte format of
+ * src/convert/bytecode.rs (a tree saved by the Rust crate loads here and the other way round; MIP bricks in a file
+ * are skipped, MIP maps are written as disabled). to_bytes hands out a library-owned buffer: release it with
+ * svx_bytes_free. from_bytes / load validate size and brick_dim like Octree::new and return SVX_E_DECODE on
+ * malformed input, SVX_E_IO when the file cannot be read or written. */
+SVX_API int32_t svx_octree_to_bytes(const svx_octree* tree, uint8_t** bytes, uint64_t* len);
+SVX_API void svx_bytes_free(uint8_t* bytes);
+SVX_API int32_t svx_octree_from_bytes(const uint8_t* bytes, uint64_t len, svx_octree** out);
+SVX_API int32_t svx_octree_save(const svx_octree* tree, const char* path);
+SVX_API int32_t svx_octree_load(const char* path, svx_octree** out);
 
 /* ---- OctreeGPUHost: render-data upload ---------------------------------------------------------------- */
 /* OctreeGPUHost{tree}, src/raytracing/bevy/types.rs:80-87. Serialises the WHOLE tree into coalesced SoA

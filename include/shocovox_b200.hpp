@@ -36,6 +36,8 @@ struct OctreeError : std::runtime_error {
             case SVX_E_INVALID_STRUCTURE: return "InvalidStructure";
             case SVX_E_INVALID_POSITION: return "InvalidPosition";
             case SVX_E_INVALID_ARGUMENT: return "InvalidArgument";
+            case SVX_E_DECODE: return "Decode";
+            case SVX_E_IO: return "Io";
             case SVX_E_CUDA: return "Cuda";
             case SVX_E_OUT_OF_MEMORY: return "OutOfMemory";
             default: return "Unknown";
@@ -155,6 +157,26 @@ class Octree {
     uint32_t get_size() const { return svx_octree_size(h_); }
     void set_auto_simplify(bool v) { check(svx_octree_set_auto_simplify(h_, v ? 1 : 0)); }  // pub auto_simplify
     uint64_t structure_hash() const { return svx_octree_structure_hash(h_); }
+    // Octree::to_bytes / from_bytes / save / load (bencode, src/octree/mod.rs:138-168)
+    std::vector<uint8_t> to_bytes() const {
+        uint8_t* p = nullptr;
+        uint64_t n = 0;
+        check(svx_octree_to_bytes(h_, &p, &n));
+        std::vector<uint8_t> out(p, p + n);
+        svx_bytes_free(p);
+        return out;
+    }
+    static Octree from_bytes(const std::vector<uint8_t>& bytes) {
+        Octree t;
+        check(svx_octree_from_bytes(bytes.data(), bytes.size(), &t.h_));
+        return t;
+    }
+    void save(const std::string& path) const { check(svx_octree_save(h_, path.c_str())); }
+    static Octree load(const std::string& path) {
+        Octree t;
+        check(svx_octree_load(path.c_str(), &t.h_));
+        return t;
+    }
     svx_octree* handle() const { return h_; }
 
    private:

@@ -17,6 +17,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -212,6 +213,11 @@ class Octree {
     bool probe_brick(const Ray& ray, V3f& p, const Brick& brick, const Cube& bounds, const V3f& scale, Hit& out,
                      RayStats* st) const;
 };
+
+// bencode persistence, src/convert/bytecode.rs + src/octree/mod.rs:138-148 (svx_oracle_bytecode.cpp); from_bytes
+// returns status 6 for bytes that are not an encoded Octree
+std::string octree_to_bytes(const Octree& t);
+Status octree_from_bytes(const uint8_t* data, size_t len, Octree** out);
 
 // ---- spatial functions (exposed for known-answer tests)
 uint8_t hash_region(V3f offset, float size_half);                    // src/spatial/math/mod.rs:11-19

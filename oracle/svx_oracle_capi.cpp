@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -155,6 +156,22 @@ int32_t svxo_octree_describe_path(void* tp, uint32_t x, uint32_t y, uint32_t z, 
     snprintf(out, cap, "%s", s.c_str());
     return (int32_t)s.size();
 }
+// Octree::to_bytes / from_bytes (src/octree/mod.rs:138-148). The buffer is malloc'ed: release with svxo_bytes_free.
+int32_t svxo_octree_to_bytes(void* t, uint8_t** bytes, uint64_t* len) {
+    const std::string s = octree_to_bytes(*(Octree*)t);
+    *bytes = (uint8_t*)std::malloc(s.size() ? s.size() : 1);
+    std::memcpy(*bytes, s.data(), s.size());
+    *len = s.size();
+    return 0;
+}
+void svxo_bytes_free(uint8_t* bytes) { std::free(bytes); }
+int32_t svxo_octree_from_bytes(const uint8_t* bytes, uint64_t len, void** out) {
+    Octree* t = nullptr;
+    const Status s = octree_from_bytes(bytes, (size_t)len, &t);
+    *out = t;
+    return s;
+}
+
 uint64_t svxo_octree_structure_hash(void* t) { return ((Octree*)t)->structure_hash(); }
 uint64_t svxo_octree_node_count(void* t) { return ((Octree*)t)->nodes.len(); }
 uint64_t svxo_octree_palette_sizes(void* t, uint64_t* n_data) {

@@ -27,6 +27,8 @@ E_INVALID_BRICK_DIMENSION = 2
 E_INVALID_STRUCTURE = 3
 E_INVALID_POSITION = 4
 E_INVALID_ARGUMENT = 5
+E_DECODE = 6
+E_IO = 7
 E_CUDA = -1
 E_OUT_OF_MEMORY = -2
 
@@ -44,6 +46,8 @@ class OctreeError(Exception):
         E_INVALID_STRUCTURE: "InvalidStructure",
         E_INVALID_POSITION: "InvalidPosition",
         E_INVALID_ARGUMENT: "InvalidArgument",
+        E_DECODE: "Decode",
+        E_IO: "Io",
         E_CUDA: "Cuda",
         E_OUT_OF_MEMORY: "OutOfMemory",
     }
@@ -129,6 +133,7 @@ EXPORTS = [
     "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
     "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
     "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count",
+    "svx_octree_to_bytes", "svx_bytes_free", "svx_octree_from_bytes", "svx_octree_save", "svx_octree_load",
     "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
     "svx_view_set_glass_mode", "svx_view_set_resolution", "svx_view_resolution", "svx_view_set_shard",
@@ -176,6 +181,12 @@ def lib() -> C.CDLL:
     L.svx_octree_brick_dim.argtypes = [vp]
     L.svx_octree_brick_dim.restype = u32
     L.svx_octree_set_auto_simplify.argtypes = [vp, i32]
+    L.svx_octree_to_bytes.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.svx_bytes_free.argtypes = [vp]
+    L.svx_bytes_free.restype = None
+    L.svx_octree_from_bytes.argtypes = [C.c_char_p, u64, C.POINTER(vp)]
+    L.svx_octree_save.argtypes = [vp, C.c_char_p]
+    L.svx_octree_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.svx_octree_structure_hash.argtypes = [vp]
     L.svx_octree_structure_hash.restype = u64
     L.svx_octree_node_count.argtypes = [vp]
@@ -417,6 +428,36 @@ class Octree:
 
     def node_count(self) -> int:
         return int(lib().svx_octree_node_count(self._h))
+
+    # ---- bencode persistence, src/octree/mod.rs:138-168 ----
+    @classmethod
+    def _adopt(cls, handle: C.c_void_p) -> "Octree":
+        t = cls.__new__(cls)
+        t._h = handle
+        return t
+
+    def to_bytes(self) -> bytes:
+        buf, n = C.c_void_p(), C.c_uint64()
+        _check(lib().svx_octree_to_bytes(self._h, C.byref(buf), C.byref(n)))
+        try:
+            return C.string_at(buf, n.value)
+        finally:
+            lib().svx_bytes_free(buf)
+
+    @classmethod
+    def from_bytes(cls, data: bytes) -> "Octree":
+        h = C.c_void_p()
+        _check(lib().svx_octree_from_bytes(bytes(data), len(data), C.byref(h)))
+        return cls._adopt(h)
+
+    def save(self, path: str):
+        _check(lib().svx_octree_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str) -> "Octree":
+        h = C.c_void_p()
+        _check(lib().svx_octree_load(str(path).encode(), C.byref(h)))
+        return cls._adopt(h)
 
     # `Octree::get_by_ray(&Ray)`: one ray, on the GPU (a host is created on first use and reloaded after edits)
     def get_by_ray(self, ray: Ray, device: int = 0) -> Optional[RayHit]:

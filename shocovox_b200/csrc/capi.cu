@@ -527,6 +527,49 @@ int32_t svx_octree_set_auto_simplify(svx_octree* t, int32_t enabled) {
 uint64_t svx_octree_structure_hash(const svx_octree* t) { return t ? t->tree->structure_hash() : 0; }
 uint64_t svx_octree_node_count(const svx_octree* t) { return t ? t->tree->nodes().size() : 0; }
 
+int32_t svx_octree_to_bytes(const svx_octree* t, uint8_t** bytes, uint64_t* len) {
+    if (!t || !bytes || !len) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::string s;
+    t->tree->to_bytes(&s);
+    uint8_t* buf = (uint8_t*)std::malloc(s.size() ? s.size() : 1);
+    if (!buf) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
+    std::memcpy(buf, s.data(), s.size());
+    *bytes = buf;
+    *len = s.size();
+    return SVX_OK;
+}
+void svx_bytes_free(uint8_t* bytes) { std::free(bytes); }
+static int32_t wrap_tree(int32_t status, HostOctree* tree, svx_octree** out, const char* what) {
+    if (status != SVX_OK) return fail(status, what);
+    svx_octree* t = new (std::nothrow) svx_octree();
+    if (!t) {
+        delete tree;
+        return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
+    }
+    t->tree = tree;
+    *out = t;
+    return SVX_OK;
+}
+int32_t svx_octree_from_bytes(const uint8_t* bytes, uint64_t len, svx_octree** out) {
+    if (!bytes || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    HostOctree* tree = nullptr;
+    const int32_t s = HostOctree::from_bytes(bytes, (size_t)len, &tree);
+    return wrap_tree(s, tree, out, "not a bencoded Octree");
+}
+int32_t svx_octree_save(const svx_octree* t, const char* path) {
+    if (!t || !path) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    const int32_t s = t->tree->save(path);
+    return s == SVX_OK ? SVX_OK : fail(s, "cannot write the file");
+}
+int32_t svx_octree_load(const char* path, svx_octree** out) {
+    if (!path || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    HostOctree* tree = nullptr;
+    const int32_t s = HostOctree::load(path, &tree);
+    return wrap_tree(s, tree, out, "cannot load an Octree from the file");
+}
+
 // ---- gpu host -------------------------------------------------------------------------------------------------
 int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host** out) {
     if (!tree || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");

@@ -12,6 +12,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -54,6 +55,11 @@ class HostOctree {
     int32_t clear_at_lod(uint32_t x, uint32_t y, uint32_t z, uint32_t clear_size);  // src/octree/update/clear.rs:55-348
     svx_entry get(uint32_t x, uint32_t y, uint32_t z) const;
     uint64_t structure_hash() const;
+    // bencode persistence in the reference's byte format (host_octree_io.cpp; src/octree/mod.rs:138-168)
+    void to_bytes(std::string* out) const;
+    static int32_t from_bytes(const uint8_t* data, size_t len, HostOctree** out);
+    int32_t save(const char* path) const;
+    static int32_t load(const char* path, HostOctree** out);
 
     uint32_t size() const { return size_; }
     uint32_t brick_dim() const { return dim_; }

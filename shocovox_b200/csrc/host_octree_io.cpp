@@ -1,0 +1,468 @@
+// Bencode persistence of the host octree: Octree::to_bytes / from_bytes / save / load of the reference
+// (src/octree/mod.rs:138-168) in the byte format its ToBencode / FromBencode impls define
+// (src/convert/bytecode.rs, src/object_pool.rs:25-137), so a tree saved by the Rust crate can be rendered here and
+// the other way round. `file:line` citations are relative to the reference checkout.
+//
+// Bencode (the `bendy` crate, Cargo.toml:19): integer = i<decimal>e, byte string = <len>:<bytes>, list = l<items>e.
+//
+//   Octree        = l i<auto_simplify> i<octree_size> i<brick_dim> NODES CHILDREN MIPS COLORS DATAS STRATEGY e   (bytecode.rs:579-598)
+//   NODES         = l i<first_available> l ITEM* e e            ObjectPool (object_pool.rs:97-108)
+//   ITEM          = l i<reserved> CONTENT e                     ReusableItem (object_pool.rs:25-36)
+//   CONTENT       = 1:#  |  l 2:## i<occupied_bits> e  |  l 3:### BRICK x8 e  |  l 4:##u# BRICK e   (bytecode.rs:166-196)
+//   BRICK         = 2:#b  |  l 3:#b# i<voxel> e  |  l 4:##b# i<len> i<voxel>*len 1:# e              (bytecode.rs:67-91)
+//   CHILDREN      = l ( 5:##x##  |  l 5:##c## i<key> x8 e  |  l 5:##b## i<bitmap> e )* e            (bytecode.rs:289-311)
+//   MIPS          = l BRICK* e                                  one per node; MIP maps are not built here: all 2:#b
+//   COLORS        = l ( l i<r> i<g> i<b> i<a> e )* e            (bytecode.rs:11-22)
+//   DATAS         = l i<u32>* e                                 Octree<T = u32>
+//   STRATEGY      = l i<enabled> i<n> (i<level> i<method>)*n i<m> (i<level> i<threshold*1000>)*m e    (bytecode.rs:343-363)
+//
+// The reference writes the two strategy maps in HashMap iteration order (random per process); we write them sorted
+// by level. MIP bricks found in a loaded file are skipped and the strategy is stored as disabled: this build
+// renders get_by_ray (MIPs off), see DESIGN.md.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "host_octree.hpp"
+
+namespace svx {
+
+namespace {
+
+struct Writer {
+    std::string& s;
+    void integer(uint64_t v) {
+        char buf[24];
+        int n = 0;
+        do {
+            buf[n++] = (char)('0' + v % 10);
+            v /= 10;
+        } while (v);
+        s.push_back('i');
+        while (n) s.push_back(buf[--n]);
+        s.push_back('e');
+    }
+    void str(const char* lit) {
+        const size_t n = std::strlen(lit);
+        s.append(std::to_string(n));
+        s.push_back(':');
+        s.append(lit, n);
+    }
+    void open() { s.push_back('l'); }
+    void close() { s.push_back('e'); }
+};
+
+struct Reader {
+    const uint8_t* p;
+    const uint8_t* end;
+    bool ok = true;
+
+    bool fail() {
+        ok = false;
+        return false;
+    }
+    bool peek_list() const { return p < end && *p == 'l'; }
+    bool peek_int() const { return p < end && *p == 'i'; }
+    bool peek_bytes() const { return p < end && *p >= '0' && *p <= '9'; }
+    bool at_close() const { return p < end && *p == 'e'; }
+    bool open() {
+        if (!peek_list()) return fail();
+        ++p;
+        return true;
+    }
+    bool close() {
+        if (!at_close()) return fail();
+        ++p;
+        return true;
+    }
+    bool integer(uint64_t* out) {
+        if (!peek_int()) return fail();
+        ++p;
+        uint64_t v = 0;
+        bool any = false;
+        while (p < end && *p >= '0' && *p <= '9') {
+            const uint64_t d = (uint64_t)(*p - '0');
+            if (v > (UINT64_MAX - d) / 10) return fail();
+            v = v * 10 + d;
+            ++p;
+            any = true;
+        }
+        if (!any || p >= end || *p != 'e') return fail();  // no negative numbers anywhere in the format
+        ++p;
+        *out = v;
+        return true;
+    }
+    bool bytes(const char** s, size_t* n) {
+        if (!peek_bytes()) return fail();
+        size_t len = 0;
+        while (p < end && *p >= '0' && *p <= '9') {
+            if (len > (SIZE_MAX - 9) / 10) return fail();
+            len = len * 10 + (size_t)(*p - '0');
+            ++p;
+        }
+        if (p >= end || *p != ':') return fail();
+        ++p;
+        if ((size_t)(end - p) < len) return fail();
+        *s = (const char*)p;
+        *n = len;
+        p += len;
+        return true;
+    }
+    bool marker(const char* lit) {
+        const char* s;
+        size_t n;
+        if (!bytes(&s, &n)) return false;
+        if (n != std::strlen(lit) || std::memcmp(s, lit, n) != 0) return fail();
+        return true;
+    }
+    // skips one item of any type
+    bool skip() {
+        if (peek_int()) {
+            uint64_t v;
+            return integer(&v);
+        }
+        if (peek_bytes()) {
+            const char* s;
+            size_t n;
+            return bytes(&s, &n);
+        }
+        if (!open()) return false;
+        while (ok && !at_close()) {
+            if (p >= end) return fail();
+            if (!skip()) return false;
+        }
+        return close();
+    }
+};
+
+bool is_marker(const char* s, size_t n, const char* lit) { return n == std::strlen(lit) && std::memcmp(s, lit, n) == 0; }
+
+}  // namespace
+
+// ---- encode ---------------------------------------------------------------------------------------------------
+void HostOctree::to_bytes(std::string* out) const {
+    out->clear();
+    Writer w{*out};
+    auto brick = [&](const BrickRef& b) {  // bytecode.rs:67-91
+        if (b.kind == BK_EMPTY) {
+            w.str("#b");
+        } else if (b.kind == BK_SOLID) {
+            w.open();
+            w.str("#b#");
+            w.integer(b.value);
+            w.close();
+        } else {
+            const uint32_t* v = brick_data(b.value);
+            w.open();
+            w.str("##b#");
+            w.integer(vol_);
+            for (uint32_t i = 0; i < vol_; ++i) w.integer(v[i]);
+            w.str("#");
+            w.close();
+        }
+    };
+    w.open();
+    w.integer(auto_simplify ? 1 : 0);
+    w.integer(size_);
+    w.integer(dim_);
+    // nodes: ObjectPool { first_available, buffer } (object_pool.rs:97-108)
+    w.open();
+    w.integer(first_available_);
+    w.open();
+    for (const NodeRec& n : nodes_) {
+        w.open();
+        w.integer(n.reserved ? 1 : 0);
+        switch (n.kind) {  // bytecode.rs:166-196
+            case NK_INTERNAL:
+                w.open();
+                w.str("##");
+                w.integer(n.ocbits);
+                w.close();
+                break;
+            case NK_LEAF:
+                w.open();
+                w.str("###");
+                for (int o = 0; o < 8; ++o) brick(n.brick[o]);
+                w.close();
+                break;
+            case NK_UNIFORM:
+                w.open();
+                w.str("##u#");
+                brick(n.brick[0]);
+                w.close();
+                break;
+            default: w.str("#"); break;
+        }
+        w.close();
+    }
+    w.close();
+    w.close();
+    // node_children (bytecode.rs:289-311)
+    w.open();
+    for (const NodeRec& n : nodes_) {
+        if (n.link == LK_CHILDREN) {
+            w.open();
+            w.str("##c##");
+            for (int o = 0; o < 8; ++o) w.integer(n.child[o]);
+            w.close();
+        } else if (n.link == LK_BITMAP) {
+            w.open();
+            w.str("##b##");
+            w.integer(n.leaf_bits);
+            w.close();
+        } else {
+            w.str("##x##");
+        }
+    }
+    w.close();
+    // node_mips: one BrickData::Empty per node (MIP maps stay disabled, mipmap.rs:591-604)
+    w.open();
+    for (size_t i = 0; i < nodes_.size(); ++i) w.str("#b");
+    w.close();
+    w.open();
+    for (const svx_albedo& a : colors_) {  // bytecode.rs:11-22
+        w.open();
+        w.integer(a.r);
+        w.integer(a.g);
+        w.integer(a.b);
+        w.integer(a.a);
+        w.close();
+    }
+    w.close();
+    w.open();
+    for (uint32_t d : datas_) w.integer(d);
+    w.close();
+    // MIPMapStrategy::default() with enabled = false (mipmap.rs:591-604), thresholds as `(thr * 1000.) as u32`
+    w.open();
+    w.integer(0);
+    w.integer(4);
+    const uint64_t methods[4][2] = {{1, 1}, {2, 0}, {3, 0}, {4, 0}};  // 1: PointFilter, 2..4: BoxFilter (bytecode.rs:436-450)
+    for (auto& m : methods) {
+        w.integer(m[0]);
+        w.integer(m[1]);
+    }
+    w.integer(3);
+    const uint64_t thr[3][2] = {{2, 100}, {3, 50}, {4, 20}};
+    for (auto& t : thr) {
+        w.integer(t[0]);
+        w.integer(t[1]);
+    }
+    w.close();
+    w.close();
+}
+
+// ---- decode ---------------------------------------------------------------------------------------------------
+int32_t HostOctree::from_bytes(const uint8_t* data, size_t len, HostOctree** out) {
+    *out = nullptr;
+    if (!data) return SVX_E_DECODE;
+    Reader r{data, data + len};
+    uint64_t auto_simplify = 0, size = 0, dim = 0;
+    if (!r.open() || !r.integer(&auto_simplify) || !r.integer(&size) || !r.integer(&dim)) return SVX_E_DECODE;
+    if (auto_simplify > 1 || size > 0xFFFFFFFFull || dim > 0xFFFFFFFFull) return SVX_E_DECODE;
+    HostOctree* t = nullptr;
+    const int32_t created = create((uint32_t)size, (uint32_t)dim, &t);  // the same validation as Octree::new
+    if (created != SVX_OK) return created;
+    struct Guard {
+        HostOctree* t;
+        ~Guard() { delete t; }
+    } guard{t};
+    t->auto_simplify = auto_simplify == 1;
+    t->nodes_.clear();
+
+    auto brick = [&](BrickRef* b) -> bool {  // bytecode.rs:94-160
+        b->kind = BK_EMPTY;
+        b->value = NIL;
+        if (r.peek_bytes()) return r.marker("#b");
+        if (!r.open()) return false;
+        const char* s;
+        size_t n;
+        if (!r.bytes(&s, &n)) return false;
+        if (is_marker(s, n, "#b#")) {
+            uint64_t v;
+            if (!r.integer(&v) || v > 0xFFFFFFFFull) return r.fail();
+            b->kind = BK_SOLID;
+            b->value = (uint32_t)v;
+        } else if (is_marker(s, n, "##b#")) {
+            uint64_t count;
+            if (!r.integer(&count) || count != t->vol_) return r.fail();
+            const uint32_t h = t->brick_alloc(NIL);
+            b->kind = BK_PARTED;
+            b->value = h;
+            uint32_t* v = t->brick_mut(h);
+            for (uint32_t i = 0; i < t->vol_; ++i) {
+                uint64_t x;
+                if (!r.integer(&x) || x > 0xFFFFFFFFull) return r.fail();
+                v[i] = (uint32_t)x;
+            }
+            if (r.peek_bytes() && !r.marker("#")) return false;  // trailing "#" (the decoder of the reference ignores it)
+        } else {
+            return r.fail();
+        }
+        return r.close();
+    };
+
+    // nodes
+    uint64_t first_available = 0;
+    if (!r.open() || !r.integer(&first_available) || !r.open()) return SVX_E_DECODE;
+    while (r.ok && !r.at_close()) {
+        NodeRec n;
+        uint64_t reserved;
+        if (!r.open() || !r.integer(&reserved) || reserved > 1) return SVX_E_DECODE;
+        n.reserved = (uint8_t)reserved;
+        if (r.peek_bytes()) {
+            if (!r.marker("#")) return SVX_E_DECODE;
+            n.kind = NK_NOTHING;
+        } else {
+            const char* s;
+            size_t k;
+            if (!r.open() || !r.bytes(&s, &k)) return SVX_E_DECODE;
+            if (is_marker(s, k, "##")) {
+                n.kind = NK_INTERNAL;
+                if (!r.integer(&n.ocbits)) return SVX_E_DECODE;
+            } else if (is_marker(s, k, "###")) {
+                n.kind = NK_LEAF;
+                for (int o = 0; o < 8; ++o)
+                    if (!brick(&n.brick[o])) return SVX_E_DECODE;
+            } else if (is_marker(s, k, "##u#")) {
+                n.kind = NK_UNIFORM;
+                if (!brick(&n.brick[0])) return SVX_E_DECODE;
+            } else {
+                return SVX_E_DECODE;
+            }
+            if (!r.close()) return SVX_E_DECODE;
+        }
+        if (!r.close()) return SVX_E_DECODE;
+        if (!n.reserved) {
+            // ObjectPool::free leaves the dead item in an un-reserved slot (object_pool.rs:213-221) and the reference writes
+            // it out; nothing ever reads it (push overwrites it, :172-176). This host tree keeps freed slots empty.
+            for (auto& b : n.brick) t->brick_release(b);
+            n.kind = NK_NOTHING;
+            n.ocbits = 0;
+        }
+        t->nodes_.push_back(n);
+    }
+    if (!r.close() || !r.close() || t->nodes_.empty()) return SVX_E_DECODE;
+    t->first_available_ = (size_t)std::min<uint64_t>(first_available, t->nodes_.size());
+    // node_children, parallel to the node buffer
+    if (!r.open()) return SVX_E_DECODE;
+    size_t ci = 0;
+    while (r.ok && !r.at_close()) {
+        NodeRec scratch;
+        NodeRec& n = ci < t->nodes_.size() ? t->nodes_[ci] : scratch;
+        ++ci;
+        if (r.peek_bytes()) {
+            if (!r.marker("##x##")) return SVX_E_DECODE;
+            n.link = LK_NONE;
+            continue;
+        }
+        const char* s;
+        size_t k;
+        if (!r.open() || !r.bytes(&s, &k)) return SVX_E_DECODE;
+        if (is_marker(s, k, "##c##")) {
+            n.link = LK_CHILDREN;
+            for (int o = 0; o < 8; ++o) {
+                uint64_t c;
+                if (!r.integer(&c) || c > 0xFFFFFFFFull) return SVX_E_DECODE;
+                n.child[o] = (uint32_t)c;
+            }
+        } else if (is_marker(s, k, "##b##")) {
+            n.link = LK_BITMAP;
+            if (!r.integer(&n.leaf_bits)) return SVX_E_DECODE;
+        } else {
+            return SVX_E_DECODE;
+        }
+        if (!r.close()) return SVX_E_DECODE;
+    }
+    if (!r.close()) return SVX_E_DECODE;
+    // node_mips: skipped
+    if (!r.skip()) return SVX_E_DECODE;
+    // palettes (bytecode.rs:640-655: later duplicates win in the lookup maps)
+    if (!r.open()) return SVX_E_DECODE;
+    while (r.ok && !r.at_close()) {
+        uint64_t c[4];
+        if (!r.open()) return SVX_E_DECODE;
+        for (auto& v : c)
+            if (!r.integer(&v) || v > 255) return SVX_E_DECODE;
+        if (!r.close()) return SVX_E_DECODE;
+        const svx_albedo a{(uint8_t)c[0], (uint8_t)c[1], (uint8_t)c[2], (uint8_t)c[3]};
+        t->color_index_[((uint32_t)a.r << 24) | ((uint32_t)a.g << 16) | ((uint32_t)a.b << 8) | a.a] = (uint32_t)t->colors_.size();
+        t->colors_.push_back(a);
+    }
+    if (!r.close() || !r.open()) return SVX_E_DECODE;
+    while (r.ok && !r.at_close()) {
+        uint64_t d;
+        if (!r.integer(&d) || d > 0xFFFFFFFFull) return SVX_E_DECODE;
+        t->data_index_[(uint32_t)d] = (uint32_t)t->datas_.size();
+        t->datas_.push_back((uint32_t)d);
+    }
+    if (!r.close()) return SVX_E_DECODE;
+    if (!r.skip()) return SVX_E_DECODE;  // MIPMapStrategy
+    if (!r.close() || r.p != r.end) return SVX_E_DECODE;
+    if (t->colors_.size() > 0xFFFF || t->datas_.size() > 0xFFFF) return SVX_E_DECODE;  // u16 palette indices, types.rs:188-191
+    // Untrusted input: the reference would bounds-panic on a palette index beyond its palette and recurse forever on a
+    // child cycle. Reject both here so that get(), the serialiser and the kernels can trust the tree.
+    auto value_ok = [&](uint32_t v) {
+        const uint32_t ci = v & 0xFFFFu, di = v >> 16;
+        return (ci == 0xFFFFu || ci < t->colors_.size()) && (di == 0xFFFFu || di < t->datas_.size());
+    };
+    for (const NodeRec& n : t->nodes_) {
+        if (!n.reserved) continue;
+        for (const BrickRef& b : n.brick) {
+            if (b.kind == BK_SOLID && !value_ok(b.value)) return SVX_E_DECODE;
+            if (b.kind == BK_PARTED) {
+                const uint32_t* v = t->brick_data(b.value);
+                for (uint32_t i = 0; i < t->vol_; ++i)
+                    if (!value_ok(v[i])) return SVX_E_DECODE;
+            }
+        }
+    }
+    {
+        std::vector<uint8_t> seen(t->nodes_.size(), 0);
+        std::vector<std::pair<uint32_t, uint32_t>> todo{{0u, t->size_}};  // (key, node size)
+        seen[0] = 1;
+        while (!todo.empty()) {
+            const auto [key, node_size] = todo.back();
+            todo.pop_back();
+            const NodeRec& n = t->nodes_[key];
+            if (n.kind != NK_INTERNAL || n.link != LK_CHILDREN) continue;
+            for (uint32_t c : n.child) {
+                if (!t->key_is_valid(c)) continue;
+                if (seen[c] || node_size / 2 < t->dim_) return SVX_E_DECODE;  // shared / cyclic child, or below brick size (a UniformLeaf can be as small as one brick)
+                seen[c] = 1;
+                todo.push_back({c, node_size / 2});
+            }
+        }
+    }
+    t->revision_ += 1;
+    guard.t = nullptr;
+    *out = t;
+    return SVX_OK;
+}
+
+int32_t HostOctree::save(const char* path) const {  // octree/mod.rs:144-150
+    std::string bytes;
+    to_bytes(&bytes);
+    std::FILE* f = std::fopen(path, "wb");
+    if (!f) return SVX_E_IO;
+    const bool ok = std::fwrite(bytes.data(), 1, bytes.size(), f) == bytes.size();
+    return (std::fclose(f) == 0 && ok) ? SVX_OK : SVX_E_IO;
+}
+
+int32_t HostOctree::load(const char* path, HostOctree** out) {  // octree/mod.rs:153-159
+    *out = nullptr;
+    std::FILE* f = std::fopen(path, "rb");
+    if (!f) return SVX_E_IO;
+    std::string bytes;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) bytes.append(buf, n);
+    const bool ok = !std::ferror(f);
+    std::fclose(f);
+    if (!ok) return SVX_E_IO;
+    return from_bytes((const uint8_t*)bytes.data(), bytes.size(), out);
+}
+
+}  // namespace svx

@@ -83,7 +83,7 @@ assert ENTRY_DTYPE.itemsize == C.sizeof(Entry)
 
 
 def build(force: bool = False) -> Path:
-    srcs = [ORACLE_DIR / n for n in ("svx_oracle.cpp", "svx_oracle_capi.cpp", "svx_oracle.hpp", "Makefile")]
+    srcs = [ORACLE_DIR / n for n in ("svx_oracle.cpp", "svx_oracle_bytecode.cpp", "svx_oracle_capi.cpp", "svx_oracle.hpp", "Makefile")]
     stale = (not LIB_PATH.exists()) or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", str(ORACLE_DIR)], check=True, capture_output=True)
@@ -120,6 +120,11 @@ def lib() -> C.CDLL:
     L.svxo_octree_insert_batch.restype = i32
     L.svxo_octree_get.argtypes = [vp, u32, u32, u32, C.POINTER(Entry)]
     L.svxo_octree_get_sweep.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp]
+    L.svxo_octree_to_bytes.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.svxo_bytes_free.argtypes = [vp]
+    L.svxo_bytes_free.restype = None
+    L.svxo_octree_from_bytes.argtypes = [C.c_char_p, u64, C.POINTER(vp)]
+    L.svxo_octree_from_bytes.restype = i32
     L.svxo_octree_structure_hash.argtypes = [vp]
     L.svxo_octree_structure_hash.restype = u64
     L.svxo_octree_node_count.argtypes = [vp]
@@ -255,6 +260,24 @@ class OracleOctree:
 
     def structure_hash(self) -> int:
         return lib().svxo_octree_structure_hash(self._h)
+
+    def to_bytes(self) -> bytes:  # Octree::to_bytes, src/octree/mod.rs:138-142
+        buf, n = C.c_void_p(), C.c_uint64()
+        lib().svxo_octree_to_bytes(self._h, C.byref(buf), C.byref(n))
+        try:
+            return C.string_at(buf, n.value)
+        finally:
+            lib().svxo_bytes_free(buf)
+
+    @classmethod
+    def from_bytes(cls, data: bytes) -> "OracleOctree":  # Octree::from_bytes, src/octree/mod.rs:145-148
+        h = C.c_void_p()
+        status = lib().svxo_octree_from_bytes(bytes(data), len(data), C.byref(h))
+        if status != OK:
+            raise ValueError(status)
+        t = cls.__new__(cls)
+        t._h, t.status = h, OK
+        return t
 
     def node_count(self) -> int:
         return lib().svxo_octree_node_count(self._h)

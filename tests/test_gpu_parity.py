@@ -277,6 +277,24 @@ def test_render_is_deterministic_and_counts_launches():
     assert f["kernel_ms"] > 0 and f["hit_id"]
 
 
+def test_tree_loaded_from_bytes_renders_the_same_frame(tmp_path):
+    """Octree::save -> Octree::load (bencode, src/octree/mod.rs:144-159): the loaded tree serialises to the same device
+    buffers, so the frame is identical; the oracle's own bytes (stale pool slots included) load and render the same too."""
+    scene = scenes.colonnade_scene(128, 4)
+    cam = scenes.colonnade_camera(128)
+    tree, otree = both_trees(scene)
+    path = tmp_path / "tree.svx"
+    tree.save(str(path))
+    frames = []
+    for t in (tree, S.Octree.load(str(path)), S.Octree.from_bytes(otree.to_bytes())):
+        view = S.OctreeGPUHost(t).create_new_view(64, viewport(cam), (640, 360))
+        frames.append(view.render_to_host())
+    ora = otree.render(oracle_camera(cam), 640, 360)
+    assert int((frames[0]["hit_id"] != S.MISS).sum()) > 10000
+    for f in frames:
+        assert_frames_equal(f, ora)
+
+
 def test_pipelined_read_back_delivers_the_same_frames():
     """svx_view_render_to_host_async / svx_view_wait_host: frames alternate between two framebuffer slots and their
     copies overlap the next kernel; every frame must equal the synchronous render of the same pose, also when
