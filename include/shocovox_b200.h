@@ -111,6 +111,15 @@ typedef struct svx_gpu_stats {
     uint32_t tree_size, brick_dim, depth, colours;
 } svx_gpu_stats;
 
+/* What the last render-data upload of a host moved: everything the first time, afterwards the node tables plus the
+ * bricks written since the previous upload */
+typedef struct svx_upload_stats {
+    uint64_t bricks; /* bricks copied host -> device */
+    uint64_t bytes;  /* bytes copied host -> device (nodes, palette, voxels, occupancy bits) */
+    uint32_t full;   /* 1: first upload of this host */
+    uint32_t reserved_;
+} svx_upload_stats;
+
 /* ---- library ------------------------------------------------------------------------------------------- */
 SVX_API const char* svx_version(void);
 SVX_API const char* svx_last_error_message(void); /* thread-local text of the last failing call */
@@ -164,9 +173,13 @@ SVX_API int32_t svx_octree_load(const char* path, svx_octree** out);
  * octree handle must outlive the host. */
 SVX_API int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host** out);
 SVX_API void svx_gpu_host_free(svx_gpu_host* host);
-/* Re-serialise and re-upload after the tree was edited (OctreeGPUView::reload, src/raytracing/bevy/mod.rs:56-60).
- * A no-op when the tree has not been modified since the last upload. */
+/* Bring the device copy up to date after the tree was edited (OctreeGPUView::reload, src/raytracing/bevy/mod.rs:56-60;
+ * the job of write_to_gpu's per-request node / brick uploads, bevy/data.rs:365-773). Incremental: the node tables and
+ * the palette are replaced, of the bricks only those written since this host's last upload are copied. A no-op when
+ * the tree has not been modified. Waits for the device first: no render may be in flight on another thread. */
 SVX_API int32_t svx_gpu_host_reload(svx_gpu_host* host);
+/* What the most recent upload / reload of this host copied */
+SVX_API int32_t svx_gpu_host_last_upload(const svx_gpu_host* host, svx_upload_stats* out);
 SVX_API int32_t svx_gpu_host_stats(const svx_gpu_host* host, svx_gpu_stats* out);
 /* Octree::get_by_ray (src/raytracing/raytracing_on_cpu.rs:316-318) for n rays at once, on the GPU.
  * `rays` and `hits` are HOST arrays; n = 1 is the reference's single-ray call. */

@@ -194,7 +194,12 @@ class OctreeGPUHost {  // OctreeGPUHost { tree }: uploads the whole tree to `dev
     OctreeGPUHost& operator=(const OctreeGPUHost&) = delete;
     ~OctreeGPUHost() { svx_gpu_host_free(h_); }
 
-    void reload() { check(svx_gpu_host_reload(h_)); }
+    void reload() { check(svx_gpu_host_reload(h_)); }  // incremental: node tables + the bricks written since the last upload
+    svx_upload_stats last_upload() const {
+        svx_upload_stats s{};
+        check(svx_gpu_host_last_upload(h_, &s));
+        return s;
+    }
     svx_gpu_stats stats() const {
         svx_gpu_stats s{};
         check(svx_gpu_host_stats(h_, &s));

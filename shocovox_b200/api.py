@@ -97,6 +97,10 @@ class _Frame(C.Structure):
     ]
 
 
+class _UploadStats(C.Structure):
+    _fields_ = [("bricks", C.c_uint64), ("bytes", C.c_uint64), ("full", C.c_uint32), ("reserved_", C.c_uint32)]
+
+
 class _GpuStats(C.Structure):
     _fields_ = [
         ("nodes", C.c_uint64),
@@ -134,7 +138,7 @@ EXPORTS = [
     "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
     "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count",
     "svx_octree_to_bytes", "svx_bytes_free", "svx_octree_from_bytes", "svx_octree_save", "svx_octree_load",
-    "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
+    "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_last_upload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
     "svx_view_set_glass_mode", "svx_view_set_resolution", "svx_view_resolution", "svx_view_set_shard",
     "svx_view_set_schedule", "svx_view_set_compact_rows", "svx_view_frame_pointers", "svx_view_export_frame_ipc", "svx_view_set_peer_frame_ipc",
@@ -196,6 +200,7 @@ def lib() -> C.CDLL:
     L.svx_gpu_host_free.restype = None
     L.svx_gpu_host_reload.argtypes = [vp]
     L.svx_gpu_host_stats.argtypes = [vp, C.POINTER(_GpuStats)]
+    L.svx_gpu_host_last_upload.argtypes = [vp, C.POINTER(_UploadStats)]
     L.svx_gpu_host_get_by_rays.argtypes = [vp, vp, u64, vp]
     L.svx_gpu_host_create_view.argtypes = [vp, u32, C.POINTER(_Viewport), u32, u32, C.POINTER(vp)]
     L.svx_view_free.argtypes = [vp]
@@ -492,6 +497,12 @@ class OctreeGPUHost:
         s = _GpuStats()
         _check(lib().svx_gpu_host_stats(self._h, C.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in _GpuStats._fields_}
+
+    def last_upload(self) -> dict:
+        """What the most recent upload / reload copied: {"bricks", "bytes", "full"}."""
+        s = _UploadStats()
+        _check(lib().svx_gpu_host_last_upload(self._h, C.byref(s)))
+        return {"bricks": int(s.bricks), "bytes": int(s.bytes), "full": bool(s.full)}
 
     def get_by_rays(self, rays: np.ndarray) -> np.ndarray:
         """rays: [n,6] f32 (origin xyz, direction xyz) -> structured array (HIT_DTYPE)."""

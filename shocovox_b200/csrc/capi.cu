@@ -130,7 +130,6 @@ struct svx_gpu_host {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
-    SerialisedTree host_copy;  // kept only for stats (vectors are released after upload)
     svx_gpu_stats stats{};
     DeviceTree dev{};
     void* d_node_head = nullptr;
@@ -138,9 +137,14 @@ struct svx_gpu_host {
     void* d_voxels = nullptr;
     void* d_brick_bits = nullptr;
     void* d_palette = nullptr;
+    size_t node_capacity = 0;     // nodes the node_head / node_slot allocations hold
+    size_t palette_capacity = 0;  // colours the palette allocation holds
+    size_t brick_capacity = 0;    // bricks the voxels / brick_bits allocations hold
     LaunchConfig cfg;
     uint64_t launches = 0;
     uint64_t uploaded_revision = ~0ull;
+    bool uploaded = false;
+    svx_upload_stats last_upload{};
     // scratch for get_by_rays
     float* d_rays = nullptr;
     RayHitRecord* d_hits = nullptr;
@@ -191,51 +195,112 @@ void free_device_tree(svx_gpu_host* h) {
     cudaFree(h->d_brick_bits);
     cudaFree(h->d_palette);
     h->d_node_head = h->d_node_slot = h->d_voxels = h->d_brick_bits = h->d_palette = nullptr;
+    h->node_capacity = h->palette_capacity = h->brick_capacity = 0;
+    h->uploaded = false;
 }
 
+// Makes `*ptr` hold at least `need` elements of `elem` bytes (capacity grows by 1.5x), optionally keeping the first
+// `keep` elements (device-to-device copy on the host's stream).
+cudaError_t grow_device_array(void** ptr, size_t* capacity, size_t need, size_t elem, size_t keep, cudaStream_t stream) {
+    if (need <= *capacity && *ptr) return cudaSuccess;
+    const size_t cap = std::max<size_t>(std::max(need, *capacity + *capacity / 2), 1);
+    void* fresh = nullptr;
+    cudaError_t e = cudaMalloc(&fresh, std::max<size_t>(cap * elem, 16));
+    if (e != cudaSuccess) return e;
+    if (*ptr && keep) {
+        e = cudaMemcpyAsync(fresh, *ptr, keep * elem, cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            cudaFree(fresh);
+            return e;
+        }
+    }
+    cudaFree(*ptr);
+    *ptr = fresh;
+    *capacity = cap;
+    return cudaSuccess;
+}
+
+// Render-data upload (OctreeGPUHost::create_new_view / write_to_gpu, src/raytracing/bevy/data.rs:111, :365).
+// The node tables and the palette are re-serialised and replaced; bricks are mirrored by pool handle, and only the
+// ones written since the revision this host last uploaded are copied (all of them the first time).
 int32_t upload(svx_gpu_host* h) {
-    SerialisedTree s;
-    serialise(*h->octree->tree, &s);
+    const HostOctree& tree = *h->octree->tree;
+    SerialisedNodes s;
+    serialise_nodes(tree, &s);
+    const size_t pool = tree.brick_pool_size();
+    const size_t vol = tree.brick_volume(), words = s.bit_words;
     // the brick DDA addresses brick_bits with a 32-bit word offset (traverse.cuh: traverse_brick); 2^32 words are
     // 2^37 voxels, far beyond what the u32 voxel array of the same tree could hold in 180 GB
-    if (s.brick_bits.size() > 0xFFFFFFFFull) return SVX_E_CUDA;
-    free_device_tree(h);
-    auto put = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
-        if (e != cudaSuccess) return e;
-        return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
-    };
-    CUDA_TRY(put(&h->d_node_head, s.node_head.data(), s.node_head.size() * sizeof(NodeHead)));
-    CUDA_TRY(put(&h->d_node_slot, s.node_slot.data(), s.node_slot.size() * 4));
-    CUDA_TRY(put(&h->d_voxels, s.voxels.data(), s.voxels.size() * 4));
-    CUDA_TRY(put(&h->d_brick_bits, s.brick_bits.data(), s.brick_bits.size() * 4));
-    CUDA_TRY(put(&h->d_palette, s.palette.data(), s.palette.size() * 4));
+    if (pool * words > 0xFFFFFFFFull) return fail(SVX_E_OUT_OF_MEMORY, "brick pool exceeds 2^32 occupancy words");
+    const bool first = !h->uploaded;
+    svx_upload_stats up{};
+    up.full = first ? 1u : 0u;
+
+    // nodes + palette: small, replaced wholesale
+    const size_t n_nodes = s.node_head.size();
+    size_t slot_capacity = h->node_capacity * 8, head_capacity = h->node_capacity;
+    CUDA_TRY(grow_device_array(&h->d_node_head, &head_capacity, n_nodes, sizeof(NodeHead), 0, h->stream));
+    CUDA_TRY(grow_device_array(&h->d_node_slot, &slot_capacity, head_capacity * 8, 4, 0, h->stream));
+    h->node_capacity = head_capacity;
+    CUDA_TRY(grow_device_array(&h->d_palette, &h->palette_capacity, s.palette.size(), 4, 0, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_node_head, s.node_head.data(), n_nodes * sizeof(NodeHead), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_node_slot, s.node_slot.data(), n_nodes * 8 * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_palette, s.palette.data(), s.palette.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    up.bytes += n_nodes * (sizeof(NodeHead) + 32) + s.palette.size() * 4;
+
+    // bricks: grow keeping what is resident, then copy the runs of handles written since the last upload
+    const size_t resident = first ? 0 : std::min(h->brick_capacity, pool);
+    size_t voxel_capacity = h->brick_capacity, bits_capacity = h->brick_capacity;
+    CUDA_TRY(grow_device_array(&h->d_voxels, &voxel_capacity, pool, vol * 4, resident, h->stream));
+    CUDA_TRY(grow_device_array(&h->d_brick_bits, &bits_capacity, voxel_capacity, words * 4, resident, h->stream));
+    h->brick_capacity = voxel_capacity;
+    std::vector<uint32_t> bits;
+    for (size_t a = 0; a < pool;) {
+        if (!first && tree.brick_revision((uint32_t)a) <= h->uploaded_revision) {
+            ++a;
+            continue;
+        }
+        size_t b = a + 1;
+        while (b < pool && (first || tree.brick_revision((uint32_t)b) > h->uploaded_revision)) ++b;
+        bits.resize((b - a) * words);
+        for (size_t k = a; k < b; ++k) brick_occupancy_words(tree, (uint32_t)k, bits.data() + (k - a) * words);
+        // pageable sources: cudaMemcpyAsync returns once the data is staged, `bits` can be reused for the next run
+        CUDA_TRY(cudaMemcpyAsync((uint32_t*)h->d_voxels + a * vol, tree.brick_pool() + a * vol, (b - a) * vol * 4,
+                                 cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync((uint32_t*)h->d_brick_bits + a * words, bits.data(), (b - a) * words * 4,
+                                 cudaMemcpyHostToDevice, h->stream));
+        up.bricks += b - a;
+        up.bytes += (b - a) * (vol + words) * 4;
+        a = b;
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    const uint32_t vol = s.brick_dim * s.brick_dim * s.brick_dim;
     DeviceTree& d = h->dev;
     d.node_head = (const NodeHead*)h->d_node_head;
     d.node_slot = (const uint32_t*)h->d_node_slot;
     d.voxels = (const uint32_t*)h->d_voxels;
     d.brick_bits = (const uint32_t*)h->d_brick_bits;
     d.palette = (const uint32_t*)h->d_palette;
-    d.n_nodes = (uint32_t)s.node_head.size();
-    d.n_bricks = (uint32_t)(s.voxels.size() / vol);
+    d.n_nodes = (uint32_t)n_nodes;
+    d.n_bricks = (uint32_t)pool;
     d.tree_size = s.tree_size;
     d.brick_dim = s.brick_dim;
     d.brick_shift = s.brick_shift;
     d.bit_words = s.bit_words;
-    d.n_colors = (uint32_t)h->octree->tree->color_palette().size();
+    d.n_colors = (uint32_t)tree.color_palette().size();
     d.inv_tree_size = 1.0f / (float)s.tree_size;
     d.inv_brick_dim = 1.0f / (float)s.brick_dim;
-    h->stats.nodes = s.node_head.size();
-    h->stats.bricks = d.n_bricks;
-    h->stats.voxel_bytes = s.voxels.size() * 4;
-    h->stats.total_bytes = s.total_bytes();
+    h->stats.nodes = n_nodes;
+    h->stats.bricks = s.live_bricks;
+    h->stats.voxel_bytes = pool * vol * 4;
+    h->stats.total_bytes = n_nodes * (sizeof(NodeHead) + 32) + s.palette.size() * 4 + pool * (vol + words) * 4;
     h->stats.tree_size = s.tree_size;
     h->stats.brick_dim = s.brick_dim;
     h->stats.depth = s.depth;
     h->stats.colours = d.n_colors;
     h->uploaded_revision = s.revision;
+    h->uploaded = true;
+    h->last_upload = up;
     return SVX_OK;
 }
 
@@ -628,6 +693,12 @@ int32_t svx_gpu_host_reload(svx_gpu_host* h) {
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
     return upload(h);
+}
+
+int32_t svx_gpu_host_last_upload(const svx_gpu_host* h, svx_upload_stats* out) {
+    if (!h || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = h->last_upload;
+    return SVX_OK;
 }
 
 int32_t svx_gpu_host_stats(const svx_gpu_host* h, svx_gpu_stats* out) {

@@ -5,9 +5,18 @@
 
 namespace svx {
 
-void serialise(const HostOctree& tree, SerialisedTree* out) {
-    SerialisedTree& s = *out;
-    s = SerialisedTree();
+void brick_occupancy_words(const HostOctree& tree, uint32_t handle, uint32_t* words) {
+    const uint32_t vol = tree.brick_volume();
+    const uint32_t n_words = (vol + 31) / 32;
+    const uint32_t* src = tree.brick_data(handle);
+    for (uint32_t w = 0; w < n_words; ++w) words[w] = 0u;
+    for (uint32_t i = 0; i < vol; ++i)
+        if (!tree.value_is_empty(src[i])) words[i >> 5] |= 1u << (i & 31);
+}
+
+void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
+    SerialisedNodes& s = *out;
+    s = SerialisedNodes();
     s.tree_size = tree.size();
     s.brick_dim = tree.brick_dim();
     s.brick_shift = 0;
@@ -32,22 +41,9 @@ void serialise(const HostOctree& tree, SerialisedTree* out) {
 
     s.node_head.resize(order.size());
     s.node_slot.assign(order.size() * 8, NIL);
-    uint32_t n_bricks = 0;
-    auto add_brick = [&](uint32_t handle) {
-        const uint32_t idx = n_bricks++;
-        s.voxels.resize((size_t)n_bricks * vol);
-        s.brick_bits.resize((size_t)n_bricks * s.bit_words, 0u);
-        const uint32_t* src = tree.brick_data(handle);
-        std::memcpy(s.voxels.data() + (size_t)idx * vol, src, (size_t)vol * 4);
-        uint32_t* bits = s.brick_bits.data() + (size_t)idx * s.bit_words;
-        for (uint32_t i = 0; i < vol; ++i)
-            if (!tree.value_is_empty(src[i])) bits[i >> 5] |= 1u << (i & 31);
-        return idx;
-    };
     auto slot_of = [&](const BrickRef& b) -> uint32_t {
-        if (b.kind == BK_SOLID) return b.value;
-        if (b.kind == BK_PARTED) return add_brick(b.value);
-        return NIL;
+        if (b.kind == BK_PARTED) ++s.live_bricks;
+        return b.kind == BK_EMPTY ? NIL : b.value;  // Solid: the palette value ; Parted: the pool handle
     };
 
     for (size_t i = 0; i < order.size(); ++i) {
@@ -90,10 +86,6 @@ void serialise(const HostOctree& tree, SerialisedTree* out) {
     s.palette.resize(pal.size() ? pal.size() : 1, 0u);
     for (size_t i = 0; i < pal.size(); ++i)
         s.palette[i] = (uint32_t)pal[i].r | ((uint32_t)pal[i].g << 8) | ((uint32_t)pal[i].b << 16) | ((uint32_t)pal[i].a << 24);
-    if (s.voxels.empty()) {  // keep device pointers non-null
-        s.voxels.assign(1, NIL);
-        s.brick_bits.assign(1, 0u);
-    }
 }
 
 }  // namespace svx

@@ -11,13 +11,17 @@
 //        aux    = UniformLeaf: the brick slot (below); otherwise NIL
 //   node_slot[8i + o] : u32   Internal: child node index or NIL (validity resolved on the host)
 //                             Leaf: brick slot of octant o
-//        brick slot = palette value (Solid) | brick index (Parted) | NIL (Empty)
+//        brick slot = palette value (Solid) | brick handle (Parted) | NIL (Empty)
 //   voxels[brick * dim^3 + x + y*dim + z*dim^2] : u32 palette values (reference flat_projection order)
 //   brick_bits[brick * words + ...] : 1 bit per voxel, set when the voxel is NOT empty (pix_points_to_empty false);
 //        the DDA walks these bits and fetches the 4-byte voxel only for the hit
 //   palette[c] : RGBA8, r in the low byte
 //
-// Nodes are numbered breadth-first from the root (index 0), so the top levels share cache lines.
+// Nodes are numbered breadth-first from the root (index 0), so the top levels share cache lines; they are a few
+// hundred KB at most and are re-serialised on every reload. Bricks are the bulk (C3: 550 MB) and are NOT renumbered:
+// the device brick index is the host pool handle, so `voxels` mirrors the host's pooled voxel array one to one and a
+// reload after an edit uploads only the bricks written since the last upload (HostOctree::brick_revision) - the job
+// the reference's streaming cache does per node request (src/raytracing/bevy/data.rs:365-773).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -48,19 +52,18 @@ struct DeviceTree {
     float inv_brick_dim;        // 1 / brick_dim (exact, power of two)
 };
 
-struct SerialisedTree {
+// Host image of the node part of the device layout
+struct SerialisedNodes {
     std::vector<NodeHead> node_head;
     std::vector<uint32_t> node_slot;
-    std::vector<uint32_t> voxels;
-    std::vector<uint32_t> brick_bits;
     std::vector<uint32_t> palette;
     uint32_t tree_size = 0, brick_dim = 0, brick_shift = 0, bit_words = 0, depth = 0;
+    uint64_t live_bricks = 0;  // parted bricks referenced by reachable nodes
     uint64_t revision = 0;
-    size_t total_bytes() const {
-        return node_head.size() * sizeof(NodeHead) + (node_slot.size() + voxels.size() + brick_bits.size() + palette.size()) * 4;
-    }
 };
 
-void serialise(const HostOctree& tree, SerialisedTree* out);
+void serialise_nodes(const HostOctree& tree, SerialisedNodes* out);
+// brick_bits words of one brick of the host pool (`words` receives bit_words entries)
+void brick_occupancy_words(const HostOctree& tree, uint32_t handle, uint32_t* words);
 
 }  // namespace svx

@@ -147,6 +147,7 @@ uint32_t HostOctree::brick_alloc(uint32_t fill) {
     } else {
         h = (uint32_t)(voxels_.size() / vol_);
         voxels_.resize(voxels_.size() + vol_);
+        brick_rev_.push_back(revision_);
         witness_.push_back(0u);
         witness2_.push_back(0xFFFFFFFFu);
     }

@@ -70,6 +70,11 @@ class HostOctree {
     // read access for the serialiser
     const std::vector<NodeRec>& nodes() const { return nodes_; }
     const uint32_t* brick_data(uint32_t handle) const { return voxels_.data() + (size_t)handle * vol_; }
+    // the brick pool as the device mirrors it (handle-indexed) and the revision() at which a brick was last written:
+    // a GPU copy taken at revision R is stale exactly in the bricks with brick_revision(h) > R
+    size_t brick_pool_size() const { return brick_rev_.size(); }
+    const uint32_t* brick_pool() const { return voxels_.data(); }
+    uint64_t brick_revision(uint32_t handle) const { return brick_rev_[handle]; }
     const std::vector<svx_albedo>& color_palette() const { return colors_; }
     const std::vector<uint32_t>& data_palette() const { return datas_; }
     bool key_is_valid(size_t key) const { return key < nodes_.size() && nodes_[key].reserved; }
@@ -86,7 +91,10 @@ class HostOctree {
     uint32_t brick_alloc(uint32_t fill);
     uint32_t brick_clone(uint32_t handle);
     void brick_release(BrickRef& b);
-    uint32_t* brick_mut(uint32_t handle) { return voxels_.data() + (size_t)handle * vol_; }
+    uint32_t* brick_mut(uint32_t handle) {
+        brick_rev_[handle] = revision_;
+        return voxels_.data() + (size_t)handle * vol_;
+    }
     BrickRef brick_copy(const BrickRef& b);
     bool brick_equal(const BrickRef& a, const BrickRef& b) const;
     bool brick_homogeneous(const BrickRef& b, uint32_t* v) const;
@@ -122,6 +130,7 @@ class HostOctree {
     size_t first_available_ = 0;
     std::vector<uint32_t> voxels_;
     std::vector<uint32_t> free_bricks_;
+    std::vector<uint64_t> brick_rev_;  // per brick handle: revision_ of the mutation that last wrote it
     mutable std::vector<uint32_t> witness2_;  // per brick: a 2x2x2 block known to be non-uniform (NIL = none known)
     mutable std::vector<uint32_t> witness_;  // per brick: a voxel index known to differ from voxel 0 (0 = none known)
     std::vector<svx_albedo> colors_;

@@ -242,6 +242,60 @@ def test_reload_after_edit():
     assert_frames_equal(after, otree.render(oracle_camera(cam), 150, 150))
 
 
+def test_incremental_reload_uploads_only_written_bricks_and_matches_a_fresh_upload():
+    """svx_gpu_host_reload copies the node tables plus the bricks written since the host's last upload (device brick
+    index = host pool handle). After every batch of random edits the frame must equal the oracle's and the frame of a
+    brand-new host (full upload) of the same tree; the pool growing past the device capacity keeps resident bricks."""
+    rng = np.random.default_rng(21)
+    size, dim = 128, 8
+    ptree, otree = ProductOctree(size, dim), O.OracleOctree(size, dim)  # both report OctreeError as a status code
+    tree = ptree.tree
+    for t in (ptree, otree):
+        t.insert((3, 3, 3), 0xFF0000FF)
+    cam = scenes.cpu_render_camera(size)
+    res = (320, 240)
+    host = S.OctreeGPUHost(tree)
+    view = host.create_new_view(1, viewport(cam), res)
+    assert host.last_upload()["full"] and host.last_upload()["bricks"] == 1
+    pool_before = host.stats()["voxel_bytes"]
+    for batch in range(8):
+        for _ in range(int(rng.integers(1, 60))):
+            pos = tuple(int(v) for v in rng.integers(0, size, 3))
+            op = int(rng.integers(0, 6))
+            col = (int(rng.integers(1, 5)) * 50, int(rng.integers(0, 255)), 90, 255)
+            lod = int(2 ** rng.integers(0, 3)) * dim
+            status = []
+            for t in (ptree, otree):
+                if op <= 2:
+                    status.append(t.insert(pos, col))
+                elif op == 3:
+                    status.append(t.insert_at_lod(pos, lod, col))
+                elif op == 4:
+                    status.append(t.clear(pos))
+                else:
+                    status.append(t.clear_at_lod(pos, lod))
+            assert status[0] == status[1]
+        assert tree.structure_hash() == otree.structure_hash()
+        view.reload()
+        up = host.last_upload()
+        assert not up["full"]
+        assert up["bricks"] <= 60 * 9  # an edit touches at most its own brick or the 8 a diluted brick turns into
+        got = view.render_to_host()
+        assert_frames_equal(got, otree.render(oracle_camera(cam), *res))
+        fresh = S.OctreeGPUHost(tree).create_new_view(1, viewport(cam), res).render_to_host()
+        for k in got:
+            assert np.array_equal(got[k], fresh[k]), (batch, k)
+    assert host.stats()["voxel_bytes"] > pool_before  # the brick pool grew (device arrays were re-allocated, contents kept)
+    # one more voxel into an existing brick: exactly that brick travels
+    for t in (ptree, otree):
+        t.insert((3, 3, 4), 0x00FF00FF)
+    view.reload()
+    assert host.last_upload()["bricks"] == 1
+    assert_frames_equal(view.render_to_host(), otree.render(oracle_camera(cam), *res))
+    view.reload()  # nothing edited: no-op, the stats of the previous upload stay
+    assert host.last_upload()["bricks"] == 1
+
+
 def test_row_band_shards_compose_the_full_frame():
     """Screen sharding used for multi-GPU: the union of the shards equals the unsharded frame byte for byte."""
     scene = scenes.cpu_render_scene()
