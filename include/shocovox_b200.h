@@ -115,9 +115,9 @@ typedef struct svx_gpu_stats {
  * bricks written since the previous upload */
 typedef struct svx_upload_stats {
     uint64_t bricks; /* bricks copied host -> device */
-    uint64_t bytes;  /* bytes copied host -> device (nodes, palette, voxels, occupancy bits) */
+    uint64_t bytes;  /* bytes copied host -> device (nodes, palettes, voxels, brick handle list) */
     uint32_t full;   /* 1: first upload of this host */
-    uint32_t reserved_;
+    float bits_kernel_ms; /* CUDA-event time of the kernel that derives the occupancy bit-bricks of the copied bricks */
 } svx_upload_stats;
 
 /* ---- library ------------------------------------------------------------------------------------------- */

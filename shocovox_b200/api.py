@@ -98,7 +98,7 @@ class _Frame(C.Structure):
 
 
 class _UploadStats(C.Structure):
-    _fields_ = [("bricks", C.c_uint64), ("bytes", C.c_uint64), ("full", C.c_uint32), ("reserved_", C.c_uint32)]
+    _fields_ = [("bricks", C.c_uint64), ("bytes", C.c_uint64), ("full", C.c_uint32), ("bits_kernel_ms", C.c_float)]
 
 
 class _GpuStats(C.Structure):
@@ -499,10 +499,10 @@ class OctreeGPUHost:
         return {k: int(getattr(s, k)) for k, _ in _GpuStats._fields_}
 
     def last_upload(self) -> dict:
-        """What the most recent upload / reload copied: {"bricks", "bytes", "full"}."""
+        """What the most recent upload / reload copied: {"bricks", "bytes", "full", "bits_kernel_ms"}."""
         s = _UploadStats()
         _check(lib().svx_gpu_host_last_upload(self._h, C.byref(s)))
-        return {"bricks": int(s.bricks), "bytes": int(s.bytes), "full": bool(s.full)}
+        return {"bricks": int(s.bricks), "bytes": int(s.bytes), "full": bool(s.full), "bits_kernel_ms": float(s.bits_kernel_ms)}
 
     def get_by_rays(self, rays: np.ndarray) -> np.ndarray:
         """rays: [n,6] f32 (origin xyz, direction xyz) -> structured array (HIT_DTYPE)."""

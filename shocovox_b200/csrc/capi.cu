@@ -137,6 +137,9 @@ struct svx_gpu_host {
     void* d_voxels = nullptr;
     void* d_brick_bits = nullptr;
     void* d_palette = nullptr;
+    void* d_data_palette = nullptr;  // bit tables "colour shows" / "data carries", input of the occupancy-bit kernel
+    void* d_handles = nullptr;       // brick handles of the current upload, input of the occupancy-bit kernel
+    size_t data_palette_capacity = 0, handle_capacity = 0;
     size_t node_capacity = 0;     // nodes the node_head / node_slot allocations hold
     size_t palette_capacity = 0;  // colours the palette allocation holds
     size_t brick_capacity = 0;    // bricks the voxels / brick_bits allocations hold
@@ -194,8 +197,10 @@ void free_device_tree(svx_gpu_host* h) {
     cudaFree(h->d_voxels);
     cudaFree(h->d_brick_bits);
     cudaFree(h->d_palette);
-    h->d_node_head = h->d_node_slot = h->d_voxels = h->d_brick_bits = h->d_palette = nullptr;
-    h->node_capacity = h->palette_capacity = h->brick_capacity = 0;
+    cudaFree(h->d_data_palette);
+    cudaFree(h->d_handles);
+    h->d_node_head = h->d_node_slot = h->d_voxels = h->d_brick_bits = h->d_palette = h->d_data_palette = h->d_handles = nullptr;
+    h->node_capacity = h->palette_capacity = h->brick_capacity = h->data_palette_capacity = h->handle_capacity = 0;
     h->uploaded = false;
 }
 
@@ -255,7 +260,7 @@ int32_t upload(svx_gpu_host* h) {
     CUDA_TRY(grow_device_array(&h->d_voxels, &voxel_capacity, pool, vol * 4, resident, h->stream));
     CUDA_TRY(grow_device_array(&h->d_brick_bits, &bits_capacity, voxel_capacity, words * 4, resident, h->stream));
     h->brick_capacity = voxel_capacity;
-    std::vector<uint32_t> bits;
+    std::vector<uint32_t> handles;
     for (size_t a = 0; a < pool;) {
         if (!first && tree.brick_revision((uint32_t)a) <= h->uploaded_revision) {
             ++a;
@@ -263,18 +268,13 @@ int32_t upload(svx_gpu_host* h) {
         }
         size_t b = a + 1;
         while (b < pool && (first || tree.brick_revision((uint32_t)b) > h->uploaded_revision)) ++b;
-        bits.resize((b - a) * words);
-        for (size_t k = a; k < b; ++k) brick_occupancy_words(tree, (uint32_t)k, bits.data() + (k - a) * words);
-        // pageable sources: cudaMemcpyAsync returns once the data is staged, `bits` can be reused for the next run
         CUDA_TRY(cudaMemcpyAsync((uint32_t*)h->d_voxels + a * vol, tree.brick_pool() + a * vol, (b - a) * vol * 4,
                                  cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(cudaMemcpyAsync((uint32_t*)h->d_brick_bits + a * words, bits.data(), (b - a) * words * 4,
-                                 cudaMemcpyHostToDevice, h->stream));
+        for (size_t k = a; k < b; ++k) handles.push_back((uint32_t)k);
         up.bricks += b - a;
-        up.bytes += (b - a) * (vol + words) * 4;
+        up.bytes += (b - a) * vol * 4;
         a = b;
     }
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
     DeviceTree& d = h->dev;
     d.node_head = (const NodeHead*)h->d_node_head;
     d.node_slot = (const uint32_t*)h->d_node_slot;
@@ -290,6 +290,38 @@ int32_t upload(svx_gpu_host* h) {
     d.n_colors = (uint32_t)tree.color_palette().size();
     d.inv_tree_size = 1.0f / (float)s.tree_size;
     d.inv_brick_dim = 1.0f / (float)s.brick_dim;
+    // occupancy bit-bricks of the uploaded bricks, computed on the device from the resident voxels and both palettes
+    if (!handles.empty()) {
+        const std::vector<svx_albedo>& colors = tree.color_palette();
+        const std::vector<uint32_t>& datas = tree.data_palette();
+        const uint32_t color_words = (uint32_t)(colors.size() + 31) / 32, data_words = (uint32_t)(datas.size() + 31) / 32;
+        std::vector<uint32_t> tables(color_words + data_words, 0u);
+        for (size_t c = 0; c < colors.size(); ++c)
+            if (colors[c].a != 0) tables[c >> 5] |= 1u << (c & 31);
+        for (size_t k = 0; k < datas.size(); ++k)
+            if (datas[k] != 0) tables[color_words + (k >> 5)] |= 1u << (k & 31);
+        CUDA_TRY(grow_device_array(&h->d_data_palette, &h->data_palette_capacity, tables.size(), 4, 0, h->stream));
+        CUDA_TRY(grow_device_array(&h->d_handles, &h->handle_capacity, handles.size(), 4, 0, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_data_palette, tables.data(), tables.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_handles, handles.data(), handles.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        up.bytes += (tables.size() + handles.size()) * 4;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        cudaEventRecord(e0, h->stream);
+        const cudaError_t launched = launch_occupancy_bits(d, (const uint32_t*)h->d_data_palette, color_words, data_words,
+                                                           (const uint32_t*)h->d_handles, (uint32_t)handles.size(),
+                                                           (uint32_t*)h->d_brick_bits, h->stream);
+        cudaEventRecord(e1, h->stream);
+        const cudaError_t synced = cudaStreamSynchronize(h->stream);
+        if (launched == cudaSuccess && synced == cudaSuccess) cudaEventElapsedTime(&up.bits_kernel_ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        CUDA_TRY(launched);
+        CUDA_TRY(synced);
+        h->launches += 1;
+    }
+    else CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->stats.nodes = n_nodes;
     h->stats.bricks = s.live_bricks;
     h->stats.voxel_bytes = pool * vol * 4;

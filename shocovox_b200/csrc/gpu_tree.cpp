@@ -5,15 +5,6 @@
 
 namespace svx {
 
-void brick_occupancy_words(const HostOctree& tree, uint32_t handle, uint32_t* words) {
-    const uint32_t vol = tree.brick_volume();
-    const uint32_t n_words = (vol + 31) / 32;
-    const uint32_t* src = tree.brick_data(handle);
-    for (uint32_t w = 0; w < n_words; ++w) words[w] = 0u;
-    for (uint32_t i = 0; i < vol; ++i)
-        if (!tree.value_is_empty(src[i])) words[i >> 5] |= 1u << (i & 31);
-}
-
 void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
     SerialisedNodes& s = *out;
     s = SerialisedNodes();

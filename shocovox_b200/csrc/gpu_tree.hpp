@@ -14,7 +14,8 @@
 //        brick slot = palette value (Solid) | brick handle (Parted) | NIL (Empty)
 //   voxels[brick * dim^3 + x + y*dim + z*dim^2] : u32 palette values (reference flat_projection order)
 //   brick_bits[brick * words + ...] : 1 bit per voxel, set when the voxel is NOT empty (pix_points_to_empty false);
-//        the DDA walks these bits and fetches the 4-byte voxel only for the hit
+//        the DDA walks these bits and fetches the 4-byte voxel only for the hit. Computed ON THE DEVICE from the
+//        uploaded voxels (kernels.cu: occupancy_bits_kernel)
 //   palette[c] : RGBA8, r in the low byte
 //
 // Nodes are numbered breadth-first from the root (index 0), so the top levels share cache lines; they are a few
@@ -63,7 +64,5 @@ struct SerialisedNodes {
 };
 
 void serialise_nodes(const HostOctree& tree, SerialisedNodes* out);
-// brick_bits words of one brick of the host pool (`words` receives bit_words entries)
-void brick_occupancy_words(const HostOctree& tree, uint32_t handle, uint32_t* words);
 
 }  // namespace svx

@@ -1,5 +1,7 @@
 // sm_100a kernels of the primary-ray path: the viewport kernel (ray generation + traversal + framebuffer) and the
 // batched get_by_ray kernel. Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see build.py).
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "traverse.cuh"
 
@@ -157,6 +159,103 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rays_kernel(const DeviceTree tr
     out[i] = h;
 }
 
+// pix_points_to_empty (reference src/octree/node.rs:405-427) negated: does this palette value show or carry anything?
+// `shows` / `carries` are bit tables in shared memory over the WHOLE u16 index range (2048 words each): bit c of `shows`
+// = colour c exists and has albedo.a != 0, bit d of `carries` = user data d exists and is not zero. Indices beyond the
+// palettes, and 0xFFFF = "none", read a 0 bit, so the test needs no compare and no branch.
+constexpr uint32_t TABLE_WORDS = 65536u / 32u;
+__device__ __forceinline__ bool voxel_occupied(const uint32_t* shows, const uint32_t* carries, uint32_t v) {
+    const uint32_t ci = v & 0xFFFFu, di = v >> 16;
+    return (((shows[ci >> 5] >> (ci & 31u)) | (carries[di >> 5] >> (di & 31u))) & 1u) != 0u;
+}
+
+// Both kernels start by staging the two bit tables in shared memory (`tables`, host-built = color_words words, then
+// data_words words; the rest of each 2048-word table is zero).
+__device__ __forceinline__ void stage_tables(uint32_t* smem, const uint32_t* __restrict__ tables, uint32_t color_words,
+                                             uint32_t data_words) {
+    for (uint32_t i = threadIdx.x; i < TABLE_WORDS; i += blockDim.x) {
+        smem[i] = i < color_words ? __ldg(tables + i) : 0u;
+        smem[TABLE_WORDS + i] = i < data_words ? __ldg(tables + color_words + i) : 0u;
+    }
+    __syncthreads();
+}
+
+// Occupancy bit-bricks of the listed bricks. HBM-bound streaming kernel: 4 B read per voxel, 1 bit written.
+// Bricks of >= 32 voxels (brick_dim >= 4): a thread loads 4 voxels with one 16-byte load, 8 neighbouring lanes make one
+// 32-voxel word (butterfly OR of their nibbles), so a warp turns 512 contiguous bytes into 4 words per step; all
+// index arithmetic is shifts (volume and words per brick are powers of two).
+__global__ void __launch_bounds__(256) occupancy_bits_kernel(const DeviceTree tree, const uint32_t* __restrict__ tables,
+                                                             uint32_t color_words, uint32_t data_words,
+                                                             const uint32_t* __restrict__ handles, uint32_t n,
+                                                             uint32_t* __restrict__ bits_out) {
+    __shared__ uint32_t smem[2 * TABLE_WORDS];
+    stage_tables(smem, tables, color_words, data_words);
+    const uint32_t* shows = smem;
+    const uint32_t* carries = smem + TABLE_WORDS;
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & 7u;
+    const uint32_t vol_shift = 3u * tree.brick_shift;  // log2(voxels per brick) >= 5 here
+    const uint32_t word_shift = vol_shift - 5u;        // log2(words per brick)
+    // 32-bit word counters: the host guarantees n * words_per_brick < 2^32 (capi.cu: upload)
+    const uint32_t total_words = n << word_shift;
+    const uint32_t groups = (gridDim.x * blockDim.x) >> 3;  // 8-lane groups in the grid, one word each per step
+    constexpr int UNROLL = 4;  // independent 16-byte loads in flight per thread (64 B): covers HBM latency at this occupancy
+    const uint32_t trips = (uint32_t)(((uint64_t)total_words + (uint64_t)groups * UNROLL - 1) / ((uint64_t)groups * UNROLL));
+    const uint32_t word_mask = (1u << word_shift) - 1u;
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    for (uint32_t t = 0; t < trips; ++t) {  // same trip count for every lane: the shuffles stay converged
+        uint4 v[UNROLL];
+        uint32_t out_index[UNROLL];  // word index into bits_out; fits 32 bits by the same guarantee
+        bool valid[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t w64 = ((uint64_t)t * UNROLL + (uint64_t)u) * groups + g;
+            valid[u] = w64 < total_words;
+            const uint32_t w = (uint32_t)w64;
+            v[u] = make_uint4(NIL, NIL, NIL, NIL);
+            out_index[u] = 0u;
+            if (valid[u]) {
+                const uint32_t handle = __ldg(handles + (w >> word_shift));
+                const uint32_t word = w & word_mask;
+                out_index[u] = (handle << word_shift) + word;
+                v[u] = __ldg(reinterpret_cast<const uint4*>(tree.voxels + ((size_t)handle << vol_shift)) + ((word << 3) + sub));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            // voxel data is coherent (air, single-material runs): four equal palette values need one table test
+            uint32_t nib;
+            if (v[u].x == v[u].y && v[u].z == v[u].w && v[u].x == v[u].z)
+                nib = voxel_occupied(shows, carries, v[u].x) ? 0xFu : 0u;
+            else
+                nib = (voxel_occupied(shows, carries, v[u].x) ? 1u : 0u) | (voxel_occupied(shows, carries, v[u].y) ? 2u : 0u) |
+                      (voxel_occupied(shows, carries, v[u].z) ? 4u : 0u) | (voxel_occupied(shows, carries, v[u].w) ? 8u : 0u);
+            uint32_t part = nib << (4u * sub);  // NIL voxels (lanes past the end) are never occupied
+            part |= __shfl_xor_sync(0xFFFFFFFFu, part, 1);
+            part |= __shfl_xor_sync(0xFFFFFFFFu, part, 2);
+            part |= __shfl_xor_sync(0xFFFFFFFFu, part, 4);
+            if (sub == 0u && valid[u]) bits_out[out_index[u]] = part;
+        }
+    }
+}
+
+// The same for bricks of fewer than 32 voxels (brick_dim 1 or 2: one partly used word per brick), one warp per brick.
+__global__ void __launch_bounds__(256) occupancy_bits_small_kernel(const DeviceTree tree, const uint32_t* __restrict__ tables,
+                                                                   uint32_t color_words, uint32_t data_words,
+                                                                   const uint32_t* __restrict__ handles, uint32_t n,
+                                                                   uint32_t* __restrict__ bits_out) {
+    __shared__ uint32_t smem[2 * TABLE_WORDS];
+    stage_tables(smem, tables, color_words, data_words);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t vol = 1u << (3u * tree.brick_shift);
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n; b += warps) {  // warp-uniform bounds
+        const uint32_t handle = __ldg(handles + b);
+        const bool occupied = lane < vol && voxel_occupied(smem, smem + TABLE_WORDS, __ldg(tree.voxels + (size_t)handle * vol + lane));
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, occupied);
+        if (lane == 0) bits_out[handle] = mask;
+    }
+}
+
 // Evaluates the closed forms that replace the reference's tables, for every table index.
 __global__ void lut_selftest_kernel(uint64_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,6 +303,22 @@ cudaError_t launch_rays(const DeviceTree& tree, const float* rays, uint64_t n, R
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + BLOCK_THREADS - 1) / BLOCK_THREADS);
     rays_kernel<<<blocks, BLOCK_THREADS, 0, stream>>>(tree, rays, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_occupancy_bits(const DeviceTree& tree, const uint32_t* tables, uint32_t color_words, uint32_t data_words,
+                                  const uint32_t* handles, uint32_t n, uint32_t* bits_out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if (color_words > 2048u || data_words > 2048u) return cudaErrorInvalidValue;  // u16 palette indices (types.rs:188-191)
+    const unsigned machine = 148u * 8u * 2u;  // two waves of the 8 CTAs an SM holds (32 registers x 256 threads), then grid-stride
+    if (tree.brick_shift < 2u) {
+        const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n + 7) / 8, machine);
+        occupancy_bits_small_kernel<<<grid, 256, 0, stream>>>(tree, tables, color_words, data_words, handles, n, bits_out);
+    } else {
+        const uint64_t total_words = (uint64_t)n * tree.bit_words;
+        const unsigned grid = (unsigned)std::min<uint64_t>((total_words + 31) / 32, machine);  // 32 words per CTA and step
+        occupancy_bits_kernel<<<grid, 256, 0, stream>>>(tree, tables, color_words, data_words, handles, n, bits_out);
+    }
     return cudaGetLastError();
 }
 

@@ -47,6 +47,13 @@ struct LaunchConfig {
 cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig& cfg, cudaStream_t stream);
 cudaError_t launch_rays(const DeviceTree& tree, const float* rays /* [n][6] */, uint64_t n, RayHitRecord* out,
                         const LaunchConfig& cfg, cudaStream_t stream);
+// Render-data upload, device side: the occupancy bit-bricks (gpu_tree.hpp: brick_bits) of the listed bricks, computed
+// from the voxels already resident in `tree.voxels`. A voxel's bit is set unless pix_points_to_empty holds for it
+// (reference src/octree/node.rs:405-427): (no colour index or albedo.a == 0) and (no data index or data == 0).
+// `tables` (device) = color_words words with bit c set when colour c has albedo.a != 0, then data_words words with bit d
+// set when user data d != 0; `handles` = n device-resident brick handles; `bits_out` = the brick_bits array.
+cudaError_t launch_occupancy_bits(const DeviceTree& tree, const uint32_t* tables, uint32_t color_words, uint32_t data_words,
+                                  const uint32_t* handles, uint32_t n, uint32_t* bits_out, cudaStream_t stream);
 // Fills out[0..512) with RAY_TO_NODE mask words, out[512..520) octant masks, then 27*8 step results, evaluated by
 // the device closed forms; the host compares them with tables regenerated from the reference's generator logic.
 cudaError_t launch_lut_selftest(uint64_t* out /* device, 512 + 8 + 216 entries */, cudaStream_t stream);

@@ -44,7 +44,11 @@ def main():
         reload_ms = (time.perf_counter() - t0) * 1e3
         out["edits"].append({"inserts": k, "insert_ms": edit_ms, "reload_ms": reload_ms, **host.last_upload()})
         print(f"{sc.name}: {k:5d} inserts {edit_ms:8.2f} ms, reload {reload_ms:8.2f} ms, {host.last_upload()}", flush=True)
-    print(f"{sc.name}: full upload {full_ms:.1f} ms {out['full']}")
+    full = out["full"]
+    algo = full["bricks"] * (sc.brick_dim ** 3) * (4 + 1 / 8)  # 4 B read per voxel, 1 bit written
+    gbs = algo / (full["bits_kernel_ms"] * 1e-3) / 1e9 if full["bits_kernel_ms"] > 0 else 0.0
+    out["bits_kernel_gbs"] = gbs
+    print(f"{sc.name}: full upload {full_ms:.1f} ms {full}; occupancy_bits_kernel {full['bits_kernel_ms']:.4f} ms = {gbs:.0f} GB/s algorithmic")
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / f"reload_probe_{name}.json").write_text(json.dumps(out, indent=1))
 
