@@ -156,9 +156,40 @@ SVX_API int32_t svx_octree_set_auto_simplify(svx_octree* tree, int32_t enabled);
 /* Key-order independent digest of the reachable tree (node kinds, occupancy bits, bricks, palettes) */
 SVX_API uint64_t svx_octree_structure_hash(const svx_octree* tree);
 SVX_API uint64_t svx_octree_node_count(const svx_octree* tree);
+
+/* ---- MIP maps: Octree::albedo_mip_map_resampling_strategy() -> StrategyUpdater, src/octree/mod.rs:379,
+ * src/octree/mipmap.rs:716-938. Every node owns one MIP brick (types.rs:186) holding a simplified view of its content;
+ * edits refresh the affected MIP voxels (insert.rs:371, clear.rs:335) and get_by_ray_at_lod reads them. */
+typedef enum svx_mip_method { /* MIPResamplingMethods, src/octree/types.rs:106-139 */
+    SVX_MIP_BOX_FILTER = 0,      /* gamma-2 average of the cell one level below; adds colours to the palette (default) */
+    SVX_MIP_POINT_FILTER = 1,    /* most frequent colour of the cell one level below */
+    SVX_MIP_POINT_FILTER_BD = 2, /* most frequent colour of the voxels at the bottom ("bottom dominant") */
+    SVX_MIP_POSTERIZE = 3,       /* average of the largest group of similar colours; parameter = similarity in [0, 1] */
+    SVX_MIP_POSTERIZE_BD = 4
+} svx_mip_method;
+/* StrategyUpdater::switch_albedo_mip_maps, mipmap.rs:858-872: enabling recalculates every MIP of a non-empty tree */
+SVX_API int32_t svx_octree_switch_albedo_mip_maps(svx_octree* tree, int32_t enabled);
+SVX_API int32_t svx_octree_mip_maps_enabled(const svx_octree* tree); /* MIPMapStrategy::is_enabled, mipmap.rs:693 */
+/* StrategyUpdater::recalculate_mips, mipmap.rs:798-855 */
+SVX_API int32_t svx_octree_recalculate_mips(svx_octree* tree);
+/* set_method_at / get_method_at, mipmap.rs:650-672, :758-771 (threshold clamped to [0, 1]; default BoxFilter) */
+SVX_API int32_t svx_octree_mip_set_method_at(svx_octree* tree, uint64_t mip_level, int32_t method, float threshold);
+SVX_API int32_t svx_octree_mip_get_method_at(const svx_octree* tree, uint64_t mip_level, int32_t* method, float* threshold);
+/* set_color_similarity_thr_at / get_new_color_similarity_at, mipmap.rs:610-640, :726-745 */
+SVX_API int32_t svx_octree_mip_set_color_similarity_thr_at(svx_octree* tree, uint64_t mip_level, float threshold);
+SVX_API float svx_octree_mip_get_color_similarity_at(const svx_octree* tree, uint64_t mip_level);
+/* StrategyUpdater::reset, mipmap.rs:718-721: back to MIPMapStrategy::default() (disabled) */
+SVX_API int32_t svx_octree_mip_reset(svx_octree* tree);
+/* sample_root_mip (mipmap.rs:897-937, the reference's test hook): the MIP voxel (x, y, z) of the root (octant 8) or of
+ * the root's child in `octant` */
+SVX_API int32_t svx_octree_mip_sample_root(const svx_octree* tree, uint32_t octant, uint32_t x, uint32_t y, uint32_t z,
+                                           svx_entry* out);
+/* Digest of the strategy and of the MIP bricks of all reachable nodes */
+SVX_API uint64_t svx_octree_mip_hash(const svx_octree* tree);
+
 /* Octree::to_bytes / from_bytes / save / load, src/octree/mod.rs:138-168: the bencode byte format of
- * src/convert/bytecode.rs (a tree saved by the Rust crate loads here and the other way round; MIP bricks in a file
- * are skipped, MIP maps are written as disabled). to_bytes hands out a library-owned buffer: release it with
+ * src/convert/bytecode.rs (a tree saved by the Rust crate loads here and the other way round, MIP bricks and MIP
+ * strategy included). to_bytes hands out a library-owned buffer: release it with
  * svx_bytes_free. from_bytes / load validate size and brick_dim like Octree::new and return SVX_E_DECODE on
  * malformed input, SVX_E_IO when the file cannot be read or written. */
 SVX_API int32_t svx_octree_to_bytes(const svx_octree* tree, uint8_t** bytes, uint64_t* len);
@@ -184,6 +215,11 @@ SVX_API int32_t svx_gpu_host_stats(const svx_gpu_host* host, svx_gpu_stats* out)
 /* Octree::get_by_ray (src/raytracing/raytracing_on_cpu.rs:316-318) for n rays at once, on the GPU.
  * `rays` and `hits` are HOST arrays; n = 1 is the reference's single-ray call. */
 SVX_API int32_t svx_gpu_host_get_by_rays(svx_gpu_host* host, const svx_ray* rays, uint64_t n, svx_hit* hits);
+/* Octree::get_by_ray_at_lod (src/raytracing/raytracing_on_cpu.rs:325-565): the same query with the level-of-detail
+ * branch (:368-386) - a node whose MIP level is below `travelled distance / viewing_distance` answers with its MIP
+ * brick. viewing_distance = FLT_MAX is get_by_ray. MIP hits carry no user data (the reference's own warning). */
+SVX_API int32_t svx_gpu_host_get_by_rays_at_lod(svx_gpu_host* host, const svx_ray* rays, uint64_t n, float viewing_distance,
+                                                svx_hit* hits);
 
 /* ---- OctreeGPUView: viewport + framebuffer -------------------------------------------------------------- */
 /* OctreeGPUHost::create_new_view, src/raytracing/bevy/data.rs:111-166. `size_hint` is the reference's node-cache
@@ -195,6 +231,11 @@ SVX_API void svx_view_free(svx_view* view);
 SVX_API int32_t svx_view_get_viewport(const svx_view* view, svx_viewport* out);
 SVX_API int32_t svx_view_set_viewport(svx_view* view, const svx_viewport* viewport);
 SVX_API int32_t svx_view_set_glass_mode(svx_view* view, int32_t mode /* svx_glass_mode */);
+/* The viewing distance every pixel's get_by_ray_at_lod uses. Default FLT_MAX = get_by_ray (no level of detail); the
+ * reference's own GPU path feeds viewport.frustum.z here (assets/shaders/viewport_render.wgsl:631-638). Ignored while
+ * the tree's MIP maps are disabled (raytracing_on_cpu.rs:369). */
+SVX_API int32_t svx_view_set_viewing_distance(svx_view* view, float viewing_distance);
+SVX_API int32_t svx_view_get_viewing_distance(const svx_view* view, float* viewing_distance);
 /* OctreeGPUView::set_resolution / resolution, src/raytracing/bevy/mod.rs:62-88 */
 SVX_API int32_t svx_view_set_resolution(svx_view* view, uint32_t width, uint32_t height);
 SVX_API int32_t svx_view_resolution(const svx_view* view, uint32_t* width, uint32_t* height);

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <unordered_map>
 
 namespace svxo {
@@ -489,9 +490,10 @@ static bool bound_contains(const Cube& b, V3f p) {
 static uint8_t child_octant_for(const Cube& b, V3f p) { return hash_region(p - b.min_position, b.size / 2.0f); }
 
 // mod.rs:209-371
-Entry Octree::get(V3u position_u) const {
-    size_t current_node_key = 0;
-    Cube current_bounds{unit(0.0f), (float)octree_size};
+Entry Octree::get(V3u position_u) const { return get_internal(0, Cube{unit(0.0f), (float)octree_size}, position_u); }
+
+// mod.rs:220-371
+Entry Octree::get_internal(size_t current_node_key, Cube current_bounds, V3u position_u) const {
     const V3f position = to_f32(position_u);
     if (!bound_contains(current_bounds, position)) return Entry();
     for (;;) {
@@ -1227,7 +1229,8 @@ Status Octree::insert_at_lod_internal(bool overwrite_if_empty, V3u position_u, u
                                            &new_occupied_bits);
         }
         store_occupied_bits(node_key, new_occupied_bits);
-        // update_mip: MIP maps disabled (mipmap.rs:297-300) -> no-op
+        // update MIP maps (insert.rs:371); `position` is the caller's u32 position
+        update_mip(node_key, node_bounds, position_u);
 
         const NodeKind k = nodes.item[node_key].kind;
         if (k == NodeKind::Leaf || k == NodeKind::UniformLeaf) {
@@ -1482,10 +1485,414 @@ Status Octree::clear_at_lod(V3u position_u, uint32_t clear_size) {
             node_children[node_key] = Children();
         else
             store_occupied_bits(node_key, new_occupied_bits);
+        update_mip(node_key, node_bounds, position_u);  // clear.rs:335
         if (simplifyable) simplifyable = simplify(node_key);
         if (previous_occupied_bits == new_occupied_bits) break;
     }
     return OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// octree/mipmap.rs
+// ---------------------------------------------------------------------------------------------
+// MIPMapStrategy::default(), mipmap.rs:591-604
+MipStrategy::MipStrategy() {
+    enabled = false;
+    resampling_methods = {{1, {MipMethod::PointFilter, 0.0f}},
+                          {2, {MipMethod::BoxFilter, 0.0f}},
+                          {3, {MipMethod::BoxFilter, 0.0f}},
+                          {4, {MipMethod::BoxFilter, 0.0f}}};
+    resampling_color_matching_thresholds = {{2, 0.1f}, {3, 0.05f}, {4, 0.02f}};
+}
+
+// mipmap.rs:617-630
+void Octree::mip_set_color_similarity_thr_at(size_t mip_level, float thr) {
+    mip_map_strategy.resampling_color_matching_thresholds[mip_level] = clampf(thr, 0.0f, 1.0f);
+}
+// mipmap.rs:610-615
+float Octree::mip_get_new_color_similarity_at(size_t mip_level) const {
+    auto it = mip_map_strategy.resampling_color_matching_thresholds.find(mip_level);
+    return it == mip_map_strategy.resampling_color_matching_thresholds.end() ? 0.0f : it->second;
+}
+// mipmap.rs:657-672
+void Octree::mip_set_method_at(size_t mip_level, MipSampler method) {
+    if (method.method == MipMethod::Posterize || method.method == MipMethod::PosterizeBD)
+        method.thr = clampf(method.thr, 0.0f, 1.0f);
+    else
+        method.thr = 0.0f;
+    mip_map_strategy.resampling_methods[mip_level] = method;
+}
+// mipmap.rs:650-655
+MipSampler Octree::mip_get_method_at(size_t mip_level) const {
+    auto it = mip_map_strategy.resampling_methods.find(mip_level);
+    return it == mip_map_strategy.resampling_methods.end() ? MipSampler{} : it->second;
+}
+
+namespace {
+// Albedou32, mipmap.rs:36-121. The reference computes in u32; in a release build `-` and `pow` wrap, and
+// (2^32 - d)^2 mod 2^32 == d^2, so the wrapped distance below is the plain Euclidean one (a debug build panics).
+struct Albedou32 {
+    uint32_t r, g, b, a;
+    bool operator==(const Albedou32& o) const { return r == o.r && g == o.g && b == o.b && a == o.a; }
+};
+inline Albedou32 au_from(Albedo c) { return {c.r, c.g, c.b, c.a}; }
+inline Albedou32 au_pow2(Albedou32 c) { return {c.r * c.r, c.g * c.g, c.b * c.b, c.a * c.a}; }
+inline Albedou32 au_add(Albedou32 x, Albedou32 y) { return {x.r + y.r, x.g + y.g, x.b + y.b, x.a + y.a}; }
+inline Albedou32 au_sub(Albedou32 x, Albedou32 y) { return {x.r - y.r, x.g - y.g, x.b - y.b, x.a - y.a}; }
+inline uint32_t f2u32(float v) {  // `f32 as u32`: saturating, NaN -> 0
+    if (!(v == v)) return 0;
+    if (v <= 0.0f) return 0;
+    if (v >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)v;
+}
+inline Albedou32 au_div(Albedou32 c, uint32_t d) {  // :88-98
+    return {f2u32(std::round((float)c.r / (float)d)), f2u32(std::round((float)c.g / (float)d)),
+            f2u32(std::round((float)c.b / (float)d)), f2u32(std::round((float)c.a / (float)d))};
+}
+inline Albedou32 au_sqrt(Albedou32 c) {  // :47-53
+    return {f2u32(std::round(std::sqrt((float)c.r))), f2u32(std::round(std::sqrt((float)c.g))),
+            f2u32(std::round(std::sqrt((float)c.b))), f2u32(std::round(std::sqrt((float)c.a)))};
+}
+inline float au_length(Albedou32 c) {  // :44-46
+    return std::sqrt((float)(uint32_t)(c.r * c.r + c.g * c.g + c.b * c.b + c.a * c.a));
+}
+inline Albedo au_to_albedo(Albedou32 c) {  // :112-121
+    return {(uint8_t)std::min(c.r, 255u), (uint8_t)std::min(c.g, 255u), (uint8_t)std::min(c.b, 255u),
+            (uint8_t)std::min(c.a, 255u)};
+}
+inline uint8_t f2u8(float v) {  // `f32 as u8`
+    if (!(v == v)) return 0;
+    if (v <= 0.0f) return 0;
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+inline bool albedo_eq(Albedo x, Albedo y) { return x.r == y.r && x.g == y.g && x.b == y.b && x.a == y.a; }
+
+// MIPResaplingFunction::execute, mipmap.rs:133-263. `sample_fn` returns false for None.
+//
+// DETERMINISM NOTE. PointFilter and Posterize keep their candidates in a std HashMap and the reference takes
+// `into_iter().max_by_key(count)` (the LAST maximum in iteration order) - with Rust's randomly seeded hasher a tie
+// between two colours is resolved differently from run to run, and Posterize's `for .. in albedo_counts.iter()` picks
+// "the first bucket within the threshold" in that same random order. Any of those outcomes is a valid reference
+// result; this restatement (and the product) fix the order to FIRST-SEEN: buckets are kept in the order their first
+// sample arrived (x outer, y, z inner), a re-keyed Posterize bucket keeps its place, and a tie goes to the earliest.
+template <typename F>
+bool mip_sample(const MipSampler& sampler, V3u sample_start, uint32_t sample_size, F&& sample_fn, Albedo* out) {
+    switch (sampler.method) {
+        case MipMethod::BoxFilter: {
+            bool have = false;
+            float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            int32_t entry_count = 0;
+            for (uint32_t x = sample_start.x; x < sample_start.x + sample_size; ++x)
+                for (uint32_t y = sample_start.y; y < sample_start.y + sample_size; ++y)
+                    for (uint32_t z = sample_start.z; z < sample_start.z + sample_size; ++z) {
+                        Albedo c;
+                        if (!sample_fn(V3u{x, y, z}, &c)) continue;
+                        if (!have) {
+                            have = true;
+                            entry_count = 1;
+                            s0 = (float)c.r * (float)c.r;
+                            s1 = (float)c.g * (float)c.g;
+                            s2 = (float)c.b * (float)c.b;
+                            s3 = (float)c.a * (float)c.a;
+                        } else {
+                            entry_count += 1;
+                            s0 += (float)c.r * (float)c.r;
+                            s1 += (float)c.g * (float)c.g;
+                            s2 += (float)c.b * (float)c.b;
+                            s3 += (float)c.a * (float)c.a;
+                        }
+                    }
+            if (!have) return false;
+            out->r = f2u8(fmin_(std::sqrt(s0 / (float)entry_count), 255.0f));
+            out->g = f2u8(fmin_(std::sqrt(s1 / (float)entry_count), 255.0f));
+            out->b = f2u8(fmin_(std::sqrt(s2 / (float)entry_count), 255.0f));
+            out->a = f2u8(fmin_(std::sqrt(s3 / (float)entry_count), 255.0f));
+            return true;
+        }
+        case MipMethod::PointFilter:
+        case MipMethod::PointFilterBD: {
+            std::vector<std::pair<Albedo, uint32_t>> counts;
+            for (uint32_t x = sample_start.x; x < sample_start.x + sample_size; ++x)
+                for (uint32_t y = sample_start.y; y < sample_start.y + sample_size; ++y)
+                    for (uint32_t z = sample_start.z; z < sample_start.z + sample_size; ++z) {
+                        Albedo c;
+                        if (!sample_fn(V3u{x, y, z}, &c)) continue;
+                        bool found = false;
+                        for (auto& e : counts)
+                            if (albedo_eq(e.first, c)) {
+                                e.second += 1;
+                                found = true;
+                                break;
+                            }
+                        if (!found) counts.push_back({c, 1});
+                    }
+            if (counts.empty()) return false;
+            size_t best = 0;
+            for (size_t i = 1; i < counts.size(); ++i)
+                if (counts[i].second > counts[best].second) best = i;
+            *out = counts[best].first;
+            return true;
+        }
+        case MipMethod::Posterize:
+        case MipMethod::PosterizeBD: {
+            const float thr = sampler.thr;
+            std::vector<std::pair<Albedou32, uint32_t>> counts;  // squared sums, occurrence counts
+            for (uint32_t x = sample_start.x; x < sample_start.x + sample_size; ++x)
+                for (uint32_t y = sample_start.y; y < sample_start.y + sample_size; ++y)
+                    for (uint32_t z = sample_start.z; z < sample_start.z + sample_size; ++z) {
+                        Albedo c;
+                        if (!sample_fn(V3u{x, y, z}, &c)) continue;
+                        size_t hit = counts.size();
+                        for (size_t i = 0; i < counts.size(); ++i) {
+                            const Albedou32 poster_color = au_sqrt(au_div(counts[i].first, counts[i].second));
+                            if (au_length(au_sub(poster_color, au_from(c))) < (thr * 255.0f)) {
+                                hit = i;
+                                break;
+                            }
+                        }
+                        if (hit < counts.size()) {
+                            // remove(old key) + insert(new key, count + 1); an insert onto an existing key replaces
+                            // that entry's count (HashMap::insert) - the colliding bucket is dropped
+                            const Albedou32 new_sum = au_add(counts[hit].first, au_pow2(au_from(c)));
+                            const uint32_t new_count = counts[hit].second + 1;
+                            counts[hit] = {new_sum, new_count};
+                            for (size_t i = 0; i < counts.size(); ++i)
+                                if (i != hit && counts[i].first == new_sum) {
+                                    counts.erase(counts.begin() + (ptrdiff_t)i);
+                                    break;
+                                }
+                        } else {
+                            const Albedou32 key = au_pow2(au_from(c));
+                            bool replaced = false;
+                            for (auto& e : counts)
+                                if (e.first == key) {
+                                    e.second = 1;
+                                    replaced = true;
+                                    break;
+                                }
+                            if (!replaced) counts.push_back({key, 1});
+                        }
+                    }
+            if (counts.empty()) return false;
+            size_t best = 0;
+            for (size_t i = 1; i < counts.size(); ++i)
+                if (counts[i].second > counts[best].second) best = i;
+            *out = au_to_albedo(au_sqrt(au_div(counts[best].first, counts[best].second)));
+            return true;
+        }
+    }
+    return false;
+}
+
+inline bool entry_albedo(const Entry& e, Albedo* out) {  // OctreeEntry::albedo, mod.rs:79-86
+    if (e.kind == EntryKind::Visual || e.kind == EntryKind::Complex) {
+        *out = e.albedo;
+        return true;
+    }
+    return false;
+}
+// Albedo::distance_from, detail.rs:82-89
+inline float albedo_distance(Albedo x, Albedo y) {
+    const float dr = (float)x.r - (float)y.r, dg = (float)x.g - (float)y.g, db = (float)x.b - (float)y.b,
+                da = (float)x.a - (float)y.a;
+    return std::sqrt(dr * dr + dg * dg + db * db + da * da);
+}
+inline uint32_t f2u32_round(float v) { return f2u32(std::round(v)); }  // From<V3c<f32>> for V3c<u32>, vector.rs:326-336
+}  // namespace
+
+// mipmap.rs:296-584
+void Octree::update_mip(size_t node_key, const Cube& node_bounds, V3u position) {
+    if (!mip_map_strategy.enabled) return;
+    ensure_mips();
+    const size_t mip_level = f2usize(std::log2(node_bounds.size / (float)brick_dim));
+    MipSampler sampler;  // MIPResamplingMethods::default() == BoxFilter
+    {
+        auto it = mip_map_strategy.resampling_methods.find(mip_level);
+        if (it != mip_map_strategy.resampling_methods.end()) sampler = it->second;
+    }
+    const bool dominant_bottom = sampler.method == MipMethod::PointFilterBD;  // :309-314: PosterizeBD is NOT matched here
+
+    const NodeKind kind = nodes.item[node_key].kind;
+    V3u sample_start{0, 0, 0};
+    uint32_t sample_size = 0;
+    const uint32_t size_u = f2u32(node_bounds.size);
+    switch (kind) {
+        case NodeKind::Nothing: return;
+        case NodeKind::UniformLeaf:
+            // Uniform leaf nodes need no MIP, their content is equivalent with it (:331-337)
+            node_mips[node_key] = Brick();
+            return;
+        case NodeKind::Leaf: {
+            sample_size = std::min(size_u / brick_dim, brick_dim * 2);
+            const V3u t = {(position.x - (position.x % sample_size)) * 2 * brick_dim,
+                           (position.y - (position.y % sample_size)) * 2 * brick_dim,
+                           (position.z - (position.z % sample_size)) * 2 * brick_dim};
+            const V3f f = to_f32(t) / node_bounds.size;
+            sample_start = {f2u32_round(std::floor(f.x)), f2u32_round(std::floor(f.y)), f2u32_round(std::floor(f.z))};
+            break;
+        }
+        case NodeKind::Internal:
+            if (dominant_bottom) {
+                sample_size = size_u / brick_dim;
+                const V3f f = to_f32(V3u{position.x - (position.x % sample_size), position.y - (position.y % sample_size),
+                                         position.z - (position.z % sample_size)});
+                sample_start = {f2u32_round(std::floor(f.x)), f2u32_round(std::floor(f.y)), f2u32_round(std::floor(f.z))};
+            } else {
+                sample_size = 2;
+                const V3f pos_in_bounds = to_f32(position) - node_bounds.min_position;
+                const V3f f = pos_in_bounds * 2.0f * (float)brick_dim / node_bounds.size;  // into 2*DIM space
+                sample_start = {f2u32_round(std::floor(f.x)), f2u32_round(std::floor(f.y)), f2u32_round(std::floor(f.z))};
+                sample_start = {sample_start.x - (sample_start.x % 2), sample_start.y - (sample_start.y % 2),
+                                sample_start.z - (sample_start.z % 2)};
+            }
+            break;
+    }
+
+    auto sample_tree = [&](V3u pos, Albedo* out) { return entry_albedo(get_internal(node_key, node_bounds, pos), out); };
+    Albedo sampled_color{0, 0, 0, 0};
+    bool have_color = false;
+    if (kind == NodeKind::Leaf || (kind == NodeKind::Internal && dominant_bottom)) {
+        have_color = mip_sample(sampler, sample_start, sample_size, sample_tree, &sampled_color);
+    } else {  // Internal: sample the MIPs of the children; the range spans 0 .. 2*brick_dim (:458-511)
+        const Children& ch = node_children[node_key];
+        if ((size_t)EMPTY_MARKER_U32 != child_of(ch, hash_region(to_f32(sample_start), (float)brick_dim))) {
+            auto sample_child_mips = [&](V3u pos, Albedo* out) -> bool {
+                const uint8_t child_octant = hash_region(to_f32(pos), (float)brick_dim);
+                const size_t child_key = child_of(ch, child_octant);
+                if ((size_t)EMPTY_MARKER_U32 == child_key) return false;
+                if (child_key >= node_mips.size()) return false;  // the reference would index out of bounds and panic
+                const V3f off = luts().octant_offset[child_octant] * (float)brick_dim;
+                const V3u p = {pos.x - f2u32_round(off.x), pos.y - f2u32_round(off.y), pos.z - f2u32_round(off.z)};
+                const Brick& m = node_mips[child_key];
+                switch (m.kind) {
+                    case BrickKind::Empty: return false;
+                    case BrickKind::Solid: return entry_albedo(pix_get_ref(m.solid), out);
+                    case BrickKind::Parted: return entry_albedo(pix_get_ref(m.data[flat_projection(p.x, p.y, p.z, brick_dim)]), out);
+                }
+                return false;
+            };
+            have_color = mip_sample(sampler, sample_start, sample_size, sample_child_mips, &sampled_color);
+        }
+    }
+    if (!have_color) return;  // a MIP entry is never cleared (:513-548 only ever writes Some)
+
+    // Assemble MIP entry (:513-548)
+    Entry visual;
+    visual.kind = EntryKind::Visual;
+    visual.albedo = sampled_color;
+    uint32_t mip_entry;
+    auto thr_it = mip_map_strategy.resampling_color_matching_thresholds.find(mip_level);
+    if (thr_it != mip_map_strategy.resampling_color_matching_thresholds.end()) {
+        const float color_distance_threshold = thr_it->second * 255.0f;
+        bool found = false;
+        size_t similar = 0;
+        for (size_t i = 0; i < voxel_color_palette.size(); ++i)
+            if (albedo_distance(sampled_color, voxel_color_palette[i]) < color_distance_threshold) {
+                similar = i;
+                found = true;
+                break;
+            }
+        mip_entry = found ? pix_visual((uint16_t)similar) : add_to_palette(visual);
+    } else {
+        mip_entry = add_to_palette(visual);
+    }
+
+    // Set MIP entry (:550-581)
+    const V3s pim = matrix_index_for(node_bounds, position, brick_dim);
+    const size_t flat = flat_projection(pim.x, pim.y, pim.z, brick_dim);
+    Brick& mip = node_mips[node_key];
+    const size_t volume = (size_t)brick_dim * brick_dim * brick_dim;
+    switch (mip.kind) {
+        case BrickKind::Empty:
+            mip.data.assign(volume, EMPTY_MARKER_U32);
+            mip.kind = BrickKind::Parted;
+            break;
+        case BrickKind::Solid:
+            mip.data.assign(volume, mip.solid);
+            mip.kind = BrickKind::Parted;
+            break;
+        case BrickKind::Parted: break;
+    }
+    mip.witness = 0;
+    mip.witness2 = 0xFFFFFFFFu;
+    if (flat < mip.data.size()) mip.data[flat] = mip_entry;
+}
+
+// mipmap.rs:875-892
+void Octree::recalculate_mip(size_t node_key, const Cube& node_bounds) {
+    if (!mip_map_strategy.enabled) return;
+    for (uint32_t x = 0; x < brick_dim; ++x)
+        for (uint32_t y = 0; y < brick_dim; ++y)
+            for (uint32_t z = 0; z < brick_dim; ++z) {
+                const V3f o = V3f{(float)x, (float)y, (float)z} * node_bounds.size / (float)brick_dim;
+                const V3f pos = node_bounds.min_position + V3f{std::round(o.x), std::round(o.y), std::round(o.z)};
+                update_mip(node_key, node_bounds, V3u{f2u32_round(pos.x), f2u32_round(pos.y), f2u32_round(pos.z)});
+            }
+}
+
+// mipmap.rs:798-855: depth first, children (ascending octant) before their parent
+void Octree::recalculate_mips() {
+    node_mips.assign(nodes.len(), Brick());
+    struct Frame {
+        size_t key;
+        Cube bounds;
+        uint8_t target_octant;
+    };
+    std::vector<Frame> node_stack;
+    node_stack.push_back({0, Cube{unit(0.0f), (float)octree_size}, 0});
+    while (!node_stack.empty()) {
+        Frame& top = node_stack.back();
+        if (OOB_OCTANT == top.target_octant) {
+            const size_t key = top.key;
+            const Cube bounds = top.bounds;
+            recalculate_mip(key, bounds);
+            node_stack.pop_back();
+            if (!node_stack.empty()) node_stack.back().target_octant += 1;
+            continue;
+        }
+        switch (nodes.item[top.key].kind) {
+            case NodeKind::Nothing:
+                // unreachable!() in the reference: only a Nothing ROOT can get here and the public entry point
+                // (switch_albedo_mip_maps) checks for it; recalculate_mips() on an empty tree would panic
+                node_stack.pop_back();
+                break;
+            case NodeKind::Internal: {
+                const size_t child = child_of(node_children[top.key], top.target_octant);
+                if (nodes.key_is_valid(child) && nodes.item[child].kind != NodeKind::Nothing) {
+                    const Cube cb = child_bounds_for(top.bounds, top.target_octant);
+                    node_stack.push_back({child, cb, 0});
+                } else {
+                    top.target_octant += 1;
+                }
+                break;
+            }
+            case NodeKind::Leaf:
+            case NodeKind::UniformLeaf: top.target_octant = OOB_OCTANT; break;
+        }
+    }
+}
+
+// mipmap.rs:858-872
+void Octree::switch_albedo_mip_maps(bool enabled) {
+    const bool mips_on_previously = mip_map_strategy.enabled;
+    mip_map_strategy.enabled = enabled;
+    if (mip_map_strategy.enabled && mips_on_previously != enabled && nodes.item[0].kind != NodeKind::Nothing)
+        recalculate_mips();
+}
+
+// mipmap.rs:897-937
+Entry Octree::sample_root_mip(uint8_t octant, V3u position) const {
+    const size_t node_key = OOB_OCTANT == octant ? 0 : child_of(node_children[0], octant);
+    if (!nodes.key_is_valid(node_key) || node_key >= node_mips.size()) return Entry();
+    const Brick& m = node_mips[node_key];
+    switch (m.kind) {
+        case BrickKind::Empty: return Entry();
+        case BrickKind::Solid: return pix_get_ref(m.solid);
+        case BrickKind::Parted: return pix_get_ref(m.data[flat_projection(position.x, position.y, position.z, brick_dim)]);
+    }
+    return Entry();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1530,6 +1937,33 @@ uint64_t Octree::structure_hash() const {
     h = mix64(h, 0xDA7A);
     for (uint32_t d : voxel_data_palette) h = mix64(h, d);
     return mix64(h, hash_node(0));
+}
+
+// MIP digest: the strategy plus the MIP brick of every reachable node, in the same traversal order as hash_node
+static uint64_t mip_hash_node(const Octree& t, size_t key) {
+    static const Brick none;
+    uint64_t h = mix64(0x313D, hash_brick(key < t.node_mips.size() ? t.node_mips[key] : none));
+    if (t.nodes.item[key].kind == NodeKind::Internal)
+        for (uint8_t o = 0; o < 8; ++o) {
+            const size_t c = child_of(t.node_children[key], o);
+            h = mix64(h, t.nodes.key_is_valid(c) ? mip_hash_node(t, c) : 0x5EED);
+        }
+    return h;
+}
+uint64_t Octree::mip_hash() const {
+    uint64_t h = mix64(0x57A7, mip_map_strategy.enabled ? 1 : 0);
+    for (const auto& m : mip_map_strategy.resampling_methods) {
+        uint32_t bits;
+        std::memcpy(&bits, &m.second.thr, 4);
+        h = mix64(mix64(mix64(h, m.first), (uint64_t)m.second.method), bits);
+    }
+    h = mix64(h, 0x7447);
+    for (const auto& m : mip_map_strategy.resampling_color_matching_thresholds) {
+        uint32_t bits;
+        std::memcpy(&bits, &m.second, 4);
+        h = mix64(mix64(h, m.first), bits);
+    }
+    return mix64(h, mip_hash_node(*this, 0));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1626,8 +2060,11 @@ bool Octree::probe_brick(const Ray& ray, V3f& p, const Brick& brick, const Cube&
     return false;
 }
 
-// :316-565 (viewing_distance = f32::MAX, MIP maps disabled -> the LOD branch :369-386 is dead)
-Hit Octree::get_by_ray(const Ray& ray, RayStats* st) const {
+// :316-318
+Hit Octree::get_by_ray(const Ray& ray, RayStats* st) const { return get_by_ray_at_lod(ray, std::numeric_limits<float>::max(), st); }
+
+// :325-565
+Hit Octree::get_by_ray_at_lod(const Ray& ray, float viewing_distance, RayStats* st) const {
     Hit result;
     const Luts& l = luts();
     const V3f ray_scale_factors = get_dda_scale_factors(ray);
@@ -1650,6 +2087,9 @@ Hit Octree::get_by_ray(const Ray& ray, RayStats* st) const {
         }
     }
     size_t current_node_key;
+    // :349; never reset at a restart from the root and not decremented by the root push, so it drifts by +1 per
+    // completed root cycle (and the other way when the 4-entry ring stack loses entries) - kept as is
+    float mip_level = std::log2((float)octree_size / (float)brick_dim);
 
     auto bitmap_index = [&](const V3f& bp) -> size_t {
         // `f.floor() as usize` saturates; an index > 3 bounds-panics in the reference
@@ -1675,6 +2115,21 @@ Hit Octree::get_by_ray(const Ray& ray, RayStats* st) const {
             const Node& cur = nodes.item[current_node_key];
             bool do_backtrack_after_leaf_miss = (cur.kind == NodeKind::UniformLeaf);
 
+            // :368-386 the node's MIP stands in for its content once the ray has travelled far enough; a miss
+            // leaves ray_current_point advanced by the brick walk and target_octant untouched
+            if (mip_map_strategy.enabled) {
+                const float m2 = mip_level * 2.0f;
+                const V3f q = ray_current_point / m2;
+                const V3f aligned = V3f{std::round(q.x), std::round(q.y), std::round(q.z)} * m2;
+                if (mip_level < length(ray.origin - aligned) / viewing_distance) {
+                    if (st) st->mip_probes++;
+                    static const Brick no_mip;
+                    const Brick& mip = current_node_key < node_mips.size() ? node_mips[current_node_key] : no_mip;
+                    if (probe_brick(ray, ray_current_point, mip, current_bounds, ray_scale_factors, result, st))
+                        return result;
+                }
+            }
+
             if (target_octant != OOB_OCTANT) {
                 if (cur.kind == NodeKind::UniformLeaf) {
                     if (probe_brick(ray, ray_current_point, cur.ubrick, current_bounds, ray_scale_factors, result, st))
@@ -1698,6 +2153,7 @@ Hit Octree::get_by_ray(const Ray& ray, RayStats* st) const {
                 0 == (current_node_occupied_bits & l.ray_to_node_occupancy[flat_pos_in_bitmap][direction_lut_index])) {
                 // POP
                 node_stack.pop(nullptr);
+                mip_level += 1.0f;
                 if (const uint32_t* parent = node_stack.last()) {
                     current_node_key = *parent;
                     const V3f current_bound_center = current_bounds.min_position + unit(current_bounds.size / 2.0f);
@@ -1724,6 +2180,7 @@ Hit Octree::get_by_ray(const Ray& ray, RayStats* st) const {
                 current_bounds = target_bounds;
                 target_octant = hash_region(ray_current_point - target_bounds.min_position, target_bounds.size / 2.0f);
                 node_stack.push(target_child_key);
+                mip_level -= 1.0f;
             } else {
                 // ADVANCE
                 for (;;) {

@@ -17,6 +17,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -138,11 +139,26 @@ struct NodeStack {
     T* last_mut() { return 0 == count ? nullptr : &data[head_index]; }
 };
 
+// src/octree/types.rs:104-139 MIPResamplingMethods; :149-161 MIPMapStrategy (HashMap -> ordered map: the reference never
+// depends on the iteration order of these two maps except when it writes them to a file, where any order is valid)
+enum class MipMethod : uint8_t { BoxFilter = 0, PointFilter = 1, PointFilterBD = 2, Posterize = 3, PosterizeBD = 4 };
+struct MipSampler {
+    MipMethod method = MipMethod::BoxFilter;
+    float thr = 0.0f;  // Posterize / PosterizeBD parameter
+};
+struct MipStrategy {
+    bool enabled = false;
+    std::map<size_t, MipSampler> resampling_methods;
+    std::map<size_t, float> resampling_color_matching_thresholds;
+    MipStrategy();  // MIPMapStrategy::default(), mipmap.rs:591-604
+};
+
 struct RayStats {
     uint32_t node_iters = 0;    // iterations of the inner `while !node_stack.is_empty()` loop (raytracing_on_cpu.rs:356)
     uint32_t voxel_fetches = 0; // brick voxel reads in traverse_brick (raytracing_on_cpu.rs:218)
     uint32_t outer_iters = 0;   // iterations of `while target_octant != OOB_OCTANT` (raytracing_on_cpu.rs:352)
     uint32_t would_panic = 0;   // an index the Rust code would have bounds-panicked on
+    uint32_t mip_probes = 0;    // LOD branch taken: a node's MIP brick was probed (raytracing_on_cpu.rs:377)
     uint32_t crawl_iters = 0;   // outer iterations whose node loop ran once: the root failed its occupancy test and was popped
 };
 
@@ -166,7 +182,20 @@ class Octree {
     Status clear_at_lod(V3u position, uint32_t clear_size);           // src/octree/update/clear.rs:55-348
     Entry get(V3u position) const;
     uint32_t get_size() const { return octree_size; }
-    Hit get_by_ray(const Ray& ray, RayStats* stats = nullptr) const;
+    Hit get_by_ray(const Ray& ray, RayStats* stats = nullptr) const;  // raytracing_on_cpu.rs:316-318
+    Hit get_by_ray_at_lod(const Ray& ray, float viewing_distance, RayStats* stats = nullptr) const;  // :325-565
+
+    // ---- MIP maps: src/octree/mipmap.rs (svx_oracle_mip.cpp); StrategyUpdater methods :716-938
+    MipStrategy mip_map_strategy;
+    std::vector<Brick> node_mips;  // types.rs:186; always as long as the node buffer
+    void switch_albedo_mip_maps(bool enabled);                       // mipmap.rs:858-872
+    void recalculate_mips();                                         // mipmap.rs:798-855
+    void mip_set_method_at(size_t mip_level, MipSampler method);     // mipmap.rs:657-672
+    MipSampler mip_get_method_at(size_t mip_level) const;            // mipmap.rs:650-655
+    void mip_set_color_similarity_thr_at(size_t mip_level, float thr);  // mipmap.rs:617-630
+    float mip_get_new_color_similarity_at(size_t mip_level) const;   // mipmap.rs:610-615
+    void mip_reset() { mip_map_strategy = MipStrategy(); }           // mipmap.rs:718-721
+    Entry sample_root_mip(uint8_t octant, V3u position) const;       // mipmap.rs:897-937 (the reference's test hook)
 
     bool auto_simplify = true;
 
@@ -185,6 +214,7 @@ class Octree {
     bool pix_points_to_empty(uint32_t index) const;
     Entry pix_get_ref(uint32_t index) const;
     uint64_t structure_hash() const;  // key-order independent hash of the reachable tree
+    uint64_t mip_hash() const;        // the same for the MIP strategy and the MIP bricks of the reachable nodes
 
    private:
     Status insert_at_lod_internal(bool overwrite_if_empty, V3u position, uint32_t insert_size, const Entry& data);
@@ -206,6 +236,10 @@ class Octree {
     bool brick_is_empty_throughout(const Brick& b, uint8_t octant) const;
     bool brick_is_part_empty_throughout(const Brick& b, uint8_t part_octant, uint8_t target_octant) const;
     uint64_t hash_node(size_t key) const;
+    Entry get_internal(size_t node_key, Cube bounds, V3u position) const;  // mod.rs:220-371
+    void ensure_mips() { if (node_mips.size() < nodes.len()) node_mips.resize(nodes.len()); }  // insert.rs:168, detail.rs:356
+    void update_mip(size_t node_key, const Cube& node_bounds, V3u position);  // mipmap.rs:296-584
+    void recalculate_mip(size_t node_key, const Cube& node_bounds);           // mipmap.rs:875-892
 
     // ray helpers
     bool traverse_brick(const Ray& ray, V3f& p, const std::vector<uint32_t>& brick, const Cube& bounds,

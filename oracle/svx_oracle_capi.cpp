@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <thread>
 
@@ -47,7 +48,7 @@ struct svxo_hit {
     float impact_point[3];
     float normal[3];
     float distance;  // (impact_point - ray.origin).length(), vector.rs:75-77
-    uint32_t node_iters, voxel_fetches, outer_iters, would_panic, crawl_iters;
+    uint32_t node_iters, voxel_fetches, outer_iters, would_panic, crawl_iters, mip_probes;
 };
 
 struct svxo_camera {
@@ -196,19 +197,54 @@ static void fill_hit(const Hit& h, const Ray& ray, const RayStats& st, svxo_hit*
     out->outer_iters = st.outer_iters;
     out->would_panic = st.would_panic;
     out->crawl_iters = st.crawl_iters;
+    out->mip_probes = st.mip_probes;
 }
 
-void svxo_octree_get_by_ray(void* t, const float origin[3], const float direction[3], svxo_hit* out) {
+// Octree::get_by_ray_at_lod (raytracing_on_cpu.rs:325); get_by_ray is viewing_distance = f32::MAX (:316-318)
+void svxo_octree_get_by_ray_at_lod(void* t, const float origin[3], const float direction[3], float viewing_distance,
+                                   svxo_hit* out) {
     Ray ray{{origin[0], origin[1], origin[2]}, {direction[0], direction[1], direction[2]}};
     RayStats st;
-    Hit h = ((Octree*)t)->get_by_ray(ray, &st);
+    Hit h = ((Octree*)t)->get_by_ray_at_lod(ray, viewing_distance, &st);
     fill_hit(h, ray, st, out);
+}
+void svxo_octree_get_by_ray(void* t, const float origin[3], const float direction[3], svxo_hit* out) {
+    svxo_octree_get_by_ray_at_lod(t, origin, direction, std::numeric_limits<float>::max(), out);
 }
 
 // rays[n][6] = origin xyz, direction xyz
-void svxo_octree_get_by_rays(void* t, const float* rays, uint64_t n, svxo_hit* out) {
-    for (uint64_t i = 0; i < n; ++i) svxo_octree_get_by_ray(t, rays + 6 * i, rays + 6 * i + 3, &out[i]);
+void svxo_octree_get_by_rays_at_lod(void* t, const float* rays, uint64_t n, float viewing_distance, svxo_hit* out) {
+    for (uint64_t i = 0; i < n; ++i)
+        svxo_octree_get_by_ray_at_lod(t, rays + 6 * i, rays + 6 * i + 3, viewing_distance, &out[i]);
 }
+void svxo_octree_get_by_rays(void* t, const float* rays, uint64_t n, svxo_hit* out) {
+    svxo_octree_get_by_rays_at_lod(t, rays, n, std::numeric_limits<float>::max(), out);
+}
+
+// ---- MIP maps (src/octree/mipmap.rs): StrategyUpdater surface + the reference's sample_root_mip test hook
+void svxo_octree_mip_switch(void* t, int32_t enabled) { ((Octree*)t)->switch_albedo_mip_maps(enabled != 0); }
+int32_t svxo_octree_mip_enabled(void* t) { return ((Octree*)t)->mip_map_strategy.enabled ? 1 : 0; }
+// method: 0 BoxFilter, 1 PointFilter, 2 PointFilterBD, 3 Posterize(thr), 4 PosterizeBD(thr)
+void svxo_octree_mip_set_method_at(void* t, uint64_t level, uint32_t method, float thr) {
+    ((Octree*)t)->mip_set_method_at((size_t)level, MipSampler{(MipMethod)method, thr});
+}
+uint32_t svxo_octree_mip_get_method_at(void* t, uint64_t level, float* thr) {
+    const MipSampler m = ((Octree*)t)->mip_get_method_at((size_t)level);
+    if (thr) *thr = m.thr;
+    return (uint32_t)m.method;
+}
+void svxo_octree_mip_set_color_similarity_thr_at(void* t, uint64_t level, float thr) {
+    ((Octree*)t)->mip_set_color_similarity_thr_at((size_t)level, thr);
+}
+float svxo_octree_mip_get_color_similarity_at(void* t, uint64_t level) {
+    return ((Octree*)t)->mip_get_new_color_similarity_at((size_t)level);
+}
+void svxo_octree_mip_reset(void* t) { ((Octree*)t)->mip_reset(); }
+void svxo_octree_mip_recalculate(void* t) { ((Octree*)t)->recalculate_mips(); }
+void svxo_octree_mip_sample_root(void* t, uint32_t octant, uint32_t x, uint32_t y, uint32_t z, svxo_entry* out) {
+    from_entry(((Octree*)t)->sample_root_mip((uint8_t)octant, V3u{x, y, z}), out);
+}
+uint64_t svxo_octree_mip_hash(void* t) { return ((Octree*)t)->mip_hash(); }
 
 void svxo_make_pixel_ray(const svxo_camera* c, uint32_t w, uint32_t h, uint32_t x, uint32_t y, float out[6]) {
     Camera cam{{c->origin[0], c->origin[1], c->origin[2]}, {c->direction[0], c->direction[1], c->direction[2]},
@@ -223,20 +259,21 @@ void svxo_make_pixel_ray(const svxo_camera* c, uint32_t w, uint32_t h, uint32_t 
 // Outputs (any may be null) are full [h*w] planes; only the listed rows are written. counters[6] (optional) receives
 // {sum node_iters, sum voxel_fetches, sum outer_iters, rays that entered the root cube, would_panic, sum crawl_iters}.
 // Returns wall-clock seconds spent in the pixel loop.
-double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
-                        uint32_t threads, uint32_t* hit_id, uint8_t* albedo, float* distance, float* normal,
-                        uint64_t* counters) {
+// counters[6] (7 values in the _lod variant: + MIP probes). viewing_distance as in get_by_ray_at_lod.
+double svxo_render_rows_lod(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
+                            uint32_t threads, float viewing_distance, uint32_t* hit_id, uint8_t* albedo, float* distance,
+                            float* normal, uint64_t* counters7) {
     Octree* tree = (Octree*)t;
     Camera cam{{c->origin[0], c->origin[1], c->origin[2]}, {c->direction[0], c->direction[1], c->direction[2]},
                c->glass_width, c->glass_height, c->glass_distance};
     if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
-    std::atomic<uint64_t> acc[6];
+    std::atomic<uint64_t> acc[7];
     for (auto& a : acc) a = 0;
     constexpr uint64_t CHUNK = 64;
     const uint64_t total = (uint64_t)n_rows * w;
     std::atomic<uint64_t> next{0};
     auto worker = [&]() {
-        uint64_t local[6] = {0, 0, 0, 0, 0, 0};
+        uint64_t local[7] = {0, 0, 0, 0, 0, 0, 0};
         for (;;) {
             const uint64_t begin = next.fetch_add(CHUNK);
             if (begin >= total) break;
@@ -246,7 +283,7 @@ double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, c
                 const uint32_t y = h - 1 - row;
                 const Ray ray = make_pixel_ray(cam, w, h, x, y);
                 RayStats st;
-                const Hit hit = tree->get_by_ray(ray, &st);
+                const Hit hit = tree->get_by_ray_at_lod(ray, viewing_distance, &st);
                 const size_t i = (size_t)row * w + x;
                 if (hit_id) hit_id[i] = hit.hit ? hit.palette_value : 0xFFFFFFFFu;
                 if (albedo) {
@@ -271,9 +308,10 @@ double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, c
                 local[3] += st.outer_iters > 0 ? 1 : 0;
                 local[4] += st.would_panic;
                 local[5] += st.crawl_iters;
+                local[6] += st.mip_probes;
             }
         }
-        for (int k = 0; k < 6; ++k) acc[k] += local[k];
+        for (int k = 0; k < 7; ++k) acc[k] += local[k];
     };
     const auto t0 = std::chrono::steady_clock::now();
     if (threads == 1) {
@@ -284,9 +322,19 @@ double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, c
         for (auto& th : pool) th.join();
     }
     const auto t1 = std::chrono::steady_clock::now();
-    if (counters)
-        for (int k = 0; k < 6; ++k) counters[k] = acc[k];
+    if (counters7)
+        for (int k = 0; k < 7; ++k) counters7[k] = acc[k];
     return std::chrono::duration<double>(t1 - t0).count();
+}
+double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
+                        uint32_t threads, uint32_t* hit_id, uint8_t* albedo, float* distance, float* normal,
+                        uint64_t* counters) {
+    uint64_t c7[7];
+    const double s = svxo_render_rows_lod(t, c, w, h, rows, n_rows, threads, std::numeric_limits<float>::max(), hit_id,
+                                          albedo, distance, normal, c7);
+    if (counters)
+        for (int k = 0; k < 6; ++k) counters[k] = c7[k];
+    return s;
 }
 
 // Rows [row_begin, row_end) of one frame

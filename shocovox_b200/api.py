@@ -35,6 +35,9 @@ E_OUT_OF_MEMORY = -2
 ENTRY_EMPTY, ENTRY_VISUAL, ENTRY_INFORMATIVE, ENTRY_COMPLEX = 0, 1, 2, 3
 GLASS_AT_FOV, GLASS_AT_FRUSTUM_Z = 0, 1
 MISS = 0xFFFFFFFF
+F32_MAX = 3.4028234663852886e38  # f32::MAX: the viewing distance of Octree::get_by_ray (raytracing_on_cpu.rs:316-318)
+# MIPResamplingMethods (src/octree/types.rs:106-139) as (method, parameter) of the C ABI's svx_mip_method
+MIP_BOX_FILTER, MIP_POINT_FILTER, MIP_POINT_FILTER_BD, MIP_POSTERIZE, MIP_POSTERIZE_BD = 0, 1, 2, 3, 4
 
 
 class OctreeError(Exception):
@@ -137,6 +140,10 @@ EXPORTS = [
     "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
     "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
     "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count",
+    "svx_octree_switch_albedo_mip_maps", "svx_octree_mip_maps_enabled", "svx_octree_recalculate_mips",
+    "svx_octree_mip_set_method_at", "svx_octree_mip_get_method_at", "svx_octree_mip_set_color_similarity_thr_at",
+    "svx_octree_mip_get_color_similarity_at", "svx_octree_mip_reset", "svx_octree_mip_sample_root", "svx_octree_mip_hash",
+    "svx_gpu_host_get_by_rays_at_lod", "svx_view_set_viewing_distance", "svx_view_get_viewing_distance",
     "svx_octree_to_bytes", "svx_bytes_free", "svx_octree_from_bytes", "svx_octree_save", "svx_octree_load",
     "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_last_upload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
@@ -195,6 +202,22 @@ def lib() -> C.CDLL:
     L.svx_octree_structure_hash.restype = u64
     L.svx_octree_node_count.argtypes = [vp]
     L.svx_octree_node_count.restype = u64
+    f32 = C.c_float
+    L.svx_octree_switch_albedo_mip_maps.argtypes = [vp, i32]
+    L.svx_octree_mip_maps_enabled.argtypes = [vp]
+    L.svx_octree_recalculate_mips.argtypes = [vp]
+    L.svx_octree_mip_set_method_at.argtypes = [vp, u64, i32, f32]
+    L.svx_octree_mip_get_method_at.argtypes = [vp, u64, C.POINTER(i32), C.POINTER(f32)]
+    L.svx_octree_mip_set_color_similarity_thr_at.argtypes = [vp, u64, f32]
+    L.svx_octree_mip_get_color_similarity_at.argtypes = [vp, u64]
+    L.svx_octree_mip_get_color_similarity_at.restype = f32
+    L.svx_octree_mip_reset.argtypes = [vp]
+    L.svx_octree_mip_sample_root.argtypes = [vp, u32, u32, u32, u32, C.POINTER(_Entry)]
+    L.svx_octree_mip_hash.argtypes = [vp]
+    L.svx_octree_mip_hash.restype = u64
+    L.svx_gpu_host_get_by_rays_at_lod.argtypes = [vp, vp, u64, f32, vp]
+    L.svx_view_set_viewing_distance.argtypes = [vp, f32]
+    L.svx_view_get_viewing_distance.argtypes = [vp, C.POINTER(f32)]
     L.svx_gpu_host_create.argtypes = [vp, i32, C.POINTER(vp)]
     L.svx_gpu_host_free.argtypes = [vp]
     L.svx_gpu_host_free.restype = None
@@ -434,6 +457,10 @@ class Octree:
     def node_count(self) -> int:
         return int(lib().svx_octree_node_count(self._h))
 
+    # ---- MIP maps: Octree::albedo_mip_map_resampling_strategy() (src/octree/mod.rs:379) ----
+    def albedo_mip_map_resampling_strategy(self) -> "StrategyUpdater":
+        return StrategyUpdater(self)
+
     # ---- bencode persistence, src/octree/mod.rs:138-168 ----
     @classmethod
     def _adopt(cls, handle: C.c_void_p) -> "Octree":
@@ -466,13 +493,80 @@ class Octree:
 
     # `Octree::get_by_ray(&Ray)`: one ray, on the GPU (a host is created on first use and reloaded after edits)
     def get_by_ray(self, ray: Ray, device: int = 0) -> Optional[RayHit]:
+        return self.get_by_ray_at_lod(ray, F32_MAX, device)
+
+    # `Octree::get_by_ray_at_lod(&Ray, viewing_distance)` (src/raytracing/raytracing_on_cpu.rs:325)
+    def get_by_ray_at_lod(self, ray: Ray, viewing_distance: float, device: int = 0) -> Optional[RayHit]:
         host = getattr(self, "_ray_host", None)
         if host is None or host.device != device:
             host = OctreeGPUHost(self, device)
             self._ray_host = host
         else:
             host.reload()
-        return host.get_by_ray(ray)
+        return host.get_by_ray(ray, viewing_distance)
+
+
+class StrategyUpdater:
+    """StrategyUpdater<'a, T> (src/octree/types.rs:142, src/octree/mipmap.rs:716-938): chainable MIP map settings of one
+    tree, e.g. `tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True).set_method_at(1, MIP_BOX_FILTER)`."""
+
+    def __init__(self, tree: Octree):
+        self._tree = tree
+
+    def reset(self) -> "StrategyUpdater":
+        _check(lib().svx_octree_mip_reset(self._tree.handle))
+        return self
+
+    def is_enabled(self) -> bool:
+        return bool(lib().svx_octree_mip_maps_enabled(self._tree.handle))
+
+    def switch_albedo_mip_maps(self, enabled: bool) -> "StrategyUpdater":
+        _check(lib().svx_octree_switch_albedo_mip_maps(self._tree.handle, 1 if enabled else 0))
+        return self
+
+    def recalculate_mips(self) -> "StrategyUpdater":
+        _check(lib().svx_octree_recalculate_mips(self._tree.handle))
+        return self
+
+    def get_new_color_similarity_at(self, mip_level: int) -> float:
+        return float(lib().svx_octree_mip_get_color_similarity_at(self._tree.handle, int(mip_level)))
+
+    def set_color_similarity_thr_at(self, mip_level: int, similarity_thr: float) -> "StrategyUpdater":
+        _check(lib().svx_octree_mip_set_color_similarity_thr_at(self._tree.handle, int(mip_level), float(similarity_thr)))
+        return self
+
+    def set_color_similarity_thr(self, levels) -> "StrategyUpdater":
+        for mip_level, thr in levels:
+            self.set_color_similarity_thr_at(mip_level, thr)
+        return self
+
+    def get_method_at(self, mip_level: int):
+        """-> (method, parameter); the parameter is the Posterize threshold, 0.0 for the other methods"""
+        m, thr = C.c_int32(), C.c_float()
+        _check(lib().svx_octree_mip_get_method_at(self._tree.handle, int(mip_level), C.byref(m), C.byref(thr)))
+        return int(m.value), float(thr.value)
+
+    def set_method_at(self, mip_level: int, method: int, threshold: float = 0.0) -> "StrategyUpdater":
+        _check(lib().svx_octree_mip_set_method_at(self._tree.handle, int(mip_level), int(method), float(threshold)))
+        return self
+
+    def set_method(self, levels) -> "StrategyUpdater":
+        for mip_level, method in levels:
+            if isinstance(method, (tuple, list)):
+                self.set_method_at(mip_level, method[0], method[1])
+            else:
+                self.set_method_at(mip_level, method)
+        return self
+
+    def sample_root_mip(self, octant: int, position) -> OctreeEntry:
+        """The reference's test hook (mipmap.rs:897-937): MIP voxel of the root (octant 8) or of one of its children."""
+        e = _Entry()
+        _check(lib().svx_octree_mip_sample_root(self._tree.handle, int(octant), int(position[0]), int(position[1]),
+                                                int(position[2]), C.byref(e)))
+        return OctreeEntry._from_c(e)
+
+    def mip_hash(self) -> int:
+        return int(lib().svx_octree_mip_hash(self._tree.handle))
 
 
 # ---- OctreeGPUHost / OctreeGPUView ----------------------------------------------------------------------------------
@@ -504,16 +598,18 @@ class OctreeGPUHost:
         _check(lib().svx_gpu_host_last_upload(self._h, C.byref(s)))
         return {"bricks": int(s.bricks), "bytes": int(s.bytes), "full": bool(s.full), "bits_kernel_ms": float(s.bits_kernel_ms)}
 
-    def get_by_rays(self, rays: np.ndarray) -> np.ndarray:
-        """rays: [n,6] f32 (origin xyz, direction xyz) -> structured array (HIT_DTYPE)."""
+    def get_by_rays(self, rays: np.ndarray, viewing_distance: float = F32_MAX) -> np.ndarray:
+        """rays: [n,6] f32 (origin xyz, direction xyz) -> structured array (HIT_DTYPE). viewing_distance is
+        get_by_ray_at_lod's parameter; the default (f32::MAX) is get_by_ray."""
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
         out = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
-        _check(lib().svx_gpu_host_get_by_rays(self._h, rays.ctypes.data, rays.shape[0], out.ctypes.data))
+        _check(lib().svx_gpu_host_get_by_rays_at_lod(self._h, rays.ctypes.data, rays.shape[0], float(viewing_distance),
+                                                     out.ctypes.data))
         return out
 
-    def get_by_ray(self, ray: Ray) -> Optional[RayHit]:
+    def get_by_ray(self, ray: Ray, viewing_distance: float = F32_MAX) -> Optional[RayHit]:
         r = np.concatenate([np.asarray(ray.origin, dtype=np.float32), np.asarray(ray.direction, dtype=np.float32)])
-        h = self.get_by_rays(r[None, :])[0]
+        h = self.get_by_rays(r[None, :], viewing_distance)[0]
         if not h["hit"]:
             return None
         kind = int(h["entry_kind"])
@@ -557,6 +653,16 @@ class OctreeGPUView:
 
     def set_glass_mode(self, mode: int):
         _check(lib().svx_view_set_glass_mode(self._h, int(mode)))
+
+    def set_viewing_distance(self, viewing_distance: float):
+        """Viewing distance of every pixel's get_by_ray_at_lod (default f32::MAX = get_by_ray; the reference's GPU
+        path uses viewport.frustum.z). Only matters while the tree's MIP maps are enabled."""
+        _check(lib().svx_view_set_viewing_distance(self._h, float(viewing_distance)))
+
+    def viewing_distance(self) -> float:
+        d = C.c_float()
+        _check(lib().svx_view_get_viewing_distance(self._h, C.byref(d)))
+        return float(d.value)
 
     def set_resolution(self, resolution: Sequence[int]):
         _check(lib().svx_view_set_resolution(self._h, int(resolution[0]), int(resolution[1])))

@@ -17,7 +17,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libshocovox_b200.so"
-SOURCES = ["host_octree.cpp", "host_octree_io.cpp", "gpu_tree.cpp", "kernels.cu", "capi.cu"]
+SOURCES = ["host_octree.cpp", "host_octree_mip.cpp", "host_octree_io.cpp", "gpu_tree.cpp", "kernels.cu", "capi.cu"]
 HEADERS = ["host_octree.hpp", "gpu_tree.hpp", "kernels.cuh", "traverse.cuh", "../../include/shocovox_b200.h"]
 
 

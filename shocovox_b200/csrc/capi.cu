@@ -134,6 +134,7 @@ struct svx_gpu_host {
     DeviceTree dev{};
     void* d_node_head = nullptr;
     void* d_node_slot = nullptr;
+    void* d_node_mip = nullptr;
     void* d_voxels = nullptr;
     void* d_brick_bits = nullptr;
     void* d_palette = nullptr;
@@ -158,6 +159,7 @@ struct svx_view {
     svx_gpu_host* host = nullptr;
     svx_viewport viewport{};
     int32_t glass_mode = SVX_GLASS_AT_FOV;
+    float viewing_distance = 3.402823466e+38f;  // f32::MAX: Octree::get_by_ray (raytracing_on_cpu.rs:316-318)
     uint32_t width = 0, height = 0;
     uint32_t rank = 0, world = 1, band_rows = 8, compact = 0;
     // peer framebuffers opened from CUDA IPC handles (fused gather: the kernel stores straight into another GPU)
@@ -194,11 +196,13 @@ namespace {
 void free_device_tree(svx_gpu_host* h) {
     cudaFree(h->d_node_head);
     cudaFree(h->d_node_slot);
+    cudaFree(h->d_node_mip);
     cudaFree(h->d_voxels);
     cudaFree(h->d_brick_bits);
     cudaFree(h->d_palette);
     cudaFree(h->d_data_palette);
     cudaFree(h->d_handles);
+    h->d_node_mip = nullptr;
     h->d_node_head = h->d_node_slot = h->d_voxels = h->d_brick_bits = h->d_palette = h->d_data_palette = h->d_handles = nullptr;
     h->node_capacity = h->palette_capacity = h->brick_capacity = h->data_palette_capacity = h->handle_capacity = 0;
     h->uploaded = false;
@@ -244,15 +248,17 @@ int32_t upload(svx_gpu_host* h) {
 
     // nodes + palette: small, replaced wholesale
     const size_t n_nodes = s.node_head.size();
-    size_t slot_capacity = h->node_capacity * 8, head_capacity = h->node_capacity;
+    size_t slot_capacity = h->node_capacity * 8, head_capacity = h->node_capacity, mip_capacity = h->node_capacity;
     CUDA_TRY(grow_device_array(&h->d_node_head, &head_capacity, n_nodes, sizeof(NodeHead), 0, h->stream));
     CUDA_TRY(grow_device_array(&h->d_node_slot, &slot_capacity, head_capacity * 8, 4, 0, h->stream));
+    CUDA_TRY(grow_device_array(&h->d_node_mip, &mip_capacity, head_capacity, 4, 0, h->stream));
     h->node_capacity = head_capacity;
     CUDA_TRY(grow_device_array(&h->d_palette, &h->palette_capacity, s.palette.size(), 4, 0, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_node_head, s.node_head.data(), n_nodes * sizeof(NodeHead), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_node_slot, s.node_slot.data(), n_nodes * 8 * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_node_mip, s.node_mip.data(), n_nodes * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_palette, s.palette.data(), s.palette.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    up.bytes += n_nodes * (sizeof(NodeHead) + 32) + s.palette.size() * 4;
+    up.bytes += n_nodes * (sizeof(NodeHead) + 36) + s.palette.size() * 4;
 
     // bricks: grow keeping what is resident, then copy the runs of handles written since the last upload
     const size_t resident = first ? 0 : std::min(h->brick_capacity, pool);
@@ -278,6 +284,8 @@ int32_t upload(svx_gpu_host* h) {
     DeviceTree& d = h->dev;
     d.node_head = (const NodeHead*)h->d_node_head;
     d.node_slot = (const uint32_t*)h->d_node_slot;
+    d.node_mip = (const uint32_t*)h->d_node_mip;
+    d.mips_enabled = s.mips_enabled ? 1u : 0u;
     d.voxels = (const uint32_t*)h->d_voxels;
     d.brick_bits = (const uint32_t*)h->d_brick_bits;
     d.palette = (const uint32_t*)h->d_palette;
@@ -325,7 +333,7 @@ int32_t upload(svx_gpu_host* h) {
     h->stats.nodes = n_nodes;
     h->stats.bricks = s.live_bricks;
     h->stats.voxel_bytes = pool * vol * 4;
-    h->stats.total_bytes = n_nodes * (sizeof(NodeHead) + 32) + s.palette.size() * 4 + pool * (vol + words) * 4;
+    h->stats.total_bytes = n_nodes * (sizeof(NodeHead) + 36) + s.palette.size() * 4 + pool * (vol + words) * 4;
     h->stats.tree_size = s.tree_size;
     h->stats.brick_dim = s.brick_dim;
     h->stats.depth = s.depth;
@@ -419,6 +427,7 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
         }
     }
     f->compact = v->compact;
+    f->viewing_distance = v->viewing_distance;
     const bool alt = v->target_slot == 1;
     f->hit_id = v->use_peer ? (uint32_t*)v->peer_base[0] : (alt ? v->alt_hit_id : v->d_hit_id);
     f->albedo = v->use_peer ? (uint32_t*)v->peer_base[1] : (alt ? v->alt_albedo : v->d_albedo);
@@ -624,6 +633,51 @@ int32_t svx_octree_set_auto_simplify(svx_octree* t, int32_t enabled) {
 uint64_t svx_octree_structure_hash(const svx_octree* t) { return t ? t->tree->structure_hash() : 0; }
 uint64_t svx_octree_node_count(const svx_octree* t) { return t ? t->tree->nodes().size() : 0; }
 
+// ---- MIP maps: StrategyUpdater, src/octree/mipmap.rs:716-938
+int32_t svx_octree_switch_albedo_mip_maps(svx_octree* t, int32_t enabled) {
+    if (!t) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    t->tree->switch_albedo_mip_maps(enabled != 0);
+    return SVX_OK;
+}
+int32_t svx_octree_mip_maps_enabled(const svx_octree* t) { return (t && t->tree->mips_enabled()) ? 1 : 0; }
+int32_t svx_octree_recalculate_mips(svx_octree* t) {
+    if (!t) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    t->tree->recalculate_mips();
+    return SVX_OK;
+}
+int32_t svx_octree_mip_set_method_at(svx_octree* t, uint64_t mip_level, int32_t method, float threshold) {
+    if (!t) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    if (method < SVX_MIP_BOX_FILTER || method > SVX_MIP_POSTERIZE_BD) return fail(SVX_E_INVALID_ARGUMENT, "bad MIP resampling method");
+    t->tree->mip_set_method_at((size_t)mip_level, (uint32_t)method, threshold);
+    return SVX_OK;
+}
+int32_t svx_octree_mip_get_method_at(const svx_octree* t, uint64_t mip_level, int32_t* method, float* threshold) {
+    if (!t || !method) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    const MipSampler m = t->tree->mip_get_method_at((size_t)mip_level);
+    *method = (int32_t)m.method;
+    if (threshold) *threshold = m.thr;
+    return SVX_OK;
+}
+int32_t svx_octree_mip_set_color_similarity_thr_at(svx_octree* t, uint64_t mip_level, float threshold) {
+    if (!t) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    t->tree->mip_set_color_similarity_thr_at((size_t)mip_level, threshold);
+    return SVX_OK;
+}
+float svx_octree_mip_get_color_similarity_at(const svx_octree* t, uint64_t mip_level) {
+    return t ? t->tree->mip_get_color_similarity_at((size_t)mip_level) : 0.0f;
+}
+int32_t svx_octree_mip_reset(svx_octree* t) {
+    if (!t) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    t->tree->mip_reset();
+    return SVX_OK;
+}
+int32_t svx_octree_mip_sample_root(const svx_octree* t, uint32_t octant, uint32_t x, uint32_t y, uint32_t z, svx_entry* out) {
+    if (!t || !out || octant > 8) return fail(SVX_E_INVALID_ARGUMENT, "bad argument");
+    *out = t->tree->sample_root_mip(octant, x, y, z);
+    return SVX_OK;
+}
+uint64_t svx_octree_mip_hash(const svx_octree* t) { return t ? t->tree->mip_hash() : 0; }
+
 int32_t svx_octree_to_bytes(const svx_octree* t, uint8_t** bytes, uint64_t* len) {
     if (!t || !bytes || !len) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     std::string s;
@@ -740,6 +794,11 @@ int32_t svx_gpu_host_stats(const svx_gpu_host* h, svx_gpu_stats* out) {
 }
 
 int32_t svx_gpu_host_get_by_rays(svx_gpu_host* h, const svx_ray* rays, uint64_t n, svx_hit* hits) {
+    return svx_gpu_host_get_by_rays_at_lod(h, rays, n, 3.402823466e+38f, hits);
+}
+
+int32_t svx_gpu_host_get_by_rays_at_lod(svx_gpu_host* h, const svx_ray* rays, uint64_t n, float viewing_distance,
+                                        svx_hit* hits) {
     if (!h || (n && (!rays || !hits))) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     if (n == 0) return SVX_OK;
     std::lock_guard<std::mutex> lock(h->mu);
@@ -756,7 +815,7 @@ int32_t svx_gpu_host_get_by_rays(svx_gpu_host* h, const svx_ray* rays, uint64_t 
     }
     static_assert(sizeof(svx_ray) == 24, "svx_ray is six packed floats");
     CUDA_TRY(cudaMemcpyAsync(h->d_rays, rays, n * sizeof(svx_ray), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(launch_rays(h->dev, h->d_rays, n, h->d_hits, h->cfg, h->stream));
+    CUDA_TRY(launch_rays(h->dev, h->d_rays, n, viewing_distance, h->d_hits, h->cfg, h->stream));
     h->launches += 1;
     std::vector<RayHitRecord> rec(n);
     CUDA_TRY(cudaMemcpyAsync(rec.data(), h->d_hits, n * sizeof(RayHitRecord), cudaMemcpyDeviceToHost, h->stream));
@@ -862,6 +921,17 @@ int32_t svx_view_set_glass_mode(svx_view* v, int32_t mode) {
     if (!v || (mode != SVX_GLASS_AT_FOV && mode != SVX_GLASS_AT_FRUSTUM_Z)) return fail(SVX_E_INVALID_ARGUMENT, "bad mode");
     std::lock_guard<std::mutex> lock(v->mu);
     v->glass_mode = mode;
+    return SVX_OK;
+}
+int32_t svx_view_set_viewing_distance(svx_view* v, float viewing_distance) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    v->viewing_distance = viewing_distance;
+    return SVX_OK;
+}
+int32_t svx_view_get_viewing_distance(const svx_view* v, float* viewing_distance) {
+    if (!v || !viewing_distance) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *viewing_distance = v->viewing_distance;
     return SVX_OK;
 }
 int32_t svx_view_set_resolution(svx_view* v, uint32_t width, uint32_t height) {

@@ -32,6 +32,8 @@ void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
 
     s.node_head.resize(order.size());
     s.node_slot.assign(order.size() * 8, NIL);
+    s.node_mip.assign(order.size(), NIL);
+    s.mips_enabled = tree.mips_enabled();
     auto slot_of = [&](const BrickRef& b) -> uint32_t {
         if (b.kind == BK_PARTED) ++s.live_bricks;
         return b.kind == BK_EMPTY ? NIL : b.value;  // Solid: the palette value ; Parted: the pool handle
@@ -54,6 +56,10 @@ void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
         } else if (n.kind == NK_UNIFORM) {
             h.meta |= (uint32_t)n.brick[0].kind << 2;
             h.aux = slot_of(n.brick[0]);
+        }
+        if (s.mips_enabled) {
+            h.meta |= (uint32_t)n.mip.kind << 18;
+            s.node_mip[i] = slot_of(n.mip);
         }
         s.node_head[i] = h;
     }

@@ -8,10 +8,14 @@
 //        ocbits = stored_occupied_bits(node)   (reference src/octree/detail.rs:524-544, resolved on the host)
 //        meta   = kind[1:0] | brick kind of octant o at [2+2o+1 : 2+2o]   (0 empty, 1 parted, 2 solid)
 //                 kind: 0 Nothing, 1 Internal, 2 Leaf, 3 UniformLeaf (its brick kind sits in octant 0's field)
+//                 bits [19:18]: kind of the node's MIP brick (reference node_mips[key], src/octree/types.rs:186)
 //        aux    = UniformLeaf: the brick slot (below); otherwise NIL
 //   node_slot[8i + o] : u32   Internal: child node index or NIL (validity resolved on the host)
 //                             Leaf: brick slot of octant o
 //        brick slot = palette value (Solid) | brick handle (Parted) | NIL (Empty)
+//   node_mip[i] : u32   brick slot of the node's MIP brick; read only by the level-of-detail branch of
+//                       get_by_ray_at_lod (raytracing_on_cpu.rs:368-386), and only present in the layout's hot loop
+//                       when the tree's MIP maps are enabled (mips_enabled selects the kernel variant)
 //   voxels[brick * dim^3 + x + y*dim + z*dim^2] : u32 palette values (reference flat_projection order)
 //   brick_bits[brick * words + ...] : 1 bit per voxel, set when the voxel is NOT empty (pix_points_to_empty false);
 //        the DDA walks these bits and fetches the 4-byte voxel only for the hit. Computed ON THE DEVICE from the
@@ -39,6 +43,7 @@ struct NodeHead {
 struct DeviceTree {
     const NodeHead* node_head;
     const uint32_t* node_slot;
+    const uint32_t* node_mip;
     const uint32_t* voxels;
     const uint32_t* brick_bits;
     const uint32_t* palette;
@@ -49,6 +54,7 @@ struct DeviceTree {
     uint32_t brick_shift;       // log2(brick_dim)
     uint32_t bit_words;         // u32 words of brick_bits per brick
     uint32_t n_colors;
+    uint32_t mips_enabled;      // MIPMapStrategy::is_enabled (mipmap.rs:693): the LOD kernel variant runs
     float inv_tree_size;        // 1 / tree_size (exact, power of two)
     float inv_brick_dim;        // 1 / brick_dim (exact, power of two)
 };
@@ -57,9 +63,11 @@ struct DeviceTree {
 struct SerialisedNodes {
     std::vector<NodeHead> node_head;
     std::vector<uint32_t> node_slot;
+    std::vector<uint32_t> node_mip;
     std::vector<uint32_t> palette;
     uint32_t tree_size = 0, brick_dim = 0, brick_shift = 0, bit_words = 0, depth = 0;
-    uint64_t live_bricks = 0;  // parted bricks referenced by reachable nodes
+    uint64_t live_bricks = 0;  // parted bricks referenced by reachable nodes (MIP bricks included)
+    bool mips_enabled = false;
     uint64_t revision = 0;
 };
 

@@ -87,6 +87,7 @@ int32_t HostOctree::create(uint32_t size, uint32_t brick_dim, HostOctree** out) 
     t->dim_ = brick_dim;
     t->vol_ = brick_dim * brick_dim * brick_dim;
     t->pool_push();  // the root is key 0 and starts as Nothing
+    t->mip_defaults();
     *out = t;
     return SVX_OK;
 }
@@ -339,11 +340,14 @@ void HostOctree::store_occupied_bits(size_t key, uint64_t bits) {
 // get, src/octree/mod.rs:209-371
 // ------------------------------------------------------------------------------------------------------------
 svx_entry HostOctree::get(uint32_t x, uint32_t y, uint32_t z) const {
+    return get_from(0, BoundsF{0, 0, 0, (float)size_}, x, y, z);
+}
+
+// get_internal, mod.rs:220-371: the same walk started at any node
+svx_entry HostOctree::get_from(size_t key, BoundsF b, uint32_t x, uint32_t y, uint32_t z) const {
     const float px = (float)x, py = (float)y, pz = (float)z;
-    BoundsF b{0, 0, 0, (float)size_};
     svx_entry none{};
     if (!contains(b, px, py, pz)) return none;
-    size_t key = 0;
     for (;;) {
         const NodeRec& n = nodes_[key];
         if (n.kind == NK_NOTHING) return none;
@@ -874,6 +878,7 @@ int32_t HostOctree::insert_at_lod_internal(bool overwrite, uint32_t x, uint32_t 
                                   (uint32_t)round_index(pz - nb.z), (uint32_t)actual_update_size, (uint32_t)to_index(nb.size));
         }
         store_occupied_bits(key, bits);
+        update_mip(key, nb, x, y, z);  // insert.rs:371
         const uint8_t k = nodes_[key].kind;
         if (k == NK_LEAF || k == NK_UNIFORM) {
             simplifyable = simplify(key);
@@ -1104,6 +1109,7 @@ int32_t HostOctree::clear_at_lod(uint32_t x, uint32_t y, uint32_t z, uint32_t cl
         } else {
             store_occupied_bits(key, bits);
         }
+        update_mip(key, path[i].b, x, y, z);  // clear.rs:335
         if (simplifyable) simplifyable = simplify(key);
         if (previous == bits) break;
     }

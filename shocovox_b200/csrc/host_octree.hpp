@@ -12,6 +12,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -40,6 +41,17 @@ struct NodeRec {
     uint8_t kind = NK_NOTHING;
     uint8_t link = LK_NONE;
     uint8_t reserved = 0;    // ObjectPool's `reserved` flag, src/object_pool.rs:9-12
+    // node_mips[key] (types.rs:186): a brick of the same pool holding the node's simplified view. It belongs to the
+    // KEY, not to the node content: the reference never resets it when a key is freed and reused, so neither
+    // clear_content() nor pool_free() touch it
+    BrickRef mip;
+};
+
+// MIPResamplingMethods (types.rs:106-139); the numbering is the C ABI's SVX_MIP_*
+enum MipMethod : uint32_t { MIP_BOX = 0, MIP_POINT = 1, MIP_POINT_BD = 2, MIP_POSTERIZE = 3, MIP_POSTERIZE_BD = 4 };
+struct MipSampler {
+    uint32_t method = MIP_BOX;
+    float thr = 0.0f;
 };
 
 struct BoundsF {  // Cube, src/spatial/mod.rs:18-21
@@ -55,6 +67,23 @@ class HostOctree {
     int32_t clear_at_lod(uint32_t x, uint32_t y, uint32_t z, uint32_t clear_size);  // src/octree/update/clear.rs:55-348
     svx_entry get(uint32_t x, uint32_t y, uint32_t z) const;
     uint64_t structure_hash() const;
+
+    // ---- MIP maps (host_octree_mip.cpp; reference src/octree/mipmap.rs, StrategyUpdater :716-938)
+    bool mips_enabled() const { return mips_enabled_; }
+    void switch_albedo_mip_maps(bool enabled);                                  // :858-872
+    void recalculate_mips();                                                    // :798-855
+    void mip_set_method_at(size_t level, uint32_t method, float thr);           // :657-672
+    MipSampler mip_get_method_at(size_t level) const;                           // :650-655
+    void mip_set_color_similarity_thr_at(size_t level, float thr);              // :617-630
+    float mip_get_color_similarity_at(size_t level) const;                      // :610-615
+    void mip_reset();                                                           // :718-721
+    svx_entry sample_root_mip(uint32_t octant, uint32_t x, uint32_t y, uint32_t z) const;  // :897-937
+    uint64_t mip_hash() const;
+    const std::map<size_t, MipSampler>& mip_methods() const { return mip_methods_; }
+    const std::map<size_t, float>& mip_thresholds() const { return mip_thresholds_; }
+    // persistence hooks (host_octree_io.cpp)
+    void mip_load_strategy(bool enabled, std::map<size_t, MipSampler> methods, std::map<size_t, float> thresholds);
+    void mip_load_brick(size_t key, uint8_t kind, uint32_t solid, const uint32_t* voxels);
     // bencode persistence in the reference's byte format (host_octree_io.cpp; src/octree/mod.rs:138-168)
     void to_bytes(std::string* out) const;
     static int32_t from_bytes(const uint8_t* data, size_t len, HostOctree** out);
@@ -124,6 +153,13 @@ class HostOctree {
     void dilute(const uint32_t* src, uint32_t out_handles[8]);
     uint64_t hash_node(size_t key) const;
     uint64_t hash_brick(const BrickRef& b) const;
+    uint64_t mip_hash_node(size_t key) const;
+    svx_entry get_from(size_t key, BoundsF b, uint32_t x, uint32_t y, uint32_t z) const;  // get_internal, mod.rs:220-371
+    void update_mip(size_t key, const BoundsF& nb, uint32_t x, uint32_t y, uint32_t z);  // mipmap.rs:296-584
+    void recalculate_mip(size_t key, const BoundsF& nb);                                  // mipmap.rs:875-892
+    bool mip_gather_children(size_t key, const uint32_t start[3], std::vector<svx_albedo>* out) const;
+    bool mip_reduce(const MipSampler& how, const std::vector<svx_albedo>& samples, svx_albedo* out) const;
+    void mip_defaults();
 
     uint32_t size_ = 0, dim_ = 0, vol_ = 0;
     std::vector<NodeRec> nodes_;
@@ -137,6 +173,10 @@ class HostOctree {
     std::vector<uint32_t> datas_;
     std::unordered_map<uint32_t, uint32_t> color_index_, data_index_;
     uint64_t revision_ = 0;
+    bool mips_enabled_ = false;
+    std::map<size_t, MipSampler> mip_methods_;
+    std::map<size_t, float> mip_thresholds_;
+    mutable std::vector<svx_albedo> mip_scratch_;
 };
 
 // Spatial helpers shared by host code (reference src/spatial/math/mod.rs)

@@ -48,7 +48,8 @@ __device__ __forceinline__ void glass_vector(const FrameParams& f, uint32_t x, u
 }
 
 // One pixel of the frame: ray generation, rejection tests, get_by_ray, framebuffer stores.
-// (x, lr) = column and shard-local row.
+// (x, lr) = column and shard-local row. LOD: the tree's MIP maps are enabled (traverse.cuh: traverse<LOD>).
+template <bool LOD>
 __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr) {
     if (x >= f.width || lr >= f.rows_local) return;
     // shard-local row -> image row (interleaved bands of 2^band_shift rows)
@@ -83,7 +84,7 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
         if (root_entry(r, tree_size, px, py, pz, target_octant)) {
             ray_setup(r);
             TraceResult res;
-            if (traverse(tree, r, px, py, pz, target_octant, res)) {
+            if (traverse<LOD>(tree, r, px, py, pz, target_octant, res, f.viewing_distance)) {
                 hit_id = res.palette_value;
                 const uint32_t ci = res.palette_value & 0xFFFFu;
                 if (ci < 0xFFFFu && ci < tree.n_colors) rgba = __ldg(tree.palette + ci);
@@ -101,15 +102,21 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
-    shade_pixel(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+    shade_pixel<false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+}
+// The same frame over a tree with MIP maps: get_by_ray_at_lod(ray, f.viewing_distance) per pixel
+__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kernel(const DeviceTree tree, const FrameParams f) {
+    int tx, ty;
+    pixel_of_thread(tx, ty);
+    shade_pixel<true>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
 }
 
 // Persistent schedule: the grid is sized to the machine (SMs x resident CTAs) and every WARP pulls 8x4 pixel tiles from a
 // global counter until the frame is done, so a long ray delays one warp, not the seven that share its CTA, and the SMs
 // stay busy to the end of the frame. `counters[f.counter_slot]` is this launch's ticket counter; the other slot is
 // zeroed for the next launch (launches of one view are ordered on one stream).
-__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel_persistent(const DeviceTree tree, const FrameParams f,
-                                                                                          uint32_t* __restrict__ counters) {
+template <bool LOD>
+__device__ __forceinline__ void render_persistent_body(const DeviceTree& tree, const FrameParams& f, uint32_t* __restrict__ counters) {
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[f.counter_slot ^ 1u] = 0u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (f.width + 7u) >> 3, tiles_y = (f.rows_local + 3u) >> 2;
@@ -129,13 +136,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel_p
         for (uint32_t k = 0; k < SVX_TICKET_TILES; ++k) {
             const uint32_t sub = (first & 7u) + k;
             const uint32_t ttx = (bx << 2) + (sub & 3u), tty = (by << 1) + (sub >> 2);
-            if (ttx < tiles_x && tty < tiles_y) shade_pixel(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
+            if (ttx < tiles_x && tty < tiles_y) shade_pixel<LOD>(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
         }
     }
 }
+__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel_persistent(const DeviceTree tree, const FrameParams f,
+                                                                                          uint32_t* __restrict__ counters) {
+    render_persistent_body<false>(tree, f, counters);
+}
+__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kernel_persistent(const DeviceTree tree, const FrameParams f,
+                                                                                              uint32_t* __restrict__ counters) {
+    render_persistent_body<true>(tree, f, counters);
+}
 
-__global__ void __launch_bounds__(BLOCK_THREADS) rays_kernel(const DeviceTree tree, const float* __restrict__ rays,
-                                                             uint64_t n, RayHitRecord* __restrict__ out) {
+template <bool LOD>
+__device__ __forceinline__ void rays_body(const DeviceTree& tree, const float* __restrict__ rays, uint64_t n,
+                                          float viewing_distance, RayHitRecord* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     RayConst r;
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rays_kernel(const DeviceTree tr
     r.dx = rays[6 * i + 3]; r.dy = rays[6 * i + 4]; r.dz = rays[6 * i + 5];
     ray_setup(r);
     TraceResult res;
-    const bool hit = trace_ray(tree, r, res);
+    const bool hit = trace_ray<LOD>(tree, r, res, viewing_distance);
     RayHitRecord h;
     h.hit = hit ? 1u : 0u;
     h.palette_value = hit ? res.palette_value : NIL;
@@ -157,6 +173,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rays_kernel(const DeviceTree tr
         h.distance = sqrtf((vx * vx) + (vy * vy) + (vz * vz));
     }
     out[i] = h;
+}
+__global__ void __launch_bounds__(BLOCK_THREADS) rays_kernel(const DeviceTree tree, const float* __restrict__ rays,
+                                                             uint64_t n, RayHitRecord* __restrict__ out) {
+    rays_body<false>(tree, rays, n, 0.0f, out);
+}
+__global__ void __launch_bounds__(BLOCK_THREADS) rays_lod_kernel(const DeviceTree tree, const float* __restrict__ rays,
+                                                                 uint64_t n, float viewing_distance,
+                                                                 RayHitRecord* __restrict__ out) {
+    rays_body<true>(tree, rays, n, viewing_distance, out);
 }
 
 // pix_points_to_empty (reference src/octree/node.rs:405-427) negated: does this palette value show or carry anything?
@@ -290,19 +315,28 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
     if (cfg.persistent && cfg.tile_counters) {
         // blocks_x * blocks_y * 8 tickets cover the frame in 32x8 blocks; ragged edges are skipped inside the kernel
         const unsigned grid = (unsigned)(cfg.sm_count * SVX_MIN_BLOCKS);
-        render_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+        if (tree.mips_enabled)
+            render_lod_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+        else
+            render_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
         return cudaGetLastError();
     }
     dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
-    render_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+    if (tree.mips_enabled)
+        render_lod_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+    else
+        render_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rays(const DeviceTree& tree, const float* rays, uint64_t n, RayHitRecord* out, const LaunchConfig&,
-                        cudaStream_t stream) {
+cudaError_t launch_rays(const DeviceTree& tree, const float* rays, uint64_t n, float viewing_distance, RayHitRecord* out,
+                        const LaunchConfig&, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + BLOCK_THREADS - 1) / BLOCK_THREADS);
-    rays_kernel<<<blocks, BLOCK_THREADS, 0, stream>>>(tree, rays, n, out);
+    if (tree.mips_enabled)
+        rays_lod_kernel<<<blocks, BLOCK_THREADS, 0, stream>>>(tree, rays, n, viewing_distance, out);
+    else
+        rays_kernel<<<blocks, BLOCK_THREADS, 0, stream>>>(tree, rays, n, out);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,7 @@ struct FrameParams {
     uint32_t cull_x0, cull_x1, cull_row0, cull_row1;
     uint32_t counter_slot; // persistent schedule: which of the two ticket counters this launch consumes
     uint32_t compact;      // 1: store shard-local row lr at output row lr (band-major compact buffer for gathers)
+    float viewing_distance;  // get_by_ray_at_lod's parameter (raytracing_on_cpu.rs:325); only read when tree.mips_enabled
     uint32_t* hit_id;      // [h*w]
     uint32_t* albedo;      // [h*w]
     float* distance;       // [h*w]
@@ -45,8 +46,8 @@ struct LaunchConfig {
 };
 
 cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig& cfg, cudaStream_t stream);
-cudaError_t launch_rays(const DeviceTree& tree, const float* rays /* [n][6] */, uint64_t n, RayHitRecord* out,
-                        const LaunchConfig& cfg, cudaStream_t stream);
+cudaError_t launch_rays(const DeviceTree& tree, const float* rays /* [n][6] */, uint64_t n, float viewing_distance,
+                        RayHitRecord* out, const LaunchConfig& cfg, cudaStream_t stream);
 // Render-data upload, device side: the occupancy bit-bricks (gpu_tree.hpp: brick_bits) of the listed bricks, computed
 // from the voxels already resident in `tree.voxels`. A voxel's bit is set unless pix_points_to_empty holds for it
 // (reference src/octree/node.rs:405-427): (no colour index or albedo.a == 0) and (no data index or data == 0).

@@ -307,11 +307,34 @@ __device__ __forceinline__ float crawl_apply(float x, int q, uint32_t n) {
     return __uint_as_float((bits & 0x7F800000u) | (Xn & 0x7FFFFFu));
 }
 
-// The loops of get_by_ray_at_lod(ray, f32::MAX), raytracing_on_cpu.rs:349-565 (MIP maps off: :369-386 is dead code),
-// entered with the point / octant root_entry produced and a fully set-up RayConst.
+// The level-of-detail test of get_by_ray_at_lod, raytracing_on_cpu.rs:370-376:
+//     mip_level < (ray.origin - (p / (mip_level * 2.)).round() * (mip_level * 2.)).length() / viewing_distance
+// mip_level * 2 is not a power of two in general: IEEE division, f32::round = roundf (half away from zero). A
+// mip_level of 0 gives inf / NaN operands and a false comparison, a negative one (the level drifts, see below) just
+// computes - both exactly as in the reference.
+__device__ __forceinline__ bool lod_wants_mip(const RayConst& r, float px, float py, float pz, float mip_level,
+                                              float viewing_distance) {
+    const float m2 = mip_level * 2.0f;
+    const float ax = roundf(px / m2) * m2, ay = roundf(py / m2) * m2, az = roundf(pz / m2) * m2;
+    const float wx = r.ox - ax, wy = r.oy - ay, wz = r.oz - az;
+    return mip_level < sqrtf((wx * wx) + (wy * wy) + (wz * wz)) / viewing_distance;
+}
+
+// The loops of get_by_ray_at_lod, raytracing_on_cpu.rs:349-565, entered with the point / octant root_entry produced
+// and a fully set-up RayConst.
+//   LOD = false: the tree's MIP maps are disabled, so the level-of-detail branch (:368-386) is dead code and
+//                viewing_distance is irrelevant - Octree::get_by_ray on a tree as every BASELINE config builds it.
+//   LOD = true : MIP maps enabled. `mip_level` follows the reference literally: it starts at log2(size / dim) (:349),
+//                loses 1 per PUSH below the root and gains 1 per POP including the root's, and is NOT reset when the
+//                walk restarts from the root - so it drifts upwards by one per root cycle and downwards whenever the
+//                4-entry ring stack has dropped entries. The crawl fast-forward is replaced by single steps, because
+//                every failing root iteration also raises mip_level and re-evaluates the LOD test.
+template <bool LOD>
 __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r, float px, float py, float pz,
-                                         uint32_t target_octant, TraceResult& out) {
+                                         uint32_t target_octant, TraceResult& out, float viewing_distance = 0.0f) {
     const float tree_size = (float)t.tree_size;
+    // log2 of a power of two: (size / dim) = 2^k exactly, k read from the exponent field
+    float mip_level = LOD ? (float)((int)((__float_as_uint(tree_size * t.inv_brick_dim) >> 23) & 0xFFu) - 127) : 0.0f;
     // NodeStack<u32, 4>, raytracing_on_cpu.rs:20-82: a ring buffer that overwrites its oldest entry.
     // Held as a 4-deep shift register (s0 = newest): pushing drops the oldest entry, popping removes the newest,
     // which is exactly what the ring buffer does; entries beyond `count` are never read.
@@ -340,10 +363,13 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 const float cpx = rust_clamp((px * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
                 const float cpy = rust_clamp((py * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
                 const float cpz = rust_clamp((pz * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+                // LOD: the root's MIP is probed before the occupancy test (:368-386) - leave that to the node loop
+                if (LOD && lod_wants_mip(r, px, py, pz, mip_level, viewing_distance)) break;
                 if ((root_hd.x | root_hd.y) != 0u &&
                     ray_may_hit(root_hd.x, root_hd.y, bitmap_coord(cpx), bitmap_coord(cpy), bitmap_coord(cpz), r.dirbits))
                     break;  // the root survives its test: run the node loop below
-                if (++fails >= 2u) {
+                if (LOD) mip_level += 1.0f;  // the root's POP (:447)
+                if (!LOD && ++fails >= 2u) {
                     // a run of failing iterations: apply as many nudges as provably change nothing, at once
                     if (remx == 0u) { const CrawlAxis a = crawl_limit(px, cwx, quarter, inv_quarter); qx = a.q; remx = a.limit; }
                     if (remy == 0u) { const CrawlAxis a = crawl_limit(py, cwy, quarter, inv_quarter); qy = a.q; remy = a.limit; }
@@ -383,6 +409,16 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             const uint4 hd = __ldg(reinterpret_cast<const uint4*>(t.node_head) + cur);
             const uint32_t oc_lo = hd.x, oc_hi = hd.y, meta = hd.z;
             const uint32_t kind = meta & 3u;
+            if (LOD) {
+                // :368-386 far enough away, the node's MIP brick stands in for its content. A miss leaves the point
+                // where the brick walk ended and target_octant as it was.
+                if (lod_wants_mip(r, px, py, pz, mip_level, viewing_distance)) {
+                    const uint32_t mkind = (meta >> 18) & 3u;
+                    if (mkind != BK_EMPTY &&
+                        probe_brick(t, r, px, py, pz, mkind, __ldg(t.node_mip + cur), bx, by, bz, bsize, binv, out))
+                        return true;
+                }
+            }
             if (target_octant != OOB_OCTANT) {
                 if (kind == NK_UNIFORM) {
                     if (probe_brick(t, r, px, py, pz, (meta >> 2) & 3u, hd.w, bx, by, bz, bsize, binv, out)) return true;
@@ -405,6 +441,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             if (kind == NK_UNIFORM || target_octant == OOB_OCTANT || (oc_lo | oc_hi) == 0u ||
                 !ray_may_hit(oc_lo, oc_hi, bitmap_coord(bpx), bitmap_coord(bpy), bitmap_coord(bpz), r.dirbits)) {
                 // POP (:445-474)
+                if (LOD) mip_level += 1.0f;
                 count -= 1u;
                 s0 = s1; s1 = s2; s2 = s3;
                 if (count != 0u) {
@@ -441,6 +478,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 target_octant = hash_region(px - bx, py - by, pz - bz, hs * 0.5f);
                 s3 = s2; s2 = s1; s1 = s0; s0 = child;
                 count = min(count + 1u, 4u);
+                if (LOD) mip_level -= 1.0f;
             } else {
                 // ADVANCE (:497-544)
                 const float q = 4.0f * binv;  // `step * 4. / size` is +-q or +0 (sic: 4/size cells)
@@ -480,15 +518,16 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
     return false;
 }
 
-// Octree::get_by_ray (raytracing_on_cpu.rs:316-318) for a ray whose origin / direction are set in `r`
-__device__ __forceinline__ bool trace_ray(const DeviceTree& t, RayConst& r, TraceResult& out) {
+// Octree::get_by_ray / get_by_ray_at_lod (raytracing_on_cpu.rs:316-325) for a ray whose origin / direction are set in `r`
+template <bool LOD>
+__device__ __forceinline__ bool trace_ray(const DeviceTree& t, RayConst& r, TraceResult& out, float viewing_distance = 0.0f) {
     float px, py, pz;
     uint32_t target_octant;
     out.palette_value = NIL;
     if (certain_root_miss(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, (float)t.tree_size)) return false;
     if (!root_entry(r, (float)t.tree_size, px, py, pz, target_octant)) return false;
     ray_setup(r);
-    return traverse(t, r, px, py, pz, target_octant, out);
+    return traverse<LOD>(t, r, px, py, pz, target_octant, out, viewing_distance);
 }
 
 // cube_impact_normal, spatial/raytracing/mod.rs:106-134

@@ -46,6 +46,7 @@ class Hit(C.Structure):
         ("outer_iters", C.c_uint32),
         ("would_panic", C.c_uint32),
         ("crawl_iters", C.c_uint32),
+        ("mip_probes", C.c_uint32),
     ]
 
 
@@ -74,6 +75,7 @@ HIT_DTYPE = np.dtype(
         ("outer_iters", "<u4"),
         ("would_panic", "<u4"),
         ("crawl_iters", "<u4"),
+        ("mip_probes", "<u4"),
     ]
 )
 assert HIT_DTYPE.itemsize == C.sizeof(Hit)
@@ -133,6 +135,24 @@ def lib() -> C.CDLL:
     L.svxo_octree_palette_sizes.restype = u64
     L.svxo_octree_get_by_ray.argtypes = [vp, f3, f3, C.POINTER(Hit)]
     L.svxo_octree_get_by_rays.argtypes = [vp, vp, u64, vp]
+    L.svxo_octree_get_by_ray_at_lod.argtypes = [vp, f3, f3, f32, C.POINTER(Hit)]
+    L.svxo_octree_get_by_rays_at_lod.argtypes = [vp, vp, u64, f32, vp]
+    L.svxo_octree_mip_switch.argtypes = [vp, i32]
+    L.svxo_octree_mip_enabled.argtypes = [vp]
+    L.svxo_octree_mip_enabled.restype = i32
+    L.svxo_octree_mip_set_method_at.argtypes = [vp, u64, u32, f32]
+    L.svxo_octree_mip_get_method_at.argtypes = [vp, u64, f3]
+    L.svxo_octree_mip_get_method_at.restype = u32
+    L.svxo_octree_mip_set_color_similarity_thr_at.argtypes = [vp, u64, f32]
+    L.svxo_octree_mip_get_color_similarity_at.argtypes = [vp, u64]
+    L.svxo_octree_mip_get_color_similarity_at.restype = f32
+    L.svxo_octree_mip_reset.argtypes = [vp]
+    L.svxo_octree_mip_recalculate.argtypes = [vp]
+    L.svxo_octree_mip_sample_root.argtypes = [vp, u32, u32, u32, u32, C.POINTER(Entry)]
+    L.svxo_octree_mip_hash.argtypes = [vp]
+    L.svxo_octree_mip_hash.restype = u64
+    L.svxo_render_rows_lod.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, u32, u32, f32, vp, vp, vp, vp, vp]
+    L.svxo_render_rows_lod.restype = C.c_double
     L.svxo_make_pixel_ray.argtypes = [C.POINTER(Camera), u32, u32, u32, u32, f3]
     L.svxo_render.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, vp, vp, vp, vp, vp]
     L.svxo_render.restype = C.c_double
@@ -293,9 +313,62 @@ class OracleOctree:
         lib().svxo_octree_get_by_rays(self._h, rays.ctypes.data, rays.shape[0], out.ctypes.data)
         return out
 
-    def render(self, cam: Camera, w: int, h: int, threads: int = 0, rows=None, want_normal=False, row_list=None):
+    # ---- MIP maps / LOD (src/octree/mipmap.rs, raytracing_on_cpu.rs:325)
+    def get_by_ray_at_lod(self, origin, direction, viewing_distance: float) -> Hit:
+        h = Hit()
+        lib().svxo_octree_get_by_ray_at_lod(self._h, _f3(origin), _f3(direction), viewing_distance, C.byref(h))
+        return h
+
+    def get_by_rays_at_lod(self, rays: np.ndarray, viewing_distance: float) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        out = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        lib().svxo_octree_get_by_rays_at_lod(self._h, rays.ctypes.data, rays.shape[0], viewing_distance, out.ctypes.data)
+        return out
+
+    def switch_albedo_mip_maps(self, enabled: bool):
+        lib().svxo_octree_mip_switch(self._h, 1 if enabled else 0)
+        return self
+
+    def mip_enabled(self) -> bool:
+        return bool(lib().svxo_octree_mip_enabled(self._h))
+
+    def set_method_at(self, level: int, method: int, thr: float = 0.0):
+        lib().svxo_octree_mip_set_method_at(self._h, level, method, thr)
+        return self
+
+    def get_method_at(self, level: int):
+        thr = C.c_float()
+        m = lib().svxo_octree_mip_get_method_at(self._h, level, C.byref(thr))
+        return m, thr.value
+
+    def set_color_similarity_thr_at(self, level: int, thr: float):
+        lib().svxo_octree_mip_set_color_similarity_thr_at(self._h, level, thr)
+        return self
+
+    def get_new_color_similarity_at(self, level: int) -> float:
+        return lib().svxo_octree_mip_get_color_similarity_at(self._h, level)
+
+    def mip_reset(self):
+        lib().svxo_octree_mip_reset(self._h)
+        return self
+
+    def recalculate_mips(self):
+        lib().svxo_octree_mip_recalculate(self._h)
+        return self
+
+    def sample_root_mip(self, octant: int, pos):
+        e = Entry()
+        lib().svxo_octree_mip_sample_root(self._h, octant, int(pos[0]), int(pos[1]), int(pos[2]), C.byref(e))
+        return e.key()
+
+    def mip_hash(self) -> int:
+        return lib().svxo_octree_mip_hash(self._h)
+
+    def render(self, cam: Camera, w: int, h: int, threads: int = 0, rows=None, want_normal=False, row_list=None,
+               viewing_distance: float = 3.4028234663852886e38):
         """Returns dict(hit_id u32[h,w], albedo u8[h,w,4], distance f32[h,w], seconds, counters).
-        rows=(r0, r1) renders a contiguous range, row_list an explicit list of image rows (others stay untouched)."""
+        rows=(r0, r1) renders a contiguous range, row_list an explicit list of image rows (others stay untouched).
+        viewing_distance: get_by_ray_at_lod's parameter (default f32::MAX == get_by_ray)."""
         r0, r1 = rows if rows is not None else (0, h)
         if row_list is None:
             row_list = np.arange(r0, r1, dtype=np.uint32)
@@ -304,15 +377,16 @@ class OracleOctree:
         albedo = np.zeros((h, w, 4), dtype=np.uint8)
         dist = np.zeros((h, w), dtype=np.float32)
         normal = np.zeros((h, w, 3), dtype=np.float32) if want_normal else None
-        counters = np.zeros(6, dtype=np.uint64)
-        secs = lib().svxo_render_rows(
-            self._h, C.byref(cam), w, h, row_list.ctypes.data, len(row_list), threads, hit_id.ctypes.data,
+        counters = np.zeros(7, dtype=np.uint64)
+        secs = lib().svxo_render_rows_lod(
+            self._h, C.byref(cam), w, h, row_list.ctypes.data, len(row_list), threads, viewing_distance, hit_id.ctypes.data,
             albedo.ctypes.data, dist.ctypes.data, normal.ctypes.data if want_normal else None, counters.ctypes.data,
         )
         return {
             "hit_id": hit_id, "albedo": albedo, "distance": dist, "normal": normal, "seconds": secs, "rows": row_list,
             "node_iters": int(counters[0]), "voxel_fetches": int(counters[1]), "outer_iters": int(counters[2]),
             "rays_in_root": int(counters[3]), "would_panic": int(counters[4]), "crawl_iters": int(counters[5]),
+            "mip_probes": int(counters[6]),
         }
 
 

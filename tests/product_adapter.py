@@ -60,3 +60,50 @@ class ProductOctree:
 
     def node_count(self):
         return self.tree.node_count()
+
+    # ---- MIP maps (StrategyUpdater surface, duck-typed like tests/oracle_lib.OracleOctree)
+    def _strategy(self):
+        return self.tree.albedo_mip_map_resampling_strategy()
+
+    def switch_albedo_mip_maps(self, enabled):
+        self._strategy().switch_albedo_mip_maps(enabled)
+        return self
+
+    def mip_enabled(self):
+        return self._strategy().is_enabled()
+
+    def set_method_at(self, level, method, thr=0.0):
+        self._strategy().set_method_at(level, method, thr)
+        return self
+
+    def get_method_at(self, level):
+        return self._strategy().get_method_at(level)
+
+    def set_color_similarity_thr_at(self, level, thr):
+        self._strategy().set_color_similarity_thr_at(level, thr)
+        return self
+
+    def get_new_color_similarity_at(self, level):
+        return self._strategy().get_new_color_similarity_at(level)
+
+    def mip_reset(self):
+        self._strategy().reset()
+        return self
+
+    def recalculate_mips(self):
+        self._strategy().recalculate_mips()
+        return self
+
+    def sample_root_mip(self, octant, pos):
+        e = self._strategy().sample_root_mip(octant, pos)
+        if e.kind == S.api.ENTRY_EMPTY:
+            return (O.EMPTY,)
+        rgba = (e.albedo.r, e.albedo.g, e.albedo.b, e.albedo.a) if e.albedo is not None else None
+        if e.kind == S.api.ENTRY_VISUAL:
+            return (O.VISUAL, rgba)
+        if e.kind == S.api.ENTRY_INFORMATIVE:
+            return (O.INFORMATIVE, e.data)
+        return (O.COMPLEX, rgba, e.data)
+
+    def mip_hash(self):
+        return self._strategy().mip_hash()
