@@ -114,6 +114,37 @@ static void test_save_load() {
     EXPECT(error_of([&] { Octree::from_bytes(std::vector<uint8_t>(bytes.begin(), bytes.end() - 3)); }) == SVX_E_DECODE);
 }
 
+// src/octree/tests.rs:365-468 (mipmap_tests::test_mixed_mip_lvl2_where_dim_is_4) through the StrategyUpdater mirror
+static void test_mip_maps() {
+    const Albedo red = Albedo::from(0xFF0000FF), green = Albedo::from(0x00FF00FF), blue = Albedo::from(0x0000FFFF);
+    Octree tree = Octree::create(16, 4);
+    tree.set_auto_simplify(false);
+    tree.albedo_mip_map_resampling_strategy()
+        .switch_albedo_mip_maps(true)
+        .set_method_at(1, MIPResamplingMethods::BoxFilter())
+        .set_method_at(2, MIPResamplingMethods::BoxFilter());
+    const std::pair<V3c<uint32_t>, Albedo> voxels[] = {
+        {{0, 0, 0}, red}, {{0, 0, 1}, green}, {{0, 1, 0}, red}, {{0, 1, 1}, green}, {{1, 0, 0}, red}, {{1, 0, 1}, green},
+        {{8, 0, 0}, red}, {{8, 0, 1}, green}, {{8, 1, 0}, blue}, {{8, 1, 1}, green}, {{9, 1, 0}, red}, {{9, 0, 1}, blue}};
+    for (const auto& v : voxels) tree.insert(v.first, v.second);
+    const uint8_t m2 = 180, m3 = 147;  // sqrt(255^2 / 2), sqrt(255^2 / 3), truncated
+    StrategyUpdater mips = tree.albedo_mip_map_resampling_strategy();
+    EXPECT(mips.is_enabled());
+    EXPECT(mips.sample_root_mip(0, {0, 0, 0}) == OctreeEntry::Visual(Albedo{m2, m2, 0, 255}));
+    EXPECT(mips.sample_root_mip(1, {0, 0, 0}) == OctreeEntry::Visual(Albedo{m3, m3, m3, 255}));
+    EXPECT(mips.sample_root_mip(8, {0, 0, 0}) == OctreeEntry::Visual(Albedo{m2, m2, 0, 255}));
+    EXPECT(mips.sample_root_mip(8, {2, 0, 0}) == OctreeEntry::Visual(Albedo{m3, m3, m3, 255}));
+    EXPECT(mips.sample_root_mip(8, {1, 1, 1}).is_none());
+    EXPECT(mips.get_method_at(1) == MIPResamplingMethods::BoxFilter());
+    EXPECT(mips.set_method_at(3, MIPResamplingMethods::Posterize(2.0f)).get_method_at(3) == MIPResamplingMethods::Posterize(1.0f));
+    EXPECT(mips.get_new_color_similarity_at(3) == 0.05f);
+    // the MIPs and their strategy travel with the tree
+    Octree copy = Octree::from_bytes(tree.to_bytes());
+    EXPECT(copy.albedo_mip_map_resampling_strategy().is_enabled());
+    EXPECT(copy.albedo_mip_map_resampling_strategy().sample_root_mip(8, {2, 0, 0}) == OctreeEntry::Visual(Albedo{m3, m3, m3, 255}));
+    EXPECT(!mips.reset().is_enabled());
+}
+
 // without a CUDA device the ray path must throw, never fall back to the CPU
 static void test_no_cpu_fallback() {
     if (svx_cuda_device_count() > 0) return;
@@ -128,6 +159,7 @@ int main() {
     test_insert_and_clear_at_lod();
     test_errors();
     test_save_load();
+    test_mip_maps();
     test_no_cpu_fallback();
     std::puts("octree_api_test: ok");
     return 0;

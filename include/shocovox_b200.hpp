@@ -16,6 +16,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <limits>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -115,6 +116,61 @@ struct Frame {  // host copy of one rendered frame, image order (row 0 = top)
     std::vector<float> distance;
 };
 
+// MIPResamplingMethods (src/octree/types.rs:106-139): the method plus, for the Posterize variants, its threshold
+struct MIPResamplingMethods {
+    svx_mip_method method = SVX_MIP_BOX_FILTER;
+    float threshold = 0.0f;
+    static MIPResamplingMethods BoxFilter() { return {SVX_MIP_BOX_FILTER, 0.0f}; }
+    static MIPResamplingMethods PointFilter() { return {SVX_MIP_POINT_FILTER, 0.0f}; }
+    static MIPResamplingMethods PointFilterBD() { return {SVX_MIP_POINT_FILTER_BD, 0.0f}; }
+    static MIPResamplingMethods Posterize(float thr) { return {SVX_MIP_POSTERIZE, thr}; }
+    static MIPResamplingMethods PosterizeBD(float thr) { return {SVX_MIP_POSTERIZE_BD, thr}; }
+    bool operator==(const MIPResamplingMethods& o) const { return method == o.method && threshold == o.threshold; }
+};
+
+// StrategyUpdater<'a, T> (src/octree/types.rs:142, src/octree/mipmap.rs:716-938): chainable MIP map settings of one tree
+class StrategyUpdater {
+   public:
+    explicit StrategyUpdater(svx_octree* tree) : h_(tree) {}
+    StrategyUpdater& reset() {
+        check(svx_octree_mip_reset(h_));
+        return *this;
+    }
+    bool is_enabled() const { return svx_octree_mip_maps_enabled(h_) != 0; }
+    StrategyUpdater& switch_albedo_mip_maps(bool enabled) {
+        check(svx_octree_switch_albedo_mip_maps(h_, enabled ? 1 : 0));
+        return *this;
+    }
+    StrategyUpdater& recalculate_mips() {
+        check(svx_octree_recalculate_mips(h_));
+        return *this;
+    }
+    float get_new_color_similarity_at(size_t mip_level) const { return svx_octree_mip_get_color_similarity_at(h_, mip_level); }
+    StrategyUpdater& set_color_similarity_thr_at(size_t mip_level, float similarity_thr) {
+        check(svx_octree_mip_set_color_similarity_thr_at(h_, mip_level, similarity_thr));
+        return *this;
+    }
+    MIPResamplingMethods get_method_at(size_t mip_level) const {
+        int32_t m = 0;
+        float thr = 0.0f;
+        check(svx_octree_mip_get_method_at(h_, mip_level, &m, &thr));
+        return {(svx_mip_method)m, thr};
+    }
+    StrategyUpdater& set_method_at(size_t mip_level, MIPResamplingMethods method) {
+        check(svx_octree_mip_set_method_at(h_, mip_level, method.method, method.threshold));
+        return *this;
+    }
+    // the reference's test hook (mipmap.rs:897-937); octant 8 (OOB_OCTANT) samples the root's own MIP
+    OctreeEntry sample_root_mip(uint32_t octant, V3c<uint32_t> position) const {
+        svx_entry e{};
+        check(svx_octree_mip_sample_root(h_, octant, position.x, position.y, position.z, &e));
+        return OctreeEntry::from_c(e);
+    }
+
+   private:
+    svx_octree* h_;
+};
+
 class Octree {
    public:
     static Octree create(uint32_t size, uint32_t brick_dimension) {  // Octree::new
@@ -157,6 +213,8 @@ class Octree {
     uint32_t get_size() const { return svx_octree_size(h_); }
     void set_auto_simplify(bool v) { check(svx_octree_set_auto_simplify(h_, v ? 1 : 0)); }  // pub auto_simplify
     uint64_t structure_hash() const { return svx_octree_structure_hash(h_); }
+    // Octree::albedo_mip_map_resampling_strategy, src/octree/mod.rs:379
+    StrategyUpdater albedo_mip_map_resampling_strategy() { return StrategyUpdater(h_); }
     // Octree::to_bytes / from_bytes / save / load (bencode, src/octree/mod.rs:138-168)
     std::vector<uint8_t> to_bytes() const {
         uint8_t* p = nullptr;
@@ -206,17 +264,20 @@ class OctreeGPUHost {  // OctreeGPUHost { tree }: uploads the whole tree to `dev
         return s;
     }
     // Octree::get_by_ray(&Ray) -> Option<(OctreeEntry, V3c<f32>, V3c<f32>)>, on the GPU
-    std::optional<RayHit> get_by_ray(const Ray& ray) {
-        std::vector<std::optional<RayHit>> r = get_by_rays({ray});
+    std::optional<RayHit> get_by_ray(const Ray& ray) { return get_by_ray_at_lod(ray, std::numeric_limits<float>::max()); }
+    // Octree::get_by_ray_at_lod(&Ray, viewing_distance), src/raytracing/raytracing_on_cpu.rs:325
+    std::optional<RayHit> get_by_ray_at_lod(const Ray& ray, float viewing_distance) {
+        std::vector<std::optional<RayHit>> r = get_by_rays({ray}, viewing_distance);
         return r[0];
     }
-    std::vector<std::optional<RayHit>> get_by_rays(const std::vector<Ray>& rays) {
+    std::vector<std::optional<RayHit>> get_by_rays(const std::vector<Ray>& rays,
+                                                   float viewing_distance = std::numeric_limits<float>::max()) {
         std::vector<svx_ray> in(rays.size());
         for (size_t i = 0; i < rays.size(); ++i)
             in[i] = svx_ray{{rays[i].origin.x, rays[i].origin.y, rays[i].origin.z},
                             {rays[i].direction.x, rays[i].direction.y, rays[i].direction.z}};
         std::vector<svx_hit> out(rays.size());
-        check(svx_gpu_host_get_by_rays(h_, in.data(), in.size(), out.data()));
+        check(svx_gpu_host_get_by_rays_at_lod(h_, in.data(), in.size(), viewing_distance, out.data()));
         std::vector<std::optional<RayHit>> res(rays.size());
         for (size_t i = 0; i < rays.size(); ++i) {
             if (!out[i].hit) continue;
@@ -260,6 +321,14 @@ class OctreeGPUView {
                         {c.frustum[0], c.frustum[1], c.frustum[2]}, c.fov};
     }
     void set_glass_mode(svx_glass_mode m) { check(svx_view_set_glass_mode(h_, m)); }
+    // viewing distance of every pixel's get_by_ray_at_lod (default f32::MAX = get_by_ray; the reference's GPU path
+    // feeds viewport.frustum.z); only matters while the tree's MIP maps are enabled
+    void set_viewing_distance(float d) { check(svx_view_set_viewing_distance(h_, d)); }
+    float viewing_distance() const {
+        float d = 0.0f;
+        check(svx_view_get_viewing_distance(h_, &d));
+        return d;
+    }
     void set_resolution(std::array<uint32_t, 2> r) { check(svx_view_set_resolution(h_, r[0], r[1])); }  // bevy/mod.rs:62-82
     std::array<uint32_t, 2> resolution() const {
         uint32_t w = 0, h = 0;

@@ -180,10 +180,10 @@ std::string octree_to_bytes(const Octree& t) {
         }
     }
     s += "e";
-    // node_mips: MIP maps are disabled (mipmap.rs:591-604) so every entry is BrickData::Empty; the vector is kept as long
-    // as the node buffer (insert.rs:168-169, detail.rs:356-397 resize it to nodes.len())
+    // node_mips (bytecode.rs:591): one BrickData per node key; the vector is as long as the node buffer
+    // (insert.rs:168-169, detail.rs:356-397 resize it to nodes.len())
     s += "l";
-    for (size_t i = 0; i < t.nodes.len(); ++i) put_str(s, "#b");
+    for (size_t i = 0; i < t.nodes.len(); ++i) put_brick(s, i < t.node_mips.size() ? t.node_mips[i] : Brick());
     s += "e";
     s += "l";
     for (const Albedo& a : t.voxel_color_palette) {  // Albedo::encode, bytecode.rs:13-20
@@ -198,19 +198,31 @@ std::string octree_to_bytes(const Octree& t) {
     s += "l";
     for (uint32_t d : t.voxel_data_palette) put_int(s, d);
     s += "e";
-    // MIPMapStrategy::default() (mipmap.rs:591-604) through MIPMapStrategy::encode (bytecode.rs:344-362), maps in
-    // ascending level order (the reference iterates a HashMap: any order is a valid file)
+    // MIPMapStrategy::encode (bytecode.rs:436-453) with MIPResamplingMethods::encode (:519-535); maps in ascending
+    // level order (the reference iterates a HashMap: any order is a valid file)
+    auto milli = [](float thr) -> uint64_t {  // `(thr * 1000.) as u32`
+        const float v = thr * 1000.0f;
+        if (!(v > 0.0f)) return 0;
+        return v >= 4294967296.0f ? 0xFFFFFFFFull : (uint64_t)(uint32_t)v;
+    };
     s += "l";
-    put_int(s, 0);
-    put_int(s, 4);
-    put_int(s, 1); put_int(s, 1);  // PointFilter
-    put_int(s, 2); put_int(s, 0);  // BoxFilter
-    put_int(s, 3); put_int(s, 0);
-    put_int(s, 4); put_int(s, 0);
-    put_int(s, 3);
-    put_int(s, 2); put_int(s, (uint32_t)(0.1f * 1000.0f));
-    put_int(s, 3); put_int(s, (uint32_t)(0.05f * 1000.0f));
-    put_int(s, 4); put_int(s, (uint32_t)(0.02f * 1000.0f));
+    put_int(s, t.mip_map_strategy.enabled ? 1 : 0);
+    put_int(s, t.mip_map_strategy.resampling_methods.size());
+    for (const auto& m : t.mip_map_strategy.resampling_methods) {
+        put_int(s, m.first);
+        switch (m.second.method) {
+            case MipMethod::BoxFilter: put_int(s, 0); break;
+            case MipMethod::PointFilter: put_int(s, 1); break;
+            case MipMethod::PointFilterBD: put_int(s, 2); break;
+            case MipMethod::Posterize: put_int(s, 3 + milli(m.second.thr)); break;
+            case MipMethod::PosterizeBD: put_int(s, 1003 + milli(m.second.thr)); break;
+        }
+    }
+    put_int(s, t.mip_map_strategy.resampling_color_matching_thresholds.size());
+    for (const auto& m : t.mip_map_strategy.resampling_color_matching_thresholds) {
+        put_int(s, m.first);
+        put_int(s, milli(m.second));
+    }
     s += "e";
     s += "e";
     return s;
@@ -296,7 +308,16 @@ Status octree_from_bytes(const uint8_t* data, size_t len, Octree** out) {
         t->node_children.push_back(ch);
     }
     t->node_children.resize(t->nodes.len());
-    if (f[5].kind != Item::List) return bad;  // node_mips: MIP maps stay off in the oracle
+    // node_mips (bytecode.rs:638)
+    if (f[5].kind != Item::List) return bad;
+    t->node_mips.clear();
+    for (const Item& m : f[5].list) {
+        Brick b;
+        if (!get_brick(m, &b)) return bad;
+        if (b.kind == BrickKind::Parted && b.data.size() != (size_t)t->brick_dim * t->brick_dim * t->brick_dim) return bad;
+        t->node_mips.push_back(std::move(b));
+    }
+    t->node_mips.resize(t->nodes.len());
     // palettes and their lookup maps (bytecode.rs:640-655)
     if (f[6].kind != Item::List || f[7].kind != Item::List || f[8].kind != Item::List) return bad;
     for (size_t i = 0; i < f[6].list.size(); ++i) {
@@ -312,6 +333,40 @@ Status octree_from_bytes(const uint8_t* data, size_t len, Octree** out) {
         if (f[7].list[i].kind != Item::Int) return bad;
         t->voxel_data_palette.push_back((uint32_t)f[7].list[i].integer);
         t->data_lookup_[(uint32_t)f[7].list[i].integer] = i;
+    }
+    // MIPMapStrategy::decode_bencode_object (bytecode.rs:456-516), MIPResamplingMethods (:537-569)
+    {
+        const std::vector<Item>& m = f[8].list;
+        size_t k = 0;
+        auto next_int = [&](uint64_t* v) {
+            if (k >= m.size() || m[k].kind != Item::Int) return false;
+            *v = m[k++].integer;
+            return true;
+        };
+        uint64_t enabled, n;
+        if (!next_int(&enabled) || enabled > 1 || !next_int(&n)) return bad;
+        t->mip_map_strategy.enabled = enabled == 1;
+        t->mip_map_strategy.resampling_methods.clear();
+        t->mip_map_strategy.resampling_color_matching_thresholds.clear();
+        for (uint64_t i = 0; i < n; ++i) {
+            uint64_t level, code;
+            if (!next_int(&level) || !next_int(&code)) return bad;
+            MipSampler smp;
+            if (code == 0) smp.method = MipMethod::BoxFilter;
+            else if (code == 1) smp.method = MipMethod::PointFilter;
+            else if (code == 2) smp.method = MipMethod::PointFilterBD;
+            else if (code >= 3 && code < 1002) smp = MipSampler{MipMethod::Posterize, ((float)(uint32_t)code - 3.0f) / 1000.0f};
+            else if (code >= 1003 && code < 2001) smp = MipSampler{MipMethod::PosterizeBD, ((float)(uint32_t)code - 1003.0f) / 1000.0f};
+            else return bad;
+            t->mip_map_strategy.resampling_methods[(size_t)level] = smp;
+        }
+        if (!next_int(&n)) return bad;
+        for (uint64_t i = 0; i < n; ++i) {
+            uint64_t level, milli;
+            if (!next_int(&level) || !next_int(&milli)) return bad;
+            t->mip_map_strategy.resampling_color_matching_thresholds[(size_t)level] = (float)(uint32_t)milli / 1000.0f;
+        }
+        if (k != m.size()) return bad;
     }
     *out = hold.release();
     return OK;

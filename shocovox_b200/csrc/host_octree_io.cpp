@@ -11,17 +11,20 @@
 //   CONTENT       = 1:#  |  l 2:## i<occupied_bits> e  |  l 3:### BRICK x8 e  |  l 4:##u# BRICK e   (bytecode.rs:166-196)
 //   BRICK         = 2:#b  |  l 3:#b# i<voxel> e  |  l 4:##b# i<len> i<voxel>*len 1:# e              (bytecode.rs:67-91)
 //   CHILDREN      = l ( 5:##x##  |  l 5:##c## i<key> x8 e  |  l 5:##b## i<bitmap> e )* e            (bytecode.rs:289-311)
-//   MIPS          = l BRICK* e                                  one per node; MIP maps are not built here: all 2:#b
+//   MIPS          = l BRICK* e                                  node_mips, one per node (types.rs:186)
 //   COLORS        = l ( l i<r> i<g> i<b> i<a> e )* e            (bytecode.rs:11-22)
 //   DATAS         = l i<u32>* e                                 Octree<T = u32>
-//   STRATEGY      = l i<enabled> i<n> (i<level> i<method>)*n i<m> (i<level> i<threshold*1000>)*m e    (bytecode.rs:343-363)
+//   STRATEGY      = l i<enabled> i<n> (i<level> i<method>)*n i<m> (i<level> i<threshold*1000>)*m e    (bytecode.rs:436-453)
+//   method        = 0 BoxFilter | 1 PointFilter | 2 PointFilterBD | 3 + thr*1000 Posterize | 1003 + thr*1000 PosterizeBD
+//                   (bytecode.rs:519-535; the decoder :537-569 accepts 3..1002 and 1003..2001 exclusive, so
+//                   Posterize(0.999) cannot be read back and Posterize(1.0) comes back as PosterizeBD(0.0) - kept)
 //
 // The reference writes the two strategy maps in HashMap iteration order (random per process); we write them sorted
-// by level. MIP bricks found in a loaded file are skipped and the strategy is stored as disabled: this build
-// renders get_by_ray (MIPs off), see DESIGN.md.
+// by level.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -218,9 +221,9 @@ void HostOctree::to_bytes(std::string* out) const {
         }
     }
     w.close();
-    // node_mips: one BrickData::Empty per node (MIP maps stay disabled, mipmap.rs:591-604)
+    // node_mips: one brick per node key (bytecode.rs:591)
     w.open();
-    for (size_t i = 0; i < nodes_.size(); ++i) w.str("#b");
+    for (const NodeRec& n : nodes_) brick(n.mip);
     w.close();
     w.open();
     for (const svx_albedo& a : colors_) {  // bytecode.rs:11-22
@@ -235,20 +238,27 @@ void HostOctree::to_bytes(std::string* out) const {
     w.open();
     for (uint32_t d : datas_) w.integer(d);
     w.close();
-    // MIPMapStrategy::default() with enabled = false (mipmap.rs:591-604), thresholds as `(thr * 1000.) as u32`
+    // MIPMapStrategy (bytecode.rs:436-453): thresholds and Posterize parameters as `(thr * 1000.) as u32`
+    auto milli = [](float thr) -> uint64_t {
+        const float v = thr * 1000.0f;
+        if (!(v > 0.0f)) return 0;
+        return v >= 4294967296.0f ? 0xFFFFFFFFull : (uint64_t)(uint32_t)v;
+    };
     w.open();
-    w.integer(0);
-    w.integer(4);
-    const uint64_t methods[4][2] = {{1, 1}, {2, 0}, {3, 0}, {4, 0}};  // 1: PointFilter, 2..4: BoxFilter (bytecode.rs:436-450)
-    for (auto& m : methods) {
-        w.integer(m[0]);
-        w.integer(m[1]);
+    w.integer(mips_enabled_ ? 1 : 0);
+    w.integer(mip_methods_.size());
+    for (const auto& m : mip_methods_) {
+        w.integer(m.first);
+        switch (m.second.method) {  // bytecode.rs:519-535
+            case MIP_POSTERIZE: w.integer(3 + milli(m.second.thr)); break;
+            case MIP_POSTERIZE_BD: w.integer(1003 + milli(m.second.thr)); break;
+            default: w.integer(m.second.method); break;
+        }
     }
-    w.integer(3);
-    const uint64_t thr[3][2] = {{2, 100}, {3, 50}, {4, 20}};
-    for (auto& t : thr) {
-        w.integer(t[0]);
-        w.integer(t[1]);
+    w.integer(mip_thresholds_.size());
+    for (const auto& t : mip_thresholds_) {
+        w.integer(t.first);
+        w.integer(milli(t.second));
     }
     w.close();
     w.close();
@@ -377,8 +387,17 @@ int32_t HostOctree::from_bytes(const uint8_t* data, size_t len, HostOctree** out
         if (!r.close()) return SVX_E_DECODE;
     }
     if (!r.close()) return SVX_E_DECODE;
-    // node_mips: skipped
-    if (!r.skip()) return SVX_E_DECODE;
+    // node_mips, parallel to the node buffer (bytecode.rs:638)
+    if (!r.open()) return SVX_E_DECODE;
+    size_t mi = 0;
+    while (r.ok && !r.at_close()) {
+        BrickRef scratch;
+        BrickRef* m = mi < t->nodes_.size() ? &t->nodes_[mi].mip : &scratch;
+        ++mi;
+        if (!brick(m)) return SVX_E_DECODE;
+        if (m == &scratch) t->brick_release(scratch);
+    }
+    if (!r.close()) return SVX_E_DECODE;
     // palettes (bytecode.rs:640-655: later duplicates win in the lookup maps)
     if (!r.open()) return SVX_E_DECODE;
     while (r.ok && !r.at_close()) {
@@ -399,7 +418,38 @@ int32_t HostOctree::from_bytes(const uint8_t* data, size_t len, HostOctree** out
         t->datas_.push_back((uint32_t)d);
     }
     if (!r.close()) return SVX_E_DECODE;
-    if (!r.skip()) return SVX_E_DECODE;  // MIPMapStrategy
+    // MIPMapStrategy (bytecode.rs:456-516)
+    {
+        uint64_t enabled = 0, count = 0;
+        if (!r.open() || !r.integer(&enabled) || enabled > 1 || !r.integer(&count)) return SVX_E_DECODE;
+        std::map<size_t, MipSampler> methods;
+        for (uint64_t i = 0; i < count; ++i) {
+            uint64_t level, code;
+            if (!r.integer(&level) || !r.integer(&code) || code > 0xFFFFFFFFull) return SVX_E_DECODE;
+            MipSampler m;
+            if (code <= 2) {
+                m.method = (uint32_t)code;
+            } else if (code >= 3 && code < 1002) {
+                m.method = MIP_POSTERIZE;
+                m.thr = ((float)(uint32_t)code - 3.0f) / 1000.0f;
+            } else if (code >= 1003 && code < 2001) {
+                m.method = MIP_POSTERIZE_BD;
+                m.thr = ((float)(uint32_t)code - 1003.0f) / 1000.0f;
+            } else {
+                return SVX_E_DECODE;
+            }
+            methods[(size_t)level] = m;
+        }
+        if (!r.integer(&count)) return SVX_E_DECODE;
+        std::map<size_t, float> thresholds;
+        for (uint64_t i = 0; i < count; ++i) {
+            uint64_t level, milli;
+            if (!r.integer(&level) || !r.integer(&milli) || milli > 0xFFFFFFFFull) return SVX_E_DECODE;
+            thresholds[(size_t)level] = (float)(uint32_t)milli / 1000.0f;
+        }
+        if (!r.close()) return SVX_E_DECODE;
+        t->mip_load_strategy(enabled == 1, std::move(methods), std::move(thresholds));
+    }
     if (!r.close() || r.p != r.end) return SVX_E_DECODE;
     if (t->colors_.size() > 0xFFFF || t->datas_.size() > 0xFFFF) return SVX_E_DECODE;  // u16 palette indices, types.rs:188-191
     // Untrusted input: the reference would bounds-panic on a palette index beyond its palette and recurse forever on a
@@ -408,16 +458,20 @@ int32_t HostOctree::from_bytes(const uint8_t* data, size_t len, HostOctree** out
         const uint32_t ci = v & 0xFFFFu, di = v >> 16;
         return (ci == 0xFFFFu || ci < t->colors_.size()) && (di == 0xFFFFu || di < t->datas_.size());
     };
-    for (const NodeRec& n : t->nodes_) {
-        if (!n.reserved) continue;
-        for (const BrickRef& b : n.brick) {
-            if (b.kind == BK_SOLID && !value_ok(b.value)) return SVX_E_DECODE;
-            if (b.kind == BK_PARTED) {
-                const uint32_t* v = t->brick_data(b.value);
-                for (uint32_t i = 0; i < t->vol_; ++i)
-                    if (!value_ok(v[i])) return SVX_E_DECODE;
-            }
+    auto brick_ok = [&](const BrickRef& b) {
+        if (b.kind == BK_SOLID) return value_ok(b.value);
+        if (b.kind == BK_PARTED) {
+            const uint32_t* v = t->brick_data(b.value);
+            for (uint32_t i = 0; i < t->vol_; ++i)
+                if (!value_ok(v[i])) return false;
         }
+        return true;
+    };
+    for (const NodeRec& n : t->nodes_) {
+        if (!brick_ok(n.mip)) return SVX_E_DECODE;  // a MIP belongs to the key and survives a freed slot
+        if (!n.reserved) continue;
+        for (const BrickRef& b : n.brick)
+            if (!brick_ok(b)) return SVX_E_DECODE;
     }
     {
         std::vector<uint8_t> seen(t->nodes_.size(), 0);

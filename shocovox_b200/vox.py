@@ -218,6 +218,27 @@ def load_vox(path_or_bytes, brick_dimension: int = 8):
     return tree_size, xyz.astype(np.uint32), rgba.astype(np.uint8)
 
 
+def load_vox_file(path_or_bytes, brick_dimension: int = 8, mip_enabled: bool = False, mip_methods=None,
+                  mip_color_similarity=None):
+    """`Octree::load_vox_file(brick_dimension, path)` and, with the MIP arguments, `MIPMapStrategy::load_vox_file`
+    (src/convert/magicavoxel.rs:207-250): the strategy is installed on the empty tree BEFORE the voxels are inserted, so
+    every insert refreshes the MIPs as it goes (insert.rs:371) - `MIPMapStrategy::default().set_enabled(true)
+    .load_vox_file(..)` is what examples/minecraft.rs:57-60 and examples/sponza.rs:66-67 do.
+    mip_methods = {level: method | (method, threshold)}, mip_color_similarity = {level: threshold}: applied on top of
+    MIPMapStrategy::default(), like the reference's builder calls."""
+    from .api import Octree
+
+    tree_size, xyz, rgba = load_vox(path_or_bytes, brick_dimension)
+    tree = Octree(tree_size, brick_dimension)
+    strategy = tree.albedo_mip_map_resampling_strategy()
+    strategy.set_method(list((mip_methods or {}).items()))
+    strategy.set_color_similarity_thr(list((mip_color_similarity or {}).items()))
+    if mip_enabled:
+        strategy.switch_albedo_mip_maps(True)  # the tree is still empty: nothing to recalculate (mipmap.rs:866-871)
+    tree.insert_batch(xyz, rgba)
+    return tree
+
+
 def write_vox(models, palette: Optional[np.ndarray] = None, placements=None) -> bytes:
     """Minimal .vox writer (for tests): models = [(size, voxels[n,4] with 0-based palette index)], optional scene graph
     placements = [(translation(3), rotation_byte or None)] per model."""

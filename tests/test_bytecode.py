@@ -170,14 +170,14 @@ def test_third_encoder_reproduces_the_literal():
 
 def test_hand_built_documents_load(IO):
     """A file nobody's encoder wrote: parted and solid bricks, a uniform leaf, user data, an unreserved pool slot,
-    the strategy maps in another order and a MIP brick that must be skipped."""
+    the strategy maps in another order, MIP bricks and a non-default MIP strategy."""
     dim, vol = 2, 8
     parted = [0xFFFF0000, NIL, NIL, NIL, NIL, NIL, NIL, 0x00000001]          # colour 0 at (0,0,0); colour 1 + data 0 at (1,1,1)
     nodes = [(1, ("I", 0xFFFFFFFFFFFFFFFF)), (1, ("L", [parted, 0x0000FFFF, None, None, None, None, None, None])),
              (0, None), (1, ("U", 0xFFFF0001))]
     children = [[1, NIL, NIL, NIL, NIL, NIL, NIL, 3], 0xFF, None, 0xFFFFFFFFFFFFFFFF]
     doc = tree_doc(False, 8, dim, 2, nodes, children, [(255, 0, 0, 255), (0, 255, 0, 255)], [7])
-    doc[5] = ["#b", ["#b#", 5], "#b", ["##b#", vol, *([3] * vol), "#"]]      # node_mips with content
+    doc[5] = ["#b", ["#b#", 0xFFFF0001], "#b", ["##b#", vol, *([0xFFFF0000] * vol), "#"]]   # node_mips with content
     doc[8] = [1, 2, 4, 0, 1, 1003, 1, 3, 50]                                  # enabled, PosterizeBD(0.0) at level 1, one threshold
     t = IO.from_bytes(benc(doc))
     assert t.get((0, 0, 0)) == K((255, 0, 0, 255))
@@ -189,10 +189,67 @@ def test_hand_built_documents_load(IO):
     for p in ((4, 4, 4), (7, 7, 7), (5, 6, 4)):                               # UniformLeaf(Solid(colour 1))
         assert t.get(p) == K((0, 255, 0, 255))
     assert t.get((4, 0, 0)) == K()
-    # saved again, MIPs are written as disabled and empty; everything else survives
+    # the MIP bricks and the MIP strategy are part of the tree (bytecode.rs:591-594, :638-668)
+    assert t.mip_enabled()
+    assert t.get_method_at(1) == (4, 0.0) and t.get_method_at(4)[0] == 0 and t.get_method_at(2)[0] == 0
+    assert t.get_new_color_similarity_at(3) == float(np.float32(50) / np.float32(1000)) and t.get_new_color_similarity_at(2) == 0.0
+    assert t.sample_root_mip(0, (1, 0, 1)) == K((0, 255, 0, 255))             # node 1: Solid MIP, colour 1
+    assert t.sample_root_mip(7, (1, 1, 1)) == K((255, 0, 0, 255))             # node 3: Parted MIP, colour 0 everywhere
+    assert t.sample_root_mip(8, (0, 0, 0)) == K()                             # root: no MIP
+    # saved again, everything survives
     again = IO.from_bytes(IO.to_bytes(t))
-    assert again.structure_hash() == t.structure_hash()
+    assert again.structure_hash() == t.structure_hash() and again.mip_hash() == t.mip_hash()
     assert IO.to_bytes(again) == IO.to_bytes(t)
+    # the product rejects a MIP voxel pointing beyond the palette like any other voxel (the reference panics on use)
+    if IO is ProductIO:
+        doc[5][1] = ["#b#", 5]
+        with pytest.raises(ValueError):
+            IO.from_bytes(benc(doc))
+
+
+def test_posterize_codes_decode_like_the_reference(IO):
+    """MIPResamplingMethods (bytecode.rs:519-569): 3 + thr*1000 / 1003 + thr*1000 with the decoder's exclusive ranges:
+    1002 and anything from 2001 up are errors, 1003 (what Posterize(1.0) writes) reads back as PosterizeBD(0.0)."""
+    doc = tree_doc(True, 4, 1, 1, [(1, None)], [None], [], [])
+    for code, want in [(0, (0, 0.0)), (1, (1, 0.0)), (2, (2, 0.0)), (3, (3, 0.0)), (253, (3, 0.25)), (1001, (3, float(np.float32(998) / np.float32(1000)))),
+                       (1003, (4, 0.0)), (1503, (4, 0.5)), (2000, (4, float(np.float32(997) / np.float32(1000))))]:
+        doc[8] = [0, 1, 6, code, 0]
+        assert IO.from_bytes(benc(doc)).get_method_at(6) == want, code
+    for code in (1002, 2001, 5000):
+        doc[8] = [0, 1, 6, code, 0]
+        with pytest.raises(ValueError):
+            IO.from_bytes(benc(doc))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 4])
+def test_trees_with_mips_round_trip_and_both_codecs_agree(dim):
+    rng = np.random.default_rng(11 + dim)
+    size = 16 * dim
+    prod, ora = ProductOctree(size, dim), OracleOctree(size, dim)
+    for t in (prod, ora):
+        t.switch_albedo_mip_maps(True).set_method_at(2, 3, 0.25).set_method_at(3, 2).set_color_similarity_thr_at(1, 0.03)
+    for _ in range(200):
+        pos = tuple(int(v) for v in rng.integers(0, size, 3))
+        col = (int(rng.integers(1, 5)) * 50, int(rng.integers(0, 3)) * 100, 200, 255)
+        clear = rng.integers(0, 6) == 0
+        for t in (prod, ora):
+            if clear:
+                t.clear(pos)
+            else:
+                t.insert(pos, col)
+    bp, bo = prod.tree.to_bytes(), ora.to_bytes()
+    assert bp == canonical(bo)
+    p2, o2 = ProductIO.from_bytes(bo), OracleOctree.from_bytes(bp)
+    for t in (p2, o2):
+        assert t.mip_enabled() and t.get_method_at(2) == (3, 0.25) and t.get_method_at(3) == (2, 0.0)
+        assert t.structure_hash() == prod.structure_hash() and t.mip_hash() == ora.mip_hash()
+    assert p2.tree.to_bytes() == bp and o2.to_bytes() == bp
+    # the loaded copies keep updating their MIPs like the originals
+    for _ in range(50):
+        pos = tuple(int(v) for v in rng.integers(0, size, 3))
+        for t in (prod, ora, p2, o2):
+            t.insert(pos, (9, 9, 9, 255))
+    assert prod.mip_hash() == ora.mip_hash() == p2.mip_hash() == o2.mip_hash()
 
 
 # ---- (3) the two codecs against each other -----------------------------------------------------------------------

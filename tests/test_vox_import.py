@@ -75,3 +75,25 @@ def test_reference_assets_when_present(name):
     assert a.structure_hash() == b.structure_hash()
     hits = sum(1 for p in xyz[:200] if b.get(tuple(int(q) for q in p)) != (O.EMPTY,))
     assert hits == min(200, len(xyz))
+
+
+def test_load_vox_file_with_a_mip_strategy_updates_mips_while_inserting():
+    """MIPMapStrategy::default().set_enabled(true).load_vox_file(..) (magicavoxel.rs:207-250; examples/minecraft.rs:57-60):
+    the MIPs are built incrementally by the inserts; the oracle fed the same insert sequence must end up identical."""
+    size, v = _model(7, 32)
+    pal = np.random.default_rng(8).integers(1, 256, (256, 4)).astype(np.uint8)
+    pal[:, 3] = 255
+    blob = vox.write_vox([(size, v)], palette=pal)
+    tree = vox.load_vox_file(blob, 4, mip_enabled=True, mip_methods={2: S.MIP_POINT_FILTER, 3: (S.MIP_POSTERIZE, 0.2)},
+                             mip_color_similarity={1: 0.01})
+    su = tree.albedo_mip_map_resampling_strategy()
+    assert su.is_enabled() and su.get_method_at(2) == (S.MIP_POINT_FILTER, 0.0) and su.get_method_at(1)[0] == S.MIP_POINT_FILTER
+    tree_size, xyz, rgba = vox.load_vox(blob, 4)
+    o = O.OracleOctree(tree_size, 4)
+    o.set_method_at(2, 1).set_method_at(3, 3, 0.2).set_color_similarity_thr_at(1, 0.01).switch_albedo_mip_maps(True)
+    o.insert_batch(xyz, rgba)
+    assert tree.structure_hash() == o.structure_hash() and su.mip_hash() == o.mip_hash()
+    assert su.sample_root_mip(8, (0, 0, 0)).kind in (S.api.ENTRY_EMPTY, S.api.ENTRY_VISUAL)
+    plain = vox.load_vox_file(blob, 4)
+    assert not plain.albedo_mip_map_resampling_strategy().is_enabled()
+    assert plain.get_sweep((0, 0, 0), (8, 8, 8)).tobytes() == tree.get_sweep((0, 0, 0), (8, 8, 8)).tobytes()
