@@ -320,6 +320,22 @@ __device__ __forceinline__ bool lod_wants_mip(const RayConst& r, float px, float
     return mip_level < sqrtf((wx * wx) + (wy * wy) + (wz * wz)) / viewing_distance;
 }
 
+// "The LOD test stays false for the rest of this crawl": lets the LOD variant use the crawl fast-forward.
+// While the root keeps failing its occupancy test, every iteration adds 1 to mip_level (L) and direction * 0.1 to p.
+// The test is L' < |origin - a'| / vd with a' = p' rounded to the grid of 2L', so |p' - a'| <= sqrt(3) L', and p' stays
+// inside the cube, so |origin - p'| <= |origin - p| + sqrt(3) size. It is therefore false whenever
+//     L' (1 - sqrt(3) / vd) >= (|origin - p| + sqrt(3) size) / vd ,
+// which for vd >= 4 follows from L' >= L >= 1.77 (|origin - p| + 1.74 size) / vd. The check below asks for
+// L vd >= 4 (|origin - p| + 2 size): more than twice that, far beyond the few ulp the f32 evaluation of the test can be
+// off by. L < 4e6 keeps L + n an exact integer in f32 for any fast-forward count n (< 2^23).
+__device__ __forceinline__ bool lod_quiescent(const RayConst& r, float px, float py, float pz, float mip_level,
+                                              float viewing_distance, float tree_size) {
+    if (!(viewing_distance >= 4.0f) || !(mip_level < 4.0e6f)) return false;
+    const float wx = px - r.ox, wy = py - r.oy, wz = pz - r.oz;
+    const float reach = sqrtf((wx * wx) + (wy * wy) + (wz * wz)) + 2.0f * tree_size;
+    return mip_level * viewing_distance >= 4.0f * reach;  // NaN / 0 * inf compare false
+}
+
 // The loops of get_by_ray_at_lod, raytracing_on_cpu.rs:349-565, entered with the point / octant root_entry produced
 // and a fully set-up RayConst.
 //   LOD = false: the tree's MIP maps are disabled, so the level-of-detail branch (:368-386) is dead code and
@@ -327,8 +343,9 @@ __device__ __forceinline__ bool lod_wants_mip(const RayConst& r, float px, float
 //   LOD = true : MIP maps enabled. `mip_level` follows the reference literally: it starts at log2(size / dim) (:349),
 //                loses 1 per PUSH below the root and gains 1 per POP including the root's, and is NOT reset when the
 //                walk restarts from the root - so it drifts upwards by one per root cycle and downwards whenever the
-//                4-entry ring stack has dropped entries. The crawl fast-forward is replaced by single steps, because
-//                every failing root iteration also raises mip_level and re-evaluates the LOD test.
+//                4-entry ring stack has dropped entries. Every failing root iteration of the crawl also raises
+//                mip_level and re-evaluates the LOD test, so the crawl fast-forward runs only once lod_quiescent()
+//                proves the test false for the rest of the crawl (then n nudges are also n increments of mip_level).
 template <bool LOD>
 __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r, float px, float py, float pz,
                                          uint32_t target_octant, TraceResult& out, float viewing_distance = 0.0f) {
@@ -368,8 +385,12 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 if ((root_hd.x | root_hd.y) != 0u &&
                     ray_may_hit(root_hd.x, root_hd.y, bitmap_coord(cpx), bitmap_coord(cpy), bitmap_coord(cpz), r.dirbits))
                     break;  // the root survives its test: run the node loop below
-                if (LOD) mip_level += 1.0f;  // the root's POP (:447)
-                if (!LOD && ++fails >= 2u) {
+                bool regular = true;
+                if (LOD) {
+                    mip_level += 1.0f;  // the root's POP (:447)
+                    regular = lod_quiescent(r, px, py, pz, mip_level, viewing_distance, tree_size);
+                }
+                if (regular && ++fails >= 2u) {
                     // a run of failing iterations: apply as many nudges as provably change nothing, at once
                     if (remx == 0u) { const CrawlAxis a = crawl_limit(px, cwx, quarter, inv_quarter); qx = a.q; remx = a.limit; }
                     if (remy == 0u) { const CrawlAxis a = crawl_limit(py, cwy, quarter, inv_quarter); qy = a.q; remy = a.limit; }
@@ -379,6 +400,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                         px = crawl_apply(px, qx, n);
                         py = crawl_apply(py, qy, n);
                         pz = crawl_apply(pz, qz, n);
+                        if (LOD) mip_level += (float)n;  // n more root POPs; exact: integers below 2^24
                         if (remx != 0xFFFFFFFFu) remx -= n;
                         if (remy != 0xFFFFFFFFu) remy -= n;
                         if (remz != 0xFFFFFFFFu) remz -= n;

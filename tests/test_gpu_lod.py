@@ -180,3 +180,30 @@ def test_single_ray_get_by_ray_at_lod_mirror():
     assert near.entry.data == 7 and far.entry.data is None  # "Simplified views do not contain user data!" (:323)
     assert far.entry.albedo not in (S.Albedo.from_u32(0xFF0000FF), S.Albedo.from_u32(0x00FF00FF))  # a blended colour
     assert far.impact_point == tuple(float(v) for v in of.impact_point)
+
+
+def test_crawl_under_lod_is_exact_on_a_large_tree():
+    """With MIP maps on, every failing root iteration of the 0.1-nudge crawl also raises mip_level and re-evaluates the
+    LOD test; the kernel fast-forwards only once lod_quiescent() (traverse.cuh) proves the test stays false. Rays
+    skimming a 512^3 terrain, from outside and from inside, over viewing distances on both sides of that switch."""
+    scene = scenes.terrain_scene(512, 8, 4321, 1, shell=4)
+    tree, otree = mip_trees(scene)
+    cam = scenes.terrain_camera(512)
+    ocam = oracle_camera(cam)
+    skim = np.stack([O.pixel_ray(ocam, 320, 180, x, y) for y in range(0, 180, 5) for x in range(0, 320, 5)])
+    rng = np.random.default_rng(9)
+    origin = rng.uniform(1, 511, (2000, 3)).astype(np.float32)
+    origin[:, 1] = rng.uniform(200, 511, 2000).astype(np.float32)
+    d = rng.normal(size=(2000, 3)).astype(np.float32)
+    d[:, 1] = np.abs(d[:, 1]) * 0.2
+    ln = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2], dtype=np.float32)
+    inside = np.concatenate([origin, (d / ln[:, None]).astype(np.float32)], axis=1)
+    host = S.OctreeGPUHost(tree)
+    crawled = 0
+    for rays in (skim, inside):
+        for vd in (F32_MAX, 1.0e6, 5000.0, 700.0, 90.0, 12.0, 4.0, 3.9, 0.7):
+            g = host.get_by_rays(rays, vd)
+            o = otree.get_by_rays_at_lod(rays, vd)
+            assert_rays_equal(g, o)
+            crawled = max(crawled, int(o["outer_iters"].max()))
+    assert crawled > 2000  # the crawl really happens

@@ -2,7 +2,9 @@
 """Randomised GPU-vs-oracle parity soak (GPU box): random trees (sizes, brick dims, edit mixes incl. insert_at_lod and
 clear), random rays (outside / inside / axis-parallel / grazing), every output field compared bit for bit.
 
-    python tools/fuzz_parity.py [--seconds 120] [--seed 0]
+    python tools/fuzz_parity.py [--seconds 120] [--seed 0] [--mips]
+--mips: every tree gets MIP maps (random strategy, switched on before, midway or after the edits) and the rays are
+queried through get_by_ray_at_lod at random viewing distances (src/raytracing/raytracing_on_cpu.rs:325).
 Writes gpurun_out/fuzz_parity.json. Exit code 1 on the first mismatch (the failing case is printed).
 """
 import argparse
@@ -93,51 +95,83 @@ def main():
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--rays", type=int, default=20000)
+    ap.add_argument("--mips", action="store_true")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
-    cases = rays_total = hits_total = 0
+    cases = rays_total = hits_total = mip_probes_total = 0
     configs = [(4, 1), (8, 1), (8, 2), (16, 2), (16, 4), (32, 4), (32, 8), (64, 8), (64, 16), (128, 8), (128, 32), (256, 8), (512, 8), (1024, 16), (32, 1)]
     while time.time() - t0 < args.seconds:
         size, dim = configs[int(rng.integers(0, len(configs)))]
+        if args.mips and size > 256:
+            continue
         ops = random_tree_ops(rng, size, dim)
         a, b = O.OracleOctree(size, dim), ProductOctree(size, dim)
-        apply(a, ops)
-        apply(b, ops)
+        vds = [S.F32_MAX]
+        if args.mips:
+            for lvl in range(1, 6):
+                m = int(rng.integers(0, 6))
+                if m == 2 and lvl > 3:
+                    m = 1  # PointFilterBD samples (2^level)^3 voxels per MIP voxel: keep the soak moving
+                if m < 5:
+                    thr = float(rng.choice([0.0, 0.05, 0.2, 0.5, 1.0]))
+                    for t in (a, b):
+                        t.set_method_at(lvl, m, thr)
+                if rng.random() < 0.3:
+                    thr = float(rng.choice([0.0, 0.01, 0.1, 0.4]))
+                    for t in (a, b):
+                        t.set_color_similarity_thr_at(lvl, thr)
+            when = int(rng.integers(0, 3))  # MIPs on: before the edits / midway / after (one recalculation)
+            cut = 0 if when == 0 else (len(ops) // 2 if when == 1 else len(ops))
+            for t in (a, b):
+                apply(t, ops[:cut])
+                t.switch_albedo_mip_maps(True)
+                apply(t, ops[cut:])
+            if a.mip_hash() != b.mip_hash():
+                print("MIP MISMATCH", size, dim, when, ops[:20])
+                return 1
+            vds = [S.F32_MAX] + [float(v) for v in rng.choice([0.5, 3.0, 10.0, 40.0, 150.0, 600.0, 4000.0], 2, replace=False)]
+        else:
+            apply(a, ops)
+            apply(b, ops)
         if a.structure_hash() != b.structure_hash():
             print("TREE SHAPE MISMATCH", size, dim, ops[:20])
             return 1
-        rays = random_rays(rng, size, args.rays)
-        g = S.OctreeGPUHost(b.tree).get_by_rays(rays)
-        o = a.get_by_rays(rays)
-        ok = (np.array_equal(g["hit"], o["hit"]) and np.array_equal(g["palette_value"], o["palette_value"])
-              and np.array_equal(g["rgba"], o["rgba"]) and np.array_equal(g["data"], o["data"])
-              and np.array_equal(bits(g["impact_point"]), bits(o["impact_point"]))
-              and np.array_equal(bits(g["normal"]), bits(o["normal"])) and np.array_equal(bits(g["distance"]), bits(o["distance"])))
-        if not ok:
-            fields = {
-                "hit": g["hit"] != o["hit"], "palette_value": g["palette_value"] != o["palette_value"],
-                "entry_kind": g["entry_kind"] != o["entry_kind"],
-                "rgba": (g["rgba"] != o["rgba"]).any(axis=1), "data": g["data"] != o["data"],
-                "impact_point": (bits(g["impact_point"]) != bits(o["impact_point"])).any(axis=1),
-                "normal": (bits(g["normal"]) != bits(o["normal"])).any(axis=1),
-                "distance": bits(g["distance"]) != bits(o["distance"]),
-            }
-            print("RAY MISMATCH size", size, "dim", dim, "case", cases, {k: int(v.sum()) for k, v in fields.items()})
-            for k, v in fields.items():
-                idx = np.nonzero(v)[0][:3]
-                for i in idx:
-                    print(" ", k, "ray", rays[i].tolist(), "gpu", g[i], "oracle", {n: o[i][n] for n in g.dtype.names})
-            return 1
-        if int(o["would_panic"].sum()):
-            print("note: reference would have panicked on", int(o["would_panic"].sum()), "rays in case", cases)
+        host = S.OctreeGPUHost(b.tree)
+        for vd in vds:
+            rays = random_rays(rng, size, args.rays)
+            g = host.get_by_rays(rays, vd)
+            o = a.get_by_rays_at_lod(rays, vd)
+            ok = (np.array_equal(g["hit"], o["hit"]) and np.array_equal(g["palette_value"], o["palette_value"])
+                  and np.array_equal(g["rgba"], o["rgba"]) and np.array_equal(g["data"], o["data"])
+                  and np.array_equal(bits(g["impact_point"]), bits(o["impact_point"]))
+                  and np.array_equal(bits(g["normal"]), bits(o["normal"])) and np.array_equal(bits(g["distance"]), bits(o["distance"])))
+            if not ok:
+                fields = {
+                    "hit": g["hit"] != o["hit"], "palette_value": g["palette_value"] != o["palette_value"],
+                    "entry_kind": g["entry_kind"] != o["entry_kind"],
+                    "rgba": (g["rgba"] != o["rgba"]).any(axis=1), "data": g["data"] != o["data"],
+                    "impact_point": (bits(g["impact_point"]) != bits(o["impact_point"])).any(axis=1),
+                    "normal": (bits(g["normal"]) != bits(o["normal"])).any(axis=1),
+                    "distance": bits(g["distance"]) != bits(o["distance"]),
+                }
+                print("RAY MISMATCH size", size, "dim", dim, "case", cases, {k: int(v.sum()) for k, v in fields.items()})
+                for k, v in fields.items():
+                    idx = np.nonzero(v)[0][:3]
+                    for i in idx:
+                        print(" ", k, "ray", rays[i].tolist(), "gpu", g[i], "oracle", {n: o[i][n] for n in g.dtype.names})
+                return 1
+            if int(o["would_panic"].sum()) and not args.mips:  # with MIPs a miss leaves the point outside the node: common
+                print("note: reference would have panicked on", int(o["would_panic"].sum()), "rays in case", cases)
+            rays_total += len(rays)
+            hits_total += int(o["hit"].sum())
+            mip_probes_total += int(o["mip_probes"].sum())
         cases += 1
-        rays_total += len(rays)
-        hits_total += int(o["hit"].sum())
     out = {"seed": args.seed, "seconds": round(time.time() - t0, 1), "random_trees": cases, "rays": rays_total, "hits": hits_total,
+           "mips": bool(args.mips), "mip_probes": mip_probes_total,
            "result": "every field bit-identical to the CPU oracle"}
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / f"fuzz_parity_seed{args.seed}.json").write_text(json.dumps(out))
+    (ROOT / "gpurun_out" / f"fuzz_parity_{'mips_' if args.mips else ''}seed{args.seed}.json").write_text(json.dumps(out))
     print(json.dumps(out))
     return 0
 

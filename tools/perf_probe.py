@@ -1,5 +1,9 @@
 #!/usr/bin/env python3
-"""Quick kernel-time probe over several scenes (GPU box). Prints ms/frame (L2 flushed) and Grays/s per scene."""
+"""Quick kernel-time probe over several scenes (GPU box). Prints ms/frame (L2 flushed) and Grays/s per scene.
+
+    python tools/perf_probe.py [--mips VIEWING_DISTANCE] [scene ...]
+--mips: switch the trees' MIP maps on (default strategy) and render through get_by_ray_at_lod at that viewing distance
+(the LOD kernel variant); "frustum" uses each camera's viewport.frustum.z like the reference's shader does."""
 import json
 import sys
 import time
@@ -28,7 +32,13 @@ CASES = {
 
 
 def main():
-    names = sys.argv[1:] or list(CASES)
+    argv = sys.argv[1:]
+    mips = None
+    if "--mips" in argv:
+        i = argv.index("--mips")
+        mips = argv[i + 1]
+        del argv[i:i + 2]
+    names = argv or list(CASES)
     trees = {}
     out = {}
     for name in names:
@@ -36,13 +46,21 @@ def main():
         sc = mk_scene()
         if sc.name not in trees:
             t0 = time.time()
-            trees[sc.name] = (scenes.build_tree(sc, S.Octree), time.time() - t0)
+            tree = scenes.build_tree(sc, S.Octree)
+            tb = time.time() - t0
+            if mips is not None:
+                t0 = time.time()
+                tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
+                print(f"  MIP maps of {sc.name} built in {time.time() - t0:.1f} s", flush=True)
+            trees[sc.name] = (tree, tb)
         tree, tb = trees[sc.name]
         cam = mk_cam()
         host = S.OctreeGPUHost(tree)
         view = host.create_new_view(64, S.Viewport(cam.origin, cam.direction, cam.frustum, cam.fov), res)
         if cam.glass_at_frustum_z:
             view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+        if mips is not None:
+            view.set_viewing_distance(float(cam.frustum[2]) if mips == "frustum" else float(mips))
         ms = []
         for i in range(12):
             view.flush_l2()
@@ -63,7 +81,7 @@ def main():
         print(f"{name:24s} {out[name]['ms']:9.4f} ms (warm L2 {out[name]['ms_warm']:8.4f})  {out[name]['grays']:8.2f} Grays/s  hits {hits:8d}  nodes {st['nodes']:6d} "
               f"bricks {st['bricks']:6d} depth {st['depth']} tree {st['total_bytes'] / 1e6:7.1f} MB", flush=True)
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / "perf_probe.json").write_text(json.dumps(out, indent=1))
+    (ROOT / "gpurun_out" / ("perf_probe.json" if mips is None else f"perf_probe_mips_{mips}.json")).write_text(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":
