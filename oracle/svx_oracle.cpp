@@ -1726,6 +1726,9 @@ void Octree::update_mip(size_t node_key, const Cube& node_bounds, V3u position) 
             return;
         case NodeKind::Leaf: {
             sample_size = std::min(size_u / brick_dim, brick_dim * 2);
+            // insert_at_lod with a size <= brick_dim can split leaves into nodes SMALLER than a brick (insert.rs:137-147);
+            // for those `size / dim` is 0 and the reference panics on `position % 0` - the MIP is left alone here
+            if (sample_size == 0) return;
             const V3u t = {(position.x - (position.x % sample_size)) * 2 * brick_dim,
                            (position.y - (position.y % sample_size)) * 2 * brick_dim,
                            (position.z - (position.z % sample_size)) * 2 * brick_dim};
@@ -1736,6 +1739,7 @@ void Octree::update_mip(size_t node_key, const Cube& node_bounds, V3u position) 
         case NodeKind::Internal:
             if (dominant_bottom) {
                 sample_size = size_u / brick_dim;
+                if (sample_size == 0) return;  // as above: remainder by zero, a panic in the reference
                 const V3f f = to_f32(V3u{position.x - (position.x % sample_size), position.y - (position.y % sample_size),
                                          position.z - (position.z % sample_size)});
                 sample_start = {f2u32_round(std::floor(f.x)), f2u32_round(std::floor(f.y)), f2u32_round(std::floor(f.z))};

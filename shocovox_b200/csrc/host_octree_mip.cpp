@@ -294,7 +294,10 @@ void HostOctree::update_mip(size_t key, const BoundsF& nb, uint32_t x, uint32_t 
     if (from_voxels) {
         // sample the voxels themselves through get(): Leaf -> the 2^3 voxels under the MIP voxel (:338-375);
         // bottom-dominant Internal -> the whole (size/dim)^3 region (:376-411)
+        // insert_at_lod with a size <= brick_dim can split leaves into nodes smaller than a brick (insert.rs:137-147):
+        // there `size / dim` is 0 and the reference panics on `position % 0`; such a node keeps its MIP as it is
         uint32_t span, start[3];
+        if (node_size / dim_ == 0) return;
         if (node.kind == NK_LEAF) {
             span = std::min(node_size / dim_, dim_ * 2);
             for (int c = 0; c < 3; ++c) {

@@ -221,3 +221,23 @@ def test_enabling_mips_later_equals_recalculation():
         t.recalculate_mips()
         # BoxFilter may have added palette colours the first time; the bricks themselves must not move
         assert t.mip_hash() == h
+
+
+def test_nodes_smaller_than_a_brick_keep_their_mips_untouched():
+    """insert_at_lod with a size <= brick_dim splits leaves into nodes smaller than one brick (insert.rs:137-147). The
+    reference's update_mip then computes `position % (size / dim)` = `% 0` and panics; oracle and product skip the MIP
+    update of such a node instead (and must agree with each other everywhere else)."""
+    a, b = OracleOctree(16, 4), ProductOctree(16, 4)
+    for t in (a, b):
+        t.switch_albedo_mip_maps(True)
+        t.insert((9, 9, 13), RED)
+        t.insert_at_lod((8, 8, 12), 2, GREEN)      # aligned and lexicographically <= the child's corner
+        t.insert_at_lod((4, 6, 2), 2, BLUE)
+        t.insert((8, 9, 13), 0x123456FF)
+        t.insert((5, 6, 2), 0x654321FF)
+        t.clear((8, 8, 12))
+    assert a.structure_hash() == b.structure_hash()
+    assert a.mip_hash() == b.mip_hash()
+    a.recalculate_mips()
+    b.recalculate_mips()
+    assert a.mip_hash() == b.mip_hash()
