@@ -10,8 +10,12 @@
 // test-suite holds for the path (tests/test_oracle_*.py):
 //   src/raytracing/tests.rs:253-813 (17 literal rays), :817-911 (ring stack),
 //   src/spatial/tests.rs, src/spatial/math/tests.rs, src/spatial/raytracing/tests.rs,
-//   src/octree/update/tests.rs (insert / insert_at_lod / update black-box tests),
+//   src/octree/update/tests.rs (insert / insert_at_lod / update / clear black-box tests),
+//   src/octree/tests.rs:154-567 (the five mipmap KATs: MIP bricks after inserts and after recalculate_mips),
 //   and the literal LUT tables in src/spatial/lut.rs:154-896 (tests/golden/luts.json).
+//
+// NOT pinned by any reference test (parity = the line-by-line restatement): exact impact points, the internal tree shape,
+// and the level-of-detail branch of get_by_ray_at_lod with a finite viewing distance (raytracing_on_cpu.rs:368-386).
 //
 // All `file:line` citations are relative to /root/reference/.
 #pragma once

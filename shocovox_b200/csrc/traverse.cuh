@@ -312,8 +312,24 @@ __device__ __forceinline__ float crawl_apply(float x, int q, uint32_t n) {
 // mip_level * 2 is not a power of two in general: IEEE division, f32::round = roundf (half away from zero). A
 // mip_level of 0 gives inf / NaN operands and a false comparison, a negative one (the level drifts, see below) just
 // computes - both exactly as in the reference.
+//
+// Most evaluations are far from the boundary, so a bracketing pre-test decides them without the three IEEE divisions:
+// a (p rounded to the grid of 2L) lies within sqrt(3) L of p - plus at most 2^-22 |p| per axis from the rounded quotient
+// and product, < 1 for trees up to 2^20 - so D = |origin - a| is within s = 1.75 L + 1 of d = |origin - p|. With
+// t = L vd the test "L < D / vd" is certainly false when t - s > d and certainly true when d - s > t; both sides carry
+// a 1e-5 relative margin, two orders above what the f32 evaluation of either form can be off by. Everything in between,
+// and every odd input (L < 1, vd <= 0 or NaN, huge trees), takes the exact form.
 __device__ __forceinline__ bool lod_wants_mip(const RayConst& r, float px, float py, float pz, float mip_level,
-                                              float viewing_distance) {
+                                              float viewing_distance, float tree_size) {
+    if (mip_level >= 1.0f && viewing_distance > 0.0f && tree_size <= 1048576.0f) {
+        const float vx = px - r.ox, vy = py - r.oy, vz = pz - r.oz;
+        const float d2 = (vx * vx) + (vy * vy) + (vz * vz);
+        const float t = mip_level * viewing_distance, s = 1.75f * mip_level + 1.0f;
+        const float u = t * 0.99999f - s;
+        if (u > 0.0f && u * u > d2 * 1.00001f) return false;
+        const float v = t * 1.00001f + s;
+        if (d2 * 0.99999f > v * v) return true;
+    }
     const float m2 = mip_level * 2.0f;
     const float ax = roundf(px / m2) * m2, ay = roundf(py / m2) * m2, az = roundf(pz / m2) * m2;
     const float wx = r.ox - ax, wy = r.oy - ay, wz = r.oz - az;
@@ -381,7 +397,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 const float cpy = rust_clamp((py * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
                 const float cpz = rust_clamp((pz * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
                 // LOD: the root's MIP is probed before the occupancy test (:368-386) - leave that to the node loop
-                if (LOD && lod_wants_mip(r, px, py, pz, mip_level, viewing_distance)) break;
+                if (LOD && lod_wants_mip(r, px, py, pz, mip_level, viewing_distance, tree_size)) break;
                 if ((root_hd.x | root_hd.y) != 0u &&
                     ray_may_hit(root_hd.x, root_hd.y, bitmap_coord(cpx), bitmap_coord(cpy), bitmap_coord(cpz), r.dirbits))
                     break;  // the root survives its test: run the node loop below
@@ -434,7 +450,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             if (LOD) {
                 // :368-386 far enough away, the node's MIP brick stands in for its content. A miss leaves the point
                 // where the brick walk ended and target_octant as it was.
-                if (lod_wants_mip(r, px, py, pz, mip_level, viewing_distance)) {
+                if (lod_wants_mip(r, px, py, pz, mip_level, viewing_distance, tree_size)) {
                     const uint32_t mkind = (meta >> 18) & 3u;
                     if (mkind != BK_EMPTY &&
                         probe_brick(t, r, px, py, pz, mkind, __ldg(t.node_mip + cur), bx, by, bz, bsize, binv, out))
