@@ -23,14 +23,20 @@ namespace svx {
 #ifndef SVX_TICKET_TILES
 #define SVX_TICKET_TILES 1u   // tiles per ticket of the persistent schedule (1, 2, 4 or 8); measured: 1 is best, larger tickets lengthen the tail
 #endif
-constexpr int TILE_W = 8 * SVX_BLOCK_WARPS_X;
-constexpr int TILE_H = 4 * SVX_BLOCK_WARPS_Y;
+// Shape of the pixel tile one warp renders: 2^SVX_WARP_LOG2_W x 2^(5 - SVX_WARP_LOG2_W) pixels (3: 8x4, 4: 16x2, 5: 32x1)
+#ifndef SVX_WARP_LOG2_W
+#define SVX_WARP_LOG2_W 3
+#endif
+constexpr int WARP_LW = SVX_WARP_LOG2_W, WARP_LH = 5 - SVX_WARP_LOG2_W;
+constexpr int WARP_W = 1 << WARP_LW, WARP_H = 1 << WARP_LH;
+constexpr int TILE_W = WARP_W * SVX_BLOCK_WARPS_X;
+constexpr int TILE_H = WARP_H * SVX_BLOCK_WARPS_Y;
 constexpr int BLOCK_THREADS = 32 * SVX_BLOCK_WARPS_X * SVX_BLOCK_WARPS_Y;
 
 __device__ __forceinline__ void pixel_of_thread(int& tx, int& ty) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tx = ((warp % SVX_BLOCK_WARPS_X) << 3) + (lane & 7);
-    ty = ((warp / SVX_BLOCK_WARPS_X) << 2) + (lane >> 3);
+    tx = ((warp % SVX_BLOCK_WARPS_X) << WARP_LW) + (lane & (WARP_W - 1));
+    ty = ((warp / SVX_BLOCK_WARPS_X) << WARP_LH) + (lane >> WARP_LW);
 }
 
 // Ray generation of the caller loop, reference examples/cpu_render.rs:104-114, in its f32 operation order:
