@@ -125,6 +125,29 @@ class ClockSampler:
 
 
 # ---- CPU oracle legs -------------------------------------------------------------------------------------------------
+F32_MAX = 3.4028234663852886e38
+
+
+def viewing_distance_of(args, cam) -> float:
+    """--mips VD: get_by_ray_at_lod's viewing distance; "frustum" = the camera's viewport.frustum.z, which is what the
+    reference's own GPU path feeds (assets/shaders/viewport_render.wgsl:631-638). Without --mips: f32::MAX (get_by_ray)."""
+    if args.mips is None:
+        return F32_MAX
+    return float(cam.frustum[2]) if args.mips == "frustum" else float(args.mips)
+
+
+def enable_mips(args, product_tree=None, oracle_tree=None):
+    """--mips: MIPMapStrategy::default() switched on after construction (one recalculate_mips), on both implementations."""
+    if args.mips is None:
+        return 0.0
+    t0 = time.time()
+    if product_tree is not None:
+        product_tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
+    if oracle_tree is not None:
+        oracle_tree.switch_albedo_mip_maps(True)
+    return time.time() - t0
+
+
 def oracle_camera(cam):
     import oracle_lib as O
 
@@ -137,7 +160,7 @@ def sample_rows(height: int, n_rows: int) -> np.ndarray:
     return np.unique(np.linspace(0, height - 1, n_rows).round().astype(np.uint32))
 
 
-def oracle_timed_sample(otree, cam, res, budget_s: float, whole_frames: bool):
+def oracle_timed_sample(otree, cam, res, budget_s: float, whole_frames: bool, vd: float = F32_MAX):
     """Times the CPU oracle with all host threads on the workload: whole frames when they are quick, else a bounded
     sample of evenly spread rows sized from a probe so that the leg takes about `budget_s` seconds."""
     import oracle_lib as O
@@ -148,7 +171,7 @@ def oracle_timed_sample(otree, cam, res, budget_s: float, whole_frames: bool):
     if whole_frames:
         frames, total = [], 0.0
         while len(frames) < 12 and (total < budget_s or len(frames) < 2):
-            f = otree.render(ocam, w, h, threads=threads)
+            f = otree.render(ocam, w, h, threads=threads, viewing_distance=vd)
             frames.append(f)
             total += f["seconds"]
         best = min(frames, key=lambda f: f["seconds"])
@@ -157,11 +180,11 @@ def oracle_timed_sample(otree, cam, res, budget_s: float, whole_frames: bool):
                 "mrays": w * h / best["seconds"] / 1e6,
                 "sample": f"{len(frames)} whole frames of the workload ({w * h} rays each) on {threads} host threads; best frame"}
     probe_rows = sample_rows(h, 4)
-    probe = otree.render(ocam, w, h, threads=threads, row_list=probe_rows)
+    probe = otree.render(ocam, w, h, threads=threads, row_list=probe_rows, viewing_distance=vd)
     per_row = max(probe["seconds"] / len(probe_rows), 1e-6)
     n = int(min(h, max(8, budget_s / per_row)))
     rows = sample_rows(h, n)
-    f = otree.render(ocam, w, h, threads=threads, row_list=rows)
+    f = otree.render(ocam, w, h, threads=threads, row_list=rows, viewing_distance=vd)
     rays = len(rows) * w
     return {"frame": f, "rows": rows, "threads": threads, "rays": rays, "seconds": f["seconds"], "mrays": rays / f["seconds"] / 1e6,
             "sample": f"{len(rows)} of {h} image rows spread evenly over one frame ({rays} rays) on {threads} host threads"}
@@ -177,20 +200,22 @@ def run_reference(args, rank: int):
 
     scene, cams, res, desc = make_workload(args.workload)
     tree = scenes.build_tree(scene, O.OracleOctree)
+    enable_mips(args, oracle_tree=tree)
+    vd = viewing_distance_of(args, cams[0])
     threads = int(O.lib().svxo_hardware_threads())
     w, h = res
     whole = args.workload not in HEAVY
     rows = np.arange(h, dtype=np.uint32)
     if not whole:
-        probe = tree.render(oracle_camera(cams[0]), w, h, threads=threads, row_list=sample_rows(h, 4))
+        probe = tree.render(oracle_camera(cams[0]), w, h, threads=threads, row_list=sample_rows(h, 4), viewing_distance=vd)
         per_row = max(probe["seconds"] / 4, 1e-6)
         budget = 120.0 / max(args.steps + args.warmup, 1)
         rows = sample_rows(h, int(min(h, max(4, budget / per_row))))
     for i in range(args.warmup):
-        tree.render(oracle_camera(cams[i % len(cams)]), w, h, threads=threads, row_list=rows)
+        tree.render(oracle_camera(cams[i % len(cams)]), w, h, threads=threads, row_list=rows, viewing_distance=vd)
     t = 0.0
     for i in range(args.steps):
-        t += tree.render(oracle_camera(cams[i % len(cams)]), w, h, threads=threads, row_list=rows)["seconds"]
+        t += tree.render(oracle_camera(cams[i % len(cams)]), w, h, threads=threads, row_list=rows, viewing_distance=vd)["seconds"]
     rays = len(rows) * w
     value = rays * args.steps / t / 1e6
     sample = (f"{args.steps} steps, each {'one whole frame' if whole else f'{len(rows)} of {h} rows spread over the frame'} "
@@ -199,7 +224,8 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "resolution": list(res), "rays_per_step": rays},
+        "config": {"workload": args.workload, "description": desc, "resolution": list(res), "rays_per_step": rays,
+                   **({"mips": {"strategy": "MIPMapStrategy::default(), enabled", "viewing_distance": vd}} if args.mips is not None else {})},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -217,6 +243,9 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dot_cube_1080p", choices=list(WORKLOADS))
     ap.add_argument("--mode", default="poses", choices=["poses", "tiles", "tiles_fused"])
+    ap.add_argument("--mips", default=None, metavar="VD",
+                    help="switch the tree's MIP maps on and render through get_by_ray_at_lod at this viewing distance "
+                         "(a number, or 'frustum' for the camera's viewport.frustum.z like the reference's shader)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=8.0, help="seconds of CPU-oracle work for the cpu_baseline leg")
     ap.add_argument("--extra", action="store_true", help="also measure the other quick workloads (kernel time only)")
@@ -258,12 +287,20 @@ def main() -> int:
     w, h = res
     t_build = time.time()
     tree = scenes.build_tree(scene, S.Octree)
+    t_mips = enable_mips(args, product_tree=tree)
+    vd = viewing_distance_of(args, cams[0])
     host = S.OctreeGPUHost(tree, local_rank)
     t_build = time.time() - t_build
     vps = [S.Viewport(c.origin, c.direction, c.frustum, c.fov) for c in cams]
-    view = host.create_new_view(64, vps[0], res)
-    if cams[0].glass_at_frustum_z:
-        view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+
+    def new_view():
+        v = host.create_new_view(64, vps[0], res)
+        if cams[0].glass_at_frustum_z:
+            v.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+        v.set_viewing_distance(vd)
+        return v
+
+    view = new_view()
     tiles = args.mode != "poses" and world > 1
     rays_per_frame = w * h
     # pose mode: step i of rank r renders pose (r + i * world) mod n_poses ; tile mode: everybody renders pose i
@@ -285,7 +322,7 @@ def main() -> int:
                 with torch.cuda.stream(stream):
                     return [D.gather_bands(p, h, world, band) for p in planes]
         else:
-            target = host.create_new_view(64, vps[0], res)  # rank 0's copy is the shared destination
+            target = new_view()  # rank 0's copy is the shared destination
             blob = D.exchange_ipc_handles(target.export_frame_ipc(), src_rank=0)
             if rank != 0:
                 view.set_peer_frame_ipc(blob)
@@ -355,9 +392,7 @@ def main() -> int:
     ptrs = ptr_sets[0]
     e2e_view = view
     if tiles:  # end to end is measured on whole frames per rank (the public single-GPU call), not on shards
-        e2e_view = host.create_new_view(64, vps[0], res)
-        if cams[0].glass_at_frustum_z:
-            e2e_view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+        e2e_view = new_view()
     for i in range(3):
         e2e_view.set_viewport(vps[pose_index(i)])
         e2e_view.render_to_host_ptr(*ptrs)
@@ -416,6 +451,8 @@ def main() -> int:
             "l2": "flushed before every timed step (384 MiB memset on the launch stream, outside the event pair)",
             "tree_bytes": st["total_bytes"], "tree_nodes": st["nodes"], "tree_bricks": st["bricks"], "tree_depth": st["depth"],
             "tree_build_s": round(t_build, 3), "voxels_inserted": int(len(scene.xyz)),
+            **({"mips": {"strategy": "MIPMapStrategy::default(), enabled after construction (one recalculate_mips)",
+                         "viewing_distance": vd, "recalculate_s": round(t_mips, 3)}} if args.mips is not None else {}),
         },
         "value_warm_l2": value_warm, "ms_per_step_warm_l2": warm_ms_total / args.steps,
         "wall_ms_per_step_incl_flush": (wall1 - wall0) * 1e3 / args.steps,
@@ -446,8 +483,9 @@ def main() -> int:
 
             t0 = time.time()
             otree = scenes.build_tree(scene, O.OracleOctree)
+            enable_mips(args, oracle_tree=otree)
             t_obuild = time.time() - t0
-            o = oracle_timed_sample(otree, cams[0], res, args.cpu_budget, whole_frames=args.workload not in HEAVY)
+            o = oracle_timed_sample(otree, cams[0], res, args.cpu_budget, whole_frames=args.workload not in HEAVY, vd=vd)
             f = o["frame"]
             # algorithmic bytes of ONE launch (pose 0): counted on the sampled rays, scaled to the frame when sampled
             scale = rays_per_frame / o["rays"]
@@ -461,7 +499,7 @@ def main() -> int:
             line["roofline"] = {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "achieved_excluding_fast_forwarded_restarts": achieved_nocrawl, "frac_excluding_fast_forwarded_restarts": achieved_nocrawl / peak,
-                "peak_source": peak_src, "kernel": "svx::render_kernel",
+                "peak_source": peak_src, "kernel": "svx::render_lod_kernel" if args.mips is not None else "svx::render_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "per_ray": {"node_visits": f["node_iters"] / o["rays"], "voxel_fetches": f["voxel_fetches"] / o["rays"],
                             "restarts": f["outer_iters"] / o["rays"], "crawl_restarts": f["crawl_iters"] / o["rays"],
@@ -477,9 +515,7 @@ def main() -> int:
             line["cpu_baseline"] = {"value": o["mrays"], "unit": UNIT, "cores": o["threads"], "kind": "port", "sample": o["sample"],
                                     "oracle_tree_build_s": round(t_obuild, 2)}
             # parity spot check of what was just timed (outside every timed region): pose 0, the sampled rows
-            chk = host.create_new_view(64, vps[0], res)
-            if cams[0].glass_at_frustum_z:
-                chk.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+            chk = new_view()
             got = chk.render_to_host()
             rows = o["rows"]
             line["parity_vs_oracle"] = {
@@ -488,6 +524,8 @@ def main() -> int:
                 "albedo_equal": bool(np.array_equal(got["albedo"][rows], f["albedo"].view(np.uint32)[..., 0][rows])),
                 "distance_bits_equal": bool(np.array_equal(got["distance"][rows].view(np.uint32), f["distance"][rows].view(np.uint32))),
                 "would_panic": int(f["would_panic"]),
+                **({"mip_probes": int(f["mip_probes"]), "mip_hash_equal": bool(tree.albedo_mip_map_resampling_strategy().mip_hash() == otree.mip_hash())}
+                   if args.mips is not None else {}),
             }
         if args.extra and world == 1:
             extra = {}
