@@ -294,6 +294,7 @@ int32_t upload(svx_gpu_host* h) {
     d.tree_size = s.tree_size;
     d.brick_dim = s.brick_dim;
     d.brick_shift = s.brick_shift;
+    d.brick_dim_sq = s.brick_dim * s.brick_dim;
     d.bit_words = s.bit_words;
     d.n_colors = (uint32_t)tree.color_palette().size();
     d.inv_tree_size = 1.0f / (float)s.tree_size;

@@ -52,6 +52,7 @@ struct DeviceTree {
     uint32_t tree_size;
     uint32_t brick_dim;
     uint32_t brick_shift;       // log2(brick_dim)
+    uint32_t brick_dim_sq;      // brick_dim^2: the z stride of flat_projection
     uint32_t bit_words;         // u32 words of brick_bits per brick
     uint32_t n_colors;
     uint32_t mips_enabled;      // MIPMapStrategy::is_enabled (mipmap.rs:693): the LOD kernel variant runs

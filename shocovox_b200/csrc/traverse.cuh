@@ -149,13 +149,19 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     const float ux = r.negx ? -unit : unit, uy = r.negy ? -unit : unit, uz = r.negz ? -unit : unit;
     const float ex = r.negx ? bx - unit : bx + bsize, ey = r.negy ? by - unit : by + bsize, ez = r.negz ? bz - unit : bz + bsize;
     const uint32_t sh = t.brick_shift;
-    // flat_projection(ix, iy, iz) kept incrementally, like the reference's current_flat_index (:205-207)
-    uint32_t flat = (uint32_t)ix + ((uint32_t)iy << sh) + ((uint32_t)iz << (2 * sh));
-    const uint32_t fsx = (uint32_t)r.isx, fsy = (uint32_t)(r.isy << sh), fsz = (uint32_t)(r.isz << (2 * sh));
+    // flat_projection(ix, iy, iz) kept incrementally, like the reference's current_flat_index (:205-207) - but in
+    // MIRRORED coordinates: along an axis the ray descends, the loop counts j = dim-1 - i = i ^ (dim-1) instead of i, so
+    // every step adds +1 / +dim / +dim^2 (uniform values, no per-ray signed strides to keep or rebuild in the loop) and
+    // the real flat index is `mirrored ^ flip` with one per-brick mask. A walk that leaves the brick is caught by the
+    // corner test below before the (then meaningless) index is used again.
+    const uint32_t dmask = (uint32_t)dim - 1u;
+    const uint32_t flip = (r.negx ? dmask : 0u) | (r.negy ? dmask << sh : 0u) | (r.negz ? dmask << (2 * sh) : 0u);
+    uint32_t mirrored = ((uint32_t)ix + ((uint32_t)iy << sh) + ((uint32_t)iz << (2 * sh))) ^ flip;
     const uint32_t base = brick * t.bit_words;  // word offset of this brick's bits; all bit words fit 32 bits (gpu_tree.cpp)
     uint32_t word_index = 0xFFFFFFFFu;
     uint32_t word = 0u;
     for (;;) {
+        const uint32_t flat = mirrored ^ flip;
         if ((flat >> 5) != word_index) {
             word_index = flat >> 5;
             word = __ldg(t.brick_bits + (base + word_index));
@@ -163,10 +169,9 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
         if ((word >> (flat & 31u)) & 1u) return (int)flat;
         bool sx, sy, sz;
         dda_step(r, px, py, pz, cx, cy, cz, unit, sx, sy, sz);
-        flat += (sx ? fsx : 0u) + (sy ? fsy : 0u) + (sz ? fsz : 0u);
-        if (sx) cx = cx + ux;
-        if (sy) cy = cy + uy;
-        if (sz) cz = cz + uz;
+        if (sx) { mirrored += 1u; cx = cx + ux; }
+        if (sy) { mirrored += t.brick_dim; cy = cy + uy; }
+        if (sz) { mirrored += t.brick_dim_sq; cz = cz + uz; }
         if (cx == ex || cy == ey || cz == ez) return -1;
     }
 }
