@@ -221,12 +221,21 @@ SVX_API int32_t svx_gpu_host_get_by_rays(svx_gpu_host* host, const svx_ray* rays
 SVX_API int32_t svx_gpu_host_get_by_rays_at_lod(svx_gpu_host* host, const svx_ray* rays, uint64_t n, float viewing_distance,
                                                 svx_hit* hits);
 
+/* Octree::get_by_ray(&Ray) / get_by_ray_at_lod(&Ray, viewing_distance) on the tree handle itself
+ * (src/raytracing/raytracing_on_cpu.rs:316-325): one ray, answered on the GPU. The tree keeps a device copy on device 0,
+ * created on first use and brought up to date before every query; without a CUDA device the call fails with SVX_E_CUDA
+ * (there is no CPU ray path). For many rays use svx_gpu_host_get_by_rays. */
+SVX_API int32_t svx_octree_get_by_ray(svx_octree* tree, const svx_ray* ray, svx_hit* out);
+SVX_API int32_t svx_octree_get_by_ray_at_lod(svx_octree* tree, const svx_ray* ray, float viewing_distance, svx_hit* out);
+
 /* ---- OctreeGPUView: viewport + framebuffer -------------------------------------------------------------- */
 /* OctreeGPUHost::create_new_view, src/raytracing/bevy/data.rs:111-166. `size_hint` is the reference's node-cache
  * capacity; the whole tree is resident here so it is ignored. resolution = [width, height]. */
 SVX_API int32_t svx_gpu_host_create_view(svx_gpu_host* host, uint32_t size_hint, const svx_viewport* viewport,
                                          uint32_t width, uint32_t height, svx_view** out);
 SVX_API void svx_view_free(svx_view* view);
+/* OctreeGPUView::reload, src/raytracing/bevy/mod.rs:56-60: svx_gpu_host_reload of the host this view renders */
+SVX_API int32_t svx_view_reload(svx_view* view);
 /* OctreeSpyGlass::viewport / viewport_mut, src/raytracing/bevy/mod.rs:90-99 */
 SVX_API int32_t svx_view_get_viewport(const svx_view* view, svx_viewport* out);
 SVX_API int32_t svx_view_set_viewport(svx_view* view, const svx_viewport* viewport);

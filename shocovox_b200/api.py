@@ -144,6 +144,7 @@ EXPORTS = [
     "svx_octree_mip_set_method_at", "svx_octree_mip_get_method_at", "svx_octree_mip_set_color_similarity_thr_at",
     "svx_octree_mip_get_color_similarity_at", "svx_octree_mip_reset", "svx_octree_mip_sample_root", "svx_octree_mip_hash",
     "svx_gpu_host_get_by_rays_at_lod", "svx_view_set_viewing_distance", "svx_view_get_viewing_distance",
+    "svx_octree_get_by_ray", "svx_octree_get_by_ray_at_lod", "svx_view_reload",
     "svx_octree_to_bytes", "svx_bytes_free", "svx_octree_from_bytes", "svx_octree_save", "svx_octree_load",
     "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_last_upload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
@@ -218,6 +219,9 @@ def lib() -> C.CDLL:
     L.svx_gpu_host_get_by_rays_at_lod.argtypes = [vp, vp, u64, f32, vp]
     L.svx_view_set_viewing_distance.argtypes = [vp, f32]
     L.svx_view_get_viewing_distance.argtypes = [vp, C.POINTER(f32)]
+    L.svx_octree_get_by_ray.argtypes = [vp, C.POINTER(_Ray), C.POINTER(_Hit)]
+    L.svx_octree_get_by_ray_at_lod.argtypes = [vp, C.POINTER(_Ray), f32, C.POINTER(_Hit)]
+    L.svx_view_reload.argtypes = [vp]
     L.svx_gpu_host_create.argtypes = [vp, i32, C.POINTER(vp)]
     L.svx_gpu_host_free.argtypes = [vp]
     L.svx_gpu_host_free.restype = None
@@ -497,6 +501,16 @@ class Octree:
 
     # `Octree::get_by_ray_at_lod(&Ray, viewing_distance)` (src/raytracing/raytracing_on_cpu.rs:325)
     def get_by_ray_at_lod(self, ray: Ray, viewing_distance: float, device: int = 0) -> Optional[RayHit]:
+        if device == 0:  # svx_octree_get_by_ray_at_lod: the tree handle keeps its own device copy on device 0
+            r, h = _Ray(), _Hit()
+            r.origin[:] = [float(v) for v in ray.origin]
+            r.direction[:] = [float(v) for v in ray.direction]
+            _check(lib().svx_octree_get_by_ray_at_lod(self._h, C.byref(r), float(viewing_distance), C.byref(h)))
+            if not h.hit:
+                return None
+            e = OctreeEntry._from_c(h.entry)
+            return RayHit(e, tuple(float(v) for v in h.impact_point), tuple(float(v) for v in h.normal),
+                          int(h.palette_value), float(h.distance))
         host = getattr(self, "_ray_host", None)
         if host is None or host.device != device:
             host = OctreeGPUHost(self, device)
@@ -640,7 +654,7 @@ class OctreeGPUView:
             self._h = C.c_void_p()
 
     def reload(self):
-        self.host.reload()
+        _check(lib().svx_view_reload(self._h))
 
     def viewport(self) -> Viewport:
         v = _Viewport()

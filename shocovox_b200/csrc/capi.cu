@@ -121,8 +121,12 @@ inline Vec3 operator/(Vec3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
 
 }  // namespace
 
+struct svx_gpu_host;
 struct svx_octree {
     HostOctree* tree = nullptr;
+    // svx_octree_get_by_ray[_at_lod]: a device copy created on first use (device 0) and reloaded before every query
+    svx_gpu_host* ray_host = nullptr;
+    std::mutex ray_mu;
 };
 
 struct svx_gpu_host {
@@ -574,6 +578,7 @@ int32_t svx_octree_new(uint32_t size, uint32_t brick_dim, svx_octree** out) {
 }
 void svx_octree_free(svx_octree* tree) {
     if (!tree) return;
+    svx_gpu_host_free(tree->ray_host);
     delete tree->tree;
     delete tree;
 }
@@ -780,6 +785,28 @@ int32_t svx_gpu_host_reload(svx_gpu_host* h) {
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
     return upload(h);
+}
+
+// Octree::get_by_ray / get_by_ray_at_lod on the tree handle itself (raytracing_on_cpu.rs:316-325): one ray, on the GPU.
+int32_t svx_octree_get_by_ray_at_lod(svx_octree* t, const svx_ray* ray, float viewing_distance, svx_hit* out) {
+    if (!t || !ray || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(t->ray_mu);
+    if (!t->ray_host) {
+        const int32_t created = svx_gpu_host_create(t, 0, &t->ray_host);  // SVX_E_CUDA without a device: no CPU path
+        if (created != SVX_OK) return created;
+    } else {
+        const int32_t reloaded = svx_gpu_host_reload(t->ray_host);
+        if (reloaded != SVX_OK) return reloaded;
+    }
+    return svx_gpu_host_get_by_rays_at_lod(t->ray_host, ray, 1, viewing_distance, out);
+}
+int32_t svx_octree_get_by_ray(svx_octree* t, const svx_ray* ray, svx_hit* out) {
+    return svx_octree_get_by_ray_at_lod(t, ray, 3.402823466e+38f, out);
+}
+// OctreeGPUView::reload, src/raytracing/bevy/mod.rs:56-60
+int32_t svx_view_reload(svx_view* v) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    return svx_gpu_host_reload(v->host);
 }
 
 int32_t svx_gpu_host_last_upload(const svx_gpu_host* h, svx_upload_stats* out) {
