@@ -47,7 +47,11 @@ int main(int argc, char** argv) {
 
         OctreeGPUHost host(tree);
         OctreeGPUView view = host.create_new_view(64, vp, {W, H});
+        // define light: V3c::new(0., -1., 1.).normalized() (cpu_render.rs:97)
+        const float ll = std::sqrt((0.0f * 0.0f) + (-1.0f * -1.0f) + (1.0f * 1.0f));
+        view.set_shading({0.0f / ll, -1.0f / ll, 1.0f / ll});
         const Frame frame = view.render_to_host();
+        const std::vector<uint32_t> shaded = view.read_shaded();  // the image the reference example builds
         size_t hits = 0;
         for (uint32_t id : frame.hit_id) hits += id != 0xFFFFFFFFu;
         uint64_t digest = fnv1a(frame.hit_id.data(), frame.hit_id.size() * 4);
@@ -57,8 +61,8 @@ int main(int argc, char** argv) {
         if (argc > 3) {
             if (FILE* f = std::fopen(argv[3], "wb")) {
                 std::fprintf(f, "P6\n%u %u\n255\n", W, H);
-                for (size_t i = 0; i < frame.albedo.size(); ++i) {
-                    const uint32_t c = frame.hit_id[i] == 0xFFFFFFFFu ? 0x808080u : frame.albedo[i];
+                for (size_t i = 0; i < shaded.size(); ++i) {
+                    const uint32_t c = shaded[i];
                     const unsigned char rgb[3] = {(unsigned char)(c & 0xFF), (unsigned char)((c >> 8) & 0xFF), (unsigned char)((c >> 16) & 0xFF)};
                     std::fwrite(rgb, 1, 3, f);
                 }

@@ -245,6 +245,15 @@ SVX_API int32_t svx_view_set_glass_mode(svx_view* view, int32_t mode /* svx_glas
  * the tree's MIP maps are disabled (raytracing_on_cpu.rs:369). */
 SVX_API int32_t svx_view_set_viewing_distance(svx_view* view, float viewing_distance);
 SVX_API int32_t svx_view_get_viewing_distance(const svx_view* view, float* viewing_distance);
+/* Optional fourth framebuffer plane: the pixel the reference's caller loops write (examples/cpu_render.rs:119-136,
+ * examples/dot_cube.rs:238-256): albedo.rgb scaled by `1 - (normal . light / 2 + 0.5)`, each channel `as u8`, grey
+ * (128,128,128) on a miss, alpha 255; RGBA8 with r in the low byte. light_normal[3] is the examples'
+ * `diffuse_light_normal` (they use normalized(0,-1,1)); null switches the plane off again. While it is on,
+ * svx_view_render / svx_view_render_to_host also fill it (static schedule; the pipelined path does not copy it):
+ * fetch it with svx_view_read_shaded (host, synchronises) or svx_view_shaded_pointer (device). */
+SVX_API int32_t svx_view_set_shading(svx_view* view, const float* light_normal);
+SVX_API int32_t svx_view_read_shaded(svx_view* view, uint32_t* rgba8);
+SVX_API int32_t svx_view_shaded_pointer(const svx_view* view, void** rgba8);
 /* OctreeGPUView::set_resolution / resolution, src/raytracing/bevy/mod.rs:62-88 */
 SVX_API int32_t svx_view_set_resolution(svx_view* view, uint32_t width, uint32_t height);
 SVX_API int32_t svx_view_resolution(const svx_view* view, uint32_t* width, uint32_t* height);

@@ -323,6 +323,18 @@ class OctreeGPUView {
     void set_glass_mode(svx_glass_mode m) { check(svx_view_set_glass_mode(h_, m)); }
     // viewing distance of every pixel's get_by_ray_at_lod (default f32::MAX = get_by_ray; the reference's GPU path
     // feeds viewport.frustum.z); only matters while the tree's MIP maps are enabled
+    // the caller loops' shaded pixel (examples/cpu_render.rs:119-136) as a fourth plane; see svx_view_set_shading
+    void set_shading(V3c<float> diffuse_light_normal) {
+        const float l[3] = {diffuse_light_normal.x, diffuse_light_normal.y, diffuse_light_normal.z};
+        check(svx_view_set_shading(h_, l));
+    }
+    void disable_shading() { check(svx_view_set_shading(h_, nullptr)); }
+    std::vector<uint32_t> read_shaded() {  // RGBA8 of the last rendered frame, r in the low byte
+        const auto r = resolution();
+        std::vector<uint32_t> out(size_t(r[0]) * r[1]);
+        check(svx_view_read_shaded(h_, out.data()));
+        return out;
+    }
     void set_viewing_distance(float d) { check(svx_view_set_viewing_distance(h_, d)); }
     float viewing_distance() const {
         float d = 0.0f;

@@ -2238,4 +2238,20 @@ Ray make_pixel_ray(const Camera& cam, uint32_t w, uint32_t h, uint32_t x, uint32
     return Ray{cam.origin, normalized(glass_point - cam.origin)};
 }
 
+// examples/cpu_render.rs:119-136
+uint32_t shade_pixel(const Hit& hit, V3f l) {
+    auto as_u8 = [](float v) -> uint32_t {  // `f32 as u8`: truncating, saturating, NaN -> 0
+        if (!(v > 0.0f)) return 0u;
+        return v >= 255.0f ? 255u : (uint32_t)v;
+    };
+    if (!hit.hit) return 0xFF808080u;  // Rgb([128, 128, 128])
+    if (hit.entry.kind != EntryKind::Visual && hit.entry.kind != EntryKind::Complex) return 0xFF000000u;
+    // normal.dot(&light) (vector.rs:182-184); both normalized, so the strength is in 0..1
+    const float dot = hit.normal.x * l.x + hit.normal.y * l.y + hit.normal.z * l.z;
+    const float diffuse_light_strength = 1.0f - (dot / 2.0f + 0.5f);
+    const Albedo a = hit.entry.albedo;
+    return as_u8((float)a.r * diffuse_light_strength) | (as_u8((float)a.g * diffuse_light_strength) << 8) |
+           (as_u8((float)a.b * diffuse_light_strength) << 16) | 0xFF000000u;
+}
+
 }  // namespace svxo

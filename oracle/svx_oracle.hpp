@@ -290,5 +290,8 @@ struct Camera {
     float glass_distance;  // viewport_fov (cpu_render.rs:92) or frustum.z (dot_cube.rs:209)
 };
 Ray make_pixel_ray(const Camera& cam, uint32_t w, uint32_t h, uint32_t x, uint32_t y);
+// The pixel the caller loops write: examples/cpu_render.rs:119-136 (same in examples/dot_cube.rs:238-256). RGBA8 packed
+// with r in the low byte, alpha 255. A hit without an albedo makes the reference panic (`albedo().unwrap()`): black here.
+uint32_t shade_pixel(const Hit& hit, V3f diffuse_light_normal);
 
 }  // namespace svxo

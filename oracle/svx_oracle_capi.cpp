@@ -260,9 +260,10 @@ void svxo_make_pixel_ray(const svxo_camera* c, uint32_t w, uint32_t h, uint32_t 
 // {sum node_iters, sum voxel_fetches, sum outer_iters, rays that entered the root cube, would_panic, sum crawl_iters}.
 // Returns wall-clock seconds spent in the pixel loop.
 // counters[6] (7 values in the _lod variant: + MIP probes). viewing_distance as in get_by_ray_at_lod.
-double svxo_render_rows_lod(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
-                            uint32_t threads, float viewing_distance, uint32_t* hit_id, uint8_t* albedo, float* distance,
-                            float* normal, uint64_t* counters7) {
+// shaded (optional, [h*w] RGBA8) = the pixel of the caller loop (cpu_render.rs:119-136) under light_normal[3]
+double svxo_render_rows_shaded(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
+                               uint32_t threads, float viewing_distance, uint32_t* hit_id, uint8_t* albedo, float* distance,
+                               float* normal, uint64_t* counters7, uint32_t* shaded, const float* light_normal) {
     Octree* tree = (Octree*)t;
     Camera cam{{c->origin[0], c->origin[1], c->origin[2]}, {c->direction[0], c->direction[1], c->direction[2]},
                c->glass_width, c->glass_height, c->glass_distance};
@@ -297,6 +298,7 @@ double svxo_render_rows_lod(void* t, const svxo_camera* c, uint32_t w, uint32_t 
                                    hit.impact_point.z - ray.origin.z};
                     distance[i] = hit.hit ? std::sqrt((d.x * d.x) + (d.y * d.y) + (d.z * d.z)) : 0.0f;
                 }
+                if (shaded) shaded[i] = shade_pixel(hit, V3f{light_normal[0], light_normal[1], light_normal[2]});
                 if (normal) {
                     normal[3 * i] = hit.hit ? hit.normal.x : 0.0f;
                     normal[3 * i + 1] = hit.hit ? hit.normal.y : 0.0f;
@@ -325,6 +327,12 @@ double svxo_render_rows_lod(void* t, const svxo_camera* c, uint32_t w, uint32_t 
     if (counters7)
         for (int k = 0; k < 7; ++k) counters7[k] = acc[k];
     return std::chrono::duration<double>(t1 - t0).count();
+}
+double svxo_render_rows_lod(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
+                            uint32_t threads, float viewing_distance, uint32_t* hit_id, uint8_t* albedo, float* distance,
+                            float* normal, uint64_t* counters7) {
+    return svxo_render_rows_shaded(t, c, w, h, rows, n_rows, threads, viewing_distance, hit_id, albedo, distance, normal,
+                                   counters7, nullptr, nullptr);
 }
 double svxo_render_rows(void* t, const svxo_camera* c, uint32_t w, uint32_t h, const uint32_t* rows, uint32_t n_rows,
                         uint32_t threads, uint32_t* hit_id, uint8_t* albedo, float* distance, float* normal,

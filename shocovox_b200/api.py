@@ -145,6 +145,7 @@ EXPORTS = [
     "svx_octree_mip_get_color_similarity_at", "svx_octree_mip_reset", "svx_octree_mip_sample_root", "svx_octree_mip_hash",
     "svx_gpu_host_get_by_rays_at_lod", "svx_view_set_viewing_distance", "svx_view_get_viewing_distance",
     "svx_octree_get_by_ray", "svx_octree_get_by_ray_at_lod", "svx_view_reload",
+    "svx_view_set_shading", "svx_view_read_shaded", "svx_view_shaded_pointer",
     "svx_octree_to_bytes", "svx_bytes_free", "svx_octree_from_bytes", "svx_octree_save", "svx_octree_load",
     "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_last_upload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
@@ -222,6 +223,9 @@ def lib() -> C.CDLL:
     L.svx_octree_get_by_ray.argtypes = [vp, C.POINTER(_Ray), C.POINTER(_Hit)]
     L.svx_octree_get_by_ray_at_lod.argtypes = [vp, C.POINTER(_Ray), f32, C.POINTER(_Hit)]
     L.svx_view_reload.argtypes = [vp]
+    L.svx_view_set_shading.argtypes = [vp, vp]
+    L.svx_view_read_shaded.argtypes = [vp, vp]
+    L.svx_view_shaded_pointer.argtypes = [vp, C.POINTER(vp)]
     L.svx_gpu_host_create.argtypes = [vp, i32, C.POINTER(vp)]
     L.svx_gpu_host_free.argtypes = [vp]
     L.svx_gpu_host_free.restype = None
@@ -667,6 +671,22 @@ class OctreeGPUView:
 
     def set_glass_mode(self, mode: int):
         _check(lib().svx_view_set_glass_mode(self._h, int(mode)))
+
+    def set_shading(self, light_normal=None):
+        """Fourth plane = the shaded pixel of the reference's caller loops (examples/cpu_render.rs:119-136) under the
+        given diffuse light normal (unit vector; the examples use normalized(0,-1,1)). None switches it off."""
+        if light_normal is None:
+            _check(lib().svx_view_set_shading(self._h, None))
+        else:
+            l = np.ascontiguousarray(light_normal, dtype=np.float32)
+            _check(lib().svx_view_set_shading(self._h, l.ctypes.data))
+
+    def read_shaded(self) -> np.ndarray:
+        """The shaded plane of the last rendered frame, [h, w] RGBA8 packed in u32 (r in the low byte)."""
+        w, h = self.resolution()
+        out = np.empty((h, w), dtype=np.uint32)
+        _check(lib().svx_view_read_shaded(self._h, out.ctypes.data))
+        return out
 
     def set_viewing_distance(self, viewing_distance: float):
         """Viewing distance of every pixel's get_by_ray_at_lod (default f32::MAX = get_by_ray; the reference's GPU

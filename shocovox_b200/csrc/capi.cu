@@ -180,6 +180,10 @@ struct svx_view {
     uint32_t* d_hit_id = nullptr;
     uint32_t* d_albedo = nullptr;
     float* d_distance = nullptr;
+    // optional shaded plane (svx_view_set_shading): the pixel of the reference's caller loops, single-buffered
+    uint32_t* d_shaded = nullptr;
+    bool shading = false;
+    float light[3] = {0.0f, 0.0f, 0.0f};
     uint64_t launches = 0;
     // Pipelined read-back (svx_view_render_to_host_async): two framebuffer slots (slot 0 = the planes above, slot 1 =
     // alt_*), kernels on `stream`, device->host copies on `copy_stream`, so frame i's copy overlaps frame i+1's kernel.
@@ -433,6 +437,8 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     }
     f->compact = v->compact;
     f->viewing_distance = v->viewing_distance;
+    f->shaded = v->shading ? v->d_shaded : nullptr;
+    f->lx = v->light[0]; f->ly = v->light[1]; f->lz = v->light[2];
     const bool alt = v->target_slot == 1;
     f->hit_id = v->use_peer ? (uint32_t*)v->peer_base[0] : (alt ? v->alt_hit_id : v->d_hit_id);
     f->albedo = v->use_peer ? (uint32_t*)v->peer_base[1] : (alt ? v->alt_albedo : v->d_albedo);
@@ -446,9 +452,14 @@ int32_t alloc_frame(svx_view* v) {
     cudaFree(v->alt_hit_id);
     cudaFree(v->alt_albedo);
     cudaFree(v->alt_distance);
-    v->d_hit_id = v->d_albedo = v->alt_hit_id = v->alt_albedo = nullptr;
+    cudaFree(v->d_shaded);
+    v->d_hit_id = v->d_albedo = v->alt_hit_id = v->alt_albedo = v->d_shaded = nullptr;
     v->d_distance = v->alt_distance = nullptr;
     const size_t n = (size_t)v->width * v->height;
+    if (v->shading) {
+        CUDA_TRY(cudaMalloc((void**)&v->d_shaded, n * 4));
+        CUDA_TRY(cudaMemsetAsync(v->d_shaded, 0, n * 4, v->stream));
+    }
     CUDA_TRY(cudaMalloc((void**)&v->d_hit_id, n * 4));
     CUDA_TRY(cudaMalloc((void**)&v->d_albedo, n * 4));
     CUDA_TRY(cudaMalloc((void**)&v->d_distance, n * 4));
@@ -465,7 +476,7 @@ int32_t render_locked(svx_view* v) {
     cfg.persistent = v->persistent;
     cfg.tile_counters = v->d_counters;
     f.counter_slot = v->counter_slot;
-    if (v->persistent) v->counter_slot ^= 1u;
+    if (v->persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
     CUDA_TRY(cudaEventRecord(v->ev_start, v->stream));
     CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
     CUDA_TRY(cudaEventRecord(v->ev_stop, v->stream));
@@ -527,7 +538,7 @@ int32_t submit_async_locked(svx_view* v, uint32_t* hit_id, uint32_t* albedo, flo
     cfg.persistent = v->persistent;
     cfg.tile_counters = v->d_counters;
     f.counter_slot = v->counter_slot;
-    if (v->persistent) v->counter_slot ^= 1u;
+    if (v->persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
     CUDA_TRY(cudaEventRecord(v->slot_start[k], v->stream));
     CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
     CUDA_TRY(cudaEventRecord(v->slot_rendered[k], v->stream));
@@ -912,6 +923,7 @@ void svx_view_free(svx_view* v) {
     cudaFree(v->d_hit_id);
     cudaFree(v->d_albedo);
     cudaFree(v->d_distance);
+    cudaFree(v->d_shaded);
     if (v->copy_stream) cudaStreamSynchronize(v->copy_stream);
     cudaFree(v->alt_hit_id);
     cudaFree(v->alt_albedo);
@@ -949,6 +961,40 @@ int32_t svx_view_set_glass_mode(svx_view* v, int32_t mode) {
     if (!v || (mode != SVX_GLASS_AT_FOV && mode != SVX_GLASS_AT_FRUSTUM_Z)) return fail(SVX_E_INVALID_ARGUMENT, "bad mode");
     std::lock_guard<std::mutex> lock(v->mu);
     v->glass_mode = mode;
+    return SVX_OK;
+}
+int32_t svx_view_set_shading(svx_view* v, const float* light_normal) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    const int32_t drained = retire_locked(v, 0);
+    if (drained != SVX_OK) return drained;
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    if (!light_normal) {
+        v->shading = false;
+        return SVX_OK;
+    }
+    std::memcpy(v->light, light_normal, 12);
+    if (!v->d_shaded) {
+        const size_t n = (size_t)v->width * v->height;
+        CUDA_TRY(cudaMalloc((void**)&v->d_shaded, n * 4));
+        CUDA_TRY(cudaMemsetAsync(v->d_shaded, 0, n * 4, v->stream));
+    }
+    v->shading = true;
+    return SVX_OK;
+}
+int32_t svx_view_read_shaded(svx_view* v, uint32_t* rgba8) {
+    if (!v || !rgba8) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    if (!v->shading || !v->d_shaded) return fail(SVX_E_INVALID_ARGUMENT, "shading is not enabled on this view (svx_view_set_shading)");
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    CUDA_TRY(cudaMemcpyAsync(rgba8, v->d_shaded, (size_t)v->width * v->height * 4, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    return SVX_OK;
+}
+int32_t svx_view_shaded_pointer(const svx_view* v, void** rgba8) {
+    if (!v || !rgba8) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *rgba8 = v->shading ? v->d_shaded : nullptr;
     return SVX_OK;
 }
 int32_t svx_view_set_viewing_distance(svx_view* v, float viewing_distance) {

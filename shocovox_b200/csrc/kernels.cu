@@ -54,8 +54,12 @@ __device__ __forceinline__ void glass_vector(const FrameParams& f, uint32_t x, u
 }
 
 // One pixel of the frame: ray generation, rejection tests, get_by_ray, framebuffer stores.
+// `f32 as u8` of the caller loop's colour channels: truncating, saturating, NaN -> 0
+__device__ __forceinline__ uint32_t channel_u8(float v) { return min(__float2uint_rz(v), 255u); }
+
 // (x, lr) = column and shard-local row. LOD: the tree's MIP maps are enabled (traverse.cuh: traverse<LOD>).
-template <bool LOD>
+// SHADE: also write the caller loop's shaded pixel (examples/cpu_render.rs:119-136) to the fourth plane.
+template <bool LOD, bool SHADE>
 __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr) {
     if (x >= f.width || lr >= f.rows_local) return;
     // shard-local row -> image row (interleaved bands of 2^band_shift rows)
@@ -72,8 +76,10 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
         f.hit_id[i] = NIL;
         f.albedo[i] = 0u;
         f.distance[i] = 0.0f;
+        if (SHADE) f.shaded[i] = 0xFF808080u;
         return;
     }
+    uint32_t pixel = 0xFF808080u;  // Rgb([128, 128, 128]) on a miss (cpu_render.rs:134)
     float vx, vy, vz;
     glass_vector(f, x, y, vx, vy, vz);
     const float tree_size = (float)tree.tree_size;
@@ -96,25 +102,48 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
                 if (ci < 0xFFFFu && ci < tree.n_colors) rgba = __ldg(tree.palette + ci);
                 const float wx = res.px - r.ox, wy = res.py - r.oy, wz = res.pz - r.oz;
                 dist = sqrtf((wx * wx) + (wy * wy) + (wz * wz));  // V3c::length, vector.rs:75-77
+                if (SHADE) {
+                    // diffuse_light_strength = 1. - (normal.dot(&light) / 2. + 0.5) ; channel = (c as f32 * strength) as u8
+                    pixel = 0xFF000000u;  // a hit without a colour: the reference panics on albedo().unwrap()
+                    if (ci < 0xFFFFu && ci < tree.n_colors) {
+                        float nx, ny, nz;
+                        impact_normal(res, nx, ny, nz);
+                        const float strength = 1.0f - (((nx * f.lx + ny * f.ly) + nz * f.lz) * 0.5f + 0.5f);
+                        pixel |= channel_u8((float)(rgba & 0xFFu) * strength) | (channel_u8((float)((rgba >> 8) & 0xFFu) * strength) << 8) |
+                                 (channel_u8((float)((rgba >> 16) & 0xFFu) * strength) << 16);
+                    }
+                }
             }
         }
     }
     f.hit_id[i] = hit_id;
     f.albedo[i] = rgba;
     f.distance[i] = dist;
+    if (SHADE) f.shaded[i] = pixel;
 }
 
 // Static schedule: one CTA per 32x8 pixel block of the frame.
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
-    shade_pixel<false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+    shade_pixel<false, false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
 }
 // The same frame over a tree with MIP maps: get_by_ray_at_lod(ray, f.viewing_distance) per pixel
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
-    shade_pixel<true>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+    shade_pixel<true, false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+}
+// The same two with the shaded fourth plane (FrameParams::shaded), static schedule only
+__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_shaded_kernel(const DeviceTree tree, const FrameParams f) {
+    int tx, ty;
+    pixel_of_thread(tx, ty);
+    shade_pixel<false, true>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+}
+__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_shaded_kernel(const DeviceTree tree, const FrameParams f) {
+    int tx, ty;
+    pixel_of_thread(tx, ty);
+    shade_pixel<true, true>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
 }
 
 // Persistent schedule: the grid is sized to the machine (SMs x resident CTAs) and every WARP pulls 8x4 pixel tiles from a
@@ -142,7 +171,7 @@ __device__ __forceinline__ void render_persistent_body(const DeviceTree& tree, c
         for (uint32_t k = 0; k < SVX_TICKET_TILES; ++k) {
             const uint32_t sub = (first & 7u) + k;
             const uint32_t ttx = (bx << 2) + (sub & 3u), tty = (by << 1) + (sub >> 2);
-            if (ttx < tiles_x && tty < tiles_y) shade_pixel<LOD>(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
+            if (ttx < tiles_x && tty < tiles_y) shade_pixel<LOD, false>(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
         }
     }
 }
@@ -318,6 +347,14 @@ __global__ void lut_selftest_kernel(uint64_t* out) {
 
 cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig& cfg, cudaStream_t stream) {
     if (frame.rows_local == 0 || frame.width == 0) return cudaSuccess;
+    if (frame.shaded) {  // the shaded plane exists in the static schedule only
+        dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
+        if (tree.mips_enabled)
+            render_lod_shaded_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+        else
+            render_shaded_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+        return cudaGetLastError();
+    }
     if (cfg.persistent && cfg.tile_counters) {
         // blocks_x * blocks_y * 8 tickets cover the frame in 32x8 blocks; ragged edges are skipped inside the kernel
         const unsigned grid = (unsigned)(cfg.sm_count * SVX_MIN_BLOCKS);

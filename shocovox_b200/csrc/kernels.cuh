@@ -28,6 +28,10 @@ struct FrameParams {
     uint32_t* hit_id;      // [h*w]
     uint32_t* albedo;      // [h*w]
     float* distance;       // [h*w]
+    // optional fourth plane: the pixel the reference's caller loops write (examples/cpu_render.rs:119-136) - albedo
+    // scaled by a diffuse term from the impact normal and this light normal, grey on a miss. nullptr = not produced.
+    uint32_t* shaded;      // [h*w] RGBA8, r in the low byte
+    float lx, ly, lz;      // diffuse_light_normal (cpu_render.rs:97)
 };
 
 // Output record of the batched get_by_ray query

@@ -153,6 +153,8 @@ def lib() -> C.CDLL:
     L.svxo_octree_mip_hash.restype = u64
     L.svxo_render_rows_lod.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, u32, u32, f32, vp, vp, vp, vp, vp]
     L.svxo_render_rows_lod.restype = C.c_double
+    L.svxo_render_rows_shaded.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, u32, u32, f32, vp, vp, vp, vp, vp, vp, vp]
+    L.svxo_render_rows_shaded.restype = C.c_double
     L.svxo_make_pixel_ray.argtypes = [C.POINTER(Camera), u32, u32, u32, u32, f3]
     L.svxo_render.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, vp, vp, vp, vp, vp]
     L.svxo_render.restype = C.c_double
@@ -365,10 +367,11 @@ class OracleOctree:
         return lib().svxo_octree_mip_hash(self._h)
 
     def render(self, cam: Camera, w: int, h: int, threads: int = 0, rows=None, want_normal=False, row_list=None,
-               viewing_distance: float = 3.4028234663852886e38):
+               viewing_distance: float = 3.4028234663852886e38, light_normal=None):
         """Returns dict(hit_id u32[h,w], albedo u8[h,w,4], distance f32[h,w], seconds, counters).
         rows=(r0, r1) renders a contiguous range, row_list an explicit list of image rows (others stay untouched).
-        viewing_distance: get_by_ray_at_lod's parameter (default f32::MAX == get_by_ray)."""
+        viewing_distance: get_by_ray_at_lod's parameter (default f32::MAX == get_by_ray).
+        light_normal: also return "shaded", the RGBA8 pixel of the caller loop (cpu_render.rs:119-136) under that light."""
         r0, r1 = rows if rows is not None else (0, h)
         if row_list is None:
             row_list = np.arange(r0, r1, dtype=np.uint32)
@@ -378,11 +381,15 @@ class OracleOctree:
         dist = np.zeros((h, w), dtype=np.float32)
         normal = np.zeros((h, w, 3), dtype=np.float32) if want_normal else None
         counters = np.zeros(7, dtype=np.uint64)
-        secs = lib().svxo_render_rows_lod(
+        shaded = np.full((h, w), 0xFF808080, dtype=np.uint32) if light_normal is not None else None
+        light = np.asarray(light_normal if light_normal is not None else (0, 0, 0), dtype=np.float32)
+        secs = lib().svxo_render_rows_shaded(
             self._h, C.byref(cam), w, h, row_list.ctypes.data, len(row_list), threads, viewing_distance, hit_id.ctypes.data,
             albedo.ctypes.data, dist.ctypes.data, normal.ctypes.data if want_normal else None, counters.ctypes.data,
+            shaded.ctypes.data if shaded is not None else None, light.ctypes.data,
         )
         return {
+            "shaded": shaded,
             "hit_id": hit_id, "albedo": albedo, "distance": dist, "normal": normal, "seconds": secs, "rows": row_list,
             "node_iters": int(counters[0]), "voxel_fetches": int(counters[1]), "outer_iters": int(counters[2]),
             "rays_in_root": int(counters[3]), "would_panic": int(counters[4]), "crawl_iters": int(counters[5]),

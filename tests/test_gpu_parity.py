@@ -506,3 +506,43 @@ def test_persistent_schedule_renders_the_same_frame():
         rows = (np.arange(res[1]) // 8) % 3 == 1
         for k in ref:
             assert np.array_equal(ref[k][rows], got[k][rows]), (res, k)
+
+
+def test_shaded_plane_is_the_callers_pixel():
+    """The optional fourth plane = the pixel examples/cpu_render.rs:119-136 / dot_cube.rs:238-256 write: albedo scaled by
+    the diffuse term of the impact normal (so the normal is checked on every hit pixel too), grey on a miss."""
+    light = np.array([0.0, -1.0, 1.0], dtype=np.float32)
+    light = (light / np.sqrt((light * light).sum(dtype=np.float32), dtype=np.float32)).astype(np.float32)  # V3c::normalized
+    for scene, cam, res in [(scenes.cpu_render_scene(), scenes.cpu_render_camera(), (150, 150)),
+                            (scenes.dot_cube_scene(128, 32), scenes.dot_cube_camera(128, zoom=True), (333, 211)),
+                            (scenes.colonnade_scene(), scenes.colonnade_camera(), (320, 180))]:
+        tree, otree = both_trees(scene)
+        host = S.OctreeGPUHost(tree)
+        view = host.create_new_view(1, viewport(cam), res)
+        if cam.glass_at_frustum_z:
+            view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+        ora = otree.render(oracle_camera(cam), res[0], res[1], light_normal=light)
+        for persistent in (False, True):  # the shaded plane always comes from the static schedule
+            view.set_schedule(persistent)
+            view.set_shading(light)
+            assert_frames_equal(view.render_to_host(), ora)
+            shaded = view.read_shaded()
+            assert np.array_equal(shaded, ora["shaded"])
+            view.set_shading(None)
+            assert_frames_equal(view.render_to_host(), ora)  # and the plain kernels are back
+            with pytest.raises(S.OctreeError):
+                view.read_shaded()
+        assert (ora["shaded"] != 0xFF808080).sum() > 1000
+        # with MIP maps: the LOD kernel's shaded variant
+        tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
+        otree.switch_albedo_mip_maps(True)
+        view.reload()
+        view.set_viewing_distance(80.0)
+        view.set_shading(light)
+        ora = otree.render(oracle_camera(cam), res[0], res[1], light_normal=light, viewing_distance=80.0)
+        assert_frames_equal(view.render_to_host(), ora)
+        assert np.array_equal(view.read_shaded(), ora["shaded"])
+        view.set_resolution((64, 48))  # the plane follows a resize
+        ora = otree.render(oracle_camera(cam), 64, 48, light_normal=light, viewing_distance=80.0)
+        view.render_to_host()
+        assert np.array_equal(view.read_shaded(), ora["shaded"])
