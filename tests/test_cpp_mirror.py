@@ -61,3 +61,32 @@ def test_cpp_cpu_render_example_matches_python_mirror(tmp_path):
     want = fnv1a(f["distance"].tobytes(), fnv1a(f["albedo"].tobytes(), fnv1a(f["hit_id"].tobytes())))
     assert digest == want
     assert out.exists() and out.stat().st_size > 150 * 150 * 3
+
+
+@pytest.mark.gpu
+def test_cpp_dot_cube_example_matches_python_mirror(tmp_path):
+    """examples/dot_cube.rs through the C++ mirror (tree, viewport, Tab-key CPU render with shading), plain and with MIP
+    maps at viewing distance frustum.z; the written image must equal the Python mirror's shaded plane."""
+    exe = compile_example("dot_cube")
+    light = np.array([0.0, -1.0, 1.0], dtype=np.float32)
+    light = (light / np.sqrt((light * light).sum(dtype=np.float32), dtype=np.float32)).astype(np.float32)
+    cam = scenes.dot_cube_camera(zoom=True)
+    for flag in ([], ["--mips"]):
+        out = tmp_path / "dot.ppm"
+        res = subprocess.run([str(exe), "96", "64", str(out)] + flag, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout + res.stderr
+        tree = S.Octree(256, 32)
+        if flag:
+            tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
+        sc = scenes.dot_cube_scene()
+        tree.insert_batch(sc.xyz, sc.rgba)
+        view = S.OctreeGPUHost(tree).create_new_view(50, S.Viewport(cam.origin, cam.direction, cam.frustum, cam.fov), (96, 64))
+        view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+        if flag:
+            view.set_viewing_distance(200.0)
+        view.set_shading(light)
+        view.render_to_host()
+        want = view.read_shaded()
+        rgb = np.stack([want & 0xFF, (want >> 8) & 0xFF, (want >> 16) & 0xFF], axis=-1).astype(np.uint8)
+        data = out.read_bytes()
+        assert data.endswith(rgb.tobytes()) and len(data) == len(b"P6\n96 64\n255\n") + 96 * 64 * 3
