@@ -883,6 +883,7 @@ int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* 
     if (!h || !vp || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     if (width == 0 || height == 0) return fail(SVX_E_INVALID_ARGUMENT, "zero resolution");
+    if ((uint64_t)width * height > 0x7FFFFFFFull) return fail(SVX_E_INVALID_ARGUMENT, "resolution beyond 2^31 pixels");  // 32-bit pixel indices in the kernels
     CUDA_TRY(cudaSetDevice(h->device));
     svx_view* v = new (std::nothrow) svx_view();
     if (!v) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
@@ -1009,7 +1010,7 @@ int32_t svx_view_get_viewing_distance(const svx_view* v, float* viewing_distance
     return SVX_OK;
 }
 int32_t svx_view_set_resolution(svx_view* v, uint32_t width, uint32_t height) {
-    if (!v || width == 0 || height == 0) return fail(SVX_E_INVALID_ARGUMENT, "bad resolution");
+    if (!v || width == 0 || height == 0 || (uint64_t)width * height > 0x7FFFFFFFull) return fail(SVX_E_INVALID_ARGUMENT, "bad resolution");
     std::lock_guard<std::mutex> lock(v->mu);
     CUDA_TRY(cudaSetDevice(v->host->device));
     const int32_t drained = retire_locked(v, 0);

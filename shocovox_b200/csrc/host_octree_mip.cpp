@@ -367,8 +367,6 @@ void HostOctree::update_mip(size_t key, const BoundsF& nb, uint32_t x, uint32_t 
 // recalculate_mip, mipmap.rs:875-892
 void HostOctree::recalculate_mip(size_t key, const BoundsF& nb) {
     if (!mips_enabled_) return;
-    const float cell = nb.size / (float)dim_;
-    (void)cell;
     for (uint32_t x = 0; x < dim_; ++x)
         for (uint32_t y = 0; y < dim_; ++y)
             for (uint32_t z = 0; z < dim_; ++z) {

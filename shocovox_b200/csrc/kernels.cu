@@ -62,12 +62,15 @@ __device__ __forceinline__ uint32_t channel_u8(float v) { return min(__float2uin
 template <bool LOD, bool SHADE>
 __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr) {
     if (x >= f.width || lr >= f.rows_local) return;
-    // shard-local row -> image row (interleaved bands of 2^band_shift rows)
-    const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
-    const uint32_t row = ((band * f.world + f.rank) << f.band_shift) + within;
+    // shard-local row -> image row (interleaved bands of 2^band_shift rows); one GPU owns every row in order
+    uint32_t row = lr;
+    if (f.world != 1u) {
+        const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
+        row = ((band * f.world + f.rank) << f.band_shift) + within;
+    }
     if (row >= f.height) return;
     const uint32_t y = f.height - 1u - row;  // pixel (x, y) lands in image row h-1-y (cpu_render.rs:106)
-    const size_t i = (size_t)(f.compact ? lr : row) * f.width + x;
+    const uint32_t i = (f.compact ? lr : row) * f.width + x;  // width * height < 2^32 (checked by the host)
 
     uint32_t hit_id = NIL, rgba = 0u;
     float dist = 0.0f;

@@ -128,6 +128,9 @@ __device__ __forceinline__ void ray_setup(RayConst& r) {
 __device__ __forceinline__ int clamp_index(float v, int dim) { return min(max(__float2int_rz(v), 0), dim - 1); }
 // `v.floor() as usize` for the 4x4x4 bitmap position; the reference bounds-panics above 3, we clamp
 __device__ __forceinline__ uint32_t bitmap_coord(float v) { return (uint32_t)min(max(__float2int_rd(v), 0), 3); }
+// The same for a value that just went through rust_clamp(v, 1e-5, 4 - 1e-5) (:430-434): it is in [1e-5, 3.99999] or NaN,
+// so the floor is already 0..3 (cvt maps NaN to 0) and the integer clamp is dead code
+__device__ __forceinline__ uint32_t bitmap_coord_of_clamped(float v) { return (uint32_t)__float2int_rd(v); }
 
 // traverse_brick, raytracing_on_cpu.rs:156-252. Walks the occupancy bit-brick (1 bit per voxel, set = not empty) and
 // returns the flat index (flat_projection, math/mod.rs:35-37) of the first non-empty voxel or -1.
@@ -404,7 +407,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 // LOD: the root's MIP is probed before the occupancy test (:368-386) - leave that to the node loop
                 if (LOD && lod_wants_mip(r, px, py, pz, mip_level, viewing_distance, tree_size)) break;
                 if ((root_hd.x | root_hd.y) != 0u &&
-                    ray_may_hit(root_hd.x, root_hd.y, bitmap_coord(cpx), bitmap_coord(cpy), bitmap_coord(cpz), r.dirbits))
+                    ray_may_hit(root_hd.x, root_hd.y, bitmap_coord_of_clamped(cpx), bitmap_coord_of_clamped(cpy), bitmap_coord_of_clamped(cpz), r.dirbits))
                     break;  // the root survives its test: run the node loop below
                 bool regular = true;
                 if (LOD) {
@@ -482,7 +485,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             float bpy = rust_clamp(((py - by) * 4.0f) * binv, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
             float bpz = rust_clamp(((pz - bz) * 4.0f) * binv, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
             if (kind == NK_UNIFORM || target_octant == OOB_OCTANT || (oc_lo | oc_hi) == 0u ||
-                !ray_may_hit(oc_lo, oc_hi, bitmap_coord(bpx), bitmap_coord(bpy), bitmap_coord(bpz), r.dirbits)) {
+                !ray_may_hit(oc_lo, oc_hi, bitmap_coord_of_clamped(bpx), bitmap_coord_of_clamped(bpy), bitmap_coord_of_clamped(bpz), r.dirbits)) {
                 // POP (:445-474)
                 if (LOD) mip_level += 1.0f;
                 count -= 1u;
