@@ -142,6 +142,7 @@ struct svx_gpu_host {
     void* d_voxels = nullptr;
     void* d_brick_bits = nullptr;
     void* d_palette = nullptr;
+    void* d_ray_lut = nullptr;  // RAY_TO_NODE_OCCUPANCY_BITMASK_LUT as [dir][cell] {lo, hi}, regenerated from the generator logic
     void* d_data_palette = nullptr;  // bit tables "colour shows" / "data carries", input of the occupancy-bit kernel
     void* d_handles = nullptr;       // brick handles of the current upload, input of the occupancy-bit kernel
     size_t data_palette_capacity = 0, handle_capacity = 0;
@@ -767,9 +768,31 @@ int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host
         delete h;
         return fail(g_selftest_status, g_selftest_error);
     }
+    {   // the ray-to-node occupancy table the traversal kernels read (validated against the device closed form above)
+        uint64_t r2n[512], om[8];
+        uint32_t st[216];
+        host_tables(r2n, om, st);
+        std::vector<uint32_t> lut(8 * 64 * 2);
+        for (int cell = 0; cell < 64; ++cell)
+            for (int dir = 0; dir < 8; ++dir) {
+                lut[(dir * 64 + cell) * 2] = (uint32_t)r2n[cell * 8 + dir];
+                lut[(dir * 64 + cell) * 2 + 1] = (uint32_t)(r2n[cell * 8 + dir] >> 32);
+            }
+        e = cudaMalloc(&h->d_ray_lut, lut.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_ray_lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            cudaFree(h->d_ray_lut);
+            cudaStreamDestroy(h->stream);
+            delete h;
+            return cuda_fail(e, "ray LUT upload");
+        }
+        h->dev.ray_lut = (const uint2*)h->d_ray_lut;
+    }
     const int32_t s = upload(h);
     if (s != SVX_OK) {
         free_device_tree(h);
+        cudaFree(h->d_ray_lut);
         cudaStreamDestroy(h->stream);
         delete h;
         return s;
@@ -783,6 +806,7 @@ void svx_gpu_host_free(svx_gpu_host* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_device_tree(h);
+    cudaFree(h->d_ray_lut);
     cudaFree(h->d_rays);
     cudaFree(h->d_hits);
     cudaStreamDestroy(h->stream);

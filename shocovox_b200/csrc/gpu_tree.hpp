@@ -31,6 +31,8 @@
 #include <cstdint>
 #include <vector>
 
+#include <vector_types.h>
+
 #include "host_octree.hpp"
 
 namespace svx {
@@ -47,6 +49,10 @@ struct DeviceTree {
     const uint32_t* voxels;
     const uint32_t* brick_bits;
     const uint32_t* palette;
+    // RAY_TO_NODE_OCCUPANCY_BITMASK_LUT (reference src/spatial/lut.rs, generator :39-89) as [direction octant][cell] uint2
+    // {lo, hi}: 4 KB, identical for every tree, resident in L1. One 8-byte load replaces ~30 integer instructions of the
+    // closed form (traverse.cuh: ray_may_hit), which stays as the start-up cross-check of this very table.
+    const uint2* ray_lut;
     uint32_t n_nodes;
     uint32_t n_bricks;
     uint32_t tree_size;
