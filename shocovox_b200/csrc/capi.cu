@@ -139,6 +139,7 @@ struct svx_gpu_host {
     void* d_node_head = nullptr;
     void* d_node_slot = nullptr;
     void* d_node_mip = nullptr;
+    void* d_node_bounds = nullptr;
     void* d_voxels = nullptr;
     void* d_brick_bits = nullptr;
     void* d_palette = nullptr;
@@ -206,12 +207,13 @@ void free_device_tree(svx_gpu_host* h) {
     cudaFree(h->d_node_head);
     cudaFree(h->d_node_slot);
     cudaFree(h->d_node_mip);
+    cudaFree(h->d_node_bounds);
     cudaFree(h->d_voxels);
     cudaFree(h->d_brick_bits);
     cudaFree(h->d_palette);
     cudaFree(h->d_data_palette);
     cudaFree(h->d_handles);
-    h->d_node_mip = nullptr;
+    h->d_node_mip = h->d_node_bounds = nullptr;
     h->d_node_head = h->d_node_slot = h->d_voxels = h->d_brick_bits = h->d_palette = h->d_data_palette = h->d_handles = nullptr;
     h->node_capacity = h->palette_capacity = h->brick_capacity = h->data_palette_capacity = h->handle_capacity = 0;
     h->uploaded = false;
@@ -261,13 +263,16 @@ int32_t upload(svx_gpu_host* h) {
     CUDA_TRY(grow_device_array(&h->d_node_head, &head_capacity, n_nodes, sizeof(NodeHead), 0, h->stream));
     CUDA_TRY(grow_device_array(&h->d_node_slot, &slot_capacity, head_capacity * 8, 4, 0, h->stream));
     CUDA_TRY(grow_device_array(&h->d_node_mip, &mip_capacity, head_capacity, 4, 0, h->stream));
+    size_t bounds_capacity = h->node_capacity;
+    CUDA_TRY(grow_device_array(&h->d_node_bounds, &bounds_capacity, head_capacity, 16, 0, h->stream));
     h->node_capacity = head_capacity;
     CUDA_TRY(grow_device_array(&h->d_palette, &h->palette_capacity, s.palette.size(), 4, 0, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_node_head, s.node_head.data(), n_nodes * sizeof(NodeHead), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_node_slot, s.node_slot.data(), n_nodes * 8 * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_node_mip, s.node_mip.data(), n_nodes * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_node_bounds, s.node_bounds.data(), n_nodes * 16, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_palette, s.palette.data(), s.palette.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    up.bytes += n_nodes * (sizeof(NodeHead) + 36) + s.palette.size() * 4;
+    up.bytes += n_nodes * (sizeof(NodeHead) + 52) + s.palette.size() * 4;
 
     // bricks: grow keeping what is resident, then copy the runs of handles written since the last upload
     const size_t resident = first ? 0 : std::min(h->brick_capacity, pool);
@@ -294,6 +299,7 @@ int32_t upload(svx_gpu_host* h) {
     d.node_head = (const NodeHead*)h->d_node_head;
     d.node_slot = (const uint32_t*)h->d_node_slot;
     d.node_mip = (const uint32_t*)h->d_node_mip;
+    d.node_bounds = (const float4*)h->d_node_bounds;
     d.mips_enabled = s.mips_enabled ? 1u : 0u;
     d.voxels = (const uint32_t*)h->d_voxels;
     d.brick_bits = (const uint32_t*)h->d_brick_bits;
@@ -343,7 +349,7 @@ int32_t upload(svx_gpu_host* h) {
     h->stats.nodes = n_nodes;
     h->stats.bricks = s.live_bricks;
     h->stats.voxel_bytes = pool * vol * 4;
-    h->stats.total_bytes = n_nodes * (sizeof(NodeHead) + 36) + s.palette.size() * 4 + pool * (vol + words) * 4;
+    h->stats.total_bytes = n_nodes * (sizeof(NodeHead) + 52) + s.palette.size() * 4 + pool * (vol + words) * 4;
     h->stats.tree_size = s.tree_size;
     h->stats.brick_dim = s.brick_dim;
     h->stats.depth = s.depth;

@@ -63,6 +63,21 @@ void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
         }
         s.node_head[i] = h;
     }
+    // bounds of every node, parents before children (breadth-first order): Cube::child_bounds_for, src/spatial/mod.rs:32-39
+    s.node_bounds.assign(order.size() * 4, 0.0f);
+    s.node_bounds[3] = (float)s.tree_size;
+    for (size_t i = 0; i < order.size(); ++i) {
+        if ((s.node_head[i].meta & 3u) != NK_INTERNAL) continue;
+        const float half = s.node_bounds[i * 4 + 3] * 0.5f;
+        for (int o = 0; o < 8; ++o) {
+            const uint32_t c = s.node_slot[i * 8 + o];
+            if (c == NIL) continue;
+            s.node_bounds[c * 4 + 0] = s.node_bounds[i * 4 + 0] + (float)(o & 1) * half;         // octant bit 0: x
+            s.node_bounds[c * 4 + 1] = s.node_bounds[i * 4 + 1] + (float)((o >> 2) & 1) * half;  // bit 2: y
+            s.node_bounds[c * 4 + 2] = s.node_bounds[i * 4 + 2] + (float)((o >> 1) & 1) * half;  // bit 1: z
+            s.node_bounds[c * 4 + 3] = half;
+        }
+    }
     // depth of the deepest node (root = 1): bounds the ring-stack overflow behaviour, reported in stats
     {
         std::vector<uint32_t> d(order.size(), 1);

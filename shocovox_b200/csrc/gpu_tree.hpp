@@ -46,6 +46,7 @@ struct DeviceTree {
     const NodeHead* node_head;
     const uint32_t* node_slot;
     const uint32_t* node_mip;
+    const float4* node_bounds;  // {min x, min y, min z, size} of node i: what a POP restores (exact integers in f32)
     const uint32_t* voxels;
     const uint32_t* brick_bits;
     const uint32_t* palette;
@@ -71,6 +72,7 @@ struct SerialisedNodes {
     std::vector<NodeHead> node_head;
     std::vector<uint32_t> node_slot;
     std::vector<uint32_t> node_mip;
+    std::vector<float> node_bounds;  // 4 per node: min x, y, z, size
     std::vector<uint32_t> palette;
     uint32_t tree_size = 0, brick_dim = 0, brick_shift = 0, bit_words = 0, depth = 0;
     uint64_t live_bricks = 0;  // parted bricks referenced by reachable nodes (MIP bricks included)

@@ -344,7 +344,9 @@ __global__ void lut_selftest_kernel(uint64_t* out) {
         const uint32_t k = i - 520u;
         const uint32_t o = k & 7u, s = k >> 3;  // s = (x+1)*9 + (y+1)*3 + (z+1)
         const int sx = (int)(s / 9u) - 1, sy = (int)((s / 3u) % 3u) - 1, sz = (int)(s % 3u) - 1;
-        out[i] = step_octant(o, sx != 0, sy != 0, sz != 0, sx, sy, sz);
+        // per axis: stepped = the step component is not 0, its sign as a posbit (irrelevant for an axis that did not step)
+        const uint32_t posbits = (sx > 0 ? 1u : 0u) | (sz > 0 ? 2u : 0u) | (sy > 0 ? 4u : 0u);
+        out[i] = step_octant(o, sx != 0, sy != 0, sz != 0, posbits);
     }
 }
 

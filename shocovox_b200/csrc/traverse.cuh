@@ -82,15 +82,15 @@ __device__ __forceinline__ bool ray_may_hit_node(const DeviceTree& t, uint32_t o
 }
 
 // step_octant, spatial/raytracing/mod.rs:68-80 with OCTANT_STEP_RESULT_LUT (generate_octant_step_result_lut,
-// lut.rs:91-137): move one octant along each stepped axis, OOB when leaving the 2x2x2 block. The step arrives as
-// three "this axis stepped" predicates plus the ray's per-axis direction (+1 / -1), which is what
-// `(step as i32).signum()` of dda_step_to_next_sibling's +-1.0 / 0.0 result is.
-__device__ __forceinline__ uint32_t step_octant(uint32_t octant, bool sx, bool sy, bool sz, int isx, int isy, int isz) {
-    const int ix = (int)(octant & 1u) + (sx ? isx : 0);
-    const int iz = (int)((octant >> 1) & 1u) + (sz ? isz : 0);
-    const int iy = (int)((octant >> 2) & 1u) + (sy ? isy : 0);
-    if (((ix | iy | iz) & ~1) != 0) return OOB_OCTANT;
-    return (uint32_t)(ix | (iz << 1) | (iy << 2));
+// lut.rs:91-137): move one octant along each stepped axis, OOB when leaving the 2x2x2 block. The step arrives as three
+// "this axis stepped" predicates; its per-axis sign is the ray's (`signum` of the direction, dda_step_to_next_sibling),
+// given as `posbits` in the octant's own bit layout (bit0 x, bit1 z, bit2 y; set = the ray moves up that axis). A stepped
+// axis leaves the block exactly when the octant already sits on the side the ray moves towards, i.e. when its octant bit
+// equals its posbit; otherwise the bit flips.
+__device__ __forceinline__ uint32_t step_octant(uint32_t octant, bool sx, bool sy, bool sz, uint32_t posbits) {
+    const uint32_t stepped = (sx ? 1u : 0u) | (sz ? 2u : 0u) | (sy ? 4u : 0u);
+    if ((stepped & ~(octant ^ posbits)) != 0u) return OOB_OCTANT;
+    return octant ^ stepped;
 }
 
 struct RayConst {
@@ -99,6 +99,7 @@ struct RayConst {
     float sfx, sfy, sfz;   // get_dda_scale_factors, raytracing_on_cpu.rs:99-112
     bool negx, negy, negz; // sign bit of the direction: f32::signum is -1.0 (also for -0.0), else +1.0
     int isx, isy, isz;     // the same as integers
+    uint32_t posbits;      // !negx | !negz << 1 | !negy << 2: the step signs in the octant bit layout (step_octant)
     uint32_t dirbits;      // hash_direction, spatial/math/mod.rs:22-26
 };
 
@@ -137,6 +138,7 @@ __device__ __forceinline__ void ray_setup(RayConst& r) {
     r.isx = r.negx ? -1 : 1;
     r.isy = r.negy ? -1 : 1;
     r.isz = r.negz ? -1 : 1;
+    r.posbits = (r.negx ? 0u : 1u) | (r.negz ? 0u : 2u) | (r.negy ? 0u : 4u);
     r.dirbits = hash_region(1.0f + r.dx, 1.0f + r.dy, 1.0f + r.dz, 1.0f);
 }
 
@@ -508,20 +510,19 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 s0 = s1; s1 = s2; s2 = s3;
                 if (count != 0u) {
                     cur = s0;
-                    const float twice = bsize * 2.0f;
-                    const float inv_twice = binv * 0.5f;
-                    // parent min = min - min % (2*size) (:452-456). min is a non-negative exact multiple of size, so
-                    // this equals floor(min / 2size) * 2size, all steps exact in f32.
-                    const float pbx = floorf(bx * inv_twice) * twice, pby = floorf(by * inv_twice) * twice,
-                                pbz = floorf(bz * inv_twice) * twice;
-                    const float half = bsize * 0.5f;
-                    const uint32_t from = hash_region((bx + half) - pbx, (by + half) - pby, (bz + half) - pbz, bsize);
+                    // parent bounds: min - min % (2*size), size * 2 (:452-456, :470-471) - exact integer-valued f32, i.e.
+                    // the parent node's own bounds, which the serialiser stored (node_bounds); the entry below the top of
+                    // the stack is always the parent, also after the ring has dropped older entries. The octant the node
+                    // occupies in its parent, hash_region(centre - parent min, size) (:458-463), is "min differs from the
+                    // parent's min" per axis (the difference is 0 or size).
+                    const float4 pb = __ldg(t.node_bounds + cur);
+                    const uint32_t from = (uint32_t)(bx != pb.x) | ((uint32_t)(bz != pb.z) << 1) | ((uint32_t)(by != pb.y) << 2);
                     bool sx, sy, sz;
                     dda_step(r, px, py, pz, bx, by, bz, bsize, sx, sy, sz);
-                    target_octant = step_octant(from, sx, sy, sz, r.isx, r.isy, r.isz);
-                    bsize = twice;
-                    binv = inv_twice;
-                    bx = pbx; by = pby; bz = pbz;
+                    target_octant = step_octant(from, sx, sy, sz, r.posbits);
+                    bsize = pb.w;
+                    binv = binv * 0.5f;
+                    bx = pb.x; by = pb.y; bz = pb.z;
                 }
                 continue;
             }
@@ -548,7 +549,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 for (;;) {
                     bool sx, sy, sz;
                     dda_step(r, px, py, pz, tbx, tby, tbz, hs, sx, sy, sz);
-                    target_octant = step_octant(target_octant, sx, sy, sz, r.isx, r.isy, r.isz);
+                    target_octant = step_octant(target_octant, sx, sy, sz, r.posbits);
                     if (target_octant == OOB_OCTANT) break;
                     tbx = bx + (float)(target_octant & 1u) * hs;
                     tby = by + (float)((target_octant >> 2) & 1u) * hs;
