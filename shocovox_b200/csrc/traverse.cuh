@@ -546,17 +546,16 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 // ADVANCE (:497-544)
                 const float q = 4.0f * binv;  // `step * 4. / size` is +-q or +0 (sic: 4/size cells)
                 const float qx = r.negx ? -q : q, qy = r.negy ? -q : q, qz = r.negz ? -q : q;
+                // child_bounds_for(target_octant) (:506) moves by exactly +-size/2 along every stepped axis (integers: exact)
+                const float hx = r.negx ? -hs : hs, hy = r.negy ? -hs : hs, hz = r.negz ? -hs : hs;
                 for (;;) {
                     bool sx, sy, sz;
                     dda_step(r, px, py, pz, tbx, tby, tbz, hs, sx, sy, sz);
                     target_octant = step_octant(target_octant, sx, sy, sz, r.posbits);
                     if (target_octant == OOB_OCTANT) break;
-                    tbx = bx + (float)(target_octant & 1u) * hs;
-                    tby = by + (float)((target_octant >> 2) & 1u) * hs;
-                    tbz = bz + (float)((target_octant >> 1) & 1u) * hs;
-                    if (sx) bpx = bpx + qx;
-                    if (sy) bpy = bpy + qy;
-                    if (sz) bpz = bpz + qz;
+                    if (sx) { tbx = tbx + hx; bpx = bpx + qx; }
+                    if (sy) { tby = tby + hy; bpy = bpy + qy; }
+                    if (sz) { tbz = tbz + hz; bpz = bpz + qz; }
                     if (kind == NK_INTERNAL) {
                         child = __ldg(t.node_slot + (size_t)cur * 8u + target_octant);
                         if (child != NIL && octant_occupied(oc_lo, oc_hi, target_octant) &&
