@@ -161,9 +161,11 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
                                               uint32_t brick, float bx, float by, float bz, float bsize, float inv_size) {
     const int dim = (int)t.brick_dim;
     const float fdim = (float)dim;
-    const int ix = clamp_index((px - bx) * fdim * inv_size, dim);
-    const int iy = clamp_index((py - by) * fdim * inv_size, dim);
-    const int iz = clamp_index((pz - bz) * fdim * inv_size, dim);
+    // `(p - min) * dim / size` (:167-170): dim and size are powers of two, so the two scalings are one by dim / size (exact)
+    const float to_cells = fdim * inv_size;
+    const int ix = clamp_index((px - bx) * to_cells, dim);
+    const int iy = clamp_index((py - by) * to_cells, dim);
+    const int iz = clamp_index((pz - bz) * to_cells, dim);
     const float unit = bsize * t.inv_brick_dim;  // size / dim, exact: both powers of two
     float cx = bx + (float)ix * unit, cy = by + (float)iy * unit, cz = bz + (float)iz * unit;
     // `current_bounds.min_position += step * brick_unit`: step is +-1.0 or 0.0, so the addend is +-unit or +0
@@ -419,9 +421,10 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             int qx = 0, qy = 0, qz = 0;
             uint32_t remx = 0u, remy = 0u, remz = 0u;
             for (;;) {
-                const float cpx = rust_clamp((px * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
-                const float cpy = rust_clamp((py * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
-                const float cpz = rust_clamp((pz * 4.0f) * t.inv_tree_size, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+                // `p * 4 / size`: two scalings by powers of two = one by their (exact) product, inv_quarter
+                const float cpx = rust_clamp(px * inv_quarter, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+                const float cpy = rust_clamp(py * inv_quarter, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+                const float cpz = rust_clamp(pz * inv_quarter, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
                 // LOD: the root's MIP is probed before the occupancy test (:368-386) - leave that to the node loop
                 if (LOD && lod_wants_mip(r, px, py, pz, mip_level, viewing_distance, tree_size)) break;
                 if ((root_hd.x | root_hd.y) != 0u &&
@@ -491,17 +494,20 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                     if (bkind != BK_EMPTY) {
                         const float hs = bsize * 0.5f;
                         const uint32_t slot = __ldg(t.node_slot + (size_t)cur * 8u + target_octant);
-                        if (probe_brick(t, r, px, py, pz, bkind, slot, bx + (float)(target_octant & 1u) * hs,
-                                        by + (float)((target_octant >> 2) & 1u) * hs,
-                                        bz + (float)((target_octant >> 1) & 1u) * hs, hs, binv * 2.0f, out))
+                        // child_bounds_for: min + offset * size / 2 with offset 0 or 1 per axis = min or min + size/2
+                        if (probe_brick(t, r, px, py, pz, bkind, slot, (target_octant & 1u) ? bx + hs : bx,
+                                        (target_octant & 4u) ? by + hs : by, (target_octant & 2u) ? bz + hs : bz, hs,
+                                        binv * 2.0f, out))
                             return true;
                     }
                 }
             }
             // position inside the node in 4x4x4 bitmap cells (:425-436)
-            float bpx = rust_clamp(((px - bx) * 4.0f) * binv, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
-            float bpy = rust_clamp(((py - by) * 4.0f) * binv, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
-            float bpz = rust_clamp(((pz - bz) * 4.0f) * binv, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+            // `(p - min) * 4 / size`: the two scalings by powers of two are one by their exact product 4 / size
+            const float cells = 4.0f * binv;
+            float bpx = rust_clamp((px - bx) * cells, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+            float bpy = rust_clamp((py - by) * cells, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+            float bpz = rust_clamp((pz - bz) * cells, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
             if (kind == NK_UNIFORM || target_octant == OOB_OCTANT || (oc_lo | oc_hi) == 0u ||
                 !ray_may_hit_node(t, oc_lo, oc_hi, bitmap_coord_of_clamped(bpx), bitmap_coord_of_clamped(bpy), bitmap_coord_of_clamped(bpz), r.dirbits)) {
                 // POP (:445-474)
@@ -527,9 +533,9 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 continue;
             }
             const float hs = bsize * 0.5f;
-            float tbx = bx + (float)(target_octant & 1u) * hs;
-            float tby = by + (float)((target_octant >> 2) & 1u) * hs;
-            float tbz = bz + (float)((target_octant >> 1) & 1u) * hs;
+            float tbx = (target_octant & 1u) ? bx + hs : bx;
+            float tby = (target_octant & 4u) ? by + hs : by;
+            float tbz = (target_octant & 2u) ? bz + hs : bz;
             // NodeChildren::child(): only Internal nodes carry child keys (node.rs:49-54)
             uint32_t child = (kind == NK_INTERNAL) ? __ldg(t.node_slot + (size_t)cur * 8u + target_octant) : NIL;
             if (child != NIL && octant_occupied(oc_lo, oc_hi, target_octant)) {
@@ -544,8 +550,8 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 if (LOD) mip_level -= 1.0f;
             } else {
                 // ADVANCE (:497-544)
-                const float q = 4.0f * binv;  // `step * 4. / size` is +-q or +0 (sic: 4/size cells)
-                const float qx = r.negx ? -q : q, qy = r.negy ? -q : q, qz = r.negz ? -q : q;
+                // `step * 4. / size` is +-cells or +0 (sic: 4/size cells)
+                const float qx = r.negx ? -cells : cells, qy = r.negy ? -cells : cells, qz = r.negz ? -cells : cells;
                 // child_bounds_for(target_octant) (:506) moves by exactly +-size/2 along every stepped axis (integers: exact)
                 const float hx = r.negx ? -hs : hs, hy = r.negy ? -hs : hs, hz = r.negz ? -hs : hs;
                 for (;;) {
