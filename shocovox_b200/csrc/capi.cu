@@ -401,6 +401,7 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     // hull of the 8 projections, hence through their bounding rectangle. Done in double, padded by 2 pixels; any corner
     // not safely in front of the eye (camera inside or beside the cube) disables the cull.
     f->cull_x0 = 0; f->cull_x1 = v->width - 1; f->cull_row0 = 0; f->cull_row1 = v->height - 1;
+    f->prefilter = 1u;  // no rectangle (camera inside / beside the cube): the per-ray approximate miss test earns its keep
     {
         const double S = (double)v->host->dev.tree_size;
         const double o[3] = {origin.x, origin.y, origin.z}, d[3] = {dir.x, dir.y, dir.z};
@@ -427,6 +428,8 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
             by0 = std::min(by0, b); by1 = std::max(by1, b);
         }
         if (ok) {
+            // inside a tight rectangle most rays do enter the cube: the prefilter would cost them more than it saves the others
+            f->prefilter = 0u;
             const double pw = (double)f->pixel_width, ph = (double)f->pixel_height;
             const double x0 = std::floor((ax0 + glass_w / 2.0) / pw) - 2.0, x1 = std::ceil((ax1 + glass_w / 2.0) / pw) + 2.0;
             const double y0 = std::floor((by0 + glass_h / 2.0) / ph) - 2.0, y1 = std::ceil((by1 + glass_h / 2.0) / ph) + 2.0;

@@ -86,9 +86,14 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
     float vx, vy, vz;
     glass_vector(f, x, y, vx, vy, vz);
     const float tree_size = (float)tree.tree_size;
-    // 1) cheap conservative rejection with an approximately normalised direction (see certain_root_miss)
-    const float rl = rsqrtf((vx * vx) + (vy * vy) + (vz * vz));
-    if (!certain_root_miss(f.ox, f.oy, f.oz, vx * rl, vy * rl, vz * rl, tree_size)) {
+    // 1) cheap conservative rejection with an approximately normalised direction (see certain_root_miss); skipped when
+    //    the host could bound the cube on the screen - inside that rectangle nearly every ray enters the cube anyway
+    bool may_hit = true;
+    if (f.prefilter) {
+        const float rl = rsqrtf((vx * vx) + (vy * vy) + (vz * vz));
+        may_hit = !certain_root_miss(f.ox, f.oy, f.oz, vx * rl, vy * rl, vz * rl, tree_size);
+    }
+    if (may_hit) {
         // 2) the reference's exact arithmetic for everything that may hit
         RayConst r;
         const float len = sqrtf((vx * vx) + (vy * vy) + (vz * vz));

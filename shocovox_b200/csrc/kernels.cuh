@@ -22,6 +22,7 @@ struct FrameParams {
     // pixels outside [cull_x0, cull_x1] x [cull_row0, cull_row1] (image coordinates, inclusive) certainly miss the root
     // cube: a conservative screen-space bound of the cube's projection computed on the host (capi.cu)
     uint32_t cull_x0, cull_x1, cull_row0, cull_row1;
+    uint32_t prefilter;    // 1: run the approximate root-miss test per ray (no cull rectangle available for this pose)
     uint32_t counter_slot; // persistent schedule: which of the two ticket counters this launch consumes
     uint32_t compact;      // 1: store shard-local row lr at output row lr (band-major compact buffer for gathers)
     float viewing_distance;  // get_by_ray_at_lod's parameter (raytracing_on_cpu.rs:325); only read when tree.mips_enabled
