@@ -136,10 +136,8 @@ struct svx_gpu_host {
     std::mutex mu;
     svx_gpu_stats stats{};
     DeviceTree dev{};
-    void* d_node_head = nullptr;
-    void* d_node_slot = nullptr;
+    void* d_node_rec = nullptr;  // 64-byte node records: head | 8 slots | bounds
     void* d_node_mip = nullptr;
-    void* d_node_bounds = nullptr;
     void* d_voxels = nullptr;
     void* d_brick_bits = nullptr;
     void* d_palette = nullptr;
@@ -204,17 +202,15 @@ struct svx_view {
 namespace {
 
 void free_device_tree(svx_gpu_host* h) {
-    cudaFree(h->d_node_head);
-    cudaFree(h->d_node_slot);
+    cudaFree(h->d_node_rec);
     cudaFree(h->d_node_mip);
-    cudaFree(h->d_node_bounds);
     cudaFree(h->d_voxels);
     cudaFree(h->d_brick_bits);
     cudaFree(h->d_palette);
     cudaFree(h->d_data_palette);
     cudaFree(h->d_handles);
-    h->d_node_mip = h->d_node_bounds = nullptr;
-    h->d_node_head = h->d_node_slot = h->d_voxels = h->d_brick_bits = h->d_palette = h->d_data_palette = h->d_handles = nullptr;
+    h->d_node_mip = nullptr;
+    h->d_node_rec = h->d_voxels = h->d_brick_bits = h->d_palette = h->d_data_palette = h->d_handles = nullptr;
     h->node_capacity = h->palette_capacity = h->brick_capacity = h->data_palette_capacity = h->handle_capacity = 0;
     h->uploaded = false;
 }
@@ -259,18 +255,22 @@ int32_t upload(svx_gpu_host* h) {
 
     // nodes + palette: small, replaced wholesale
     const size_t n_nodes = s.node_head.size();
-    size_t slot_capacity = h->node_capacity * 8, head_capacity = h->node_capacity, mip_capacity = h->node_capacity;
-    CUDA_TRY(grow_device_array(&h->d_node_head, &head_capacity, n_nodes, sizeof(NodeHead), 0, h->stream));
-    CUDA_TRY(grow_device_array(&h->d_node_slot, &slot_capacity, head_capacity * 8, 4, 0, h->stream));
+    size_t head_capacity = h->node_capacity, mip_capacity = h->node_capacity;
+    CUDA_TRY(grow_device_array(&h->d_node_rec, &head_capacity, n_nodes, 64, 0, h->stream));
     CUDA_TRY(grow_device_array(&h->d_node_mip, &mip_capacity, head_capacity, 4, 0, h->stream));
-    size_t bounds_capacity = h->node_capacity;
-    CUDA_TRY(grow_device_array(&h->d_node_bounds, &bounds_capacity, head_capacity, 16, 0, h->stream));
     h->node_capacity = head_capacity;
     CUDA_TRY(grow_device_array(&h->d_palette, &h->palette_capacity, s.palette.size(), 4, 0, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_node_head, s.node_head.data(), n_nodes * sizeof(NodeHead), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_node_slot, s.node_slot.data(), n_nodes * 8 * 4, cudaMemcpyHostToDevice, h->stream));
+    // interleave head / slots / bounds into the 64-byte records (gpu_tree.hpp: DeviceTree::node_rec)
+    std::vector<uint32_t> records(n_nodes * 16);
+    for (size_t i = 0; i < n_nodes; ++i) {
+        uint32_t* rec = records.data() + i * 16;
+        std::memcpy(rec, &s.node_head[i], 16);
+        std::memcpy(rec + 4, s.node_slot.data() + i * 8, 32);
+        std::memcpy(rec + 12, s.node_bounds.data() + i * 4, 16);
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_node_rec, records.data(), records.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_node_mip, s.node_mip.data(), n_nodes * 4, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_node_bounds, s.node_bounds.data(), n_nodes * 16, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));  // `records` is a local staging buffer
     CUDA_TRY(cudaMemcpyAsync(h->d_palette, s.palette.data(), s.palette.size() * 4, cudaMemcpyHostToDevice, h->stream));
     up.bytes += n_nodes * (sizeof(NodeHead) + 52) + s.palette.size() * 4;
 
@@ -296,10 +296,8 @@ int32_t upload(svx_gpu_host* h) {
         a = b;
     }
     DeviceTree& d = h->dev;
-    d.node_head = (const NodeHead*)h->d_node_head;
-    d.node_slot = (const uint32_t*)h->d_node_slot;
+    d.node_rec = (const uint4*)h->d_node_rec;
     d.node_mip = (const uint32_t*)h->d_node_mip;
-    d.node_bounds = (const float4*)h->d_node_bounds;
     d.mips_enabled = s.mips_enabled ? 1u : 0u;
     d.voxels = (const uint32_t*)h->d_voxels;
     d.brick_bits = (const uint32_t*)h->d_brick_bits;

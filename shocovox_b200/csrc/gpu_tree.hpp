@@ -2,7 +2,8 @@
 //
 // The reference uploads 4-byte granular arrays on demand (metadata / node_children / node_ocbits / voxels,
 // reference src/raytracing/bevy/types.rs:216-279, bevy/cache.rs:413-539). Here the whole tree is resident and a
-// node visit is ONE 16-byte load:
+// node visit is ONE 16-byte load, the three per-node tables below are interleaved into one 64-byte record per node
+// (DeviceTree::node_rec):
 //
 //   node_head[i] : uint4 { ocbits.lo, ocbits.hi, meta, aux }
 //        ocbits = stored_occupied_bits(node)   (reference src/octree/detail.rs:524-544, resolved on the host)
@@ -43,10 +44,11 @@ struct NodeHead {
 
 // POD handed to kernels by value
 struct DeviceTree {
-    const NodeHead* node_head;
-    const uint32_t* node_slot;
+    // One 64-byte record per node, so that everything a node visit touches shares a cache line and one address:
+    //   uint4[0] = node_head   uint4[1..2] = node_slot[0..7]   uint4[3] = node_bounds {min x, min y, min z, size} as f32
+    // (the bounds are what a POP restores; exact integers in f32)
+    const uint4* node_rec;
     const uint32_t* node_mip;
-    const float4* node_bounds;  // {min x, min y, min z, size} of node i: what a POP restores (exact integers in f32)
     const uint32_t* voxels;
     const uint32_t* brick_bits;
     const uint32_t* palette;

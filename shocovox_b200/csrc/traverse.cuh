@@ -93,6 +93,14 @@ __device__ __forceinline__ uint32_t step_octant(uint32_t octant, bool sx, bool s
     return octant ^ stepped;
 }
 
+// The 64-byte record of node i (gpu_tree.hpp): [0] head, [1..2] the eight slots, [3] the bounds
+__device__ __forceinline__ const uint4* node_record(const DeviceTree& t, uint32_t i) { return t.node_rec + (size_t)i * 4u; }
+__device__ __forceinline__ uint4 node_head_of(const uint4* rec) { return __ldg(rec); }
+__device__ __forceinline__ uint32_t node_slot_of(const uint4* rec, uint32_t octant) {
+    return __ldg(reinterpret_cast<const uint32_t*>(rec + 1) + octant);
+}
+__device__ __forceinline__ float4 node_bounds_of(const uint4* rec) { return __ldg(reinterpret_cast<const float4*>(rec + 3)); }
+
 struct RayConst {
     float ox, oy, oz;      // origin
     float dx, dy, dz;      // direction
@@ -406,7 +414,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
     float binv = t.inv_tree_size;  // 1 / bsize, exact (powers of two), tracked alongside bsize
 
     // the root record is needed on every restart; Internal / Nothing roots can crawl (a leaf root probes bricks)
-    const uint4 root_hd = __ldg(reinterpret_cast<const uint4*>(t.node_head));
+    const uint4 root_hd = node_head_of(t.node_rec);
     const bool root_can_crawl = (root_hd.z & 3u) == NK_INTERNAL || (root_hd.z & 3u) == NK_NOTHING;
     const float cwx = r.dx * 0.1f, cwy = r.dy * 0.1f, cwz = r.dz * 0.1f;  // `ray.direction * 0.1` (:551)
     const float quarter = tree_size * 0.25f, inv_quarter = t.inv_tree_size * 4.0f;
@@ -473,7 +481,8 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
         count = min(count + 1u, 4u);
         while (count != 0u) {
             // cur == top of the stack here: one 16-byte load serves occupancy bits and node kind
-            const uint4 hd = __ldg(reinterpret_cast<const uint4*>(t.node_head) + cur);
+            const uint4* rec = node_record(t, cur);
+            const uint4 hd = node_head_of(rec);
             const uint32_t oc_lo = hd.x, oc_hi = hd.y, meta = hd.z;
             const uint32_t kind = meta & 3u;
             if (LOD) {
@@ -493,7 +502,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                     const uint32_t bkind = (meta >> (2u + 2u * target_octant)) & 3u;
                     if (bkind != BK_EMPTY) {
                         const float hs = bsize * 0.5f;
-                        const uint32_t slot = __ldg(t.node_slot + (size_t)cur * 8u + target_octant);
+                        const uint32_t slot = node_slot_of(rec, target_octant);
                         // child_bounds_for: min + offset * size / 2 with offset 0 or 1 per axis = min or min + size/2
                         if (probe_brick(t, r, px, py, pz, bkind, slot, (target_octant & 1u) ? bx + hs : bx,
                                         (target_octant & 4u) ? by + hs : by, (target_octant & 2u) ? bz + hs : bz, hs,
@@ -521,7 +530,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                     // the stack is always the parent, also after the ring has dropped older entries. The octant the node
                     // occupies in its parent, hash_region(centre - parent min, size) (:458-463), is "min differs from the
                     // parent's min" per axis (the difference is 0 or size).
-                    const float4 pb = __ldg(t.node_bounds + cur);
+                    const float4 pb = node_bounds_of(node_record(t, cur));
                     const uint32_t from = (uint32_t)(bx != pb.x) | ((uint32_t)(bz != pb.z) << 1) | ((uint32_t)(by != pb.y) << 2);
                     bool sx, sy, sz;
                     dda_step(r, px, py, pz, bx, by, bz, bsize, sx, sy, sz);
@@ -537,7 +546,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             float tby = (target_octant & 4u) ? by + hs : by;
             float tbz = (target_octant & 2u) ? bz + hs : bz;
             // NodeChildren::child(): only Internal nodes carry child keys (node.rs:49-54)
-            uint32_t child = (kind == NK_INTERNAL) ? __ldg(t.node_slot + (size_t)cur * 8u + target_octant) : NIL;
+            uint32_t child = (kind == NK_INTERNAL) ? node_slot_of(rec, target_octant) : NIL;
             if (child != NIL && octant_occupied(oc_lo, oc_hi, target_octant)) {
                 // PUSH (:484-492)
                 cur = child;
@@ -563,7 +572,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                     if (sy) { tby = tby + hy; bpy = bpy + qy; }
                     if (sz) { tbz = tbz + hz; bpz = bpz + qz; }
                     if (kind == NK_INTERNAL) {
-                        child = __ldg(t.node_slot + (size_t)cur * 8u + target_octant);
+                        child = node_slot_of(rec, target_octant);
                         if (child != NIL && octant_occupied(oc_lo, oc_hi, target_octant) &&
                             ray_may_hit_node(t, oc_lo, oc_hi, bitmap_coord(bpx), bitmap_coord(bpy), bitmap_coord(bpz), r.dirbits))
                             break;
