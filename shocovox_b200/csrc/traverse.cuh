@@ -7,8 +7,10 @@
 // written as multiplications by the exact reciprocal: x / 2^k and x * 2^-k are the same real number, both correctly
 // rounded, hence the same bits. Node bounds are exact small integers in f32.
 //
-// The reference's look-up tables (src/spatial/lut.rs) are replaced by closed forms of their generator logic
-// (lut.rs:12-152): no table loads on the hot path. gpu_selftest.cu checks every table entry against the closed forms.
+// The reference's small look-up tables (src/spatial/lut.rs) are replaced by closed forms of their generator logic
+// (lut.rs:12-152); the 4 KB RAY_TO_NODE_OCCUPANCY_BITMASK_LUT is read as a table (DeviceTree::ray_lut, regenerated on
+// the host, L1-resident): measured, one 8-byte load beats its ~33-instruction closed form. The start-up self-test
+// (capi.cu: run_selftest) checks every table entry against the closed forms.
 // `file:line` citations are relative to the reference checkout.
 #pragma once
 #include <cstdint>
