@@ -76,10 +76,10 @@ __device__ __forceinline__ bool ray_may_hit(uint32_t oc_lo, uint32_t oc_hi, uint
 __device__ __forceinline__ bool ray_may_hit_node(const DeviceTree& t, uint32_t oc_lo, uint32_t oc_hi, uint32_t cx, uint32_t cy,
                                                  uint32_t cz, uint32_t dirbits) {
 #if SVX_RAY_LUT
-    const uint2 m = __ldg(t.ray_lut + ((dirbits << 6) + cx + (cy << 2) + (cz << 4)));
+    const uint2 m = __ldg(t.ray_lut + (((dirbits & 7u) << 6) + cx + (cy << 2) + (cz << 4)));
     return ((oc_lo & m.x) | (oc_hi & m.y)) != 0u;
 #else
-    return ray_may_hit(oc_lo, oc_hi, cx, cy, cz, dirbits);
+    return ray_may_hit(oc_lo, oc_hi, cx, cy, cz, dirbits & 7u);
 #endif
 }
 
@@ -109,8 +109,11 @@ struct RayConst {
     float sfx, sfy, sfz;   // get_dda_scale_factors, raytracing_on_cpu.rs:99-112
     bool negx, negy, negz; // sign bit of the direction: f32::signum is -1.0 (also for -0.0), else +1.0
     int isx, isy, isz;     // the same as integers
-    uint32_t posbits;      // !negx | !negz << 1 | !negy << 2: the step signs in the octant bit layout (step_octant)
-    uint32_t dirbits;      // hash_direction, spatial/math/mod.rs:22-26
+    // bits 0-2: hash_direction (spatial/math/mod.rs:22-26), the ray-to-node table index. bits 3-5: the step signs in the
+    // octant bit layout, !negx | !negz << 1 | !negy << 2 (step_octant). They differ for components in (-2^-25, -0]
+    // (`1 + d >= 1` rounds those to "positive"), so both are kept - in one register, or the compiler rebuilds the second
+    // from the sign predicates at every use.
+    uint32_t dirbits;
 };
 
 // dda_step_to_next_sibling, raytracing_on_cpu.rs:124-152.
@@ -148,8 +151,7 @@ __device__ __forceinline__ void ray_setup(RayConst& r) {
     r.isx = r.negx ? -1 : 1;
     r.isy = r.negy ? -1 : 1;
     r.isz = r.negz ? -1 : 1;
-    r.posbits = (r.negx ? 0u : 1u) | (r.negz ? 0u : 2u) | (r.negy ? 0u : 4u);
-    r.dirbits = hash_region(1.0f + r.dx, 1.0f + r.dy, 1.0f + r.dz, 1.0f);
+    r.dirbits = hash_region(1.0f + r.dx, 1.0f + r.dy, 1.0f + r.dz, 1.0f) | (r.negx ? 0u : 8u) | (r.negz ? 0u : 16u) | (r.negy ? 0u : 32u);
 }
 
 // `(v as i32).clamp(0, dim-1)`: cvt.rzi saturates and maps NaN to 0 like Rust's `as`
@@ -536,7 +538,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                     const uint32_t from = (uint32_t)(bx != pb.x) | ((uint32_t)(bz != pb.z) << 1) | ((uint32_t)(by != pb.y) << 2);
                     bool sx, sy, sz;
                     dda_step(r, px, py, pz, bx, by, bz, bsize, sx, sy, sz);
-                    target_octant = step_octant(from, sx, sy, sz, r.posbits);
+                    target_octant = step_octant(from, sx, sy, sz, r.dirbits >> 3);
                     bsize = pb.w;
                     binv = binv * 0.5f;
                     bx = pb.x; by = pb.y; bz = pb.z;
@@ -568,7 +570,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 for (;;) {
                     bool sx, sy, sz;
                     dda_step(r, px, py, pz, tbx, tby, tbz, hs, sx, sy, sz);
-                    target_octant = step_octant(target_octant, sx, sy, sz, r.posbits);
+                    target_octant = step_octant(target_octant, sx, sy, sz, r.dirbits >> 3);
                     if (target_octant == OOB_OCTANT) break;
                     if (sx) { tbx = tbx + hx; bpx = bpx + qx; }
                     if (sy) { tby = tby + hy; bpy = bpy + qy; }
