@@ -56,7 +56,22 @@ def build(force: bool = False, verbose: bool = False, out: Path = LIB, defines=(
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
     (PKG / ("build_ptxas.log" if out == LIB else out.name + ".ptxas.log")).write_text(res.stderr)
+    check_no_packed_fma(out)
     return out
+
+
+def check_no_packed_fma(lib: Path) -> None:
+    """The kernels use Blackwell's packed f32 add / mul (FADD2 / FMUL2, traverse.cuh). ptxas 12.9 contracts a packed multiply
+    that feeds a packed add into FFMA2 even for `.rn` operands and with --fmad=false - one rounding instead of the reference's
+    two. The sources avoid that pattern; a library that contains FFMA2 anyway is refused rather than shipped."""
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([tool, "-sass", str(lib)], capture_output=True, text=True)
+    if sass.returncode != 0:
+        raise RuntimeError("cuobjdump failed on " + str(lib) + ":\n" + sass.stderr[-2000:])
+    fused = [ln.strip() for ln in sass.stdout.splitlines() if "FFMA2" in ln]
+    if fused:
+        lib.unlink()
+        raise RuntimeError(f"{len(fused)} packed fused multiply-adds in the SASS (results would differ from the reference): {fused[0]}")
 
 
 if __name__ == "__main__":

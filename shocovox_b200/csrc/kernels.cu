@@ -59,7 +59,8 @@ __device__ __forceinline__ uint32_t channel_u8(float v) { return min(__float2uin
 
 // (x, lr) = column and shard-local row. LOD: the tree's MIP maps are enabled (traverse.cuh: traverse<LOD>).
 // SHADE: also write the caller loop's shaded pixel (examples/cpu_render.rs:119-136) to the fourth plane.
-template <bool LOD, bool SHADE>
+// BS >= 0: the tree's brick dimension is the compile-time constant 2^BS (traverse.cuh: brick_dim_of); -1 = read it from the tree.
+template <bool LOD, bool SHADE, int BS = -1>
 __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr) {
     if (x >= f.width || lr >= f.rows_local) return;
     // shard-local row -> image row (interleaved bands of 2^band_shift rows); one GPU owns every row in order
@@ -104,7 +105,7 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
         if (root_entry(r, tree_size, px, py, pz, target_octant)) {
             ray_setup(r);
             TraceResult res;
-            if (traverse<LOD>(tree, r, px, py, pz, target_octant, res, f.viewing_distance)) {
+            if (traverse<LOD, BS>(tree, r, px, py, pz, target_octant, res, f.viewing_distance)) {
                 hit_id = res.palette_value;
                 const uint32_t ci = res.palette_value & 0xFFFFu;
                 if (ci < 0xFFFFu && ci < tree.n_colors) rgba = __ldg(tree.palette + ci);
@@ -142,6 +143,24 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kern
     pixel_of_thread(tx, ty);
     shade_pixel<true, false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
 }
+// The static-schedule kernels specialised for the two brick dimensions the reference's examples use (8: cpu_render.rs:14,
+// 32: dot_cube.rs:56, minecraft.rs:24, sponza.rs:24): brick strides, masks and 1 / dim are immediates in the voxel loop.
+// Same code, same results; launch_render picks the instantiation from DeviceTree::brick_shift.
+#define SVX_RENDER_KERNEL_FOR_BRICK(NAME, LOD, BS)                                                                          \
+    __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) NAME(const DeviceTree tree, const FrameParams f) {      \
+        int tx, ty;                                                                                                         \
+        pixel_of_thread(tx, ty);                                                                                            \
+        shade_pixel<LOD, false, BS>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);                           \
+    }
+SVX_RENDER_KERNEL_FOR_BRICK(render_kernel_brick8, false, 3)
+SVX_RENDER_KERNEL_FOR_BRICK(render_kernel_brick32, false, 5)
+SVX_RENDER_KERNEL_FOR_BRICK(render_lod_kernel_brick8, true, 3)
+SVX_RENDER_KERNEL_FOR_BRICK(render_lod_kernel_brick32, true, 5)
+#undef SVX_RENDER_KERNEL_FOR_BRICK
+#ifndef SVX_BRICK_SPECIALISED
+#define SVX_BRICK_SPECIALISED 1   // 0: always launch the generic kernels (A/B measurements, tools/probe_variants.sh)
+#endif
+
 // The same two with the shaded fourth plane (FrameParams::shaded), static schedule only
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_shaded_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
@@ -375,10 +394,18 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
         return cudaGetLastError();
     }
     dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
-    if (tree.mips_enabled)
-        render_lod_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
-    else
-        render_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+    // the specialised instantiations hard-code everything DeviceTree derives from brick_shift; anything else is generic
+    const bool consistent = tree.brick_dim == (1u << tree.brick_shift) && tree.brick_dim_sq == tree.brick_dim * tree.brick_dim;
+    const uint32_t shift = (SVX_BRICK_SPECIALISED && consistent) ? tree.brick_shift : 0xFFFFFFFFu;
+    if (tree.mips_enabled) {
+        if (shift == 3u) render_lod_kernel_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+        else if (shift == 5u) render_lod_kernel_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+        else render_lod_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+    } else {
+        if (shift == 3u) render_kernel_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+        else if (shift == 5u) render_kernel_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+        else render_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+    }
     return cudaGetLastError();
 }
 

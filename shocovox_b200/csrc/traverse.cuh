@@ -116,6 +116,20 @@ struct RayConst {
     uint32_t dirbits;
 };
 
+// Blackwell's packed f32 arithmetic (sm_100: add / sub / mul.rn.f32x2 -> FADD2 / FMUL2, two IEEE round-to-nearest results per
+// issued instruction) for the x and y components of the DDA's vector operations; z stays scalar. Each half is the same
+// correctly rounded operation as the scalar instruction, so results are unchanged. A packed multiply must never feed a
+// packed add directly: ptxas 12.9 contracts that pair into FFMA2 even for .rn operands and under --fmad=false (one
+// rounding instead of two); sums of products therefore use scalar adds, and the build refuses a library with FFMA2 in it
+// (build.py: check_no_packed_fma).
+#ifndef SVX_PACKED_DDA
+#define SVX_PACKED_DDA 1
+#endif
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); return v; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t v; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b)); return v; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t v; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b)); return v; }
+
 // dda_step_to_next_sibling, raytracing_on_cpu.rs:124-152.
 //   steps_needed = size * signum.max(0.) - signum * (p - min)      (signum = +-1.0)
 // is `size - (p - min)` for signum +1 (x*1 and 1*x are exact) and `0 - (-(p - min))` = p - min for signum -1; the
@@ -123,6 +137,23 @@ struct RayConst {
 // makes its scale factor NaN, hence d NaN, in both forms. Outputs: which axes stepped (min_step == d_axis).
 __device__ __forceinline__ void dda_step(const RayConst& r, float& px, float& py, float& pz, float bx, float by,
                                          float bz, float bsize, bool& sx, bool& sy, bool& sz) {
+#if SVX_PACKED_DDA
+    float dfx, dfy;
+    unpack2(sub2(pack2(px, py), pack2(bx, by)), dfx, dfy);
+    const float dfz = pz - bz;
+    const float nx = r.negx ? dfx : (bsize - dfx);
+    const float ny = r.negy ? dfy : (bsize - dfy);
+    const float nz = r.negz ? dfz : (bsize - dfz);
+    float tx, ty;
+    unpack2(mul2(pack2(nx, ny), pack2(r.sfx, r.sfy)), tx, ty);
+    const float d_x = fabsf(tx), d_y = fabsf(ty), d_z = fabsf(nz * r.sfz);
+    const float m = fminf(fminf(d_x, d_y), d_z);
+    float mx, my;
+    unpack2(mul2(pack2(r.dx, r.dy), pack2(m, m)), mx, my);  // the sums stay scalar: see the note on FFMA2 above
+    px = px + mx;
+    py = py + my;
+    pz = pz + r.dz * m;
+#else
     const float dfx = px - bx, dfy = py - by, dfz = pz - bz;
     const float nx = r.negx ? dfx : (bsize - dfx);
     const float ny = r.negy ? dfy : (bsize - dfy);
@@ -134,9 +165,40 @@ __device__ __forceinline__ void dda_step(const RayConst& r, float& px, float& py
     px = px + r.dx * m;
     py = py + r.dy * m;
     pz = pz + r.dz * m;
+#endif
     sx = (m == d_x);
     sy = (m == d_y);
     sz = (m == d_z);
+}
+
+// The same step against a cube whose size stays fixed over several steps (the sibling walk of ADVANCE): steps_needed in the
+// sign-free form (p - min) - off with off = 0 along a descending axis and `size` along an ascending one, precomputed by
+// the caller. RN(d - size) = -RN(size - d) and d - 0 = d, and only the magnitude is used (`.abs()`, :139-143), so this is
+// dda_step's value for either sign without the per-axis select.
+struct DdaStep {
+    float m, d_x, d_y, d_z;  // min_step and the per-axis distances it was chosen from: axis a stepped iff m == d_a
+};
+__device__ __forceinline__ DdaStep dda_step_off(const RayConst& r, float& px, float& py, float& pz, uint64_t bxy, float bz,
+                                                uint64_t offxy, float offz, bool& sx, bool& sy, bool& sz) {
+    float tx, ty;
+    unpack2(mul2(sub2(sub2(pack2(px, py), bxy), offxy), pack2(r.sfx, r.sfy)), tx, ty);
+    const float d_x = fabsf(tx), d_y = fabsf(ty), d_z = fabsf(((pz - bz) - offz) * r.sfz);
+    const float m = fminf(fminf(d_x, d_y), d_z);
+    float mx, my;
+    unpack2(mul2(pack2(r.dx, r.dy), pack2(m, m)), mx, my);
+    px = px + mx;
+    py = py + my;
+    pz = pz + r.dz * m;
+    sx = (m == d_x);
+    sy = (m == d_y);
+    sz = (m == d_z);
+    return DdaStep{m, d_x, d_y, d_z};
+}
+
+// `if (m == d) { a += da; b += db; }` as one compare and two predicated additions
+__device__ __forceinline__ void add_both_if_equal(float m, float d, float& a, float da, float& b, float db) {
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.rn.f32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
+        : "+f"(a), "+f"(b) : "f"(m), "f"(d), "f"(da), "f"(db));
 }
 
 // Everything get_by_ray derives from the direction before the loop (raytracing_on_cpu.rs:331-332)
@@ -152,6 +214,9 @@ __device__ __forceinline__ void ray_setup(RayConst& r) {
     r.isy = r.negy ? -1 : 1;
     r.isz = r.negz ? -1 : 1;
     r.dirbits = hash_region(1.0f + r.dx, 1.0f + r.dy, 1.0f + r.dz, 1.0f) | (r.negx ? 0u : 8u) | (r.negz ? 0u : 16u) | (r.negy ? 0u : 32u);
+    // opaque from here on: the value lives in its register instead of being rebuilt (three additions, six compares,
+    // selects) inside the node and sibling loops, which is what the compiler otherwise prefers
+    asm volatile("" : "+r"(r.dirbits));
 }
 
 // `(v as i32).clamp(0, dim-1)`: cvt.rzi saturates and maps NaN to 0 like Rust's `as`
@@ -162,6 +227,15 @@ __device__ __forceinline__ uint32_t bitmap_coord(float v) { return (uint32_t)min
 // so the floor is already 0..3 (cvt maps NaN to 0) and the integer clamp is dead code
 __device__ __forceinline__ uint32_t bitmap_coord_of_clamped(float v) { return (uint32_t)__float2int_rd(v); }
 
+// Brick geometry. BS >= 0: the brick dimension 2^BS is a compile-time constant of the kernel instantiation (the host
+// picks the instantiation that matches DeviceTree::brick_shift, kernels.cu: launch_render), so strides, masks and the
+// reciprocal are immediates instead of constant-bank loads and registers inside the voxel loop. BS < 0: read from the tree.
+template <int BS> __device__ __forceinline__ uint32_t brick_shift_of(const DeviceTree& t) { if constexpr (BS >= 0) return (uint32_t)BS; else return t.brick_shift; }
+template <int BS> __device__ __forceinline__ uint32_t brick_dim_of(const DeviceTree& t) { if constexpr (BS >= 0) return 1u << BS; else return t.brick_dim; }
+template <int BS> __device__ __forceinline__ uint32_t brick_dim_sq_of(const DeviceTree& t) { if constexpr (BS >= 0) return 1u << (2 * BS); else return t.brick_dim_sq; }
+template <int BS> __device__ __forceinline__ uint32_t bit_words_of(const DeviceTree& t) { if constexpr (BS >= 0) return ((1u << (3 * BS)) + 31u) / 32u; else return t.bit_words; }
+template <int BS> __device__ __forceinline__ float inv_brick_dim_of(const DeviceTree& t) { if constexpr (BS >= 0) return 1.0f / (float)(1u << BS); else return t.inv_brick_dim; }
+
 // traverse_brick, raytracing_on_cpu.rs:156-252. Walks the occupancy bit-brick (1 bit per voxel, set = not empty) and
 // returns the flat index (flat_projection, math/mod.rs:35-37) of the first non-empty voxel or -1.
 // The loop carries only what a step needs: the flat index (it addresses the bit and, on a hit, gives the voxel index
@@ -169,21 +243,22 @@ __device__ __forceinline__ uint32_t bitmap_coord_of_clamped(float v) { return (u
 // on the integer index (:193-203) is done on that corner instead: corners are exact multiples of `unit` (integers),
 // every step moves a stepped axis by exactly one cell, so the walk has left the brick exactly when a corner equals
 // the first corner outside (min - unit going down, min + size going up).
+template <int BS>
 __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayConst& r, float& px, float& py, float& pz,
                                               uint32_t brick, float bx, float by, float bz, float bsize, float inv_size) {
-    const int dim = (int)t.brick_dim;
+    const int dim = (int)brick_dim_of<BS>(t);
     const float fdim = (float)dim;
     // `(p - min) * dim / size` (:167-170): dim and size are powers of two, so the two scalings are one by dim / size (exact)
     const float to_cells = fdim * inv_size;
     const int ix = clamp_index((px - bx) * to_cells, dim);
     const int iy = clamp_index((py - by) * to_cells, dim);
     const int iz = clamp_index((pz - bz) * to_cells, dim);
-    const float unit = bsize * t.inv_brick_dim;  // size / dim, exact: both powers of two
+    const float unit = bsize * inv_brick_dim_of<BS>(t);  // size / dim, exact: both powers of two
     float cx = bx + (float)ix * unit, cy = by + (float)iy * unit, cz = bz + (float)iz * unit;
     // `current_bounds.min_position += step * brick_unit`: step is +-1.0 or 0.0, so the addend is +-unit or +0
     const float ux = r.negx ? -unit : unit, uy = r.negy ? -unit : unit, uz = r.negz ? -unit : unit;
     const float ex = r.negx ? bx - unit : bx + bsize, ey = r.negy ? by - unit : by + bsize, ez = r.negz ? bz - unit : bz + bsize;
-    const uint32_t sh = t.brick_shift;
+    const uint32_t sh = brick_shift_of<BS>(t);
     // flat_projection(ix, iy, iz) kept incrementally, like the reference's current_flat_index (:205-207) - but in
     // MIRRORED coordinates: along an axis the ray descends, the loop counts j = dim-1 - i = i ^ (dim-1) instead of i, so
     // every step adds +1 / +dim / +dim^2 (uniform values, no per-ray signed strides to keep or rebuild in the loop) and
@@ -192,9 +267,53 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     const uint32_t dmask = (uint32_t)dim - 1u;
     const uint32_t flip = (r.negx ? dmask : 0u) | (r.negy ? dmask << sh : 0u) | (r.negz ? dmask << (2 * sh) : 0u);
     uint32_t mirrored = ((uint32_t)ix + ((uint32_t)iy << sh) + ((uint32_t)iz << (2 * sh))) ^ flip;
-    const uint32_t base = brick * t.bit_words;  // word offset of this brick's bits; all bit words fit 32 bits (gpu_tree.cpp)
-    uint32_t word_index = 0xFFFFFFFFu;
+    const uint32_t base = brick * bit_words_of<BS>(t);  // word offset of this brick's bits; all bit words fit 32 bits (gpu_tree.cpp)
     uint32_t word = 0u;
+#if SVX_PACKED_DDA
+    // dda_step with the x and y components packed. `steps_needed` in the sign-free form (p - corner) - off, off = 0 along a
+    // descending axis and `unit` along an ascending one: RN(d - unit) = -RN(unit - d) and d - 0 = d, and only the magnitude
+    // is used (the `.abs()` of :139-143), so this is dda_step's value for either sign without a per-axis select.
+    const uint64_t offxy = pack2(r.negx ? 0.0f : unit, r.negy ? 0.0f : unit), sfxy = pack2(r.sfx, r.sfy), dxy = pack2(r.dx, r.dy);
+    float offz = r.negz ? 0.0f : unit;
+    asm volatile("" : "+f"(offz));  // a loop constant in a register (otherwise rebuilt from `unit` and the sign on every step)
+    uint64_t pxy = pack2(px, py);
+    // The loop counts the COMPLEMENT of the flat index (mirrored ^ ~flip): the voxel's bit is then moved to the sign position
+    // by a left shift of (~flat & 31) = 31 - (flat & 31), a one-instruction test; word indices are compared complemented.
+    uint32_t nflip = ~flip;
+    asm volatile("" : "+r"(nflip));  // keeps the complement a loop constant (the compiler would rather complement on every step)
+    uint32_t nword_index = 0u;  // no complemented word index of a brick is 0 (their upper bits are set)
+    uint32_t nflat;
+    for (;;) {
+        nflat = mirrored ^ nflip;
+        if ((nflat >> 5) != nword_index) {
+            nword_index = nflat >> 5;
+            word = __ldg(t.brick_bits + (base + (~nflat >> 5)));
+        }
+        if ((int)(word << (nflat & 31u)) < 0) break;
+        float tx, ty;
+        unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
+        const float tz = ((pz - cz) - offz) * r.sfz;
+        const float d_x = fabsf(tx), d_y = fabsf(ty), d_z = fabsf(tz);
+        const float m = fminf(fminf(d_x, d_y), d_z);
+        float mx, my, qx, qy;
+        unpack2(mul2(dxy, pack2(m, m)), mx, my);
+        unpack2(pxy, qx, qy);
+        pxy = pack2(qx + mx, qy + my);
+        pz = pz + r.dz * m;
+        // `if (m == d) { mirrored += stride; corner += u; }` per axis, as predicated instructions
+        asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
+            : "+r"(mirrored), "+f"(cx) : "f"(m), "f"(d_x), "r"(1u), "f"(ux));
+        asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
+            : "+r"(mirrored), "+f"(cy) : "f"(m), "f"(d_y), "r"(brick_dim_of<BS>(t)), "f"(uy));
+        asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
+            : "+r"(mirrored), "+f"(cz) : "f"(m), "f"(d_z), "r"(brick_dim_sq_of<BS>(t)), "f"(uz));
+        if (cx == ex || cy == ey || cz == ez) break;
+    }
+    unpack2(pxy, px, py);
+    // the walk ended on a set bit (corners strictly inside the brick) or by leaving it (a corner on the first plane outside)
+    return (cx == ex || cy == ey || cz == ez) ? -1 : (int)~nflat;
+#else
+    uint32_t word_index = 0xFFFFFFFFu;
     for (;;) {
         const uint32_t flat = mirrored ^ flip;
         if ((flat >> 5) != word_index) {
@@ -205,13 +324,15 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
         bool sx, sy, sz;
         dda_step(r, px, py, pz, cx, cy, cz, unit, sx, sy, sz);
         if (sx) { mirrored += 1u; cx = cx + ux; }
-        if (sy) { mirrored += t.brick_dim; cy = cy + uy; }
-        if (sz) { mirrored += t.brick_dim_sq; cz = cz + uz; }
+        if (sy) { mirrored += brick_dim_of<BS>(t); cy = cy + uy; }
+        if (sz) { mirrored += brick_dim_sq_of<BS>(t); cz = cz + uz; }
         if (cx == ex || cy == ey || cz == ez) return -1;
     }
+#endif
 }
 
 // probe_brick, raytracing_on_cpu.rs:256-312. kind: 0 empty, 1 parted, 2 solid
+template <int BS>
 __device__ __forceinline__ bool probe_brick(const DeviceTree& t, const RayConst& r, float& px, float& py, float& pz,
                                             uint32_t kind, uint32_t slot, float bx, float by, float bz, float bsize,
                                             float inv_size, TraceResult& out) {
@@ -222,14 +343,14 @@ __device__ __forceinline__ bool probe_brick(const DeviceTree& t, const RayConst&
         out.bx = bx; out.by = by; out.bz = bz; out.bsize = bsize;
         return true;
     }
-    const int flat = traverse_brick(t, r, px, py, pz, slot, bx, by, bz, bsize, inv_size);
+    const int flat = traverse_brick<BS>(t, r, px, py, pz, slot, bx, by, bz, bsize, inv_size);
     if (flat < 0) return false;
-    const uint32_t dmask = t.brick_dim - 1u, sh = t.brick_shift;
+    const uint32_t dmask = brick_dim_of<BS>(t) - 1u, sh = brick_shift_of<BS>(t);
     const int hx = (int)((uint32_t)flat & dmask), hy = (int)(((uint32_t)flat >> sh) & dmask), hz = (int)((uint32_t)flat >> (2u * sh));
-    out.palette_value = __ldg(t.voxels + ((size_t)slot << (3 * t.brick_shift)) + flat);
+    out.palette_value = __ldg(t.voxels + ((size_t)slot << (3u * sh)) + flat);
     out.px = px; out.py = py; out.pz = pz;
     // hit_bounds: min + idx * size / dim (the division is by a power of two), size / dim
-    const float inv_dim = t.inv_brick_dim;
+    const float inv_dim = inv_brick_dim_of<BS>(t);
     out.bx = bx + ((float)hx * bsize) * inv_dim;
     out.by = by + ((float)hy * bsize) * inv_dim;
     out.bz = bz + ((float)hz * bsize) * inv_dim;
@@ -402,12 +523,12 @@ __device__ __forceinline__ bool lod_quiescent(const RayConst& r, float px, float
 //                4-entry ring stack has dropped entries. Every failing root iteration of the crawl also raises
 //                mip_level and re-evaluates the LOD test, so the crawl fast-forward runs only once lod_quiescent()
 //                proves the test false for the rest of the crawl (then n nudges are also n increments of mip_level).
-template <bool LOD>
+template <bool LOD, int BS = -1>
 __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r, float px, float py, float pz,
                                          uint32_t target_octant, TraceResult& out, float viewing_distance = 0.0f) {
     const float tree_size = (float)t.tree_size;
     // log2 of a power of two: (size / dim) = 2^k exactly, k read from the exponent field
-    float mip_level = LOD ? (float)((int)((__float_as_uint(tree_size * t.inv_brick_dim) >> 23) & 0xFFu) - 127) : 0.0f;
+    float mip_level = LOD ? (float)((int)((__float_as_uint(tree_size * inv_brick_dim_of<BS>(t)) >> 23) & 0xFFu) - 127) : 0.0f;
     // NodeStack<u32, 4>, raytracing_on_cpu.rs:20-82: a ring buffer that overwrites its oldest entry.
     // Held as a 4-deep shift register (s0 = newest): pushing drops the oldest entry, popping removes the newest,
     // which is exactly what the ring buffer does; entries beyond `count` are never read.
@@ -495,20 +616,20 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 if (lod_wants_mip(r, px, py, pz, mip_level, viewing_distance, tree_size)) {
                     const uint32_t mkind = (meta >> 18) & 3u;
                     if (mkind != BK_EMPTY &&
-                        probe_brick(t, r, px, py, pz, mkind, __ldg(t.node_mip + cur), bx, by, bz, bsize, binv, out))
+                        probe_brick<BS>(t, r, px, py, pz, mkind, __ldg(t.node_mip + cur), bx, by, bz, bsize, binv, out))
                         return true;
                 }
             }
             if (target_octant != OOB_OCTANT) {
                 if (kind == NK_UNIFORM) {
-                    if (probe_brick(t, r, px, py, pz, (meta >> 2) & 3u, hd.w, bx, by, bz, bsize, binv, out)) return true;
+                    if (probe_brick<BS>(t, r, px, py, pz, (meta >> 2) & 3u, hd.w, bx, by, bz, bsize, binv, out)) return true;
                 } else if (kind == NK_LEAF) {
                     const uint32_t bkind = (meta >> (2u + 2u * target_octant)) & 3u;
                     if (bkind != BK_EMPTY) {
                         const float hs = bsize * 0.5f;
                         const uint32_t slot = node_slot_of(rec, target_octant);
                         // child_bounds_for: min + offset * size / 2 with offset 0 or 1 per axis = min or min + size/2
-                        if (probe_brick(t, r, px, py, pz, bkind, slot, (target_octant & 1u) ? bx + hs : bx,
+                        if (probe_brick<BS>(t, r, px, py, pz, bkind, slot, (target_octant & 1u) ? bx + hs : bx,
                                         (target_octant & 4u) ? by + hs : by, (target_octant & 2u) ? bz + hs : bz, hs,
                                         binv * 2.0f, out))
                             return true;
@@ -567,14 +688,31 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 const float qx = r.negx ? -cells : cells, qy = r.negy ? -cells : cells, qz = r.negz ? -cells : cells;
                 // child_bounds_for(target_octant) (:506) moves by exactly +-size/2 along every stepped axis (integers: exact)
                 const float hx = r.negx ? -hs : hs, hy = r.negy ? -hs : hs, hz = r.negz ? -hs : hs;
+#if SVX_PACKED_DDA
+                uint64_t offxy = pack2(r.negx ? 0.0f : hs, r.negy ? 0.0f : hs);
+                float offz = r.negz ? 0.0f : hs;
+                asm volatile("" : "+l"(offxy), "+f"(offz));  // loop constants in registers, not rebuilt per step
+                uint64_t tbxy = pack2(tbx, tby);  // carried as a pair: the sibling's bounds are not needed after the walk
+#endif
                 for (;;) {
                     bool sx, sy, sz;
+#if SVX_PACKED_DDA
+                    const DdaStep st = dda_step_off(r, px, py, pz, tbxy, tbz, offxy, offz, sx, sy, sz);
+                    target_octant = step_octant(target_octant, sx, sy, sz, r.dirbits >> 3);
+                    if (target_octant == OOB_OCTANT) break;
+                    unpack2(tbxy, tbx, tby);
+                    add_both_if_equal(st.m, st.d_x, tbx, hx, bpx, qx);
+                    add_both_if_equal(st.m, st.d_y, tby, hy, bpy, qy);
+                    add_both_if_equal(st.m, st.d_z, tbz, hz, bpz, qz);
+                    tbxy = pack2(tbx, tby);
+#else
                     dda_step(r, px, py, pz, tbx, tby, tbz, hs, sx, sy, sz);
                     target_octant = step_octant(target_octant, sx, sy, sz, r.dirbits >> 3);
                     if (target_octant == OOB_OCTANT) break;
                     if (sx) { tbx = tbx + hx; bpx = bpx + qx; }
                     if (sy) { tby = tby + hy; bpy = bpy + qy; }
                     if (sz) { tbz = tbz + hz; bpz = bpz + qz; }
+#endif
                     if (kind == NK_INTERNAL) {
                         child = node_slot_of(rec, target_octant);
                         if (child != NIL && octant_occupied(oc_lo, oc_hi, target_octant) &&

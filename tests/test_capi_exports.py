@@ -72,3 +72,18 @@ def test_product_does_not_reference_the_oracle():
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.hpp")) + list(pkg.rglob("*.cuh")):
         text = p.read_text()
         assert "svxo_" not in text and "oracle_lib" not in text and "libsvx_oracle" not in text, p
+
+
+def test_built_library_has_no_packed_fused_multiply_add():
+    """The DDA uses packed f32 add / mul (FADD2 / FMUL2); a packed FMA (FFMA2) would round once where the reference
+    (raytracing_on_cpu.rs:124-152, Rust never contracts) rounds twice. build.py refuses such a library; check the one in the tree."""
+    import shutil
+    import subprocess
+
+    from shocovox_b200 import build
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([tool, "-sass", str(build.LIB)], capture_output=True, text=True, check=True).stdout
+    assert "FADD2" in sass and "FMUL2" in sass, "the packed f32 path is not in the built kernels"
+    assert "FFMA2" not in sass
+    build.check_no_packed_fma(build.LIB)
