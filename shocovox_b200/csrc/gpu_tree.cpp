@@ -55,7 +55,7 @@ void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
             }
         } else if (n.kind == NK_UNIFORM) {
             h.meta |= (uint32_t)n.brick[0].kind << 2;
-            h.aux = slot_of(n.brick[0]);
+            slot[0] = slot_of(n.brick[0]);
         }
         if (s.mips_enabled) {
             h.meta |= (uint32_t)n.mip.kind << 18;
@@ -63,7 +63,8 @@ void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
         }
         s.node_head[i] = h;
     }
-    // bounds of every node, parents before children (breadth-first order): Cube::child_bounds_for, src/spatial/mod.rs:32-39
+    // bounds and parent of every node, parents before children (breadth-first order): Cube::child_bounds_for,
+    // src/spatial/mod.rs:32-39. Every node but the root has exactly one parent (from_bytes rejects shared children).
     s.node_bounds.assign(order.size() * 4, 0.0f);
     s.node_bounds[3] = (float)s.tree_size;
     for (size_t i = 0; i < order.size(); ++i) {
@@ -72,6 +73,7 @@ void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
         for (int o = 0; o < 8; ++o) {
             const uint32_t c = s.node_slot[i * 8 + o];
             if (c == NIL) continue;
+            s.node_head[c].aux = (uint32_t)i;
             s.node_bounds[c * 4 + 0] = s.node_bounds[i * 4 + 0] + (float)(o & 1) * half;         // octant bit 0: x
             s.node_bounds[c * 4 + 1] = s.node_bounds[i * 4 + 1] + (float)((o >> 2) & 1) * half;  // bit 2: y
             s.node_bounds[c * 4 + 2] = s.node_bounds[i * 4 + 2] + (float)((o >> 1) & 1) * half;  // bit 1: z

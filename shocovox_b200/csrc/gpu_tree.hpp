@@ -10,9 +10,12 @@
 //        meta   = kind[1:0] | brick kind of octant o at [2+2o+1 : 2+2o]   (0 empty, 1 parted, 2 solid)
 //                 kind: 0 Nothing, 1 Internal, 2 Leaf, 3 UniformLeaf (its brick kind sits in octant 0's field)
 //                 bits [19:18]: kind of the node's MIP brick (reference node_mips[key], src/octree/types.rs:186)
-//        aux    = UniformLeaf: the brick slot (below); otherwise NIL
+//        aux    = index of the parent node (NIL for the root). The reference keeps the path in a 4-entry ring stack
+//                 (NodeStack, raytracing_on_cpu.rs:20-82); its entries are always the current node's nearest ancestors, so
+//                 a POP needs the parent index and a count of valid entries, not the entries themselves
 //   node_slot[8i + o] : u32   Internal: child node index or NIL (validity resolved on the host)
 //                             Leaf: brick slot of octant o
+//                             UniformLeaf: slot 0 = the brick slot of its one brick
 //        brick slot = palette value (Solid) | brick handle (Parted) | NIL (Empty)
 //   node_mip[i] : u32   brick slot of the node's MIP brick; read only by the level-of-detail branch of
 //                       get_by_ray_at_lod (raytracing_on_cpu.rs:368-386), and only present in the layout's hot loop

@@ -529,10 +529,11 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
     const float tree_size = (float)t.tree_size;
     // log2 of a power of two: (size / dim) = 2^k exactly, k read from the exponent field
     float mip_level = LOD ? (float)((int)((__float_as_uint(tree_size * inv_brick_dim_of<BS>(t)) >> 23) & 0xFFu) - 127) : 0.0f;
-    // NodeStack<u32, 4>, raytracing_on_cpu.rs:20-82: a ring buffer that overwrites its oldest entry.
-    // Held as a 4-deep shift register (s0 = newest): pushing drops the oldest entry, popping removes the newest,
-    // which is exactly what the ring buffer does; entries beyond `count` are never read.
-    uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
+    // NodeStack<u32, 4>, raytracing_on_cpu.rs:20-82: a ring buffer that overwrites its oldest entry. Pushes are always a
+    // child of the current top, so the valid entries are the current node and its nearest ancestors, at most four; what
+    // the ring loses when it wraps is only HOW MANY of them can still be popped. The kernel keeps that count and takes
+    // the entry below the top from the node record (NodeHead::aux = parent index) - the same nodes in the same order,
+    // including the early "stack empty" restarts from the root in trees deeper than four levels.
     uint32_t count = 0;
     uint32_t cur = 0;
     float bx = 0.0f, by = 0.0f, bz = 0.0f, bsize = tree_size;
@@ -602,8 +603,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
         bx = by = bz = 0.0f;
         bsize = tree_size;
         binv = t.inv_tree_size;
-        s3 = s2; s2 = s1; s1 = s0; s0 = 0u;
-        count = min(count + 1u, 4u);
+        count = min(count + 1u, 4u);  // node_stack.push(root)
         while (count != 0u) {
             // cur == top of the stack here: one 16-byte load serves occupancy bits and node kind
             const uint4* rec = node_record(t, cur);
@@ -622,7 +622,8 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             }
             if (target_octant != OOB_OCTANT) {
                 if (kind == NK_UNIFORM) {
-                    if (probe_brick<BS>(t, r, px, py, pz, (meta >> 2) & 3u, hd.w, bx, by, bz, bsize, binv, out)) return true;
+                    const uint32_t ubk = (meta >> 2) & 3u;
+                    if (ubk != BK_EMPTY && probe_brick<BS>(t, r, px, py, pz, ubk, node_slot_of(rec, 0u), bx, by, bz, bsize, binv, out)) return true;
                 } else if (kind == NK_LEAF) {
                     const uint32_t bkind = (meta >> (2u + 2u * target_octant)) & 3u;
                     if (bkind != BK_EMPTY) {
@@ -647,9 +648,8 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 // POP (:445-474)
                 if (LOD) mip_level += 1.0f;
                 count -= 1u;
-                s0 = s1; s1 = s2; s2 = s3;
                 if (count != 0u) {
-                    cur = s0;
+                    cur = hd.w;  // the entry below the top of the stack: this node's parent
                     // parent bounds: min - min % (2*size), size * 2 (:452-456, :470-471) - exact integer-valued f32, i.e.
                     // the parent node's own bounds, which the serialiser stored (node_bounds); the entry below the top of
                     // the stack is always the parent, also after the ring has dropped older entries. The octant the node
@@ -679,8 +679,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 bsize = hs;
                 binv = binv * 2.0f;
                 target_octant = hash_region(px - bx, py - by, pz - bz, hs * 0.5f);
-                s3 = s2; s2 = s1; s1 = s0; s0 = child;
-                count = min(count + 1u, 4u);
+                count = min(count + 1u, 4u);  // node_stack.push(child)
                 if (LOD) mip_level -= 1.0f;
             } else {
                 // ADVANCE (:497-544)
