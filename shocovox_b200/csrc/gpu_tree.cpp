@@ -74,6 +74,7 @@ void serialise_nodes(const HostOctree& tree, SerialisedNodes* out) {
             const uint32_t c = s.node_slot[i * 8 + o];
             if (c == NIL) continue;
             s.node_head[c].aux = (uint32_t)i;
+            s.node_head[c].meta |= (uint32_t)o << 20;  // the octant this node occupies in its parent
             s.node_bounds[c * 4 + 0] = s.node_bounds[i * 4 + 0] + (float)(o & 1) * half;         // octant bit 0: x
             s.node_bounds[c * 4 + 1] = s.node_bounds[i * 4 + 1] + (float)((o >> 2) & 1) * half;  // bit 2: y
             s.node_bounds[c * 4 + 2] = s.node_bounds[i * 4 + 2] + (float)((o >> 1) & 1) * half;  // bit 1: z

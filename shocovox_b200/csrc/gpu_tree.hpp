@@ -10,6 +10,8 @@
 //        meta   = kind[1:0] | brick kind of octant o at [2+2o+1 : 2+2o]   (0 empty, 1 parted, 2 solid)
 //                 kind: 0 Nothing, 1 Internal, 2 Leaf, 3 UniformLeaf (its brick kind sits in octant 0's field)
 //                 bits [19:18]: kind of the node's MIP brick (reference node_mips[key], src/octree/types.rs:186)
+//                 bits [22:20]: the octant this node occupies in its parent (what a POP derives from the two bounds,
+//                               raytracing_on_cpu.rs:458-463)
 //        aux    = index of the parent node (NIL for the root). The reference keeps the path in a 4-entry ring stack
 //                 (NodeStack, raytracing_on_cpu.rs:20-82); its entries are always the current node's nearest ancestors, so
 //                 a POP needs the parent index and a count of valid entries, not the entries themselves

@@ -201,6 +201,12 @@ __device__ __forceinline__ void add_both_if_equal(float m, float d, float& a, fl
         : "+f"(a), "+f"(b) : "f"(m), "f"(d), "f"(da), "f"(db));
 }
 
+// `negative ? -v : v` for v >= +0 as one logic instruction: v with the sign bit of `direction` (f32::signum's sign, also for
+// -0.0). And `negative ? 0 : v` from that: max(+-v, 0).
+__device__ __forceinline__ float with_sign_of(float v, float direction) {
+    return __uint_as_float(__float_as_uint(v) | (__float_as_uint(direction) & 0x80000000u));
+}
+
 // Everything get_by_ray derives from the direction before the loop (raytracing_on_cpu.rs:331-332)
 __device__ __forceinline__ void ray_setup(RayConst& r) {
     auto sq = [](float v) { return v * v; };  // `.powf(2.)` == x*x
@@ -256,7 +262,7 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     const float unit = bsize * inv_brick_dim_of<BS>(t);  // size / dim, exact: both powers of two
     float cx = bx + (float)ix * unit, cy = by + (float)iy * unit, cz = bz + (float)iz * unit;
     // `current_bounds.min_position += step * brick_unit`: step is +-1.0 or 0.0, so the addend is +-unit or +0
-    const float ux = r.negx ? -unit : unit, uy = r.negy ? -unit : unit, uz = r.negz ? -unit : unit;
+    const float ux = with_sign_of(unit, r.dx), uy = with_sign_of(unit, r.dy), uz = with_sign_of(unit, r.dz);
     const float ex = r.negx ? bx - unit : bx + bsize, ey = r.negy ? by - unit : by + bsize, ez = r.negz ? bz - unit : bz + bsize;
     const uint32_t sh = brick_shift_of<BS>(t);
     // flat_projection(ix, iy, iz) kept incrementally, like the reference's current_flat_index (:205-207) - but in
@@ -273,8 +279,8 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     // dda_step with the x and y components packed. `steps_needed` in the sign-free form (p - corner) - off, off = 0 along a
     // descending axis and `unit` along an ascending one: RN(d - unit) = -RN(unit - d) and d - 0 = d, and only the magnitude
     // is used (the `.abs()` of :139-143), so this is dda_step's value for either sign without a per-axis select.
-    const uint64_t offxy = pack2(r.negx ? 0.0f : unit, r.negy ? 0.0f : unit), sfxy = pack2(r.sfx, r.sfy), dxy = pack2(r.dx, r.dy);
-    float offz = r.negz ? 0.0f : unit;
+    const uint64_t offxy = pack2(fmaxf(ux, 0.0f), fmaxf(uy, 0.0f)), sfxy = pack2(r.sfx, r.sfy), dxy = pack2(r.dx, r.dy);  // negative ? 0 : unit
+    float offz = fmaxf(uz, 0.0f);
     asm volatile("" : "+f"(offz));  // a loop constant in a register (otherwise rebuilt from `unit` and the sign on every step)
     uint64_t pxy = pack2(px, py);
     // The loop counts the COMPLEMENT of the flat index (mirrored ^ ~flip): the voxel's bit is then moved to the sign position
@@ -640,8 +646,15 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             // position inside the node in 4x4x4 bitmap cells (:425-436)
             // `(p - min) * 4 / size`: the two scalings by powers of two are one by their exact product 4 / size
             const float cells = 4.0f * binv;
+#if SVX_PACKED_DDA
+            float bpx, bpy;
+            unpack2(mul2(sub2(pack2(px, py), pack2(bx, by)), pack2(cells, cells)), bpx, bpy);
+            bpx = rust_clamp(bpx, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+            bpy = rust_clamp(bpy, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+#else
             float bpx = rust_clamp((px - bx) * cells, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
             float bpy = rust_clamp((py - by) * cells, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
+#endif
             float bpz = rust_clamp((pz - bz) * cells, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
             if (kind == NK_UNIFORM || target_octant == OOB_OCTANT || (oc_lo | oc_hi) == 0u ||
                 !ray_may_hit_node(t, oc_lo, oc_hi, bitmap_coord_of_clamped(bpx), bitmap_coord_of_clamped(bpy), bitmap_coord_of_clamped(bpz), r.dirbits)) {
@@ -651,12 +664,11 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 if (count != 0u) {
                     cur = hd.w;  // the entry below the top of the stack: this node's parent
                     // parent bounds: min - min % (2*size), size * 2 (:452-456, :470-471) - exact integer-valued f32, i.e.
-                    // the parent node's own bounds, which the serialiser stored (node_bounds); the entry below the top of
-                    // the stack is always the parent, also after the ring has dropped older entries. The octant the node
-                    // occupies in its parent, hash_region(centre - parent min, size) (:458-463), is "min differs from the
-                    // parent's min" per axis (the difference is 0 or size).
+                    // the parent node's own bounds, which the serialiser stored (node_bounds). The octant the node
+                    // occupies in its parent, hash_region(centre - parent min, size) (:458-463), is a property of the tree:
+                    // the serialiser stored it in the node's meta word.
                     const float4 pb = node_bounds_of(node_record(t, cur));
-                    const uint32_t from = (uint32_t)(bx != pb.x) | ((uint32_t)(bz != pb.z) << 1) | ((uint32_t)(by != pb.y) << 2);
+                    const uint32_t from = (meta >> 20) & 7u;
                     bool sx, sy, sz;
                     dda_step(r, px, py, pz, bx, by, bz, bsize, sx, sy, sz);
                     target_octant = step_octant(from, sx, sy, sz, r.dirbits >> 3);
@@ -678,18 +690,25 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 bx = tbx; by = tby; bz = tbz;
                 bsize = hs;
                 binv = binv * 2.0f;
+#if SVX_PACKED_DDA
+                float rx, ry;
+                unpack2(sub2(pack2(px, py), pack2(bx, by)), rx, ry);
+                target_octant = hash_region(rx, ry, pz - bz, hs * 0.5f);
+#else
                 target_octant = hash_region(px - bx, py - by, pz - bz, hs * 0.5f);
+#endif
                 count = min(count + 1u, 4u);  // node_stack.push(child)
                 if (LOD) mip_level -= 1.0f;
             } else {
                 // ADVANCE (:497-544)
                 // `step * 4. / size` is +-cells or +0 (sic: 4/size cells)
-                const float qx = r.negx ? -cells : cells, qy = r.negy ? -cells : cells, qz = r.negz ? -cells : cells;
+                float qx = with_sign_of(cells, r.dx), qy = with_sign_of(cells, r.dy), qz = with_sign_of(cells, r.dz);
+                asm volatile("" : "+f"(qx), "+f"(qy), "+f"(qz));  // loop constants in registers, not rebuilt per step
                 // child_bounds_for(target_octant) (:506) moves by exactly +-size/2 along every stepped axis (integers: exact)
-                const float hx = r.negx ? -hs : hs, hy = r.negy ? -hs : hs, hz = r.negz ? -hs : hs;
+                const float hx = with_sign_of(hs, r.dx), hy = with_sign_of(hs, r.dy), hz = with_sign_of(hs, r.dz);
 #if SVX_PACKED_DDA
-                uint64_t offxy = pack2(r.negx ? 0.0f : hs, r.negy ? 0.0f : hs);
-                float offz = r.negz ? 0.0f : hs;
+                uint64_t offxy = pack2(fmaxf(hx, 0.0f), fmaxf(hy, 0.0f));  // negative ? 0 : hs
+                float offz = fmaxf(hz, 0.0f);
                 asm volatile("" : "+l"(offxy), "+f"(offz));  // loop constants in registers, not rebuilt per step
                 uint64_t tbxy = pack2(tbx, tby);  // carried as a pair: the sibling's bounds are not needed after the walk
 #endif
