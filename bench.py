@@ -499,7 +499,10 @@ def main() -> int:
             line["roofline"] = {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "achieved_excluding_fast_forwarded_restarts": achieved_nocrawl, "frac_excluding_fast_forwarded_restarts": achieved_nocrawl / peak,
-                "peak_source": peak_src, "kernel": "svx::render_lod_kernel" if args.mips is not None else "svx::render_kernel",
+                "peak_source": peak_src,
+                # kernels.cu: launch_render picks the instantiation for the tree's brick dimension (8 / 32: compile-time strides)
+                "kernel": ("svx::render_lod_kernel" if args.mips is not None else "svx::render_kernel")
+                          + {8: "_brick8", 32: "_brick32"}.get(int(scene.brick_dim), ""),
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "per_ray": {"node_visits": f["node_iters"] / o["rays"], "voxel_fetches": f["voxel_fetches"] / o["rays"],
                             "restarts": f["outer_iters"] / o["rays"], "crawl_restarts": f["crawl_iters"] / o["rays"],

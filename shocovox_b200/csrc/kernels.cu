@@ -236,11 +236,11 @@ __device__ __forceinline__ void rays_body(const DeviceTree& tree, const float* _
     }
     out[i] = h;
 }
-__global__ void __launch_bounds__(BLOCK_THREADS) rays_kernel(const DeviceTree tree, const float* __restrict__ rays,
+__global__ void __launch_bounds__(BLOCK_THREADS, 6) rays_kernel(const DeviceTree tree, const float* __restrict__ rays,
                                                              uint64_t n, RayHitRecord* __restrict__ out) {
     rays_body<false>(tree, rays, n, 0.0f, out);
 }
-__global__ void __launch_bounds__(BLOCK_THREADS) rays_lod_kernel(const DeviceTree tree, const float* __restrict__ rays,
+__global__ void __launch_bounds__(BLOCK_THREADS, 6) rays_lod_kernel(const DeviceTree tree, const float* __restrict__ rays,
                                                                  uint64_t n, float viewing_distance,
                                                                  RayHitRecord* __restrict__ out) {
     rays_body<true>(tree, rays, n, viewing_distance, out);

@@ -125,6 +125,12 @@ struct RayConst {
 #ifndef SVX_PACKED_DDA
 #define SVX_PACKED_DDA 1
 #endif
+// 1: the voxel loop loads its 32-voxel occupancy word on every step (one L1-resident load, 34 issued instructions per step).
+// 0: it keeps the word in a register and reloads when the word index changes (36 without / 41 with a reload). Measured on
+// B200: the unconditional load is 3-9 % faster per frame - the kernel is bound by instruction issue, not by L1.
+#ifndef SVX_BRICK_WORD_ALWAYS
+#define SVX_BRICK_WORD_ALWAYS 1
+#endif
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); return v; }
 __device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t v; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b)); return v; }
@@ -242,6 +248,14 @@ template <int BS> __device__ __forceinline__ uint32_t brick_dim_sq_of(const Devi
 template <int BS> __device__ __forceinline__ uint32_t bit_words_of(const DeviceTree& t) { if constexpr (BS >= 0) return ((1u << (3 * BS)) + 31u) / 32u; else return t.bit_words; }
 template <int BS> __device__ __forceinline__ float inv_brick_dim_of(const DeviceTree& t) { if constexpr (BS >= 0) return 1.0f / (float)(1u << BS); else return t.inv_brick_dim; }
 
+// &base[i] formed by one multiply-add on the address (mad.wide.u32); written in PTX because the compiler otherwise
+// distributes the scaling over the index expression and spends four instructions on it
+__device__ __forceinline__ const uint32_t* word_address(const uint32_t* base, uint32_t i) {
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(i), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<const uint32_t*>(a);
+}
+
 // traverse_brick, raytracing_on_cpu.rs:156-252. Walks the occupancy bit-brick (1 bit per voxel, set = not empty) and
 // returns the flat index (flat_projection, math/mod.rs:35-37) of the first non-empty voxel or -1.
 // The loop carries only what a step needs: the flat index (it addresses the bit and, on a hit, gives the voxel index
@@ -287,14 +301,24 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     // by a left shift of (~flat & 31) = 31 - (flat & 31), a one-instruction test; word indices are compared complemented.
     uint32_t nflip = ~flip;
     asm volatile("" : "+r"(nflip));  // keeps the complement a loop constant (the compiler would rather complement on every step)
+    // word (flat >> 5) of the brick = bits[(nflat >> 5) ^ 0x07FFFFFF]
+    const uint32_t* bits = t.brick_bits + base;
+    asm volatile("" : "+l"(bits));  // the address of the brick's words stays in a register pair
+#if !SVX_BRICK_WORD_ALWAYS
     uint32_t nword_index = 0u;  // no complemented word index of a brick is 0 (their upper bits are set)
+#endif
     uint32_t nflat;
     for (;;) {
         nflat = mirrored ^ nflip;
+#if SVX_BRICK_WORD_ALWAYS
+        // one L1-resident load per step instead of "same word as before?" bookkeeping: fewer issued instructions
+        word = __ldg(word_address(bits, (nflat >> 5) ^ 0x07FFFFFFu));
+#else
         if ((nflat >> 5) != nword_index) {
             nword_index = nflat >> 5;
-            word = __ldg(t.brick_bits + (base + (~nflat >> 5)));
+            word = __ldg(word_address(bits, nword_index ^ 0x07FFFFFFu));
         }
+#endif
         if ((int)(word << (nflat & 31u)) < 0) break;
         float tx, ty;
         unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
