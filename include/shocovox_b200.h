@@ -209,6 +209,17 @@ SVX_API void svx_gpu_host_free(svx_gpu_host* host);
  * the palette are replaced, of the bricks only those written since this host's last upload are copied. A no-op when
  * the tree has not been modified. Waits for the device first: no render may be in flight on another thread. */
 SVX_API int32_t svx_gpu_host_reload(svx_gpu_host* host);
+/* Host image of the node table a host uploads: one 64-byte record per node in breadth-first order (root = record 0):
+ *   u32[0..1] stored occupied bits lo / hi (src/octree/detail.rs:524-544)
+ *   u32[2]    meta: node kind [1:0] (0 Nothing, 1 Internal, 2 Leaf, 3 UniformLeaf), brick kind of octant o at
+ *             [3+2o : 2+2o] (0 empty, 1 parted, 2 solid), MIP brick kind [19:18], octant in the parent [22:20]
+ *   u32[3]    index of the parent record (0xFFFFFFFF for the root)
+ *   u32[4..11] Internal: child record per octant or 0xFFFFFFFF; Leaf: brick slot per octant; UniformLeaf: slot 0
+ *   f32[12..15] bounds: min x, y, z, size
+ * This is the flattening the reference does in OctreeRenderData (src/raytracing/bevy/types.rs:216-279) for its own shader;
+ * it needs no GPU. `records` may be NULL to query the count; otherwise `capacity` records are available and the call
+ * fails with SVX_E_INVALID_ARGUMENT when the tree has more. */
+SVX_API int32_t svx_octree_render_data_nodes(const svx_octree* tree, void* records, uint64_t capacity, uint64_t* n_nodes);
 /* What the most recent upload / reload of this host copied */
 SVX_API int32_t svx_gpu_host_last_upload(const svx_gpu_host* host, svx_upload_stats* out);
 SVX_API int32_t svx_gpu_host_stats(const svx_gpu_host* host, svx_gpu_stats* out);

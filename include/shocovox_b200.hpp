@@ -213,6 +213,14 @@ class Octree {
     uint32_t get_size() const { return svx_octree_size(h_); }
     void set_auto_simplify(bool v) { check(svx_octree_set_auto_simplify(h_, v ? 1 : 0)); }  // pub auto_simplify
     uint64_t structure_hash() const { return svx_octree_structure_hash(h_); }
+    // Host image of the uploaded node table, 16 u32 per node (svx_octree_render_data_nodes; OctreeRenderData, bevy/types.rs:216-279)
+    std::vector<std::array<uint32_t, 16>> render_data_nodes() const {
+        uint64_t n = 0;
+        check(svx_octree_render_data_nodes(h_, nullptr, 0, &n));
+        std::vector<std::array<uint32_t, 16>> records(n);
+        check(svx_octree_render_data_nodes(h_, records.data(), n, &n));
+        return records;
+    }
     // Octree::albedo_mip_map_resampling_strategy, src/octree/mod.rs:379
     StrategyUpdater albedo_mip_map_resampling_strategy() { return StrategyUpdater(h_); }
     // Octree::to_bytes / from_bytes / save / load (bencode, src/octree/mod.rs:138-168)

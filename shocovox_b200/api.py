@@ -139,7 +139,7 @@ EXPORTS = [
     "svx_version", "svx_last_error_message", "svx_cuda_device_count",
     "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
     "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
-    "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count",
+    "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count", "svx_octree_render_data_nodes",
     "svx_octree_switch_albedo_mip_maps", "svx_octree_mip_maps_enabled", "svx_octree_recalculate_mips",
     "svx_octree_mip_set_method_at", "svx_octree_mip_get_method_at", "svx_octree_mip_set_color_similarity_thr_at",
     "svx_octree_mip_get_color_similarity_at", "svx_octree_mip_reset", "svx_octree_mip_sample_root", "svx_octree_mip_hash",
@@ -231,6 +231,7 @@ def lib() -> C.CDLL:
     L.svx_gpu_host_free.restype = None
     L.svx_gpu_host_reload.argtypes = [vp]
     L.svx_gpu_host_stats.argtypes = [vp, C.POINTER(_GpuStats)]
+    L.svx_octree_render_data_nodes.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.svx_gpu_host_last_upload.argtypes = [vp, C.POINTER(_UploadStats)]
     L.svx_gpu_host_get_by_rays.argtypes = [vp, vp, u64, vp]
     L.svx_gpu_host_create_view.argtypes = [vp, u32, C.POINTER(_Viewport), u32, u32, C.POINTER(vp)]
@@ -504,6 +505,16 @@ class Octree:
         return self.get_by_ray_at_lod(ray, F32_MAX, device)
 
     # `Octree::get_by_ray_at_lod(&Ray, viewing_distance)` (src/raytracing/raytracing_on_cpu.rs:325)
+    def render_data_nodes(self) -> np.ndarray:
+        """Host image of the uploaded node table: [n, 16] u32, one 64-byte record per node in breadth-first order
+        (include/shocovox_b200.h: svx_octree_render_data_nodes; the reference's OctreeRenderData, bevy/types.rs:216-279).
+        Needs no GPU."""
+        n = C.c_uint64(0)
+        _check(lib().svx_octree_render_data_nodes(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 16), dtype=np.uint32)
+        _check(lib().svx_octree_render_data_nodes(self._h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out
+
     def get_by_ray_at_lod(self, ray: Ray, viewing_distance: float, device: int = 0) -> Optional[RayHit]:
         if device == 0:  # svx_octree_get_by_ray_at_lod: the tree handle keeps its own device copy on device 0
             r, h = _Ray(), _Hit()

@@ -237,6 +237,16 @@ cudaError_t grow_device_array(void** ptr, size_t* capacity, size_t need, size_t 
     return cudaSuccess;
 }
 
+// interleave head / slots / bounds into the 64-byte records (gpu_tree.hpp: DeviceTree::node_rec)
+void pack_node_records(const SerialisedNodes& s, uint32_t* records) {
+    for (size_t i = 0; i < s.node_head.size(); ++i) {
+        uint32_t* rec = records + i * 16;
+        std::memcpy(rec, &s.node_head[i], 16);
+        std::memcpy(rec + 4, s.node_slot.data() + i * 8, 32);
+        std::memcpy(rec + 12, s.node_bounds.data() + i * 4, 16);
+    }
+}
+
 // Render-data upload (OctreeGPUHost::create_new_view / write_to_gpu, src/raytracing/bevy/data.rs:111, :365).
 // The node tables and the palette are re-serialised and replaced; bricks are mirrored by pool handle, and only the
 // ones written since the revision this host last uploaded are copied (all of them the first time).
@@ -260,14 +270,8 @@ int32_t upload(svx_gpu_host* h) {
     CUDA_TRY(grow_device_array(&h->d_node_mip, &mip_capacity, head_capacity, 4, 0, h->stream));
     h->node_capacity = head_capacity;
     CUDA_TRY(grow_device_array(&h->d_palette, &h->palette_capacity, s.palette.size(), 4, 0, h->stream));
-    // interleave head / slots / bounds into the 64-byte records (gpu_tree.hpp: DeviceTree::node_rec)
     std::vector<uint32_t> records(n_nodes * 16);
-    for (size_t i = 0; i < n_nodes; ++i) {
-        uint32_t* rec = records.data() + i * 16;
-        std::memcpy(rec, &s.node_head[i], 16);
-        std::memcpy(rec + 4, s.node_slot.data() + i * 8, 32);
-        std::memcpy(rec + 12, s.node_bounds.data() + i * 4, 16);
-    }
+    pack_node_records(s, records.data());
     CUDA_TRY(cudaMemcpyAsync(h->d_node_rec, records.data(), records.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_node_mip, s.node_mip.data(), n_nodes * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));  // `records` is a local staging buffer
@@ -855,6 +859,21 @@ int32_t svx_gpu_host_last_upload(const svx_gpu_host* h, svx_upload_stats* out) {
     if (!h || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     *out = h->last_upload;
     return SVX_OK;
+}
+
+int32_t svx_octree_render_data_nodes(const svx_octree* t, void* records, uint64_t capacity, uint64_t* n_nodes) {
+    if (!t || !t->tree || !n_nodes) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    try {
+        SerialisedNodes s;
+        serialise_nodes(*t->tree, &s);
+        *n_nodes = s.node_head.size();
+        if (!records) return SVX_OK;
+        if (capacity < s.node_head.size()) return fail(SVX_E_INVALID_ARGUMENT, "record buffer too small");
+        pack_node_records(s, static_cast<uint32_t*>(records));
+        return SVX_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SVX_E_OUT_OF_MEMORY, "out of host memory");
+    }
 }
 
 int32_t svx_gpu_host_stats(const svx_gpu_host* h, svx_gpu_stats* out) {
