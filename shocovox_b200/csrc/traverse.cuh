@@ -128,6 +128,11 @@ struct RayConst {
 // 1: the voxel loop loads its 32-voxel occupancy word on every step (one L1-resident load, 34 issued instructions per step).
 // 0: it keeps the word in a register and reloads when the word index changes (36 without / 41 with a reload). Measured on
 // B200: the unconditional load is 3-9 % faster per frame - the kernel is bound by instruction issue, not by L1.
+// 1: one instantiation of the brick walk serves UniformLeaf nodes and the octants of Leaf nodes (smaller kernel, the two
+// kinds of lanes converge in the walk); 0: one instantiation per kind
+#ifndef SVX_SINGLE_PROBE_SITE
+#define SVX_SINGLE_PROBE_SITE 1
+#endif
 #ifndef SVX_BRICK_WORD_ALWAYS
 #define SVX_BRICK_WORD_ALWAYS 1
 #endif
@@ -650,6 +655,25 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                         return true;
                 }
             }
+#if SVX_SINGLE_PROBE_SITE
+            if (target_octant != OOB_OCTANT && kind >= NK_LEAF) {
+                // One call site for both leaf kinds (:393-421): the brick walk is instantiated once, and lanes that sit in a
+                // UniformLeaf walk their bricks together with lanes that sit in an octant of a Leaf.
+                const bool uniform = kind == NK_UNIFORM;
+                const uint32_t o = uniform ? 0u : target_octant;
+                const uint32_t bkind = (meta >> (2u + 2u * o)) & 3u;
+                if (bkind != BK_EMPTY) {
+                    // child_bounds_for: min + offset * size / 2 with offset 0 or 1 per axis = min or min + size/2
+                    const float hs = bsize * 0.5f;
+                    const float cbx = (!uniform && (o & 1u)) ? bx + hs : bx;
+                    const float cby = (!uniform && (o & 4u)) ? by + hs : by;
+                    const float cbz = (!uniform && (o & 2u)) ? bz + hs : bz;
+                    if (probe_brick<BS>(t, r, px, py, pz, bkind, node_slot_of(rec, o), cbx, cby, cbz, uniform ? bsize : hs,
+                                        uniform ? binv : binv * 2.0f, out))
+                        return true;
+                }
+            }
+#else
             if (target_octant != OOB_OCTANT) {
                 if (kind == NK_UNIFORM) {
                     const uint32_t ubk = (meta >> 2) & 3u;
@@ -667,6 +691,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                     }
                 }
             }
+#endif
             // position inside the node in 4x4x4 bitmap cells (:425-436)
             // `(p - min) * 4 / size`: the two scalings by powers of two are one by their exact product 4 / size
             const float cells = 4.0f * binv;
