@@ -206,6 +206,26 @@ Cube child_bounds_for(const Cube& c, uint8_t octant) {
     return Cube{c.min_position + (luts().octant_offset[octant] * child_size), child_size};
 }
 
+V3f cross_product(V3f a, V3f b) { return cross(a, b); }
+
+// plane_line_intersection, src/spatial/raytracing/mod.rs:86-104. V3c::dot (vector.rs:182-184) sums left to right.
+bool plane_line_intersection(V3f plane_point, V3f plane_normal, V3f line_origin, V3f line_direction, float* distance) {
+    auto dot = [](V3f a, V3f b) { return a.x * b.x + a.y * b.y + a.z * b.z; };
+    const V3f origins_diff = plane_point - line_origin;
+    const float plane_line_dot_to_plane = dot(origins_diff, plane_normal);
+    const float directions_dot = dot(line_direction, plane_normal);
+    if (0.0f == directions_dot) {
+        // line and plane are parallel: distance 0 when the origin is already on the plane, otherwise no intersection
+        if (0.0f == dot(origins_diff, plane_normal)) {
+            *distance = 0.0f;
+            return true;
+        }
+        return false;
+    }
+    *distance = plane_line_dot_to_plane / directions_dot;
+    return true;
+}
+
 bool intersect_ray(const Cube& c, const Ray& ray, bool* has_distance, float* distance) {
     const V3f max_position = c.min_position + unit(c.size);
     const float t1 = (c.min_position.x - ray.origin.x) / ray.direction.x;

@@ -266,6 +266,9 @@ void set_occupancy_in_bitmap_64bits(size_t px, size_t py, size_t pz, size_t size
                                     uint64_t* bitmap);               // src/spatial/math/mod.rs:114-162
 Cube child_bounds_for(const Cube& c, uint8_t octant);                // src/spatial/mod.rs:32-39
 bool intersect_ray(const Cube& c, const Ray& ray, bool* has_distance, float* distance);  // src/spatial/raytracing/mod.rs:32-61
+// src/spatial/raytracing/mod.rs:86-104 (not on the ray path; the reference keeps it "for debugging or new implementations")
+bool plane_line_intersection(V3f plane_point, V3f plane_normal, V3f line_origin, V3f line_direction, float* distance);
+V3f cross_product(V3f a, V3f b);  // V3c::cross, src/spatial/math/vector.rs:186-192 (the callers' `up x direction`)
 uint8_t step_octant(uint8_t octant, V3f step);                       // src/spatial/raytracing/mod.rs:68-80
 V3f cube_impact_normal(const Cube& c, V3f impact_point);             // src/spatial/raytracing/mod.rs:106-134
 V3f get_dda_scale_factors(const Ray& ray);                           // src/raytracing/raytracing_on_cpu.rs:99-112

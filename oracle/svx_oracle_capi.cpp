@@ -384,6 +384,16 @@ int32_t svxo_intersect_ray(const float min_pos[3], float size, const float origi
     *d = dist;
     return hit ? (has ? 2 : 1) : 0;
 }
+// returns 1 = Some(d), 0 = None
+int32_t svxo_plane_line_intersection(const float plane_point[3], const float plane_normal[3], const float line_origin[3],
+                                     const float line_direction[3], float* d) {
+    auto v = [](const float* p) { return V3f{p[0], p[1], p[2]}; };
+    return plane_line_intersection(v(plane_point), v(plane_normal), v(line_origin), v(line_direction), d) ? 1 : 0;
+}
+void svxo_cross(const float a[3], const float b[3], float out[3]) {
+    const V3f c = cross_product(V3f{a[0], a[1], a[2]}, V3f{b[0], b[1], b[2]});
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
 uint32_t svxo_step_octant(uint32_t octant, float sx, float sy, float sz) {
     return step_octant((uint8_t)octant, V3f{sx, sy, sz});
 }

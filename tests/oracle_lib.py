@@ -174,6 +174,9 @@ def lib() -> C.CDLL:
     L.svxo_child_bounds_for.argtypes = [f3, f32, u32, f3]
     L.svxo_intersect_ray.argtypes = [f3, f32, f3, f3, f3]
     L.svxo_intersect_ray.restype = i32
+    L.svxo_plane_line_intersection.argtypes = [f3, f3, f3, f3, f3]
+    L.svxo_plane_line_intersection.restype = i32
+    L.svxo_cross.argtypes = [f3, f3, f3]
     L.svxo_step_octant.argtypes = [u32, f32, f32, f32]
     L.svxo_step_octant.restype = u32
     L.svxo_cube_impact_normal.argtypes = [f3, f32, f3, f3]

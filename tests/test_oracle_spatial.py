@@ -118,6 +118,33 @@ def test_intersect_edge_cases():
     assert kind == 2 and d > 0.0
 
 
+def _plane_line(plane_point, plane_normal, line_origin, line_direction):
+    f3 = C.c_float * 3
+    d = C.c_float(0)
+    some = L.svxo_plane_line_intersection(f3(*plane_point), f3(*plane_normal), f3(*line_origin), f3(*line_direction), C.byref(d))
+    return d.value if some else None
+
+
+# src/spatial/raytracing/tests.rs:6-39
+def test_plane_line_intersection():
+    assert _plane_line((0, 0, 0), (0, 1, 0), (0, 1, 0), (1, 0, 0)) is None
+    assert _plane_line((0, 0, 0), (0, 1, 0), (0, 1, 0), (0, -1, 0)) == 1.0
+    assert _plane_line((0, 0, 0), (0, 1, 0), (0, 0, 0), (1, 0, 0)) == 0.0
+
+
+# src/spatial/math/tests.rs:12-25
+def test_negative_intersection():
+    assert _plane_line((0, 0, 0), (0, 1, 0), (0, 1, 0), (0, 1, 0)) == -1.0
+
+
+# src/spatial/tests.rs:7-14
+def test_cross_product():
+    f3 = C.c_float * 3
+    out = f3()
+    L.svxo_cross(f3(3, 0, 2), f3(-1, 4, 2), out)
+    assert tuple(out) == (-8.0, -8.0, 12.0)
+
+
 # src/spatial/math/tests.rs:27-51
 def test_edge_case_cube_top_hit():
     origin = np.array([8.965594, 10.0, -4.4292345], dtype=np.float32)
