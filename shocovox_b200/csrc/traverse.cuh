@@ -264,7 +264,8 @@ __device__ __forceinline__ const uint32_t* word_address(const uint32_t* base, ui
 // traverse_brick, raytracing_on_cpu.rs:156-252. Walks the occupancy bit-brick (1 bit per voxel, set = not empty) and
 // returns the flat index (flat_projection, math/mod.rs:35-37) of the first non-empty voxel or -1.
 // The loop carries only what a step needs: the flat index (it addresses the bit and, on a hit, gives the voxel index
-// back), the current 32-voxel word in a register, and the min corner of the current cell. The reference's bounds check
+// back) and the min corner of the current cell; the 32-voxel occupancy word is loaded on every step (L1-resident, see
+// SVX_BRICK_WORD_ALWAYS). The reference's bounds check
 // on the integer index (:193-203) is done on that corner instead: corners are exact multiples of `unit` (integers),
 // every step moves a stepped axis by exactly one cell, so the walk has left the brick exactly when a corner equals
 // the first corner outside (min - unit going down, min + size going up).
@@ -303,7 +304,7 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     asm volatile("" : "+f"(offz));  // a loop constant in a register (otherwise rebuilt from `unit` and the sign on every step)
     uint64_t pxy = pack2(px, py);
     // The loop counts the COMPLEMENT of the flat index (mirrored ^ ~flip): the voxel's bit is then moved to the sign position
-    // by a left shift of (~flat & 31) = 31 - (flat & 31), a one-instruction test; word indices are compared complemented.
+    // by a left shift of (~flat & 31) = 31 - (flat & 31), a one-instruction test.
     uint32_t nflip = ~flip;
     asm volatile("" : "+r"(nflip));  // keeps the complement a loop constant (the compiler would rather complement on every step)
     // word (flat >> 5) of the brick = bits[(nflat >> 5) ^ 0x07FFFFFF]
