@@ -124,6 +124,11 @@ typedef struct svx_upload_stats {
 SVX_API const char* svx_version(void);
 SVX_API const char* svx_last_error_message(void); /* thread-local text of the last failing call */
 SVX_API int32_t svx_cuda_device_count(void);      /* 0 when no usable CUDA device exists */
+/* Device self-test of the shared-reciprocal form of the per-ray divisions (csrc/traverse.cuh: Reciprocal / div_by, an
+ * experimental kernel option that is off by default): compares it with the IEEE `a / b` on `n` pseudo-random operand pairs
+ * inside the range the kernels would use it for. `mismatches` must come back 0 before a build with that option may ship.
+ * Mirrors the role of the reference's own arithmetic KATs (src/spatial/math/tests.rs). SVX_E_CUDA without a device. */
+SVX_API int32_t svx_selftest_division(int32_t device, uint64_t n, uint64_t seed, uint64_t* mismatches, uint64_t* tested);
 
 /* ---- Octree: construction and point queries (host) --------------------------------------------------- */
 /* Octree::new, src/octree/mod.rs:173-205 (validation order kept: brick dimension, size, structure) */

@@ -137,6 +137,7 @@ assert VIEWPORT_DTYPE.itemsize == C.sizeof(_Viewport)
 # every symbol include/shocovox_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "svx_version", "svx_last_error_message", "svx_cuda_device_count",
+    "svx_selftest_division",
     "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
     "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
     "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count", "svx_octree_render_data_nodes",
@@ -178,6 +179,7 @@ def lib() -> C.CDLL:
     L.svx_version.restype = C.c_char_p
     L.svx_last_error_message.restype = C.c_char_p
     L.svx_cuda_device_count.restype = i32
+    L.svx_selftest_division.argtypes = [i32, u64, u64, C.POINTER(u64), C.POINTER(u64)]
     L.svx_octree_new.argtypes = [u32, u32, C.POINTER(vp)]
     L.svx_octree_free.argtypes = [vp]
     L.svx_octree_free.restype = None

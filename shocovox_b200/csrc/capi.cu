@@ -584,6 +584,24 @@ int32_t svx_cuda_device_count(void) {
     return n;
 }
 
+int32_t svx_selftest_division(int32_t device, uint64_t n, uint64_t seed, uint64_t* mismatches, uint64_t* tested) {
+    if (!mismatches || !tested) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *mismatches = *tested = 0;
+    if (svx_cuda_device_count() <= device || device < 0) return fail(SVX_E_CUDA, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    unsigned long long* counts = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&counts, 16));
+    unsigned long long host[2] = {0, 0};
+    cudaError_t e = cudaMemset(counts, 0, 16);
+    if (e == cudaSuccess) e = launch_div_selftest(n, seed, counts, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(host, counts, 16, cudaMemcpyDeviceToHost);
+    cudaFree(counts);
+    if (e != cudaSuccess) return cuda_fail(e, "division self-test");
+    *mismatches = host[0];
+    *tested = host[1];
+    return SVX_OK;
+}
+
 // ---- octree ---------------------------------------------------------------------------------------------------
 int32_t svx_octree_new(uint32_t size, uint32_t brick_dim, svx_octree** out) {
     if (!out) return fail(SVX_E_INVALID_ARGUMENT, "out is null");

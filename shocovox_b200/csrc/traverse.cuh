@@ -218,12 +218,53 @@ __device__ __forceinline__ float with_sign_of(float v, float direction) {
     return __uint_as_float(__float_as_uint(v) | (__float_as_uint(direction) & 0x80000000u));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Divisions that share a divisor (EXPERIMENTAL, off by default: SVX_SHARED_RCP).
+//
+// nvcc expands every IEEE `a / b` (div.rn.f32) into the same fast path - r0 = MUFU.RCP(b); e = fma(r0, -b, 1);
+// r = fma(r0, e, r0); q0 = a * r; rem = fma(q0, -b, a); q = fma(r, rem, q0) - guarded by FCHK(a, b), with a slow path for
+// operands near the ends of the exponent range. The per-ray set-up divides by each direction component four times (two
+// slab distances, two scale-factor ratios) and by the length three times, and every one of those expansions recomputes
+// the refined reciprocal r. `Reciprocal` computes r once per divisor and `div_by` is the remaining three operations of
+// the very same sequence, so the quotient is the fast path's, bit for bit. In place of FCHK a range test confines every
+// operand to [2^-40, 2^40] - far inside the region where no intermediate (r, q0, rem) can overflow, underflow or become
+// subnormal - and anything else takes the plain `/`. Before a build with SVX_SHARED_RCP=1 may ship, div_selftest_kernel
+// (kernels.cu, svx_selftest_division) must report zero mismatches against `/` on the device.
+#ifndef SVX_SHARED_RCP
+#define SVX_SHARED_RCP 0
+#endif
+struct Reciprocal {
+    float b, r;
+};
+__device__ __forceinline__ Reciprocal reciprocal_of(float b) {
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b));
+    const float e = __fmaf_rn(r0, -b, 1.0f);
+    return Reciprocal{b, __fmaf_rn(r0, e, r0)};
+}
+__device__ __forceinline__ float div_by(float a, const Reciprocal& d) {
+    const float q0 = __fmul_rn(a, d.r);
+    const float rem = __fmaf_rn(q0, -d.b, a);
+    return __fmaf_rn(d.r, rem, q0);
+}
+// every |v| within [2^-40, 2^40] (false for NaN)
+__device__ __forceinline__ bool div_operands_ok(float a, float b, float c) {
+    const float lo = fminf(fminf(fabsf(a), fabsf(b)), fabsf(c)), hi = fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(c));
+    return a == a && b == b && c == c && lo >= 9.094947017729282e-13f && hi <= 1099511627776.0f;
+}
+
+// The part of ray_setup that does not divide
+__device__ __forceinline__ void ray_setup_signs(RayConst& r);
+
 // Everything get_by_ray derives from the direction before the loop (raytracing_on_cpu.rs:331-332)
 __device__ __forceinline__ void ray_setup(RayConst& r) {
     auto sq = [](float v) { return v * v; };  // `.powf(2.)` == x*x
     r.sfx = sqrtf(1.0f + sq(r.dz / r.dx) + sq(r.dy / r.dx));
     r.sfy = sqrtf(sq(r.dx / r.dy) + 1.0f + sq(r.dz / r.dy));
     r.sfz = sqrtf((sq(r.dx / r.dz) + 1.0f) + sq(r.dy / r.dz));
+    ray_setup_signs(r);
+}
+__device__ __forceinline__ void ray_setup_signs(RayConst& r) {
     r.negx = signbit(r.dx);
     r.negy = signbit(r.dy);
     r.negz = signbit(r.dz);
@@ -431,6 +472,39 @@ __device__ __forceinline__ bool root_entry(const RayConst& r, float tree_size, f
     py = r.oy + r.dy * d;
     pz = r.oz + r.dz * d;
     target_octant = hash_region(px, py, pz, tree_size * 0.5f);
+    return true;
+}
+
+// root_entry followed by ray_setup, as the viewport kernels call them, with the twelve divisions by the direction's
+// components sharing one refined reciprocal per component when every operand is in the safe range (see Reciprocal);
+// otherwise exactly the two functions above.
+__device__ __forceinline__ bool root_entry_and_setup(RayConst& r, float tree_size, float& px, float& py, float& pz,
+                                                     uint32_t& target_octant) {
+#if SVX_SHARED_RCP
+    const float n1 = 0.0f - r.ox, n2 = tree_size - r.ox, n3 = 0.0f - r.oy, n4 = tree_size - r.oy, n5 = 0.0f - r.oz, n6 = tree_size - r.oz;
+    if (div_operands_ok(r.dx, r.dy, r.dz) && div_operands_ok(n1, n3, n5) && div_operands_ok(n2, n4, n6)) {
+        const Reciprocal rx = reciprocal_of(r.dx), ry = reciprocal_of(r.dy), rz = reciprocal_of(r.dz);
+        const float t1 = div_by(n1, rx), t2 = div_by(n2, rx);
+        const float t3 = div_by(n3, ry), t4 = div_by(n4, ry);
+        const float t5 = div_by(n5, rz), t6 = div_by(n6, rz);
+        const float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+        const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+        if (tmax < 0.0f || tmin > tmax) return false;
+        const float d = (tmin < 0.0f) ? 0.0f : tmin;
+        px = r.ox + r.dx * d;
+        py = r.oy + r.dy * d;
+        pz = r.oz + r.dz * d;
+        target_octant = hash_region(px, py, pz, tree_size * 0.5f);
+        auto sq = [](float v) { return v * v; };
+        r.sfx = sqrtf(1.0f + sq(div_by(r.dz, rx)) + sq(div_by(r.dy, rx)));
+        r.sfy = sqrtf(sq(div_by(r.dx, ry)) + 1.0f + sq(div_by(r.dz, ry)));
+        r.sfz = sqrtf((sq(div_by(r.dx, rz)) + 1.0f) + sq(div_by(r.dy, rz)));
+        ray_setup_signs(r);
+        return true;
+    }
+#endif
+    if (!root_entry(r, tree_size, px, py, pz, target_octant)) return false;
+    ray_setup(r);
     return true;
 }
 
