@@ -87,3 +87,27 @@ def test_built_library_has_no_packed_fused_multiply_add():
     assert "FADD2" in sass and "FMUL2" in sass, "the packed f32 path is not in the built kernels"
     assert "FFMA2" not in sass
     build.check_no_packed_fma(build.LIB)
+
+
+def test_packed_fma_check_refuses_a_contracted_library(tmp_path):
+    """What the check exists for: ptxas 12.9 contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 although every operand says
+    .rn and --fmad=false is given. A library built from exactly that pattern must be refused (and removed)."""
+    import subprocess
+
+    from shocovox_b200 import build
+
+    src = tmp_path / "contract.cu"
+    src.write_text(
+        '#include <cstdint>\n'
+        'extern "C" __global__ void k(const uint64_t* a, const uint64_t* b, uint64_t* c) {\n'
+        '    uint64_t p, s;\n'
+        '    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(a[threadIdx.x]), "l"(b[threadIdx.x]));\n'
+        '    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(p), "l"(c[threadIdx.x]));\n'
+        '    c[threadIdx.x] = s;\n'
+        '}\n')
+    lib = tmp_path / "libcontract.so"
+    subprocess.run([build.nvcc_path(), "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false",
+                    "-cudart", "static", "-o", str(lib), str(src)], check=True, capture_output=True)
+    with pytest.raises(RuntimeError, match="packed fused multiply-add"):
+        build.check_no_packed_fma(lib)
+    assert not lib.exists()
