@@ -225,6 +225,15 @@ SVX_API int32_t svx_gpu_host_reload(svx_gpu_host* host);
  * it needs no GPU. `records` may be NULL to query the count; otherwise `capacity` records are available and the call
  * fails with SVX_E_INVALID_ARGUMENT when the tree has more. */
 SVX_API int32_t svx_octree_render_data_nodes(const svx_octree* tree, void* records, uint64_t capacity, uint64_t* n_nodes);
+/* Host image of the brick part of the render data: the pooled voxel array (`voxels_per_brick` palette values per brick,
+ * flat_projection order, indexed by the brick slots of the node records) and its 1-bit-per-voxel occupancy
+ * (`words_per_brick` u32 per brick; bit set unless pix_points_to_empty, src/octree/node.rs:405-427 - the device derives the
+ * same words itself during an upload). Either buffer may be NULL; both NULL queries the sizes. No GPU needed. */
+SVX_API int32_t svx_octree_render_data_bricks(const svx_octree* tree, uint32_t* voxels, uint32_t* bits, uint64_t capacity_bricks,
+                                              uint64_t* n_bricks, uint32_t* voxels_per_brick, uint32_t* words_per_brick);
+/* RAY_TO_NODE_OCCUPANCY_BITMASK_LUT (src/spatial/lut.rs, regenerated from its generator logic :39-89) in the layout the
+ * kernels read: [direction octant 0..8][cell 0..64] {lo, hi} = 1024 u32 */
+SVX_API int32_t svx_render_data_ray_lut(uint32_t* lut);
 /* What the most recent upload / reload of this host copied */
 SVX_API int32_t svx_gpu_host_last_upload(const svx_gpu_host* host, svx_upload_stats* out);
 SVX_API int32_t svx_gpu_host_stats(const svx_gpu_host* host, svx_gpu_stats* out);

@@ -82,6 +82,18 @@ void host_tables(uint64_t* ray2node /*512*/, uint64_t* octmask /*8*/, uint32_t* 
                 }
 }
 
+// RAY_TO_NODE_OCCUPANCY_BITMASK_LUT in the layout the kernels read (DeviceTree::ray_lut): [direction octant][cell] {lo, hi}
+void make_ray_lut(uint32_t* lut /* 8 * 64 * 2 */) {
+    uint64_t r2n[512], om[8];
+    uint32_t st[216];
+    host_tables(r2n, om, st);
+    for (int cell = 0; cell < 64; ++cell)
+        for (int dir = 0; dir < 8; ++dir) {
+            lut[(dir * 64 + cell) * 2] = (uint32_t)r2n[cell * 8 + dir];
+            lut[(dir * 64 + cell) * 2 + 1] = (uint32_t)(r2n[cell * 8 + dir] >> 32);
+        }
+}
+
 std::once_flag g_selftest_once;
 int32_t g_selftest_status = SVX_OK;
 std::string g_selftest_error;
@@ -798,15 +810,8 @@ int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host
         return fail(g_selftest_status, g_selftest_error);
     }
     {   // the ray-to-node occupancy table the traversal kernels read (validated against the device closed form above)
-        uint64_t r2n[512], om[8];
-        uint32_t st[216];
-        host_tables(r2n, om, st);
         std::vector<uint32_t> lut(8 * 64 * 2);
-        for (int cell = 0; cell < 64; ++cell)
-            for (int dir = 0; dir < 8; ++dir) {
-                lut[(dir * 64 + cell) * 2] = (uint32_t)r2n[cell * 8 + dir];
-                lut[(dir * 64 + cell) * 2 + 1] = (uint32_t)(r2n[cell * 8 + dir] >> 32);
-            }
+        make_ray_lut(lut.data());
         e = cudaMalloc(&h->d_ray_lut, lut.size() * 4);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_ray_lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -892,6 +897,40 @@ int32_t svx_octree_render_data_nodes(const svx_octree* t, void* records, uint64_
     } catch (const std::bad_alloc&) {
         return fail(SVX_E_OUT_OF_MEMORY, "out of host memory");
     }
+}
+
+int32_t svx_octree_render_data_bricks(const svx_octree* t, uint32_t* voxels, uint32_t* bits, uint64_t capacity, uint64_t* n_bricks,
+                                      uint32_t* voxels_per_brick, uint32_t* words_per_brick) {
+    if (!t || !t->tree || !n_bricks || !voxels_per_brick || !words_per_brick) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    const HostOctree& tree = *t->tree;
+    const size_t pool = tree.brick_pool_size(), vol = tree.brick_volume(), words = (vol + 31) / 32;
+    *n_bricks = pool;
+    *voxels_per_brick = (uint32_t)vol;
+    *words_per_brick = (uint32_t)words;
+    if (!voxels && !bits) return SVX_OK;
+    if (capacity < pool) return fail(SVX_E_INVALID_ARGUMENT, "brick buffers too small");
+    if (voxels && pool) std::memcpy(voxels, tree.brick_pool(), pool * vol * 4);
+    if (bits) {
+        // a voxel's bit is set unless pix_points_to_empty holds for it (src/octree/node.rs:405-427): (no colour index or
+        // albedo.a == 0) and (no data index or data == 0) - what occupancy_bits_kernel computes on the device
+        const std::vector<svx_albedo>& colors = tree.color_palette();
+        const std::vector<uint32_t>& datas = tree.data_palette();
+        const uint32_t* v = tree.brick_pool();
+        std::memset(bits, 0, pool * words * 4);
+        for (size_t b = 0; b < pool; ++b)
+            for (size_t i = 0; i < vol; ++i) {
+                const uint32_t value = v[b * vol + i], ci = value & 0xFFFFu, di = value >> 16;
+                const bool shows = ci < colors.size() && colors[ci].a != 0, carries = di < datas.size() && datas[di] != 0;
+                if (shows || carries) bits[b * words + (i >> 5)] |= 1u << (i & 31);
+            }
+    }
+    return SVX_OK;
+}
+
+int32_t svx_render_data_ray_lut(uint32_t* lut) {
+    if (!lut) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    make_ray_lut(lut);
+    return SVX_OK;
 }
 
 int32_t svx_gpu_host_stats(const svx_gpu_host* h, svx_gpu_stats* out) {

@@ -14,7 +14,12 @@
 // `file:line` citations are relative to the reference checkout.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
+// SVX_HOST_MIRROR: this header compiled by the HOST compiler in tests/host_mirror (test infrastructure, never part of the
+// library): the PTX fragments below get plain C++ equivalents so that the kernels' logic - the transformed arithmetic,
+// the mirrored brick walk, the parent-index stack, the crawl fast-forward - can be checked against the oracle without a
+// GPU. Device compilation is unaffected (SVX_HOST_MIRROR is never defined there).
 
 #include "gpu_tree.hpp"
 
@@ -136,10 +141,17 @@ struct RayConst {
 #ifndef SVX_BRICK_WORD_ALWAYS
 #define SVX_BRICK_WORD_ALWAYS 1
 #endif
+#ifndef SVX_HOST_MIRROR
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); return v; }
 __device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t v; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b)); return v; }
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t v; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b)); return v; }
+#else  // tests/host_mirror: the same helpers for the host compiler (each half is one IEEE operation, as on the device)
+inline uint64_t pack2(float lo, float hi) { uint32_t a, b; std::memcpy(&a, &lo, 4); std::memcpy(&b, &hi, 4); return (uint64_t)a | ((uint64_t)b << 32); }
+inline void unpack2(uint64_t v, float& lo, float& hi) { const uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32); std::memcpy(&lo, &a, 4); std::memcpy(&hi, &b, 4); }
+inline uint64_t sub2(uint64_t a, uint64_t b) { float al, ah, bl, bh; unpack2(a, al, ah); unpack2(b, bl, bh); return pack2(al - bl, ah - bh); }
+inline uint64_t mul2(uint64_t a, uint64_t b) { float al, ah, bl, bh; unpack2(a, al, ah); unpack2(b, bl, bh); return pack2(al * bl, ah * bh); }
+#endif
 
 // dda_step_to_next_sibling, raytracing_on_cpu.rs:124-152.
 //   steps_needed = size * signum.max(0.) - signum * (p - min)      (signum = +-1.0)
@@ -208,8 +220,12 @@ __device__ __forceinline__ DdaStep dda_step_off(const RayConst& r, float& px, fl
 
 // `if (m == d) { a += da; b += db; }` as one compare and two predicated additions
 __device__ __forceinline__ void add_both_if_equal(float m, float d, float& a, float da, float& b, float db) {
+#ifndef SVX_HOST_MIRROR
     asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.rn.f32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
         : "+f"(a), "+f"(b) : "f"(m), "f"(d), "f"(da), "f"(db));
+#else
+    if (m == d) { a = a + da; b = b + db; }
+#endif
 }
 
 // `negative ? -v : v` for v >= +0 as one logic instruction: v with the sign bit of `direction` (f32::signum's sign, also for
@@ -238,7 +254,11 @@ struct Reciprocal {
 };
 __device__ __forceinline__ Reciprocal reciprocal_of(float b) {
     float r0;
+#ifndef SVX_HOST_MIRROR
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b));
+#else
+    r0 = 1.0f / b;  // the host has no MUFU.RCP; only SVX_SHARED_RCP builds use this
+#endif
     const float e = __fmaf_rn(r0, -b, 1.0f);
     return Reciprocal{b, __fmaf_rn(r0, e, r0)};
 }
@@ -274,7 +294,9 @@ __device__ __forceinline__ void ray_setup_signs(RayConst& r) {
     r.dirbits = hash_region(1.0f + r.dx, 1.0f + r.dy, 1.0f + r.dz, 1.0f) | (r.negx ? 0u : 8u) | (r.negz ? 0u : 16u) | (r.negy ? 0u : 32u);
     // opaque from here on: the value lives in its register instead of being rebuilt (three additions, six compares,
     // selects) inside the node and sibling loops, which is what the compiler otherwise prefers
+#ifndef SVX_HOST_MIRROR
     asm volatile("" : "+r"(r.dirbits));
+#endif
 }
 
 // `(v as i32).clamp(0, dim-1)`: cvt.rzi saturates and maps NaN to 0 like Rust's `as`
@@ -297,9 +319,13 @@ template <int BS> __device__ __forceinline__ float inv_brick_dim_of(const Device
 // &base[i] formed by one multiply-add on the address (mad.wide.u32); written in PTX because the compiler otherwise
 // distributes the scaling over the index expression and spends four instructions on it
 __device__ __forceinline__ const uint32_t* word_address(const uint32_t* base, uint32_t i) {
+#ifndef SVX_HOST_MIRROR
     uint64_t a;
     asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(i), "l"(reinterpret_cast<uint64_t>(base)));
     return reinterpret_cast<const uint32_t*>(a);
+#else
+    return base + i;
+#endif
 }
 
 // traverse_brick, raytracing_on_cpu.rs:156-252. Walks the occupancy bit-brick (1 bit per voxel, set = not empty) and
@@ -342,15 +368,21 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     // is used (the `.abs()` of :139-143), so this is dda_step's value for either sign without a per-axis select.
     const uint64_t offxy = pack2(fmaxf(ux, 0.0f), fmaxf(uy, 0.0f)), sfxy = pack2(r.sfx, r.sfy), dxy = pack2(r.dx, r.dy);  // negative ? 0 : unit
     float offz = fmaxf(uz, 0.0f);
+#ifndef SVX_HOST_MIRROR
     asm volatile("" : "+f"(offz));  // a loop constant in a register (otherwise rebuilt from `unit` and the sign on every step)
+#endif
     uint64_t pxy = pack2(px, py);
     // The loop counts the COMPLEMENT of the flat index (mirrored ^ ~flip): the voxel's bit is then moved to the sign position
     // by a left shift of (~flat & 31) = 31 - (flat & 31), a one-instruction test.
     uint32_t nflip = ~flip;
+#ifndef SVX_HOST_MIRROR
     asm volatile("" : "+r"(nflip));  // keeps the complement a loop constant (the compiler would rather complement on every step)
+#endif
     // word (flat >> 5) of the brick = bits[(nflat >> 5) ^ 0x07FFFFFF]
     const uint32_t* bits = t.brick_bits + base;
+#ifndef SVX_HOST_MIRROR
     asm volatile("" : "+l"(bits));  // the address of the brick's words stays in a register pair
+#endif
 #if !SVX_BRICK_WORD_ALWAYS
     uint32_t nword_index = 0u;  // no complemented word index of a brick is 0 (their upper bits are set)
 #endif
@@ -378,12 +410,18 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
         pxy = pack2(qx + mx, qy + my);
         pz = pz + r.dz * m;
         // `if (m == d) { mirrored += stride; corner += u; }` per axis, as predicated instructions
+#ifndef SVX_HOST_MIRROR
         asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
             : "+r"(mirrored), "+f"(cx) : "f"(m), "f"(d_x), "r"(1u), "f"(ux));
         asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
             : "+r"(mirrored), "+f"(cy) : "f"(m), "f"(d_y), "r"(brick_dim_of<BS>(t)), "f"(uy));
         asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
             : "+r"(mirrored), "+f"(cz) : "f"(m), "f"(d_z), "r"(brick_dim_sq_of<BS>(t)), "f"(uz));
+#else
+        if (m == d_x) { mirrored += 1u; cx = cx + ux; }
+        if (m == d_y) { mirrored += brick_dim_of<BS>(t); cy = cy + uy; }
+        if (m == d_z) { mirrored += brick_dim_sq_of<BS>(t); cz = cz + uz; }
+#endif
         if (cx == ex || cy == ey || cz == ez) break;
     }
     unpack2(pxy, px, py);
@@ -827,13 +865,17 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                 // ADVANCE (:497-544)
                 // `step * 4. / size` is +-cells or +0 (sic: 4/size cells)
                 float qx = with_sign_of(cells, r.dx), qy = with_sign_of(cells, r.dy), qz = with_sign_of(cells, r.dz);
+#ifndef SVX_HOST_MIRROR
                 asm volatile("" : "+f"(qx), "+f"(qy), "+f"(qz));  // loop constants in registers, not rebuilt per step
+#endif
                 // child_bounds_for(target_octant) (:506) moves by exactly +-size/2 along every stepped axis (integers: exact)
                 const float hx = with_sign_of(hs, r.dx), hy = with_sign_of(hs, r.dy), hz = with_sign_of(hs, r.dz);
 #if SVX_PACKED_DDA
                 uint64_t offxy = pack2(fmaxf(hx, 0.0f), fmaxf(hy, 0.0f));  // negative ? 0 : hs
                 float offz = fmaxf(hz, 0.0f);
+#ifndef SVX_HOST_MIRROR
                 asm volatile("" : "+l"(offxy), "+f"(offz));  // loop constants in registers, not rebuilt per step
+#endif
                 uint64_t tbxy = pack2(tbx, tby);  // carried as a pair: the sibling's bounds are not needed after the walk
 #endif
                 for (;;) {
