@@ -26,17 +26,16 @@ SRC = ROOT / "tests" / "host_mirror" / "host_mirror.cpp"
 HIT = np.dtype([("hit", "<u4"), ("palette_value", "<u4"), ("impact_point", "<f4", 3), ("normal", "<f4", 3), ("distance", "<f4")])
 
 
-@pytest.fixture(scope="module")
-def mirror():
+def build_mirror(name: str, defines=()):
     out = ROOT / "tests" / "host_mirror" / "build"
     out.mkdir(exist_ok=True)
-    lib = out / "libhost_mirror.so"
+    lib = out / f"lib{name}.so"
     csrc = ROOT / "shocovox_b200" / "csrc"
     deps = [SRC, csrc / "traverse.cuh", csrc / "gpu_tree.hpp", csrc / "kernels.cuh"]
     if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
         cuda_include = Path(product_build.nvcc_path()).resolve().parent.parent / "include"
         res = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-                              f"-I{cuda_include}", f"-I{csrc}", f"-I{ROOT / 'include'}", "-o", str(lib), str(SRC)],
+                              *[f"-D{d}" for d in defines], f"-I{cuda_include}", f"-I{csrc}", f"-I{ROOT / 'include'}", "-o", str(lib), str(SRC)],
                              capture_output=True, text=True)
         assert res.returncode == 0, res.stderr[-3000:]
     L = C.CDLL(str(lib))
@@ -44,6 +43,18 @@ def mirror():
                                               C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
     L.svx_host_mirror_get_by_rays.restype = C.c_int
     return L
+
+
+@pytest.fixture(scope="module")
+def mirror():
+    """the kernel code as the library builds it (default options)"""
+    return build_mirror("host_mirror")
+
+
+@pytest.fixture(scope="module")
+def mirror_shared_rcp():
+    """the same with the experimental shared-reciprocal divisions of the per-ray set-up (SVX_SHARED_RCP=1, off in the library)"""
+    return build_mirror("host_mirror_shared_rcp", ["SVX_SHARED_RCP=1"])
 
 
 def bits(a):
@@ -144,3 +155,15 @@ def test_edits_are_followed(mirror):
                 else:
                     t.clear(p)
         assert_same_hits(mirror_rays(mirror, ptree.tree, rays), otree.get_by_rays(rays))
+
+
+@pytest.mark.parametrize("name", ["cpu_render_64_8", "dot_cube_128_32", "colonnade_256_8", "terrain_256_8_shell"])
+def test_shared_reciprocal_option_keeps_every_bit(mirror_shared_rcp, name):
+    """SVX_SHARED_RCP=1 (traverse.cuh: root_entry_and_setup with one refined reciprocal per divisor, off by default) must not
+    change a result: its wiring - which numerator meets which reciprocal, the range guards, the fall-back to plain `/` for
+    axis-parallel rays and origins on a bounding plane - is checked here; that the device's reciprocal sequence itself
+    equals div.rn is what svx_selftest_division checks on the GPU."""
+    scene = SCENES[name]()
+    tree, otree = scenes.build_tree(scene, S.Octree), scenes.build_tree(scene, O.OracleOctree)
+    rays = random_rays(scene.tree_size, 20000, 1 + zlib.crc32(name.encode()) % 1000)
+    assert_same_hits(mirror_rays(mirror_shared_rcp, tree, rays), otree.get_by_rays(rays))
