@@ -225,6 +225,11 @@ SVX_API int32_t svx_gpu_host_reload(svx_gpu_host* host);
  * it needs no GPU. `records` may be NULL to query the count; otherwise `capacity` records are available and the call
  * fails with SVX_E_INVALID_ARGUMENT when the tree has more. */
 SVX_API int32_t svx_octree_render_data_nodes(const svx_octree* tree, void* records, uint64_t capacity, uint64_t* n_nodes);
+/* The same plus the second per-node table of the render data: the brick slot of every node's MIP brick (reference
+ * node_mips[key], src/octree/types.rs:186; 0xFFFFFFFF = none or MIP maps disabled), read only by the level-of-detail branch
+ * of get_by_ray_at_lod (raytracing_on_cpu.rs:368-386). Either output may be NULL. */
+SVX_API int32_t svx_octree_render_data_nodes_with_mips(const svx_octree* tree, void* records, uint32_t* mip_slots, uint64_t capacity,
+                                                       uint64_t* n_nodes);
 /* Host image of the brick part of the render data: the pooled voxel array (`voxels_per_brick` palette values per brick,
  * flat_projection order, indexed by the brick slots of the node records) and its 1-bit-per-voxel occupancy
  * (`words_per_brick` u32 per brick; bit set unless pix_points_to_empty, src/octree/node.rs:405-427 - the device derives the

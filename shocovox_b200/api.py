@@ -140,7 +140,7 @@ EXPORTS = [
     "svx_selftest_division",
     "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
     "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
-    "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count", "svx_octree_render_data_nodes", "svx_octree_render_data_bricks", "svx_render_data_ray_lut",
+    "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count", "svx_octree_render_data_nodes", "svx_octree_render_data_nodes_with_mips", "svx_octree_render_data_bricks", "svx_render_data_ray_lut",
     "svx_octree_switch_albedo_mip_maps", "svx_octree_mip_maps_enabled", "svx_octree_recalculate_mips",
     "svx_octree_mip_set_method_at", "svx_octree_mip_get_method_at", "svx_octree_mip_set_color_similarity_thr_at",
     "svx_octree_mip_get_color_similarity_at", "svx_octree_mip_reset", "svx_octree_mip_sample_root", "svx_octree_mip_hash",
@@ -234,6 +234,7 @@ def lib() -> C.CDLL:
     L.svx_gpu_host_reload.argtypes = [vp]
     L.svx_gpu_host_stats.argtypes = [vp, C.POINTER(_GpuStats)]
     L.svx_octree_render_data_nodes.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.svx_octree_render_data_nodes_with_mips.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
     L.svx_octree_render_data_bricks.argtypes = [vp, vp, vp, u64, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]
     L.svx_render_data_ray_lut.argtypes = [vp]
     L.svx_gpu_host_last_upload.argtypes = [vp, C.POINTER(_UploadStats)]
@@ -517,6 +518,14 @@ class Octree:
         _check(lib().svx_octree_render_data_nodes(self._h, None, 0, C.byref(n)))
         out = np.zeros((n.value, 16), dtype=np.uint32)
         _check(lib().svx_octree_render_data_nodes(self._h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out
+
+    def render_data_mip_slots(self) -> np.ndarray:
+        """Brick slot of every node's MIP brick, in the order of render_data_nodes() (svx_octree_render_data_nodes_with_mips)."""
+        n = C.c_uint64(0)
+        _check(lib().svx_octree_render_data_nodes_with_mips(self._h, None, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        _check(lib().svx_octree_render_data_nodes_with_mips(self._h, None, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
         return out
 
     def render_data_bricks(self):

@@ -885,14 +885,20 @@ int32_t svx_gpu_host_last_upload(const svx_gpu_host* h, svx_upload_stats* out) {
 }
 
 int32_t svx_octree_render_data_nodes(const svx_octree* t, void* records, uint64_t capacity, uint64_t* n_nodes) {
+    return svx_octree_render_data_nodes_with_mips(t, records, nullptr, capacity, n_nodes);
+}
+
+int32_t svx_octree_render_data_nodes_with_mips(const svx_octree* t, void* records, uint32_t* mip_slots, uint64_t capacity,
+                                               uint64_t* n_nodes) {
     if (!t || !t->tree || !n_nodes) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     try {
         SerialisedNodes s;
         serialise_nodes(*t->tree, &s);
         *n_nodes = s.node_head.size();
-        if (!records) return SVX_OK;
+        if (!records && !mip_slots) return SVX_OK;
         if (capacity < s.node_head.size()) return fail(SVX_E_INVALID_ARGUMENT, "record buffer too small");
-        pack_node_records(s, static_cast<uint32_t*>(records));
+        if (records) pack_node_records(s, static_cast<uint32_t*>(records));
+        if (mip_slots) std::memcpy(mip_slots, s.node_mip.data(), s.node_mip.size() * 4);
         return SVX_OK;
     } catch (const std::bad_alloc&) {
         return fail(SVX_E_OUT_OF_MEMORY, "out of host memory");

@@ -5,7 +5,8 @@
 // nvcc / ptxas make of the same source (FMA contraction, packed instructions): that stays with the `-m gpu` parity tests.
 // The product has no CPU ray path; nothing outside tests/ builds or loads this file.
 //
-// Mirrors rays_body<false> of csrc/kernels.cu (Octree::get_by_ray, reference src/raytracing/raytracing_on_cpu.rs:316-565).
+// Mirrors rays_body<LOD> of csrc/kernels.cu (Octree::get_by_ray / get_by_ray_at_lod, reference
+// src/raytracing/raytracing_on_cpu.rs:316-565).
 #define SVX_HOST_MIRROR 1
 #include <math.h>
 
@@ -45,8 +46,9 @@ static inline T max(T a, T b) { return a < b ? b : a; }
 
 namespace {
 
-template <int BS>
-void trace_range(const svx::DeviceTree& tree, const float* rays, uint64_t begin, uint64_t end, svx::RayHitRecord* out) {
+template <bool LOD, int BS>
+void trace_range(const svx::DeviceTree& tree, const float* rays, uint64_t begin, uint64_t end, float viewing_distance,
+                 svx::RayHitRecord* out) {
     using namespace svx;
     for (uint64_t i = begin; i < end; ++i) {
         RayConst r;
@@ -60,7 +62,7 @@ void trace_range(const svx::DeviceTree& tree, const float* rays, uint64_t begin,
         // trace_ray (traverse.cuh) with the brick dimension as a template argument, as the viewport kernels instantiate it
         if (!certain_root_miss(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, (float)tree.tree_size) &&
             root_entry_and_setup(r, (float)tree.tree_size, px, py, pz, target_octant))
-            hit = traverse<false, BS>(tree, r, px, py, pz, target_octant, res);
+            hit = traverse<LOD, BS>(tree, r, px, py, pz, target_octant, res, viewing_distance);
         RayHitRecord h;
         h.hit = hit ? 1u : 0u;
         h.palette_value = hit ? res.palette_value : NIL;
@@ -80,14 +82,17 @@ void trace_range(const svx::DeviceTree& tree, const float* rays, uint64_t begin,
 }  // namespace
 
 // specialise != 0: use the compile-time brick dimension instantiation when the tree's dimension is 8 or 32 (what
-// launch_render does); 0: always the generic code. Returns 0, or 1 for inconsistent arguments.
+// launch_render does); 0: always the generic code. node_mip != NULL: the tree's MIP maps are enabled - the LOD
+// instantiation runs, as in the library (DeviceTree::mips_enabled selects it, not the viewing distance).
+// Returns 0, or 1 for inconsistent arguments.
 extern "C" int svx_host_mirror_get_by_rays(const uint32_t* node_rec, uint32_t n_nodes, const uint32_t* voxels, const uint32_t* bits,
                                            uint32_t n_bricks, const uint32_t* ray_lut, uint32_t tree_size, uint32_t brick_dim,
-                                           int specialise, const float* rays, uint64_t n, svx::RayHitRecord* out, int threads) {
+                                           int specialise, const float* rays, uint64_t n, svx::RayHitRecord* out, int threads,
+                                           const uint32_t* node_mip, float viewing_distance) {
     if (!node_rec || !ray_lut || !rays || !out || n_nodes == 0 || brick_dim == 0 || (brick_dim & (brick_dim - 1))) return 1;
     svx::DeviceTree t{};
     t.node_rec = reinterpret_cast<const uint4*>(node_rec);
-    t.node_mip = nullptr;
+    t.node_mip = node_mip;
     t.voxels = voxels;
     t.brick_bits = bits;
     t.palette = nullptr;
@@ -101,7 +106,7 @@ extern "C" int svx_host_mirror_get_by_rays(const uint32_t* node_rec, uint32_t n_
     t.brick_dim_sq = brick_dim * brick_dim;
     t.bit_words = (brick_dim * brick_dim * brick_dim + 31u) / 32u;
     t.n_colors = 0;
-    t.mips_enabled = 0;
+    t.mips_enabled = node_mip ? 1u : 0u;
     t.inv_tree_size = 1.0f / (float)tree_size;
     t.inv_brick_dim = 1.0f / (float)brick_dim;
     const int nt = std::max(1, threads);
@@ -109,9 +114,16 @@ extern "C" int svx_host_mirror_get_by_rays(const uint32_t* node_rec, uint32_t n_
     for (int k = 0; k < nt; ++k) {
         const uint64_t b = n * k / nt, e = n * (k + 1) / nt;
         pool.emplace_back([=] {
-            if (specialise && t.brick_shift == 3u) trace_range<3>(t, rays, b, e, out);
-            else if (specialise && t.brick_shift == 5u) trace_range<5>(t, rays, b, e, out);
-            else trace_range<-1>(t, rays, b, e, out);
+            const uint32_t shift = specialise ? t.brick_shift : 0xFFFFFFFFu;
+            if (node_mip) {
+                if (shift == 3u) trace_range<true, 3>(t, rays, b, e, viewing_distance, out);
+                else if (shift == 5u) trace_range<true, 5>(t, rays, b, e, viewing_distance, out);
+                else trace_range<true, -1>(t, rays, b, e, viewing_distance, out);
+            } else {
+                if (shift == 3u) trace_range<false, 3>(t, rays, b, e, viewing_distance, out);
+                else if (shift == 5u) trace_range<false, 5>(t, rays, b, e, viewing_distance, out);
+                else trace_range<false, -1>(t, rays, b, e, viewing_distance, out);
+            }
         });
     }
     for (auto& th : pool) th.join();

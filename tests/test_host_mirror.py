@@ -40,7 +40,7 @@ def build_mirror(name: str, defines=()):
         assert res.returncode == 0, res.stderr[-3000:]
     L = C.CDLL(str(lib))
     L.svx_host_mirror_get_by_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
-                                              C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+                                              C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_float]
     L.svx_host_mirror_get_by_rays.restype = C.c_int
     return L
 
@@ -62,16 +62,19 @@ def bits(a):
     return np.where(np.isnan(a), np.uint32(0x7FC00000), a.view(np.uint32))  # NaNs compare equal (0/0 normals at a cell centre)
 
 
-def mirror_rays(L, tree, rays, specialise=1):
-    """get_by_ray for every ray through the host build of the kernel code, on the host images of the render data"""
+def mirror_rays(L, tree, rays, specialise=1, viewing_distance=None):
+    """get_by_ray (viewing_distance None: the tree has no MIP maps) or get_by_ray_at_lod for every ray through the host build
+    of the kernel code, on the host images of the render data"""
     rec = tree.render_data_nodes()
+    mips = tree.render_data_mip_slots() if viewing_distance is not None else None
     voxels, occ = tree.render_data_bricks()
     lut = np.zeros(1024, dtype=np.uint32)
     assert S.lib().svx_render_data_ray_lut(lut.ctypes.data_as(C.c_void_p)) == 0
     rays = np.ascontiguousarray(rays, dtype=np.float32)
     out = np.zeros(len(rays), dtype=HIT)
     rc = L.svx_host_mirror_get_by_rays(rec.ctypes.data, len(rec), voxels.ctypes.data, occ.ctypes.data, len(voxels), lut.ctypes.data,
-                                       tree.get_size(), tree.brick_dim(), specialise, rays.ctypes.data, len(rays), out.ctypes.data, 8)
+                                       tree.get_size(), tree.brick_dim(), specialise, rays.ctypes.data, len(rays), out.ctypes.data, 8,
+                                       mips.ctypes.data if mips is not None else None, float(viewing_distance or 0.0))
     assert rc == 0
     return out
 
@@ -167,3 +170,33 @@ def test_shared_reciprocal_option_keeps_every_bit(mirror_shared_rcp, name):
     tree, otree = scenes.build_tree(scene, S.Octree), scenes.build_tree(scene, O.OracleOctree)
     rays = random_rays(scene.tree_size, 20000, 1 + zlib.crc32(name.encode()) % 1000)
     assert_same_hits(mirror_rays(mirror_shared_rcp, tree, rays), otree.get_by_rays(rays))
+
+
+F32_MAX = 3.4028234663852886e38
+LOD_SCENES = {
+    "cpu_render_64_8": lambda: scenes.cpu_render_scene(64, 8),
+    "cpu_render_32_1": lambda: scenes.cpu_render_scene(32, 1),
+    "dot_cube_128_32": lambda: scenes.dot_cube_scene(128, 32),
+    "colonnade_256_8": scenes.colonnade_scene,
+    "terrain_256_8_shell": lambda: scenes.terrain_scene(256, 8, 4321, 1, shell=3),  # deeper than the 4-entry ring stack
+}
+
+
+@pytest.mark.parametrize("name", list(LOD_SCENES))
+def test_level_of_detail_branch_bit_exact(mirror, name):
+    """get_by_ray_at_lod (raytracing_on_cpu.rs:325-386: the node's MIP brick answers when the node is far enough away) through
+    traverse<LOD = true>: the drifting mip_level, the bracketing pre-test of the LOD condition, the crawl fast-forward under
+    LOD - for viewing distances on both sides of every decision, and the degenerate ones."""
+    scene = LOD_SCENES[name]()
+    tree, otree = scenes.build_tree(scene, S.Octree), scenes.build_tree(scene, O.OracleOctree)
+    tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
+    otree.switch_albedo_mip_maps(True)
+    assert tree.albedo_mip_map_resampling_strategy().mip_hash() == otree.mip_hash()
+    rays = random_rays(scene.tree_size, 6000, 3 + zlib.crc32(name.encode()) % 1000)
+    probes = 0
+    for vd in (F32_MAX, 1000.0, 50.0, 3.0, 0.5, 0.0, -1.0, float("inf"), float("nan")):
+        want = otree.get_by_rays_at_lod(rays, vd)
+        assert_same_hits(mirror_rays(mirror, tree, rays, viewing_distance=vd), want)
+        probes += int(want["hit"].sum())
+    assert probes > 1000
+    assert_same_hits(mirror_rays(mirror, tree, rays[:2000], specialise=0, viewing_distance=50.0), otree.get_by_rays_at_lod(rays[:2000], 50.0))
