@@ -2,9 +2,11 @@
 """Randomised GPU-vs-oracle parity soak (GPU box): random trees (sizes, brick dims, edit mixes incl. insert_at_lod and
 clear), random rays (outside / inside / axis-parallel / grazing), every output field compared bit for bit.
 
-    python tools/fuzz_parity.py [--seconds 120] [--seed 0] [--mips]
+    python tools/fuzz_parity.py [--seconds 120] [--seed 0] [--mips] [--host-mirror]
 --mips: every tree gets MIP maps (random strategy, switched on before, midway or after the edits) and the rays are
 queried through get_by_ray_at_lod at random viewing distances (src/raytracing/raytracing_on_cpu.rs:325).
+--host-mirror: no GPU - the rays go through the host build of the kernels' source (tests/host_mirror: traverse.cuh compiled by
+g++) instead of the device; checks the logic of the GPU path, not what nvcc / ptxas make of it.
 Writes gpurun_out/fuzz_parity.json. Exit code 1 on the first mismatch (the failing case is printed).
 """
 import argparse
@@ -96,7 +98,13 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--rays", type=int, default=20000)
     ap.add_argument("--mips", action="store_true")
+    ap.add_argument("--host-mirror", action="store_true")
     args = ap.parse_args()
+    mirror = None
+    if args.host_mirror:
+        import test_host_mirror as HM
+
+        mirror = HM.build_mirror("host_mirror")
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
     cases = rays_total = hits_total = mip_probes_total = 0
@@ -137,12 +145,20 @@ def main():
         if a.structure_hash() != b.structure_hash():
             print("TREE SHAPE MISMATCH", size, dim, ops[:20])
             return 1
-        host = S.OctreeGPUHost(b.tree)
+        host = None if mirror else S.OctreeGPUHost(b.tree)
         for vd in vds:
             rays = random_rays(rng, size, args.rays)
-            g = host.get_by_rays(rays, vd)
             o = a.get_by_rays_at_lod(rays, vd)
-            ok = (np.array_equal(g["hit"], o["hit"]) and np.array_equal(g["palette_value"], o["palette_value"])
+            if mirror:  # the host build of the kernel code; it returns the palette value, not the resolved entry
+                m = HM.mirror_rays(mirror, b.tree, rays, specialise=int(rng.integers(0, 2)), viewing_distance=vd if args.mips else None)
+                g = np.zeros(len(rays), dtype=o.dtype)
+                for k in ("rgba", "data", "entry_kind"):
+                    g[k] = o[k]
+                g["hit"], g["palette_value"] = m["hit"], m["palette_value"]
+                g["impact_point"], g["normal"], g["distance"] = m["impact_point"], m["normal"], m["distance"]
+            else:
+                g = host.get_by_rays(rays, vd)
+            ok = (np.array_equal(g["hit"] != 0, o["hit"] != 0) and np.array_equal(g["palette_value"], o["palette_value"])
                   and np.array_equal(g["rgba"], o["rgba"]) and np.array_equal(g["data"], o["data"])
                   and np.array_equal(bits(g["impact_point"]), bits(o["impact_point"]))
                   and np.array_equal(bits(g["normal"]), bits(o["normal"])) and np.array_equal(bits(g["distance"]), bits(o["distance"])))
@@ -168,10 +184,10 @@ def main():
             mip_probes_total += int(o["mip_probes"].sum())
         cases += 1
     out = {"seed": args.seed, "seconds": round(time.time() - t0, 1), "random_trees": cases, "rays": rays_total, "hits": hits_total,
-           "mips": bool(args.mips), "mip_probes": mip_probes_total,
+           "mips": bool(args.mips), "mip_probes": mip_probes_total, "through": "host mirror (CPU)" if mirror else "GPU",
            "result": "every field bit-identical to the CPU oracle"}
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / f"fuzz_parity_{'mips_' if args.mips else ''}seed{args.seed}.json").write_text(json.dumps(out))
+    (ROOT / "gpurun_out" / f"fuzz_parity_{'host_mirror_' if mirror else ''}{'mips_' if args.mips else ''}seed{args.seed}.json").write_text(json.dumps(out))
     print(json.dumps(out))
     return 0
 
