@@ -99,12 +99,14 @@ def main():
     ap.add_argument("--rays", type=int, default=20000)
     ap.add_argument("--mips", action="store_true")
     ap.add_argument("--host-mirror", action="store_true")
+    ap.add_argument("--mirror-define", action="append", default=[], help="with --host-mirror: build the mirror with -D<this> (e.g. SVX_SHARED_RCP=1)")
     args = ap.parse_args()
     mirror = None
     if args.host_mirror:
         import test_host_mirror as HM
 
-        mirror = HM.build_mirror("host_mirror")
+        tag = "".join(c if c.isalnum() else "_" for c in "_".join(args.mirror_define))
+        mirror = HM.build_mirror("host_mirror" + ("_" + tag if tag else ""), args.mirror_define)
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
     cases = rays_total = hits_total = mip_probes_total = 0
@@ -184,7 +186,7 @@ def main():
             mip_probes_total += int(o["mip_probes"].sum())
         cases += 1
     out = {"seed": args.seed, "seconds": round(time.time() - t0, 1), "random_trees": cases, "rays": rays_total, "hits": hits_total,
-           "mips": bool(args.mips), "mip_probes": mip_probes_total, "through": "host mirror (CPU)" if mirror else "GPU",
+           "mips": bool(args.mips), "mip_probes": mip_probes_total, "through": ("host mirror (CPU)" + (" built with " + " ".join(args.mirror_define) if args.mirror_define else "")) if mirror else "GPU",
            "result": "every field bit-identical to the CPU oracle"}
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / f"fuzz_parity_{'host_mirror_' if mirror else ''}{'mips_' if args.mips else ''}seed{args.seed}.json").write_text(json.dumps(out))
