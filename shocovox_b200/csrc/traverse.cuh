@@ -15,6 +15,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <cuda_runtime.h>
 // SVX_HOST_MIRROR: this header compiled by the HOST compiler in tests/host_mirror (test infrastructure, never part of the
 // library): the PTX fragments below get plain C++ equivalents so that the kernels' logic - the transformed arithmetic,
@@ -137,6 +138,15 @@ struct RayConst {
 // kinds of lanes converge in the walk); 0: one instantiation per kind
 #ifndef SVX_SINGLE_PROBE_SITE
 #define SVX_SINGLE_PROBE_SITE 1
+#endif
+// EXPERIMENTAL, off by default: the voxel step measures from the FAR plane of the current cell, `p - (corner + off)`, one packed
+// subtraction instead of two, whenever the walk is entered with p inside the brick (up to a quarter voxel). `p - corner`
+// is then exact on every step - corner is a multiple of unit, p lies within the cell up to a few ulp because every step
+// re-targets a plane of the current cell, so corner / 2 <= p <= 2 corner (Sterbenz) or corner = 0 - and
+// RN((p - corner) - off) = RN(p - (corner + off)) with corner + off exact (small integers). A walk entered from further
+// away (possible only after a MIP miss) keeps the two-subtraction form.
+#ifndef SVX_FAR_PLANE_DDA
+#define SVX_FAR_PLANE_DDA 0
 #endif
 #ifndef SVX_BRICK_WORD_ALWAYS
 #define SVX_BRICK_WORD_ALWAYS 1
@@ -386,6 +396,75 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
 #if !SVX_BRICK_WORD_ALWAYS
     uint32_t nword_index = 0u;  // no complemented word index of a brick is 0 (their upper bits are set)
 #endif
+#if SVX_FAR_PLANE_DDA
+    // entered inside the brick (the unclamped cell coordinates are within a quarter voxel of it)? NaN fails
+    const float vx = (px - bx) * to_cells, vy = (py - by) * to_cells, vz = (pz - bz) * to_cells;
+    const bool inside = vx >= -0.25f && vy >= -0.25f && vz >= -0.25f && vx <= fdim + 0.25f && vy <= fdim + 0.25f && vz <= fdim + 0.25f;
+    float ex_ = ex, ey_ = ey, ez_ = ez;
+    if (inside) {  // corners and exit planes become far planes: + off (exact, small integers)
+        float ox_, oy_;
+        unpack2(offxy, ox_, oy_);
+        cx = cx + ox_; cy = cy + oy_; cz = cz + offz;
+        ex_ = ex + ox_; ey_ = ey + oy_; ez_ = ez + offz;
+    }
+    uint32_t nflat = 0u;
+    auto walk = [&](auto far) {
+        constexpr bool FAR = decltype(far)::value;
+        const float ex = ex_, ey = ey_, ez = ez_;
+    for (;;) {
+            nflat = mirrored ^ nflip;
+    #if SVX_BRICK_WORD_ALWAYS
+            // one L1-resident load per step instead of "same word as before?" bookkeeping: fewer issued instructions
+            word = __ldg(word_address(bits, (nflat >> 5) ^ 0x07FFFFFFu));
+    #else
+            if ((nflat >> 5) != nword_index) {
+                nword_index = nflat >> 5;
+                word = __ldg(word_address(bits, nword_index ^ 0x07FFFFFFu));
+            }
+    #endif
+            if ((int)(word << (nflat & 31u)) < 0) break;
+            float tx, ty;
+    #if SVX_FAR_PLANE_DDA
+            float tz;
+            if constexpr (FAR) {  // cx, cy, cz are the far planes here
+                unpack2(mul2(sub2(pxy, pack2(cx, cy)), sfxy), tx, ty);
+                tz = (pz - cz) * r.sfz;
+            } else {
+                unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
+                tz = ((pz - cz) - offz) * r.sfz;
+            }
+    #else
+            unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
+            const float tz = ((pz - cz) - offz) * r.sfz;
+    #endif
+            const float d_x = fabsf(tx), d_y = fabsf(ty), d_z = fabsf(tz);
+            const float m = fminf(fminf(d_x, d_y), d_z);
+            float mx, my, qx, qy;
+            unpack2(mul2(dxy, pack2(m, m)), mx, my);
+            unpack2(pxy, qx, qy);
+            pxy = pack2(qx + mx, qy + my);
+            pz = pz + r.dz * m;
+            // `if (m == d) { mirrored += stride; corner += u; }` per axis, as predicated instructions
+    #ifndef SVX_HOST_MIRROR
+            asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
+                : "+r"(mirrored), "+f"(cx) : "f"(m), "f"(d_x), "r"(1u), "f"(ux));
+            asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
+                : "+r"(mirrored), "+f"(cy) : "f"(m), "f"(d_y), "r"(brick_dim_of<BS>(t)), "f"(uy));
+            asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
+                : "+r"(mirrored), "+f"(cz) : "f"(m), "f"(d_z), "r"(brick_dim_sq_of<BS>(t)), "f"(uz));
+    #else
+            if (m == d_x) { mirrored += 1u; cx = cx + ux; }
+            if (m == d_y) { mirrored += brick_dim_of<BS>(t); cy = cy + uy; }
+            if (m == d_z) { mirrored += brick_dim_sq_of<BS>(t); cz = cz + uz; }
+    #endif
+            if (cx == ex || cy == ey || cz == ez) break;
+        }
+    };
+    if (inside) walk(std::true_type{}); else walk(std::false_type{});
+    const float ex_final = ex_, ey_final = ey_, ez_final = ez_;
+    unpack2(pxy, px, py);
+    return (cx == ex_final || cy == ey_final || cz == ez_final) ? -1 : (int)~nflat;
+#else
     uint32_t nflat;
     for (;;) {
         nflat = mirrored ^ nflip;
@@ -400,8 +479,19 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
 #endif
         if ((int)(word << (nflat & 31u)) < 0) break;
         float tx, ty;
+#if SVX_FAR_PLANE_DDA
+        float tz;
+        if constexpr (FAR) {  // cx, cy, cz are the far planes here
+            unpack2(mul2(sub2(pxy, pack2(cx, cy)), sfxy), tx, ty);
+            tz = (pz - cz) * r.sfz;
+        } else {
+            unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
+            tz = ((pz - cz) - offz) * r.sfz;
+        }
+#else
         unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
         const float tz = ((pz - cz) - offz) * r.sfz;
+#endif
         const float d_x = fabsf(tx), d_y = fabsf(ty), d_z = fabsf(tz);
         const float m = fminf(fminf(d_x, d_y), d_z);
         float mx, my, qx, qy;
@@ -427,6 +517,7 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     unpack2(pxy, px, py);
     // the walk ended on a set bit (corners strictly inside the brick) or by leaving it (a corner on the first plane outside)
     return (cx == ex || cy == ey || cz == ez) ? -1 : (int)~nflat;
+#endif
 #else
     uint32_t word_index = 0xFFFFFFFFu;
     for (;;) {
