@@ -36,6 +36,7 @@ typedef enum svx_status {
     SVX_E_INVALID_ARGUMENT = 5,        /* null handle / bad enum / zero resolution */
     SVX_E_DECODE = 6,                  /* from_bytes / load: not a bencoded Octree (the reference panics, octree/mod.rs:147) */
     SVX_E_IO = 7,                      /* save / load: std::io::Error */
+    SVX_E_TIMEOUT = 8,                 /* multi-GPU gather: a member did not deliver its share of the frame in time */
     SVX_E_CUDA = -1,                   /* CUDA runtime error (svx_last_error_message has the text) */
     SVX_E_OUT_OF_MEMORY = -2
 } svx_status;
@@ -89,9 +90,29 @@ typedef struct svx_viewport {
  * (examples/dot_cube.rs:209, sponza.rs:179). The view takes it as a mode. */
 typedef enum svx_glass_mode { SVX_GLASS_AT_FOV = 0, SVX_GLASS_AT_FRUSTUM_Z = 1 } svx_glass_mode;
 
+/* What the GPUs of a tile-sharded frame send to the GPU that assembles it (svx_view_gather_*, svx_multi_*) */
+typedef enum svx_wire_format {
+    SVX_WIRE_THREE_PLANES = 0, /* hit id, albedo and distance: 12 bytes per pixel cross NVLink */
+    SVX_WIRE_ID_DISTANCE = 1   /* hit id and distance, 8 bytes per pixel; the assembling GPU resolves albedo =
+                                  palette[hit_id & 0xFFFF] for the received rows (same tree, same palette: same bytes) */
+} svx_wire_format;
+
+/* Everything another process needs to render into a root view's framebuffer; plain bytes, ship them any way you like */
+typedef struct svx_gather_handle {
+    uint8_t ipc[64];         /* cudaIpcMemHandle_t of the root's frame allocation (three planes + completion flags) */
+    uint32_t width, height;  /* the root's resolution: a joining view must have the same */
+    uint32_t world, rows_per_band;
+    int32_t wire;            /* svx_wire_format */
+    int32_t device;          /* CUDA device ordinal of the root */
+    uint64_t plane_bytes;    /* distance between the planes inside the allocation */
+    uint64_t generation;     /* changes when the root reallocates its frame */
+    uint8_t reserved[24];
+} svx_gather_handle;
+
 typedef struct svx_octree svx_octree;     /* Octree<u32>,    src/octree/types.rs:169-207      */
 typedef struct svx_gpu_host svx_gpu_host; /* OctreeGPUHost,  src/raytracing/bevy/types.rs:80-87 */
 typedef struct svx_view svx_view;         /* OctreeGPUView,  src/raytracing/bevy/types.rs:92-130 */
+typedef struct svx_multi svx_multi;       /* one OctreeGPUHost + OctreeGPUView per GPU of this process, rendering one frame together */
 
 /* Device-resident frame produced by svx_view_render: SoA, image order (row 0 = top, pixel (x, y) of the
  * reference's caller loop lands in row h-1-y, examples/cpu_render.rs:106). Pointers are CUDA device pointers
@@ -298,16 +319,47 @@ SVX_API int32_t svx_view_set_schedule(svx_view* view, int32_t persistent);
 SVX_API int32_t svx_view_set_compact_rows(svx_view* view, int32_t enabled);
 /* Device pointers of the view's framebuffer planes (valid until set_resolution / free) */
 SVX_API int32_t svx_view_frame_pointers(const svx_view* view, void** hit_id, void** albedo, void** distance);
-/* Fused gather over NVLink: export this view's framebuffer planes as three 64-byte CUDA IPC handles, and make another
- * view (in another process, on another GPU) store its shard straight into them from inside the traversal kernel.
- * Passing null detaches. The exporting view must outlive every importer. */
-SVX_API int32_t svx_view_export_frame_ipc(const svx_view* view, uint8_t* handles_3x64);
-SVX_API int32_t svx_view_set_peer_frame_ipc(svx_view* view, const uint8_t* handles_3x64);
+/* ---- Tile-sharded frames over several GPUs, one process per GPU ----------------------------------------------
+ * The reference renders on one device (no multi-GPU code); rays are independent and the tree is read-only,
+ * so `world` GPUs, each with its own replica of the tree (its own svx_gpu_host), render the rows
+ * (row / rows_per_band) % world == rank of ONE frame. The gather is fused into the viewport kernel: a peer's kernel
+ * stores its pixels straight into the root view's framebuffer over NVLink (CUDA IPC mapping) and the hand-over runs on
+ * device-side flags - no host barrier and no collective per frame. Protocol of one frame (every member calls
+ * svx_view_render once, in any order, from its own process):
+ *   root : viewport kernel (publishes "go" for this frame, renders rank 0's rows) + a kernel that waits until every
+ *          peer's rows have arrived (and, with SVX_WIRE_ID_DISTANCE, resolves their albedo)
+ *   peer : a kernel that waits for "go" (so a frame the root's consumer still reads is never overwritten) + viewport
+ *          kernel storing into the root's planes; its last CTA publishes "done"
+ * After the root's stream has passed the render call the root's framebuffer holds the complete frame, byte-identical to
+ * a single-GPU render. A member that does not show up within SVX_GATHER_TIMEOUT_MS (default 5000) makes the waiting
+ * side's next synchronising call return SVX_E_TIMEOUT instead of hanging the device.
+ *
+ * svx_view_gather_open : makes `root` rank 0 of a `world`-way gather and (out != NULL) fills the handle to ship to the
+ *                        other processes. Idempotent for the same shape. The root must outlive its peers' membership.
+ * svx_view_gather_join : another process, `rank` in 1..world-1, same resolution as the root.
+ * svx_view_gather_join_local : the same for a view of THIS process (any device with peer access to the root's, or the
+ *                        root's own device), where CUDA IPC cannot be used.
+ * svx_view_gather_close: leaves the gather (root or peer); the view renders whole frames into its own framebuffer again.
+ * While a view is a member, set_resolution / set_shard / compact rows / the shaded plane / the pipelined read-back
+ * are refused. */
+SVX_API int32_t svx_view_gather_open(svx_view* root, uint32_t world, uint32_t rows_per_band, int32_t wire /* svx_wire_format */,
+                                     svx_gather_handle* out);
+SVX_API int32_t svx_view_gather_join(svx_view* view, uint32_t rank, const svx_gather_handle* handle);
+SVX_API int32_t svx_view_gather_join_local(svx_view* view, uint32_t rank, svx_view* root);
+SVX_API int32_t svx_view_gather_close(svx_view* view);
+/* role: 0 none, 1 root, 2 peer; frames = render calls since the gather was opened / joined. Any output may be NULL. */
+SVX_API int32_t svx_view_gather_info(const svx_view* view, int32_t* role, uint32_t* rank, uint32_t* world, uint32_t* frames);
 /* One frame: in-kernel ray generation (examples/cpu_render.rs:78-114) + get_by_ray per pixel + framebuffer write.
  * Asynchronous on the view's stream unless `out` is non-null, in which case the call synchronises and fills it. */
 SVX_API int32_t svx_view_render(svx_view* view, svx_frame* out);
-/* Same frame, delivered into HOST buffers (any may be null): includes the device->host copies. */
+/* Same frame, delivered into HOST buffers (any may be null): includes the device->host copies. The buffers are
+ * full-frame planes [h*w]; a view sharded with svx_view_set_shard copies only the rows it owns into them (strided
+ * copies of whole bands), so several GPUs - or processes sharing the host planes - assemble one frame in host memory,
+ * each over its own PCIe link. Passing albedo = NULL ships 8 bytes per pixel: albedo is palette[hit_id & 0xFFFF]. */
 SVX_API int32_t svx_view_render_to_host(svx_view* view, uint32_t* hit_id, uint32_t* albedo, float* distance);
+/* The framebuffer as it stands, without rendering: waits for the view's stream, then copies whole planes (any may be
+ * null). On the root of a gather this is the assembled frame of the last svx_view_render. */
+SVX_API int32_t svx_view_read_frame(svx_view* view, uint32_t* hit_id, uint32_t* albedo, float* distance);
 /* Pipelined variant: returns as soon as the kernel and the copies are queued. Frames alternate between two framebuffer
  * slots; the copies run on a second stream, so frame i's device->host copy overlaps frame i+1's kernel. At most two
  * frames are in flight (a third submission first waits for the oldest). The host buffers must stay valid, and are not
@@ -333,6 +385,31 @@ SVX_API int32_t svx_view_timer_stop(svx_view* view, float* elapsed_ms);
 SVX_API int32_t svx_view_flush_l2(svx_view* view);
 /* Number of kernel launches this view/host has issued since creation (bench.py's gpu_launches claim) */
 SVX_API uint64_t svx_view_launch_count(const svx_view* view);
+
+/* ---- svx_multi: one process drives several GPUs --------------------------------------------------------- */
+/* One replica of the tree (OctreeGPUHost) and one view per listed device; devices[0] assembles the frame. The same
+ * device-side protocol as svx_view_gather_* with peer access instead of CUDA IPC. The octree must outlive the handle.
+ * (A device may be listed more than once: each entry gets its own replica and stream.) */
+SVX_API int32_t svx_multi_create(const svx_octree* tree, const int32_t* devices, uint32_t n_devices, const svx_viewport* viewport,
+                                 uint32_t width, uint32_t height, uint32_t rows_per_band, int32_t wire /* svx_wire_format */,
+                                 svx_multi** out);
+SVX_API void svx_multi_free(svx_multi* multi);
+SVX_API uint32_t svx_multi_device_count(const svx_multi* multi);
+SVX_API svx_view* svx_multi_view(svx_multi* multi, uint32_t i); /* the gather member on devices[i] (owned by `multi`) */
+SVX_API int32_t svx_multi_set_viewport(svx_multi* multi, const svx_viewport* viewport);
+SVX_API int32_t svx_multi_set_glass_mode(svx_multi* multi, int32_t mode);
+SVX_API int32_t svx_multi_set_viewing_distance(svx_multi* multi, float viewing_distance);
+SVX_API int32_t svx_multi_reload(svx_multi* multi); /* svx_gpu_host_reload of every replica after the tree was edited */
+/* One frame, tile-sharded over all devices, assembled in devices[0]'s framebuffer. Asynchronous unless `out` is given
+ * (then: synchronises devices[0], kernel_ms = the root's viewport kernel plus its wait for the slowest peer). */
+SVX_API int32_t svx_multi_render(svx_multi* multi, svx_frame* out);
+/* The same frame into HOST planes [h*w] (any may be NULL): every GPU copies the rows it rendered over its own PCIe link,
+ * no NVLink hop. Use page-locked buffers (cudaHostRegister with cudaHostRegisterPortable) for overlapping copies. */
+SVX_API int32_t svx_multi_render_to_host(svx_multi* multi, uint32_t* hit_id, uint32_t* albedo, float* distance);
+/* Batch mode (pose-sharded): pose k is rendered by device k % n into host planes [n_poses][h*w]; nothing is exchanged
+ * between the GPUs. kernel_ms_total (optional) = summed kernel time over all devices. */
+SVX_API int32_t svx_multi_render_poses(svx_multi* multi, const svx_viewport* poses, uint32_t n_poses, uint32_t* hit_id,
+                                       uint32_t* albedo, float* distance, float* kernel_ms_total);
 
 #ifdef __cplusplus
 }

@@ -6,6 +6,7 @@ the host-side mirror of the reference crate's API (api.py) and the synthetic ben
 from .api import (  # noqa: F401
     Albedo, Octree, OctreeEntry, OctreeError, OctreeGPUHost, OctreeGPUView, Ray, RayHit, Viewport,
     GLASS_AT_FOV, GLASS_AT_FRUSTUM_Z, MISS, cuda_device_count, entry, lib, library_path, normalized,
+    MultiGPU, WIRE_THREE_PLANES, WIRE_ID_DISTANCE, E_TIMEOUT,
     StrategyUpdater, F32_MAX, MIP_BOX_FILTER, MIP_POINT_FILTER, MIP_POINT_FILTER_BD, MIP_POSTERIZE, MIP_POSTERIZE_BD,
 )
 

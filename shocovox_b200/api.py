@@ -151,8 +151,11 @@ EXPORTS = [
     "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_last_upload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
     "svx_view_set_glass_mode", "svx_view_set_resolution", "svx_view_resolution", "svx_view_set_shard",
-    "svx_view_set_schedule", "svx_view_set_compact_rows", "svx_view_frame_pointers", "svx_view_export_frame_ipc", "svx_view_set_peer_frame_ipc",
-    "svx_view_render", "svx_view_render_to_host", "svx_view_render_to_host_async", "svx_view_wait_host", "svx_view_render_batch", "svx_view_cuda_stream", "svx_view_device",
+    "svx_view_set_schedule", "svx_view_set_compact_rows", "svx_view_frame_pointers", "svx_view_gather_open", "svx_view_gather_join", "svx_view_gather_join_local",
+    "svx_view_gather_close", "svx_view_gather_info",
+    "svx_multi_create", "svx_multi_free", "svx_multi_device_count", "svx_multi_view", "svx_multi_set_viewport", "svx_multi_set_glass_mode",
+    "svx_multi_set_viewing_distance", "svx_multi_reload", "svx_multi_render", "svx_multi_render_to_host", "svx_multi_render_poses",
+    "svx_view_render", "svx_view_read_frame", "svx_view_render_to_host", "svx_view_render_to_host_async", "svx_view_wait_host", "svx_view_render_batch", "svx_view_cuda_stream", "svx_view_device",
     "svx_view_synchronize", "svx_view_timer_start", "svx_view_timer_stop", "svx_view_flush_l2", "svx_view_launch_count",
 ]
 
@@ -251,10 +254,28 @@ def lib() -> C.CDLL:
     L.svx_view_set_schedule.argtypes = [vp, i32]
     L.svx_view_set_compact_rows.argtypes = [vp, i32]
     L.svx_view_frame_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
-    L.svx_view_export_frame_ipc.argtypes = [vp, vp]
-    L.svx_view_set_peer_frame_ipc.argtypes = [vp, vp]
+    L.svx_view_gather_open.argtypes = [vp, u32, u32, i32, vp]
+    L.svx_view_gather_join.argtypes = [vp, u32, vp]
+    L.svx_view_gather_join_local.argtypes = [vp, u32, vp]
+    L.svx_view_gather_close.argtypes = [vp]
+    L.svx_view_gather_info.argtypes = [vp, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+    L.svx_multi_create.argtypes = [vp, C.POINTER(i32), u32, C.POINTER(_Viewport), u32, u32, u32, i32, C.POINTER(vp)]
+    L.svx_multi_free.argtypes = [vp]
+    L.svx_multi_free.restype = None
+    L.svx_multi_device_count.argtypes = [vp]
+    L.svx_multi_device_count.restype = u32
+    L.svx_multi_view.argtypes = [vp, u32]
+    L.svx_multi_view.restype = vp
+    L.svx_multi_set_viewport.argtypes = [vp, C.POINTER(_Viewport)]
+    L.svx_multi_set_glass_mode.argtypes = [vp, i32]
+    L.svx_multi_set_viewing_distance.argtypes = [vp, f32]
+    L.svx_multi_reload.argtypes = [vp]
+    L.svx_multi_render.argtypes = [vp, C.POINTER(_Frame)]
+    L.svx_multi_render_to_host.argtypes = [vp, vp, vp, vp]
+    L.svx_multi_render_poses.argtypes = [vp, vp, u32, vp, vp, vp, C.POINTER(C.c_float)]
     L.svx_view_render.argtypes = [vp, C.POINTER(_Frame)]
     L.svx_view_render_to_host.argtypes = [vp, vp, vp, vp]
+    L.svx_view_read_frame.argtypes = [vp, vp, vp, vp]
     L.svx_view_render_to_host_async.argtypes = [vp, vp, vp, vp]
     L.svx_view_wait_host.argtypes = [vp, u32, C.POINTER(C.c_float)]
     L.svx_view_render_batch.argtypes = [vp, vp, u32, vp, vp, vp, C.POINTER(C.c_float)]
@@ -269,6 +290,11 @@ def lib() -> C.CDLL:
     L.svx_view_launch_count.restype = u64
     _lib = L
     return L
+
+
+WIRE_THREE_PLANES, WIRE_ID_DISTANCE = 0, 1  # svx_wire_format
+GATHER_HANDLE_BYTES = 128
+E_TIMEOUT = 8
 
 
 def _check(status: int):
@@ -755,17 +781,37 @@ class OctreeGPUView:
         _check(lib().svx_view_frame_pointers(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return int(a.value or 0), int(b.value or 0), int(c.value or 0)
 
-    def export_frame_ipc(self) -> bytes:
-        buf = (C.c_uint8 * 192)()
-        _check(lib().svx_view_export_frame_ipc(self._h, buf))
+    # ---- tile-sharded frames, one process per GPU (svx_view_gather_*) ------------------------------------------------
+    def gather_open(self, world: int, rows_per_band: int = 8, wire: int = WIRE_THREE_PLANES, export: bool = True) -> Optional[bytes]:
+        """Makes this view rank 0 (the assembling GPU) of a `world`-way gather; returns the 128-byte handle to ship to
+        the other processes (None with export=False: local peers only)."""
+        if not export:
+            _check(lib().svx_view_gather_open(self._h, int(world), int(rows_per_band), int(wire), None))
+            return None
+        buf = (C.c_uint8 * GATHER_HANDLE_BYTES)()
+        _check(lib().svx_view_gather_open(self._h, int(world), int(rows_per_band), int(wire), buf))
         return bytes(buf)
 
-    def set_peer_frame_ipc(self, handles: Optional[bytes]):
-        if handles is None:
-            _check(lib().svx_view_set_peer_frame_ipc(self._h, None))
-            return
-        buf = (C.c_uint8 * 192).from_buffer_copy(handles)
-        _check(lib().svx_view_set_peer_frame_ipc(self._h, buf))
+    def gather_join(self, rank: int, handle: bytes):
+        """Another process' view becomes rank `rank` (1..world-1): its kernel stores into the root's framebuffer."""
+        if len(handle) != GATHER_HANDLE_BYTES:
+            raise OctreeError(E_INVALID_ARGUMENT, "a gather handle is %d bytes" % GATHER_HANDLE_BYTES)
+        buf = (C.c_uint8 * GATHER_HANDLE_BYTES).from_buffer_copy(handle)
+        _check(lib().svx_view_gather_join(self._h, int(rank), buf))
+
+    def gather_join_local(self, rank: int, root: "OctreeGPUView"):
+        """The same for a root view of this process (peer access or the same device instead of CUDA IPC)."""
+        _check(lib().svx_view_gather_join_local(self._h, int(rank), root._h))
+        self._gather_root = root  # the root must outlive this membership
+
+    def gather_close(self):
+        _check(lib().svx_view_gather_close(self._h))
+        self._gather_root = None
+
+    def gather_info(self) -> dict:
+        role, rank, world, frames = C.c_int32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().svx_view_gather_info(self._h, C.byref(role), C.byref(rank), C.byref(world), C.byref(frames)))
+        return {"role": ("none", "root", "peer")[role.value], "rank": int(rank.value), "world": int(world.value), "frames": int(frames.value)}
 
     def render(self, sync: bool = True) -> Optional[dict]:
         """Renders one frame on the device. With sync, returns device pointers and the kernel's CUDA-event time."""
@@ -789,6 +835,16 @@ class OctreeGPUView:
             distance = np.empty((h, w), dtype=np.float32)
         ptr = lambda a: None if a is None else a.ctypes.data
         _check(lib().svx_view_render_to_host(self._h, ptr(hit_id), ptr(albedo), ptr(distance)))
+        return {"hit_id": hit_id, "albedo": albedo, "distance": distance}
+
+    def read_frame(self, want=("hit_id", "albedo", "distance")) -> dict:
+        """The framebuffer as it stands (no render): on the root of a gather, the assembled frame of the last render."""
+        w, h = self.resolution()
+        hit_id = np.empty((h, w), dtype=np.uint32) if "hit_id" in want else None
+        albedo = np.empty((h, w), dtype=np.uint32) if "albedo" in want else None
+        distance = np.empty((h, w), dtype=np.float32) if "distance" in want else None
+        ptr = lambda a: None if a is None else a.ctypes.data
+        _check(lib().svx_view_read_frame(self._h, ptr(hit_id), ptr(albedo), ptr(distance)))
         return {"hit_id": hit_id, "albedo": albedo, "distance": distance}
 
     def render_to_host_ptr(self, hit_id_ptr: int, albedo_ptr: int, distance_ptr: int):
@@ -840,3 +896,83 @@ class OctreeGPUView:
 
     def launch_count(self) -> int:
         return int(lib().svx_view_launch_count(self._h))
+
+
+class MultiGPU:
+    """svx_multi: one process drives several GPUs - one tree replica and one view per device, ONE frame per render call,
+    tile-sharded in row bands and assembled in devices[0]'s framebuffer by the viewport kernels themselves (peer stores +
+    device-side flags). The reference has no multi-GPU path; the contract is byte-equality with the single-GPU frame."""
+
+    def __init__(self, tree: Octree, devices: Sequence[int], viewport: Viewport, resolution: Sequence[int], rows_per_band: int = 8,
+                 wire: int = WIRE_THREE_PLANES):
+        self.tree = tree
+        self.devices = [int(d) for d in devices]
+        self.resolution = [int(resolution[0]), int(resolution[1])]
+        self._h = C.c_void_p()
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        vp = viewport._c()
+        _check(lib().svx_multi_create(tree.handle, arr, len(self.devices), C.byref(vp), self.resolution[0], self.resolution[1],
+                                      int(rows_per_band), int(wire), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
+            _lib.svx_multi_free(self._h)
+            self._h = C.c_void_p()
+
+    def set_viewport(self, viewport: Viewport):
+        vp = viewport._c()
+        _check(lib().svx_multi_set_viewport(self._h, C.byref(vp)))
+
+    def set_glass_mode(self, mode: int):
+        _check(lib().svx_multi_set_glass_mode(self._h, int(mode)))
+
+    def set_viewing_distance(self, viewing_distance: float):
+        _check(lib().svx_multi_set_viewing_distance(self._h, float(viewing_distance)))
+
+    def reload(self):
+        _check(lib().svx_multi_reload(self._h))
+
+    def render(self, sync: bool = True) -> Optional[dict]:
+        if not sync:
+            _check(lib().svx_multi_render(self._h, None))
+            return None
+        f = _Frame()
+        _check(lib().svx_multi_render(self._h, C.byref(f)))
+        return {"width": f.width, "height": f.height, "hit_id": f.hit_id, "albedo": f.albedo, "distance": f.distance,
+                "kernel_ms": float(f.kernel_ms)}
+
+    def read_root_frame(self) -> dict:
+        """Renders one frame through the gather and copies the assembled planes from devices[0]."""
+        f = self.render(sync=True)
+        w, h = self.resolution
+        out = {"hit_id": np.empty((h, w), dtype=np.uint32), "albedo": np.empty((h, w), dtype=np.uint32),
+               "distance": np.empty((h, w), dtype=np.float32), "kernel_ms": f["kernel_ms"]}
+        root = C.c_void_p(lib().svx_multi_view(self._h, 0))
+        _check(lib().svx_view_read_frame(root, out["hit_id"].ctypes.data, out["albedo"].ctypes.data, out["distance"].ctypes.data))
+        return out
+
+    def render_to_host(self, want=("hit_id", "albedo", "distance")) -> dict:
+        w, h = self.resolution
+        hit_id = np.empty((h, w), dtype=np.uint32) if "hit_id" in want else None
+        albedo = np.empty((h, w), dtype=np.uint32) if "albedo" in want else None
+        distance = np.empty((h, w), dtype=np.float32) if "distance" in want else None
+        ptr = lambda a: None if a is None else a.ctypes.data
+        _check(lib().svx_multi_render_to_host(self._h, ptr(hit_id), ptr(albedo), ptr(distance)))
+        return {"hit_id": hit_id, "albedo": albedo, "distance": distance}
+
+    def render_to_host_ptr(self, hit_id_ptr: int, albedo_ptr: int, distance_ptr: int):
+        _check(lib().svx_multi_render_to_host(self._h, hit_id_ptr or None, albedo_ptr or None, distance_ptr or None))
+
+    def render_poses(self, poses: Sequence[Viewport], want=("hit_id", "albedo", "distance")) -> dict:
+        w, h = self.resolution
+        n = len(poses)
+        arr = np.zeros(n, dtype=VIEWPORT_DTYPE)
+        for i, p in enumerate(poses):
+            arr[i] = (tuple(np.float32(p.origin)), tuple(np.float32(p.direction)), tuple(np.float32(p.frustum)), p.fov)
+        hit_id = np.empty((n, h, w), dtype=np.uint32) if "hit_id" in want else None
+        albedo = np.empty((n, h, w), dtype=np.uint32) if "albedo" in want else None
+        distance = np.empty((n, h, w), dtype=np.float32) if "distance" in want else None
+        ms = C.c_float()
+        ptr = lambda a: None if a is None else a.ctypes.data
+        _check(lib().svx_multi_render_poses(self._h, arr.ctypes.data, n, ptr(hit_id), ptr(albedo), ptr(distance), C.byref(ms)))
+        return {"hit_id": hit_id, "albedo": albedo, "distance": distance, "kernel_ms": float(ms.value)}

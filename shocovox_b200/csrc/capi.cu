@@ -11,10 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/shocovox_b200.h"
-#include "gpu_tree.hpp"
-#include "host_octree.hpp"
-#include "kernels.cuh"
+#include "capi_internal.hpp"
 
 using namespace svx;
 
@@ -23,9 +20,9 @@ using namespace svx;
 #endif
 
 namespace {
-
 thread_local std::string g_last_error;
-
+}
+namespace svx {
 int32_t fail(int32_t code, const std::string& msg) {
     g_last_error = msg;
     return code;
@@ -33,11 +30,9 @@ int32_t fail(int32_t code, const std::string& msg) {
 int32_t cuda_fail(cudaError_t e, const char* what) {
     return fail(SVX_E_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
-#define CUDA_TRY(expr)                                        \
-    do {                                                      \
-        cudaError_t e__ = (expr);                             \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
-    } while (0)
+}  // namespace svx
+
+namespace {
 
 // ---- the reference's tables, regenerated from their generator logic (reference src/spatial/lut.rs:12-152), used
 // ---- ONLY to validate the device closed forms once per process
@@ -132,84 +127,6 @@ inline Vec3 operator*(Vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 inline Vec3 operator/(Vec3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
 
 }  // namespace
-
-struct svx_gpu_host;
-struct svx_octree {
-    HostOctree* tree = nullptr;
-    // svx_octree_get_by_ray[_at_lod]: a device copy created on first use (device 0) and reloaded before every query
-    svx_gpu_host* ray_host = nullptr;
-    std::mutex ray_mu;
-};
-
-struct svx_gpu_host {
-    const svx_octree* octree = nullptr;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::mutex mu;
-    svx_gpu_stats stats{};
-    DeviceTree dev{};
-    void* d_node_rec = nullptr;  // 64-byte node records: head | 8 slots | bounds
-    void* d_node_mip = nullptr;
-    void* d_voxels = nullptr;
-    void* d_brick_bits = nullptr;
-    void* d_palette = nullptr;
-    void* d_ray_lut = nullptr;  // RAY_TO_NODE_OCCUPANCY_BITMASK_LUT as [dir][cell] {lo, hi}, regenerated from the generator logic
-    void* d_data_palette = nullptr;  // bit tables "colour shows" / "data carries", input of the occupancy-bit kernel
-    void* d_handles = nullptr;       // brick handles of the current upload, input of the occupancy-bit kernel
-    size_t data_palette_capacity = 0, handle_capacity = 0;
-    size_t node_capacity = 0;     // nodes the node_head / node_slot allocations hold
-    size_t palette_capacity = 0;  // colours the palette allocation holds
-    size_t brick_capacity = 0;    // bricks the voxels / brick_bits allocations hold
-    LaunchConfig cfg;
-    uint64_t launches = 0;
-    uint64_t uploaded_revision = ~0ull;
-    bool uploaded = false;
-    svx_upload_stats last_upload{};
-    // scratch for get_by_rays
-    float* d_rays = nullptr;
-    RayHitRecord* d_hits = nullptr;
-    uint64_t ray_capacity = 0;
-};
-
-struct svx_view {
-    svx_gpu_host* host = nullptr;
-    svx_viewport viewport{};
-    int32_t glass_mode = SVX_GLASS_AT_FOV;
-    float viewing_distance = 3.402823466e+38f;  // f32::MAX: Octree::get_by_ray (raytracing_on_cpu.rs:316-318)
-    uint32_t width = 0, height = 0;
-    uint32_t rank = 0, world = 1, band_rows = 8, compact = 0;
-    // peer framebuffers opened from CUDA IPC handles (fused gather: the kernel stores straight into another GPU)
-    void* peer_base[3] = {nullptr, nullptr, nullptr};
-    bool use_peer = false;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-    cudaEvent_t tm_start = nullptr, tm_stop = nullptr;
-    uint32_t* d_counters = nullptr;  // two ticket counters of the persistent schedule (ping-pong across launches)
-    uint32_t counter_slot = 0;
-    bool persistent = false;
-    void* d_flush = nullptr;
-    size_t flush_bytes = 0;
-    uint32_t* d_hit_id = nullptr;
-    uint32_t* d_albedo = nullptr;
-    float* d_distance = nullptr;
-    // optional shaded plane (svx_view_set_shading): the pixel of the reference's caller loops, single-buffered
-    uint32_t* d_shaded = nullptr;
-    bool shading = false;
-    float light[3] = {0.0f, 0.0f, 0.0f};
-    uint64_t launches = 0;
-    // Pipelined read-back (svx_view_render_to_host_async): two framebuffer slots (slot 0 = the planes above, slot 1 =
-    // alt_*), kernels on `stream`, device->host copies on `copy_stream`, so frame i's copy overlaps frame i+1's kernel.
-    cudaStream_t copy_stream = nullptr;
-    uint32_t* alt_hit_id = nullptr;
-    uint32_t* alt_albedo = nullptr;
-    float* alt_distance = nullptr;
-    cudaEvent_t slot_start[2] = {nullptr, nullptr}, slot_rendered[2] = {nullptr, nullptr}, slot_copied[2] = {nullptr, nullptr};
-    bool slot_busy[2] = {false, false};
-    uint64_t async_frames = 0;   // frames submitted through the pipelined path
-    float async_kernel_ms = 0.0f;  // summed kernel time of the pipelined frames retired so far
-    uint32_t target_slot = 0;    // which slot make_frame_constants points the kernel at
-    std::mutex mu;
-};
 
 namespace {
 
@@ -463,20 +380,29 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     f->viewing_distance = v->viewing_distance;
     f->shaded = v->shading ? v->d_shaded : nullptr;
     f->lx = v->light[0]; f->ly = v->light[1]; f->lz = v->light[2];
+    f->go_flag = f->done_flag = f->cta_counter = nullptr;
+    f->frame_seq = 0;
+    if (v->gather_role == GATHER_PEER) {
+        // the root's planes (same resolution, checked at join); 8-byte wire format: no albedo crosses NVLink
+        char* base = static_cast<char*>(v->peer_block);
+        f->hit_id = reinterpret_cast<uint32_t*>(base);
+        f->albedo = v->gather_wire == SVX_WIRE_ID_DISTANCE ? nullptr : reinterpret_cast<uint32_t*>(base + v->peer_plane_bytes);
+        f->distance = reinterpret_cast<float*>(base + 2 * v->peer_plane_bytes);
+        return;
+    }
     const bool alt = v->target_slot == 1;
-    f->hit_id = v->use_peer ? (uint32_t*)v->peer_base[0] : (alt ? v->alt_hit_id : v->d_hit_id);
-    f->albedo = v->use_peer ? (uint32_t*)v->peer_base[1] : (alt ? v->alt_albedo : v->d_albedo);
-    f->distance = v->use_peer ? (float*)v->peer_base[2] : (alt ? v->alt_distance : v->d_distance);
+    f->hit_id = alt ? v->alt_hit_id : v->d_hit_id;
+    f->albedo = alt ? v->alt_albedo : v->d_albedo;
+    f->distance = alt ? v->alt_distance : v->d_distance;
 }
 
 int32_t alloc_frame(svx_view* v) {
-    cudaFree(v->d_hit_id);
-    cudaFree(v->d_albedo);
-    cudaFree(v->d_distance);
+    cudaFree(v->frame_block);
     cudaFree(v->alt_hit_id);
     cudaFree(v->alt_albedo);
     cudaFree(v->alt_distance);
     cudaFree(v->d_shaded);
+    v->frame_block = nullptr;
     v->d_hit_id = v->d_albedo = v->alt_hit_id = v->alt_albedo = v->d_shaded = nullptr;
     v->d_distance = v->alt_distance = nullptr;
     const size_t n = (size_t)v->width * v->height;
@@ -484,16 +410,51 @@ int32_t alloc_frame(svx_view* v) {
         CUDA_TRY(cudaMalloc((void**)&v->d_shaded, n * 4));
         CUDA_TRY(cudaMemsetAsync(v->d_shaded, 0, n * 4, v->stream));
     }
-    CUDA_TRY(cudaMalloc((void**)&v->d_hit_id, n * 4));
-    CUDA_TRY(cudaMalloc((void**)&v->d_albedo, n * 4));
-    CUDA_TRY(cudaMalloc((void**)&v->d_distance, n * 4));
-    CUDA_TRY(cudaMemsetAsync(v->d_hit_id, 0xFF, n * 4, v->stream));
-    CUDA_TRY(cudaMemsetAsync(v->d_albedo, 0, n * 4, v->stream));
-    CUDA_TRY(cudaMemsetAsync(v->d_distance, 0, n * 4, v->stream));
+    // three planes and the gather flags in one allocation (one IPC handle exports all of it), planes 256-byte aligned
+    v->plane_bytes = (n * 4 + 255) & ~(size_t)255;
+    CUDA_TRY(cudaMalloc(&v->frame_block, 3 * v->plane_bytes + sizeof(GatherSync)));
+    v->frame_generation += 1;
+    char* base = static_cast<char*>(v->frame_block);
+    v->d_hit_id = reinterpret_cast<uint32_t*>(base);
+    v->d_albedo = reinterpret_cast<uint32_t*>(base + v->plane_bytes);
+    v->d_distance = reinterpret_cast<float*>(base + 2 * v->plane_bytes);
+    CUDA_TRY(cudaMemsetAsync(v->d_hit_id, 0xFF, v->plane_bytes, v->stream));
+    CUDA_TRY(cudaMemsetAsync(v->d_albedo, 0, 2 * v->plane_bytes + sizeof(GatherSync), v->stream));
     return SVX_OK;
 }
 
+}  // namespace
+
+namespace svx {
+
+// Rejects what would make every ray of a frame NaN (the reference debug-asserts `ray.is_valid()`,
+// spatial/raytracing/mod.rs:14-16, and hangs in release builds): non-finite fields, a zero direction, or a direction
+// parallel to the fixed up vector (0, 1, 0) - `up x direction` is the zero vector then and its normalisation 0 / 0.
+int32_t validate_viewport(const svx_viewport& vp) {
+    const float all[10] = {vp.origin[0], vp.origin[1], vp.origin[2], vp.direction[0], vp.direction[1], vp.direction[2],
+                           vp.frustum[0], vp.frustum[1], vp.frustum[2], vp.fov};
+    for (float x : all)
+        if (!std::isfinite(x)) return fail(SVX_E_INVALID_ARGUMENT, "viewport: non-finite field");
+    if (vp.direction[0] == 0.0f && vp.direction[2] == 0.0f)
+        return fail(SVX_E_INVALID_ARGUMENT, "viewport: the direction is zero or parallel to the up vector (0, 1, 0)");
+    const float clen = std::sqrt((vp.direction[2] * vp.direction[2]) + (vp.direction[0] * vp.direction[0]));
+    if (!(clen > 0.0f) || !std::isfinite(clen)) return fail(SVX_E_INVALID_ARGUMENT, "viewport: degenerate direction");
+    return SVX_OK;
+}
+
+int32_t check_view_error(svx_view* v) {
+    if (!v->h_error || *v->h_error == 0u) return SVX_OK;
+    const uint32_t code = *v->h_error;
+    *v->h_error = 0u;
+    if (code >= 0x100u)
+        return fail(SVX_E_TIMEOUT, "gather: rank " + std::to_string(code - 0x100u) + " never saw the root's go flag for this frame");
+    return fail(SVX_E_TIMEOUT, "gather: peer rank " + std::to_string(code - 1u) + " did not deliver its rows in time");
+}
+
+// One frame on the view's stream. A gather peer first waits (on the device) for the root's licence to overwrite the
+// shared framebuffer; a gather root follows its own rows with the kernel that waits for the peers' rows.
 int32_t render_locked(svx_view* v) {
+    std::shared_lock<std::shared_mutex> tree_lock(v->host->dev_mu);
     FrameParams f;
     make_frame_constants(v, &f);
     LaunchConfig cfg = v->host->cfg;
@@ -501,10 +462,76 @@ int32_t render_locked(svx_view* v) {
     cfg.tile_counters = v->d_counters;
     f.counter_slot = v->counter_slot;
     if (v->persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
+    if (v->gather_role == GATHER_PEER) {
+        v->frame_seq += 1;
+        GatherSync* sync = gather_sync_of(v->peer_block, v->peer_plane_bytes);
+        CUDA_TRY(launch_wait_flag(&sync->go, v->frame_seq, v->gather_timeout_ns, v->h_error, 0x100u + v->rank, v->stream));
+        v->launches += 1;
+        f.done_flag = &sync->done[v->rank].seq;
+        f.cta_counter = v->d_cta_counter;
+        f.frame_seq = v->frame_seq;
+    } else if (v->gather_role == GATHER_ROOT) {
+        v->frame_seq += 1;
+        f.go_flag = &gather_sync_of(v->frame_block, v->plane_bytes)->go;
+        f.frame_seq = v->frame_seq;
+    }
     CUDA_TRY(cudaEventRecord(v->ev_start, v->stream));
     CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
-    CUDA_TRY(cudaEventRecord(v->ev_stop, v->stream));
     v->launches += 1;
+    if (v->gather_role == GATHER_ROOT) {
+        GatherSync* sync = gather_sync_of(v->frame_block, v->plane_bytes);
+        GatherComplete g{};
+        g.done_flags = &sync->done[0].seq;
+        g.done_stride = (uint32_t)(sizeof(sync->done[0]) / 4);
+        g.world = v->world;
+        g.frame_seq = v->frame_seq;
+        g.fill_albedo = v->gather_wire == SVX_WIRE_ID_DISTANCE ? 1u : 0u;
+        g.width = v->width;
+        g.height = v->height;
+        g.band_shift = f.band_shift;
+        g.hit_id = v->d_hit_id;
+        g.albedo = v->d_albedo;
+        g.palette = v->host->dev.palette;
+        g.n_colors = v->host->dev.n_colors;
+        g.timeout_ns = v->gather_timeout_ns;
+        g.error = v->h_error;
+        CUDA_TRY(launch_gather_complete(g, v->host->cfg.sm_count, v->stream));
+        v->launches += 1;
+    }
+    CUDA_TRY(cudaEventRecord(v->ev_stop, v->stream));
+    return SVX_OK;
+}
+
+// The rows this view owns, device -> host, into full-frame host planes (any may be null). A local shard (set_shard
+// without a gather) copies only its own bands - strided copies whose rows are whole bands - so that several GPUs (or
+// processes sharing the host buffers) assemble one frame over their own PCIe links.
+int32_t copy_frame_to_host(svx_view* v, cudaStream_t stream, uint32_t* hit_id, uint32_t* albedo, float* distance) {
+    if (v->gather_role == GATHER_PEER) return fail(SVX_E_INVALID_ARGUMENT, "a gather peer has no local frame to read back: read the root's");
+    const void* src[3] = {v->d_hit_id, v->d_albedo, v->d_distance};
+    void* dst[3] = {hit_id, albedo, distance};
+    const size_t row_bytes = (size_t)v->width * 4;
+    for (int p = 0; p < 3; ++p) {
+        if (!dst[p]) continue;
+        if (v->world == 1 || v->gather_role == GATHER_ROOT) {
+            CUDA_TRY(cudaMemcpyAsync(dst[p], src[p], row_bytes * v->height, cudaMemcpyDeviceToHost, stream));
+            continue;
+        }
+        if (v->compact) return fail(SVX_E_INVALID_ARGUMENT, "compact shards are read through svx_view_frame_pointers");
+        const uint32_t band = v->band_rows, bands = (v->height + band - 1) / band;
+        uint32_t full = 0;  // whole bands this shard owns; the image's last band may be partial
+        for (uint32_t b = v->rank; b < bands; b += v->world)
+            if ((b + 1) * band <= v->height) ++full;
+        const size_t first = (size_t)v->rank * band * row_bytes, band_bytes = (size_t)band * row_bytes, pitch = band_bytes * v->world;
+        if (full)
+            CUDA_TRY(cudaMemcpy2DAsync((char*)dst[p] + first, pitch, (const char*)src[p] + first, pitch, band_bytes, full,
+                                       cudaMemcpyDeviceToHost, stream));
+        const uint32_t last = bands - 1;
+        if (last % v->world == v->rank && (last + 1) * band > v->height) {
+            const size_t off = (size_t)last * band_bytes;
+            CUDA_TRY(cudaMemcpyAsync((char*)dst[p] + off, (const char*)src[p] + off, row_bytes * (v->height - last * band),
+                                     cudaMemcpyDeviceToHost, stream));
+        }
+    }
     return SVX_OK;
 }
 
@@ -546,7 +573,7 @@ int32_t ensure_pipeline(svx_view* v) {
 
 // One pipelined frame: kernel into the next slot on the render stream, copies of that slot on the copy stream.
 int32_t submit_async_locked(svx_view* v, uint32_t* hit_id, uint32_t* albedo, float* distance) {
-    if (v->use_peer) return fail(SVX_E_INVALID_ARGUMENT, "a view that stores into a peer framebuffer has no local frame to read back");
+    if (v->gather_role != GATHER_NONE) return fail(SVX_E_INVALID_ARGUMENT, "the pipelined read-back is not available on a gather member");
     int32_t s = ensure_pipeline(v);
     if (s != SVX_OK) return s;
     const uint32_t k = (uint32_t)(v->async_frames & 1u);
@@ -555,6 +582,7 @@ int32_t submit_async_locked(svx_view* v, uint32_t* hit_id, uint32_t* albedo, flo
         if (s != SVX_OK) return s;
     }
     v->target_slot = k;
+    std::shared_lock<std::shared_mutex> tree_lock(v->host->dev_mu);
     FrameParams f;
     make_frame_constants(v, &f);
     v->target_slot = 0;
@@ -567,14 +595,20 @@ int32_t submit_async_locked(svx_view* v, uint32_t* hit_id, uint32_t* albedo, flo
     CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
     CUDA_TRY(cudaEventRecord(v->slot_rendered[k], v->stream));
     v->launches += 1;
+    tree_lock.unlock();
     CUDA_TRY(cudaStreamWaitEvent(v->copy_stream, v->slot_rendered[k], 0));
-    const size_t bytes = (size_t)v->width * v->height * 4;
-    const uint32_t* src_hit = k ? v->alt_hit_id : v->d_hit_id;
-    const uint32_t* src_alb = k ? v->alt_albedo : v->d_albedo;
-    const float* src_dist = k ? v->alt_distance : v->d_distance;
-    if (hit_id) CUDA_TRY(cudaMemcpyAsync(hit_id, src_hit, bytes, cudaMemcpyDeviceToHost, v->copy_stream));
-    if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo, src_alb, bytes, cudaMemcpyDeviceToHost, v->copy_stream));
-    if (distance) CUDA_TRY(cudaMemcpyAsync(distance, src_dist, bytes, cudaMemcpyDeviceToHost, v->copy_stream));
+    if (k == 0) {
+        const int32_t copied = copy_frame_to_host(v, v->copy_stream, hit_id, albedo, distance);
+        if (copied != SVX_OK) return copied;
+    } else {  // slot 1 has its own planes: point the copy helper at them for the duration of the call
+        uint32_t* const keep_hit = v->d_hit_id;
+        uint32_t* const keep_alb = v->d_albedo;
+        float* const keep_dist = v->d_distance;
+        v->d_hit_id = v->alt_hit_id; v->d_albedo = v->alt_albedo; v->d_distance = v->alt_distance;
+        const int32_t copied = copy_frame_to_host(v, v->copy_stream, hit_id, albedo, distance);
+        v->d_hit_id = keep_hit; v->d_albedo = keep_alb; v->d_distance = keep_dist;
+        if (copied != SVX_OK) return copied;
+    }
     CUDA_TRY(cudaEventRecord(v->slot_copied[k], v->copy_stream));
     v->slot_busy[k] = true;
     v->async_frames += 1;
@@ -676,10 +710,13 @@ int32_t svx_octree_get(const svx_octree* t, uint32_t x, uint32_t y, uint32_t z, 
 int32_t svx_octree_get_sweep(const svx_octree* t, uint32_t x0, uint32_t y0, uint32_t z0, uint32_t nx, uint32_t ny,
                              uint32_t nz, svx_entry* out) {
     if (!t || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    const uint64_t size = t->tree->size();
+    if ((uint64_t)x0 + nx > size || (uint64_t)y0 + ny > size || (uint64_t)z0 + nz > size)
+        return fail(SVX_E_INVALID_POSITION, "the sweep box leaves the tree");
     size_t i = 0;
-    for (uint32_t x = x0; x < x0 + nx; ++x)
-        for (uint32_t y = y0; y < y0 + ny; ++y)
-            for (uint32_t z = z0; z < z0 + nz; ++z) out[i++] = t->tree->get(x, y, z);
+    for (uint64_t x = x0; x < (uint64_t)x0 + nx; ++x)
+        for (uint64_t y = y0; y < (uint64_t)y0 + ny; ++y)
+            for (uint64_t z = z0; z < (uint64_t)z0 + nz; ++z) out[i++] = t->tree->get((uint32_t)x, (uint32_t)y, (uint32_t)z);
     return SVX_OK;
 }
 uint32_t svx_octree_size(const svx_octree* t) { return t ? t->tree->size() : 0; }
@@ -851,6 +888,9 @@ int32_t svx_gpu_host_reload(svx_gpu_host* h) {
     if (!h) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(h->mu);
     if (h->uploaded_revision == h->octree->tree->revision()) return SVX_OK;  // nothing was edited since the last upload
+    // no view can snapshot `dev` or launch while this is held; whatever was launched before is drained below, so the
+    // arrays upload() replaces or frees are no longer in use
+    std::unique_lock<std::shared_mutex> tree_lock(h->dev_mu);
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
     return upload(h);
@@ -953,6 +993,16 @@ int32_t svx_gpu_host_get_by_rays_at_lod(svx_gpu_host* h, const svx_ray* rays, ui
                                         svx_hit* hits) {
     if (!h || (n && (!rays || !hits))) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     if (n == 0) return SVX_OK;
+    // Ray::is_valid (spatial/raytracing/mod.rs:14-16) is a debug assertion in the reference; a NaN or zero direction would
+    // make the traversal spin. Finite origins and finite non-zero directions only.
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* o = rays[i].origin;
+        const float* d = rays[i].direction;
+        const bool finite = std::isfinite(o[0]) && std::isfinite(o[1]) && std::isfinite(o[2]) && std::isfinite(d[0]) &&
+                            std::isfinite(d[1]) && std::isfinite(d[2]);
+        if (!finite || (d[0] == 0.0f && d[1] == 0.0f && d[2] == 0.0f))
+            return fail(SVX_E_INVALID_ARGUMENT, "ray " + std::to_string(i) + ": non-finite origin / direction or zero direction");
+    }
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     if (n > h->ray_capacity) {
@@ -997,6 +1047,8 @@ int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* 
     *out = nullptr;
     if (width == 0 || height == 0) return fail(SVX_E_INVALID_ARGUMENT, "zero resolution");
     if ((uint64_t)width * height > 0x7FFFFFFFull) return fail(SVX_E_INVALID_ARGUMENT, "resolution beyond 2^31 pixels");  // 32-bit pixel indices in the kernels
+    const int32_t valid = validate_viewport(*vp);
+    if (valid != SVX_OK) return valid;
     CUDA_TRY(cudaSetDevice(h->device));
     svx_view* v = new (std::nothrow) svx_view();
     if (!v) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
@@ -1018,12 +1070,16 @@ int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* 
         svx_view_free(v);
         return s;
     }
-    e = cudaMalloc((void**)&v->d_counters, 2 * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemsetAsync(v->d_counters, 0, 2 * sizeof(uint32_t), v->stream);
+    e = cudaMalloc((void**)&v->d_counters, 4 * sizeof(uint32_t));  // two tile tickets + the gather's retired-CTA counter
+    if (e == cudaSuccess) e = cudaMemsetAsync(v->d_counters, 0, 4 * sizeof(uint32_t), v->stream);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_error, sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) {
         svx_view_free(v);
         return cuda_fail(e, "tile counters");
     }
+    *v->h_error = 0u;
+    v->d_cta_counter = v->d_counters + 2;
+    if (const char* t = std::getenv("SVX_GATHER_TIMEOUT_MS")) v->gather_timeout_ns = (uint64_t)std::max(1L, std::atol(t)) * 1000000ull;
     const char* env = std::getenv("SVX_SCHEDULE");  // "persistent" | "static" (tuning override)
     v->persistent = env ? std::strcmp(env, "persistent") == 0 : SVX_DEFAULT_PERSISTENT;
     *out = v;
@@ -1034,9 +1090,8 @@ void svx_view_free(svx_view* v) {
     if (!v) return;
     cudaSetDevice(v->host->device);
     if (v->stream) cudaStreamSynchronize(v->stream);
-    cudaFree(v->d_hit_id);
-    cudaFree(v->d_albedo);
-    cudaFree(v->d_distance);
+    svx_view_gather_close(v);
+    cudaFree(v->frame_block);
     cudaFree(v->d_shaded);
     if (v->copy_stream) cudaStreamSynchronize(v->copy_stream);
     cudaFree(v->alt_hit_id);
@@ -1052,10 +1107,9 @@ void svx_view_free(svx_view* v) {
     if (v->ev_stop) cudaEventDestroy(v->ev_stop);
     if (v->tm_start) cudaEventDestroy(v->tm_start);
     if (v->tm_stop) cudaEventDestroy(v->tm_stop);
-    for (int i = 0; i < 3; ++i)
-        if (v->peer_base[i]) cudaIpcCloseMemHandle(v->peer_base[i]);
     cudaFree(v->d_flush);
     cudaFree(v->d_counters);
+    if (v->h_error) cudaFreeHost(v->h_error);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
 }
@@ -1067,6 +1121,8 @@ int32_t svx_view_get_viewport(const svx_view* v, svx_viewport* out) {
 }
 int32_t svx_view_set_viewport(svx_view* v, const svx_viewport* vp) {
     if (!v || !vp) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    const int32_t valid = validate_viewport(*vp);
+    if (valid != SVX_OK) return valid;
     std::lock_guard<std::mutex> lock(v->mu);
     v->viewport = *vp;
     return SVX_OK;
@@ -1080,6 +1136,7 @@ int32_t svx_view_set_glass_mode(svx_view* v, int32_t mode) {
 int32_t svx_view_set_shading(svx_view* v, const float* light_normal) {
     if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(v->mu);
+    if (light_normal && v->gather_role != GATHER_NONE) return fail(SVX_E_INVALID_ARGUMENT, "the shaded plane is not gathered: leave the gather first");
     CUDA_TRY(cudaSetDevice(v->host->device));
     const int32_t drained = retire_locked(v, 0);
     if (drained != SVX_OK) return drained;
@@ -1125,6 +1182,8 @@ int32_t svx_view_get_viewing_distance(const svx_view* v, float* viewing_distance
 int32_t svx_view_set_resolution(svx_view* v, uint32_t width, uint32_t height) {
     if (!v || width == 0 || height == 0 || (uint64_t)width * height > 0x7FFFFFFFull) return fail(SVX_E_INVALID_ARGUMENT, "bad resolution");
     std::lock_guard<std::mutex> lock(v->mu);
+    // peers hold mappings of (and store into) the root's frame allocation, and every member's shard assumes one resolution
+    if (v->gather_role != GATHER_NONE) return fail(SVX_E_INVALID_ARGUMENT, "close the gather before changing the resolution");
     CUDA_TRY(cudaSetDevice(v->host->device));
     const int32_t drained = retire_locked(v, 0);
     if (drained != SVX_OK) return drained;
@@ -1143,6 +1202,7 @@ int32_t svx_view_set_shard(svx_view* v, uint32_t rank, uint32_t world, uint32_t 
     if (!v || world == 0 || rank >= world || rows_per_band == 0 || (rows_per_band & (rows_per_band - 1)) != 0)
         return fail(SVX_E_INVALID_ARGUMENT, "bad shard (rows_per_band must be a power of two)");
     std::lock_guard<std::mutex> lock(v->mu);
+    if (v->gather_role != GATHER_NONE) return fail(SVX_E_INVALID_ARGUMENT, "a gather member's shard is set by the gather");
     v->rank = rank;
     v->world = world;
     v->band_rows = rows_per_band;
@@ -1163,6 +1223,7 @@ int32_t svx_view_set_schedule(svx_view* v, int32_t persistent) {
 int32_t svx_view_set_compact_rows(svx_view* v, int32_t enabled) {
     if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(v->mu);
+    if (enabled && v->gather_role != GATHER_NONE) return fail(SVX_E_INVALID_ARGUMENT, "a gather member stores at image rows");
     v->compact = enabled ? 1u : 0u;
     return SVX_OK;
 }
@@ -1172,39 +1233,6 @@ int32_t svx_view_frame_pointers(const svx_view* v, void** hit_id, void** albedo,
     if (hit_id) *hit_id = v->d_hit_id;
     if (albedo) *albedo = v->d_albedo;
     if (distance) *distance = v->d_distance;
-    return SVX_OK;
-}
-
-int32_t svx_view_export_frame_ipc(const svx_view* v, uint8_t* handles /* 3 x 64 bytes */) {
-    if (!v || !handles) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
-    CUDA_TRY(cudaSetDevice(v->host->device));
-    void* ptrs[3] = {v->d_hit_id, v->d_albedo, v->d_distance};
-    for (int i = 0; i < 3; ++i) {
-        cudaIpcMemHandle_t h;
-        CUDA_TRY(cudaIpcGetMemHandle(&h, ptrs[i]));
-        std::memcpy(handles + 64 * i, &h, 64);
-    }
-    return SVX_OK;
-}
-
-int32_t svx_view_set_peer_frame_ipc(svx_view* v, const uint8_t* handles /* 3 x 64 bytes, or null to detach */) {
-    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
-    std::lock_guard<std::mutex> lock(v->mu);
-    CUDA_TRY(cudaSetDevice(v->host->device));
-    CUDA_TRY(cudaStreamSynchronize(v->stream));
-    for (int i = 0; i < 3; ++i) {
-        if (v->peer_base[i]) cudaIpcCloseMemHandle(v->peer_base[i]);
-        v->peer_base[i] = nullptr;
-    }
-    v->use_peer = false;
-    if (!handles) return SVX_OK;
-    for (int i = 0; i < 3; ++i) {
-        cudaIpcMemHandle_t h;
-        std::memcpy(&h, handles + 64 * i, 64);
-        CUDA_TRY(cudaIpcOpenMemHandle(&v->peer_base[i], h, cudaIpcMemLazyEnablePeerAccess));
-    }
-    v->use_peer = true;
     return SVX_OK;
 }
 
@@ -1218,15 +1246,19 @@ int32_t svx_view_render(svx_view* v, svx_frame* out) {
     if (s != SVX_OK) return s;
     if (out) {
         CUDA_TRY(cudaStreamSynchronize(v->stream));
+        const int32_t arrived = check_view_error(v);
+        if (arrived != SVX_OK) return arrived;
         float ms = 0.0f;
         CUDA_TRY(cudaEventElapsedTime(&ms, v->ev_start, v->ev_stop));
         out->width = v->width;
         out->height = v->height;
         out->row_begin = 0;
         out->row_end = v->height;
-        out->hit_id = v->d_hit_id;
-        out->albedo = v->d_albedo;
-        out->distance = v->d_distance;
+        // a gather peer has no frame of its own: the pixels are in the root's
+        const bool peer = v->gather_role == GATHER_PEER;
+        out->hit_id = peer ? nullptr : v->d_hit_id;
+        out->albedo = peer ? nullptr : v->d_albedo;
+        out->distance = peer ? nullptr : v->d_distance;
         out->kernel_ms = ms;
     }
     return SVX_OK;
@@ -1240,12 +1272,27 @@ int32_t svx_view_render_to_host(svx_view* v, uint32_t* hit_id, uint32_t* albedo,
     if (drained != SVX_OK) return drained;
     const int32_t s = render_locked(v);
     if (s != SVX_OK) return s;
+    if (v->gather_role != GATHER_PEER) {
+        const int32_t copied = copy_frame_to_host(v, v->stream, hit_id, albedo, distance);
+        if (copied != SVX_OK) return copied;
+    }
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    return check_view_error(v);
+}
+
+int32_t svx_view_read_frame(svx_view* v, uint32_t* hit_id, uint32_t* albedo, float* distance) {
+    if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(v->mu);
+    if (v->gather_role == GATHER_PEER) return fail(SVX_E_INVALID_ARGUMENT, "a gather peer has no local frame: read the root's");
+    CUDA_TRY(cudaSetDevice(v->host->device));
+    const int32_t drained = retire_locked(v, 0);
+    if (drained != SVX_OK) return drained;
     const size_t bytes = (size_t)v->width * v->height * 4;
     if (hit_id) CUDA_TRY(cudaMemcpyAsync(hit_id, v->d_hit_id, bytes, cudaMemcpyDeviceToHost, v->stream));
     if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo, v->d_albedo, bytes, cudaMemcpyDeviceToHost, v->stream));
     if (distance) CUDA_TRY(cudaMemcpyAsync(distance, v->d_distance, bytes, cudaMemcpyDeviceToHost, v->stream));
     CUDA_TRY(cudaStreamSynchronize(v->stream));
-    return SVX_OK;
+    return check_view_error(v);
 }
 
 int32_t svx_view_render_to_host_async(svx_view* v, uint32_t* hit_id, uint32_t* albedo, float* distance) {
@@ -1297,7 +1344,7 @@ int32_t svx_view_synchronize(svx_view* v) {
     if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     CUDA_TRY(cudaSetDevice(v->host->device));
     CUDA_TRY(cudaStreamSynchronize(v->stream));
-    return SVX_OK;
+    return check_view_error(v);
 }
 int32_t svx_view_timer_start(svx_view* v) {
     if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");

@@ -78,7 +78,7 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
     // 0) pixels outside the projected bounding rectangle of the root cube are sky (host-computed, conservative)
     if (x < f.cull_x0 || x > f.cull_x1 || row < f.cull_row0 || row > f.cull_row1) {
         f.hit_id[i] = NIL;
-        f.albedo[i] = 0u;
+        if (f.albedo) f.albedo[i] = 0u;
         f.distance[i] = 0.0f;
         if (SHADE) f.shaded[i] = 0xFF808080u;
         return;
@@ -133,22 +133,60 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
         }
     }
     f.hit_id[i] = hit_id;
-    f.albedo[i] = rgba;
+    if (f.albedo) f.albedo[i] = rgba;  // nullptr: a gather peer shipping 8 B per pixel (kernels.cuh: FrameParams)
     f.distance[i] = dist;
     if (SHADE) f.shaded[i] = pixel;
+}
+
+// ---- tile-sharded gather: flags between the GPUs that render one frame together (kernels.cuh: FrameParams) ----------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Root: the first CTA tells the peers that the framebuffer may be overwritten with frame `frame_seq`.
+__device__ __forceinline__ void gather_prologue(const FrameParams& f) {
+    if (f.go_flag != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) st_release_sys(f.go_flag, f.frame_seq);
+}
+// Peer: the last CTA to retire tells the root that this GPU's share of frame `frame_seq` is in the root's memory. The
+// barrier orders every pixel store of the CTA before thread 0's system-scope fence; the CTA that finds the counter
+// complete has observed all the others' increments (each made after such a fence) and fences again before the release.
+__device__ __forceinline__ void gather_epilogue(const FrameParams& f) {
+    if (f.done_flag == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(f.cta_counter, 1u) == gridDim.x * gridDim.y - 1u) {
+            *f.cta_counter = 0u;  // launches of one view are ordered on one stream: the next one counts from zero
+            __threadfence_system();
+            st_release_sys(f.done_flag, f.frame_seq);
+        }
+    }
 }
 
 // Static schedule: one CTA per 32x8 pixel block of the frame.
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
+    gather_prologue(f);
     shade_pixel<false, false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+    gather_epilogue(f);
 }
 // The same frame over a tree with MIP maps: get_by_ray_at_lod(ray, f.viewing_distance) per pixel
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
+    gather_prologue(f);
     shade_pixel<true, false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+    gather_epilogue(f);
 }
 // The static-schedule kernels specialised for the two brick dimensions the reference's examples use (8: cpu_render.rs:14,
 // 32: dot_cube.rs:56, minecraft.rs:24, sponza.rs:24): brick strides, masks and 1 / dim are immediates in the voxel loop.
@@ -157,7 +195,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kern
     __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) NAME(const DeviceTree tree, const FrameParams f) {      \
         int tx, ty;                                                                                                         \
         pixel_of_thread(tx, ty);                                                                                            \
+        gather_prologue(f);                                                                                                 \
         shade_pixel<LOD, false, BS>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);                           \
+        gather_epilogue(f);                                                                                                 \
     }
 SVX_RENDER_KERNEL_FOR_BRICK(render_kernel_brick8, false, 3)
 SVX_RENDER_KERNEL_FOR_BRICK(render_kernel_brick32, false, 5)
@@ -172,12 +212,16 @@ SVX_RENDER_KERNEL_FOR_BRICK(render_lod_kernel_brick32, true, 5)
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_shaded_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
+    gather_prologue(f);
     shade_pixel<false, true>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+    gather_epilogue(f);
 }
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_shaded_kernel(const DeviceTree tree, const FrameParams f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
+    gather_prologue(f);
     shade_pixel<true, true>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+    gather_epilogue(f);
 }
 
 // Persistent schedule: the grid is sized to the machine (SMs x resident CTAs) and every WARP pulls 8x4 pixel tiles from a
@@ -211,11 +255,15 @@ __device__ __forceinline__ void render_persistent_body(const DeviceTree& tree, c
 }
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel_persistent(const DeviceTree tree, const FrameParams f,
                                                                                           uint32_t* __restrict__ counters) {
+    gather_prologue(f);
     render_persistent_body<false>(tree, f, counters);
+    gather_epilogue(f);
 }
 __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kernel_persistent(const DeviceTree tree, const FrameParams f,
                                                                                               uint32_t* __restrict__ counters) {
+    gather_prologue(f);
     render_persistent_body<true>(tree, f, counters);
+    gather_epilogue(f);
 }
 
 template <bool LOD>
@@ -467,6 +515,85 @@ __global__ void div_selftest_kernel(uint64_t n, uint64_t seed, unsigned long lon
 
 cudaError_t launch_div_selftest(uint64_t n, uint64_t seed, unsigned long long* counts, cudaStream_t stream) {
     div_selftest_kernel<<<148 * 8, 256, 0, stream>>>(n, seed, counts);
+    return cudaGetLastError();
+}
+
+// One thread waits until *flag has reached `want` (sequence numbers: compared modulo 2^32). The flag may live in another
+// GPU's memory (a peer polling the root's `go` over NVLink): the poll backs off between reads. A flag that does not
+// arrive within timeout_ns is reported through the host-mapped error word instead of hanging the device.
+__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t want, uint64_t timeout_ns, uint32_t* error, uint32_t error_code) {
+    const uint64_t t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
+        if (globaltimer_ns() - t0 > timeout_ns) {
+            *error = error_code;
+            __threadfence_system();
+            return;
+        }
+        __nanosleep(100);
+    }
+}
+
+// Root side of the gather: every CTA waits until all peers have published `frame_seq` in their done word (their pixels are
+// then in this GPU's memory), and - for the 8-byte wire format - resolves the albedo of the peers' rows from the hit ids
+// exactly as the viewport kernel does for its own pixels (palette[hit_id & 0xFFFF], 0 without a colour).
+__global__ void __launch_bounds__(256) gather_complete_kernel(const GatherComplete g) {
+    __shared__ uint32_t arrived;
+    if (threadIdx.x == 0) {
+        arrived = 1u;
+        const uint64_t t0 = globaltimer_ns();
+        for (uint32_t r = 1; r < g.world && arrived; ++r) {
+            const uint32_t* flag = g.done_flags + (size_t)r * g.done_stride;
+            while ((int32_t)(ld_acquire_sys(flag) - g.frame_seq) < 0) {
+                if (globaltimer_ns() - t0 > g.timeout_ns) {
+                    arrived = 0u;
+                    if (blockIdx.x == 0) {
+                        *g.error = 1u + r;
+                        __threadfence_system();
+                    }
+                    break;
+                }
+                __nanosleep(40);
+            }
+        }
+    }
+    __syncthreads();
+    if (!arrived || !g.fill_albedo) return;
+    const bool vec = (g.width & 3u) == 0u;
+    for (uint32_t row = blockIdx.x; row < g.height; row += gridDim.x) {
+        if (((row >> g.band_shift) % g.world) == 0u) continue;  // the root's own rows already carry their albedo
+        const size_t base = (size_t)row * g.width;
+        if (vec) {
+            const uint4* src = reinterpret_cast<const uint4*>(g.hit_id + base);
+            uint4* dst = reinterpret_cast<uint4*>(g.albedo + base);
+            for (uint32_t x = threadIdx.x; x < (g.width >> 2); x += blockDim.x) {
+                const uint4 h = __ldcg(src + x);
+                uint4 a;
+                const uint32_t c0 = h.x & 0xFFFFu, c1 = h.y & 0xFFFFu, c2 = h.z & 0xFFFFu, c3 = h.w & 0xFFFFu;
+                a.x = (c0 < 0xFFFFu && c0 < g.n_colors) ? __ldg(g.palette + c0) : 0u;
+                a.y = (c1 < 0xFFFFu && c1 < g.n_colors) ? __ldg(g.palette + c1) : 0u;
+                a.z = (c2 < 0xFFFFu && c2 < g.n_colors) ? __ldg(g.palette + c2) : 0u;
+                a.w = (c3 < 0xFFFFu && c3 < g.n_colors) ? __ldg(g.palette + c3) : 0u;
+                dst[x] = a;
+            }
+        } else {
+            for (uint32_t x = threadIdx.x; x < g.width; x += blockDim.x) {
+                const uint32_t c = __ldcg(g.hit_id + base + x) & 0xFFFFu;
+                g.albedo[base + x] = (c < 0xFFFFu && c < g.n_colors) ? __ldg(g.palette + c) : 0u;
+            }
+        }
+    }
+}
+
+cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t want, uint64_t timeout_ns, uint32_t* error, uint32_t error_code,
+                             cudaStream_t stream) {
+    wait_flag_kernel<<<1, 1, 0, stream>>>(flag, want, timeout_ns, error, error_code);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_complete(const GatherComplete& g, int sm_count, cudaStream_t stream) {
+    // waiting only: one CTA. Filling: two CTAs per SM stream the peers' rows (HBM-bound, 4 B read + 4 B written per pixel)
+    const unsigned grid = g.fill_albedo ? (unsigned)std::min<uint32_t>(g.height, (uint32_t)sm_count * 2u) : 1u;
+    gather_complete_kernel<<<grid, 256, 0, stream>>>(g);
     return cudaGetLastError();
 }
 

@@ -33,6 +33,35 @@ struct FrameParams {
     // scaled by a diffuse term from the impact normal and this light normal, grey on a miss. nullptr = not produced.
     uint32_t* shaded;      // [h*w] RGBA8, r in the low byte
     float lx, ly, lz;      // diffuse_light_normal (cpu_render.rs:97)
+    // Tile-sharded gather (multi_gpu.cu): one frame rendered by `world` GPUs into the ROOT GPU's framebuffer, the peers'
+    // stores crossing NVLink from inside this kernel. All three are nullptr outside a gather.
+    //   go_flag    root only: the first CTA publishes `frame_seq` here (release, system scope) - the peers' licence to
+    //              overwrite the root's framebuffer with frame `frame_seq` (everything the consumer queued before this
+    //              launch has retired by then)
+    //   done_flag  peers only: the root's done[rank] word, written with `frame_seq` by the last CTA of this launch to
+    //              retire, after a system-scope fence: all of this GPU's pixels are in the root's memory
+    //   cta_counter peers only: local counter of retired CTAs (reset by the CTA that finds it complete)
+    // A peer launched with albedo == nullptr ships 8 B per pixel (hit id + distance); the root fills the albedo of the
+    // peers' rows from its own palette (gather_complete_kernel).
+    uint32_t* go_flag;
+    uint32_t* done_flag;
+    uint32_t* cta_counter;
+    uint32_t frame_seq;
+};
+
+// What the root's completion kernel needs besides the frame: which rows the peers own and the palette to resolve albedo with
+struct GatherComplete {
+    const uint32_t* done_flags;   // root memory: done[r] word of peer r at done_flags[r * done_stride]
+    uint32_t done_stride;         // in u32 words
+    uint32_t world, frame_seq;
+    uint32_t fill_albedo;         // 1: peers shipped hit id + distance only
+    uint32_t width, height, band_shift;
+    const uint32_t* hit_id;
+    uint32_t* albedo;
+    const uint32_t* palette;
+    uint32_t n_colors;
+    uint64_t timeout_ns;
+    uint32_t* error;              // host-mapped word: set to 1 + the late peer's rank on a timeout
 };
 
 // Output record of the batched get_by_ray query
@@ -51,6 +80,13 @@ struct LaunchConfig {
 };
 
 cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, const LaunchConfig& cfg, cudaStream_t stream);
+// Gather protocol, device side (multi_gpu.cu drives it):
+//   launch_wait_flag      one thread spins (acquire, system scope) until *flag >= want; a peer waits for the root's `go`
+//   launch_gather_complete the root waits for every peer's done word, then (8-byte wire format) resolves the albedo of
+//                          the peers' rows. Both give up after timeout_ns and report through the host-mapped error word.
+cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t want, uint64_t timeout_ns, uint32_t* error, uint32_t error_code,
+                             cudaStream_t stream);
+cudaError_t launch_gather_complete(const GatherComplete& g, int sm_count, cudaStream_t stream);
 cudaError_t launch_rays(const DeviceTree& tree, const float* rays /* [n][6] */, uint64_t n, float viewing_distance,
                         RayHitRecord* out, const LaunchConfig& cfg, cudaStream_t stream);
 // Render-data upload, device side: the occupancy bit-bricks (gpu_tree.hpp: brick_bits) of the listed bricks, computed

@@ -479,19 +479,8 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
 #endif
         if ((int)(word << (nflat & 31u)) < 0) break;
         float tx, ty;
-#if SVX_FAR_PLANE_DDA
-        float tz;
-        if constexpr (FAR) {  // cx, cy, cz are the far planes here
-            unpack2(mul2(sub2(pxy, pack2(cx, cy)), sfxy), tx, ty);
-            tz = (pz - cz) * r.sfz;
-        } else {
-            unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
-            tz = ((pz - cz) - offz) * r.sfz;
-        }
-#else
         unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
         const float tz = ((pz - cz) - offz) * r.sfz;
-#endif
         const float d_x = fabsf(tx), d_y = fabsf(ty), d_z = fabsf(tz);
         const float m = fminf(fminf(d_x, d_y), d_z);
         float mx, my, qx, qy;
@@ -586,6 +575,11 @@ __device__ __forceinline__ bool certain_root_miss(float ox, float oy, float oz, 
     return (tmax < -e) || ((tmin - tmax) > 2.0f * e);
 }
 
+// Not part of the reference: an entry point that is not finite (origin or direction at the ends of the f32 range, NaN
+// rays) makes every DDA distance NaN, no axis ever steps and the walks below would spin forever - the reference trips its
+// debug assertions or hangs on its CPU thread there. The kernels report a miss instead. x - x is 0 for finite x, NaN otherwise.
+__device__ __forceinline__ bool all_finite(float x, float y, float z) { return ((x - x) + (y - y)) + (z - z) == 0.0f; }
+
 // Cube::intersect_ray on the root cube + the entry point and octant (spatial/raytracing/mod.rs:32-61,
 // raytracing_on_cpu.rs:335-348). Needs only origin and direction of `r`. Returns false when the ray misses.
 __device__ __forceinline__ bool root_entry(const RayConst& r, float tree_size, float& px, float& py, float& pz,
@@ -600,9 +594,14 @@ __device__ __forceinline__ bool root_entry(const RayConst& r, float tree_size, f
     px = r.ox + r.dx * d;
     py = r.oy + r.dy * d;
     pz = r.oz + r.dz * d;
+    if (!all_finite(px, py, pz)) return false;
     target_octant = hash_region(px, py, pz, tree_size * 0.5f);
     return true;
 }
+
+// Not part of the reference either: with all three scale factors NaN (a zero or NaN direction) every DDA distance is NaN,
+// `min_step == distance` holds on no axis and nothing ever steps. One finite factor is enough (f32::min ignores NaN).
+__device__ __forceinline__ bool no_usable_scale_factor(const RayConst& r) { return r.sfx != r.sfx && r.sfy != r.sfy && r.sfz != r.sfz; }
 
 // root_entry followed by ray_setup, as the viewport kernels call them, with the twelve divisions by the direction's
 // components sharing one refined reciprocal per component when every operand is in the safe range (see Reciprocal);
@@ -623,18 +622,19 @@ __device__ __forceinline__ bool root_entry_and_setup(RayConst& r, float tree_siz
         px = r.ox + r.dx * d;
         py = r.oy + r.dy * d;
         pz = r.oz + r.dz * d;
+        if (!all_finite(px, py, pz)) return false;
         target_octant = hash_region(px, py, pz, tree_size * 0.5f);
         auto sq = [](float v) { return v * v; };
         r.sfx = sqrtf(1.0f + sq(div_by(r.dz, rx)) + sq(div_by(r.dy, rx)));
         r.sfy = sqrtf(sq(div_by(r.dx, ry)) + 1.0f + sq(div_by(r.dz, ry)));
         r.sfz = sqrtf((sq(div_by(r.dx, rz)) + 1.0f) + sq(div_by(r.dy, rz)));
         ray_setup_signs(r);
-        return true;
+        return !no_usable_scale_factor(r);
     }
 #endif
     if (!root_entry(r, tree_size, px, py, pz, target_octant)) return false;
     ray_setup(r);
-    return true;
+    return !no_usable_scale_factor(r);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -783,6 +783,10 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
     const bool root_can_crawl = (root_hd.z & 3u) == NK_INTERNAL || (root_hd.z & 3u) == NK_NOTHING;
     const float cwx = r.dx * 0.1f, cwy = r.dy * 0.1f, cwz = r.dz * 0.1f;  // `ray.direction * 0.1` (:551)
     const float quarter = tree_size * 0.25f, inv_quarter = t.inv_tree_size * 4.0f;
+    // Defensive cap on restarts from the root (not in the reference): once `direction * 0.1` is below half an ulp of p on
+    // every axis (trees of 2^20 and more) the nudge no longer moves p and the reference's outer loop never ends. 2^26
+    // iterations are far beyond any ray that makes progress (a 2^19 tree is crossed in < 2^24 nudges); then: a miss.
+    uint32_t restart_budget = 1u << 26;
 
     while (target_octant != OOB_OCTANT) {
         if (root_can_crawl) {
@@ -794,6 +798,10 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             int qx = 0, qy = 0, qz = 0;
             uint32_t remx = 0u, remy = 0u, remz = 0u;
             for (;;) {
+                if (--restart_budget == 0u) {
+                    out.palette_value = NIL;
+                    return false;
+                }
                 // `p * 4 / size`: two scalings by powers of two = one by their (exact) product, inv_quarter
                 const float cpx = rust_clamp(px * inv_quarter, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
                 const float cpy = rust_clamp(py * inv_quarter, FLOAT_ERROR_TOLERANCE, 4.0f - FLOAT_ERROR_TOLERANCE);
@@ -814,7 +822,11 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
                     if (remy == 0u) { const CrawlAxis a = crawl_limit(py, cwy, quarter, inv_quarter); qy = a.q; remy = a.limit; }
                     if (remz == 0u) { const CrawlAxis a = crawl_limit(pz, cwz, quarter, inv_quarter); qz = a.q; remz = a.limit; }
                     const uint32_t n = min(min(remx, remy), remz);
-                    if (n != 0u && n != 0xFFFFFFFFu) {
+                    if (n == 0xFFFFFFFFu) {  // the nudge rounds away on every axis: p can never change again (the reference spins)
+                        out.palette_value = NIL;
+                        return false;
+                    }
+                    if (n != 0u) {
                         px = crawl_apply(px, qx, n);
                         py = crawl_apply(py, qy, n);
                         pz = crawl_apply(pz, qz, n);
@@ -1000,6 +1012,7 @@ __device__ __forceinline__ bool traverse(const DeviceTree& t, const RayConst& r,
             }
         }
         // restart from the root after a 0.1 nudge (:548-562)
+        if (--restart_budget == 0u) break;
         px = px + cwx;
         py = py + cwy;
         pz = pz + cwz;
@@ -1021,6 +1034,7 @@ __device__ __forceinline__ bool trace_ray(const DeviceTree& t, RayConst& r, Trac
     if (certain_root_miss(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, (float)t.tree_size)) return false;
     if (!root_entry(r, (float)t.tree_size, px, py, pz, target_octant)) return false;
     ray_setup(r);
+    if (no_usable_scale_factor(r)) return false;
     return traverse<LOD>(t, r, px, py, pz, target_octant, out, viewing_distance);
 }
 

@@ -8,9 +8,10 @@ Rays are independent and the tree is read-only while rendering, so the path shar
                  load balance: sky vs geometry; BASELINE config 4). The bands have to end up in one framebuffer:
                    - `gather_bands`: every rank renders into a compact band-major buffer and the buffers are
                      all-gathered (NCCL over NVLink; gloo in the CPU tests) and de-interleaved;
-                   - fused: the traversal kernel of rank r stores its pixels straight into rank 0's framebuffer through
-                     CUDA-IPC peer mappings (api.OctreeGPUView.export_frame_ipc / set_peer_frame_ipc), so the gather
-                     rides on the kernel's own stores and needs no collective at all.
+                   - fused (the product path, csrc/multi_gpu.cu): the traversal kernel of rank r stores its pixels
+                     straight into rank 0's framebuffer through a CUDA-IPC peer mapping and the hand-over runs on
+                     device-side flags (api.OctreeGPUView.gather_open / gather_join); `open_gather` below does the one-off
+                     handle exchange, after which a frame needs no host barrier and no collective at all.
 
 The functions here are backend-agnostic (they take tensors and a process group), which is what lets the world_size-2
 gloo tests in tests/test_distributed_cpu.py cover the host logic without a GPU.
@@ -83,10 +84,24 @@ def device_tensor(ptr: int, shape: Sequence[int], dtype_str: str, device_index: 
         return torch.as_tensor(_Wrapper(), device=f"cuda:{device_index}")
 
 
-def exchange_ipc_handles(my_handles: bytes, src_rank: int = 0, group=None) -> bytes:
-    """Broadcasts rank `src_rank`'s 192-byte framebuffer IPC handle blob to every rank (fused gather set-up)."""
+def broadcast_bytes(blob, src_rank: int = 0, group=None) -> bytes:
+    """Broadcasts a small byte string (e.g. the 128-byte gather handle of rank `src_rank`'s root view) to every rank."""
     import torch.distributed as dist
 
-    box = [my_handles if dist.get_rank(group) == src_rank else None]
+    box = [blob if dist.get_rank(group) == src_rank else None]
     dist.broadcast_object_list(box, src=src_rank, group=group)
     return box[0]
+
+
+def open_gather(view, rank: int, world: int, band: int = 8, wire: int = 0, group=None):
+    """One-off set-up of the fused tile-sharded gather over `world` processes (one per GPU): rank 0's view becomes the
+    root whose framebuffer assembles the frame, every other rank's view joins with the broadcast handle. Afterwards each
+    rank just calls view.render(): the synchronisation per frame is on the devices (svx_view_gather_*)."""
+    import torch.distributed as dist
+
+    handle = view.gather_open(world, band, wire) if rank == 0 else None
+    handle = broadcast_bytes(handle, 0, group)
+    if rank != 0:
+        view.gather_join(rank, handle)
+    dist.barrier(group)  # every peer has mapped the root's frame before the first frame is rendered
+    return handle
