@@ -1,13 +1,20 @@
 #!/usr/bin/env python3
 """Primary-ray throughput of the B200 path on the reference's named configs (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--mode poses|tiles|tiles_fused]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+                    [--mode auto|tiles_fused|tiles_nccl|poses] [--wire 8|12] [--no-extra]
 
-A step = one pass of the hot path over one batch: one full frame (in-kernel ray generation + get_by_ray per pixel +
-framebuffer write) per GPU. Default workload = BASELINE configs[1], examples/dot_cube at 1920x1080 on one B200.
-N > 1 (torchrun, one rank per GPU): camera poses are sharded over the ranks (batch mode of the north star), the tree is
-replicated, there is no data-path collective -> weak scaling. `--mode tiles` / `tiles_fused` instead split ONE frame into
-row bands (strong scaling) and gather them with NCCL, or with stores into rank 0's framebuffer from inside the kernel.
+A step = one pass of the hot path over one batch: ONE full frame (in-kernel ray generation + get_by_ray per pixel +
+framebuffer write). Default workload = BASELINE configs[3], the sponza-scale mixed-resolution tree at 3840x2160 (the
+configuration the north-star target is quoted on: "at 4K", "screen-tile sharded over 2/4/8").
+N = 1: one GPU renders the frame. N > 1 (torchrun, one rank per GPU): the SAME frame is split into interleaved bands of 8
+image rows, every rank renders its bands from its own replica of the tree, and the traversal kernels of ranks 1..N-1 store
+their pixels straight into rank 0's framebuffer over NVLink (CUDA IPC; device-side go / done flags, no host barrier, no
+collective per frame: csrc/multi_gpu.cu). The step time is rank 0's: its own kernel plus the wait until the slowest peer's
+rows have arrived -> strong scaling. `--mode tiles_nccl` gathers compact bands with NCCL instead (comparison), `--mode poses`
+shards camera poses (BASELINE configs[4]; no exchange, weak scaling).
+extra_workloads (on by default): N = 1: configs[1] dot_cube 1080p, configs[2] minecraft-style 4K, configs[4] terrain pose
+1080p, each with ms/frame, roofline fraction and parity against the oracle; N > 1: configs[4], all 256 poses pose-sharded.
 
 Prints ONE JSON line (rank 0). `value` is device-timed with CUDA events on the launching stream, L2 flushed before
 every timed step; `e2e` goes through the public API with host buffers (pose in, framebuffer out, copies timed).
@@ -51,7 +58,8 @@ WORKLOADS = {
     "terrain_poses_1080p": ("terrain_poses", {}, (1920, 1080),
                             "BASELINE configs[4]: 256 camera poses orbiting a 1024/8 value-noise terrain, 1920x1080 per pose, pose k -> rank k mod N"),
 }
-HEAVY = {"minecraft_4k", "sponza_4k", "terrain_poses_1080p"}  # the CPU leg samples rows instead of whole frames
+HEAVY = {"minecraft_4k", "sponza_4k", "terrain_poses_1080p"}
+BAND_ROWS = 8  # rows per band of the tile-sharded frame  # the CPU leg samples rows instead of whole frames
 
 
 def make_workload(name: str):
@@ -222,7 +230,8 @@ def run_reference(args, rank: int):
               f"({rays} rays) on {threads} host threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "strong" if (args.gpus > 1 and args.mode != "poses") else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "resolution": list(res), "rays_per_step": rays,
                    **({"mips": {"strategy": "MIPMapStrategy::default(), enabled", "viewing_distance": vd}} if args.mips is not None else {})},
@@ -235,20 +244,198 @@ def run_reference(args, rank: int):
 
 
 # ---- our arm ---------------------------------------------------------------------------------------------------------
+def peak_hbm():
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        return float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+def kernel_name(scene, mips: bool) -> str:
+    # kernels.cu: launch_render picks the instantiation for the tree's brick dimension (8 / 32: compile-time strides)
+    return ("svx::render_lod_kernel" if mips else "svx::render_kernel") + {8: "_brick8", 32: "_brick32"}.get(int(scene.brick_dim), "")
+
+
+def oracle_leg(name, scene, cam, res, vd, args, ms_per_launch, rays_per_launch, tree_bytes, check_view, mips_tree=None, budget=None):
+    """CPU oracle on a bounded sample of the workload: cpu_baseline, the algorithmic bytes of one launch (roofline) and a
+    parity check of the frame `check_view` renders (outside every timed region). ms_per_launch / rays_per_launch describe the
+    launch of the dominant kernel that was timed (a whole frame, or this rank's share of it)."""
+    import oracle_lib as O
+    from shocovox_b200 import scenes
+
+    peak, peak_src = peak_hbm()
+    w, h = res
+    rays_per_frame = w * h
+    t0 = time.time()
+    otree = scenes.build_tree(scene, O.OracleOctree)
+    enable_mips(args, oracle_tree=otree)
+    t_obuild = time.time() - t0
+    o = oracle_timed_sample(otree, cam, res, budget if budget is not None else args.cpu_budget, whole_frames=name not in HEAVY, vd=vd)
+    f = o["frame"]
+    scale = rays_per_frame / o["rays"]
+    alg_bytes = 12 * rays_per_frame + (16 * f["node_iters"] + 4 * f["voxel_fetches"]) * scale  # one whole frame
+    share = rays_per_launch / rays_per_frame
+    t_kernel = ms_per_launch * 1e-3
+    achieved = alg_bytes * share / t_kernel / 1e9
+    alg_bytes_nocrawl = alg_bytes - 16 * f["crawl_iters"] * scale
+    achieved_nocrawl = alg_bytes_nocrawl * share / t_kernel / 1e9
+    traffic = None
+    tpath = ROOT / "profiles" / "ncu_traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get(name)
+    out = {}
+    out["roofline"] = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "achieved_excluding_fast_forwarded_restarts": achieved_nocrawl, "frac_excluding_fast_forwarded_restarts": achieved_nocrawl / peak,
+        "peak_source": peak_src, "kernel": kernel_name(scene, args.mips is not None),
+        "kernel_ms_per_launch": ms_per_launch, "rays_per_launch": rays_per_launch,
+        "algorithmic_bytes_per_launch": alg_bytes * share,
+        "per_ray": {"node_visits": f["node_iters"] / o["rays"], "voxel_fetches": f["voxel_fetches"] / o["rays"],
+                    "restarts": f["outer_iters"] / o["rays"], "crawl_restarts": f["crawl_iters"] / o["rays"],
+                    "bytes": alg_bytes / rays_per_frame, "rays_entering_root": f["rays_in_root"] / o["rays"]},
+        "compulsory_bound_ms": (tree_bytes + 12 * rays_per_frame) / (peak * 1e9) * 1e3,
+        "note": "B_ray = 12 + 16 N_node + 4 N_vox, N counted by the CPU oracle executing the reference algorithm on "
+                + ("the same rays" if scale == 1 else "a row sample of the same frame, scaled")
+                + " (SURVEY 8(d)). A frac above 1 on crawl-heavy scenes is not skipped work: the reference's 0.1-nudge restarts"
+                  " (crawl_restarts per ray, 16 B each in the formula) are applied in closed form, bit-exactly, without touching memory;"
+                  " frac_excluding_fast_forwarded_restarts leaves them out. ncu: the kernel is instruction-issue bound over an L1/L2-resident tree, DRAM traffic is small",
+    }
+    out["cpu_baseline"] = {"value": o["mrays"], "unit": UNIT, "cores": o["threads"], "kind": "port", "sample": o["sample"],
+                           "oracle_tree_build_s": round(t_obuild, 2)}
+    # the reference's own caller loop is single-threaded (examples/cpu_render.rs:104-105): the same on ONE host thread
+    try:  # an auxiliary figure: it must never cost the bench line
+        per_row_1t = o["seconds"] / len(o["rows"]) * o["threads"]
+        rows_1t = sample_rows(h, int(min(h, max(8, 2.0 / max(per_row_1t, 1e-6)))))
+        f1 = otree.render(oracle_camera(cam), w, h, threads=1, row_list=rows_1t, viewing_distance=vd)
+        out["cpu_baseline"]["single_thread_value"] = len(rows_1t) * w / f1["seconds"] / 1e6
+        out["cpu_baseline"]["single_thread_sample"] = f"{len(rows_1t)} of {h} image rows ({len(rows_1t) * w} rays) on 1 host thread"
+    except Exception as e:  # noqa: BLE001
+        out["cpu_baseline"]["single_thread_value"] = None
+        out["cpu_baseline"]["single_thread_sample"] = f"failed: {e}"
+    got = check_view() if callable(check_view) else check_view
+    rows = o["rows"]
+    out["parity_vs_oracle"] = {
+        "rows_checked": int(len(rows)),
+        "hit_id_equal": bool(np.array_equal(got["hit_id"][rows], f["hit_id"][rows])),
+        "albedo_equal": bool(np.array_equal(got["albedo"][rows], f["albedo"].view(np.uint32)[..., 0][rows])),
+        "distance_bits_equal": bool(np.array_equal(got["distance"][rows].view(np.uint32), f["distance"][rows].view(np.uint32))),
+        "would_panic": int(f["would_panic"]),
+        **({"mip_probes": int(f["mip_probes"]), "mip_hash_equal": bool(mips_tree.albedo_mip_map_resampling_strategy().mip_hash() == otree.mip_hash())}
+           if (args.mips is not None and mips_tree is not None) else {}),
+    }
+    return out
+
+
+def timed_frames(view, vps, n, warm=3):
+    """ms per frame of `n` L2-flushed renders cycling through the poses `vps` (after `warm` untimed ones)."""
+    ms = []
+    for i in range(warm + n):
+        view.set_viewport(vps[i % len(vps)])
+        view.flush_l2()
+        k = view.render(sync=True)["kernel_ms"]
+        if i >= warm:
+            ms.append(k)
+    return ms
+
+
+def extra_single_gpu(name, args, local_rank):
+    """One more BASELINE config on this GPU: kernel ms/frame (L2 flushed), roofline fraction and parity against the oracle."""
+    import shocovox_b200 as S
+    from shocovox_b200 import scenes
+
+    scene, cams, res, desc = make_workload(name)
+    tree = scenes.build_tree(scene, S.Octree)
+    host = S.OctreeGPUHost(tree, local_rank)
+    vps = [S.Viewport(c.origin, c.direction, c.frustum, c.fov) for c in cams]
+    view = host.create_new_view(64, vps[0], res)
+    if cams[0].glass_at_frustum_z:
+        view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
+    ms0 = timed_frames(view, vps[:1], 10)
+    out = {"description": desc, "resolution": list(res), "ms_per_frame": float(np.mean(ms0)),
+           "mrays_per_s": res[0] * res[1] / (np.mean(ms0) * 1e-3) / 1e6, "tree_bytes": host.stats()["total_bytes"]}
+    if len(vps) > 1:  # a pose batch: 8 poses spread over the orbit
+        spread = vps[:: max(1, len(vps) // 8)][:8]
+        msp = timed_frames(view, spread, 16)
+        out["poses_sampled"] = len(spread)
+        out["ms_per_frame_over_poses"] = float(np.mean(msp))
+        out["mrays_per_s_over_poses"] = res[0] * res[1] / (np.mean(msp) * 1e-3) / 1e6
+        view.set_viewport(vps[0])
+    if not args.no_cpu_baseline:
+        leg = oracle_leg(name, scene, cams[0], res, F32_MAX, args, float(np.mean(ms0)), res[0] * res[1], out["tree_bytes"],
+                         view.render_to_host, budget=min(args.cpu_budget, 4.0))
+        out["roofline_frac"] = leg["roofline"]["frac"]
+        out["roofline"] = {k: leg["roofline"][k] for k in ("achieved", "peak", "frac", "frac_excluding_fast_forwarded_restarts", "kernel",
+                                                            "algorithmic_bytes_per_launch", "per_ray", "traffic")}
+        out["cpu_baseline"] = leg["cpu_baseline"]
+        out["parity_vs_oracle"] = leg["parity_vs_oracle"]
+    return out
+
+
+def extra_pose_batch(args, rank, local_rank, world, dist, torch):
+    """BASELINE configs[4] on all ranks: 256 poses over the 1024/8 terrain, pose k -> rank k mod N, no exchange."""
+    import shocovox_b200 as S
+    from shocovox_b200 import scenes
+
+    name = "terrain_poses_1080p"
+    scene, cams, res, desc = make_workload(name)
+    tree = scenes.build_tree(scene, S.Octree)
+    host = S.OctreeGPUHost(tree, local_rank)
+    vps = [S.Viewport(c.origin, c.direction, c.frustum, c.fov) for c in cams]
+    view = host.create_new_view(64, vps[0], res)
+    mine = list(range(rank, len(vps), world))
+    for k in mine[:3]:
+        view.set_viewport(vps[k])
+        view.render(sync=True)
+    view.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+    total = 0.0
+    for k in mine:
+        view.set_viewport(vps[k])
+        view.flush_l2()
+        total += view.render(sync=True)["kernel_ms"]
+    t = torch.tensor([total], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total = float(t.item())
+    out = {"description": desc, "resolution": list(res), "poses": len(vps), "parallelism": "pose-sharded x%d (tree replicated, no exchange)" % world,
+           "ms_per_batch": total, "ms_per_pose_per_gpu": total / max(len(mine), 1), "mrays_per_s": len(vps) * res[0] * res[1] / (total * 1e-3) / 1e6}
+    if rank == 0 and not args.no_cpu_baseline:
+        import oracle_lib as O
+
+        otree = scenes.build_tree(scene, O.OracleOctree)
+        rows = sample_rows(res[1], 32)
+        ok = {"hit_id_equal": True, "albedo_equal": True, "distance_bits_equal": True}
+        checked = [k for k in (0, 64, 128, 192) if k < len(vps)]
+        for k in checked:
+            view.set_viewport(vps[k])
+            got = view.render_to_host()
+            f = otree.render(oracle_camera(cams[k]), res[0], res[1], threads=int(O.lib().svxo_hardware_threads()), row_list=rows)
+            ok["hit_id_equal"] &= bool(np.array_equal(got["hit_id"][rows], f["hit_id"][rows]))
+            ok["albedo_equal"] &= bool(np.array_equal(got["albedo"][rows], f["albedo"].view(np.uint32)[..., 0][rows]))
+            ok["distance_bits_equal"] &= bool(np.array_equal(got["distance"][rows].view(np.uint32), f["distance"][rows].view(np.uint32)))
+        out["parity_vs_oracle"] = {"poses_checked": checked, "rows_per_pose": int(len(rows)), **ok}
+    return name, out
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dot_cube_1080p", choices=list(WORKLOADS))
-    ap.add_argument("--mode", default="poses", choices=["poses", "tiles", "tiles_fused"])
+    ap.add_argument("--workload", default="sponza_4k", choices=list(WORKLOADS))
+    ap.add_argument("--mode", default="auto", choices=["auto", "poses", "tiles_nccl", "tiles_fused"],
+                    help="N > 1: auto = tiles_fused (one frame, row bands, fused gather into rank 0's framebuffer)")
+    ap.add_argument("--wire", type=int, default=8, choices=[8, 12],
+                    help="tiles_fused: bytes per pixel the peers send (12 = hit id, albedo, distance; 8 = hit id and distance, rank 0 "
+                         "resolves albedo = palette[hit id] for the received rows)")
     ap.add_argument("--mips", default=None, metavar="VD",
                     help="switch the tree's MIP maps on and render through get_by_ray_at_lod at this viewing distance "
                          "(a number, or 'frustum' for the camera's viewport.frustum.z like the reference's shader)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=8.0, help="seconds of CPU-oracle work for the cpu_baseline leg")
-    ap.add_argument("--extra", action="store_true", help="also measure the other quick workloads (kernel time only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads (the other BASELINE configs)")
+    ap.add_argument("--extra", action="store_true", help=argparse.SUPPRESS)  # round-1 flag, accepted and ignored
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -282,6 +469,13 @@ def main() -> int:
 
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mode = args.mode
+    if world == 1:
+        mode = "single"
+    elif mode == "auto":
+        mode = "tiles_fused"
+    tiles = mode in ("tiles_fused", "tiles_nccl")
+    wire = S.WIRE_ID_DISTANCE if args.wire == 8 else S.WIRE_THREE_PLANES
 
     scene, cams, res, desc = make_workload(args.workload)
     w, h = res
@@ -301,37 +495,25 @@ def main() -> int:
         return v
 
     view = new_view()
-    tiles = args.mode != "poses" and world > 1
     rays_per_frame = w * h
-    # pose mode: step i of rank r renders pose (r + i * world) mod n_poses ; tile mode: everybody renders pose i
+    # pose mode: step i of rank r renders pose (r + i * world) mod n_poses ; otherwise everybody renders pose i
     def pose_index(i):
-        return (i if tiles else rank + i * world) % len(vps)
+        return (rank + i * world if mode == "poses" else i) % len(vps)
 
     gather = None
-    target = None
-    if tiles:
-        band = 8
-        view.set_shard(rank, world, band)
-        if args.mode == "tiles":
-            view.set_compact_rows(True)
-            lr = D.padded_local_rows(h, world, band)
-            planes = [D.device_tensor(p, (h, w), dt, local_rank)[:lr] for p, dt in zip(view.frame_pointers(), ("<i4", "<i4", "<f4"))]
-            stream = torch.cuda.ExternalStream(view.cuda_stream(), device=local_rank)
+    if mode == "tiles_fused":
+        D.open_gather(view, rank, world, BAND_ROWS, wire)
+    elif mode == "tiles_nccl":
+        view.set_shard(rank, world, BAND_ROWS)
+        view.set_compact_rows(True)
+        lr = D.padded_local_rows(h, world, BAND_ROWS)
+        planes = [D.device_tensor(p, (h, w), dt, local_rank)[:lr] for p, dt in zip(view.frame_pointers(), ("<i4", "<i4", "<f4"))]
+        stream = torch.cuda.ExternalStream(view.cuda_stream(), device=local_rank)
 
-            def gather():
-                with torch.cuda.stream(stream):
-                    return [D.gather_bands(p, h, world, band) for p in planes]
-        else:
-            target = new_view()  # rank 0's copy is the shared destination
-            blob = D.exchange_ipc_handles(target.export_frame_ipc(), src_rank=0)
-            if rank != 0:
-                view.set_peer_frame_ipc(blob)
-            else:
-                view = target
-                if cams[0].glass_at_frustum_z:
-                    view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
-                view.set_shard(0, world, band)
-    rays_per_rank_step = sum(1 for r in range(h) if (r // 8) % world == rank) * w if tiles else rays_per_frame
+        def gather():
+            with torch.cuda.stream(stream):
+                return [D.gather_bands(p, h, world, BAND_ROWS) for p in planes]
+    rays_per_rank_step = sum(1 for r in range(h) if (r // BAND_ROWS) % world == rank) * w if tiles else rays_per_frame
 
     def barrier():
         view.synchronize()
@@ -342,7 +524,9 @@ def main() -> int:
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    # ---- device-timed region: L2 flushed before every step, CUDA events around each render on its stream ----------
+    # ---- device-timed region: L2 flushed before every step, CUDA events around each step on its stream -----------------
+    # tiles_fused: rank 0's event pair spans its viewport kernel (which publishes `go` to the peers) and the kernel that
+    # waits for every peer's rows, i.e. the complete frame; a peer's pair spans its own viewport kernel. Max over ranks.
     for i in range(args.warmup):
         view.set_viewport(vps[pose_index(i)])
         view.flush_l2()
@@ -356,213 +540,199 @@ def main() -> int:
     for i in range(args.steps):
         view.set_viewport(vps[pose_index(i)])
         view.flush_l2()
-        if gather:  # the gather is part of the step: one stopwatch around kernel + collective on the same stream
+        if gather:  # the NCCL gather is part of the step: one stopwatch around kernel + collective on the same stream
             view.timer_start()
             view.render(sync=False)
             gather()
             dev_ms_total += view.timer_stop()
         else:
             dev_ms_total += view.render(sync=True)["kernel_ms"]
-        if tiles and not gather:
-            barrier()  # fused mode: a frame is complete when every rank's kernel has retired
     wall1 = time.perf_counter()
     barrier()
     sampler.window(False)
 
-    # warm-L2 variant (a viewer re-rendering the same resident tree): back-to-back launches, one event pair
+    # warm-L2 variant (a viewer re-rendering the same resident tree): back-to-back frames, one event pair
     for i in range(3):
         view.render(sync=True)
+    barrier()
     view.timer_start()
     for i in range(args.steps):
         view.set_viewport(vps[pose_index(i)])
         view.render(sync=False)
     warm_ms_total = view.timer_stop()
+    barrier()
 
-    # ---- end to end through the public API: pose in (host), framebuffer out (pinned host) --------------------------
+    # ---- the gathered frame must be the single-GPU frame, byte for byte (checked in the run, outside the timed regions) --
+    gathered_equal = None
+    if mode == "tiles_fused":
+        view.set_viewport(vps[0])
+        view.render(sync=False)
+        view.synchronize()
+        if rank == 0:
+            got = view.read_frame()
+            whole = new_view().render_to_host()
+            gathered_equal = all(bool(np.array_equal(got[k].view(np.uint32), whole[k].view(np.uint32))) for k in ("hit_id", "albedo", "distance"))
+        barrier()
+
+    # ---- end to end through the public API: pose in (host), framebuffer out (pinned host planes) -----------------------
+    # N = 1: view.set_viewport(pose) + view.render_to_host_async(pinned planes). N > 1 (tiles): every rank renders ITS
+    # bands of the frame into its own framebuffer and copies exactly those rows into host planes all ranks share
+    # (POSIX shared memory, page-locked in every process): the frame is assembled in host memory over N PCIe links.
     n_px = w * h
-    try:
-        import torch as _t  # plumbing only: pinned host buffers
-
-        bufs = [[_t.empty(n_px, dtype=_t.int32).pin_memory(), _t.empty(n_px, dtype=_t.int32).pin_memory(),
-                 _t.empty(n_px, dtype=_t.float32).pin_memory()] for _ in range(2)]
-        ptr_sets = [[b.data_ptr() for b in bs] for bs in bufs]
-    except Exception:
-        bufs = [[np.empty(n_px, dtype=np.uint32), np.empty(n_px, dtype=np.uint32), np.empty(n_px, dtype=np.float32)] for _ in range(2)]
-        ptr_sets = [[a.ctypes.data for a in bs] for bs in bufs]
-    ptrs = ptr_sets[0]
+    shared = None
     e2e_view = view
-    if tiles:  # end to end is measured on whole frames per rank (the public single-GPU call), not on shards
+    if tiles:
         e2e_view = new_view()
-    for i in range(3):
-        e2e_view.set_viewport(vps[pose_index(i)])
-        e2e_view.render_to_host_ptr(*ptrs)
-    barrier()
+        e2e_view.set_shard(rank, world, BAND_ROWS)
+        shared = D.SharedPinnedPlanes(f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}", n_px, 2, rank)
+        ptr_sets = shared.sets
+        pinned = shared.pinned
+    else:
+        try:
+            import torch as _t  # plumbing only: pinned host buffers
+
+            bufs = [[_t.empty(n_px, dtype=_t.int32).pin_memory(), _t.empty(n_px, dtype=_t.int32).pin_memory(),
+                     _t.empty(n_px, dtype=_t.float32).pin_memory()] for _ in range(2)]
+            ptr_sets = [[b.data_ptr() for b in bs] for bs in bufs]
+            pinned = True
+        except Exception:
+            bufs = [[np.empty(n_px, dtype=np.uint32), np.empty(n_px, dtype=np.uint32), np.empty(n_px, dtype=np.float32)] for _ in range(2)]
+            ptr_sets = [[a.ctypes.data for a in bs] for bs in bufs]
+            pinned = False
+
+    def e2e_loop(planes_of, pipelined=True):
+        """wall ms of `steps` frames: pose in, host planes out; planes_of(set) -> the three host pointers (0 = not delivered)"""
+        for i in range(3):
+            e2e_view.set_viewport(vps[pose_index(i)])
+            e2e_view.render_to_host_ptr(*planes_of(ptr_sets[i & 1]))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_view.set_viewport(vps[pose_index(i)])  # the step's input: one 40-byte pose, handed over as launch parameters
+            if pipelined:
+                # two host plane sets, frame i's copies overlap frame i+1's kernel; every step still ends with the PREVIOUS
+                # step's frame complete in host memory, the last one after the loop
+                e2e_view.render_to_host_async_ptr(*planes_of(ptr_sets[i & 1]))
+                e2e_view.wait_host(1)
+            else:
+                e2e_view.render_to_host_ptr(*planes_of(ptr_sets[0]))  # kernel + device->host copies, synchronised
+        if pipelined:
+            e2e_view.wait_host(0)
+        if dist is not None:
+            dist.barrier()  # the frame is complete when every rank's rows are in the shared planes
+        return (time.perf_counter() - t0) * 1e3
+
     sampler.window(True)
-    e0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_view.set_viewport(vps[pose_index(i)])  # the step's input: one 40-byte pose, handed over as launch parameters
-        e2e_view.render_to_host_ptr(*ptrs)         # kernel + three device->host copies, synchronised
-    e1 = time.perf_counter()
+    e2e_ms_total = e2e_loop(lambda p: p)
+    e2e_sync_ms_total = e2e_loop(lambda p: p, pipelined=False)
+    e2e_8b_ms_total = e2e_loop(lambda p: (p[0], 0, p[2]))  # hit id + distance: albedo is palette[hit_id & 0xFFFF]
     sampler.window(False)
-    barrier()
-    e2e_sync_ms_total = (e1 - e0) * 1e3
-    # pipelined hand-over (svx_view_render_to_host_async): two pinned buffer sets, frame i's copies overlap frame i+1's
-    # kernel; every step still ends with the PREVIOUS step's frame complete in host memory, the last one after the loop
-    for i in range(3):
-        e2e_view.set_viewport(vps[pose_index(i)])
-        e2e_view.render_to_host_async_ptr(*ptr_sets[i & 1])
-        e2e_view.wait_host(1)
-    e2e_view.wait_host(0)
-    barrier()
-    sampler.window(True)
-    e0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_view.set_viewport(vps[pose_index(i)])
-        e2e_view.render_to_host_async_ptr(*ptr_sets[i & 1])
-        e2e_view.wait_host(1)
-    e2e_view.wait_host(0)
-    e1 = time.perf_counter()
-    sampler.window(False)
-    barrier()
-    e2e_ms_total = (e1 - e0) * 1e3
+    e2e_equal = None
+    if shared is not None:  # the host-assembled frame of the last full-planes loop against rank 0's own whole frame
+        e2e_loop(lambda p: p, pipelined=False)
+        if rank == 0:
+            whole = new_view()
+            whole.set_viewport(vps[pose_index(args.steps - 1)])
+            wf = whole.render_to_host()
+            e2e_equal = all(bool(np.array_equal(shared.plane(0, k, np.uint32), wf[name].reshape(-1).view(np.uint32)))
+                            for k, name in enumerate(("hit_id", "albedo", "distance")))
+        barrier()
     clocks = sampler.stop()
 
     if dist is not None:  # max over ranks
-        t = torch.tensor([dev_ms_total, warm_ms_total, e2e_ms_total, e2e_sync_ms_total], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([dev_ms_total, warm_ms_total, e2e_ms_total, e2e_sync_ms_total, e2e_8b_ms_total], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms_total, warm_ms_total, e2e_ms_total, e2e_sync_ms_total = [float(v) for v in t.tolist()]
+        dev_ms_total, warm_ms_total, e2e_ms_total, e2e_sync_ms_total, e2e_8b_ms_total = [float(v) for v in t.tolist()]
 
-    frames_per_step = 1 if tiles else world
+    frames_per_step = world if mode == "poses" else 1
     total_rays = rays_per_frame * frames_per_step * args.steps
     value = total_rays / (dev_ms_total * 1e-3) / 1e6
     value_warm = total_rays / (warm_ms_total * 1e-3) / 1e6
-    e2e_value = rays_per_frame * world * args.steps / (e2e_ms_total * 1e-3) / 1e6
     st = host.stats()
-    par = {"poses": "pose-sharded x%d (tree replicated, no collective)" % world,
-           "tiles": "one frame in row bands of 8 over %d GPUs + NCCL all_gather of compact bands" % world,
-           "tiles_fused": "one frame in row bands of 8 over %d GPUs, kernels store into rank 0's framebuffer over NVLink (CUDA IPC)" % world}[args.mode if world > 1 else "poses"]
+    par = {"single": "one GPU renders the whole frame",
+           "poses": "pose-sharded x%d (tree replicated, no exchange)" % world,
+           "tiles_nccl": "one frame in interleaved bands of %d rows over %d GPUs + NCCL all_gather of compact bands" % (BAND_ROWS, world),
+           "tiles_fused": "one frame in interleaved bands of %d rows over %d GPUs (tree replicated); fused gather: the traversal kernels of ranks "
+                          "1..%d store into rank 0's framebuffer over NVLink (CUDA IPC), %d B/pixel on the wire, device-side go/done flags, "
+                          "no host barrier and no collective per frame" % (BAND_ROWS, world, world - 1, args.wire)}[mode]
+    launches_per_step = {"single": 1, "poses": 1, "tiles_nccl": 1, "tiles_fused": 2}[mode]
+    e2e_frames = (world if mode == "poses" else 1) * args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True,
-        "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak" if mode == "poses" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": args.workload, "description": desc, "resolution": list(res), "rays_per_step_per_gpu": rays_per_rank_step,
-            "poses": len(vps), "parallelism": par,
+            "workload": args.workload, "description": desc, "resolution": list(res), "rays_per_step": rays_per_frame * frames_per_step,
+            "rays_per_step_per_gpu": rays_per_rank_step, "poses": len(vps), "parallelism": par,
             "l2": "flushed before every timed step (384 MiB memset on the launch stream, outside the event pair)",
             "tree_bytes": st["total_bytes"], "tree_nodes": st["nodes"], "tree_bricks": st["bricks"], "tree_depth": st["depth"],
             "tree_build_s": round(t_build, 3), "voxels_inserted": int(len(scene.xyz)),
+            **({"gathered_frame_equals_single_gpu_frame": gathered_equal} if mode == "tiles_fused" else {}),
             **({"mips": {"strategy": "MIPMapStrategy::default(), enabled after construction (one recalculate_mips)",
                          "viewing_distance": vd, "recalculate_s": round(t_mips, 3)}} if args.mips is not None else {}),
         },
         "value_warm_l2": value_warm, "ms_per_step_warm_l2": warm_ms_total / args.steps,
         "wall_ms_per_step_incl_flush": (wall1 - wall0) * 1e3 / args.steps,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 40, "d2h_bytes_per_step": 12 * n_px,
+        "e2e": {"value": rays_per_frame * e2e_frames / (e2e_ms_total * 1e-3) / 1e6, "unit": UNIT,
+                "h2d_bytes_per_step": 40 * world, "d2h_bytes_per_step": 12 * n_px * (world if mode == "poses" else 1),
                 "ms_per_step": e2e_ms_total / args.steps,
                 "synchronised_ms_per_step": e2e_sync_ms_total / args.steps,
-                "synchronised_value": rays_per_frame * world * args.steps / (e2e_sync_ms_total * 1e-3) / 1e6,
-                "note": "per step: view.set_viewport(pose) + view.render_to_host_async(pinned hit_id, albedo, distance) + wait for the "
-                        "previous frame; two pinned buffer sets, copies on a second stream overlap the next kernel; wall clock over all "
-                        "steps incl. the final drain. synchronised_* = the same with render_to_host and a stream sync every step"},
-        "gpu_launches": int(args.steps),
+                "synchronised_value": rays_per_frame * e2e_frames / (e2e_sync_ms_total * 1e-3) / 1e6,
+                "id_distance": {"value": rays_per_frame * e2e_frames / (e2e_8b_ms_total * 1e-3) / 1e6, "ms_per_step": e2e_8b_ms_total / args.steps,
+                                "d2h_bytes_per_step": 8 * n_px * (world if mode == "poses" else 1),
+                                "note": "svx_view_render_to_host with albedo = NULL: hit id and distance planes only, 8 B/pixel; albedo "
+                                        "of a pixel is palette[hit_id & 0xFFFF], a lookup in a table the host already holds"},
+                "host_planes": ("POSIX shared memory mapped by every rank, " if shared is not None else "") + ("page-locked" if pinned else "PAGEABLE (pinning failed)"),
+                **({"host_assembled_frame_equals_single_gpu_frame": e2e_equal} if shared is not None else {}),
+                "note": ("per step and rank: view.set_viewport(pose) + view.render_to_host_async(shared host planes) on the rank's shard: its "
+                         "kernel renders its bands, strided device->host copies put exactly those rows into the common frame, each GPU over its own "
+                         "PCIe link; " if tiles else
+                         "per step: view.set_viewport(pose) + view.render_to_host_async(pinned hit_id, albedo, distance) + wait for the previous frame; ")
+                        + "two host plane sets, copies on a second stream overlap the next kernel; wall clock over all steps incl. the final drain"
+                          " (and a barrier over the ranks). synchronised_* = the same with render_to_host and a stream sync every step"},
+        "gpu_launches": int(args.steps * launches_per_step),
         "gpu_launches_total_incl_warmup_and_e2e": int(view.launch_count() + (e2e_view.launch_count() if e2e_view is not view else 0)),
         "clocks": clocks,
     }
+    if shared is not None:
+        shared.close()
 
-    if rank == 0:
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-        traffic = None
-        tpath = ROOT / "profiles" / "ncu_traffic.json"
-        if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get(args.workload)
-        if not args.no_cpu_baseline:
-            import oracle_lib as O
-
-            t0 = time.time()
-            otree = scenes.build_tree(scene, O.OracleOctree)
-            enable_mips(args, oracle_tree=otree)
-            t_obuild = time.time() - t0
-            o = oracle_timed_sample(otree, cams[0], res, args.cpu_budget, whole_frames=args.workload not in HEAVY, vd=vd)
-            f = o["frame"]
-            # algorithmic bytes of ONE launch (pose 0): counted on the sampled rays, scaled to the frame when sampled
-            scale = rays_per_frame / o["rays"]
-            alg_bytes = 12 * rays_per_frame + (16 * f["node_iters"] + 4 * f["voxel_fetches"]) * scale
-            t_kernel = dev_ms_total / args.steps * 1e-3
-            achieved = alg_bytes * (rays_per_rank_step / rays_per_frame) / t_kernel / 1e9
-            # the same figure without the restarts the kernel fast-forwards in closed form (crawl iterations: the root
-            # fails its occupancy test and is popped; 16 B each in the reference, no memory access at all here)
-            alg_bytes_nocrawl = alg_bytes - 16 * f["crawl_iters"] * scale
-            achieved_nocrawl = alg_bytes_nocrawl * (rays_per_rank_step / rays_per_frame) / t_kernel / 1e9
-            line["roofline"] = {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "achieved_excluding_fast_forwarded_restarts": achieved_nocrawl, "frac_excluding_fast_forwarded_restarts": achieved_nocrawl / peak,
-                "peak_source": peak_src,
-                # kernels.cu: launch_render picks the instantiation for the tree's brick dimension (8 / 32: compile-time strides)
-                "kernel": ("svx::render_lod_kernel" if args.mips is not None else "svx::render_kernel")
-                          + {8: "_brick8", 32: "_brick32"}.get(int(scene.brick_dim), ""),
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "per_ray": {"node_visits": f["node_iters"] / o["rays"], "voxel_fetches": f["voxel_fetches"] / o["rays"],
-                            "restarts": f["outer_iters"] / o["rays"], "crawl_restarts": f["crawl_iters"] / o["rays"],
-                            "bytes": alg_bytes / rays_per_frame,
-                            "rays_entering_root": f["rays_in_root"] / o["rays"]},
-                "compulsory_bound_ms": (st["total_bytes"] + 12 * rays_per_frame) / (peak * 1e9) * 1e3,
-                "note": "B_ray = 12 + 16 N_node + 4 N_vox, N counted by the CPU oracle executing the reference algorithm on "
-                        + ("the same rays" if scale == 1 else "a row sample of the same frame, scaled")
-                        + " (SURVEY 8(d)). A frac above 1 on crawl-heavy scenes is not skipped work: the reference's 0.1-nudge restarts"
-                          " (crawl_restarts per ray, 16 B each in the formula) are applied in closed form, bit-exactly, without touching memory;"
-                          " frac_excluding_fast_forwarded_restarts leaves them out. ncu: the kernel is instruction-issue bound over an L1/L2-resident tree, DRAM traffic is negligible",
-            }
-            line["cpu_baseline"] = {"value": o["mrays"], "unit": UNIT, "cores": o["threads"], "kind": "port", "sample": o["sample"],
-                                    "oracle_tree_build_s": round(t_obuild, 2)}
-            # the reference's own caller loop is single-threaded (examples/cpu_render.rs:104-105): the same on ONE host
-            # thread, on a row sample sized for about two seconds
-            try:  # an auxiliary figure: it must never cost the bench line
-                per_row_1t = o["seconds"] / len(o["rows"]) * o["threads"]
-                rows_1t = sample_rows(res[1], int(min(res[1], max(8, 2.0 / max(per_row_1t, 1e-6)))))
-                f1 = otree.render(oracle_camera(cams[0]), res[0], res[1], threads=1, row_list=rows_1t, viewing_distance=vd)
-                line["cpu_baseline"]["single_thread_value"] = len(rows_1t) * res[0] / f1["seconds"] / 1e6
-                line["cpu_baseline"]["single_thread_sample"] = f"{len(rows_1t)} of {res[1]} image rows ({len(rows_1t) * res[0]} rays) on 1 host thread"
+    if rank == 0 and not args.no_cpu_baseline:
+        chk = new_view()
+        leg = oracle_leg(args.workload, scene, cams[0], res, vd, args, dev_ms_total / args.steps, rays_per_rank_step, st["total_bytes"],
+                         chk.render_to_host, mips_tree=tree)
+        if tiles:
+            leg["roofline"]["note"] += (". N > 1: the launch is rank 0's share of the frame and its duration the whole step (viewport kernel + "
+                                        "wait for the slowest peer), so this frac is a lower bound for the kernel itself")
+        line.update(leg)
+    if not args.no_extra and args.mips is None:
+        extra = {}
+        if world == 1:
+            for name in ("dot_cube_1080p", "minecraft_4k", "terrain_poses_1080p"):
+                if name == args.workload:
+                    continue
+                try:
+                    extra[name] = extra_single_gpu(name, args, local_rank)
+                except Exception as e:  # noqa: BLE001  an extra workload must never cost the headline line
+                    extra[name] = {"error": repr(e)}
+        elif tiles:
+            try:
+                name, out = extra_pose_batch(args, rank, local_rank, world, dist, torch)
+                extra[name] = out
             except Exception as e:  # noqa: BLE001
-                line["cpu_baseline"]["single_thread_value"] = None
-                line["cpu_baseline"]["single_thread_sample"] = f"failed: {e}"
-            # parity spot check of what was just timed (outside every timed region): pose 0, the sampled rows
-            chk = new_view()
-            got = chk.render_to_host()
-            rows = o["rows"]
-            line["parity_vs_oracle"] = {
-                "rows_checked": int(len(rows)),
-                "hit_id_equal": bool(np.array_equal(got["hit_id"][rows], f["hit_id"][rows])),
-                "albedo_equal": bool(np.array_equal(got["albedo"][rows], f["albedo"].view(np.uint32)[..., 0][rows])),
-                "distance_bits_equal": bool(np.array_equal(got["distance"][rows].view(np.uint32), f["distance"][rows].view(np.uint32))),
-                "would_panic": int(f["would_panic"]),
-                **({"mip_probes": int(f["mip_probes"]), "mip_hash_equal": bool(tree.albedo_mip_map_resampling_strategy().mip_hash() == otree.mip_hash())}
-                   if args.mips is not None else {}),
-            }
-        if args.extra and world == 1:
-            extra = {}
-            for name in ("dot_cube_1080p_fov", "cpu_render_1080p", "cpu_render_4k", "dot_cube_4k"):
-                sc2, cams2, res2, _ = make_workload(name)
-                tr2 = scenes.build_tree(sc2, S.Octree) if sc2.name != scene.name else tree
-                h2 = S.OctreeGPUHost(tr2, local_rank)
-                v2 = h2.create_new_view(64, S.Viewport(cams2[0].origin, cams2[0].direction, cams2[0].frustum, cams2[0].fov), res2)
-                if cams2[0].glass_at_frustum_z:
-                    v2.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
-                ms = []
-                for i in range(13):
-                    v2.flush_l2()
-                    k = v2.render(sync=True)["kernel_ms"]
-                    if i >= 3:
-                        ms.append(k)
-                extra[name] = {"ms_per_frame": float(np.mean(ms)), "mrays_per_s": res2[0] * res2[1] / (np.mean(ms) * 1e-3) / 1e6}
-            line["extra_workloads"] = extra
+                extra["terrain_poses_1080p"] = {"error": repr(e)}
+        line["extra_workloads"] = extra
+    if rank == 0:
         print(json.dumps(line))
-    if tiles and args.mode == "tiles_fused" and rank != 0:
-        view.set_peer_frame_ipc(None)
+    if mode == "tiles_fused":
+        if dist is not None:
+            dist.barrier()
+        if rank != 0:
+            view.gather_close()
     if dist is not None:
         dist.barrier()
+        if rank == 0 and mode == "tiles_fused":
+            view.gather_close()
         dist.destroy_process_group()
     return 0
 

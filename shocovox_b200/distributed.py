@@ -105,3 +105,54 @@ def open_gather(view, rank: int, world: int, band: int = 8, wire: int = 0, group
         view.gather_join(rank, handle)
     dist.barrier(group)  # every peer has mapped the root's frame before the first frame is rendered
     return handle
+
+
+class SharedPinnedPlanes:
+    """`sets` x (hit_id u32, albedo u32, distance f32) full-frame host planes in ONE POSIX shared-memory file that every
+    rank maps and page-locks (cudaHostRegister), so that each rank's GPU copies the rows it rendered straight into the
+    common frame over its own PCIe link (svx_view_render_to_host on a sharded view). Rank 0 creates and unlinks the file."""
+
+    def __init__(self, tag: str, n_px: int, sets: int, rank: int, group=None):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        self.path = f"/dev/shm/svx_planes_{tag}"
+        self.rank = rank
+        nbytes = sets * 3 * n_px * 4
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        dist.barrier(group)
+        self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(nbytes,))
+        self.ptr = self.map.ctypes.data
+        self.nbytes = nbytes
+        self.map[:] = 0  # touch every page before pinning
+        rc = torch.cuda.cudart().cudaHostRegister(self.ptr, nbytes, 0)
+        self.pinned = int(rc) == 0
+        self.sets = []
+        for s in range(sets):
+            base = s * 3 * n_px * 4
+            self.sets.append([self.ptr + base, self.ptr + base + n_px * 4, self.ptr + base + 2 * n_px * 4])
+        self.n_px = n_px
+        dist.barrier(group)
+
+    def plane(self, s: int, k: int, dtype):
+        import numpy as np
+
+        off = (s * 3 + k) * self.n_px * 4
+        return self.map[off:off + self.n_px * 4].view(dtype)
+
+    def close(self, group=None):
+        import os
+        import torch
+        import torch.distributed as dist
+
+        if self.pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.ptr)
+        dist.barrier(group)
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass

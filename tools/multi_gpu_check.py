@@ -1,7 +1,10 @@
 #!/usr/bin/env python3
-"""Run under torchrun (one rank per GPU): one frame split into row bands over the ranks must equal the 1-GPU frame
-byte for byte, for (a) the NCCL all-gather of compact bands and (b) the fused variant where every rank's traversal
-kernel stores straight into rank 0's framebuffer through CUDA-IPC peer mappings. Also times both.
+"""Run under torchrun (one rank per GPU): ONE frame split into row bands over the ranks must equal the 1-GPU frame byte
+for byte, for
+  (a) the fused gather (csrc/multi_gpu.cu): every rank's viewport kernel stores straight into rank 0's framebuffer
+      through a CUDA-IPC mapping, go / done flags on the devices, no host barrier per frame - both wire formats;
+  (b) the comparison path: compact bands + one NCCL all-gather per plane + de-interleave (shocovox_b200.distributed).
+Also times both (device events on rank 0 for (a): viewport kernel + wait for the slowest peer).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/multi_gpu_check.py [--workload cpu_render_1080p] [--steps 20]
@@ -29,6 +32,7 @@ def main():
     ap.add_argument("--workload", default="cpu_render_1080p")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--band", type=int, default=8)
+    ap.add_argument("--skip-nccl", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local_rank)
@@ -46,6 +50,9 @@ def main():
             v.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
         return v
 
+    def same(got, ref):
+        return all(bool(np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32))) for k in ("hit_id", "albedo", "distance"))
+
     report = {"world": world, "workload": args.workload, "resolution": list(res)}
     # reference frame: every rank renders the full frame alone (also the 1-GPU timing)
     full = new_view()
@@ -55,78 +62,77 @@ def main():
         full.flush_l2()
         ms.append(full.render(sync=True)["kernel_ms"])
     report["single_gpu_ms"] = float(np.mean(ms))
+    ok_all = True
 
-    # (a) compact bands + NCCL all-gather
-    lr = D.padded_local_rows(h, world, args.band)
-    va = new_view()  # framebuffer is (h, w); only the first `lr` rows are used when compact
-    va.set_shard(rank, world, args.band)
-    va.set_compact_rows(True)
-    ptrs = va.frame_pointers()
-    planes = [D.device_tensor(p, (h, w), dt, local_rank)[:lr] for p, dt in zip(ptrs, ("<i4", "<i4", "<f4"))]
-    stream = torch.cuda.ExternalStream(va.cuda_stream(), device=local_rank)
-
-    def step_a():
-        va.render(sync=False)
-        with torch.cuda.stream(stream):
-            return [D.gather_bands(p, h, world, args.band) for p in planes]
-
-    out = step_a()
-    torch.cuda.synchronize()
-    ok_a = True
-    for got, name in zip(out, ("hit_id", "albedo", "distance")):
-        ok_a &= bool(np.array_equal(got.cpu().numpy().view(np.uint32), ref[name].view(np.uint32)))
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_a()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t_a = (time.perf_counter() - t0) / args.steps * 1e3
-    report["nccl_gather"] = {"equal_to_single_gpu": ok_a, "ms_per_frame_wall": t_a}
-
-    # (b) fused: kernels store straight into rank 0's framebuffer over NVLink (CUDA IPC peer mapping)
-    target = new_view()  # rank 0's is the destination
-    blob = D.exchange_ipc_handles(target.export_frame_ipc(), src_rank=0)
-    vb = new_view()
-    vb.set_shard(rank, world, args.band)
-    if rank != 0:
-        vb.set_peer_frame_ipc(blob)
-    else:
-        # rank 0 renders its own bands into the same destination buffers
-        vb = target
-        vb.set_shard(0, world, args.band)
-
-    def step_b():
-        vb.render(sync=False)
-        vb.synchronize()
-
-    step_b()
-    dist.barrier()
-    ok_b = True
-    if rank == 0:
-        p = target.frame_pointers()
-        for ptr, dt, name in zip(p, ("<i4", "<i4", "<f4"), ("hit_id", "albedo", "distance")):
-            got = D.device_tensor(ptr, (h, w), dt, local_rank).cpu().numpy()
-            ok_b &= bool(np.array_equal(got.view(np.uint32), ref[name].view(np.uint32)))
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_b()
+    # (a) fused gather, both wire formats
+    for wire, name in ((S.WIRE_THREE_PLANES, "fused_12B"), (S.WIRE_ID_DISTANCE, "fused_8B")):
+        v = new_view()
+        D.open_gather(v, rank, world, args.band, wire)
+        ok = True
+        for i in range(3):  # several frames: the sequence numbers advance on every member
+            v.render(sync=False)
+            v.synchronize()
+            if rank == 0:
+                ok &= same(v.read_frame(), ref)
         dist.barrier()
-    torch.cuda.synchronize()
-    t_b = (time.perf_counter() - t0) / args.steps * 1e3
-    report["fused_peer_stores"] = {"equal_to_single_gpu": ok_b if rank == 0 else None, "ms_per_frame_wall": t_b}
-    flags = torch.tensor([int(ok_a), int(ok_b)], device=f"cuda:{local_rank}")
-    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    if rank != 0:
-        vb.set_peer_frame_ipc(None)
-    dist.barrier()
+        times = []
+        for i in range(args.steps):
+            v.flush_l2()
+            if rank == 0:
+                times.append(v.render(sync=True)["kernel_ms"])
+            else:
+                v.render(sync=False)
+        v.synchronize()
+        dist.barrier()
+        if rank == 0:
+            ok &= same(v.read_frame(), ref)
+        flag = torch.tensor([int(ok)], device=f"cuda:{local_rank}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok_all &= bool(flag.item())
+        report[name] = {"equal_to_single_gpu": bool(flag.item()), "ms_per_frame_device": float(np.mean(times)) if times else None}
+        dist.barrier()
+        if rank != 0:
+            v.gather_close()
+        dist.barrier()
+        if rank == 0:
+            v.gather_close()
+
+    # (b) compact bands + NCCL all-gather
+    if not args.skip_nccl:
+        lr = D.padded_local_rows(h, world, args.band)
+        va = new_view()  # framebuffer is (h, w); only the first `lr` rows are used when compact
+        va.set_shard(rank, world, args.band)
+        va.set_compact_rows(True)
+        ptrs = va.frame_pointers()
+        planes = [D.device_tensor(p, (h, w), dt, local_rank)[:lr] for p, dt in zip(ptrs, ("<i4", "<i4", "<f4"))]
+        stream = torch.cuda.ExternalStream(va.cuda_stream(), device=local_rank)
+
+        def step_a():
+            va.render(sync=False)
+            with torch.cuda.stream(stream):
+                return [D.gather_bands(p, h, world, args.band) for p in planes]
+
+        out = step_a()
+        torch.cuda.synchronize()
+        ok_a = all(bool(np.array_equal(got.cpu().numpy().view(np.uint32), ref[name].view(np.uint32)))
+                   for got, name in zip(out, ("hit_id", "albedo", "distance")))
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_a()
+        torch.cuda.synchronize()
+        dist.barrier()
+        flag = torch.tensor([int(ok_a)], device=f"cuda:{local_rank}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok_all &= bool(flag.item())
+        report["nccl_gather"] = {"equal_to_single_gpu": bool(flag.item()), "ms_per_frame_wall": (time.perf_counter() - t0) / args.steps * 1e3}
     if rank == 0:
-        report["all_ranks_ok"] = bool(flags.min().item() == 1)
+        report["all_ranks_ok"] = ok_all
         print(json.dumps(report))
+    dist.barrier()
     dist.destroy_process_group()
-    return 0 if flags.min().item() == 1 else 1
+    return 0 if ok_all else 1
 
 
 if __name__ == "__main__":
