@@ -145,11 +145,6 @@ typedef struct svx_upload_stats {
 SVX_API const char* svx_version(void);
 SVX_API const char* svx_last_error_message(void); /* thread-local text of the last failing call */
 SVX_API int32_t svx_cuda_device_count(void);      /* 0 when no usable CUDA device exists */
-/* Device self-test of the shared-reciprocal form of the per-ray divisions (csrc/traverse.cuh: Reciprocal / div_by, an
- * experimental kernel option that is off by default): compares it with the IEEE `a / b` on `n` pseudo-random operand pairs
- * inside the range the kernels would use it for. `mismatches` must come back 0 before a build with that option may ship.
- * Mirrors the role of the reference's own arithmetic KATs (src/spatial/math/tests.rs). SVX_E_CUDA without a device. */
-SVX_API int32_t svx_selftest_division(int32_t device, uint64_t n, uint64_t seed, uint64_t* mismatches, uint64_t* tested);
 
 /* ---- Octree: construction and point queries (host) --------------------------------------------------- */
 /* Octree::new, src/octree/mod.rs:173-205 (validation order kept: brick dimension, size, structure) */
@@ -223,6 +218,20 @@ SVX_API void svx_bytes_free(uint8_t* bytes);
 SVX_API int32_t svx_octree_from_bytes(const uint8_t* bytes, uint64_t len, svx_octree** out);
 SVX_API int32_t svx_octree_save(const svx_octree* tree, const char* path);
 SVX_API int32_t svx_octree_load(const char* path, svx_octree** out);
+
+/* MagicaVoxel `.vox` import. Octree::load_vox_file(filename, brick_dimension), src/convert/magicavoxel.rs:266-289: the
+ * scene graph of frame 0 is walked (iterate_vox_tree, :105-197), models are placed at translation - size/2 with their
+ * 90-degree rotations (:349-385), converted from MagicaVoxel's right-handed z-up to the crate's left-handed y-up (swap of
+ * y and z), shifted to the minimum corner, and every voxel is inserted as a Visual entry with its palette colour; the
+ * tree size is the next power of two of the largest extent (:266-271). SVX_E_DECODE for a malformed file, for a file
+ * without RGBA chunk (MagicaVoxel's built-in default palette is not reproduced) or without a scene graph (the reference
+ * panics); SVX_E_INVALID_* when Octree::new refuses (size, brick_dim) - the reference panics there as well.
+ * MIPMapStrategy::load_vox_file (:207-250) = svx_vox_required_tree_size + svx_octree_new + the svx_octree_mip_* settings +
+ * svx_octree_insert_vox: the strategy is installed on the empty tree, every insert then refreshes the MIPs as it goes. */
+SVX_API int32_t svx_octree_load_vox(const char* path, uint32_t brick_dim, svx_octree** out);
+SVX_API int32_t svx_octree_load_vox_bytes(const uint8_t* bytes, uint64_t len, uint32_t brick_dim, svx_octree** out);
+SVX_API int32_t svx_vox_required_tree_size(const uint8_t* bytes, uint64_t len, uint32_t* tree_size);
+SVX_API int32_t svx_octree_insert_vox(svx_octree* tree, const uint8_t* bytes, uint64_t len); /* load_vox_data_internal, :349-385 */
 
 /* ---- OctreeGPUHost: render-data upload ---------------------------------------------------------------- */
 /* OctreeGPUHost{tree}, src/raytracing/bevy/types.rs:80-87. Serialises the WHOLE tree into coalesced SoA

@@ -137,7 +137,6 @@ assert VIEWPORT_DTYPE.itemsize == C.sizeof(_Viewport)
 # every symbol include/shocovox_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "svx_version", "svx_last_error_message", "svx_cuda_device_count",
-    "svx_selftest_division",
     "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
     "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
     "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count", "svx_octree_render_data_nodes", "svx_octree_render_data_nodes_with_mips", "svx_octree_render_data_bricks", "svx_render_data_ray_lut",
@@ -148,6 +147,7 @@ EXPORTS = [
     "svx_octree_get_by_ray", "svx_octree_get_by_ray_at_lod", "svx_view_reload",
     "svx_view_set_shading", "svx_view_read_shaded", "svx_view_shaded_pointer",
     "svx_octree_to_bytes", "svx_bytes_free", "svx_octree_from_bytes", "svx_octree_save", "svx_octree_load",
+    "svx_octree_load_vox", "svx_octree_load_vox_bytes", "svx_vox_required_tree_size", "svx_octree_insert_vox",
     "svx_gpu_host_create", "svx_gpu_host_free", "svx_gpu_host_reload", "svx_gpu_host_last_upload", "svx_gpu_host_stats", "svx_gpu_host_get_by_rays",
     "svx_gpu_host_create_view", "svx_view_free", "svx_view_get_viewport", "svx_view_set_viewport",
     "svx_view_set_glass_mode", "svx_view_set_resolution", "svx_view_resolution", "svx_view_set_shard",
@@ -182,7 +182,6 @@ def lib() -> C.CDLL:
     L.svx_version.restype = C.c_char_p
     L.svx_last_error_message.restype = C.c_char_p
     L.svx_cuda_device_count.restype = i32
-    L.svx_selftest_division.argtypes = [i32, u64, u64, C.POINTER(u64), C.POINTER(u64)]
     L.svx_octree_new.argtypes = [u32, u32, C.POINTER(vp)]
     L.svx_octree_free.argtypes = [vp]
     L.svx_octree_free.restype = None
@@ -205,6 +204,10 @@ def lib() -> C.CDLL:
     L.svx_octree_from_bytes.argtypes = [C.c_char_p, u64, C.POINTER(vp)]
     L.svx_octree_save.argtypes = [vp, C.c_char_p]
     L.svx_octree_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.svx_octree_load_vox.argtypes = [C.c_char_p, u32, C.POINTER(vp)]
+    L.svx_octree_load_vox_bytes.argtypes = [C.c_char_p, u64, u32, C.POINTER(vp)]
+    L.svx_vox_required_tree_size.argtypes = [C.c_char_p, u64, C.POINTER(u32)]
+    L.svx_octree_insert_vox.argtypes = [vp, C.c_char_p, u64]
     L.svx_octree_structure_hash.argtypes = [vp]
     L.svx_octree_structure_hash.restype = u64
     L.svx_octree_node_count.argtypes = [vp]
@@ -532,6 +535,30 @@ class Octree:
         return cls._adopt(h)
 
     # `Octree::get_by_ray(&Ray)`: one ray, on the GPU (a host is created on first use and reloaded after edits)
+    @classmethod
+    def load_vox_file(cls, filename, brick_dimension: int, mip_strategy=None) -> "Octree":
+        """`Octree::load_vox_file(filename, brick_dimension)` (src/convert/magicavoxel.rs:266-289); `filename` may also be
+        the file's bytes. mip_strategy = callable(StrategyUpdater) applied to the EMPTY tree before the voxels go in -
+        `MIPMapStrategy::default().set_enabled(true).load_vox_file(..)` of examples/minecraft.rs:57-60 is
+        `mip_strategy=lambda s: s.switch_albedo_mip_maps(True)` (magicavoxel.rs:207-250)."""
+        data = bytes(filename) if isinstance(filename, (bytes, bytearray)) else None
+        if mip_strategy is None:
+            h = C.c_void_p()
+            if data is None:
+                _check(lib().svx_octree_load_vox(str(filename).encode(), int(brick_dimension), C.byref(h)))
+            else:
+                _check(lib().svx_octree_load_vox_bytes(data, len(data), int(brick_dimension), C.byref(h)))
+            return cls._adopt(h)
+        if data is None:
+            with open(filename, "rb") as f:
+                data = f.read()
+        size = C.c_uint32()
+        _check(lib().svx_vox_required_tree_size(data, len(data), C.byref(size)))
+        tree = cls(int(size.value), int(brick_dimension))
+        mip_strategy(tree.albedo_mip_map_resampling_strategy())
+        _check(lib().svx_octree_insert_vox(tree.handle, data, len(data)))
+        return tree
+
     def get_by_ray(self, ray: Ray, device: int = 0) -> Optional[RayHit]:
         return self.get_by_ray_at_lod(ray, F32_MAX, device)
 

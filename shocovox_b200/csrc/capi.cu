@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "capi_internal.hpp"
+#include "vox_import.hpp"
 
 using namespace svx;
 
@@ -21,6 +23,15 @@ using namespace svx;
 
 namespace {
 thread_local std::string g_last_error;
+// SVX_DEBUG_CUDA=1: report (and clear) an error some earlier runtime call left behind, at the named point
+void debug_stale(const char* where) {
+    static const bool on = std::getenv("SVX_DEBUG_CUDA") != nullptr;
+    if (!on) return;
+    const cudaError_t e = cudaGetLastError();
+    int dev = -1;
+    cudaGetDevice(&dev);
+    std::fprintf(stderr, "[svx] %s: last error %s, current device %d\n", where, cudaGetErrorName(e), dev);
+}
 }
 namespace svx {
 int32_t fail(int32_t code, const std::string& msg) {
@@ -260,6 +271,7 @@ int32_t upload(svx_gpu_host* h) {
         CUDA_TRY(cudaMemcpyAsync(h->d_data_palette, tables.data(), tables.size() * 4, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaMemcpyAsync(h->d_handles, handles.data(), handles.size() * 4, cudaMemcpyHostToDevice, h->stream));
         up.bytes += (tables.size() + handles.size()) * 4;
+        debug_stale("upload: before the occupancy-bit launch");
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         CUDA_TRY(cudaEventCreate(&e0));
         CUDA_TRY(cudaEventCreate(&e1));
@@ -630,24 +642,6 @@ int32_t svx_cuda_device_count(void) {
     return n;
 }
 
-int32_t svx_selftest_division(int32_t device, uint64_t n, uint64_t seed, uint64_t* mismatches, uint64_t* tested) {
-    if (!mismatches || !tested) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
-    *mismatches = *tested = 0;
-    if (svx_cuda_device_count() <= device || device < 0) return fail(SVX_E_CUDA, "no such CUDA device");
-    CUDA_TRY(cudaSetDevice(device));
-    unsigned long long* counts = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&counts, 16));
-    unsigned long long host[2] = {0, 0};
-    cudaError_t e = cudaMemset(counts, 0, 16);
-    if (e == cudaSuccess) e = launch_div_selftest(n, seed, counts, 0);
-    if (e == cudaSuccess) e = cudaMemcpy(host, counts, 16, cudaMemcpyDeviceToHost);
-    cudaFree(counts);
-    if (e != cudaSuccess) return cuda_fail(e, "division self-test");
-    *mismatches = host[0];
-    *tested = host[1];
-    return SVX_OK;
-}
-
 // ---- octree ---------------------------------------------------------------------------------------------------
 int32_t svx_octree_new(uint32_t size, uint32_t brick_dim, svx_octree** out) {
     if (!out) return fail(SVX_E_INVALID_ARGUMENT, "out is null");
@@ -817,6 +811,35 @@ int32_t svx_octree_load(const char* path, svx_octree** out) {
     return wrap_tree(s, tree, out, "cannot load an Octree from the file");
 }
 
+// ---- MagicaVoxel import: Octree::load_vox_file, src/convert/magicavoxel.rs:266-289 -----------------------------------------
+int32_t svx_octree_load_vox_bytes(const uint8_t* bytes, uint64_t len, uint32_t brick_dim, svx_octree** out) {
+    if (!bytes || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    HostOctree* tree = nullptr;
+    std::string why;
+    const int32_t s = vox_load(bytes, (size_t)len, brick_dim, &tree, &why);
+    return wrap_tree(s, tree, out, why.c_str());
+}
+int32_t svx_octree_load_vox(const char* path, uint32_t brick_dim, svx_octree** out) {
+    if (!path || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    std::vector<uint8_t> bytes;
+    if (vox_read_file(path, &bytes) != SVX_OK) return fail(SVX_E_IO, "cannot read the file");
+    return svx_octree_load_vox_bytes(bytes.data(), bytes.size(), brick_dim, out);
+}
+int32_t svx_vox_required_tree_size(const uint8_t* bytes, uint64_t len, uint32_t* tree_size) {
+    if (!bytes || !tree_size) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::string why;
+    const int32_t s = vox_required_tree_size(bytes, (size_t)len, tree_size, &why);
+    return s == SVX_OK ? SVX_OK : fail(s, why);
+}
+int32_t svx_octree_insert_vox(svx_octree* t, const uint8_t* bytes, uint64_t len) {
+    if (!t || !bytes) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::string why;
+    const int32_t s = vox_insert_into(bytes, (size_t)len, t->tree, &why);
+    return s == SVX_OK ? SVX_OK : fail(s, why);
+}
+
 // ---- gpu host -------------------------------------------------------------------------------------------------
 int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host** out) {
     if (!tree || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
@@ -828,6 +851,7 @@ int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host
         return fail(SVX_E_CUDA, "no CUDA device available: the ray path has no CPU fallback");
     }
     if (device < 0 || device >= n) return fail(SVX_E_INVALID_ARGUMENT, "device index out of range");
+    debug_stale("svx_gpu_host_create: entry");
     CUDA_TRY(cudaSetDevice(device));
     svx_gpu_host* h = new (std::nothrow) svx_gpu_host();
     if (!h) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
@@ -860,6 +884,7 @@ int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host
         }
         h->dev.ray_lut = (const uint2*)h->d_ray_lut;
     }
+    debug_stale("svx_gpu_host_create: before upload");
     const int32_t s = upload(h);
     if (s != SVX_OK) {
         free_device_tree(h);

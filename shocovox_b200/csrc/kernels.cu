@@ -99,15 +99,7 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
         RayConst r;
         const float len = sqrtf((vx * vx) + (vy * vy) + (vz * vz));
         r.ox = f.ox; r.oy = f.oy; r.oz = f.oz;
-#if SVX_SHARED_RCP
-        if (div_operands_ok(vx, vy, vz) && div_operands_ok(len, len, len)) {  // `(glass_point - origin) / length`, one reciprocal
-            const Reciprocal rl = reciprocal_of(len);
-            r.dx = div_by(vx, rl); r.dy = div_by(vy, rl); r.dz = div_by(vz, rl);
-        } else
-#endif
-        {
-            r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
-        }
+        r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
         float px, py, pz;
         uint32_t target_octant;
         if (root_entry_and_setup(r, tree_size, px, py, pz, target_octant)) {
@@ -488,33 +480,6 @@ cudaError_t launch_occupancy_bits(const DeviceTree& tree, const uint32_t* tables
         const unsigned grid = (unsigned)std::min<uint64_t>((total_words + 31) / 32, machine);  // 32 words per CTA and step
         occupancy_bits_kernel<<<grid, 256, 0, stream>>>(tree, tables, color_words, data_words, handles, n, bits_out);
     }
-    return cudaGetLastError();
-}
-
-// Compares div_by(a, reciprocal_of(b)) (traverse.cuh: the shared-divisor form of the per-ray divisions) with the IEEE
-// `a / b` on pseudo-random operand pairs inside the range the kernels accept for it, every mantissa pattern equally
-// likely, exponents uniform in [-40, 40). counts[0] += pairs whose bits differ; counts[1] += pairs tested.
-__global__ void div_selftest_kernel(uint64_t n, uint64_t seed, unsigned long long* counts) {
-    unsigned long long bad = 0, done = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;  // splitmix64
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        z ^= z >> 31;
-        const uint32_t lo = (uint32_t)z, hi = (uint32_t)(z >> 32);
-        const float a = __uint_as_float((lo & 0x807FFFFFu) | ((87u + (lo >> 23) % 80u) << 23));
-        const float b = __uint_as_float((hi & 0x807FFFFFu) | ((87u + (hi >> 23) % 80u) << 23));
-        if (!div_operands_ok(a, b, b)) continue;
-        const float want = a / b, got = div_by(a, reciprocal_of(b));
-        bad += __float_as_uint(want) != __float_as_uint(got);
-        done += 1;
-    }
-    atomicAdd(&counts[0], bad);
-    atomicAdd(&counts[1], done);
-}
-
-cudaError_t launch_div_selftest(uint64_t n, uint64_t seed, unsigned long long* counts, cudaStream_t stream) {
-    div_selftest_kernel<<<148 * 8, 256, 0, stream>>>(n, seed, counts);
     return cudaGetLastError();
 }
 

@@ -99,8 +99,5 @@ cudaError_t launch_occupancy_bits(const DeviceTree& tree, const uint32_t* tables
 // Fills out[0..512) with RAY_TO_NODE mask words, out[512..520) octant masks, then 27*8 step results, evaluated by
 // the device closed forms; the host compares them with tables regenerated from the reference's generator logic.
 cudaError_t launch_lut_selftest(uint64_t* out /* device, 512 + 8 + 216 entries */, cudaStream_t stream);
-// counts[0] += operand pairs (of n pseudo-random ones) for which the shared-reciprocal division of traverse.cuh differs
-// from the IEEE `a / b`, counts[1] += pairs tested; counts = two device u64, zeroed by the caller
-cudaError_t launch_div_selftest(uint64_t n, uint64_t seed, unsigned long long* counts, cudaStream_t stream);
 
 }  // namespace svx

@@ -139,15 +139,6 @@ struct RayConst {
 #ifndef SVX_SINGLE_PROBE_SITE
 #define SVX_SINGLE_PROBE_SITE 1
 #endif
-// EXPERIMENTAL, off by default: the voxel step measures from the FAR plane of the current cell, `p - (corner + off)`, one packed
-// subtraction instead of two, whenever the walk is entered with p inside the brick (up to a quarter voxel). `p - corner`
-// is then exact on every step - corner is a multiple of unit, p lies within the cell up to a few ulp because every step
-// re-targets a plane of the current cell, so corner / 2 <= p <= 2 corner (Sterbenz) or corner = 0 - and
-// RN((p - corner) - off) = RN(p - (corner + off)) with corner + off exact (small integers). A walk entered from further
-// away (possible only after a MIP miss) keeps the two-subtraction form.
-#ifndef SVX_FAR_PLANE_DDA
-#define SVX_FAR_PLANE_DDA 0
-#endif
 #ifndef SVX_BRICK_WORD_ALWAYS
 #define SVX_BRICK_WORD_ALWAYS 1
 #endif
@@ -242,45 +233,6 @@ __device__ __forceinline__ void add_both_if_equal(float m, float d, float& a, fl
 // -0.0). And `negative ? 0 : v` from that: max(+-v, 0).
 __device__ __forceinline__ float with_sign_of(float v, float direction) {
     return __uint_as_float(__float_as_uint(v) | (__float_as_uint(direction) & 0x80000000u));
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Divisions that share a divisor (EXPERIMENTAL, off by default: SVX_SHARED_RCP).
-//
-// nvcc expands every IEEE `a / b` (div.rn.f32) into the same fast path - r0 = MUFU.RCP(b); e = fma(r0, -b, 1);
-// r = fma(r0, e, r0); q0 = a * r; rem = fma(q0, -b, a); q = fma(r, rem, q0) - guarded by FCHK(a, b), with a slow path for
-// operands near the ends of the exponent range. The per-ray set-up divides by each direction component four times (two
-// slab distances, two scale-factor ratios) and by the length three times, and every one of those expansions recomputes
-// the refined reciprocal r. `Reciprocal` computes r once per divisor and `div_by` is the remaining three operations of
-// the very same sequence, so the quotient is the fast path's, bit for bit. In place of FCHK a range test confines every
-// operand to [2^-40, 2^40] - far inside the region where no intermediate (r, q0, rem) can overflow, underflow or become
-// subnormal - and anything else takes the plain `/`. Before a build with SVX_SHARED_RCP=1 may ship, div_selftest_kernel
-// (kernels.cu, svx_selftest_division) must report zero mismatches against `/` on the device.
-#ifndef SVX_SHARED_RCP
-#define SVX_SHARED_RCP 0
-#endif
-struct Reciprocal {
-    float b, r;
-};
-__device__ __forceinline__ Reciprocal reciprocal_of(float b) {
-    float r0;
-#ifndef SVX_HOST_MIRROR
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b));
-#else
-    r0 = 1.0f / b;  // the host has no MUFU.RCP; only SVX_SHARED_RCP builds use this
-#endif
-    const float e = __fmaf_rn(r0, -b, 1.0f);
-    return Reciprocal{b, __fmaf_rn(r0, e, r0)};
-}
-__device__ __forceinline__ float div_by(float a, const Reciprocal& d) {
-    const float q0 = __fmul_rn(a, d.r);
-    const float rem = __fmaf_rn(q0, -d.b, a);
-    return __fmaf_rn(d.r, rem, q0);
-}
-// every |v| within [2^-40, 2^40] (false for NaN)
-__device__ __forceinline__ bool div_operands_ok(float a, float b, float c) {
-    const float lo = fminf(fminf(fabsf(a), fabsf(b)), fabsf(c)), hi = fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(c));
-    return a == a && b == b && c == c && lo >= 9.094947017729282e-13f && hi <= 1099511627776.0f;
 }
 
 // The part of ray_setup that does not divide
@@ -396,75 +348,6 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
 #if !SVX_BRICK_WORD_ALWAYS
     uint32_t nword_index = 0u;  // no complemented word index of a brick is 0 (their upper bits are set)
 #endif
-#if SVX_FAR_PLANE_DDA
-    // entered inside the brick (the unclamped cell coordinates are within a quarter voxel of it)? NaN fails
-    const float vx = (px - bx) * to_cells, vy = (py - by) * to_cells, vz = (pz - bz) * to_cells;
-    const bool inside = vx >= -0.25f && vy >= -0.25f && vz >= -0.25f && vx <= fdim + 0.25f && vy <= fdim + 0.25f && vz <= fdim + 0.25f;
-    float ex_ = ex, ey_ = ey, ez_ = ez;
-    if (inside) {  // corners and exit planes become far planes: + off (exact, small integers)
-        float ox_, oy_;
-        unpack2(offxy, ox_, oy_);
-        cx = cx + ox_; cy = cy + oy_; cz = cz + offz;
-        ex_ = ex + ox_; ey_ = ey + oy_; ez_ = ez + offz;
-    }
-    uint32_t nflat = 0u;
-    auto walk = [&](auto far) {
-        constexpr bool FAR = decltype(far)::value;
-        const float ex = ex_, ey = ey_, ez = ez_;
-    for (;;) {
-            nflat = mirrored ^ nflip;
-    #if SVX_BRICK_WORD_ALWAYS
-            // one L1-resident load per step instead of "same word as before?" bookkeeping: fewer issued instructions
-            word = __ldg(word_address(bits, (nflat >> 5) ^ 0x07FFFFFFu));
-    #else
-            if ((nflat >> 5) != nword_index) {
-                nword_index = nflat >> 5;
-                word = __ldg(word_address(bits, nword_index ^ 0x07FFFFFFu));
-            }
-    #endif
-            if ((int)(word << (nflat & 31u)) < 0) break;
-            float tx, ty;
-    #if SVX_FAR_PLANE_DDA
-            float tz;
-            if constexpr (FAR) {  // cx, cy, cz are the far planes here
-                unpack2(mul2(sub2(pxy, pack2(cx, cy)), sfxy), tx, ty);
-                tz = (pz - cz) * r.sfz;
-            } else {
-                unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
-                tz = ((pz - cz) - offz) * r.sfz;
-            }
-    #else
-            unpack2(mul2(sub2(sub2(pxy, pack2(cx, cy)), offxy), sfxy), tx, ty);
-            const float tz = ((pz - cz) - offz) * r.sfz;
-    #endif
-            const float d_x = fabsf(tx), d_y = fabsf(ty), d_z = fabsf(tz);
-            const float m = fminf(fminf(d_x, d_y), d_z);
-            float mx, my, qx, qy;
-            unpack2(mul2(dxy, pack2(m, m)), mx, my);
-            unpack2(pxy, qx, qy);
-            pxy = pack2(qx + mx, qy + my);
-            pz = pz + r.dz * m;
-            // `if (m == d) { mirrored += stride; corner += u; }` per axis, as predicated instructions
-    #ifndef SVX_HOST_MIRROR
-            asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
-                : "+r"(mirrored), "+f"(cx) : "f"(m), "f"(d_x), "r"(1u), "f"(ux));
-            asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
-                : "+r"(mirrored), "+f"(cy) : "f"(m), "f"(d_y), "r"(brick_dim_of<BS>(t)), "f"(uy));
-            asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %2, %3;\n\t@p add.u32 %0, %0, %4;\n\t@p add.rn.f32 %1, %1, %5;\n\t}"
-                : "+r"(mirrored), "+f"(cz) : "f"(m), "f"(d_z), "r"(brick_dim_sq_of<BS>(t)), "f"(uz));
-    #else
-            if (m == d_x) { mirrored += 1u; cx = cx + ux; }
-            if (m == d_y) { mirrored += brick_dim_of<BS>(t); cy = cy + uy; }
-            if (m == d_z) { mirrored += brick_dim_sq_of<BS>(t); cz = cz + uz; }
-    #endif
-            if (cx == ex || cy == ey || cz == ez) break;
-        }
-    };
-    if (inside) walk(std::true_type{}); else walk(std::false_type{});
-    const float ex_final = ex_, ey_final = ey_, ez_final = ez_;
-    unpack2(pxy, px, py);
-    return (cx == ex_final || cy == ey_final || cz == ez_final) ? -1 : (int)~nflat;
-#else
     uint32_t nflat;
     for (;;) {
         nflat = mirrored ^ nflip;
@@ -506,7 +389,6 @@ __device__ __forceinline__ int traverse_brick(const DeviceTree& t, const RayCons
     unpack2(pxy, px, py);
     // the walk ended on a set bit (corners strictly inside the brick) or by leaving it (a corner on the first plane outside)
     return (cx == ex || cy == ey || cz == ez) ? -1 : (int)~nflat;
-#endif
 #else
     uint32_t word_index = 0xFFFFFFFFu;
     for (;;) {
@@ -603,35 +485,11 @@ __device__ __forceinline__ bool root_entry(const RayConst& r, float tree_size, f
 // `min_step == distance` holds on no axis and nothing ever steps. One finite factor is enough (f32::min ignores NaN).
 __device__ __forceinline__ bool no_usable_scale_factor(const RayConst& r) { return r.sfx != r.sfx && r.sfy != r.sfy && r.sfz != r.sfz; }
 
-// root_entry followed by ray_setup, as the viewport kernels call them, with the twelve divisions by the direction's
-// components sharing one refined reciprocal per component when every operand is in the safe range (see Reciprocal);
-// otherwise exactly the two functions above.
+// root_entry followed by ray_setup, as the viewport kernels call them. (Sharing one refined reciprocal per divisor among
+// the twelve divisions was built, validated bit for bit and measured in round 2: 0-1.5 % slower on every scene - the range
+// guards cost what the shorter division sequences saved - and removed; profiles/r02_experiment_shared_rcp_far_plane.log.)
 __device__ __forceinline__ bool root_entry_and_setup(RayConst& r, float tree_size, float& px, float& py, float& pz,
                                                      uint32_t& target_octant) {
-#if SVX_SHARED_RCP
-    const float n1 = 0.0f - r.ox, n2 = tree_size - r.ox, n3 = 0.0f - r.oy, n4 = tree_size - r.oy, n5 = 0.0f - r.oz, n6 = tree_size - r.oz;
-    if (div_operands_ok(r.dx, r.dy, r.dz) && div_operands_ok(n1, n3, n5) && div_operands_ok(n2, n4, n6)) {
-        const Reciprocal rx = reciprocal_of(r.dx), ry = reciprocal_of(r.dy), rz = reciprocal_of(r.dz);
-        const float t1 = div_by(n1, rx), t2 = div_by(n2, rx);
-        const float t3 = div_by(n3, ry), t4 = div_by(n4, ry);
-        const float t5 = div_by(n5, rz), t6 = div_by(n6, rz);
-        const float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
-        const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
-        if (tmax < 0.0f || tmin > tmax) return false;
-        const float d = (tmin < 0.0f) ? 0.0f : tmin;
-        px = r.ox + r.dx * d;
-        py = r.oy + r.dy * d;
-        pz = r.oz + r.dz * d;
-        if (!all_finite(px, py, pz)) return false;
-        target_octant = hash_region(px, py, pz, tree_size * 0.5f);
-        auto sq = [](float v) { return v * v; };
-        r.sfx = sqrtf(1.0f + sq(div_by(r.dz, rx)) + sq(div_by(r.dy, rx)));
-        r.sfy = sqrtf(sq(div_by(r.dx, ry)) + 1.0f + sq(div_by(r.dz, ry)));
-        r.sfz = sqrtf((sq(div_by(r.dx, rz)) + 1.0f) + sq(div_by(r.dy, rz)));
-        ray_setup_signs(r);
-        return !no_usable_scale_factor(r);
-    }
-#endif
     if (!root_entry(r, tree_size, px, py, pz, target_octant)) return false;
     ray_setup(r);
     return !no_usable_scale_factor(r);

@@ -12,13 +12,16 @@ Follows the reference's loader (src/convert/magicavoxel.rs, which sits on the th
     (src/spatial/math/mod.rs:195-199), relative to the minimum corner found by `load_vox_file_internal` (:297-347);
   * tree size = next power of two of the largest extent (:266-271).
 
-The result is a voxel list in the reference's insertion order for `Octree.insert_batch`. Files without a scene graph
-(only SIZE/XYZI) are accepted too, as a single model at the origin.
+The result is a voxel list in the reference's insertion order for `Octree.insert_batch`.
 
-Parity status: UNPINNED. The reference's loader cannot be run here (Rust), and `dot_vox` is not in the checkout; the
-tests cover a writer/reader round trip, the rotation-byte known-answer test of magicavoxel.rs:392-413, and voxel counts
-of the reference's own small assets when they are present. Known divergence: files without an RGBA chunk get a neutral
-ramp instead of MagicaVoxel's built-in default palette (which `dot_vox` embeds and this repo does not).
+This module is the independent SECOND reader (numpy) that cross-checks the product's loader, csrc/vox_import.cpp behind
+`svx_octree_load_vox` / `Octree.load_vox_file`, plus a small `.vox` writer for tests. Like the C++ loader it refuses files
+without an RGBA chunk (dot_vox substitutes MagicaVoxel's built-in default palette, which is not reproduced here) and files
+without a scene graph (the reference panics on `vox_tree.scenes[0]`).
+
+Parity status: the parsing layer is UNPINNED (the reference's loader cannot be run here and `dot_vox` is not in the
+checkout); the placement arithmetic is pinned by the rotation known-answer test of magicavoxel.rs:392-413, and two
+independent implementations agree on the reference's own assets (tests/test_vox_import.py).
 """
 from __future__ import annotations
 
@@ -38,14 +41,8 @@ class VoxModel:
 @dataclass
 class VoxScene:
     models: List[VoxModel] = field(default_factory=list)
-    palette: np.ndarray = field(default_factory=lambda: default_palette())
+    palette: Optional[np.ndarray] = None  # the RGBA chunk; None = the file has none
     nodes: Dict[int, dict] = field(default_factory=dict)  # scene graph by node id
-
-
-def default_palette() -> np.ndarray:
-    """A neutral 256-entry RGBA ramp used when the file carries no RGBA chunk."""
-    i = np.arange(256, dtype=np.uint32)
-    return np.stack([(i * 37) & 0xFF, (i * 91) & 0xFF, (i * 151) & 0xFF, np.full(256, 255)], axis=1).astype(np.uint8)
 
 
 def parse_rotation_matrix(b: int) -> np.ndarray:
@@ -97,7 +94,7 @@ def parse_vox(data: bytes) -> VoxScene:
         elif cid == b"XYZI":
             (n,) = struct.unpack_from("<i", data, body)
             v = np.frombuffer(data, dtype=np.uint8, count=4 * n, offset=body + 4).reshape(n, 4).copy()
-            v[:, 3] = v[:, 3] - 1  # palette indices are 1-based in the file (wraps 0 -> 255 like dot_vox's u8 arithmetic)
+            v[:, 3] = np.where(v[:, 3] > 0, v[:, 3] - 1, 0)  # 1-based in the file; dot_vox: `i.saturating_sub(1)`
             scene.models.append(VoxModel(tuple(pending_size or (0, 0, 0)), v))
         elif cid == b"RGBA":
             pal = np.frombuffer(data, dtype=np.uint8, count=1024, offset=body).reshape(256, 4).copy()
@@ -136,10 +133,8 @@ def parse_vox(data: bytes) -> VoxScene:
 
 def iterate_models(scene: VoxScene, frame: int = 0):
     """iterate_vox_tree, magicavoxel.rs:105-197: yields (model, translation[3], rotation[3,3])."""
-    if not scene.nodes:
-        for m in scene.models:  # no scene graph: every model at the origin, unrotated
-            yield m, np.zeros(3, dtype=np.int64), np.eye(3, dtype=np.int64)
-        return
+    if 0 not in scene.nodes:
+        raise ValueError("no scene graph (the reference panics on vox_tree.scenes[0], magicavoxel.rs:112)")
     root = scene.nodes[0]
     if root["kind"] != "transform":
         raise ValueError("the root node of a MagicaVoxel scene graph should be a transform")
@@ -187,6 +182,8 @@ def load_vox(path_or_bytes, brick_dimension: int = 8):
     """-> (tree_size, xyz u32[n,3], rgba u8[n,4]) in the reference's insertion order (Octree::load_vox_file)."""
     data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else open(path_or_bytes, "rb").read()
     scene = parse_vox(bytes(data))
+    if scene.palette is None:
+        raise ValueError("no RGBA chunk: MagicaVoxel's built-in default palette is not reproduced by this reader")
     placed = list(iterate_models(scene, 0))
     if not placed:
         raise ValueError("no models in the file")

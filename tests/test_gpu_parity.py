@@ -549,12 +549,3 @@ def test_shaded_plane_is_the_callers_pixel():
 
 
 @pytest.mark.gpu
-def test_shared_reciprocal_division_equals_ieee_division():
-    """The experimental shared-divisor form of the per-ray divisions (traverse.cuh: Reciprocal / div_by, SVX_SHARED_RCP, off by
-    default) against div.rn.f32 on 2^28 pseudo-random operand pairs - the reference divides with IEEE `/` everywhere
-    (raytracing_on_cpu.rs:99-112, spatial/raytracing/mod.rs:32-61), so the option is only admissible while this stays at 0."""
-    import ctypes as C
-
-    bad, done = C.c_uint64(0), C.c_uint64(0)
-    assert S.lib().svx_selftest_division(0, 1 << 28, 20261017, C.byref(bad), C.byref(done)) == 0
-    assert done.value == 1 << 28 and bad.value == 0

@@ -51,12 +51,6 @@ def mirror():
     return build_mirror("host_mirror")
 
 
-@pytest.fixture(scope="module")
-def mirror_shared_rcp():
-    """the same with the experimental shared-reciprocal divisions of the per-ray set-up (SVX_SHARED_RCP=1, off in the library)"""
-    return build_mirror("host_mirror_shared_rcp", ["SVX_SHARED_RCP=1"])
-
-
 def bits(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return np.where(np.isnan(a), np.uint32(0x7FC00000), a.view(np.uint32))  # NaNs compare equal (0/0 normals at a cell centre)
@@ -158,39 +152,6 @@ def test_edits_are_followed(mirror):
                 else:
                     t.clear(p)
         assert_same_hits(mirror_rays(mirror, ptree.tree, rays), otree.get_by_rays(rays))
-
-
-@pytest.fixture(scope="module")
-def mirror_far_plane():
-    """the kernel code with the experimental far-plane form of the voxel step (SVX_FAR_PLANE_DDA=1, off in the library)"""
-    return build_mirror("host_mirror_far_plane", ["SVX_FAR_PLANE_DDA=1"])
-
-
-@pytest.mark.parametrize("name", ["cpu_render_64_8", "cpu_render_32_1", "dot_cube_128_32", "terrain_blocky_128_8"])
-def test_far_plane_voxel_step_keeps_every_bit(mirror_far_plane, name):
-    """SVX_FAR_PLANE_DDA=1: `p - (corner + off)` instead of `(p - corner) - off` for walks entered inside the brick. The claim
-    that the first subtraction is exact there (traverse.cuh, at the macro) is what this checks, plain and under LOD (MIP misses
-    are what can enter a walk from outside, the guarded fall-back)."""
-    scene = SCENES[name]()
-    tree, otree = scenes.build_tree(scene, S.Octree), scenes.build_tree(scene, O.OracleOctree)
-    rays = random_rays(scene.tree_size, 15000, 2 + zlib.crc32(name.encode()) % 1000)
-    assert_same_hits(mirror_rays(mirror_far_plane, tree, rays), otree.get_by_rays(rays))
-    tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
-    otree.switch_albedo_mip_maps(True)
-    for vd in (40.0, 2.0):
-        assert_same_hits(mirror_rays(mirror_far_plane, tree, rays[:5000], viewing_distance=vd), otree.get_by_rays_at_lod(rays[:5000], vd))
-
-
-@pytest.mark.parametrize("name", ["cpu_render_64_8", "dot_cube_128_32", "colonnade_256_8", "terrain_256_8_shell"])
-def test_shared_reciprocal_option_keeps_every_bit(mirror_shared_rcp, name):
-    """SVX_SHARED_RCP=1 (traverse.cuh: root_entry_and_setup with one refined reciprocal per divisor, off by default) must not
-    change a result: its wiring - which numerator meets which reciprocal, the range guards, the fall-back to plain `/` for
-    axis-parallel rays and origins on a bounding plane - is checked here; that the device's reciprocal sequence itself
-    equals div.rn is what svx_selftest_division checks on the GPU."""
-    scene = SCENES[name]()
-    tree, otree = scenes.build_tree(scene, S.Octree), scenes.build_tree(scene, O.OracleOctree)
-    rays = random_rays(scene.tree_size, 20000, 1 + zlib.crc32(name.encode()) % 1000)
-    assert_same_hits(mirror_rays(mirror_shared_rcp, tree, rays), otree.get_by_rays(rays))
 
 
 F32_MAX = 3.4028234663852886e38

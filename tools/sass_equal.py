@@ -15,7 +15,7 @@ import sass_loop as S  # noqa: E402
 KERNELS = ["render_kernel_brick32E", "render_kernel_brick8E", "render_kernelE", "render_lod_kernel_brick8E", "render_lod_kernel_brick32E",
            "render_lod_kernelE", "render_shaded_kernelE", "render_lod_shaded_kernelE", "render_kernel_persistentE",
            "render_lod_kernel_persistentE", "rays_kernelE", "rays_lod_kernelE", "occupancy_bits_kernelE", "occupancy_bits_small_kernelE",
-           "lut_selftest_kernelE", "div_selftest_kernelE"]
+           "lut_selftest_kernelE"]
 
 
 def normalised(lib: Path, kernel: str):
