@@ -285,20 +285,23 @@ def oracle_leg(name, scene, cam, res, vd, args, ms_per_launch, rays_per_launch, 
         traffic = json.loads(tpath.read_text()).get(name)
     out = {}
     out["roofline"] = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        # the primary figures charge only what the kernel cannot skip: restarts it resolves in closed form are left out
+        "bound": "hbm", "achieved": achieved_nocrawl, "peak": peak, "unit": "GB/s", "frac": achieved_nocrawl / peak, "traffic": traffic,
+        "achieved_task_definition": achieved, "frac_task_definition": achieved / peak,
         "achieved_excluding_fast_forwarded_restarts": achieved_nocrawl, "frac_excluding_fast_forwarded_restarts": achieved_nocrawl / peak,
         "peak_source": peak_src, "kernel": kernel_name(scene, args.mips is not None),
         "kernel_ms_per_launch": ms_per_launch, "rays_per_launch": rays_per_launch,
-        "algorithmic_bytes_per_launch": alg_bytes * share,
+        "algorithmic_bytes_per_launch": alg_bytes_nocrawl * share, "algorithmic_bytes_per_launch_task_definition": alg_bytes * share,
         "per_ray": {"node_visits": f["node_iters"] / o["rays"], "voxel_fetches": f["voxel_fetches"] / o["rays"],
                     "restarts": f["outer_iters"] / o["rays"], "crawl_restarts": f["crawl_iters"] / o["rays"],
                     "bytes": alg_bytes / rays_per_frame, "rays_entering_root": f["rays_in_root"] / o["rays"]},
         "compulsory_bound_ms": (tree_bytes + 12 * rays_per_frame) / (peak * 1e9) * 1e3,
         "note": "B_ray = 12 + 16 N_node + 4 N_vox, N counted by the CPU oracle executing the reference algorithm on "
                 + ("the same rays" if scale == 1 else "a row sample of the same frame, scaled")
-                + " (SURVEY 8(d)). A frac above 1 on crawl-heavy scenes is not skipped work: the reference's 0.1-nudge restarts"
-                  " (crawl_restarts per ray, 16 B each in the formula) are applied in closed form, bit-exactly, without touching memory;"
-                  " frac_excluding_fast_forwarded_restarts leaves them out. ncu: the kernel is instruction-issue bound over an L1/L2-resident tree, DRAM traffic is small",
+                + " (SURVEY 8(d)). `frac` / `achieved` leave out the 16 B of every 0.1-nudge restart in which the reference pops the root"
+                  " right away (crawl_restarts per ray): the kernel applies those in closed form, bit-exactly, without touching memory, so"
+                  " charging them would credit bytes that never move. *_task_definition charges them as SURVEY 8(d) literally says and exceeds"
+                  " 1 on crawl-heavy scenes for that reason. ncu: the kernel is instruction-issue bound over an L1/L2-resident tree, DRAM traffic is small",
     }
     out["cpu_baseline"] = {"value": o["mrays"], "unit": UNIT, "cores": o["threads"], "kind": "port", "sample": o["sample"],
                            "oracle_tree_build_s": round(t_obuild, 2)}
@@ -364,7 +367,7 @@ def extra_single_gpu(name, args, local_rank):
         leg = oracle_leg(name, scene, cams[0], res, F32_MAX, args, float(np.mean(ms0)), res[0] * res[1], out["tree_bytes"],
                          view.render_to_host, budget=min(args.cpu_budget, 4.0))
         out["roofline_frac"] = leg["roofline"]["frac"]
-        out["roofline"] = {k: leg["roofline"][k] for k in ("achieved", "peak", "frac", "frac_excluding_fast_forwarded_restarts", "kernel",
+        out["roofline"] = {k: leg["roofline"][k] for k in ("achieved", "peak", "frac", "frac_task_definition", "kernel",
                                                             "algorithmic_bytes_per_launch", "per_ray", "traffic")}
         out["cpu_baseline"] = leg["cpu_baseline"]
         out["parity_vs_oracle"] = leg["parity_vs_oracle"]
@@ -602,9 +605,15 @@ def main() -> int:
 
     def e2e_loop(planes_of, pipelined=True):
         """wall ms of `steps` frames: pose in, host planes out; planes_of(set) -> the three host pointers (0 = not delivered)"""
-        for i in range(3):
+        for i in range(4):  # warm-up through the SAME path as the timed frames (the pipelined one allocates its second slot once)
             e2e_view.set_viewport(vps[pose_index(i)])
-            e2e_view.render_to_host_ptr(*planes_of(ptr_sets[i & 1]))
+            if pipelined:
+                e2e_view.render_to_host_async_ptr(*planes_of(ptr_sets[i & 1]))
+                e2e_view.wait_host(1)
+            else:
+                e2e_view.render_to_host_ptr(*planes_of(ptr_sets[i & 1]))
+        if pipelined:
+            e2e_view.wait_host(0)
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):

@@ -23,6 +23,8 @@ using namespace svx;
 
 namespace {
 thread_local std::string g_last_error;
+}
+namespace svx {
 // SVX_DEBUG_CUDA=1: report (and clear) an error some earlier runtime call left behind, at the named point
 void debug_stale(const char* where) {
     static const bool on = std::getenv("SVX_DEBUG_CUDA") != nullptr;
@@ -32,8 +34,6 @@ void debug_stale(const char* where) {
     cudaGetDevice(&dev);
     std::fprintf(stderr, "[svx] %s: last error %s, current device %d\n", where, cudaGetErrorName(e), dev);
 }
-}
-namespace svx {
 int32_t fail(int32_t code, const std::string& msg) {
     g_last_error = msg;
     return code;
@@ -455,6 +455,7 @@ int32_t validate_viewport(const svx_viewport& vp) {
 }
 
 int32_t check_view_error(svx_view* v) {
+    debug_stale("check_view_error");
     if (!v->h_error || *v->h_error == 0u) return SVX_OK;
     const uint32_t code = *v->h_error;
     *v->h_error = 0u;
@@ -907,6 +908,7 @@ void svx_gpu_host_free(svx_gpu_host* h) {
     cudaFree(h->d_hits);
     cudaStreamDestroy(h->stream);
     delete h;
+    debug_stale("svx_gpu_host_free: exit");
 }
 
 int32_t svx_gpu_host_reload(svx_gpu_host* h) {
@@ -1137,6 +1139,7 @@ void svx_view_free(svx_view* v) {
     if (v->h_error) cudaFreeHost(v->h_error);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
+    debug_stale("svx_view_free: exit");
 }
 
 int32_t svx_view_get_viewport(const svx_view* v, svx_viewport* out) {

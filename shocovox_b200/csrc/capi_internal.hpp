@@ -14,6 +14,7 @@
 
 namespace svx {
 
+void debug_stale(const char* where);  // SVX_DEBUG_CUDA=1: report and clear a left-over CUDA error at the named point
 int32_t fail(int32_t code, const std::string& msg);
 int32_t cuda_fail(cudaError_t e, const char* what);
 #define CUDA_TRY(expr)                                             \

@@ -139,7 +139,12 @@ int32_t svx_view_gather_join(svx_view* v, uint32_t rank, const svx_gather_handle
     const int32_t ready = become_peer_locked(v, rank, h.world, h.rows_per_band, h.wire, h.width, h.height);
     if (ready != SVX_OK) return ready;
     void* mapped = nullptr;
-    CUDA_TRY(cudaIpcOpenMemHandle(&mapped, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t opened = cudaIpcOpenMemHandle(&mapped, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (opened != cudaSuccess) {  // not a member after all: back to a whole-frame view
+        v->rank = 0;
+        v->world = 1;
+        return cuda_fail(opened, "cudaIpcOpenMemHandle (the root must live in another process on a GPU with peer access)");
+    }
     v->peer_block = mapped;
     v->peer_plane_bytes = (size_t)h.plane_bytes;
     v->peer_is_ipc = true;
@@ -158,14 +163,20 @@ int32_t svx_view_gather_join_local(svx_view* v, uint32_t rank, svx_view* root) {
     const int mine = v->host->device, theirs = root->host->device;
     if (mine != theirs) {
         int can = 0;
-        CUDA_TRY(cudaDeviceCanAccessPeer(&can, mine, theirs));
-        if (!can) return fail(SVX_E_CUDA, "gather: no peer access between the two devices");
-        CUDA_TRY(cudaSetDevice(mine));
-        const cudaError_t e = cudaDeviceEnablePeerAccess(theirs, 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled)
-            cudaGetLastError();
-        else if (e != cudaSuccess)
-            return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+        cudaError_t e = cudaDeviceCanAccessPeer(&can, mine, theirs);
+        if (e == cudaSuccess && can) {
+            e = cudaSetDevice(mine);
+            if (e == cudaSuccess) e = cudaDeviceEnablePeerAccess(theirs, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                e = cudaSuccess;
+            }
+        }
+        if (e != cudaSuccess || !can) {
+            v->rank = 0;
+            v->world = 1;
+            return e != cudaSuccess ? cuda_fail(e, "peer access to the root's device") : fail(SVX_E_CUDA, "gather: no peer access between the two devices");
+        }
     }
     v->peer_block = root->frame_block;
     v->peer_plane_bytes = root->plane_bytes;
@@ -190,6 +201,7 @@ int32_t svx_view_gather_close(svx_view* v) {
     v->world = 1;
     v->frame_seq = 0;
     if (v->h_error) *v->h_error = 0u;
+    debug_stale("svx_view_gather_close: exit");
     return SVX_OK;
 }
 
@@ -274,6 +286,7 @@ int32_t svx_multi_create(const svx_octree* tree, const int32_t* devices, uint32_
                          uint32_t height, uint32_t rows_per_band, int32_t wire, svx_multi** out) {
     if (!tree || !devices || !viewport || !out) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
+    debug_stale("svx_multi_create: entry");
     const int32_t shape = check_gather_shape(n, rows_per_band, wire);
     if (shape != SVX_OK) return shape;
     svx_multi* m = new (std::nothrow) svx_multi();

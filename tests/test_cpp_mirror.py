@@ -29,6 +29,38 @@ def compile_example(name: str) -> Path:
     return exe
 
 
+def compile_c_example(name: str) -> Path:
+    """plain C against include/shocovox_b200.h: the header must be usable without a C++ compiler"""
+    S.lib()
+    BUILD.mkdir(exist_ok=True)
+    exe = BUILD / name
+    lib_dir = S.library_path().parent
+    cmd = ["gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "examples" / "cpp" / f"{name}.c"), "-o", str(exe),
+           f"-L{lib_dir}", "-lshocovox_b200", f"-Wl,-rpath,{lib_dir}", "-lm"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_c_multi_gpu_example_compiles_as_c():
+    compile_c_example("multi_gpu")
+
+
+@pytest.mark.gpu
+def test_c_multi_gpu_two_members():
+    """svx_multi_* from plain C with world size 2: two members on device 0, and two real devices when the box has them."""
+    exe = compile_c_example("multi_gpu")
+    runs = [["0", "0"], ["0", "0", "0", "0"]]
+    if S.cuda_device_count() >= 2:
+        runs.append(["0", "1"])
+    if S.cuda_device_count() >= 8:
+        runs.append([str(i) for i in range(8)])
+    for devices in runs:
+        res = subprocess.run([str(exe)] + devices, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert f"multi_gpu: ok ({len(devices)} members" in res.stdout
+
+
 def test_cpp_construction_api():
     exe = compile_example("octree_api_test")
     res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)

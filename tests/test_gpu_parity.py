@@ -546,6 +546,3 @@ def test_shaded_plane_is_the_callers_pixel():
         ora = otree.render(oracle_camera(cam), 64, 48, light_normal=light, viewing_distance=80.0)
         view.render_to_host()
         assert np.array_equal(view.read_shaded(), ora["shaded"])
-
-
-@pytest.mark.gpu
