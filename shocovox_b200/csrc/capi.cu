@@ -394,7 +394,8 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     f->lx = v->light[0]; f->ly = v->light[1]; f->lz = v->light[2];
     f->go_flag = f->done_flag = f->cta_counter = nullptr;
     f->frame_seq = 0;
-    if (v->gather_role == GATHER_PEER) {
+    f->gather_tuning = v->gather_tuning;
+    if (v->gather_role == GATHER_PEER && !(v->gather_tuning & GATHER_TUNE_LOCAL_STORES)) {
         // the root's planes (same resolution, checked at join); 8-byte wire format: no albedo crosses NVLink
         char* base = static_cast<char*>(v->peer_block);
         f->hit_id = reinterpret_cast<uint32_t*>(base);
@@ -471,16 +472,18 @@ int32_t render_locked(svx_view* v) {
     FrameParams f;
     make_frame_constants(v, &f);
     LaunchConfig cfg = v->host->cfg;
-    cfg.persistent = v->persistent;
+    const bool signal_kernel = v->gather_role == GATHER_PEER && (v->gather_tuning & GATHER_TUNE_SIGNAL_KERNEL);
+    cfg.persistent = v->persistent || (v->gather_role == GATHER_PEER && !(v->gather_tuning & (GATHER_TUNE_STATIC_PEERS | GATHER_TUNE_SIGNAL_KERNEL))) ||
+                     (v->gather_role == GATHER_ROOT && (v->gather_tuning & GATHER_TUNE_PERSISTENT_ROOT));
     cfg.tile_counters = v->d_counters;
     f.counter_slot = v->counter_slot;
-    if (v->persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
+    if (cfg.persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
     if (v->gather_role == GATHER_PEER) {
         v->frame_seq += 1;
         GatherSync* sync = gather_sync_of(v->peer_block, v->peer_plane_bytes);
         CUDA_TRY(launch_wait_flag(&sync->go, v->frame_seq, v->gather_timeout_ns, v->h_error, 0x100u + v->rank, v->stream));
         v->launches += 1;
-        f.done_flag = &sync->done[v->rank].seq;
+        f.done_flag = signal_kernel ? nullptr : &sync->done[v->rank].seq;
         f.cta_counter = v->d_cta_counter;
         f.frame_seq = v->frame_seq;
     } else if (v->gather_role == GATHER_ROOT) {
@@ -491,6 +494,10 @@ int32_t render_locked(svx_view* v) {
     CUDA_TRY(cudaEventRecord(v->ev_start, v->stream));
     CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
     v->launches += 1;
+    if (signal_kernel) {
+        CUDA_TRY(launch_signal_flag(&gather_sync_of(v->peer_block, v->peer_plane_bytes)->done[v->rank].seq, v->frame_seq, v->stream));
+        v->launches += 1;
+    }
     if (v->gather_role == GATHER_ROOT) {
         GatherSync* sync = gather_sync_of(v->frame_block, v->plane_bytes);
         GatherComplete g{};

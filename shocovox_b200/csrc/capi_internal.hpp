@@ -122,6 +122,7 @@ struct svx_view {
     uint32_t* d_cta_counter = nullptr;  // peer: retired CTAs of the launch in flight
     uint32_t* h_error = nullptr;        // host-mapped word the wait kernels write on a timeout (0 = fine)
     uint64_t gather_timeout_ns = 5000000000ull;
+    uint32_t gather_tuning = 0;  // GATHER_TUNE_* (kernels.cuh), from SVX_GATHER_TUNING at open / join
     // Pipelined read-back (svx_view_render_to_host_async): two framebuffer slots (slot 0 = the planes above, slot 1 =
     // alt_*), kernels on `stream`, device->host copies on `copy_stream`, so frame i's copy overlaps frame i+1's kernel.
     cudaStream_t copy_stream = nullptr;

@@ -155,7 +155,10 @@ __device__ __forceinline__ void gather_epilogue(const FrameParams& f) {
     if (f.done_flag == nullptr) return;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        if (f.gather_tuning & GATHER_TUNE_CTA_FENCE_GPU)
+            __threadfence();  // release at gpu scope towards the CTA that will publish; its system fence below is cumulative
+        else
+            __threadfence_system();
         if (atomicAdd(f.cta_counter, 1u) == gridDim.x * gridDim.y - 1u) {
             *f.cta_counter = 0u;  // launches of one view are ordered on one stream: the next one counts from zero
             __threadfence_system();
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_shad
 // global counter until the frame is done, so a long ray delays one warp, not the seven that share its CTA, and the SMs
 // stay busy to the end of the frame. `counters[f.counter_slot]` is this launch's ticket counter; the other slot is
 // zeroed for the next launch (launches of one view are ordered on one stream).
-template <bool LOD>
+template <bool LOD, int BS = -1>
 __device__ __forceinline__ void render_persistent_body(const DeviceTree& tree, const FrameParams& f, uint32_t* __restrict__ counters) {
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[f.counter_slot ^ 1u] = 0u;
     const uint32_t lane = threadIdx.x & 31u;
@@ -241,7 +244,7 @@ __device__ __forceinline__ void render_persistent_body(const DeviceTree& tree, c
         for (uint32_t k = 0; k < SVX_TICKET_TILES; ++k) {
             const uint32_t sub = (first & 7u) + k;
             const uint32_t ttx = (bx << 2) + (sub & 3u), tty = (by << 1) + (sub >> 2);
-            if (ttx < tiles_x && tty < tiles_y) shade_pixel<LOD, false>(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
+            if (ttx < tiles_x && tty < tiles_y) shade_pixel<LOD, false, BS>(tree, f, (ttx << 3) + (lane & 7u), (tty << 2) + (lane >> 3));
         }
     }
 }
@@ -257,6 +260,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kern
     render_persistent_body<true>(tree, f, counters);
     gather_epilogue(f);
 }
+// ... and for the brick dimensions of the reference's examples, like the static schedule above
+#define SVX_PERSISTENT_KERNEL_FOR_BRICK(NAME, LOD, BS)                                                                      \
+    __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) NAME(const DeviceTree tree, const FrameParams f,        \
+                                                                         uint32_t* __restrict__ counters) {                 \
+        gather_prologue(f);                                                                                                 \
+        render_persistent_body<LOD, BS>(tree, f, counters);                                                                 \
+        gather_epilogue(f);                                                                                                 \
+    }
+SVX_PERSISTENT_KERNEL_FOR_BRICK(render_kernel_persistent_brick8, false, 3)
+SVX_PERSISTENT_KERNEL_FOR_BRICK(render_kernel_persistent_brick32, false, 5)
+SVX_PERSISTENT_KERNEL_FOR_BRICK(render_lod_kernel_persistent_brick8, true, 3)
+SVX_PERSISTENT_KERNEL_FOR_BRICK(render_lod_kernel_persistent_brick32, true, 5)
+#undef SVX_PERSISTENT_KERNEL_FOR_BRICK
 
 template <bool LOD>
 __device__ __forceinline__ void rays_body(const DeviceTree& tree, const float* __restrict__ rays, uint64_t n,
@@ -431,19 +447,24 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
             render_shaded_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
         return cudaGetLastError();
     }
-    if (cfg.persistent && cfg.tile_counters) {
-        // blocks_x * blocks_y * 8 tickets cover the frame in 32x8 blocks; ragged edges are skipped inside the kernel
-        const unsigned grid = (unsigned)(cfg.sm_count * SVX_MIN_BLOCKS);
-        if (tree.mips_enabled)
-            render_lod_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
-        else
-            render_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
-        return cudaGetLastError();
-    }
-    dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
     // the specialised instantiations hard-code everything DeviceTree derives from brick_shift; anything else is generic
     const bool consistent = tree.brick_dim == (1u << tree.brick_shift) && tree.brick_dim_sq == tree.brick_dim * tree.brick_dim;
     const uint32_t shift = (SVX_BRICK_SPECIALISED && consistent) ? tree.brick_shift : 0xFFFFFFFFu;
+    if (cfg.persistent && cfg.tile_counters) {
+        // blocks_x * blocks_y * 8 tickets cover the frame in 32x8 blocks; ragged edges are skipped inside the kernel
+        const unsigned grid = (unsigned)(cfg.sm_count * SVX_MIN_BLOCKS);
+        if (tree.mips_enabled) {
+            if (shift == 3u) render_lod_kernel_persistent_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+            else if (shift == 5u) render_lod_kernel_persistent_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+            else render_lod_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+        } else {
+            if (shift == 3u) render_kernel_persistent_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+            else if (shift == 5u) render_kernel_persistent_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+            else render_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+        }
+        return cudaGetLastError();
+    }
+    dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
     if (tree.mips_enabled) {
         if (shift == 3u) render_lod_kernel_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
         else if (shift == 5u) render_lod_kernel_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
@@ -502,30 +523,53 @@ __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t want, uint64_t t
 // then in this GPU's memory), and - for the 8-byte wire format - resolves the albedo of the peers' rows from the hit ids
 // exactly as the viewport kernel does for its own pixels (palette[hit_id & 0xFFFF], 0 without a colour).
 __global__ void __launch_bounds__(256) gather_complete_kernel(const GatherComplete g) {
-    __shared__ uint32_t arrived;
+    __shared__ uint32_t arrived_mask, failed;
     if (threadIdx.x == 0) {
-        arrived = 1u;
-        const uint64_t t0 = globaltimer_ns();
-        for (uint32_t r = 1; r < g.world && arrived; ++r) {
-            const uint32_t* flag = g.done_flags + (size_t)r * g.done_stride;
-            while ((int32_t)(ld_acquire_sys(flag) - g.frame_seq) < 0) {
-                if (globaltimer_ns() - t0 > g.timeout_ns) {
-                    arrived = 0u;
-                    if (blockIdx.x == 0) {
-                        *g.error = 1u + r;
-                        __threadfence_system();
-                    }
-                    break;
-                }
-                __nanosleep(40);
-            }
-        }
+        arrived_mask = 1u;  // rank 0 is this GPU
+        failed = 0u;
     }
     __syncthreads();
-    if (!arrived || !g.fill_albedo) return;
+    const uint64_t t0 = globaltimer_ns();
+    // thread 0 waits for peer r (once per CTA); everybody learns the outcome through shared memory
+    auto wait_for = [&](uint32_t r) -> bool {
+        const bool need = !((arrived_mask >> r) & 1u);
+        __syncthreads();  // everybody has read the mask before thread 0 may change it
+        if (need) {
+            if (threadIdx.x == 0) {
+                const uint32_t* flag = g.done_flags + (size_t)r * g.done_stride;
+                bool ok = true;
+                while ((int32_t)(ld_acquire_sys(flag) - g.frame_seq) < 0) {
+                    if (globaltimer_ns() - t0 > g.timeout_ns) {
+                        ok = false;
+                        break;
+                    }
+                    __nanosleep(40);
+                }
+                if (ok) {
+                    arrived_mask |= 1u << r;
+                } else {
+                    failed = 1u;
+                    if (blockIdx.x == 0 || g.fill_albedo) *g.error = 1u + r;
+                    __threadfence_system();
+                }
+            }
+            __syncthreads();
+        }
+        return failed == 0u;
+    };
+    if (!g.fill_albedo) {  // one CTA: the frame is complete when every peer has published this frame
+        for (uint32_t r = 1; r < g.world; ++r)
+            if (!wait_for(r)) return;
+        return;
+    }
+    // 8-byte wire format: a row can be finished as soon as ITS owner has delivered, so the albedo of early peers' rows is
+    // resolved while late peers are still rendering. Every peer row belongs to exactly one CTA, so when the grid has
+    // retired every peer has been waited for.
     const bool vec = (g.width & 3u) == 0u;
     for (uint32_t row = blockIdx.x; row < g.height; row += gridDim.x) {
-        if (((row >> g.band_shift) % g.world) == 0u) continue;  // the root's own rows already carry their albedo
+        const uint32_t owner = (row >> g.band_shift) % g.world;
+        if (owner == 0u) continue;  // the root's own rows already carry their albedo
+        if (!wait_for(owner)) return;
         const size_t base = (size_t)row * g.width;
         if (vec) {
             const uint4* src = reinterpret_cast<const uint4*>(g.hit_id + base);
@@ -547,6 +591,16 @@ __global__ void __launch_bounds__(256) gather_complete_kernel(const GatherComple
             }
         }
     }
+}
+
+__global__ void signal_flag_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    st_release_sys(flag, value);
+}
+
+cudaError_t launch_signal_flag(uint32_t* flag, uint32_t value, cudaStream_t stream) {
+    signal_flag_kernel<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t want, uint64_t timeout_ns, uint32_t* error, uint32_t error_code,

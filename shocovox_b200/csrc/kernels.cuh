@@ -47,7 +47,19 @@ struct FrameParams {
     uint32_t* done_flag;
     uint32_t* cta_counter;
     uint32_t frame_seq;
+    uint32_t gather_tuning;  // GATHER_TUNE_* bits (multi_gpu.cu), 0 = the defaults
 };
+
+// Tuning bits of the gather (SVX_GATHER_TUNING, read when a view opens / joins a gather). Default 0 = what measured best
+// (profiles/r02_gather_probe_*.json): peers run the persistent schedule, so the system-scope fence that must precede the
+// `done` flag is paid once per resident CTA instead of once per 16x8-pixel block - a membar.sys per block cost 18 % of the
+// peer's kernel even with local stores.
+constexpr uint32_t GATHER_TUNE_CTA_FENCE_GPU = 1u;  // retiring CTAs fence at gpu scope, only the publishing one at system scope
+constexpr uint32_t GATHER_TUNE_STATIC_PEERS = 2u;   // peers use the static schedule (one CTA and one fence per pixel block)
+constexpr uint32_t GATHER_TUNE_LOCAL_STORES = 4u;   // measurement only: peers store into their OWN framebuffer (no NVLink traffic; the frame is wrong)
+constexpr uint32_t GATHER_TUNE_PERSISTENT_ROOT = 8u;  // the root uses the persistent schedule as well
+constexpr uint32_t GATHER_TUNE_SIGNAL_KERNEL = 16u;   // peers: static schedule, no fence in the viewport kernel; a one-thread kernel queued
+                                                      // behind it publishes `done` (kernel completion orders the stores)
 
 // What the root's completion kernel needs besides the frame: which rows the peers own and the palette to resolve albedo with
 struct GatherComplete {
@@ -87,6 +99,8 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
 cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t want, uint64_t timeout_ns, uint32_t* error, uint32_t error_code,
                              cudaStream_t stream);
 cudaError_t launch_gather_complete(const GatherComplete& g, int sm_count, cudaStream_t stream);
+//   launch_signal_flag    one thread: system fence, then *flag = value (release, system scope)
+cudaError_t launch_signal_flag(uint32_t* flag, uint32_t value, cudaStream_t stream);
 cudaError_t launch_rays(const DeviceTree& tree, const float* rays /* [n][6] */, uint64_t n, float viewing_distance,
                         RayHitRecord* out, const LaunchConfig& cfg, cudaStream_t stream);
 // Render-data upload, device side: the occupancy bit-bricks (gpu_tree.hpp: brick_bits) of the listed bricks, computed

@@ -19,6 +19,7 @@
 // and svx_multi_* for one process driving all GPUs. The reference has no multi-GPU path; what is kept is
 // the contract that the assembled frame equals the single-GPU frame byte for byte.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -47,6 +48,11 @@ int32_t check_gather_shape(uint32_t world, uint32_t rows_per_band, int32_t wire)
         return fail(SVX_E_INVALID_ARGUMENT, "gather: rows_per_band must be a power of two");
     if (wire != SVX_WIRE_THREE_PLANES && wire != SVX_WIRE_ID_DISTANCE) return fail(SVX_E_INVALID_ARGUMENT, "gather: unknown wire format");
     return SVX_OK;
+}
+
+uint32_t tuning_from_env() {
+    const char* t = std::getenv("SVX_GATHER_TUNING");
+    return t ? (uint32_t)std::strtoul(t, nullptr, 0) : 0u;
 }
 
 int32_t quiesce(svx_view* v) {
@@ -78,6 +84,7 @@ int32_t open_root_locked(svx_view* root, uint32_t world, uint32_t rows_per_band,
     root->gather_wire = wire;
     root->frame_seq = 0;
     root->gather_exports = 0;
+    root->gather_tuning = tuning_from_env();
     root->gather_role = GATHER_ROOT;
     return SVX_OK;
 }
@@ -97,6 +104,7 @@ int32_t become_peer_locked(svx_view* v, uint32_t rank, uint32_t world, uint32_t 
     v->band_rows = rows_per_band;
     v->gather_wire = wire;
     v->frame_seq = 0;
+    v->gather_tuning = tuning_from_env();
     return SVX_OK;
 }
 
