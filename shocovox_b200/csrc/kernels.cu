@@ -53,6 +53,20 @@ __device__ __forceinline__ void glass_vector(const FrameParams& f, uint32_t x, u
     vz = gz - f.oz;
 }
 
+// SVX_PIXEL_TIMING=1 builds a MEASUREMENT variant of the library (tools/pixel_timing.py; never the product): every pixel's
+// planes carry when its ray ran instead of what it hit - hit_id = SM cycles spent, albedo / distance = start / end of the
+// pixel on the GPU's nanosecond timer (low 32 bits).
+#ifndef SVX_PIXEL_TIMING
+#define SVX_PIXEL_TIMING 0
+#endif
+#if SVX_PIXEL_TIMING
+__device__ __forceinline__ uint32_t timer_ns_lo() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (uint32_t)t;
+}
+#endif
+
 // One pixel of the frame: ray generation, rejection tests, get_by_ray, framebuffer stores.
 // `f32 as u8` of the caller loop's colour channels: truncating, saturating, NaN -> 0
 __device__ __forceinline__ uint32_t channel_u8(float v) { return min(__float2uint_rz(v), 255u); }
@@ -73,6 +87,10 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
     const uint32_t y = f.height - 1u - row;  // pixel (x, y) lands in image row h-1-y (cpu_render.rs:106)
     const uint32_t i = (f.compact ? lr : row) * f.width + x;  // width * height < 2^32 (checked by the host)
 
+#if SVX_PIXEL_TIMING
+    const uint32_t timing_t0 = timer_ns_lo();
+    const long long timing_c0 = clock64();
+#endif
     uint32_t hit_id = NIL, rgba = 0u;
     float dist = 0.0f;
     // 0) pixels outside the projected bounding rectangle of the root cube are sky (host-computed, conservative)
@@ -124,6 +142,11 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
             }
         }
     }
+#if SVX_PIXEL_TIMING
+    hit_id = (uint32_t)(clock64() - timing_c0);
+    rgba = timing_t0;
+    dist = __uint_as_float(timer_ns_lo());
+#endif
     f.hit_id[i] = hit_id;
     if (f.albedo) f.albedo[i] = rgba;  // nullptr: a gather peer shipping 8 B per pixel (kernels.cuh: FrameParams)
     f.distance[i] = dist;
