@@ -8,7 +8,9 @@
  *
  * Rules
  *  - every call returns an svx_status (0 = OK); nothing throws or aborts across the boundary;
- *  - handles are created by the library and released by the caller with the matching *_free;
+ *  - handles are created by the library and released by the caller with the matching *_free, in ANY order: a host keeps
+ *    its octree alive and a view keeps its host alive until they are freed themselves (bindings whose finalisers run in
+ *    no particular order are safe); a freed handle must not be used again;
  *  - an octree handle allows one writer or many readers (caller-enforced, like `&mut self` / `&self`);
  *  - a host/view handle serialises its own calls internally and owns its CUDA stream;
  *  - ray queries run on the GPU only. There is no CPU fallback: without a CUDA device every svx_gpu_* /

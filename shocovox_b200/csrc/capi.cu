@@ -440,6 +440,29 @@ int32_t alloc_frame(svx_view* v) {
 
 namespace svx {
 
+void octree_retain(const svx_octree* t) { t->refs.fetch_add(1); }
+void octree_release(const svx_octree* t) {
+    if (!t || t->refs.fetch_sub(1) != 1) return;
+    svx_octree* tree = const_cast<svx_octree*>(t);
+    host_release(tree->ray_host);  // holds no count on the tree: it goes with it
+    delete tree->tree;
+    delete tree;
+}
+void host_release(svx_gpu_host* h) {
+    if (!h || h->refs.fetch_sub(1) != 1) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_device_tree(h);
+    cudaFree(h->d_ray_lut);
+    cudaFree(h->d_rays);
+    cudaFree(h->d_hits);
+    cudaStreamDestroy(h->stream);
+    const svx_octree* tree = h->holds_octree_ref ? h->octree : nullptr;
+    delete h;
+    debug_stale("host_release: destroyed");
+    octree_release(tree);
+}
+
 // Rejects what would make every ray of a frame NaN (the reference debug-asserts `ray.is_valid()`,
 // spatial/raytracing/mod.rs:14-16, and hangs in release builds): non-finite fields, a zero direction, or a direction
 // parallel to the fixed up vector (0, 1, 0) - `up x direction` is the zero vector then and its normalisation 0 / 0.
@@ -465,6 +488,36 @@ int32_t check_view_error(svx_view* v) {
     return fail(SVX_E_TIMEOUT, "gather: peer rank " + std::to_string(code - 1u) + " did not deliver its rows in time");
 }
 
+void invalidate_block_order(svx_view* v) { v->order_valid = false; }
+
+// Heaviest-first block order for a static-schedule launch of `f` (kernels.cuh: FrameParams::cta_order): points the launch at
+// the cost array to fill and, once a frame of this shape has been recorded and sorted, at the permutation to follow.
+static int32_t attach_block_order(svx_view* v, FrameParams* f, bool persistent, uint32_t* n_ctas) {
+    *n_ctas = 0;
+    f->cta_order = nullptr;
+    f->cta_cost = nullptr;
+    // Policy 1 (default): for the shards of a frame split four ways or more, where the tail of the launch is a large part of
+    // it - measured (profiles/r02_schedule_probe_v4.json): 1/8 of sponza 4K -8.6 %, 1/4 of minecraft 4K -20 %, but +2..4 % on
+    // halves and whole frames of sponza (the sort is not free and neighbouring blocks no longer run together), and a loss
+    // on frames too small to have a tail worth ordering.
+    if (persistent || f->shaded || v->order_policy == 0 || (v->order_policy == 1 && v->world < 4)) return SVX_OK;
+    const uint32_t n = ((f->width + 15u) / 16u) * ((f->rows_local + 7u) / 8u);  // kernels.cu: one CTA per 16x8 pixels
+    if (n < 4096u && v->order_policy != 2) return SVX_OK;
+    if (v->order_ctas != n) {
+        cudaFree(v->d_cta_cost);
+        v->d_cta_cost = v->d_cta_order = nullptr;
+        v->order_ctas = 0;
+        v->order_valid = false;
+        CUDA_TRY(cudaMalloc((void**)&v->d_cta_cost, (size_t)2 * n * sizeof(uint32_t)));
+        v->d_cta_order = v->d_cta_cost + n;
+        v->order_ctas = n;
+    }
+    f->cta_cost = v->d_cta_cost;
+    f->cta_order = v->order_valid ? v->d_cta_order : nullptr;
+    *n_ctas = n;
+    return SVX_OK;
+}
+
 // One frame on the view's stream. A gather peer first waits (on the device) for the root's licence to overwrite the
 // shared framebuffer; a gather root follows its own rows with the kernel that waits for the peers' rows.
 int32_t render_locked(svx_view* v) {
@@ -472,12 +525,15 @@ int32_t render_locked(svx_view* v) {
     FrameParams f;
     make_frame_constants(v, &f);
     LaunchConfig cfg = v->host->cfg;
-    const bool signal_kernel = v->gather_role == GATHER_PEER && (v->gather_tuning & GATHER_TUNE_SIGNAL_KERNEL);
-    cfg.persistent = v->persistent || (v->gather_role == GATHER_PEER && !(v->gather_tuning & (GATHER_TUNE_STATIC_PEERS | GATHER_TUNE_SIGNAL_KERNEL))) ||
+    const bool signal_kernel = v->gather_role == GATHER_PEER && !(v->gather_tuning & (GATHER_TUNE_INKERNEL_STATIC | GATHER_TUNE_INKERNEL_PERSISTENT));
+    cfg.persistent = v->persistent || (v->gather_role == GATHER_PEER && (v->gather_tuning & GATHER_TUNE_INKERNEL_PERSISTENT)) ||
                      (v->gather_role == GATHER_ROOT && (v->gather_tuning & GATHER_TUNE_PERSISTENT_ROOT));
     cfg.tile_counters = v->d_counters;
     f.counter_slot = v->counter_slot;
     if (cfg.persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
+    uint32_t ordered_ctas = 0;
+    const int32_t attached = attach_block_order(v, &f, cfg.persistent, &ordered_ctas);
+    if (attached != SVX_OK) return attached;
     if (v->gather_role == GATHER_PEER) {
         v->frame_seq += 1;
         GatherSync* sync = gather_sync_of(v->peer_block, v->peer_plane_bytes);
@@ -497,6 +553,13 @@ int32_t render_locked(svx_view* v) {
     if (signal_kernel) {
         CUDA_TRY(launch_signal_flag(&gather_sync_of(v->peer_block, v->peer_plane_bytes)->done[v->rank].seq, v->frame_seq, v->stream));
         v->launches += 1;
+    }
+    // the next frame's block order from this frame's costs. A root sorts while it waits for its peers; a peer has published
+    // its rows by now, so its sort is off the frame's critical path
+    if (ordered_ctas != 0 && v->gather_role != GATHER_PEER) {
+        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, v->stream));
+        v->launches += 1;
+        v->order_valid = true;
     }
     if (v->gather_role == GATHER_ROOT) {
         GatherSync* sync = gather_sync_of(v->frame_block, v->plane_bytes);
@@ -519,6 +582,11 @@ int32_t render_locked(svx_view* v) {
         v->launches += 1;
     }
     CUDA_TRY(cudaEventRecord(v->ev_stop, v->stream));
+    if (ordered_ctas != 0 && v->gather_role == GATHER_PEER) {
+        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, v->stream));
+        v->launches += 1;
+        v->order_valid = true;
+    }
     return SVX_OK;
 }
 
@@ -611,10 +679,18 @@ int32_t submit_async_locked(svx_view* v, uint32_t* hit_id, uint32_t* albedo, flo
     cfg.tile_counters = v->d_counters;
     f.counter_slot = v->counter_slot;
     if (v->persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
+    uint32_t ordered_ctas = 0;
+    const int32_t attached = attach_block_order(v, &f, cfg.persistent, &ordered_ctas);
+    if (attached != SVX_OK) return attached;
     CUDA_TRY(cudaEventRecord(v->slot_start[k], v->stream));
     CUDA_TRY(launch_render(v->host->dev, f, cfg, v->stream));
     CUDA_TRY(cudaEventRecord(v->slot_rendered[k], v->stream));
     v->launches += 1;
+    if (ordered_ctas != 0) {  // behind the "rendered" event: the copies of this frame do not wait for the sort
+        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, v->stream));
+        v->launches += 1;
+        v->order_valid = true;
+    }
     tree_lock.unlock();
     CUDA_TRY(cudaStreamWaitEvent(v->copy_stream, v->slot_rendered[k], 0));
     if (k == 0) {
@@ -665,12 +741,7 @@ int32_t svx_octree_new(uint32_t size, uint32_t brick_dim, svx_octree** out) {
     (*out)->tree = t;
     return SVX_OK;
 }
-void svx_octree_free(svx_octree* tree) {
-    if (!tree) return;
-    svx_gpu_host_free(tree->ray_host);
-    delete tree->tree;
-    delete tree;
-}
+void svx_octree_free(svx_octree* tree) { octree_release(tree); }
 int32_t svx_octree_insert(svx_octree* t, uint32_t x, uint32_t y, uint32_t z, const svx_entry* e) {
     if (!t || !e) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
     return t->tree->insert_at_lod_internal(true, x, y, z, 1, *e);
@@ -901,22 +972,12 @@ int32_t svx_gpu_host_create(const svx_octree* tree, int32_t device, svx_gpu_host
         delete h;
         return s;
     }
+    octree_retain(tree);
     *out = h;
     return SVX_OK;
 }
 
-void svx_gpu_host_free(svx_gpu_host* h) {
-    if (!h) return;
-    cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    free_device_tree(h);
-    cudaFree(h->d_ray_lut);
-    cudaFree(h->d_rays);
-    cudaFree(h->d_hits);
-    cudaStreamDestroy(h->stream);
-    delete h;
-    debug_stale("svx_gpu_host_free: exit");
-}
+void svx_gpu_host_free(svx_gpu_host* h) { host_release(h); }
 
 int32_t svx_gpu_host_reload(svx_gpu_host* h) {
     if (!h) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
@@ -937,6 +998,8 @@ int32_t svx_octree_get_by_ray_at_lod(svx_octree* t, const svx_ray* ray, float vi
     if (!t->ray_host) {
         const int32_t created = svx_gpu_host_create(t, 0, &t->ray_host);  // SVX_E_CUDA without a device: no CPU path
         if (created != SVX_OK) return created;
+        t->ray_host->holds_octree_ref = false;  // owned by the tree itself: no count, or the tree could never go
+        t->refs.fetch_sub(1);
     } else {
         const int32_t reloaded = svx_gpu_host_reload(t->ray_host);
         if (reloaded != SVX_OK) return reloaded;
@@ -1087,6 +1150,7 @@ int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* 
     svx_view* v = new (std::nothrow) svx_view();
     if (!v) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
     v->host = h;
+    h->refs.fetch_add(1);
     v->viewport = *vp;
     v->width = width;
     v->height = height;
@@ -1113,6 +1177,7 @@ int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* 
     }
     *v->h_error = 0u;
     v->d_cta_counter = v->d_counters + 2;
+    if (const char* o = std::getenv("SVX_CTA_ORDER")) v->order_policy = std::atoi(o);
     if (const char* t = std::getenv("SVX_GATHER_TIMEOUT_MS")) v->gather_timeout_ns = (uint64_t)std::max(1L, std::atol(t)) * 1000000ull;
     const char* env = std::getenv("SVX_SCHEDULE");  // "persistent" | "static" (tuning override)
     v->persistent = env ? std::strcmp(env, "persistent") == 0 : SVX_DEFAULT_PERSISTENT;
@@ -1142,11 +1207,14 @@ void svx_view_free(svx_view* v) {
     if (v->tm_start) cudaEventDestroy(v->tm_start);
     if (v->tm_stop) cudaEventDestroy(v->tm_stop);
     cudaFree(v->d_flush);
+    cudaFree(v->d_cta_cost);
     cudaFree(v->d_counters);
     if (v->h_error) cudaFreeHost(v->h_error);
     if (v->stream) cudaStreamDestroy(v->stream);
+    svx_gpu_host* host = v->host;
     delete v;
     debug_stale("svx_view_free: exit");
+    host_release(host);
 }
 
 int32_t svx_view_get_viewport(const svx_view* v, svx_viewport* out) {
@@ -1225,6 +1293,7 @@ int32_t svx_view_set_resolution(svx_view* v, uint32_t width, uint32_t height) {
     CUDA_TRY(cudaStreamSynchronize(v->stream));
     v->width = width;
     v->height = height;
+    invalidate_block_order(v);
     return alloc_frame(v);
 }
 int32_t svx_view_resolution(const svx_view* v, uint32_t* width, uint32_t* height) {
@@ -1241,6 +1310,7 @@ int32_t svx_view_set_shard(svx_view* v, uint32_t rank, uint32_t world, uint32_t 
     v->rank = rank;
     v->world = world;
     v->band_rows = rows_per_band;
+    invalidate_block_order(v);
     return SVX_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <mutex>
 #include <shared_mutex>
@@ -41,7 +42,11 @@ enum GatherRole : int32_t { GATHER_NONE = 0, GATHER_ROOT = 1, GATHER_PEER = 2 };
 }  // namespace svx
 
 struct svx_gpu_host;
+// Lifetimes: a host keeps its octree alive and a view keeps its host alive (intrusive counts), so the *_free calls may come
+// in any order - language bindings whose finalisers run in no particular order (Python's cycle collector, Rust drop order
+// of unrelated owners) cannot leave a dangling handle behind. A freed handle must still not be USED by the caller.
 struct svx_octree {
+    mutable std::atomic<int> refs{1};  // the caller's handle + one per host / multi built on it
     svx::HostOctree* tree = nullptr;
     // svx_octree_get_by_ray[_at_lod]: a device copy created on first use (device 0) and reloaded before every query
     svx_gpu_host* ray_host = nullptr;
@@ -49,6 +54,8 @@ struct svx_octree {
 };
 
 struct svx_gpu_host {
+    std::atomic<int> refs{1};          // the caller's handle + one per view
+    bool holds_octree_ref = true;      // false for the octree's own ray_host (it is destroyed WITH the octree)
     const svx_octree* octree = nullptr;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -94,6 +101,13 @@ struct svx_view {
     uint32_t* d_counters = nullptr;  // two ticket counters of the persistent schedule (ping-pong across launches)
     uint32_t counter_slot = 0;
     bool persistent = false;
+    // heaviest-first block order of the static schedule (kernels.cuh: FrameParams::cta_order): cost and order arrays of
+    // `order_ctas` blocks; `order_valid` once a frame has been recorded and sorted for the current resolution / shard
+    uint32_t* d_cta_cost = nullptr;
+    uint32_t* d_cta_order = nullptr;
+    uint32_t order_ctas = 0;
+    bool order_valid = false;
+    int32_t order_policy = 1;  // SVX_CTA_ORDER: 0 never, 1 for the shards of a frame split 4+ ways (default), 2 always
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     // Framebuffer: ONE allocation = hit_id | albedo | distance | GatherSync, the planes `plane_bytes` apart
@@ -144,10 +158,14 @@ inline GatherSync* gather_sync_of(void* frame_block, size_t plane_bytes) {
 }
 
 // capi.cu
+void octree_retain(const svx_octree* t);
+void octree_release(const svx_octree* t);
+void host_release(svx_gpu_host* h);
 int32_t validate_viewport(const svx_viewport& vp);
 int32_t render_locked(svx_view* v);       // one frame on the view's stream (gather roles included); v->mu held
 int32_t retire_locked(svx_view* v, uint32_t keep);
 int32_t check_view_error(svx_view* v);    // after a synchronise: did a gather wait give up?
+void invalidate_block_order(svx_view* v); // resolution / shard changed: the recorded block costs no longer apply
 // device -> host copies of the rows this view owns (all of them unless it is a local shard), on `stream`
 int32_t copy_frame_to_host(svx_view* v, cudaStream_t stream, uint32_t* hit_id, uint32_t* albedo, float* distance);
 

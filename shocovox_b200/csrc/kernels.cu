@@ -190,38 +190,66 @@ __device__ __forceinline__ void gather_epilogue(const FrameParams& f) {
     }
 }
 
-// Static schedule: one CTA per 32x8 pixel block of the frame.
-__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_kernel(const DeviceTree tree, const FrameParams f) {
-    int tx, ty;
-    pixel_of_thread(tx, ty);
-    gather_prologue(f);
-    shade_pixel<false, false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
-    gather_epilogue(f);
-}
-// The same frame over a tree with MIP maps: get_by_ray_at_lod(ray, f.viewing_distance) per pixel
-__global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) render_lod_kernel(const DeviceTree tree, const FrameParams f) {
-    int tx, ty;
-    pixel_of_thread(tx, ty);
-    gather_prologue(f);
-    shade_pixel<true, false>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
-    gather_epilogue(f);
-}
-// The static-schedule kernels specialised for the two brick dimensions the reference's examples use (8: cpu_render.rs:14,
-// 32: dot_cube.rs:56, minecraft.rs:24, sponza.rs:24): brick strides, masks and 1 / dim are immediates in the voxel loop.
-// Same code, same results; launch_render picks the instantiation from DeviceTree::brick_shift.
-#define SVX_RENDER_KERNEL_FOR_BRICK(NAME, LOD, BS)                                                                          \
-    __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) NAME(const DeviceTree tree, const FrameParams f) {      \
-        int tx, ty;                                                                                                         \
-        pixel_of_thread(tx, ty);                                                                                            \
-        gather_prologue(f);                                                                                                 \
-        shade_pixel<LOD, false, BS>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);                           \
-        gather_epilogue(f);                                                                                                 \
+// Which 16x8-pixel block this CTA renders: its own position in the grid, or - heaviest-first order - the block the host's
+// permutation assigns to its dispatch position (the hardware hands out CTAs in increasing linear index). Also starts the
+// block's stopwatch when costs are recorded.
+__device__ __forceinline__ void block_of_cta(const FrameParams& f, uint32_t& bx, uint32_t& by, long long* s_t0) {
+    bx = blockIdx.x;
+    by = blockIdx.y;
+    if (f.cta_order != nullptr) {
+        const uint32_t b = __ldg(f.cta_order + (blockIdx.y * gridDim.x + blockIdx.x));
+        bx = b % gridDim.x;
+        by = b / gridDim.x;
     }
-SVX_RENDER_KERNEL_FOR_BRICK(render_kernel_brick8, false, 3)
-SVX_RENDER_KERNEL_FOR_BRICK(render_kernel_brick32, false, 5)
-SVX_RENDER_KERNEL_FOR_BRICK(render_lod_kernel_brick8, true, 3)
-SVX_RENDER_KERNEL_FOR_BRICK(render_lod_kernel_brick32, true, 5)
-#undef SVX_RENDER_KERNEL_FOR_BRICK
+    if (f.cta_cost != nullptr && threadIdx.x == 0) *s_t0 = clock64();
+}
+// ... and what the block cost, once its slowest warp is done
+__device__ __forceinline__ void record_block_cost(const FrameParams& f, uint32_t bx, uint32_t by, const long long* s_t0) {
+    if (f.cta_cost == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) f.cta_cost[by * gridDim.x + bx] = (uint32_t)min((long long)0xFFFFFFFFll, clock64() - *s_t0);
+}
+
+// Static schedule: one CTA per 16x8 pixel block of the frame. ORDERED = false: block = the CTA's place in the grid, nothing
+// recorded (whole-frame views; exactly the round-1 kernels). ORDERED = true: heaviest-first order and / or cost recording
+// (FrameParams::cta_order / cta_cost), used for the shards of a frame split over several GPUs.
+template <bool LOD, int BS, bool ORDERED>
+__device__ __forceinline__ void render_static_body(const DeviceTree& tree, const FrameParams& f) {
+    int tx, ty;
+    pixel_of_thread(tx, ty);
+    gather_prologue(f);
+    if constexpr (ORDERED) {
+        __shared__ long long s_t0;
+        uint32_t bx, by;
+        block_of_cta(f, bx, by, &s_t0);
+        shade_pixel<LOD, false, BS>(tree, f, bx * TILE_W + tx, by * TILE_H + ty);
+        record_block_cost(f, bx, by, &s_t0);
+    } else {
+        shade_pixel<LOD, false, BS>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+    }
+    gather_epilogue(f);
+}
+// Instantiations: generic brick dimension (BS = -1) and the two the reference's examples use (8: cpu_render.rs:14, 32:
+// dot_cube.rs:56, minecraft.rs:24, sponza.rs:24), where brick strides, masks and 1 / dim are immediates in the voxel loop;
+// each without / with MIP maps (get_by_ray / get_by_ray_at_lod per pixel) and in raster / recorded order. Same code, same
+// results; launch_render picks the instantiation.
+#define SVX_RENDER_KERNEL(NAME, LOD, BS, ORDERED)                                                                           \
+    __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) NAME(const DeviceTree tree, const FrameParams f) {      \
+        render_static_body<LOD, BS, ORDERED>(tree, f);                                                                      \
+    }
+SVX_RENDER_KERNEL(render_kernel, false, -1, false)
+SVX_RENDER_KERNEL(render_lod_kernel, true, -1, false)
+SVX_RENDER_KERNEL(render_kernel_brick8, false, 3, false)
+SVX_RENDER_KERNEL(render_kernel_brick32, false, 5, false)
+SVX_RENDER_KERNEL(render_lod_kernel_brick8, true, 3, false)
+SVX_RENDER_KERNEL(render_lod_kernel_brick32, true, 5, false)
+SVX_RENDER_KERNEL(render_kernel_ordered, false, -1, true)
+SVX_RENDER_KERNEL(render_lod_kernel_ordered, true, -1, true)
+SVX_RENDER_KERNEL(render_kernel_ordered_brick8, false, 3, true)
+SVX_RENDER_KERNEL(render_kernel_ordered_brick32, false, 5, true)
+SVX_RENDER_KERNEL(render_lod_kernel_ordered_brick8, true, 3, true)
+SVX_RENDER_KERNEL(render_lod_kernel_ordered_brick32, true, 5, true)
+#undef SVX_RENDER_KERNEL
 #ifndef SVX_BRICK_SPECIALISED
 #define SVX_BRICK_SPECIALISED 1   // 0: always launch the generic kernels (A/B measurements, tools/probe_variants.sh)
 #endif
@@ -488,15 +516,18 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
         return cudaGetLastError();
     }
     dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
+    const bool ordered = frame.cta_order != nullptr || frame.cta_cost != nullptr;
+#define SVX_LAUNCH(K) K<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame)
     if (tree.mips_enabled) {
-        if (shift == 3u) render_lod_kernel_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
-        else if (shift == 5u) render_lod_kernel_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
-        else render_lod_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+        if (shift == 3u) { if (ordered) SVX_LAUNCH(render_lod_kernel_ordered_brick8); else SVX_LAUNCH(render_lod_kernel_brick8); }
+        else if (shift == 5u) { if (ordered) SVX_LAUNCH(render_lod_kernel_ordered_brick32); else SVX_LAUNCH(render_lod_kernel_brick32); }
+        else { if (ordered) SVX_LAUNCH(render_lod_kernel_ordered); else SVX_LAUNCH(render_lod_kernel); }
     } else {
-        if (shift == 3u) render_kernel_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
-        else if (shift == 5u) render_kernel_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
-        else render_kernel<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame);
+        if (shift == 3u) { if (ordered) SVX_LAUNCH(render_kernel_ordered_brick8); else SVX_LAUNCH(render_kernel_brick8); }
+        else if (shift == 5u) { if (ordered) SVX_LAUNCH(render_kernel_ordered_brick32); else SVX_LAUNCH(render_kernel_brick32); }
+        else { if (ordered) SVX_LAUNCH(render_kernel_ordered); else SVX_LAUNCH(render_kernel); }
     }
+#undef SVX_LAUNCH
     return cudaGetLastError();
 }
 
@@ -614,6 +645,43 @@ __global__ void __launch_bounds__(256) gather_complete_kernel(const GatherComple
             }
         }
     }
+}
+
+// Heaviest-first permutation of the blocks of a launch (FrameParams::cta_order) from the cycles each took in the frame that
+// just ended: a counting sort over 64 quarter-octave cost classes by ONE CTA (a share of a 4K frame has 8 100 - 32 400
+// blocks, a whole one 64 800). Within a class the blocks keep (roughly) their raster order, which keeps neighbours together.
+constexpr uint32_t ORDER_CLASSES = 64;
+__device__ __forceinline__ uint32_t block_cost_class(uint32_t cycles) {
+    cycles = max(cycles, 4u);
+    const uint32_t lz = 31u - (uint32_t)__clz((int)cycles);
+    const uint32_t level = 4u * lz + ((cycles >> (lz - 2u)) & 3u);  // floor(4 log2 cycles)
+    return level >= 96u ? 0u : min(96u - level, ORDER_CLASSES - 1u);  // class 0: >= 2^24 cycles; 16x8 blocks sit around 2^14 - 2^20
+}
+__global__ void __launch_bounds__(1024) order_ctas_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n) {
+    __shared__ uint32_t cursor[ORDER_CLASSES];
+    if (threadIdx.x < ORDER_CLASSES) cursor[threadIdx.x] = 0u;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&cursor[block_cost_class(__ldcg(cost + i))], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32u) {  // exclusive prefix over the classes, heaviest first: two classes per lane, then a warp scan
+        const uint32_t a = cursor[2u * threadIdx.x], b = cursor[2u * threadIdx.x + 1u];
+        uint32_t incl = a + b;
+#pragma unroll
+        for (uint32_t d = 1; d < 32u; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (threadIdx.x >= d) incl += up;
+        }
+        cursor[2u * threadIdx.x] = incl - a - b;
+        cursor[2u * threadIdx.x + 1u] = incl - b;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&cursor[block_cost_class(__ldcg(cost + i))], 1u)] = i;
+}
+
+cudaError_t launch_order_ctas(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    order_ctas_kernel<<<1, 1024, 0, stream>>>(cost, order, n);
+    return cudaGetLastError();
 }
 
 __global__ void signal_flag_kernel(uint32_t* flag, uint32_t value) {

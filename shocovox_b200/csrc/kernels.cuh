@@ -43,6 +43,16 @@ struct FrameParams {
     //   cta_counter peers only: local counter of retired CTAs (reset by the CTA that finds it complete)
     // A peer launched with albedo == nullptr ships 8 B per pixel (hit id + distance); the root fills the albedo of the
     // peers' rows from its own palette (gather_complete_kernel).
+    // Heaviest-first order of the static schedule. The end of a launch is a tail of a few long rays during which most of the
+    // machine idles - 23 us of sponza 4K's 840 us, and the same ~30 us of the 130 us ONE of eight GPUs spends on its share of
+    // that frame (profiles/r02_pixel_timing_sponza.json): it is what bounds strong scaling. So the 16x8-pixel blocks are
+    // dispatched heaviest first, by the cycles they took in the PREVIOUS frame of the view (screen-space cost changes slowly
+    // between frames): every CTA records its block's cycles in cta_cost, a one-CTA counting sort queued behind the frame
+    // (order_ctas_kernel) turns them into the next frame's permutation, and the i-th CTA the hardware dispatches renders
+    // block cta_order[i]. The traversal code itself is untouched: one broadcast load per CTA. nullptr = raster order / no
+    // recording (first frame, whole-frame views by default).
+    const uint32_t* cta_order;  // [ctas] permutation of the block ids
+    uint32_t* cta_cost;         // [ctas] cycles per block, written by this launch
     uint32_t* go_flag;
     uint32_t* done_flag;
     uint32_t* cta_counter;
@@ -50,16 +60,15 @@ struct FrameParams {
     uint32_t gather_tuning;  // GATHER_TUNE_* bits (multi_gpu.cu), 0 = the defaults
 };
 
-// Tuning bits of the gather (SVX_GATHER_TUNING, read when a view opens / joins a gather). Default 0 = what measured best
-// (profiles/r02_gather_probe_*.json): peers run the persistent schedule, so the system-scope fence that must precede the
-// `done` flag is paid once per resident CTA instead of once per 16x8-pixel block - a membar.sys per block cost 18 % of the
-// peer's kernel even with local stores.
-constexpr uint32_t GATHER_TUNE_CTA_FENCE_GPU = 1u;  // retiring CTAs fence at gpu scope, only the publishing one at system scope
-constexpr uint32_t GATHER_TUNE_STATIC_PEERS = 2u;   // peers use the static schedule (one CTA and one fence per pixel block)
-constexpr uint32_t GATHER_TUNE_LOCAL_STORES = 4u;   // measurement only: peers store into their OWN framebuffer (no NVLink traffic; the frame is wrong)
-constexpr uint32_t GATHER_TUNE_PERSISTENT_ROOT = 8u;  // the root uses the persistent schedule as well
-constexpr uint32_t GATHER_TUNE_SIGNAL_KERNEL = 16u;   // peers: static schedule, no fence in the viewport kernel; a one-thread kernel queued
-                                                      // behind it publishes `done` (kernel completion orders the stores)
+// Tuning bits of the gather (SVX_GATHER_TUNING, read when a view opens / joins a gather). Default 0 = what measured best at
+// 2, 4 and 8 GPUs (profiles/r02_gather_probe_n*.json): peers run the static schedule and publish `done` from a one-thread
+// kernel queued behind the viewport kernel - the kernel boundary orders the stores, no fence inside the viewport kernel
+// (a membar.sys per 16x8-pixel block cost 18 % of the peer's kernel even with local stores).
+constexpr uint32_t GATHER_TUNE_CTA_FENCE_GPU = 1u;    // in-kernel variants: retiring CTAs fence at gpu scope, only the publishing one at system scope
+constexpr uint32_t GATHER_TUNE_INKERNEL_STATIC = 2u;  // peers: static schedule, the viewport kernel's last CTA publishes `done` (a system fence per CTA)
+constexpr uint32_t GATHER_TUNE_LOCAL_STORES = 4u;     // measurement only: peers store into their OWN framebuffer (no NVLink traffic; the frame is wrong)
+constexpr uint32_t GATHER_TUNE_PERSISTENT_ROOT = 8u;  // the root uses the persistent schedule
+constexpr uint32_t GATHER_TUNE_INKERNEL_PERSISTENT = 16u;  // peers: persistent schedule, in-kernel `done` (one system fence per resident CTA)
 
 // What the root's completion kernel needs besides the frame: which rows the peers own and the palette to resolve albedo with
 struct GatherComplete {
@@ -99,6 +108,8 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
 cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t want, uint64_t timeout_ns, uint32_t* error, uint32_t error_code,
                              cudaStream_t stream);
 cudaError_t launch_gather_complete(const GatherComplete& g, int sm_count, cudaStream_t stream);
+//   launch_order_ctas     order[] = the block ids 0..n-1 sorted by cost class, heaviest first (FrameParams::cta_order)
+cudaError_t launch_order_ctas(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream);
 //   launch_signal_flag    one thread: system fence, then *flag = value (release, system scope)
 cudaError_t launch_signal_flag(uint32_t* flag, uint32_t value, cudaStream_t stream);
 cudaError_t launch_rays(const DeviceTree& tree, const float* rays /* [n][6] */, uint64_t n, float viewing_distance,

@@ -85,6 +85,7 @@ int32_t open_root_locked(svx_view* root, uint32_t world, uint32_t rows_per_band,
     root->frame_seq = 0;
     root->gather_exports = 0;
     root->gather_tuning = tuning_from_env();
+    invalidate_block_order(root);
     root->gather_role = GATHER_ROOT;
     return SVX_OK;
 }
@@ -105,6 +106,7 @@ int32_t become_peer_locked(svx_view* v, uint32_t rank, uint32_t world, uint32_t 
     v->gather_wire = wire;
     v->frame_seq = 0;
     v->gather_tuning = tuning_from_env();
+    invalidate_block_order(v);
     return SVX_OK;
 }
 
@@ -208,6 +210,7 @@ int32_t svx_view_gather_close(svx_view* v) {
     v->rank = 0;
     v->world = 1;
     v->frame_seq = 0;
+    invalidate_block_order(v);
     if (v->h_error) *v->h_error = 0u;
     debug_stale("svx_view_gather_close: exit");
     return SVX_OK;
@@ -287,6 +290,7 @@ void svx_multi_free(svx_multi* m) {
     for (svx_view* v : m->local) svx_view_free(v);
     for (svx_view* v : m->whole) svx_view_free(v);
     for (svx_gpu_host* h : m->hosts) svx_gpu_host_free(h);
+    octree_release(m->tree);
     delete m;
 }
 
@@ -300,6 +304,7 @@ int32_t svx_multi_create(const svx_octree* tree, const int32_t* devices, uint32_
     svx_multi* m = new (std::nothrow) svx_multi();
     if (!m) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
     m->tree = tree;
+    octree_retain(tree);
     m->n = n;
     m->width = width;
     m->height = height;

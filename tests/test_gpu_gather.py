@@ -155,3 +155,65 @@ def test_degenerate_cameras_and_rays_are_rejected_not_rendered(tree):
                      [1e30, 1e30, -1e30, -0.57735026, -0.57735026, 0.57735026]], np.float32)
     out = host.get_by_rays(rays)
     assert out.shape[0] == 3
+
+
+def test_heaviest_first_block_order_renders_the_same_frames(tree):
+    """SVX_CTA_ORDER=2 forces the recorded block order (kernels.cuh: FrameParams::cta_order) on every static launch: frame 1
+    records the cost of every 16x8 block, every later frame is dispatched heaviest-first by the previous frame's costs - also
+    when the pose has changed in between. Whole frames, shards and gather members: bytes identical to the raster order."""
+    cams = [scenes.cpu_render_camera(k=11 * i) for i in range(5)]
+    res = (640, 363)
+    want = whole_frames(tree, cams, res)
+    os.environ["SVX_CTA_ORDER"] = "2"
+    try:
+        host = S.OctreeGPUHost(tree)
+        whole = host.create_new_view(1, viewport(cams[0]), res)
+        members = [S.OctreeGPUHost(tree).create_new_view(1, viewport(cams[0]), res) for _ in range(4)]
+        shards = [host.create_new_view(1, viewport(cams[0]), res) for _ in range(4)]
+    finally:
+        del os.environ["SVX_CTA_ORDER"]
+    for r, v in enumerate(shards):
+        v.set_shard(r, 4, 8)
+    members[0].gather_open(4, 8, S.WIRE_ID_DISTANCE, export=False)
+    for r in range(1, 4):
+        members[r].gather_join_local(r, members[0])
+    for i, c in enumerate(cams):
+        whole.set_viewport(viewport(c))
+        assert_same_frame(whole.render_to_host(), want[i], f"whole frame {i}")
+        planes = {"hit_id": np.zeros((res[1], res[0]), np.uint32), "albedo": np.zeros((res[1], res[0]), np.uint32),
+                  "distance": np.zeros((res[1], res[0]), np.float32)}
+        for v in shards:
+            v.set_viewport(viewport(c))
+            v.render_to_host(planes["hit_id"], planes["albedo"], planes["distance"])
+        assert_same_frame(planes, want[i], f"shards {i}")
+        for v in reversed(members):
+            v.set_viewport(viewport(c))
+            v.render(sync=False)
+        assert_same_frame(members[0].read_frame(), want[i], f"gather {i}")
+    for v in reversed(members):
+        v.gather_close()
+
+
+def test_handles_may_be_freed_in_any_order():
+    """A view keeps its host alive and a host its octree (capi_internal.hpp): finalisers that run in no particular order -
+    Python's cycle collector after an exception, for one - must not leave dangling handles. Raw C-ABI calls."""
+    import ctypes as C
+
+    L = S.lib()
+    scene = scenes.cpu_render_scene()
+    cam = scenes.cpu_render_camera()
+    want = whole_frames(scenes.build_tree(scene, S.Octree), [cam], (96, 64))[0]
+    tree = C.c_void_p()
+    assert L.svx_octree_new(scene.tree_size, scene.brick_dim, C.byref(tree)) == 0
+    xyz, rgba = np.ascontiguousarray(scene.xyz, np.uint32), np.ascontiguousarray(scene.rgba, np.uint8)
+    assert L.svx_octree_insert_batch(tree, xyz.ctypes.data, rgba.ctypes.data, None, len(xyz)) == 0
+    host, view = C.c_void_p(), C.c_void_p()
+    assert L.svx_gpu_host_create(tree, 0, C.byref(host)) == 0
+    vp = viewport(cam)._c()
+    assert L.svx_gpu_host_create_view(host, 1, C.byref(vp), 96, 64, C.byref(view)) == 0
+    L.svx_octree_free(tree)     # the octree first,
+    L.svx_gpu_host_free(host)   # then the host: the view still renders
+    got = {"hit_id": np.empty((64, 96), np.uint32), "albedo": np.empty((64, 96), np.uint32), "distance": np.empty((64, 96), np.float32)}
+    assert L.svx_view_render_to_host(view, got["hit_id"].ctypes.data, got["albedo"].ctypes.data, got["distance"].ctypes.data) == 0
+    assert_same_frame(got, want)
+    L.svx_view_free(view)       # the last reference takes host and octree with it

@@ -21,7 +21,7 @@ from shocovox_b200 import distributed as D, scenes  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "sponza_4k"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 bands = [int(b) for b in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["8"])]
-TUNINGS = [int(t) for t in (sys.argv[4].split(",") if len(sys.argv) > 4 else ["0", "1", "2", "4", "8"])]
+TUNINGS = [int(t) for t in (sys.argv[4].split(",") if len(sys.argv) > 4 else ["0", "4", "16"])]
 rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local_rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

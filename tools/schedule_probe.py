@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Static schedule vs persistent warps in raster order vs persistent warps handing out the tiles heaviest-first (by their
-cost in the previous frame), on whole frames and on rank 0's share of a frame split over 2 / 4 / 8 GPUs (the strong-scaling
+"""Static schedule in raster order vs the static schedule dispatching its 16x8-pixel blocks heaviest-first (by their cost in
+the previous frame; SVX_CTA_ORDER) vs persistent warps pulling tiles in raster order, on whole frames and on rank 0's share of a frame split over 2 / 4 / 8 GPUs (the strong-scaling
 case: the tail of the launch does not shrink with the share). One GPU; ms per frame, L2 flushed; frames compared byte for byte.
 
     python tools/schedule_probe.py [workload ...]
@@ -25,17 +25,14 @@ for name in names:
     rec = {}
     for world in (1, 2, 4, 8):
         frames = {}
-        for mode in ("static", "persistent_raster", "persistent_ordered"):
-            if mode == "persistent_raster":
-                os.environ["SVX_TILE_ORDER"] = "raster"
-            else:
-                os.environ.pop("SVX_TILE_ORDER", None)
+        for mode in ("static", "static_ordered", "persistent"):
+            os.environ["SVX_CTA_ORDER"] = "2" if mode == "static_ordered" else "0"
             view = host.create_new_view(64, S.Viewport(cam.origin, cam.direction, cam.frustum, cam.fov), res)
             if cam.glass_at_frustum_z:
                 view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
             if world > 1:
                 view.set_shard(0, world, 8)
-            view.set_schedule(mode != "static")
+            view.set_schedule(mode == "persistent")
             ms = []
             for i in range(20):
                 view.flush_l2()
@@ -48,8 +45,8 @@ for name in names:
         rows = np.array([r for r in range(res[1]) if (r // 8) % world == 0])
         rec[f"world{world}_frames_equal"] = all(
             bool(np.array_equal(frames["static"][k][rows].view(np.uint32), frames[m][k][rows].view(np.uint32)))
-            for m in ("persistent_raster", "persistent_ordered") for k in ("hit_id", "albedo", "distance"))
+            for m in ("static_ordered", "persistent") for k in ("hit_id", "albedo", "distance"))
     out[name] = rec
     print(name, json.dumps(rec), flush=True)
-os.environ.pop("SVX_TILE_ORDER", None)
+os.environ.pop("SVX_CTA_ORDER", None)
 print(json.dumps(out))
