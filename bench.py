@@ -429,9 +429,10 @@ def main() -> int:
     ap.add_argument("--workload", default="sponza_4k", choices=list(WORKLOADS))
     ap.add_argument("--mode", default="auto", choices=["auto", "poses", "tiles_nccl", "tiles_fused"],
                     help="N > 1: auto = tiles_fused (one frame, row bands, fused gather into rank 0's framebuffer)")
-    ap.add_argument("--wire", type=int, default=8, choices=[8, 12],
+    ap.add_argument("--wire", default="auto", choices=["auto", "8", "12"],
                     help="tiles_fused: bytes per pixel the peers send (12 = hit id, albedo, distance; 8 = hit id and distance, rank 0 "
-                         "resolves albedo = palette[hit id] for the received rows)")
+                         "resolves albedo = palette[hit id] for the received rows). auto = 12 up to 4 GPUs, 8 beyond: with 7 senders the "
+                         "12-byte format is bound by what NVLink delivers into rank 0 (profiles/r02_nvlink_store_bench.json)")
     ap.add_argument("--mips", default=None, metavar="VD",
                     help="switch the tree's MIP maps on and render through get_by_ray_at_lod at this viewing distance "
                          "(a number, or 'frustum' for the camera's viewport.frustum.z like the reference's shader)")
@@ -478,7 +479,8 @@ def main() -> int:
     elif mode == "auto":
         mode = "tiles_fused"
     tiles = mode in ("tiles_fused", "tiles_nccl")
-    wire = S.WIRE_ID_DISTANCE if args.wire == 8 else S.WIRE_THREE_PLANES
+    wire_bytes = (8 if world > 4 else 12) if args.wire == "auto" else int(args.wire)
+    wire = S.WIRE_ID_DISTANCE if wire_bytes == 8 else S.WIRE_THREE_PLANES
 
     scene, cams, res, desc = make_workload(args.workload)
     w, h = res
@@ -538,6 +540,7 @@ def main() -> int:
             gather()
     barrier()
     sampler.window(True)
+    launches0 = view.launch_count()
     wall0 = time.perf_counter()
     dev_ms_total = 0.0
     for i in range(args.steps):
@@ -551,6 +554,7 @@ def main() -> int:
         else:
             dev_ms_total += view.render(sync=True)["kernel_ms"]
     wall1 = time.perf_counter()
+    timed_launches = view.launch_count() - launches0  # every kernel this rank launched inside the timed steps (counted by the library)
     barrier()
     sampler.window(False)
 
@@ -648,6 +652,12 @@ def main() -> int:
         barrier()
     clocks = sampler.stop()
 
+    per_rank_ms = [dev_ms_total / args.steps]
+    if dist is not None:
+        mine = torch.tensor([dev_ms_total / args.steps], dtype=torch.float64, device=f"cuda:{local_rank}")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank_ms = [round(float(x.item()), 5) for x in every]
     if dist is not None:  # max over ranks
         t = torch.tensor([dev_ms_total, warm_ms_total, e2e_ms_total, e2e_sync_ms_total, e2e_8b_ms_total], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -663,8 +673,7 @@ def main() -> int:
            "tiles_nccl": "one frame in interleaved bands of %d rows over %d GPUs + NCCL all_gather of compact bands" % (BAND_ROWS, world),
            "tiles_fused": "one frame in interleaved bands of %d rows over %d GPUs (tree replicated); fused gather: the traversal kernels of ranks "
                           "1..%d store into rank 0's framebuffer over NVLink (CUDA IPC), %d B/pixel on the wire, device-side go/done flags, "
-                          "no host barrier and no collective per frame" % (BAND_ROWS, world, world - 1, args.wire)}[mode]
-    launches_per_step = {"single": 1, "poses": 1, "tiles_nccl": 1, "tiles_fused": 2}[mode]
+                          "no host barrier and no collective per frame" % (BAND_ROWS, world, world - 1, wire_bytes)}[mode]
     e2e_frames = (world if mode == "poses" else 1) * args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -680,6 +689,7 @@ def main() -> int:
             **({"mips": {"strategy": "MIPMapStrategy::default(), enabled after construction (one recalculate_mips)",
                          "viewing_distance": vd, "recalculate_s": round(t_mips, 3)}} if args.mips is not None else {}),
         },
+        "ms_per_step_per_rank": per_rank_ms,
         "value_warm_l2": value_warm, "ms_per_step_warm_l2": warm_ms_total / args.steps,
         "wall_ms_per_step_incl_flush": (wall1 - wall0) * 1e3 / args.steps,
         "e2e": {"value": rays_per_frame * e2e_frames / (e2e_ms_total * 1e-3) / 1e6, "unit": UNIT,
@@ -699,7 +709,7 @@ def main() -> int:
                          "per step: view.set_viewport(pose) + view.render_to_host_async(pinned hit_id, albedo, distance) + wait for the previous frame; ")
                         + "two host plane sets, copies on a second stream overlap the next kernel; wall clock over all steps incl. the final drain"
                           " (and a barrier over the ranks). synchronised_* = the same with render_to_host and a stream sync every step"},
-        "gpu_launches": int(args.steps * launches_per_step),
+        "gpu_launches": int(timed_launches),
         "gpu_launches_total_incl_warmup_and_e2e": int(view.launch_count() + (e2e_view.launch_count() if e2e_view is not view else 0)),
         "clocks": clocks,
     }

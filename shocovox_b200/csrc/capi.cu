@@ -557,7 +557,7 @@ int32_t render_locked(svx_view* v) {
     // the next frame's block order from this frame's costs. A root sorts while it waits for its peers; a peer has published
     // its rows by now, so its sort is off the frame's critical path
     if (ordered_ctas != 0 && v->gather_role != GATHER_PEER) {
-        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, v->stream));
+        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, (uint32_t)((uint64_t)ordered_ctas * v->order_head_pct / 100u), v->stream));
         v->launches += 1;
         v->order_valid = true;
     }
@@ -583,7 +583,7 @@ int32_t render_locked(svx_view* v) {
     }
     CUDA_TRY(cudaEventRecord(v->ev_stop, v->stream));
     if (ordered_ctas != 0 && v->gather_role == GATHER_PEER) {
-        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, v->stream));
+        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, (uint32_t)((uint64_t)ordered_ctas * v->order_head_pct / 100u), v->stream));
         v->launches += 1;
         v->order_valid = true;
     }
@@ -687,7 +687,7 @@ int32_t submit_async_locked(svx_view* v, uint32_t* hit_id, uint32_t* albedo, flo
     CUDA_TRY(cudaEventRecord(v->slot_rendered[k], v->stream));
     v->launches += 1;
     if (ordered_ctas != 0) {  // behind the "rendered" event: the copies of this frame do not wait for the sort
-        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, v->stream));
+        CUDA_TRY(launch_order_ctas(v->d_cta_cost, v->d_cta_order, ordered_ctas, (uint32_t)((uint64_t)ordered_ctas * v->order_head_pct / 100u), v->stream));
         v->launches += 1;
         v->order_valid = true;
     }
@@ -1178,6 +1178,7 @@ int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* 
     *v->h_error = 0u;
     v->d_cta_counter = v->d_counters + 2;
     if (const char* o = std::getenv("SVX_CTA_ORDER")) v->order_policy = std::atoi(o);
+    if (const char* o = std::getenv("SVX_CTA_ORDER_HEAD_PCT")) v->order_head_pct = (uint32_t)std::min(100, std::max(0, std::atoi(o)));
     if (const char* t = std::getenv("SVX_GATHER_TIMEOUT_MS")) v->gather_timeout_ns = (uint64_t)std::max(1L, std::atol(t)) * 1000000ull;
     const char* env = std::getenv("SVX_SCHEDULE");  // "persistent" | "static" (tuning override)
     v->persistent = env ? std::strcmp(env, "persistent") == 0 : SVX_DEFAULT_PERSISTENT;

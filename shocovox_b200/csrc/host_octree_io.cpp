@@ -470,6 +470,10 @@ int32_t HostOctree::from_bytes(const uint8_t* data, size_t len, HostOctree** out
     for (const NodeRec& n : t->nodes_) {
         if (!brick_ok(n.mip)) return SVX_E_DECODE;  // a MIP belongs to the key and survives a freed slot
         if (!n.reserved) continue;
+        // content and connection must be of one kind: leaves carry an occupancy bitmap, internal nodes child keys (the
+        // reference only debug-asserts this, e.g. detail.rs:524-544; a file that disagrees would be walked as the wrong thing)
+        if (((n.kind == NK_LEAF || n.kind == NK_UNIFORM) && n.link == LK_CHILDREN) || (n.kind == NK_INTERNAL && n.link == LK_BITMAP))
+            return SVX_E_DECODE;
         for (const BrickRef& b : n.brick)
             if (!brick_ok(b)) return SVX_E_DECODE;
     }

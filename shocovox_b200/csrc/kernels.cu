@@ -657,8 +657,9 @@ __device__ __forceinline__ uint32_t block_cost_class(uint32_t cycles) {
     const uint32_t level = 4u * lz + ((cycles >> (lz - 2u)) & 3u);  // floor(4 log2 cycles)
     return level >= 96u ? 0u : min(96u - level, ORDER_CLASSES - 1u);  // class 0: >= 2^24 cycles; 16x8 blocks sit around 2^14 - 2^20
 }
-__global__ void __launch_bounds__(1024) order_ctas_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n) {
+__global__ void __launch_bounds__(1024) order_ctas_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n, uint32_t head) {
     __shared__ uint32_t cursor[ORDER_CLASSES];
+    __shared__ uint32_t s_cut, s_head_total, s_tail_at, s_warp_sums[32];
     if (threadIdx.x < ORDER_CLASSES) cursor[threadIdx.x] = 0u;
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&cursor[block_cost_class(__ldcg(cost + i))], 1u);
@@ -671,16 +672,52 @@ __global__ void __launch_bounds__(1024) order_ctas_kernel(const uint32_t* __rest
             const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (threadIdx.x >= d) incl += up;
         }
+        // the HEAD of the order: whole classes, heaviest first, until at least `head` blocks are in it; everything lighter
+        // keeps its raster order behind them (a fully sorted frame ends in a burst of short blocks - and of their stores, which
+        // for a gather peer all cross NVLink at once)
+        const bool a_in = incl - a - b < head, b_in = incl - b < head;
+        const uint32_t votes = __ballot_sync(0xFFFFFFFFu, b_in), votes_a = __ballot_sync(0xFFFFFFFFu, a_in);
+        if (threadIdx.x == 0) {
+            const uint32_t full = (uint32_t)__popc(votes);  // lanes whose both classes are in the head
+            s_cut = 2u * full + ((full < 32u && ((votes_a >> full) & 1u)) ? 1u : 0u);  // classes [0, s_cut) form the head
+        }
         cursor[2u * threadIdx.x] = incl - a - b;
         cursor[2u * threadIdx.x + 1u] = incl - b;
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            const uint32_t cut = s_cut;
+            s_head_total = cut >= ORDER_CLASSES ? n : cursor[cut];
+            s_tail_at = s_head_total;
+        }
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&cursor[block_cost_class(__ldcg(cost + i))], 1u)] = i;
+    const uint32_t cut = s_cut;
+    // head: scattered by class; tail: a stable compaction (running offset + block-wide scan of "is tail" flags per 1024 blocks)
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t cls = i < n ? block_cost_class(__ldcg(cost + i)) : 0u;
+        const bool tail = i < n && cls >= cut;
+        if (i < n && !tail) order[atomicAdd(&cursor[cls], 1u)] = i;
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, tail);
+        if (lane == 0) s_warp_sums[warp] = (uint32_t)__popc(mask);
+        __syncthreads();
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; ++w) before += s_warp_sums[w];
+        if (tail) order[s_tail_at + before + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t all = 0;
+            for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) all += s_warp_sums[w];
+            s_tail_at += all;
+        }
+        __syncthreads();
+    }
 }
 
-cudaError_t launch_order_ctas(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream) {
+cudaError_t launch_order_ctas(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t head, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    order_ctas_kernel<<<1, 1024, 0, stream>>>(cost, order, n);
+    order_ctas_kernel<<<1, 1024, 0, stream>>>(cost, order, n, head);
     return cudaGetLastError();
 }
 

@@ -108,8 +108,9 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
 cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t want, uint64_t timeout_ns, uint32_t* error, uint32_t error_code,
                              cudaStream_t stream);
 cudaError_t launch_gather_complete(const GatherComplete& g, int sm_count, cudaStream_t stream);
-//   launch_order_ctas     order[] = the block ids 0..n-1 sorted by cost class, heaviest first (FrameParams::cta_order)
-cudaError_t launch_order_ctas(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream);
+//   launch_order_ctas     order[] = the block ids 0..n-1: the classes holding the `head` costliest blocks first, heaviest class
+//                         first, then all other blocks in raster order (FrameParams::cta_order)
+cudaError_t launch_order_ctas(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t head, cudaStream_t stream);
 //   launch_signal_flag    one thread: system fence, then *flag = value (release, system scope)
 cudaError_t launch_signal_flag(uint32_t* flag, uint32_t value, cudaStream_t stream);
 cudaError_t launch_rays(const DeviceTree& tree, const float* rays /* [n][6] */, uint64_t n, float viewing_distance,

@@ -84,6 +84,85 @@ def test_one_voxel_tree_matches_the_hand_assembled_bytes(IO):
     assert u.structure_hash() == t.structure_hash()
 
 
+# ---- (1b) a second, larger hand-assembled literal: two levels, Parted + Solid bricks, both palettes ----------------------------
+# Octree::new(8, 2) then
+#   insert((0,0,0), Visual(255,0,0,255))            -> colour 0
+#   insert((1,1,1), Complex((0,255,0,255), 7))      -> colour 1, data 0
+#   insert_at_lod((4,4,4), 4, Visual(0,255,0,255))  -> colour 1 again (add_to_palette finds it, update/mod.rs:55-136)
+# Field order = the nine emits of Octree::encode (src/convert/bytecode.rs:585-596), each traced through its own encoder:
+#  [0..2] emit_int(auto_simplify as u8) = 1, emit_int(octree_size) = 8, emit_int(brick_dim) = 2            (:586-588)
+#  [3] ObjectPool (object_pool.rs:97-108) = l first_available l ITEM* e e; ITEM = l reserved content e (:25-36).
+#      Three pushes, keys 0, 1, 2; `allocate` (:178-202) bumps first_available only while the next slot exists, so it stops
+#      at 2. All three are reserved (1).
+#      key 0, the root: NodeContent::Internal(occupied_bits) -> l "##" bits e (bytecode.rs:214-217). The root's 4x4x4 bitmap
+#        has cells of 2 voxels: (0,0,0) and (1,1,1) both fall into cell (0,0,0) = bit 0; the 4^3 fill at (4..8)^3 covers cells
+#        x,y,z in {2,3}: bit x + 4y + 16z (BITMAP_INDEX_LUT, lut.rs:210-235) = {42,43,46,47,58,59,62,63}
+#        -> 0xCC00CC0000000001 = 14699973484109365249
+#      key 1, the child at root octant 0 (covers (0..4)^3; 4 = 2 * brick_dim, so it is a Leaf, insert.rs:130-204):
+#        NodeContent::Leaf -> l "###" brick*8 e (:218-228). Both voxels are in its octant 0 (the 2^3 brick at (0..2)^3):
+#        BrickData::Parted -> l "##b#" len voxel*len "#" e (:111-119), 8 voxels in flat_projection order x + 2y + 4z
+#        (math/mod.rs:35-37): voxel 0 = colour 0, no data = 0xFFFF0000 = 4294901760 (pix_visual, node.rs:354-403);
+#        voxel 7 = (1,1,1) = colour 1 | data 0 << 16 = 1; the six others empty_marker() = 0xFFFFFFFF. Octants 1..7:
+#        BrickData::Empty -> "#b" (:106)
+#      key 2, the child at root octant 7 (x >= 4: 1, z >= 4: 2, y >= 4: 4): insert_at_lod fills a whole 4^3 node with one value
+#        -> NodeContent::UniformLeaf(Solid(colour 1, no data = 0xFFFF0001 = 4294901761)) -> l "##u#" l "#b#" value e e (:229-232, :107-110)
+#  [4] Vec<NodeChildren<u32>> parallel to the nodes (:354-372): root = l "##c##" key*8 e with key 1 in octant 0, key 2 in
+#      octant 7, empty_marker() = 4294967295 elsewhere; the two leaves = l "##b##" bitmap e: node 1's 4x4x4 cells are single
+#      voxels, (0,0,0) -> bit 0 and (1,1,1) -> bit 1 + 4 + 16 = 21 -> 0x200001 = 2097153; node 2 is full -> u64::MAX
+#  [5] Vec<BrickData> node_mips, one per key (types.rs:186): MIP maps are off, all BrickData::Empty -> "#b"
+#  [6] colour palette = l (l r g b a e)* e (:32-38) in insertion order; [7] data palette = l 7 e
+#  [8] MIPMapStrategy::default() (:439-453; same bytes as in ONE_VOXEL above)
+TWO_LEVELS = (
+    b"l"
+    b"i1e" b"i8e" b"i2e"
+    b"l" b"i2e"
+    b"l"
+    b"l" b"i1e" b"l2:##i14699973484109365249ee" b"e"
+    b"l" b"i1e" b"l3:###"
+    b"l4:##b#i8e" b"i4294901760e" + b"i4294967295e" * 6 + b"i1e" b"1:#e"
+    + b"2:#b" * 7 + b"e" b"e"
+    b"l" b"i1e" b"l4:##u#" b"l3:#b#i4294901761ee" b"e" b"e"
+    b"e" b"e"
+    b"l"
+    b"l5:##c##" b"i1e" + b"i4294967295e" * 6 + b"i2e" b"e"
+    b"l5:##b##i2097153ee"
+    b"l5:##b##i18446744073709551615ee"
+    b"e"
+    b"l2:#b2:#b2:#be"
+    b"l" b"li255ei0ei0ei255ee" b"li0ei255ei0ei255ee" b"e"
+    b"li7ee"
+    b"l" b"i0e" b"i4e" b"i1ei1e" b"i2ei0e" b"i3ei0e" b"i4ei0e" b"i3e" b"i2ei100e" b"i3ei50e" b"i4ei20e" b"e"
+    b"e"
+)
+
+
+def build_two_levels(IO):
+    t = IO.new(8, 2)
+    assert t.insert((0, 0, 0), (255, 0, 0, 255)) == O.OK
+    assert t.insert((1, 1, 1), (0, 255, 0, 255), 7) == O.OK
+    assert t.insert_at_lod((4, 4, 4), 4, (0, 255, 0, 255)) == O.OK
+    return t
+
+
+def test_two_level_tree_matches_the_hand_assembled_bytes(IO):
+    t = build_two_levels(IO)
+    assert IO.to_bytes(t) == TWO_LEVELS
+    u = IO.from_bytes(TWO_LEVELS)
+    assert u.get((0, 0, 0)) == K((255, 0, 0, 255)) and u.get((1, 1, 1)) == K((0, 255, 0, 255), 7)
+    assert u.get((1, 0, 0)) == K() and u.get((3, 3, 3)) == K() and u.get((4, 0, 4)) == K()
+    for p in ((4, 4, 4), (7, 7, 7), (5, 6, 4)):
+        assert u.get(p) == K((0, 255, 0, 255))
+    assert u.structure_hash() == t.structure_hash()
+    # with MIP maps switched on afterwards the container changes in exactly two places: the `enabled` flag of the strategy
+    # ([8], first integer) and node_mips ([5]), which now holds Parted MIP bricks for the root and its first child (their
+    # voxel CONTENT is the business of the reference's mipmap KATs, tests/test_mipmap.py) and stays Empty for the UniformLeaf
+    t.switch_albedo_mip_maps(True) if hasattr(t, "switch_albedo_mip_maps") else t.tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
+    doc, plain = bdec(IO.to_bytes(t)), bdec(TWO_LEVELS)
+    assert doc[8] == [1] + plain[8][1:] and doc[:5] == plain[:5] and doc[6:8] == plain[6:8]
+    assert [m[0] if isinstance(m, list) else m for m in doc[5]] == [b"##b#", b"##b#", b"#b"]
+    assert all(len(m) == 2 + 8 + 1 and m[1] == 8 and m[-1] == b"#" for m in doc[5][:2])
+
+
 # ---- (2) a third encoder, from the grammar -----------------------------------------------------------------------
 def benc(v) -> bytes:
     if isinstance(v, bool):
