@@ -496,10 +496,11 @@ static int32_t attach_block_order(svx_view* v, FrameParams* f, bool persistent, 
     *n_ctas = 0;
     f->cta_order = nullptr;
     f->cta_cost = nullptr;
-    // Policy 1 (default): for the shards of a frame split four ways or more, where the tail of the launch is a large part of
-    // it - measured (profiles/r02_schedule_probe_v4.json): 1/8 of sponza 4K -8.6 %, 1/4 of minecraft 4K -20 %, but +2..4 % on
-    // halves and whole frames of sponza (the sort is not free and neighbouring blocks no longer run together), and a loss
-    // on frames too small to have a tail worth ordering.
+    // OFF by default (SVX_CTA_ORDER=1: shards of a frame split four ways or more, 2: every static launch). Measured in round 2
+    // (profiles/r02_schedule_probe_v*.json, r02_scaling_n8_*.json): alone on a GPU the order shortens 1/8 of sponza 4K by 6 %
+    // and 1/4 of minecraft 4K by 18 %, but it costs 2-10 % on halves and whole frames (the sort is not free and neighbouring
+    // blocks no longer run together), and inside the 8-GPU gather it LOSES 10 %: a sorted frame ends in a burst of short blocks
+    // whose stores all cross NVLink into rank 0 at once.
     if (persistent || f->shaded || v->order_policy == 0 || (v->order_policy == 1 && v->world < 4)) return SVX_OK;
     const uint32_t n = ((f->width + 15u) / 16u) * ((f->rows_local + 7u) / 8u);  // kernels.cu: one CTA per 16x8 pixels
     if (n < 4096u && v->order_policy != 2) return SVX_OK;

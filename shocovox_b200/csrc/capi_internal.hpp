@@ -107,8 +107,8 @@ struct svx_view {
     uint32_t* d_cta_order = nullptr;
     uint32_t order_ctas = 0;
     bool order_valid = false;
-    uint32_t order_head_pct = 12;  // SVX_CTA_ORDER_HEAD_PCT: share of the blocks dispatched heaviest-first; the rest keeps raster order
-    int32_t order_policy = 1;  // SVX_CTA_ORDER: 0 never, 1 for the shards of a frame split 4+ ways (default), 2 always
+    uint32_t order_head_pct = 100;  // SVX_CTA_ORDER_HEAD_PCT: share of the blocks dispatched heaviest-first; the rest keeps raster order
+    int32_t order_policy = 0;  // SVX_CTA_ORDER: 0 never (default), 1 for the shards of a frame split 4+ ways, 2 always
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     // Framebuffer: ONE allocation = hit_id | albedo | distance | GatherSync, the planes `plane_bytes` apart

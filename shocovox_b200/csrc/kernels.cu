@@ -55,7 +55,10 @@ __device__ __forceinline__ void glass_vector(const FrameParams& f, uint32_t x, u
 
 // SVX_PIXEL_TIMING=1 builds a MEASUREMENT variant of the library (tools/pixel_timing.py; never the product): every pixel's
 // planes carry when its ray ran instead of what it hit - hit_id = SM cycles spent, albedo / distance = start / end of the
-// pixel on the GPU's nanosecond timer (low 32 bits).
+// pixel on the GPU's nanosecond timer (low 32 bits). The end is the WARP's: lanes that leave the traversal early are parked
+// until the slowest ray of their warp is done (a stamp placed on the exit paths is not executed any earlier either - the
+// scheduler runs the lanes still in the loop first), so these are warp times; what lanes lose inside a warp is in ncu's
+// thread-efficiency counter.
 #ifndef SVX_PIXEL_TIMING
 #define SVX_PIXEL_TIMING 0
 #endif
@@ -659,7 +662,7 @@ __device__ __forceinline__ uint32_t block_cost_class(uint32_t cycles) {
 }
 __global__ void __launch_bounds__(1024) order_ctas_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n, uint32_t head) {
     __shared__ uint32_t cursor[ORDER_CLASSES];
-    __shared__ uint32_t s_cut, s_head_total, s_tail_at, s_warp_sums[32];
+    __shared__ uint32_t s_cut, s_head_total, s_warp_sums[32];
     if (threadIdx.x < ORDER_CLASSES) cursor[threadIdx.x] = 0u;
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&cursor[block_cost_class(__ldcg(cost + i))], 1u);
@@ -687,30 +690,34 @@ __global__ void __launch_bounds__(1024) order_ctas_kernel(const uint32_t* __rest
         if (threadIdx.x == 0) {
             const uint32_t cut = s_cut;
             s_head_total = cut >= ORDER_CLASSES ? n : cursor[cut];
-            s_tail_at = s_head_total;
         }
     }
     __syncthreads();
     const uint32_t cut = s_cut;
-    // head: scattered by class; tail: a stable compaction (running offset + block-wide scan of "is tail" flags per 1024 blocks)
+    // head: scattered by class; tail: a stable compaction, 1024 blocks per pass (ballot per warp, the 32 warp counts scanned by
+    // every warp with shuffles, the running offset kept in a register)
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t tail_at = s_head_total;
+    uint32_t ahead = threadIdx.x < n ? __ldcg(cost + threadIdx.x) : 0u;  // the next pass' cost is in flight while this pass synchronises
     for (uint32_t base = 0; base < n; base += blockDim.x) {
         const uint32_t i = base + threadIdx.x;
-        const uint32_t cls = i < n ? block_cost_class(__ldcg(cost + i)) : 0u;
+        const uint32_t cls = i < n ? block_cost_class(ahead) : 0u;
+        if (i + blockDim.x < n) ahead = __ldcg(cost + i + blockDim.x);
         const bool tail = i < n && cls >= cut;
         if (i < n && !tail) order[atomicAdd(&cursor[cls], 1u)] = i;
-        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, tail);
         if (lane == 0) s_warp_sums[warp] = (uint32_t)__popc(mask);
         __syncthreads();
-        uint32_t before = 0;
-        for (uint32_t w = 0; w < warp; ++w) before += s_warp_sums[w];
-        if (tail) order[s_tail_at + before + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = i;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t all = 0;
-            for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) all += s_warp_sums[w];
-            s_tail_at += all;
+        const uint32_t mine = s_warp_sums[lane];
+        uint32_t incl = mine;
+#pragma unroll
+        for (uint32_t d = 1; d < 32u; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += up;
         }
+        const uint32_t before = __shfl_sync(0xFFFFFFFFu, incl - mine, warp), total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (tail) order[tail_at + before + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = i;
+        tail_at += total;
         __syncthreads();
     }
 }

@@ -25,15 +25,14 @@ for name in names:
     rec = {}
     for world in (1, 2, 4, 8):
         frames = {}
-        for mode in ("static", "static_ordered", "static_ordered_full", "persistent"):
+        for mode in ("static", "static_ordered_12", "static_ordered_30", "static_ordered_60", "static_ordered_100"):
             os.environ["SVX_CTA_ORDER"] = "2" if mode.startswith("static_ordered") else "0"
-            os.environ["SVX_CTA_ORDER_HEAD_PCT"] = "100" if mode == "static_ordered_full" else "12"
+            os.environ["SVX_CTA_ORDER_HEAD_PCT"] = mode.rsplit("_", 1)[1] if mode.startswith("static_ordered") else "12"
             view = host.create_new_view(64, S.Viewport(cam.origin, cam.direction, cam.frustum, cam.fov), res)
             if cam.glass_at_frustum_z:
                 view.set_glass_mode(S.GLASS_AT_FRUSTUM_Z)
             if world > 1:
                 view.set_shard(0, world, 8)
-            view.set_schedule(mode == "persistent")
             ms = []
             for i in range(20):
                 view.flush_l2()
@@ -46,7 +45,7 @@ for name in names:
         rows = np.array([r for r in range(res[1]) if (r // 8) % world == 0])
         rec[f"world{world}_frames_equal"] = all(
             bool(np.array_equal(frames["static"][k][rows].view(np.uint32), frames[m][k][rows].view(np.uint32)))
-            for m in ("static_ordered", "static_ordered_full", "persistent") for k in ("hit_id", "albedo", "distance"))
+            for m in ("static_ordered_12", "static_ordered_30", "static_ordered_60", "static_ordered_100") for k in ("hit_id", "albedo", "distance"))
     out[name] = rec
     print(name, json.dumps(rec), flush=True)
 os.environ.pop("SVX_CTA_ORDER", None)
