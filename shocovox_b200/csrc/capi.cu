@@ -530,10 +530,13 @@ int32_t render_locked(svx_view* v) {
     cfg.persistent = v->persistent || (v->gather_role == GATHER_PEER && (v->gather_tuning & GATHER_TUNE_INKERNEL_PERSISTENT)) ||
                      (v->gather_role == GATHER_ROOT && (v->gather_tuning & GATHER_TUNE_PERSISTENT_ROOT));
     cfg.tile_counters = v->d_counters;
+    // a peer's pixels cross NVLink: whole 128-byte rows from a shared-memory stage (kernels.cu: render_staged_body)
+    cfg.staged_stores = v->gather_role == GATHER_PEER && !cfg.persistent &&
+                        !(v->gather_tuning & (GATHER_TUNE_DIRECT_STORES | GATHER_TUNE_LOCAL_STORES | GATHER_TUNE_INKERNEL_STATIC));
     f.counter_slot = v->counter_slot;
     if (cfg.persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
     uint32_t ordered_ctas = 0;
-    const int32_t attached = attach_block_order(v, &f, cfg.persistent, &ordered_ctas);
+    const int32_t attached = attach_block_order(v, &f, cfg.persistent || cfg.staged_stores, &ordered_ctas);
     if (attached != SVX_OK) return attached;
     if (v->gather_role == GATHER_PEER) {
         v->frame_seq += 1;

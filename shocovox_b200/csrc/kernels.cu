@@ -77,8 +77,11 @@ __device__ __forceinline__ uint32_t channel_u8(float v) { return min(__float2uin
 // (x, lr) = column and shard-local row. LOD: the tree's MIP maps are enabled (traverse.cuh: traverse<LOD>).
 // SHADE: also write the caller loop's shaded pixel (examples/cpu_render.rs:119-136) to the fourth plane.
 // BS >= 0: the tree's brick dimension is the compile-time constant 2^BS (traverse.cuh: brick_dim_of); -1 = read it from the tree.
-template <bool LOD, bool SHADE, int BS = -1>
-__device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr) {
+// STAGED: the three values go to the CTA's staging area in shared memory (`stage[plane * 128 + slot]`) instead of the
+// framebuffer; the caller writes them out as whole rows (render_staged_body). The other instantiations are unchanged by it.
+template <bool LOD, bool SHADE, int BS = -1, bool STAGED = false>
+__device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr,
+                                            uint32_t* stage = nullptr, uint32_t slot = 0) {
     if (x >= f.width || lr >= f.rows_local) return;
     // shard-local row -> image row (interleaved bands of 2^band_shift rows); one GPU owns every row in order
     uint32_t row = lr;
@@ -98,10 +101,16 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
     float dist = 0.0f;
     // 0) pixels outside the projected bounding rectangle of the root cube are sky (host-computed, conservative)
     if (x < f.cull_x0 || x > f.cull_x1 || row < f.cull_row0 || row > f.cull_row1) {
-        f.hit_id[i] = NIL;
-        if (f.albedo) f.albedo[i] = 0u;
-        f.distance[i] = 0.0f;
-        if (SHADE) f.shaded[i] = 0xFF808080u;
+        if constexpr (STAGED) {
+            stage[slot] = NIL;
+            stage[128u + slot] = 0u;
+            stage[256u + slot] = 0u;
+        } else {
+            f.hit_id[i] = NIL;
+            if (f.albedo) f.albedo[i] = 0u;
+            f.distance[i] = 0.0f;
+            if (SHADE) f.shaded[i] = 0xFF808080u;
+        }
         return;
     }
     uint32_t pixel = 0xFF808080u;  // Rgb([128, 128, 128]) on a miss (cpu_render.rs:134)
@@ -150,10 +159,16 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
     rgba = timing_t0;
     dist = __uint_as_float(timer_ns_lo());
 #endif
-    f.hit_id[i] = hit_id;
-    if (f.albedo) f.albedo[i] = rgba;  // nullptr: a gather peer shipping 8 B per pixel (kernels.cuh: FrameParams)
-    f.distance[i] = dist;
-    if (SHADE) f.shaded[i] = pixel;
+    if constexpr (STAGED) {
+        stage[slot] = hit_id;
+        stage[128u + slot] = rgba;
+        stage[256u + slot] = __float_as_uint(dist);
+    } else {
+        f.hit_id[i] = hit_id;
+        if (f.albedo) f.albedo[i] = rgba;  // nullptr: a gather peer shipping 8 B per pixel (kernels.cuh: FrameParams)
+        f.distance[i] = dist;
+        if (SHADE) f.shaded[i] = pixel;
+    }
 }
 
 // ---- tile-sharded gather: flags between the GPUs that render one frame together (kernels.cuh: FrameParams) ----------
@@ -253,6 +268,49 @@ SVX_RENDER_KERNEL(render_kernel_ordered_brick32, false, 5, true)
 SVX_RENDER_KERNEL(render_lod_kernel_ordered_brick8, true, 3, true)
 SVX_RENDER_KERNEL(render_lod_kernel_ordered_brick32, true, 5, true)
 #undef SVX_RENDER_KERNEL
+// Staged stores, for a gather peer: its pixels cross NVLink into rank 0's framebuffer, and what NVLink delivers depends on
+// how they are written - 540 GB/s into one GPU for three planes as the 32-byte row segments of 8x4-pixel warp tiles, 755 GB/s
+// as whole 128-byte lines (tools/nvlink_store_bench.cu, profiles/r02_nvlink_store_bench.json). So the CTA covers 32 x 4 pixels
+// (four warp tiles side by side), every warp leaves its tile's values in shared memory, and after one barrier warp w writes
+// row w of the block: 32 pixels, one 128-byte line per plane.
+template <bool LOD, int BS>
+__device__ __forceinline__ void render_staged_body(const DeviceTree& tree, const FrameParams& f) {
+    __shared__ uint32_t stage[3 * 128];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    gather_prologue(f);
+    {
+        const uint32_t cx = (warp << 3) + (lane & 7u), cy = lane >> 3;  // this thread's pixel inside the block
+        shade_pixel<LOD, false, BS, true>(tree, f, blockIdx.x * 32u + cx, blockIdx.y * 4u + cy, stage, cy * 32u + cx);
+    }
+    __syncthreads();
+    const uint32_t x = blockIdx.x * 32u + lane, lr = blockIdx.y * 4u + warp;
+    if (x < f.width && lr < f.rows_local) {
+        uint32_t row = lr;
+        if (f.world != 1u) {
+            const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
+            row = ((band * f.world + f.rank) << f.band_shift) + within;
+        }
+        if (row < f.height) {
+            const uint32_t i = (f.compact ? lr : row) * f.width + x, slot = warp * 32u + lane;
+            f.hit_id[i] = stage[slot];
+            if (f.albedo) f.albedo[i] = stage[128u + slot];
+            f.distance[i] = __uint_as_float(stage[256u + slot]);
+        }
+    }
+    gather_epilogue(f);
+}
+#define SVX_STAGED_KERNEL(NAME, LOD, BS)                                                                                    \
+    __global__ void __launch_bounds__(128, SVX_MIN_BLOCKS) NAME(const DeviceTree tree, const FrameParams f) {               \
+        render_staged_body<LOD, BS>(tree, f);                                                                               \
+    }
+SVX_STAGED_KERNEL(render_kernel_staged, false, -1)
+SVX_STAGED_KERNEL(render_lod_kernel_staged, true, -1)
+SVX_STAGED_KERNEL(render_kernel_staged_brick8, false, 3)
+SVX_STAGED_KERNEL(render_kernel_staged_brick32, false, 5)
+SVX_STAGED_KERNEL(render_lod_kernel_staged_brick8, true, 3)
+SVX_STAGED_KERNEL(render_lod_kernel_staged_brick32, true, 5)
+#undef SVX_STAGED_KERNEL
+
 #ifndef SVX_BRICK_SPECIALISED
 #define SVX_BRICK_SPECIALISED 1   // 0: always launch the generic kernels (A/B measurements, tools/probe_variants.sh)
 #endif
@@ -516,6 +574,21 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
             else if (shift == 5u) render_kernel_persistent_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
             else render_kernel_persistent<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
         }
+        return cudaGetLastError();
+    }
+    if (cfg.staged_stores && !frame.shaded) {
+        dim3 sgrid((frame.width + 31u) / 32u, (frame.rows_local + 3u) / 4u);
+#define SVX_LAUNCH(K) K<<<sgrid, 128, 0, stream>>>(tree, frame)
+        if (tree.mips_enabled) {
+            if (shift == 3u) SVX_LAUNCH(render_lod_kernel_staged_brick8);
+            else if (shift == 5u) SVX_LAUNCH(render_lod_kernel_staged_brick32);
+            else SVX_LAUNCH(render_lod_kernel_staged);
+        } else {
+            if (shift == 3u) SVX_LAUNCH(render_kernel_staged_brick8);
+            else if (shift == 5u) SVX_LAUNCH(render_kernel_staged_brick32);
+            else SVX_LAUNCH(render_kernel_staged);
+        }
+#undef SVX_LAUNCH
         return cudaGetLastError();
     }
     dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);

@@ -68,6 +68,7 @@ constexpr uint32_t GATHER_TUNE_CTA_FENCE_GPU = 1u;    // in-kernel variants: ret
 constexpr uint32_t GATHER_TUNE_INKERNEL_STATIC = 2u;  // peers: static schedule, the viewport kernel's last CTA publishes `done` (a system fence per CTA)
 constexpr uint32_t GATHER_TUNE_LOCAL_STORES = 4u;     // measurement only: peers store into their OWN framebuffer (no NVLink traffic; the frame is wrong)
 constexpr uint32_t GATHER_TUNE_PERSISTENT_ROOT = 8u;  // the root uses the persistent schedule
+constexpr uint32_t GATHER_TUNE_DIRECT_STORES = 32u;   // peers store from the warp tiles directly (32-byte segments) instead of staging whole rows
 constexpr uint32_t GATHER_TUNE_INKERNEL_PERSISTENT = 16u;  // peers: persistent schedule, in-kernel `done` (one system fence per resident CTA)
 
 // What the root's completion kernel needs besides the frame: which rows the peers own and the palette to resolve albedo with
@@ -97,6 +98,7 @@ struct RayHitRecord {
 struct LaunchConfig {
     int sm_count = 148;
     bool persistent = false;          // warp-granular dynamic tile schedule instead of one CTA per 32x8 block
+    bool staged_stores = false;       // static schedule with 32x4-pixel CTAs that write whole 128-byte rows (gather peers: kernels.cu)
     uint32_t* tile_counters = nullptr;  // device, two u32 ticket counters (ping-pong across launches)
 };
 
