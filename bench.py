@@ -431,8 +431,8 @@ def main() -> int:
                     help="N > 1: auto = tiles_fused (one frame, row bands, fused gather into rank 0's framebuffer)")
     ap.add_argument("--wire", default="auto", choices=["auto", "8", "12"],
                     help="tiles_fused: bytes per pixel the peers send (12 = hit id, albedo, distance; 8 = hit id and distance, rank 0 "
-                         "resolves albedo = palette[hit id] for the received rows). auto = 12 up to 4 GPUs, 8 beyond: with 7 senders the "
-                         "12-byte format is bound by what NVLink delivers into rank 0 (profiles/r02_nvlink_store_bench.json)")
+                         "resolves albedo = palette[hit id] for the received rows). auto = 12: beyond 4 GPUs the peers write whole 128-byte rows "
+                         "from a shared-memory stage, which NVLink delivers fast enough (profiles/r02_gather_probe_n8_staged.json)")
     ap.add_argument("--mips", default=None, metavar="VD",
                     help="switch the tree's MIP maps on and render through get_by_ray_at_lod at this viewing distance "
                          "(a number, or 'frustum' for the camera's viewport.frustum.z like the reference's shader)")
@@ -479,7 +479,7 @@ def main() -> int:
     elif mode == "auto":
         mode = "tiles_fused"
     tiles = mode in ("tiles_fused", "tiles_nccl")
-    wire_bytes = (8 if world > 4 else 12) if args.wire == "auto" else int(args.wire)
+    wire_bytes = 12 if args.wire == "auto" else int(args.wire)
     wire = S.WIRE_ID_DISTANCE if wire_bytes == 8 else S.WIRE_THREE_PLANES
 
     scene, cams, res, desc = make_workload(args.workload)
@@ -518,7 +518,11 @@ def main() -> int:
         def gather():
             with torch.cuda.stream(stream):
                 return [D.gather_bands(p, h, world, BAND_ROWS) for p in planes]
-    rays_per_rank_step = sum(1 for r in range(h) if (r // BAND_ROWS) % world == rank) * w if tiles else rays_per_frame
+    def owner_of_row(r):  # tiles_fused: the gather's rotated interleave (kernels.cuh: band_rotate); tiles_nccl: the plain one
+        b = r // BAND_ROWS
+        return (b % world + b // world) % world if mode == "tiles_fused" else b % world
+
+    rays_per_rank_step = sum(1 for r in range(h) if owner_of_row(r) == rank) * w if tiles else rays_per_frame
 
     def barrier():
         view.synchronize()

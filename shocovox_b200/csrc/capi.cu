@@ -337,6 +337,10 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     for (uint32_t b = v->rank; b < bands; b += v->world) ++owned_bands;
     f->rows_local = owned_bands * v->band_rows;
     (void)rows;
+    // gather members use the rotated interleave (kernels.cuh: band_rotate): every rank walks ceil(bands / world) cycles and the
+    // kernel skips the band of the last, partial cycle that falls outside the frame
+    f->band_rotate = v->gather_role != GATHER_NONE ? 1u : 0u;
+    if (f->band_rotate) f->rows_local = ((bands + v->world - 1) / v->world) * v->band_rows;
     // Conservative screen rectangle of the root cube. The looking glass is the parallelogram
     //   origin + dir*glass_d + a*right + b*up,  a in [-w/2, w/2], b in [-h/2, h/2]   (right is perpendicular to up),
     // pixel (x, y) looks through a = -w/2 + x*pw, b = -h/2 + y*ph. A cube corner P in front of the glass plane projects
@@ -530,8 +534,10 @@ int32_t render_locked(svx_view* v) {
     cfg.persistent = v->persistent || (v->gather_role == GATHER_PEER && (v->gather_tuning & GATHER_TUNE_INKERNEL_PERSISTENT)) ||
                      (v->gather_role == GATHER_ROOT && (v->gather_tuning & GATHER_TUNE_PERSISTENT_ROOT));
     cfg.tile_counters = v->d_counters;
-    // a peer's pixels cross NVLink: whole 128-byte rows from a shared-memory stage (kernels.cu: render_staged_body)
-    cfg.staged_stores = v->gather_role == GATHER_PEER && !cfg.persistent &&
+    // a peer's pixels cross NVLink: whole 128-byte rows from a shared-memory stage (kernels.cu: render_staged_body) once there
+    // are enough senders for NVLink's delivery into rank 0 to bound the frame (measured: 8 GPUs 0.228 -> 0.168 ms with the
+    // three-plane format; at 4 GPUs the stage costs 3 % and buys nothing)
+    cfg.staged_stores = v->gather_role == GATHER_PEER && !cfg.persistent && v->world > 4 &&
                         !(v->gather_tuning & (GATHER_TUNE_DIRECT_STORES | GATHER_TUNE_LOCAL_STORES | GATHER_TUNE_INKERNEL_STATIC));
     f.counter_slot = v->counter_slot;
     if (cfg.persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
@@ -576,6 +582,7 @@ int32_t render_locked(svx_view* v) {
         g.width = v->width;
         g.height = v->height;
         g.band_shift = f.band_shift;
+        g.band_rotate = f.band_rotate;
         g.hit_id = v->d_hit_id;
         g.albedo = v->d_albedo;
         g.palette = v->host->dev.palette;

@@ -77,6 +77,15 @@ __device__ __forceinline__ uint32_t channel_u8(float v) { return min(__float2uin
 // (x, lr) = column and shard-local row. LOD: the tree's MIP maps are enabled (traverse.cuh: traverse<LOD>).
 // SHADE: also write the caller loop's shaded pixel (examples/cpu_render.rs:119-136) to the fourth plane.
 // BS >= 0: the tree's brick dimension is the compile-time constant 2^BS (traverse.cuh: brick_dim_of); -1 = read it from the tree.
+// shard-local row -> image row: the rank's k-th band is global band k * world + rank (plain interleave) or, rotated,
+// k * world + (rank - k) mod world (FrameParams::band_rotate)
+__device__ __forceinline__ uint32_t image_row_of(const FrameParams& f, uint32_t lr) {
+    if (f.world == 1u) return lr;
+    const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
+    const uint32_t place = f.band_rotate ? (f.rank + f.world - band % f.world) % f.world : f.rank;
+    return ((band * f.world + place) << f.band_shift) + within;
+}
+
 // STAGED: the three values go to the CTA's staging area in shared memory (`stage[plane * 128 + slot]`) instead of the
 // framebuffer; the caller writes them out as whole rows (render_staged_body). The other instantiations are unchanged by it.
 template <bool LOD, bool SHADE, int BS = -1, bool STAGED = false>
@@ -84,11 +93,7 @@ __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameP
                                             uint32_t* stage = nullptr, uint32_t slot = 0) {
     if (x >= f.width || lr >= f.rows_local) return;
     // shard-local row -> image row (interleaved bands of 2^band_shift rows); one GPU owns every row in order
-    uint32_t row = lr;
-    if (f.world != 1u) {
-        const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
-        row = ((band * f.world + f.rank) << f.band_shift) + within;
-    }
+    const uint32_t row = image_row_of(f, lr);
     if (row >= f.height) return;
     const uint32_t y = f.height - 1u - row;  // pixel (x, y) lands in image row h-1-y (cpu_render.rs:106)
     const uint32_t i = (f.compact ? lr : row) * f.width + x;  // width * height < 2^32 (checked by the host)
@@ -285,11 +290,7 @@ __device__ __forceinline__ void render_staged_body(const DeviceTree& tree, const
     __syncthreads();
     const uint32_t x = blockIdx.x * 32u + lane, lr = blockIdx.y * 4u + warp;
     if (x < f.width && lr < f.rows_local) {
-        uint32_t row = lr;
-        if (f.world != 1u) {
-            const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
-            row = ((band * f.world + f.rank) << f.band_shift) + within;
-        }
+        const uint32_t row = image_row_of(f, lr);
         if (row < f.height) {
             const uint32_t i = (f.compact ? lr : row) * f.width + x, slot = warp * 32u + lane;
             f.hit_id[i] = stage[slot];
@@ -697,7 +698,8 @@ __global__ void __launch_bounds__(256) gather_complete_kernel(const GatherComple
     // retired every peer has been waited for.
     const bool vec = (g.width & 3u) == 0u;
     for (uint32_t row = blockIdx.x; row < g.height; row += gridDim.x) {
-        const uint32_t owner = (row >> g.band_shift) % g.world;
+        const uint32_t band = row >> g.band_shift;
+        const uint32_t owner = g.band_rotate ? (band % g.world + band / g.world) % g.world : band % g.world;
         if (owner == 0u) continue;  // the root's own rows already carry their albedo
         if (!wait_for(owner)) return;
         const size_t base = (size_t)row * g.width;

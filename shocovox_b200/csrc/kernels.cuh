@@ -18,6 +18,11 @@ struct FrameParams {
     uint32_t width, height;
     // sharding: this launch renders image rows r with (r / band_rows) % world == rank
     uint32_t rank, world, band_shift;  // bands of 2^band_shift rows
+    // 1: rotated interleave (gather members) - band g belongs to rank (g % world + g / world) % world, so the rank order
+    // shifts by one in every cycle of `world` bands and a cost pattern whose period on the screen matches the cycle (regular
+    // architecture, 64 rows at 8 GPUs) does not land on the same rank every time: at 8 GPUs one rank's share of sponza was
+    // 7 % heavier than the others' with the plain interleave (profiles/r02_gather_probe_n8_staged.json)
+    uint32_t band_rotate;
     uint32_t rows_local;   // number of image rows this shard owns
     // pixels outside [cull_x0, cull_x1] x [cull_row0, cull_row1] (image coordinates, inclusive) certainly miss the root
     // cube: a conservative screen-space bound of the cube's projection computed on the host (capi.cu)
@@ -77,7 +82,7 @@ struct GatherComplete {
     uint32_t done_stride;         // in u32 words
     uint32_t world, frame_seq;
     uint32_t fill_albedo;         // 1: peers shipped hit id + distance only
-    uint32_t width, height, band_shift;
+    uint32_t width, height, band_shift, band_rotate;
     const uint32_t* hit_id;
     uint32_t* albedo;
     const uint32_t* palette;
