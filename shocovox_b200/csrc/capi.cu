@@ -339,7 +339,8 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     (void)rows;
     // gather members use the rotated interleave (kernels.cuh: band_rotate): every rank walks ceil(bands / world) cycles and the
     // kernel skips the band of the last, partial cycle that falls outside the frame
-    f->band_rotate = v->gather_role != GATHER_NONE ? 1u : 0u;
+    f->band_rotate = (v->gather_role != GATHER_NONE && bands < 65536u) ? 1u : 0u;
+    f->world_magic = (uint32_t)((0x100000000ull + v->world - 1) / v->world);
     if (f->band_rotate) f->rows_local = ((bands + v->world - 1) / v->world) * v->band_rows;
     // Conservative screen rectangle of the root cube. The looking glass is the parallelogram
     //   origin + dir*glass_d + a*right + b*up,  a in [-w/2, w/2], b in [-h/2, h/2]   (right is perpendicular to up),

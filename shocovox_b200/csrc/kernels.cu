@@ -82,18 +82,25 @@ __device__ __forceinline__ uint32_t channel_u8(float v) { return min(__float2uin
 __device__ __forceinline__ uint32_t image_row_of(const FrameParams& f, uint32_t lr) {
     if (f.world == 1u) return lr;
     const uint32_t band = lr >> f.band_shift, within = lr & ((1u << f.band_shift) - 1u);
-    const uint32_t place = f.band_rotate ? (f.rank + f.world - band % f.world) % f.world : f.rank;
+    uint32_t place = f.rank;
+    if (f.band_rotate) {  // (rank - band) mod world without a division: the host checked that the frame has fewer than 2^16 bands
+        const uint32_t t = f.rank + f.world - (band - __umulhi(band, f.world_magic) * f.world);
+        place = t >= f.world ? t - f.world : t;
+    }
     return ((band * f.world + place) << f.band_shift) + within;
 }
 
 // STAGED: the three values go to the CTA's staging area in shared memory (`stage[plane * 128 + slot]`) instead of the
 // framebuffer; the caller writes them out as whole rows (render_staged_body). The other instantiations are unchanged by it.
-template <bool LOD, bool SHADE, int BS = -1, bool STAGED = false>
+// SHARDED = false: the launch renders a whole frame (world == 1), local rows are image rows and no band arithmetic is
+// compiled in (the whole-frame kernels are sensitive to every instruction of this prologue: +1.3 % on minecraft 4K with the
+// rotated interleave's code merely present behind a branch).
+template <bool LOD, bool SHADE, int BS = -1, bool STAGED = false, bool SHARDED = true>
 __device__ __forceinline__ void shade_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr,
                                             uint32_t* stage = nullptr, uint32_t slot = 0) {
     if (x >= f.width || lr >= f.rows_local) return;
     // shard-local row -> image row (interleaved bands of 2^band_shift rows); one GPU owns every row in order
-    const uint32_t row = image_row_of(f, lr);
+    const uint32_t row = SHARDED ? image_row_of(f, lr) : lr;
     if (row >= f.height) return;
     const uint32_t y = f.height - 1u - row;  // pixel (x, y) lands in image row h-1-y (cpu_render.rs:106)
     const uint32_t i = (f.compact ? lr : row) * f.width + x;  // width * height < 2^32 (checked by the host)
@@ -236,7 +243,7 @@ __device__ __forceinline__ void record_block_cost(const FrameParams& f, uint32_t
 // Static schedule: one CTA per 16x8 pixel block of the frame. ORDERED = false: block = the CTA's place in the grid, nothing
 // recorded (whole-frame views; exactly the round-1 kernels). ORDERED = true: heaviest-first order and / or cost recording
 // (FrameParams::cta_order / cta_cost), used for the shards of a frame split over several GPUs.
-template <bool LOD, int BS, bool ORDERED>
+template <bool LOD, int BS, bool ORDERED, bool SHARDED>
 __device__ __forceinline__ void render_static_body(const DeviceTree& tree, const FrameParams& f) {
     int tx, ty;
     pixel_of_thread(tx, ty);
@@ -245,10 +252,10 @@ __device__ __forceinline__ void render_static_body(const DeviceTree& tree, const
         __shared__ long long s_t0;
         uint32_t bx, by;
         block_of_cta(f, bx, by, &s_t0);
-        shade_pixel<LOD, false, BS>(tree, f, bx * TILE_W + tx, by * TILE_H + ty);
+        shade_pixel<LOD, false, BS, false, SHARDED>(tree, f, bx * TILE_W + tx, by * TILE_H + ty);
         record_block_cost(f, bx, by, &s_t0);
     } else {
-        shade_pixel<LOD, false, BS>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
+        shade_pixel<LOD, false, BS, false, SHARDED>(tree, f, blockIdx.x * TILE_W + tx, blockIdx.y * TILE_H + ty);
     }
     gather_epilogue(f);
 }
@@ -256,22 +263,31 @@ __device__ __forceinline__ void render_static_body(const DeviceTree& tree, const
 // dot_cube.rs:56, minecraft.rs:24, sponza.rs:24), where brick strides, masks and 1 / dim are immediates in the voxel loop;
 // each without / with MIP maps (get_by_ray / get_by_ray_at_lod per pixel) and in raster / recorded order. Same code, same
 // results; launch_render picks the instantiation.
-#define SVX_RENDER_KERNEL(NAME, LOD, BS, ORDERED)                                                                           \
+#define SVX_RENDER_KERNEL(NAME, LOD, BS, ORDERED, SHARDED)                                                                  \
     __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) NAME(const DeviceTree tree, const FrameParams f) {      \
-        render_static_body<LOD, BS, ORDERED>(tree, f);                                                                      \
+        render_static_body<LOD, BS, ORDERED, SHARDED>(tree, f);                                                             \
     }
-SVX_RENDER_KERNEL(render_kernel, false, -1, false)
-SVX_RENDER_KERNEL(render_lod_kernel, true, -1, false)
-SVX_RENDER_KERNEL(render_kernel_brick8, false, 3, false)
-SVX_RENDER_KERNEL(render_kernel_brick32, false, 5, false)
-SVX_RENDER_KERNEL(render_lod_kernel_brick8, true, 3, false)
-SVX_RENDER_KERNEL(render_lod_kernel_brick32, true, 5, false)
-SVX_RENDER_KERNEL(render_kernel_ordered, false, -1, true)
-SVX_RENDER_KERNEL(render_lod_kernel_ordered, true, -1, true)
-SVX_RENDER_KERNEL(render_kernel_ordered_brick8, false, 3, true)
-SVX_RENDER_KERNEL(render_kernel_ordered_brick32, false, 5, true)
-SVX_RENDER_KERNEL(render_lod_kernel_ordered_brick8, true, 3, true)
-SVX_RENDER_KERNEL(render_lod_kernel_ordered_brick32, true, 5, true)
+// whole frames
+SVX_RENDER_KERNEL(render_kernel, false, -1, false, false)
+SVX_RENDER_KERNEL(render_lod_kernel, true, -1, false, false)
+SVX_RENDER_KERNEL(render_kernel_brick8, false, 3, false, false)
+SVX_RENDER_KERNEL(render_kernel_brick32, false, 5, false, false)
+SVX_RENDER_KERNEL(render_lod_kernel_brick8, true, 3, false, false)
+SVX_RENDER_KERNEL(render_lod_kernel_brick32, true, 5, false, false)
+// the rows of one rank of a frame split over several GPUs
+SVX_RENDER_KERNEL(render_kernel_shard, false, -1, false, true)
+SVX_RENDER_KERNEL(render_lod_kernel_shard, true, -1, false, true)
+SVX_RENDER_KERNEL(render_kernel_shard_brick8, false, 3, false, true)
+SVX_RENDER_KERNEL(render_kernel_shard_brick32, false, 5, false, true)
+SVX_RENDER_KERNEL(render_lod_kernel_shard_brick8, true, 3, false, true)
+SVX_RENDER_KERNEL(render_lod_kernel_shard_brick32, true, 5, false, true)
+// ... and with the recorded block order / cost recording
+SVX_RENDER_KERNEL(render_kernel_ordered, false, -1, true, true)
+SVX_RENDER_KERNEL(render_lod_kernel_ordered, true, -1, true, true)
+SVX_RENDER_KERNEL(render_kernel_ordered_brick8, false, 3, true, true)
+SVX_RENDER_KERNEL(render_kernel_ordered_brick32, false, 5, true, true)
+SVX_RENDER_KERNEL(render_lod_kernel_ordered_brick8, true, 3, true, true)
+SVX_RENDER_KERNEL(render_lod_kernel_ordered_brick32, true, 5, true, true)
 #undef SVX_RENDER_KERNEL
 // Staged stores, for a gather peer: its pixels cross NVLink into rank 0's framebuffer, and what NVLink delivers depends on
 // how they are written - 540 GB/s into one GPU for three planes as the 32-byte row segments of 8x4-pixel warp tiles, 755 GB/s
@@ -593,17 +609,24 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
         return cudaGetLastError();
     }
     dim3 grid((frame.width + TILE_W - 1) / TILE_W, (frame.rows_local + TILE_H - 1) / TILE_H);
-    const bool ordered = frame.cta_order != nullptr || frame.cta_cost != nullptr;
+    const bool ordered = frame.cta_order != nullptr || frame.cta_cost != nullptr, sharded = frame.world != 1u;
 #define SVX_LAUNCH(K) K<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame)
+#define SVX_PICK(STEM, SUFFIX)                                                \
+    do {                                                                      \
+        if (ordered) SVX_LAUNCH(STEM##_ordered##SUFFIX);                      \
+        else if (sharded) SVX_LAUNCH(STEM##_shard##SUFFIX);                   \
+        else SVX_LAUNCH(STEM##SUFFIX);                                        \
+    } while (0)
     if (tree.mips_enabled) {
-        if (shift == 3u) { if (ordered) SVX_LAUNCH(render_lod_kernel_ordered_brick8); else SVX_LAUNCH(render_lod_kernel_brick8); }
-        else if (shift == 5u) { if (ordered) SVX_LAUNCH(render_lod_kernel_ordered_brick32); else SVX_LAUNCH(render_lod_kernel_brick32); }
-        else { if (ordered) SVX_LAUNCH(render_lod_kernel_ordered); else SVX_LAUNCH(render_lod_kernel); }
+        if (shift == 3u) SVX_PICK(render_lod_kernel, _brick8);
+        else if (shift == 5u) SVX_PICK(render_lod_kernel, _brick32);
+        else SVX_PICK(render_lod_kernel, );
     } else {
-        if (shift == 3u) { if (ordered) SVX_LAUNCH(render_kernel_ordered_brick8); else SVX_LAUNCH(render_kernel_brick8); }
-        else if (shift == 5u) { if (ordered) SVX_LAUNCH(render_kernel_ordered_brick32); else SVX_LAUNCH(render_kernel_brick32); }
-        else { if (ordered) SVX_LAUNCH(render_kernel_ordered); else SVX_LAUNCH(render_kernel); }
+        if (shift == 3u) SVX_PICK(render_kernel, _brick8);
+        else if (shift == 5u) SVX_PICK(render_kernel, _brick32);
+        else SVX_PICK(render_kernel, );
     }
+#undef SVX_PICK
 #undef SVX_LAUNCH
     return cudaGetLastError();
 }

@@ -23,6 +23,7 @@ struct FrameParams {
     // architecture, 64 rows at 8 GPUs) does not land on the same rank every time: at 8 GPUs one rank's share of sponza was
     // 7 % heavier than the others' with the plain interleave (profiles/r02_gather_probe_n8_staged.json)
     uint32_t band_rotate;
+    uint32_t world_magic;  // ceil(2^32 / world): band % world = band - umulhi(band, world_magic) * world, exact for band < 2^16
     uint32_t rows_local;   // number of image rows this shard owns
     // pixels outside [cull_x0, cull_x1] x [cull_row0, cull_row1] (image coordinates, inclusive) certainly miss the root
     // cube: a conservative screen-space bound of the cube's projection computed on the host (capi.cu)
