@@ -153,7 +153,32 @@ static void test_no_cpu_fallback() {
     EXPECT(error_of([&] { OctreeGPUHost host(tree); }) == SVX_E_CUDA);
 }
 
-int main() {
+// Octree::load_vox_file through the mirror (src/convert/magicavoxel.rs:266-289), plain and with a MIP strategy installed first
+static void test_load_vox_file(const char* path) {
+    Octree plain = Octree::load_vox_file(path, 8);
+    std::FILE* f = std::fopen(path, "rb");
+    EXPECT(f != nullptr);
+    std::vector<uint8_t> bytes;
+    for (int c; (c = std::fgetc(f)) != EOF;) bytes.push_back((uint8_t)c);
+    std::fclose(f);
+    Octree with_mips = Octree::load_vox_file(bytes, 8, [](StrategyUpdater s) { s.switch_albedo_mip_maps(true); });
+    EXPECT(plain.get_size() == with_mips.get_size());
+    // (the structure hash covers the palette, which the MIPs extend with averaged colours: compare the voxels themselves)
+    size_t filled = 0;
+    for (uint32_t x = 0; x < plain.get_size(); x += 3)
+        for (uint32_t y = 0; y < plain.get_size(); y += 3)
+            for (uint32_t z = 0; z < plain.get_size(); z += 3) {
+                EXPECT(plain.get({x, y, z}) == with_mips.get({x, y, z}));
+                filled += plain.get({x, y, z}).is_some() ? 1 : 0;
+            }
+    EXPECT(filled > 10);
+    EXPECT(with_mips.albedo_mip_map_resampling_strategy().is_enabled());
+    std::printf("vox size %u hash %016llx\n", plain.get_size(), (unsigned long long)plain.structure_hash());
+    EXPECT(error_of([&] { Octree::load_vox_file("/nonexistent.vox", 8); }) == SVX_E_IO);
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1) test_load_vox_file(argv[1]);
     test_simple_insert_and_get();
     test_complex_insert_and_get();
     test_insert_and_clear_at_lod();

@@ -243,6 +243,23 @@ class Octree {
         check(svx_octree_load(path.c_str(), &t.h_));
         return t;
     }
+    // Octree::load_vox_file(filename, brick_dimension), src/convert/magicavoxel.rs:266-289
+    static Octree load_vox_file(const std::string& filename, uint32_t brick_dimension) {
+        Octree t;
+        check(svx_octree_load_vox(filename.c_str(), brick_dimension, &t.h_));
+        return t;
+    }
+    // MIPMapStrategy::...::load_vox_file (magicavoxel.rs:207-250): `configure` sets the MIP strategy of the still EMPTY tree
+    // (e.g. `[](StrategyUpdater s) { s.switch_albedo_mip_maps(true); }`), then the voxels go in and refresh the MIPs as they do
+    template <typename Configure>
+    static Octree load_vox_file(const std::vector<uint8_t>& vox_bytes, uint32_t brick_dimension, Configure&& configure) {
+        uint32_t tree_size = 0;
+        check(svx_vox_required_tree_size(vox_bytes.data(), vox_bytes.size(), &tree_size));
+        Octree t = create(tree_size, brick_dimension);
+        configure(t.albedo_mip_map_resampling_strategy());
+        check(svx_octree_insert_vox(t.h_, vox_bytes.data(), vox_bytes.size()));
+        return t;
+    }
     svx_octree* handle() const { return h_; }
 
    private:
@@ -383,11 +400,73 @@ class OctreeGPUView {
         check(svx_view_wait_host(h_, keep_in_flight, &ms));
         return ms;
     }
+    // the framebuffer as it stands (on the root of a gather: the assembled frame of the last render)
+    Frame read_frame() {
+        Frame f;
+        const auto r = resolution();
+        f.width = r[0];
+        f.height = r[1];
+        f.hit_id.resize(size_t(r[0]) * r[1]);
+        f.albedo.resize(f.hit_id.size());
+        f.distance.resize(f.hit_id.size());
+        check(svx_view_read_frame(h_, f.hit_id.data(), f.albedo.data(), f.distance.data()));
+        return f;
+    }
+    // one frame over several GPUs, one process per GPU (the reference renders on one device; see svx_view_gather_* in the C
+    // header): the root's framebuffer assembles the frame, a peer's kernel stores into it
+    svx_gather_handle gather_open(uint32_t world, uint32_t rows_per_band = 8, svx_wire_format wire = SVX_WIRE_THREE_PLANES) {
+        svx_gather_handle h{};
+        check(svx_view_gather_open(h_, world, rows_per_band, wire, &h));
+        return h;
+    }
+    void gather_join(uint32_t rank, const svx_gather_handle& handle) { check(svx_view_gather_join(h_, rank, &handle)); }
+    void gather_join_local(uint32_t rank, OctreeGPUView& root) { check(svx_view_gather_join_local(h_, rank, root.h_)); }
+    void gather_close() { check(svx_view_gather_close(h_)); }
     svx_view* handle() const { return h_; }
 
    private:
     OctreeGPUHost* host_;
     svx_view* h_ = nullptr;
+};
+
+// One process driving several GPUs (svx_multi_*): a replica of the tree and a view per device, ONE frame per render call
+class MultiGPU {
+   public:
+    MultiGPU(const Octree& tree, const std::vector<int32_t>& devices, const Viewport& vp, std::array<uint32_t, 2> res,
+             uint32_t rows_per_band = 8, svx_wire_format wire = SVX_WIRE_THREE_PLANES)
+        : res_(res) {
+        const svx_viewport c = vp.to_c();
+        check(svx_multi_create(tree.handle(), devices.data(), (uint32_t)devices.size(), &c, res[0], res[1], rows_per_band, wire, &h_));
+    }
+    MultiGPU(const MultiGPU&) = delete;
+    MultiGPU& operator=(const MultiGPU&) = delete;
+    ~MultiGPU() { svx_multi_free(h_); }
+    void set_viewport(const Viewport& vp) {
+        const svx_viewport c = vp.to_c();
+        check(svx_multi_set_viewport(h_, &c));
+    }
+    void set_glass_mode(svx_glass_mode m) { check(svx_multi_set_glass_mode(h_, m)); }
+    void set_viewing_distance(float d) { check(svx_multi_set_viewing_distance(h_, d)); }
+    void reload() { check(svx_multi_reload(h_)); }
+    svx_frame render() {  // gathered in devices[0]'s framebuffer by the viewport kernels themselves
+        svx_frame f{};
+        check(svx_multi_render(h_, &f));
+        return f;
+    }
+    Frame render_to_host() {  // every GPU copies the rows it rendered over its own PCIe link
+        Frame f;
+        f.width = res_[0];
+        f.height = res_[1];
+        f.hit_id.resize(size_t(res_[0]) * res_[1]);
+        f.albedo.resize(f.hit_id.size());
+        f.distance.resize(f.hit_id.size());
+        check(svx_multi_render_to_host(h_, f.hit_id.data(), f.albedo.data(), f.distance.data()));
+        return f;
+    }
+
+   private:
+    std::array<uint32_t, 2> res_;
+    svx_multi* h_ = nullptr;
 };
 
 inline OctreeGPUView OctreeGPUHost::create_new_view(uint32_t size, const Viewport& viewport, std::array<uint32_t, 2> resolution) {

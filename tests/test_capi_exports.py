@@ -53,6 +53,36 @@ def test_null_arguments_are_rejected_not_crashed():
     assert L.svx_view_render(None, None) == api.E_INVALID_ARGUMENT
 
 
+def test_multi_gpu_and_vox_entry_points_check_their_arguments():
+    """The gather / multi / .vox entry points refuse null handles and malformed input with a status, on a box without a GPU too."""
+    import ctypes as C
+
+    L = S.lib()
+    for call in (lambda: L.svx_view_gather_open(None, 2, 8, 0, None), lambda: L.svx_view_gather_join(None, 1, None),
+                 lambda: L.svx_view_gather_join_local(None, 1, None), lambda: L.svx_view_gather_close(None),
+                 lambda: L.svx_view_gather_info(None, None, None, None, None), lambda: L.svx_view_read_frame(None, None, None, None),
+                 lambda: L.svx_multi_create(None, None, 2, None, 64, 64, 8, 0, None), lambda: L.svx_multi_render(None, None),
+                 lambda: L.svx_multi_render_to_host(None, None, None, None), lambda: L.svx_multi_set_viewport(None, None),
+                 lambda: L.svx_multi_render_poses(None, None, 1, None, None, None, None),
+                 lambda: L.svx_octree_load_vox(None, 8, None), lambda: L.svx_octree_load_vox_bytes(None, 0, 8, None),
+                 lambda: L.svx_vox_required_tree_size(None, 0, None), lambda: L.svx_octree_insert_vox(None, None, 0)):
+        assert call() == api.E_INVALID_ARGUMENT
+    L.svx_multi_free(None)  # a null handle is a no-op, like the other *_free
+    assert L.svx_multi_device_count(None) == 0 and L.svx_multi_view(None, 0) is None
+    out = C.c_void_p()
+    assert L.svx_octree_load_vox_bytes(b"VOX \x96\x00\x00\x00", 8, 8, C.byref(out)) == api.E_DECODE and not out.value
+    t = S.Octree(64, 8)
+    # svx_multi_create validates the shape before it touches a device
+    vp = S.Viewport((100.0, 100.0, 100.0), tuple(S.normalized((-1, -1, -1))))._c()
+    devs = (C.c_int32 * 2)(0, 0)
+    for world, band, wire in ((0, 8, 0), (17, 8, 0), (2, 6, 0), (2, 8, 7)):
+        assert L.svx_multi_create(t.handle, devs, world, C.byref(vp), 64, 64, band, wire, C.byref(out)) == api.E_INVALID_ARGUMENT
+    # get_sweep: a box that leaves the tree is refused instead of wrapping around in 32 bits (ADVICE r1)
+    buf = (C.c_uint8 * 64)()
+    assert L.svx_octree_get_sweep(t.handle, 60, 0, 0, 8, 1, 1, buf) == api.E_INVALID_POSITION
+    assert L.svx_octree_get_sweep(t.handle, 0xFFFFFFFF, 0, 0, 2, 1, 1, buf) == api.E_INVALID_POSITION
+
+
 def test_no_cpu_fallback_without_a_gpu():
     """Without a CUDA device the ray path must fail loudly, never fall back to host code."""
     if S.cuda_device_count() > 0:

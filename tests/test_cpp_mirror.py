@@ -63,9 +63,14 @@ def test_c_multi_gpu_two_members():
 
 def test_cpp_construction_api():
     exe = compile_example("octree_api_test")
-    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    vox_path = ROOT / "tests" / "golden" / "vox" / "navigate.vox"
+    res = subprocess.run([str(exe), str(vox_path)], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "octree_api_test: ok" in res.stdout
+    # Octree::load_vox_file through the C++ mirror builds the tree the Python mirror builds
+    want = S.Octree.load_vox_file(str(vox_path), 8)
+    line = next(l for l in res.stdout.splitlines() if l.startswith("vox size"))
+    assert int(line.split()[2]) == want.get_size() and int(line.split()[4], 16) == want.structure_hash()
 
 
 def fnv1a(data: bytes, h: int = 1469598103934665603) -> int:
