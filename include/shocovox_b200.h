@@ -322,8 +322,10 @@ SVX_API int32_t svx_view_resolution(const svx_view* view, uint32_t* width, uint3
 /* Multi-GPU sharding: this view renders image rows r with (r / rows_per_band) % world == rank. world = 1 renders
  * everything (the default). rows_per_band must be a power of two. */
 SVX_API int32_t svx_view_set_shard(svx_view* view, uint32_t rank, uint32_t world, uint32_t rows_per_band);
-/* Launch schedule of the viewport kernel: 0 = one CTA per 32x8 pixel block, 1 = persistent warps pulling 8x4 tiles from a
- * device-side ticket counter (better on frames with long-running rays). Results are identical. */
+/* Launch schedule of the viewport kernel: 0 = one CTA per 16x8 pixel block (default), 1 = persistent warps pulling 8x4 tiles
+ * from a device-side ticket counter, 2 = persistent warps whose finished lanes take new pixels while the others keep their
+ * place in the tree (lane refill; an experiment, 16-48 % slower on every measured scene - profiles/r02_experiments.md section 8).
+ * Results are identical. */
 SVX_API int32_t svx_view_set_schedule(svx_view* view, int32_t persistent);
 /* With compact rows the shard's rows are stored back to back ([rows_local][width], band-major) instead of at their image
  * rows: the layout a collective gather wants. */

@@ -797,7 +797,8 @@ class OctreeGPUView:
     def set_shard(self, rank: int, world: int, rows_per_band: int = 8):
         _check(lib().svx_view_set_shard(self._h, int(rank), int(world), int(rows_per_band)))
 
-    def set_schedule(self, persistent: bool):
+    def set_schedule(self, persistent):
+        """0 / False: static CTAs (default); 1 / True: persistent warps; 2: persistent warps with lane refill (experiment)"""
         _check(lib().svx_view_set_schedule(self._h, int(persistent)))
 
     def set_compact_rows(self, enabled: bool):

@@ -18,7 +18,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libshocovox_b200.so"
 SOURCES = ["host_octree.cpp", "host_octree_mip.cpp", "host_octree_io.cpp", "vox_import.cpp", "gpu_tree.cpp", "kernels.cu", "capi.cu", "multi_gpu.cu"]
-HEADERS = ["host_octree.hpp", "gpu_tree.hpp", "kernels.cuh", "traverse.cuh", "capi_internal.hpp", "vox_import.hpp", "../../include/shocovox_b200.h"]
+HEADERS = ["host_octree.hpp", "gpu_tree.hpp", "kernels.cuh", "traverse.cuh", "traverse_refill.cuh", "capi_internal.hpp", "vox_import.hpp", "../../include/shocovox_b200.h"]
 
 
 def nvcc_path() -> str:

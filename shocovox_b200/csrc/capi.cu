@@ -400,6 +400,9 @@ void make_frame_constants(const svx_view* v, FrameParams* f) {
     f->go_flag = f->done_flag = f->cta_counter = nullptr;
     f->frame_seq = 0;
     f->gather_tuning = v->gather_tuning;
+    f->refill_steps = v->refill_steps;
+    f->refill_min_idle = v->refill_min_idle;
+    f->refill_unit_tiles = v->refill_unit_tiles;
     if (v->gather_role == GATHER_PEER && !(v->gather_tuning & GATHER_TUNE_LOCAL_STORES)) {
         // the root's planes (same resolution, checked at join); 8-byte wire format: no albedo crosses NVLink
         char* base = static_cast<char*>(v->peer_block);
@@ -534,6 +537,7 @@ int32_t render_locked(svx_view* v) {
     const bool signal_kernel = v->gather_role == GATHER_PEER && !(v->gather_tuning & (GATHER_TUNE_INKERNEL_STATIC | GATHER_TUNE_INKERNEL_PERSISTENT));
     cfg.persistent = v->persistent || (v->gather_role == GATHER_PEER && (v->gather_tuning & GATHER_TUNE_INKERNEL_PERSISTENT)) ||
                      (v->gather_role == GATHER_ROOT && (v->gather_tuning & GATHER_TUNE_PERSISTENT_ROOT));
+    cfg.refill = cfg.persistent && v->refill && v->gather_role == GATHER_NONE;
     cfg.tile_counters = v->d_counters;
     // a peer's pixels cross NVLink: whole 128-byte rows from a shared-memory stage (kernels.cu: render_staged_body) once there
     // are enough senders for NVLink's delivery into rank 0 to bound the frame (measured: 8 GPUs 0.228 -> 0.168 ms with the
@@ -688,6 +692,7 @@ int32_t submit_async_locked(svx_view* v, uint32_t* hit_id, uint32_t* albedo, flo
     v->target_slot = 0;
     LaunchConfig cfg = v->host->cfg;
     cfg.persistent = v->persistent;
+    cfg.refill = v->persistent && v->refill;
     cfg.tile_counters = v->d_counters;
     f.counter_slot = v->counter_slot;
     if (v->persistent && !f.shaded) v->counter_slot ^= 1u;  // the shaded plane is rendered by the static schedule
@@ -1193,7 +1198,14 @@ int32_t svx_gpu_host_create_view(svx_gpu_host* h, uint32_t, const svx_viewport* 
     if (const char* o = std::getenv("SVX_CTA_ORDER_HEAD_PCT")) v->order_head_pct = (uint32_t)std::min(100, std::max(0, std::atoi(o)));
     if (const char* t = std::getenv("SVX_GATHER_TIMEOUT_MS")) v->gather_timeout_ns = (uint64_t)std::max(1L, std::atol(t)) * 1000000ull;
     const char* env = std::getenv("SVX_SCHEDULE");  // "persistent" | "static" (tuning override)
-    v->persistent = env ? std::strcmp(env, "persistent") == 0 : SVX_DEFAULT_PERSISTENT;
+    v->persistent = env ? (std::strcmp(env, "persistent") == 0 || std::strcmp(env, "refill") == 0) : SVX_DEFAULT_PERSISTENT;
+    v->refill = env && std::strcmp(env, "refill") == 0;
+    if (const char* e = std::getenv("SVX_REFILL_STEPS")) v->refill_steps = std::max(1l, std::min(1l << 20, std::atol(e)));
+    if (const char* e = std::getenv("SVX_REFILL_MIN_IDLE")) v->refill_min_idle = std::max(1l, std::min(32l, std::atol(e)));
+    if (const char* e = std::getenv("SVX_REFILL_UNIT")) {
+        const long u = std::atol(e);
+        if (u == 1 || u == 2 || u == 4 || u == 8) v->refill_unit_tiles = (uint32_t)u;
+    }
     *out = v;
     return SVX_OK;
 }
@@ -1335,6 +1347,7 @@ int32_t svx_view_set_schedule(svx_view* v, int32_t persistent) {
     CUDA_TRY(cudaMemsetAsync(v->d_counters, 0, 2 * sizeof(uint32_t), v->stream));
     v->counter_slot = 0;
     v->persistent = persistent != 0;
+    v->refill = persistent == 2;
     return SVX_OK;
 }
 

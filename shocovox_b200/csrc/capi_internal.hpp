@@ -101,6 +101,9 @@ struct svx_view {
     uint32_t* d_counters = nullptr;  // two ticket counters of the persistent schedule (ping-pong across launches)
     uint32_t counter_slot = 0;
     bool persistent = false;
+    bool refill = false;  // with `persistent`: the lane-refill schedule (svx_view_set_schedule(view, 2))
+    // SVX_REFILL_STEPS / SVX_REFILL_MIN_IDLE / SVX_REFILL_UNIT at view creation (tools/refill_probe.py)
+    uint32_t refill_steps = 64, refill_min_idle = 16, refill_unit_tiles = 1;  // the best of the sweep (profiles/r02_experiment_lane_refill.json)
     // heaviest-first block order of the static schedule (kernels.cuh: FrameParams::cta_order): cost and order arrays of
     // `order_ctas` blocks; `order_valid` once a frame has been recorded and sorted for the current resolution / shard
     uint32_t* d_cta_cost = nullptr;

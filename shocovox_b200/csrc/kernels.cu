@@ -4,6 +4,7 @@
 
 #include "kernels.cuh"
 #include "traverse.cuh"
+#include "traverse_refill.cuh"
 
 namespace svx {
 
@@ -403,6 +404,136 @@ SVX_PERSISTENT_KERNEL_FOR_BRICK(render_lod_kernel_persistent_brick8, true, 3)
 SVX_PERSISTENT_KERNEL_FOR_BRICK(render_lod_kernel_persistent_brick32, true, 5)
 #undef SVX_PERSISTENT_KERNEL_FOR_BRICK
 
+// ---- Lane refill (EXPERIMENT, svx_view_set_schedule(view, 2); north-star subsystem 2: "ballot/shuffle-based ray compaction") ----
+// Persistent warps whose lanes do not wait for the slowest ray of a tile: the traversal runs in rounds of f.refill_steps
+// node-loop iterations (traverse_resumable, traverse_refill.cuh); after a round, lanes whose ray is done write their pixel,
+// and once at least f.refill_min_idle lanes are idle they take the next pixels of the warp's pool (tiles pulled from the ticket
+// counter, handed out in order with a ballot + popc rank) while the others keep their place in the
+// tree. Framebuffer stores are per lane (scattered). Results are the same bits as every other schedule.
+
+// What shade_pixel does before and after the traversal, split for the refill schedule.
+// begin: 0 = the pixel is outside the frame, 1 = finished without a traversal (sky / certain miss: written here), 2 = a ray is on its way
+template <bool LOD, int BS>
+__device__ __forceinline__ int refill_begin_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t x, uint32_t lr, uint32_t& pix,
+                                                  RayConst& r, TraverseState& S) {
+    if (x >= f.width || lr >= f.rows_local) return 0;
+    const uint32_t row = image_row_of(f, lr);
+    if (row >= f.height) return 0;
+    const uint32_t y = f.height - 1u - row;
+    pix = (f.compact ? lr : row) * f.width + x;
+    bool may_hit = !(x < f.cull_x0 || x > f.cull_x1 || row < f.cull_row0 || row > f.cull_row1);
+    if (may_hit) {
+        float vx, vy, vz;
+        glass_vector(f, x, y, vx, vy, vz);
+        const float tree_size = (float)tree.tree_size;
+        if (f.prefilter) {
+            const float rl = rsqrtf((vx * vx) + (vy * vy) + (vz * vz));
+            may_hit = !certain_root_miss(f.ox, f.oy, f.oz, vx * rl, vy * rl, vz * rl, tree_size);
+        }
+        if (may_hit) {
+            const float len = sqrtf((vx * vx) + (vy * vy) + (vz * vz));
+            r.ox = f.ox; r.oy = f.oy; r.oz = f.oz;
+            r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
+            float px, py, pz;
+            uint32_t target_octant;
+            may_hit = root_entry_and_setup(r, tree_size, px, py, pz, target_octant);
+            if (may_hit) {
+                traverse_begin<LOD, BS>(tree, S, px, py, pz, target_octant);
+                return 2;
+            }
+        }
+    }
+    f.hit_id[pix] = NIL;
+    if (f.albedo) f.albedo[pix] = 0u;
+    f.distance[pix] = 0.0f;
+    return 1;
+}
+__device__ __forceinline__ void refill_finish_pixel(const DeviceTree& tree, const FrameParams& f, uint32_t pix, const RayConst& r,
+                                                    const TraceResult& res, bool hit) {
+    uint32_t hit_id = NIL, rgba = 0u;
+    float dist = 0.0f;
+    if (hit) {
+        hit_id = res.palette_value;
+        const uint32_t ci = res.palette_value & 0xFFFFu;
+        if (ci < 0xFFFFu && ci < tree.n_colors) rgba = __ldg(tree.palette + ci);
+        const float wx = res.px - r.ox, wy = res.py - r.oy, wz = res.pz - r.oz;
+        dist = sqrtf((wx * wx) + (wy * wy) + (wz * wz));  // V3c::length, vector.rs:75-77
+    }
+    f.hit_id[pix] = hit_id;
+    if (f.albedo) f.albedo[pix] = rgba;
+    f.distance[pix] = dist;
+}
+
+template <bool LOD, int BS>
+__device__ __forceinline__ void render_refill_body(const DeviceTree& tree, const FrameParams& f, uint32_t* __restrict__ counters) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[f.counter_slot ^ 1u] = 0u;
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    const uint32_t tiles_x = (f.width + 7u) >> 3, tiles_y = (f.rows_local + 3u) >> 2;
+    const uint32_t blocks_x = (tiles_x + 3u) >> 2, blocks_y = (tiles_y + 1u) >> 1, n_blocks = blocks_x * blocks_y;
+    // the warp's pool: f.refill_unit_tiles (1, 2, 4 or 8) consecutive 8x4 tiles of a 32x8-pixel block per ticket, `first_tile`
+    // the first of them, pixels q = next_q .. pool_size-1 still to hand out
+    const uint32_t unit = f.refill_unit_tiles, pool_size = unit << 5, n_tickets = n_blocks * (8u / unit);
+    uint32_t first_tile = 0u, next_q = pool_size;
+    bool pool_empty = false, has_ray = false;
+    uint32_t pix = 0u;
+    RayConst r;
+    TraverseState S;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !has_ray);
+        if (!pool_empty && (idle == 0xFFFFFFFFu || (uint32_t)__popc(idle) >= f.refill_min_idle)) {
+            uint32_t want = idle;
+            while (want != 0u) {
+                if (next_q >= pool_size) {
+                    uint32_t ticket = 0u;
+                    if (lane == 0) ticket = atomicAdd(&counters[f.counter_slot], 1u);
+                    ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+                    if (ticket >= n_tickets) {
+                        pool_empty = true;
+                        break;
+                    }
+                    first_tile = ticket * unit;
+                    next_q = 0u;
+                }
+                const uint32_t take = min((uint32_t)__popc(want), pool_size - next_q), rank = (uint32_t)__popc(want & below);
+                const bool served = ((want >> lane) & 1u) != 0u && rank < take;
+                if (served) {
+                    const uint32_t q = next_q + rank, tile = first_tile + (q >> 5), in_tile = q & 31u, blk = tile >> 3, sub = tile & 7u;
+                    const uint32_t ttx = ((blk % blocks_x) << 2) + (sub & 3u), tty = ((blk / blocks_x) << 1) + (sub >> 2);
+                    has_ray = refill_begin_pixel<LOD, BS>(tree, f, (ttx << 3) + (in_tile & 7u), (tty << 2) + (in_tile >> 3), pix, r, S) == 2;
+                }
+                want &= ~__ballot_sync(0xFFFFFFFFu, served);
+                next_q += take;
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, has_ray) == 0u) {
+            if (pool_empty) return;
+            continue;
+        }
+        if (has_ray) {
+            TraceResult res;
+            const int walk = traverse_resumable<LOD, BS>(tree, r, S, res, f.viewing_distance, f.refill_steps);
+            if (walk != WALK_SUSPENDED) {
+                refill_finish_pixel(tree, f, pix, r, res, walk == WALK_HIT);
+                has_ray = false;
+            }
+        }
+    }
+}
+#define SVX_REFILL_KERNEL(NAME, LOD, BS)                                                                                    \
+    __global__ void __launch_bounds__(BLOCK_THREADS, SVX_MIN_BLOCKS) NAME(const DeviceTree tree, const FrameParams f,        \
+                                                                         uint32_t* __restrict__ counters) {                 \
+        gather_prologue(f);                                                                                                 \
+        render_refill_body<LOD, BS>(tree, f, counters);                                                                     \
+        gather_epilogue(f);                                                                                                 \
+    }
+SVX_REFILL_KERNEL(render_kernel_refill, false, -1)
+SVX_REFILL_KERNEL(render_kernel_refill_brick8, false, 3)
+SVX_REFILL_KERNEL(render_kernel_refill_brick32, false, 5)
+SVX_REFILL_KERNEL(render_lod_kernel_refill, true, -1)
+SVX_REFILL_KERNEL(render_lod_kernel_refill_brick8, true, 3)
+SVX_REFILL_KERNEL(render_lod_kernel_refill_brick32, true, 5)
+#undef SVX_REFILL_KERNEL
+
 template <bool LOD>
 __device__ __forceinline__ void rays_body(const DeviceTree& tree, const float* __restrict__ rays, uint64_t n,
                                           float viewing_distance, RayHitRecord* __restrict__ out) {
@@ -579,6 +710,19 @@ cudaError_t launch_render(const DeviceTree& tree, const FrameParams& frame, cons
     // the specialised instantiations hard-code everything DeviceTree derives from brick_shift; anything else is generic
     const bool consistent = tree.brick_dim == (1u << tree.brick_shift) && tree.brick_dim_sq == tree.brick_dim * tree.brick_dim;
     const uint32_t shift = (SVX_BRICK_SPECIALISED && consistent) ? tree.brick_shift : 0xFFFFFFFFu;
+    if (cfg.persistent && cfg.refill && cfg.tile_counters) {
+        const unsigned grid = (unsigned)(cfg.sm_count * SVX_MIN_BLOCKS);
+        if (tree.mips_enabled) {
+            if (shift == 3u) render_lod_kernel_refill_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+            else if (shift == 5u) render_lod_kernel_refill_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+            else render_lod_kernel_refill<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+        } else {
+            if (shift == 3u) render_kernel_refill_brick8<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+            else if (shift == 5u) render_kernel_refill_brick32<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+            else render_kernel_refill<<<grid, BLOCK_THREADS, 0, stream>>>(tree, frame, cfg.tile_counters);
+        }
+        return cudaGetLastError();
+    }
     if (cfg.persistent && cfg.tile_counters) {
         // blocks_x * blocks_y * 8 tickets cover the frame in 32x8 blocks; ragged edges are skipped inside the kernel
         const unsigned grid = (unsigned)(cfg.sm_count * SVX_MIN_BLOCKS);

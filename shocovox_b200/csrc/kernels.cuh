@@ -64,6 +64,8 @@ struct FrameParams {
     uint32_t* cta_counter;
     uint32_t frame_seq;
     uint32_t gather_tuning;  // GATHER_TUNE_* bits (multi_gpu.cu), 0 = the defaults
+    // lane-refill schedule only: node-loop iterations per round, and how many lanes must be idle before the warp hands out pixels
+    uint32_t refill_steps, refill_min_idle, refill_unit_tiles;  // ... and 8x4 tiles per ticket (1, 2, 4, 8)
 };
 
 // Tuning bits of the gather (SVX_GATHER_TUNING, read when a view opens / joins a gather). Default 0 = what measured best at
@@ -104,6 +106,7 @@ struct RayHitRecord {
 struct LaunchConfig {
     int sm_count = 148;
     bool persistent = false;          // warp-granular dynamic tile schedule instead of one CTA per 32x8 block
+    bool refill = false;              // persistent schedule whose finished lanes take new pixels (experiment; kernels.cu: render_refill_body)
     bool staged_stores = false;       // static schedule with 32x4-pixel CTAs that write whole 128-byte rows (gather peers: kernels.cu)
     uint32_t* tile_counters = nullptr;  // device, two u32 ticket counters (ping-pong across launches)
 };

@@ -43,6 +43,9 @@ static inline T max(T a, T b) { return a < b ? b : a; }
 
 #include "kernels.cuh"   // RayHitRecord
 #include "traverse.cuh"
+#ifdef SVX_MIRROR_RESUMABLE  // = node-loop iterations per call: the suspend/resume form the lane-refill schedule runs
+#include "traverse_refill.cuh"
+#endif
 
 namespace {
 
@@ -61,8 +64,18 @@ void trace_range(const svx::DeviceTree& tree, const float* rays, uint64_t begin,
         uint32_t target_octant;
         // trace_ray (traverse.cuh) with the brick dimension as a template argument, as the viewport kernels instantiate it
         if (!certain_root_miss(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, (float)tree.tree_size) &&
-            root_entry_and_setup(r, (float)tree.tree_size, px, py, pz, target_octant))
+            root_entry_and_setup(r, (float)tree.tree_size, px, py, pz, target_octant)) {
+#ifdef SVX_MIRROR_RESUMABLE
+            TraverseState S;
+            traverse_begin<LOD, BS>(tree, S, px, py, pz, target_octant);
+            int walk;
+            do walk = traverse_resumable<LOD, BS>(tree, r, S, res, viewing_distance, (uint32_t)(SVX_MIRROR_RESUMABLE));
+            while (walk == WALK_SUSPENDED);
+            hit = walk == WALK_HIT;
+#else
             hit = traverse<LOD, BS>(tree, r, px, py, pz, target_octant, res, viewing_distance);
+#endif
+        }
         RayHitRecord h;
         h.hit = hit ? 1u : 0u;
         h.palette_value = hit ? res.palette_value : NIL;

@@ -8,6 +8,7 @@ data (svx_octree_render_data_nodes / _bricks, svx_render_data_ray_lut). Test inf
 ray path, and what nvcc / ptxas make of the same source is the business of the `-m gpu` tests."""
 import ctypes as C
 import subprocess
+import sys
 import zlib
 from pathlib import Path
 
@@ -31,7 +32,7 @@ def build_mirror(name: str, defines=()):
     out.mkdir(exist_ok=True)
     lib = out / f"lib{name}.so"
     csrc = ROOT / "shocovox_b200" / "csrc"
-    deps = [SRC, csrc / "traverse.cuh", csrc / "gpu_tree.hpp", csrc / "kernels.cuh"]
+    deps = [SRC, csrc / "traverse.cuh", csrc / "traverse_refill.cuh", csrc / "gpu_tree.hpp", csrc / "kernels.cuh"]
     if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
         cuda_include = Path(product_build.nvcc_path()).resolve().parent.parent / "include"
         res = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
@@ -182,3 +183,33 @@ def test_level_of_detail_branch_bit_exact(mirror, name):
         probes += int(want["hit"].sum())
     assert probes > 1000
     assert_same_hits(mirror_rays(mirror, tree, rays[:2000], specialise=0, viewing_distance=50.0), otree.get_by_rays_at_lod(rays[:2000], 50.0))
+
+
+# ---- the resumable form of the traversal (traverse_refill.cuh), what the lane-refill schedule runs ------------------------
+
+def test_traverse_refill_header_is_what_the_generator_makes_of_traverse_cuh():
+    """traverse_refill.cuh is derived text: tools/make_traverse_refill.py cuts traverse() out of traverse.cuh and turns its
+    locals into a state record. A change of the traversal that was not regenerated fails here."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import make_traverse_refill
+    committed = (ROOT / "shocovox_b200" / "csrc" / "traverse_refill.cuh").read_text()
+    assert make_traverse_refill.generate() == committed, "run python tools/make_traverse_refill.py"
+
+
+@pytest.mark.parametrize("quantum", [1, 3, 24])
+def test_suspended_and_resumed_traversal_is_bit_exact(quantum):
+    """traverse_begin + traverse_resumable called until it stops reporting WALK_SUSPENDED, with `quantum` node-loop iterations
+    per call (1 suspends at every possible point): every field equals the oracle's, plain and at LOD."""
+    L = build_mirror(f"host_mirror_resumable_{quantum}", defines=(f"SVX_MIRROR_RESUMABLE={quantum}",))
+    for name in ("cpu_render_64_8", "cpu_render_32_1", "dot_cube_128_32", "colonnade_256_8", "terrain_256_8_shell"):
+        scene = SCENES[name]()
+        tree, otree = scenes.build_tree(scene, S.Octree), scenes.build_tree(scene, O.OracleOctree)
+        rays = random_rays(scene.tree_size, 6000, 11 + zlib.crc32(name.encode()) % 1000)
+        want = otree.get_by_rays(rays)
+        assert want["hit"].sum() > 100
+        assert_same_hits(mirror_rays(L, tree, rays), want)
+        assert_same_hits(mirror_rays(L, tree, rays[:2000], specialise=0), want[:2000])
+        tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
+        otree.switch_albedo_mip_maps(True)
+        for vd in (F32_MAX, 50.0, 3.0, 0.0):
+            assert_same_hits(mirror_rays(L, tree, rays[:3000], viewing_distance=vd), otree.get_by_rays_at_lod(rays[:3000], vd))
