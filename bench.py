@@ -644,6 +644,16 @@ def main() -> int:
     e2e_sync_ms_total = e2e_loop(lambda p: p, pipelined=False)
     e2e_8b_ms_total = e2e_loop(lambda p: (p[0], 0, p[2]))  # hit id + distance: albedo is palette[hit_id & 0xFFFF]
     sampler.window(False)
+    # the 8-byte frame loses nothing: the albedo plane it leaves out is the tree's colour palette looked up by hit id
+    palette_equal = None
+    if rank == 0 and shared is None:
+        e2e_view.render_to_host_ptr(*ptr_sets[0])
+        ids, alb = (np.array(bufs[0][k].numpy() if pinned else bufs[0][k], copy=True).view(np.uint32) for k in (0, 1))
+        colors = tree.color_palette().astype(np.uint32)
+        packed = colors[:, 0] | (colors[:, 1] << 8) | (colors[:, 2] << 16) | (colors[:, 3] << 24)
+        index = ids & 0xFFFF
+        has_colour = (ids != 0xFFFFFFFF) & (index != 0xFFFF)
+        palette_equal = bool(np.array_equal(np.where(has_colour, packed[np.minimum(index, len(packed) - 1)], 0).astype(np.uint32), alb))
     e2e_equal = None
     if shared is not None:  # the host-assembled frame of the last full-planes loop against rank 0's own whole frame
         e2e_loop(lambda p: p, pipelined=False)
@@ -679,6 +689,18 @@ def main() -> int:
                           "1..%d store into rank 0's framebuffer over NVLink (CUDA IPC), %d B/pixel on the wire, device-side go/done flags, "
                           "no host barrier and no collective per frame" % (BAND_ROWS, world, world - 1, wire_bytes)}[mode]
     e2e_frames = (world if mode == "poses" else 1) * args.steps
+    # the box's device->host ceiling (plain pinned cudaMemcpyAsync, tools/d2h_ceiling.py on this pool's 8-GPU box): one GPU
+    # alone, and all 8 at once (the host fabric, not the GPUs' links, limits the aggregate)
+    d2h = {}
+    try:
+        ceil = json.load(open(ROOT / "profiles" / "r02_d2h_ceiling.json"))
+        gbs = ceil["one_gpu_gbs"] if world == 1 else min(world * ceil["one_gpu_gbs"], ceil["all_gpus_aggregate_gbs"])
+        e2e_gbs = 8 * n_px * e2e_frames / (e2e_8b_ms_total * 1e-3) / 1e9
+        d2h = {"d2h_gbs": e2e_gbs, "d2h_ceiling_gbs": gbs, "frac_of_d2h_ceiling": e2e_gbs / gbs,
+               "d2h_ceiling_source": "profiles/r02_d2h_ceiling.json: one GPU %.1f GB/s, 8 GPUs at once %.1f GB/s in total; "
+                                     "N GPUs = min(N x one, the 8-GPU total)" % (ceil["one_gpu_gbs"], ceil["all_gpus_aggregate_gbs"])}
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True,
@@ -696,21 +718,26 @@ def main() -> int:
         "ms_per_step_per_rank": per_rank_ms,
         "value_warm_l2": value_warm, "ms_per_step_warm_l2": warm_ms_total / args.steps,
         "wall_ms_per_step_incl_flush": (wall1 - wall0) * 1e3 / args.steps,
-        "e2e": {"value": rays_per_frame * e2e_frames / (e2e_ms_total * 1e-3) / 1e6, "unit": UNIT,
-                "h2d_bytes_per_step": 40 * world, "d2h_bytes_per_step": 12 * n_px * (world if mode == "poses" else 1),
-                "ms_per_step": e2e_ms_total / args.steps,
-                "synchronised_ms_per_step": e2e_sync_ms_total / args.steps,
-                "synchronised_value": rays_per_frame * e2e_frames / (e2e_sync_ms_total * 1e-3) / 1e6,
-                "id_distance": {"value": rays_per_frame * e2e_frames / (e2e_8b_ms_total * 1e-3) / 1e6, "ms_per_step": e2e_8b_ms_total / args.steps,
-                                "d2h_bytes_per_step": 8 * n_px * (world if mode == "poses" else 1),
-                                "note": "svx_view_render_to_host with albedo = NULL: hit id and distance planes only, 8 B/pixel; albedo "
-                                        "of a pixel is palette[hit_id & 0xFFFF], a lookup in a table the host already holds"},
+        # headline: the 8 B/pixel call; the three-plane call of the same loop is reported beside it
+        "e2e": {"value": rays_per_frame * e2e_frames / (e2e_8b_ms_total * 1e-3) / 1e6, "unit": UNIT,
+                "h2d_bytes_per_step": 40 * world, "d2h_bytes_per_step": 8 * n_px * (world if mode == "poses" else 1),
+                "ms_per_step": e2e_8b_ms_total / args.steps,
+                "planes": "hit_id + distance (svx_view_render_to_host_async with albedo = NULL): 8 B/pixel. The voxel a ray hit is its "
+                          "hit id (colour index | data index << 16, the reference's PaletteIndexValues); albedo = "
+                          "svx_octree_color_palette()[hit_id & 0xFFFF], a host lookup like the reference shader's color_palette[]",
+                **({"albedo_from_palette_equals_albedo_plane": palette_equal} if palette_equal is not None else {}),
+                **d2h,
+                "three_planes": {"value": rays_per_frame * e2e_frames / (e2e_ms_total * 1e-3) / 1e6, "ms_per_step": e2e_ms_total / args.steps,
+                                 "d2h_bytes_per_step": 12 * n_px * (world if mode == "poses" else 1),
+                                 "synchronised_ms_per_step": e2e_sync_ms_total / args.steps,
+                                 "synchronised_value": rays_per_frame * e2e_frames / (e2e_sync_ms_total * 1e-3) / 1e6,
+                                 "note": "hit_id, albedo and distance planes: 12 B/pixel, the albedo plane resolved on the GPU"},
                 "host_planes": ("POSIX shared memory mapped by every rank, " if shared is not None else "") + ("page-locked" if pinned else "PAGEABLE (pinning failed)"),
                 **({"host_assembled_frame_equals_single_gpu_frame": e2e_equal} if shared is not None else {}),
                 "note": ("per step and rank: view.set_viewport(pose) + view.render_to_host_async(shared host planes) on the rank's shard: its "
                          "kernel renders its bands, strided device->host copies put exactly those rows into the common frame, each GPU over its own "
                          "PCIe link; " if tiles else
-                         "per step: view.set_viewport(pose) + view.render_to_host_async(pinned hit_id, albedo, distance) + wait for the previous frame; ")
+                         "per step: view.set_viewport(pose) + view.render_to_host_async(pinned host planes) + wait for the previous frame; ")
                         + "two host plane sets, copies on a second stream overlap the next kernel; wall clock over all steps incl. the final drain"
                           " (and a barrier over the ranks). synchronised_* = the same with render_to_host and a stream sync every step"},
         "gpu_launches": int(timed_launches),

@@ -179,6 +179,14 @@ SVX_API int32_t svx_octree_set_auto_simplify(svx_octree* tree, int32_t enabled);
 /* Key-order independent digest of the reachable tree (node kinds, occupancy bits, bricks, palettes) */
 SVX_API uint64_t svx_octree_structure_hash(const svx_octree* tree);
 SVX_API uint64_t svx_octree_node_count(const svx_octree* tree);
+/* The palettes the tree's voxels index (voxel_color_palette / voxel_data_palette, src/octree/types.rs:191-192): a voxel is
+ * PaletteIndexValues = colour index | data index << 16, 0xFFFF = none (src/octree/types.rs:100, detail.rs:31-60) - which is
+ * also what the hit_id plane of a frame holds. Copies min(capacity, *count) entries; *count receives the palette's size
+ * (out may be NULL to ask for it). With these a caller of svx_view_render_to_host(view, hit_id, NULL, distance) resolves
+ * albedo = colours[hit_id & 0xFFFF] itself, like the reference's shader does from its color_palette buffer
+ * (assets/shaders/viewport_render.wgsl). MIP maps add colours: read the palette after switching them on. */
+SVX_API int32_t svx_octree_color_palette(const svx_octree* tree, svx_albedo* out, uint32_t capacity, uint32_t* count);
+SVX_API int32_t svx_octree_data_palette(const svx_octree* tree, uint32_t* out, uint32_t capacity, uint32_t* count);
 
 /* ---- MIP maps: Octree::albedo_mip_map_resampling_strategy() -> StrategyUpdater, src/octree/mod.rs:379,
  * src/octree/mipmap.rs:716-938. Every node owns one MIP brick (types.rs:186) holding a simplified view of its content;

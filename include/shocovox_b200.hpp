@@ -213,6 +213,21 @@ class Octree {
     uint32_t get_size() const { return svx_octree_size(h_); }
     void set_auto_simplify(bool v) { check(svx_octree_set_auto_simplify(h_, v ? 1 : 0)); }  // pub auto_simplify
     uint64_t structure_hash() const { return svx_octree_structure_hash(h_); }
+    // voxel_color_palette / voxel_data_palette (types.rs:191-192): albedo of a hit = color_palette()[hit_id & 0xFFFF]
+    std::vector<svx_albedo> color_palette() const {
+        uint32_t n = 0;
+        check(svx_octree_color_palette(h_, nullptr, 0, &n));
+        std::vector<svx_albedo> colors(n);
+        if (n) check(svx_octree_color_palette(h_, colors.data(), n, &n));
+        return colors;
+    }
+    std::vector<uint32_t> data_palette() const {
+        uint32_t n = 0;
+        check(svx_octree_data_palette(h_, nullptr, 0, &n));
+        std::vector<uint32_t> data(n);
+        if (n) check(svx_octree_data_palette(h_, data.data(), n, &n));
+        return data;
+    }
     // Host image of the uploaded node table, 16 u32 per node (svx_octree_render_data_nodes; OctreeRenderData, bevy/types.rs:216-279)
     std::vector<std::array<uint32_t, 16>> render_data_nodes() const {
         uint64_t n = 0;

@@ -139,7 +139,7 @@ EXPORTS = [
     "svx_version", "svx_last_error_message", "svx_cuda_device_count",
     "svx_octree_new", "svx_octree_free", "svx_octree_insert", "svx_octree_insert_at_lod", "svx_octree_update",
     "svx_octree_clear", "svx_octree_clear_at_lod", "svx_octree_insert_batch", "svx_octree_get", "svx_octree_get_sweep", "svx_octree_size", "svx_octree_brick_dim",
-    "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count", "svx_octree_render_data_nodes", "svx_octree_render_data_nodes_with_mips", "svx_octree_render_data_bricks", "svx_render_data_ray_lut",
+    "svx_octree_set_auto_simplify", "svx_octree_structure_hash", "svx_octree_node_count", "svx_octree_color_palette", "svx_octree_data_palette", "svx_octree_render_data_nodes", "svx_octree_render_data_nodes_with_mips", "svx_octree_render_data_bricks", "svx_render_data_ray_lut",
     "svx_octree_switch_albedo_mip_maps", "svx_octree_mip_maps_enabled", "svx_octree_recalculate_mips",
     "svx_octree_mip_set_method_at", "svx_octree_mip_get_method_at", "svx_octree_mip_set_color_similarity_thr_at",
     "svx_octree_mip_get_color_similarity_at", "svx_octree_mip_reset", "svx_octree_mip_sample_root", "svx_octree_mip_hash",
@@ -212,6 +212,8 @@ def lib() -> C.CDLL:
     L.svx_octree_structure_hash.restype = u64
     L.svx_octree_node_count.argtypes = [vp]
     L.svx_octree_node_count.restype = u64
+    L.svx_octree_color_palette.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.svx_octree_data_palette.argtypes = [vp, vp, u32, C.POINTER(u32)]
     f32 = C.c_float
     L.svx_octree_switch_albedo_mip_maps.argtypes = [vp, i32]
     L.svx_octree_mip_maps_enabled.argtypes = [vp]
@@ -499,6 +501,24 @@ class Octree:
 
     def node_count(self) -> int:
         return int(lib().svx_octree_node_count(self._h))
+
+    def color_palette(self) -> np.ndarray:
+        """voxel_color_palette (src/octree/types.rs:191) as [n][4] u8 (r, g, b, a): albedo of a hit is color_palette()[hit_id & 0xFFFF]"""
+        n = C.c_uint32(0)
+        _check(lib().svx_octree_color_palette(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), dtype=np.uint8)
+        if n.value:
+            _check(lib().svx_octree_color_palette(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def data_palette(self) -> np.ndarray:
+        """voxel_data_palette (src/octree/types.rs:192): user data of a hit is data_palette()[hit_id >> 16]"""
+        n = C.c_uint32(0)
+        _check(lib().svx_octree_data_palette(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            _check(lib().svx_octree_data_palette(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
 
     # ---- MIP maps: Octree::albedo_mip_map_resampling_strategy() (src/octree/mod.rs:379) ----
     def albedo_mip_map_resampling_strategy(self) -> "StrategyUpdater":

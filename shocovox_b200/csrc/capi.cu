@@ -818,6 +818,20 @@ int32_t svx_octree_set_auto_simplify(svx_octree* t, int32_t enabled) {
 }
 uint64_t svx_octree_structure_hash(const svx_octree* t) { return t ? t->tree->structure_hash() : 0; }
 uint64_t svx_octree_node_count(const svx_octree* t) { return t ? t->tree->nodes().size() : 0; }
+int32_t svx_octree_color_palette(const svx_octree* t, svx_albedo* out, uint32_t capacity, uint32_t* count) {
+    if (!t || !count || (!out && capacity != 0)) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    const std::vector<svx_albedo>& pal = t->tree->color_palette();
+    *count = (uint32_t)pal.size();
+    if (out) std::copy_n(pal.begin(), std::min<size_t>(capacity, pal.size()), out);
+    return SVX_OK;
+}
+int32_t svx_octree_data_palette(const svx_octree* t, uint32_t* out, uint32_t capacity, uint32_t* count) {
+    if (!t || !count || (!out && capacity != 0)) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    const std::vector<uint32_t>& pal = t->tree->data_palette();
+    *count = (uint32_t)pal.size();
+    if (out) std::copy_n(pal.begin(), std::min<size_t>(capacity, pal.size()), out);
+    return SVX_OK;
+}
 
 // ---- MIP maps: StrategyUpdater, src/octree/mipmap.rs:716-938
 int32_t svx_octree_switch_albedo_mip_maps(svx_octree* t, int32_t enabled) {

@@ -546,3 +546,35 @@ def test_shaded_plane_is_the_callers_pixel():
         ora = otree.render(oracle_camera(cam), 64, 48, light_normal=light, viewing_distance=80.0)
         view.render_to_host()
         assert np.array_equal(view.read_shaded(), ora["shaded"])
+
+
+@pytest.mark.parametrize("mips", [False, True], ids=["plain", "mips"])
+def test_albedo_plane_is_the_colour_palette_looked_up_by_hit_id(mips):
+    """svx_view_render_to_host(view, hit_id, NULL, distance) ships 8 bytes per pixel; the albedo plane it leaves out is
+    svx_octree_color_palette()[hit_id & 0xFFFF] (0 for a miss or a voxel without a colour) - checked against the plane the
+    three-plane call delivers, with MIP colours (which the box filter adds to the palette) too."""
+    import torch
+
+    scene = scenes.colonnade_scene()
+    tree = scenes.build_tree(scene, S.Octree)
+    tree.insert((3, 3, 3), None, 42)  # a voxel with user data and no colour
+    if mips:
+        tree.albedo_mip_map_resampling_strategy().switch_albedo_mip_maps(True)
+    host = S.OctreeGPUHost(tree)
+    w, h = 640, 360
+    view = host.create_new_view(1, viewport(scenes.colonnade_camera()), (w, h))
+    if mips:
+        view.set_viewing_distance(100.0)
+    full = view.render_to_host()
+    hit_id, dist = torch.empty(w * h, dtype=torch.int32).pin_memory(), torch.empty(w * h, dtype=torch.float32).pin_memory()
+    view.render_to_host_ptr(hit_id.data_ptr(), 0, dist.data_ptr())
+    ids = hit_id.numpy().view(np.uint32).reshape(h, w)
+    assert np.array_equal(ids, full["hit_id"]) and np.array_equal(bits(dist.numpy().reshape(h, w)), bits(full["distance"]))
+    colors = tree.color_palette()
+    packed = colors[:, 0].astype(np.uint32) | (colors[:, 1].astype(np.uint32) << 8) | (colors[:, 2].astype(np.uint32) << 16) | \
+        (colors[:, 3].astype(np.uint32) << 24)
+    index = ids & 0xFFFF
+    has_colour = (ids != 0xFFFFFFFF) & (index != 0xFFFF)
+    resolved = np.where(has_colour, packed[np.minimum(index, len(packed) - 1)], 0).astype(np.uint32)
+    assert has_colour.sum() > 10000 and len(np.unique(resolved)) > 3
+    assert np.array_equal(resolved, full["albedo"])

@@ -542,3 +542,23 @@ def test_random_inserts_and_clears_match_model(Tree, size, dim):
             model[p] = c
     for p in itertools.product(range(size), repeat=3):
         assert t.get(p) == (K(model[p]) if p in model else K()), p
+
+
+# voxel_color_palette / voxel_data_palette (src/octree/types.rs:191-192, add_to_palette in detail.rs): first-seen order,
+# no duplicates - what svx_octree_color_palette / svx_octree_data_palette hand out
+def test_palettes_are_readable_in_first_seen_order():
+    p, o = ProductOctree(16, 4), OracleOctree(16, 4)
+    for t in (p, o):
+        t.insert((0, 0, 0), RED)
+        t.insert((1, 0, 0), GREEN, 7)
+        t.insert((2, 0, 0), RED, 9)
+        t.insert((3, 0, 0), None, 7)
+        t.insert((4, 4, 4), BLUE)
+        t.insert((5, 5, 5), GREEN)
+    colors, data = p.tree.color_palette(), p.tree.data_palette()
+    assert colors.tolist() == [[255, 0, 0, 255], [0, 255, 0, 255], [0, 0, 255, 255]]
+    assert data.tolist() == [7, 9]
+    n_data = O.C.c_uint64(0)
+    assert O.lib().svxo_octree_palette_sizes(o._h, O.C.byref(n_data)) == len(colors) and n_data.value == len(data)
+    empty = ProductOctree(8, 2)
+    assert empty.tree.color_palette().shape == (0, 4) and empty.tree.data_palette().shape == (0,)
