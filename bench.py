@@ -535,7 +535,11 @@ def main() -> int:
 
     # ---- device-timed region: L2 flushed before every step, CUDA events around each step on its stream -----------------
     # tiles_fused: rank 0's event pair spans its viewport kernel (which publishes `go` to the peers) and the kernel that
-    # waits for every peer's rows, i.e. the complete frame; a peer's pair spans its own viewport kernel. Max over ranks.
+    # waits for every peer's rows, i.e. the complete frame - every peer's kernel runs inside that interval (it starts after
+    # `go`, the interval ends after its `done`), so rank 0's time IS the max over ranks. The peers are not timed in these
+    # steps: an event between a peer's go-wait and its viewport kernel sits on the frame's critical path
+    # (profiles/r02_graph_probe.json); their own kernel times come from a separate pass below (ms_per_step_per_rank).
+    untimed_peer = mode == "tiles_fused" and rank != 0
     for i in range(args.warmup):
         view.set_viewport(vps[pose_index(i)])
         view.flush_l2()
@@ -555,6 +559,9 @@ def main() -> int:
             view.render(sync=False)
             gather()
             dev_ms_total += view.timer_stop()
+        elif untimed_peer:
+            view.render(sync=False)
+            view.synchronize()
         else:
             dev_ms_total += view.render(sync=True)["kernel_ms"]
     wall1 = time.perf_counter()
@@ -668,7 +675,17 @@ def main() -> int:
 
     per_rank_ms = [dev_ms_total / args.steps]
     if dist is not None:
-        mine = torch.tensor([dev_ms_total / args.steps], dtype=torch.float64, device=f"cuda:{local_rank}")
+        mine_ms = dev_ms_total / args.steps
+        if mode == "tiles_fused":  # diagnostic pass: every member's own event pair (rank 0: the frame; a peer: its viewport kernel)
+            n_diag = min(args.steps, 20)
+            barrier()
+            mine_ms = 0.0
+            for i in range(n_diag):
+                view.set_viewport(vps[pose_index(i)])
+                view.flush_l2()
+                mine_ms += view.render(sync=True)["kernel_ms"] / n_diag
+            barrier()
+        mine = torch.tensor([mine_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
         per_rank_ms = [round(float(x.item()), 5) for x in every]

@@ -356,11 +356,13 @@ SVX_API int32_t svx_view_frame_pointers(const svx_view* view, void** hit_id, voi
  * side's next synchronising call return SVX_E_TIMEOUT instead of hanging the device.
  *
  * svx_view_gather_open : makes `root` rank 0 of a `world`-way gather and (out != NULL) fills the handle to ship to the
- *                        other processes. Idempotent for the same shape. The root must outlive its peers' membership.
+ *                        other processes. Idempotent for the same shape. The root must outlive the membership of peers in OTHER
+ *                        processes (they hold CUDA IPC mappings of its frame: close them first).
  * svx_view_gather_join : another process, `rank` in 1..world-1, same resolution as the root.
  * svx_view_gather_join_local : the same for a view of THIS process (any device with peer access to the root's, or the
  *                        root's own device), where CUDA IPC cannot be used.
  * svx_view_gather_close: leaves the gather (root or peer); the view renders whole frames into its own framebuffer again.
+ *                        Closing (or freeing) a root also takes its svx_view_gather_join_local peers out of the gather.
  * While a view is a member, set_resolution / set_shard / compact rows / the shaded plane / the pipelined read-back
  * are refused. */
 SVX_API int32_t svx_view_gather_open(svx_view* root, uint32_t world, uint32_t rows_per_band, int32_t wire /* svx_wire_format */,

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdint>
 #include <mutex>
+#include <vector>
 #include <shared_mutex>
 #include <string>
 
@@ -137,6 +138,10 @@ struct svx_view {
     size_t peer_plane_bytes = 0;
     bool peer_is_ipc = false;
     svx_view* local_root = nullptr;
+    // root: the peers of this process that store through this view's own pointers (svx_view_gather_join_local). Closing or
+    // freeing the root detaches them first, so none is left pointing into a freed frame. Guarded by multi_gpu.cu's
+    // membership mutex, not by `mu`.
+    std::vector<svx_view*> local_peers;
     uint32_t* d_cta_counter = nullptr;  // peer: retired CTAs of the launch in flight
     uint32_t* h_error = nullptr;        // host-mapped word the wait kernels write on a timeout (0 = fine)
     uint64_t gather_timeout_ns = 5000000000ull;
@@ -166,7 +171,8 @@ void octree_retain(const svx_octree* t);
 void octree_release(const svx_octree* t);
 void host_release(svx_gpu_host* h);
 int32_t validate_viewport(const svx_viewport& vp);
-int32_t render_locked(svx_view* v);       // one frame on the view's stream (gather roles included); v->mu held
+// one frame on the view's stream (gather roles included); v->mu held. timed: record ev_start / ev_stop around it
+int32_t render_locked(svx_view* v, bool timed);
 int32_t retire_locked(svx_view* v, uint32_t keep);
 int32_t check_view_error(svx_view* v);    // after a synchronise: did a gather wait give up?
 void invalidate_block_order(svx_view* v); // resolution / shard changed: the recorded block costs no longer apply

@@ -55,6 +55,29 @@ uint32_t tuning_from_env() {
     return t ? (uint32_t)std::strtoul(t, nullptr, 0) : 0u;
 }
 
+// Serialises joins and closes of in-process gathers (the root's local_peers list and the peers' local_root pointers);
+// taken before any view's own mutex. Render calls never take it.
+std::mutex& membership_mu() {
+    static std::mutex m;
+    return m;
+}
+
+// v->mu held (or v is being destroyed): back to a view that renders whole frames into its own framebuffer
+void leave_gather_locked(svx_view* v) {
+    cudaSetDevice(v->host->device);
+    if (v->stream) cudaStreamSynchronize(v->stream);
+    if (v->gather_role == GATHER_PEER && v->peer_is_ipc && v->peer_block) cudaIpcCloseMemHandle(v->peer_block);
+    v->peer_block = nullptr;
+    v->peer_is_ipc = false;
+    v->local_root = nullptr;
+    v->gather_role = GATHER_NONE;
+    v->rank = 0;
+    v->world = 1;
+    v->frame_seq = 0;
+    invalidate_block_order(v);
+    if (v->h_error) *v->h_error = 0u;
+}
+
 int32_t quiesce(svx_view* v) {
     CUDA_TRY(cudaSetDevice(v->host->device));
     const int32_t drained = retire_locked(v, 0);
@@ -165,6 +188,7 @@ int32_t svx_view_gather_join(svx_view* v, uint32_t rank, const svx_gather_handle
 
 int32_t svx_view_gather_join_local(svx_view* v, uint32_t rank, svx_view* root) {
     if (!v || !root || v == root) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> membership(membership_mu());
     std::lock_guard<std::mutex> lock_root(root->mu);
     std::lock_guard<std::mutex> lock(v->mu);
     if (root->gather_role != GATHER_ROOT) return fail(SVX_E_INVALID_ARGUMENT, "gather: open the root first (svx_view_gather_open)");
@@ -194,24 +218,30 @@ int32_t svx_view_gather_join_local(svx_view* v, uint32_t rank, svx_view* root) {
     v->local_root = root;
     v->gather_role = GATHER_PEER;
     root->gather_exports += 1;
+    root->local_peers.push_back(v);
     return SVX_OK;
 }
 
 int32_t svx_view_gather_close(svx_view* v) {
     if (!v) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
-    if (v->gather_role == GATHER_NONE) return SVX_OK;
-    cudaSetDevice(v->host->device);
-    if (v->stream) cudaStreamSynchronize(v->stream);
-    if (v->gather_role == GATHER_PEER && v->peer_is_ipc && v->peer_block) cudaIpcCloseMemHandle(v->peer_block);
-    v->peer_block = nullptr;
-    v->peer_is_ipc = false;
-    v->local_root = nullptr;
-    v->gather_role = GATHER_NONE;
-    v->rank = 0;
-    v->world = 1;
-    v->frame_seq = 0;
-    invalidate_block_order(v);
-    if (v->h_error) *v->h_error = 0u;
+    std::lock_guard<std::mutex> membership(membership_mu());
+    {
+        std::lock_guard<std::mutex> lock(v->mu);
+        if (v->gather_role == GATHER_NONE) return SVX_OK;
+        if (v->local_root) {  // a peer of a root in this process: the root forgets it
+            std::vector<svx_view*>& peers = v->local_root->local_peers;
+            peers.erase(std::remove(peers.begin(), peers.end(), v), peers.end());
+        }
+        leave_gather_locked(v);
+    }
+    // a root takes its in-process peers with it: they store through this view's own device pointers, which the caller
+    // may free next (peers in other processes hold CUDA IPC mappings and must be closed by their owners first)
+    std::vector<svx_view*> peers;
+    peers.swap(v->local_peers);
+    for (svx_view* p : peers) {
+        std::lock_guard<std::mutex> lock(p->mu);
+        leave_gather_locked(p);
+    }
     debug_stale("svx_view_gather_close: exit");
     return SVX_OK;
 }
@@ -374,7 +404,10 @@ int32_t svx_multi_render(svx_multi* m, svx_frame* out) {
     for (uint32_t k = 0; k < m->n; ++k) {
         svx_view* v = m->gather[m->n - 1 - k];
         int32_t s = svx_view_set_viewport(v, &m->viewport);
-        if (s == SVX_OK) s = svx_view_render(v, nullptr);
+        if (s != SVX_OK) return s;
+        std::lock_guard<std::mutex> view_lock(v->mu);
+        CUDA_TRY(cudaSetDevice(v->host->device));
+        s = render_locked(v, out != nullptr && k == m->n - 1);  // the root's event pair is the frame time reported below
         if (s != SVX_OK) return s;
     }
     if (!out) return SVX_OK;
@@ -410,7 +443,7 @@ int32_t svx_multi_render_to_host(svx_multi* m, uint32_t* hit_id, uint32_t* albed
         if (s != SVX_OK) return s;
         std::lock_guard<std::mutex> view_lock(v->mu);
         CUDA_TRY(cudaSetDevice(v->host->device));
-        s = render_locked(v);
+        s = render_locked(v, false);
         if (s == SVX_OK) s = copy_frame_to_host(v, v->stream, hit_id, albedo, distance);
         if (s != SVX_OK) return s;
     }

@@ -217,3 +217,42 @@ def test_handles_may_be_freed_in_any_order():
     assert L.svx_view_render_to_host(view, got["hit_id"].ctypes.data, got["albedo"].ctypes.data, got["distance"].ctypes.data) == 0
     assert_same_frame(got, want)
     L.svx_view_free(view)       # the last reference takes host and octree with it
+
+
+def test_a_root_that_goes_first_takes_its_in_process_peers_out_of_the_gather(tree):
+    """svx_view_gather_join_local peers store through the root view's own device pointers. Closing - or freeing - the root
+    before them detaches them (they render whole frames into their own framebuffers again) instead of leaving them
+    pointing into a freed frame. Raw C-ABI calls, so that no Python object keeps the root alive."""
+    import ctypes as C
+
+    L = S.lib()
+    cam = scenes.cpu_render_camera()
+    res = (200, 120)
+    want = whole_frames(tree, [cam], res)[0]
+    vp = viewport(cam)._c()
+    for how in ("close", "free"):
+        hosts, views = [C.c_void_p() for _ in range(3)], [C.c_void_p() for _ in range(3)]
+        for h, v in zip(hosts, views):
+            assert L.svx_gpu_host_create(tree._h, 0, C.byref(h)) == 0
+            assert L.svx_gpu_host_create_view(h, 1, C.byref(vp), res[0], res[1], C.byref(v)) == 0
+        assert L.svx_view_gather_open(views[0], 3, 8, S.WIRE_THREE_PLANES, None) == 0
+        for r in (1, 2):
+            assert L.svx_view_gather_join_local(views[r], r, views[0]) == 0
+        for r in (2, 1, 0):
+            assert L.svx_view_render(views[r], None) == 0
+        if how == "close":
+            assert L.svx_view_gather_close(views[0]) == 0
+        else:
+            L.svx_view_free(views[0])
+        role, rank, world, frames = C.c_int32(-1), C.c_uint32(9), C.c_uint32(9), C.c_uint32(9)
+        for r in (1, 2):
+            assert L.svx_view_gather_info(views[r], C.byref(role), C.byref(rank), C.byref(world), C.byref(frames)) == 0
+            assert (role.value, rank.value, world.value) == (0, 0, 1)
+            got = {"hit_id": np.empty(res[::-1], np.uint32), "albedo": np.empty(res[::-1], np.uint32), "distance": np.empty(res[::-1], np.float32)}
+            assert L.svx_view_render_to_host(views[r], got["hit_id"].ctypes.data, got["albedo"].ctypes.data, got["distance"].ctypes.data) == 0
+            assert_same_frame(got, want, f"{how}: former peer {r}")
+            assert L.svx_view_gather_close(views[r]) == 0  # closing twice is fine
+        for r in ((0, 1, 2) if how == "close" else (1, 2)):
+            L.svx_view_free(views[r])
+        for h in hosts:
+            L.svx_gpu_host_free(h)
