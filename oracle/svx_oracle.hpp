@@ -219,6 +219,10 @@ class Octree {
     Entry pix_get_ref(uint32_t index) const;
     uint64_t structure_hash() const;  // key-order independent hash of the reachable tree
     uint64_t mip_hash() const;        // the same for the MIP strategy and the MIP bricks of the reachable nodes
+    // BrickData::is_empty_throughout / is_part_empty_throughout (node.rs:107-241); public for the reference's
+    // brick_tests (src/octree/tests.rs:8-151)
+    bool brick_is_empty_throughout(const Brick& b, uint8_t octant) const;
+    bool brick_is_part_empty_throughout(const Brick& b, uint8_t part_octant, uint8_t target_octant) const;
 
    private:
     Status insert_at_lod_internal(bool overwrite_if_empty, V3u position, uint32_t insert_size, const Entry& data);
@@ -237,8 +241,6 @@ class Octree {
     bool node_is_empty(const Node& n) const;
     bool node_empty_at(size_t node_key, uint8_t target_octant) const;
     bool should_bitmap_be_empty_at_bitmap_index(size_t node_key, size_t x, size_t y, size_t z) const;
-    bool brick_is_empty_throughout(const Brick& b, uint8_t octant) const;
-    bool brick_is_part_empty_throughout(const Brick& b, uint8_t part_octant, uint8_t target_octant) const;
     uint64_t hash_node(size_t key) const;
     Entry get_internal(size_t node_key, Cube bounds, V3u position) const;  // mod.rs:220-371
     void ensure_mips() { if (node_mips.size() < nodes.len()) node_mips.resize(nodes.len()); }  // insert.rs:168, detail.rs:356

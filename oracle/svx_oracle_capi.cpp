@@ -405,6 +405,15 @@ void svxo_dda_scale_factors(const float direction[3], float out[3]) {
     V3f s = get_dda_scale_factors(Ray{{0, 0, 0}, {direction[0], direction[1], direction[2]}});
     out[0] = s.x; out[1] = s.y; out[2] = s.z;
 }
+// Octree::dda_step_to_next_sibling (raytracing_on_cpu.rs:124-152): advances `point` in place, writes the +-1 / 0 step
+void svxo_dda_step_to_next_sibling(const float origin[3], const float direction[3], float point[3], const float min_pos[3],
+                                   float size, float step_out[3]) {
+    const Ray ray{{origin[0], origin[1], origin[2]}, {direction[0], direction[1], direction[2]}};
+    V3f p{point[0], point[1], point[2]};
+    const V3f step = dda_step_to_next_sibling(ray, p, Cube{{min_pos[0], min_pos[1], min_pos[2]}, size}, get_dda_scale_factors(ray));
+    point[0] = p.x; point[1] = p.y; point[2] = p.z;
+    step_out[0] = step.x; step_out[1] = step.y; step_out[2] = step.z;
+}
 void svxo_normalized(const float v[3], float out[3]) {
     const float len = std::sqrt((v[0] * v[0]) + (v[1] * v[1]) + (v[2] * v[2]));
     out[0] = v[0] / len; out[1] = v[1] / len; out[2] = v[2] / len;
@@ -426,6 +435,63 @@ void svxo_luts(uint64_t* mask, uint32_t* index, uint32_t* step, uint64_t* ray2no
         offsets[3 * o + 1] = l.octant_offset[o].y;
         offsets[3 * o + 2] = l.octant_offset[o].z;
     }
+}
+
+// ObjectPool KAT driver (src/object_pool.rs:243-285). ops[i] = {code, arg}: 0 push(arg) -> key; 1 pop(arg) -> the
+// item, or INT64_MIN for None; 2 free(arg) -> 0 / 1; 3 get(arg) -> the item; 4 get_mut(arg.lo) = arg.hi -> 0;
+// 5 first_available; 6 len; 7 key_is_valid(arg). Items are the Internal(u64) payload of a pooled node; `pop` is
+// `free` + take (object_pool.rs:204-222).
+void svxo_node_pool_script(const int64_t* ops, uint32_t n, int64_t* out) {
+    NodePool pool;
+    for (uint32_t i = 0; i < n; ++i) {
+        const int64_t code = ops[2 * i], arg = ops[2 * i + 1];
+        out[i] = INT64_MIN;
+        switch (code) {
+            case 0: {
+                Node node;
+                node.kind = NodeKind::Internal;
+                node.occupied_bits = (uint64_t)arg;
+                out[i] = (int64_t)pool.push(std::move(node));
+                break;
+            }
+            case 1:
+                if (pool.key_is_valid((size_t)arg)) {
+                    out[i] = (int64_t)pool.item[(size_t)arg].occupied_bits;
+                    pool.free_key((size_t)arg);
+                    pool.item[(size_t)arg] = Node();  // std::mem::take
+                }
+                break;
+            case 2: out[i] = pool.free_key((size_t)arg) ? 1 : 0; break;
+            case 3: out[i] = (int64_t)pool.item[(size_t)arg].occupied_bits; break;
+            case 4:
+                pool.item[(size_t)(arg & 0xFFFFFFFF)].occupied_bits = (uint64_t)(arg >> 32);
+                out[i] = 0;
+                break;
+            case 5: out[i] = (int64_t)pool.first_available; break;
+            case 6: out[i] = (int64_t)pool.len(); break;
+            case 7: out[i] = pool.key_is_valid((size_t)arg) ? 1 : 0; break;
+        }
+    }
+}
+
+// BrickData::is_empty_throughout (node.rs:107-178; part_octant < 0) / is_part_empty_throughout (:184-241) on a brick
+// given as kind (0 Empty, 1 Parted, 2 Solid) + voxels, against the given palettes (colours as 0xRRGGBBAA).
+int32_t svxo_brick_is_empty_throughout(uint32_t brick_dim, uint32_t kind, const uint32_t* voxels, uint32_t n_voxels,
+                                       int32_t part_octant, uint32_t target_octant, const uint32_t* colors, uint32_t n_colors,
+                                       const uint32_t* datas, uint32_t n_datas) {
+    Octree* t = nullptr;
+    if (Octree::create(brick_dim * 2, brick_dim, &t) != OK) return -1;
+    for (uint32_t i = 0; i < n_colors; ++i)
+        t->voxel_color_palette.push_back(Albedo{(uint8_t)(colors[i] >> 24), (uint8_t)(colors[i] >> 16), (uint8_t)(colors[i] >> 8), (uint8_t)colors[i]});
+    t->voxel_data_palette.assign(datas, datas + n_datas);
+    Brick b;
+    b.kind = (BrickKind)kind;
+    if (b.kind == BrickKind::Solid) b.solid = voxels[0];
+    if (b.kind == BrickKind::Parted) b.data.assign(voxels, voxels + n_voxels);
+    const bool empty = part_octant < 0 ? t->brick_is_empty_throughout(b, (uint8_t)target_octant)
+                                       : t->brick_is_part_empty_throughout(b, (uint8_t)part_octant, (uint8_t)target_octant);
+    delete t;
+    return empty ? 1 : 0;
 }
 
 void svxo_node_stack_script(uint32_t size, const int32_t* ops, uint32_t n, int32_t* out) {

@@ -182,8 +182,12 @@ def lib() -> C.CDLL:
     L.svxo_cube_impact_normal.argtypes = [f3, f32, f3, f3]
     L.svxo_dda_scale_factors.argtypes = [f3, f3]
     L.svxo_normalized.argtypes = [f3, f3]
+    L.svxo_dda_step_to_next_sibling.argtypes = [f3, f3, f3, f3, f32, f3]
     L.svxo_luts.argtypes = [vp, vp, vp, vp, vp]
     L.svxo_node_stack_script.argtypes = [u32, vp, u32, vp]
+    L.svxo_node_pool_script.argtypes = [vp, u32, vp]
+    L.svxo_brick_is_empty_throughout.argtypes = [u32, u32, vp, u32, i32, u32, vp, u32, vp, u32]
+    L.svxo_brick_is_empty_throughout.restype = i32
     _lib = L
     return L
 
