@@ -883,13 +883,11 @@ uint64_t svx_octree_mip_hash(const svx_octree* t) { return t ? t->tree->mip_hash
 
 int32_t svx_octree_to_bytes(const svx_octree* t, uint8_t** bytes, uint64_t* len) {
     if (!t || !bytes || !len) return fail(SVX_E_INVALID_ARGUMENT, "null argument");
-    std::string s;
-    t->tree->to_bytes(&s);
-    uint8_t* buf = (uint8_t*)std::malloc(s.size() ? s.size() : 1);
+    size_t n = 0;
+    uint8_t* buf = t->tree->to_bytes(&n);  // malloc'd by the encoder: handed out as it is, freed by svx_bytes_free
     if (!buf) return fail(SVX_E_OUT_OF_MEMORY, "allocation failed");
-    std::memcpy(buf, s.data(), s.size());
     *bytes = buf;
-    *len = s.size();
+    *len = n;
     return SVX_OK;
 }
 void svx_bytes_free(uint8_t* bytes) { std::free(bytes); }

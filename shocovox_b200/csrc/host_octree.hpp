@@ -85,7 +85,7 @@ class HostOctree {
     void mip_load_strategy(bool enabled, std::map<size_t, MipSampler> methods, std::map<size_t, float> thresholds);
     void mip_load_brick(size_t key, uint8_t kind, uint32_t solid, const uint32_t* voxels);
     // bencode persistence in the reference's byte format (host_octree_io.cpp; src/octree/mod.rs:138-168)
-    void to_bytes(std::string* out) const;
+    uint8_t* to_bytes(size_t* len) const;  // malloc'd, the caller frees it with std::free; null = out of memory
     static int32_t from_bytes(const uint8_t* data, size_t len, HostOctree** out);
     int32_t save(const char* path) const;
     static int32_t load(const char* path, HostOctree** out);

@@ -23,8 +23,11 @@
 // by level.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <new>
 #include <string>
 #include <utility>
 #include <vector>
@@ -35,27 +38,126 @@ namespace svx {
 
 namespace {
 
+// Appends through a raw cursor into a malloc'd buffer (grown with realloc, handed to the caller as it is), head-room
+// checked once per item. The voxel runs of Parted bricks are > 99 % of a file at ~12 bytes per voxel, and they repeat a
+// handful of palette values: a small direct-mapped cache keeps the formatted text of the values seen last.
 struct Writer {
-    std::string& s;
+    char* base = nullptr;
+    char* cur = nullptr;
+    char* lim = nullptr;
+    bool failed = false;
+    struct Slot {
+        uint32_t value;
+        uint32_t len;  // 0 = never filled
+        char text[16];
+    };
+    Slot cache[1024];
+
+    Writer() {
+        for (Slot& c : cache) c.value = c.len = 0u;
+    }
+    ~Writer() { std::free(base); }
+    // the finished buffer (never null on success; the caller frees it with std::free)
+    uint8_t* release(size_t* len) {
+        if (failed) return nullptr;
+        need(1);
+        if (failed) return nullptr;
+        *len = (size_t)(cur - base);
+        uint8_t* out = (uint8_t*)base;
+        base = cur = lim = nullptr;
+        return out;
+    }
+    bool need(size_t n) {
+        if ((size_t)(lim - cur) >= n && base) return true;
+        if (failed) return false;
+        const size_t used = (size_t)(cur - base), cap = std::max(used + n, used + used / 2 + (size_t)65536);
+        char* grown = (char*)std::realloc(base, cap);
+        if (!grown) {
+            failed = true;  // everything after this point is dropped; release() reports it
+            return false;
+        }
+        base = grown;
+        cur = grown + used;
+        lim = grown + cap;
+        return true;
+    }
+    static const char* pairs() {
+        return "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+               "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+    }
+    // "i<v>e" into out[0..16): ten zero-padded digits, then the 'i' goes over the last padding zero
+    static uint32_t format_u32(uint32_t v, char* out) {
+        const char* P = pairs();
+        char buf[28];
+        const uint32_t hi = v / 100000000u, rest = v - hi * 100000000u, mid = rest / 10000u, lo = rest - mid * 10000u;
+        std::memcpy(buf + 1, P + 2 * hi, 2);
+        std::memcpy(buf + 3, P + 2 * (mid / 100u), 2);
+        std::memcpy(buf + 5, P + 2 * (mid % 100u), 2);
+        std::memcpy(buf + 7, P + 2 * (lo / 100u), 2);
+        std::memcpy(buf + 9, P + 2 * (lo % 100u), 2);
+        buf[11] = 'e';
+        const uint32_t nd = 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+                            (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+        char* b = buf + 10 - nd;
+        *b = 'i';
+        std::memcpy(out, b, 16);  // nd + 2 <= 12 bytes are meaningful
+        return nd + 2u;
+    }
     void integer(uint64_t v) {
-        char buf[24];
-        int n = 0;
-        do {
-            buf[n++] = (char)('0' + v % 10);
-            v /= 10;
-        } while (v);
-        s.push_back('i');
-        while (n) s.push_back(buf[--n]);
-        s.push_back('e');
+        if (!need(24)) return;
+        if (v <= 0xFFFFFFFFull) {
+            cur += format_u32((uint32_t)v, cur);
+            return;
+        }
+        char buf[20];
+        char* e = buf + 20;
+        char* b = e;
+        while (v >= 100) {
+            const unsigned r = (unsigned)(v % 100);
+            v /= 100;
+            b -= 2;
+            std::memcpy(b, pairs() + 2 * r, 2);
+        }
+        if (v >= 10) {
+            b -= 2;
+            std::memcpy(b, pairs() + 2 * v, 2);
+        } else {
+            *--b = (char)('0' + v);
+        }
+        *cur++ = 'i';
+        std::memcpy(cur, b, (size_t)(e - b));
+        cur += e - b;
+        *cur++ = 'e';
+    }
+    void integers(const uint32_t* v, size_t n) {  // i<v0>e i<v1>e ...: at most 12 bytes each
+        if (!need(n * 12 + 16)) return;
+        for (size_t k = 0; k < n; ++k) {
+            const uint32_t x = v[k];
+            Slot& c = cache[(x ^ ((x >> 16) * 0x9E3779B1u)) & 1023u];
+            if (c.value != x || c.len == 0u) {
+                c.value = x;
+                c.len = format_u32(x, c.text);
+            }
+            std::memcpy(cur, c.text, 16);
+            cur += c.len;
+        }
     }
     void str(const char* lit) {
         const size_t n = std::strlen(lit);
-        s.append(std::to_string(n));
-        s.push_back(':');
-        s.append(lit, n);
+        if (!need(n + 24)) return;
+        const uint32_t d = format_u32((uint32_t)n, cur);  // "i<n>e" -> "<n>:"
+        std::memmove(cur, cur + 1, d - 2);
+        cur += d - 2;
+        *cur++ = ':';
+        std::memcpy(cur, lit, n);
+        cur += n;
     }
-    void open() { s.push_back('l'); }
-    void close() { s.push_back('e'); }
+    void open() {
+        if (need(1)) *cur++ = 'l';
+    }
+    void close() {
+        if (need(1)) *cur++ = 'e';
+    }
 };
 
 struct Reader {
@@ -83,18 +185,24 @@ struct Reader {
     }
     bool integer(uint64_t* out) {
         if (!peek_int()) return fail();
-        ++p;
+        const uint8_t* first = p + 1;
+        const uint8_t* q = first;
         uint64_t v = 0;
-        bool any = false;
-        while (p < end && *p >= '0' && *p <= '9') {
-            const uint64_t d = (uint64_t)(*p - '0');
-            if (v > (UINT64_MAX - d) / 10) return fail();
-            v = v * 10 + d;
-            ++p;
-            any = true;
+        while (q < end && (unsigned)(*q - '0') <= 9u) {  // up to 19 digits cannot overflow; longer ones are re-read below
+            v = v * 10 + (uint64_t)(*q - '0');
+            ++q;
         }
-        if (!any || p >= end || *p != 'e') return fail();  // no negative numbers anywhere in the format
-        ++p;
+        const size_t digits = (size_t)(q - first);
+        if (digits == 0 || q >= end || *q != 'e') return fail();  // no negative numbers anywhere in the format
+        if (digits > 19) {
+            v = 0;
+            for (const uint8_t* c = first; c < q; ++c) {
+                const uint64_t d = (uint64_t)(*c - '0');
+                if (v > (UINT64_MAX - d) / 10) return fail();
+                v = v * 10 + d;
+            }
+        }
+        p = q + 1;
         *out = v;
         return true;
     }
@@ -146,9 +254,10 @@ bool is_marker(const char* s, size_t n, const char* lit) { return n == std::strl
 }  // namespace
 
 // ---- encode ---------------------------------------------------------------------------------------------------
-void HostOctree::to_bytes(std::string* out) const {
-    out->clear();
-    Writer w{*out};
+uint8_t* HostOctree::to_bytes(size_t* len) const {
+    std::unique_ptr<Writer> writer(new (std::nothrow) Writer());  // 24 KB of cache: not on the stack
+    if (!writer) return nullptr;
+    Writer& w = *writer;
     auto brick = [&](const BrickRef& b) {  // bytecode.rs:67-91
         if (b.kind == BK_EMPTY) {
             w.str("#b");
@@ -162,7 +271,7 @@ void HostOctree::to_bytes(std::string* out) const {
             w.open();
             w.str("##b#");
             w.integer(vol_);
-            for (uint32_t i = 0; i < vol_; ++i) w.integer(v[i]);
+            w.integers(v, vol_);
             w.str("#");
             w.close();
         }
@@ -262,6 +371,7 @@ void HostOctree::to_bytes(std::string* out) const {
     }
     w.close();
     w.close();
+    return w.release(len);
 }
 
 // ---- decode ---------------------------------------------------------------------------------------------------
@@ -501,11 +611,16 @@ int32_t HostOctree::from_bytes(const uint8_t* data, size_t len, HostOctree** out
 }
 
 int32_t HostOctree::save(const char* path) const {  // octree/mod.rs:144-150
-    std::string bytes;
-    to_bytes(&bytes);
+    size_t len = 0;
+    uint8_t* bytes = to_bytes(&len);
+    if (!bytes) return SVX_E_OUT_OF_MEMORY;
     std::FILE* f = std::fopen(path, "wb");
-    if (!f) return SVX_E_IO;
-    const bool ok = std::fwrite(bytes.data(), 1, bytes.size(), f) == bytes.size();
+    if (!f) {
+        std::free(bytes);
+        return SVX_E_IO;
+    }
+    const bool ok = std::fwrite(bytes, 1, len, f) == len;
+    std::free(bytes);
     return (std::fclose(f) == 0 && ok) ? SVX_OK : SVX_E_IO;
 }
 

@@ -354,6 +354,25 @@ def test_product_and_oracle_write_identical_bytes_and_read_each_other(scene):
     assert np.array_equal(a, b)
 
 
+def test_integers_of_every_length_are_written_like_the_oracle_writes_them():
+    """The product's encoder formats integers itself (two-digit table, a cache of recent values): user data of 1 to
+    10 digits at every power-of-ten boundary, enough distinct values to evict cache slots, repeated values, and 64-bit
+    occupancy masks must come out exactly as the oracle's `std::to_string` writes them."""
+    values = sorted({10 ** k + d for k in range(10) for d in (-1, 0, 1) if 0 < 10 ** k + d < 2 ** 32 - 1} | {1, 7, 42, 65535, 65536, 2 ** 31, 2 ** 32 - 2})
+    rng = np.random.default_rng(11)
+    values += [int(v) for v in rng.integers(1, 2 ** 32 - 1, 3000)]
+    prod, ora = S.Octree(64, 4), OracleOctree(64, 4)
+    pos = [(x, y, z) for x in range(0, 64, 2) for y in range(0, 64, 8) for z in range(0, 64, 4)]
+    for (x, y, z), v in zip(pos, values):
+        color = (x * 4 % 256, y * 4 % 256, (v % 251) + 1, 255) if v % 3 else None
+        for t in (prod, ora):
+            t.insert((x, y, z), color, v)
+            t.insert((x + 1, y, z), color, values[(v * 7) % 40])   # repeats of a few values
+    bp, bo = prod.to_bytes(), ora.to_bytes()
+    assert bp == canonical(bo)
+    assert S.Octree.from_bytes(bp).to_bytes() == bp and OracleOctree.from_bytes(bp).to_bytes() == bp
+
+
 def test_loaded_trees_keep_building_like_the_original():
     """ObjectPool state (reserved flags, first_available) and the palette lookup maps survive the round trip: the same
     edits applied to the original and to the loaded copy give identical bytes (i.e. identical node keys too)."""
