@@ -103,12 +103,19 @@ struct VoxFile {
     std::vector<svx_albedo> palette;
 };
 
+// `str::parse::<i32>()`: an optional sign, then digits only (no white space), and the value must fit an i32
 bool parse_int(const std::string& s, long* out) {
-    if (s.empty()) return false;
-    char* end = nullptr;
-    const long v = std::strtol(s.c_str(), &end, 10);
-    if (*end != '\0') return false;
-    *out = v;
+    size_t i = (!s.empty() && (s[0] == '-' || s[0] == '+')) ? 1 : 0;
+    if (i == s.size()) return false;
+    int64_t v = 0;
+    for (; i < s.size(); ++i) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        v = v * 10 + (s[i] - '0');
+        if (v > (int64_t)INT32_MAX + 1) return false;
+    }
+    if (s[0] == '-') v = -v;
+    if (v > INT32_MAX) return false;
+    *out = (long)v;
     return true;
 }
 
@@ -261,22 +268,27 @@ int32_t place_models(const VoxFile& f, std::vector<Placed>* out, std::string* wh
             const auto& fr = node.frames[frame < node.frames.size() ? frame : 0];
             Vec3i t = top.t;
             auto it = fr.find("_t");
-            if (it != fr.end()) {  // `translation + t.split(" ")...` (:139-147)
+            if (it != fr.end()) {
+                // `translation + t.split(" ").map(|x| x.parse().expect(..)).collect::<Vec<i32>>().into()` (:136-141): EVERY
+                // part must be an integer, the first three are used (vector.rs:366-371)
                 long v[3] = {0, 0, 0};
+                const std::string& s = it->second;
                 size_t a = 0;
                 int k = 0;
-                const std::string& s = it->second;
-                while (k < 3 && a <= s.size()) {
+                for (;;) {
                     const size_t b = std::min(s.find(' ', a), s.size());
-                    if (!parse_int(s.substr(a, b - a), &v[k])) {
-                        *why = "translation is not three integers";
+                    long part = 0;
+                    if (!parse_int(s.substr(a, b - a), &part)) {
+                        *why = "translation: a part is not an integer";
                         return SVX_E_DECODE;
                     }
+                    if (k < 3) v[k] = part;
                     ++k;
+                    if (b == s.size()) break;
                     a = b + 1;
                 }
-                if (k != 3) {
-                    *why = "translation is not three integers";
+                if (k < 3) {
+                    *why = "translation has fewer than three parts";
                     return SVX_E_DECODE;
                 }
                 t = {t.x + v[0], t.y + v[1], t.z + v[2]};

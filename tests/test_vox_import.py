@@ -145,3 +145,32 @@ def test_load_vox_file_with_a_mip_strategy_updates_mips_while_inserting():
     plain = S.Octree.load_vox_file(blob, 4)
     assert not plain.albedo_mip_map_resampling_strategy().is_enabled()
     assert plain.get_sweep((0, 0, 0), (8, 8, 8)).tobytes() == tree.get_sweep((0, 0, 0), (8, 8, 8)).tobytes()
+
+
+def test_scene_graph_numbers_are_parsed_as_rust_parses_them():
+    """`_t` / `_r` / `_f` go through `str::parse::<i32>()` / `<u8>()` with `unwrap()` in the reference (magicavoxel.rs:139-157):
+    anything but an optional sign and digits is a panic there and a decode error here - never a guess. A file whose text
+    is patched in place (same length, so the chunk sizes stay valid) must load when the number is still a number and be
+    refused otherwise."""
+    size, v = _model(5, 8)
+    pal = np.random.default_rng(6).integers(1, 256, (256, 4)).astype(np.uint8)
+    blob = vox.write_vox([(size, v), (size, v)], palette=pal, placements=[((0, 0, 0), None), ((120, -30, 700), None)])
+    text = b"120 -30 700"
+    assert blob.count(text) == 1
+    good = S.Octree.load_vox_file(blob, 4)
+    for patched, ok in [(b"+20 -30 700", True), (b"120 -30 70 ", False), (b" 20 -30 700", False), (b"120 -3x 700", False),
+                        (b"120  30 700", False), (b"120 -30 7e2", False), (b"120,-30,700", False),
+                        (b"1 2 3 4 500", True), (b"120 -30700 ", False), (b"120 -307000", False)]:
+        data = blob.replace(text, patched)
+        assert len(data) == len(blob)
+        if ok:
+            assert S.Octree.load_vox_file(data, 4).get_size() >= 8
+        else:
+            with pytest.raises(S.OctreeError) as e:
+                S.Octree.load_vox_file(data, 4)
+            assert e.value.code == S.api.E_DECODE
+    assert good.get_size() == 1024
+    # a number beyond i32 is refused as well (strtol would have saturated it)
+    blob = vox.write_vox([(size, v), (size, v)], palette=pal, placements=[((0, 0, 0), None), ((99999999999, 0, 0), None)])
+    with pytest.raises(S.OctreeError):
+        S.Octree.load_vox_file(blob, 4)
