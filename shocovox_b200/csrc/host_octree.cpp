@@ -497,9 +497,10 @@ size_t HostOctree::update_brick(bool overwrite, uint32_t* brick, const BoundsF& 
     matrix_index(b, x, y, z, dim_, mi);
     const size_t update_size = std::min<size_t>((size_t)dim_ - mi[0], size);
     const bool color_some = (data & 0xFFFFu) < NONE16, data_some = (data >> 16) != NONE16;
-    for (size_t ix = mi[0]; ix < std::min<size_t>(mi[0] + size, dim_); ++ix)
+    // the same box of voxels as the reference's x / y / z loops (update/mod.rs:637-675), walked in memory order (x fastest)
+    for (size_t iz = mi[2]; iz < std::min<size_t>(mi[2] + size, dim_); ++iz)
         for (size_t iy = mi[1]; iy < std::min<size_t>(mi[1] + size, dim_); ++iy)
-            for (size_t iz = mi[2]; iz < std::min<size_t>(mi[2] + size, dim_); ++iz) {
+            for (size_t ix = mi[0]; ix < std::min<size_t>(mi[0] + size, dim_); ++ix) {
                 uint32_t& v = brick[flat(ix, iy, iz, dim_)];
                 if (overwrite) {
                     v = data;
