@@ -827,6 +827,52 @@ static size_t update_brick(bool overwrite_if_empty, std::vector<uint32_t>& brick
     return update_size;
 }
 
+// ---- the block cache of Voxels (svx_oracle.hpp) ----
+static bool block_is_mixed(const std::vector<uint32_t>& v, size_t bx, size_t by, size_t bz, size_t d) {
+    const uint32_t v0 = v[flat_projection(bx * 2, by * 2, bz * 2, d)];
+    for (size_t c = 1; c < 8; ++c)
+        if (v[flat_projection(bx * 2 + (c & 1), by * 2 + ((c >> 1) & 1), bz * 2 + (c >> 2), d)] != v0) return true;
+    return false;
+}
+static void rebuild_blocks(const Voxels& v, size_t d) {
+    const size_t half = d / 2, blocks = half * half * half;
+    v.mixed_blocks.assign((blocks + 63) / 64 + 1, 0ull);
+    uint32_t count = 0;
+    for (size_t bz = 0; bz < half; ++bz)
+        for (size_t by = 0; by < half; ++by)
+            for (size_t bx = 0; bx < half; ++bx)
+                if (block_is_mixed(v, bx, by, bz, d)) {
+                    const size_t i = (bz * half + by) * half + bx;
+                    v.mixed_blocks[i >> 6] |= 1ull << (i & 63);
+                    ++count;
+                }
+    v.mixed_count = count;
+}
+// An in-place edit of a brick that lives in the tree: the literal update above, then the blocks the written box touches are
+// looked at again. (Overload resolution picks this one for every Voxels argument, so a tree brick cannot be edited past it.)
+static size_t update_brick(bool overwrite_if_empty, Voxels& brick, const Cube& brick_bounds, uint32_t brick_dim, V3u position,
+                           uint32_t size, uint32_t data) {
+    const size_t us = update_brick(overwrite_if_empty, static_cast<std::vector<uint32_t>&>(brick), brick_bounds, brick_dim, position,
+                                   size, data);
+    const size_t d = brick_dim, half = d / 2;
+    if (brick.mixed_count == Voxels::UNKNOWN || half == 0) return us;
+    const V3s mi = matrix_index_for(brick_bounds, position, brick_dim);
+    const size_t hx = std::min(mi.x + size, d), hy = std::min(mi.y + size, d), hz = std::min(mi.z + size, d);
+    if (mi.x >= hx || mi.y >= hy || mi.z >= hz) return us;
+    for (size_t bz = mi.z / 2; bz <= (hz - 1) / 2; ++bz)
+        for (size_t by = mi.y / 2; by <= (hy - 1) / 2; ++by)
+            for (size_t bx = mi.x / 2; bx <= (hx - 1) / 2; ++bx) {
+                const size_t i = (bz * half + by) * half + bx;
+                const uint64_t bit = 1ull << (i & 63);
+                const bool was = (brick.mixed_blocks[i >> 6] & bit) != 0, now = block_is_mixed(brick, bx, by, bz, d);
+                if (was != now) {
+                    brick.mixed_blocks[i >> 6] ^= bit;
+                    brick.mixed_count += now ? 1u : 0xFFFFFFFFu;
+                }
+            }
+    return us;
+}
+
 // update/mod.rs:160-549
 size_t Octree::leaf_update(bool overwrite_if_empty, size_t node_key, const Cube& node_bounds, const Cube& target_bounds,
                            size_t target_child_octant, V3u position, uint32_t size, uint32_t target_content) {
@@ -1029,31 +1075,12 @@ bool Octree::simplify(size_t node_key) {
                     is_leaf_uniform &= (b == node.bricks[0]);
                     continue;
                 }
-                auto block_uniform = [&](size_t x, size_t y, size_t z) {
-                    const uint32_t v0 = b.data[flat_projection(x * 2, y * 2, z * 2, d)];
-                    return v0 == b.data[flat_projection(x * 2 + 1, y * 2, z * 2, d)] &&
-                           v0 == b.data[flat_projection(x * 2, y * 2 + 1, z * 2, d)] &&
-                           v0 == b.data[flat_projection(x * 2, y * 2, z * 2 + 1, d)] &&
-                           v0 == b.data[flat_projection(x * 2 + 1, y * 2 + 1, z * 2, d)] &&
-                           v0 == b.data[flat_projection(x * 2, y * 2 + 1, z * 2 + 1, d)] &&
-                           v0 == b.data[flat_projection(x * 2 + 1, y * 2, z * 2 + 1, d)] &&
-                           v0 == b.data[flat_projection(x * 2 + 1, y * 2 + 1, z * 2 + 1, d)];
-                };
-                if (b.witness2 != 0xFFFFFFFFu && brick_half > 0) {
-                    const size_t w = b.witness2;
-                    if (!block_uniform(w % brick_half, (w / brick_half) % brick_half, w / (brick_half * brick_half))) {
-                        is_leaf_uniform = false;
-                        break;
-                    }
+                // "every aligned 2x2x2 block of the brick is one value" (the reference scans the brick, :884-980), from the
+                // brick's block cache
+                if (brick_half > 0) {
+                    if (b.data.mixed_count == Voxels::UNKNOWN) rebuild_blocks(b.data, d);
+                    if (b.data.mixed_count != 0) is_leaf_uniform = false;
                 }
-                b.witness2 = 0xFFFFFFFFu;
-                for (size_t x = 0; x < brick_half && is_leaf_uniform; ++x)
-                    for (size_t y = 0; y < brick_half && is_leaf_uniform; ++y)
-                        for (size_t z = 0; z < brick_half && is_leaf_uniform; ++z)
-                            if (!block_uniform(x, y, z)) {
-                                b.witness2 = (uint32_t)(x + y * brick_half + z * brick_half * brick_half);
-                                is_leaf_uniform = false;
-                            }
             }
             if (is_leaf_uniform) {
                 std::vector<uint32_t> unified(d * d * d, EMPTY_MARKER_U32);
@@ -1840,7 +1867,7 @@ void Octree::update_mip(size_t node_key, const Cube& node_bounds, V3u position) 
         case BrickKind::Parted: break;
     }
     mip.witness = 0;
-    mip.witness2 = 0xFFFFFFFFu;
+    mip.data.forget();  // written in place below
     if (flat < mip.data.size()) mip.data[flat] = mip_entry;
 }
 

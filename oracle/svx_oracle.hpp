@@ -47,16 +47,57 @@ struct Ray {
     V3f direction;
 };
 
+// The voxels of a Parted brick: a std::vector<uint32_t> (dim^3, x fastest) that also carries a BUILD-TIME cache which never
+// changes a result: which aligned 2x2x2 blocks hold more than one value, and how many do. Octree::simplify asks "is every
+// block one value?" after every insert that ends in a leaf (update/mod.rs:884-980); answering it with the reference's scan
+// was 77 % of the oracle's tree-build time on the 32^3-brick scenes. The cache is built by the first question and kept exact
+// by the one in-place writer (the update_brick overload for Voxels, svx_oracle.cpp); assigning whole contents forgets it,
+// copying a Voxels copies it along with the voxels it describes.
+struct Voxels : std::vector<uint32_t> {
+    static constexpr uint32_t UNKNOWN = 0xFFFFFFFFu;
+    mutable std::vector<uint64_t> mixed_blocks;  // bit (bz * half + by) * half + bx
+    mutable uint32_t mixed_count = UNKNOWN;
+
+    Voxels() = default;
+    Voxels(const Voxels&) = default;
+    Voxels(Voxels&&) = default;
+    Voxels& operator=(const Voxels&) = default;
+    Voxels& operator=(Voxels&&) = default;
+    Voxels& operator=(const std::vector<uint32_t>& v) {
+        std::vector<uint32_t>::operator=(v);
+        forget();
+        return *this;
+    }
+    Voxels& operator=(std::vector<uint32_t>&& v) {
+        std::vector<uint32_t>::operator=(std::move(v));
+        forget();
+        return *this;
+    }
+    void assign(size_t n, uint32_t v) {
+        std::vector<uint32_t>::assign(n, v);
+        forget();
+    }
+    template <class It>
+    void assign(It first, It last) {
+        std::vector<uint32_t>::assign(first, last);
+        forget();
+    }
+    void resize(size_t n) {
+        std::vector<uint32_t>::resize(n);
+        forget();
+    }
+    void forget() const { mixed_count = UNKNOWN; }
+};
+
 // src/octree/types.rs:40-52
 enum class BrickKind : uint8_t { Empty = 0, Parted = 1, Solid = 2 };
 struct Brick {
     BrickKind kind = BrickKind::Empty;
     uint32_t solid = 0;           // valid when kind == Solid
-    std::vector<uint32_t> data;   // valid when kind == Parted (dim^3, x fastest)
-    // build-time hints only (always re-verified, never change a result): an index that differed from data[0] /
-    // a 2x2x2 block that was non-uniform the last time the brick was scanned
+    Voxels data;                  // valid when kind == Parted (dim^3, x fastest)
+    // build-time hint only (always re-verified, never changes a result): an index that differed from data[0] the last
+    // time the brick was scanned
     mutable uint32_t witness = 0;
-    mutable uint32_t witness2 = 0xFFFFFFFFu;
     bool operator==(const Brick& o) const;
 };
 

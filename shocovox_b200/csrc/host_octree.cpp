@@ -86,6 +86,7 @@ int32_t HostOctree::create(uint32_t size, uint32_t brick_dim, HostOctree** out) 
     t->size_ = size;
     t->dim_ = brick_dim;
     t->vol_ = brick_dim * brick_dim * brick_dim;
+    t->block_words_ = std::max<uint32_t>(1u, (t->vol_ / 8u + 63u) / 64u);  // one bit per 2x2x2 block
     t->pool_push();  // the root is key 0 and starts as Nothing
     t->mip_defaults();
     *out = t;
@@ -150,17 +151,24 @@ uint32_t HostOctree::brick_alloc(uint32_t fill) {
         voxels_.resize(voxels_.size() + vol_);
         brick_rev_.push_back(revision_);
         witness_.push_back(0u);
-        witness2_.push_back(0xFFFFFFFFu);
+        block_count_.push_back(BLOCKS_UNKNOWN);
+        block_bits_.resize(block_bits_.size() + block_words_, 0ull);
     }
     std::fill_n(brick_mut(h), vol_, fill);
     witness_[h] = 0u;
-    witness2_[h] = 0xFFFFFFFFu;
+    // one value everywhere: every block is uniform
+    std::fill_n(block_bits_.begin() + (size_t)h * block_words_, block_words_, 0ull);
+    block_count_[h] = 0u;
     return h;
 }
 
 uint32_t HostOctree::brick_clone(uint32_t handle) {
     const uint32_t h = brick_alloc(NIL);
     std::memcpy(brick_mut(h), brick_data(handle), (size_t)vol_ * 4);
+    if (block_count_[handle] != BLOCKS_UNKNOWN) {  // the same voxels: the same blocks
+        std::copy_n(block_bits_.begin() + (size_t)handle * block_words_, block_words_, block_bits_.begin() + (size_t)h * block_words_);
+        block_count_[h] = block_count_[handle];
+    }
     return h;
 }
 
@@ -206,31 +214,62 @@ bool HostOctree::brick_homogeneous(const BrickRef& b, uint32_t* v) const {
 }
 
 // Is every aligned 2x2x2 block of the brick one value? (the test update/mod.rs:884-980 applies to Parted bricks when it
-// tries to express 8 bricks as one brick of half the resolution). Same answer as the reference's scan, amortised with
-// a witness: the flat index of a block corner that was found non-uniform last time.
-bool HostOctree::brick_blockwise_uniform(uint32_t handle) const {
+// tries to express 8 bricks as one brick of half the resolution - after EVERY insert that ends in a leaf). Same answer as
+// the reference's scan, from the brick's block map (host_octree.hpp: block_bits_): a scan per question cost 2 us per
+// voxel inserted into the 32^3 bricks of the blocky-terrain scene, most of its build time.
+namespace {
+inline bool block_is_uniform(const uint32_t* d, size_t bx, size_t by, size_t bz, uint32_t dim) {
+    const uint32_t* p = d + flat(2 * bx, 2 * by, 2 * bz, dim);
+    const size_t row = dim, plane = (size_t)dim * dim;
+    const uint32_t v = p[0];
+    return p[1] == v && p[row] == v && p[row + 1] == v && p[plane] == v && p[plane + 1] == v && p[plane + row] == v &&
+           p[plane + row + 1] == v;
+}
+}  // namespace
+
+void HostOctree::blocks_rebuild(uint32_t handle) const {
     const uint32_t* d = brick_data(handle);
     const size_t half = dim_ / 2;
-    auto block_uniform = [&](size_t x, size_t y, size_t z) {
-        const uint32_t v = d[flat(2 * x, 2 * y, 2 * z, dim_)];
-        for (size_t c = 1; c < 8; ++c)
-            if (d[flat(2 * x + (c & 1), 2 * y + ((c >> 1) & 1), 2 * z + (c >> 2), dim_)] != v) return false;
-        return true;
-    };
-    uint32_t& w = witness2_[handle];
-    if (w != 0xFFFFFFFFu) {
-        const size_t x = w % half, y = (w / half) % half, z = w / (half * half);
-        if (!block_uniform(x, y, z)) return false;
-    }
-    for (size_t x = 0; x < half; ++x)
-        for (size_t y = 0; y < half; ++y)
-            for (size_t z = 0; z < half; ++z)
-                if (!block_uniform(x, y, z)) {
-                    w = (uint32_t)(x + y * half + z * half * half);
-                    return false;
+    uint64_t* bits = block_bits_.data() + (size_t)handle * block_words_;
+    std::fill_n(bits, block_words_, 0ull);
+    uint32_t count = 0;
+    size_t i = 0;
+    for (size_t bz = 0; bz < half; ++bz)
+        for (size_t by = 0; by < half; ++by)
+            for (size_t bx = 0; bx < half; ++bx, ++i)
+                if (!block_is_uniform(d, bx, by, bz, dim_)) {
+                    bits[i >> 6] |= 1ull << (i & 63);
+                    ++count;
                 }
-    w = 0xFFFFFFFFu;
-    return true;
+    block_count_[handle] = count;
+}
+
+// voxels [lo, hi) of the brick were just written in place: re-examine the blocks they touch
+void HostOctree::blocks_update(uint32_t handle, const size_t lo[3], const size_t hi[3]) {
+    if (block_count_[handle] == BLOCKS_UNKNOWN) return;
+    const size_t half = dim_ / 2;
+    if (half == 0 || lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) return;
+    const uint32_t* d = brick_data(handle);
+    uint64_t* bits = block_bits_.data() + (size_t)handle * block_words_;
+    uint32_t count = block_count_[handle];
+    for (size_t bz = lo[2] / 2; bz <= (hi[2] - 1) / 2; ++bz)
+        for (size_t by = lo[1] / 2; by <= (hi[1] - 1) / 2; ++by)
+            for (size_t bx = lo[0] / 2; bx <= (hi[0] - 1) / 2; ++bx) {
+                const size_t i = (bz * half + by) * half + bx;
+                const uint64_t bit = 1ull << (i & 63);
+                const bool was = (bits[i >> 6] & bit) != 0, now = !block_is_uniform(d, bx, by, bz, dim_);
+                if (was != now) {
+                    bits[i >> 6] ^= bit;
+                    count += now ? 1u : 0xFFFFFFFFu;  // +1 / -1
+                }
+            }
+    block_count_[handle] = count;
+}
+
+bool HostOctree::brick_blockwise_uniform(uint32_t handle) const {
+    if (dim_ < 2) return true;  // no blocks to disagree (the reference's loops are empty)
+    if (block_count_[handle] == BLOCKS_UNKNOWN) blocks_rebuild(handle);
+    return block_count_[handle] == 0u;
 }
 
 // BrickData::simplify, src/octree/node.rs:316-331
@@ -491,16 +530,20 @@ void HostOctree::subdivide_leaf_to_nodes(size_t key, size_t target_octant) {
 // ------------------------------------------------------------------------------------------------------------
 // update_brick, src/octree/update/mod.rs:637-675
 // ------------------------------------------------------------------------------------------------------------
-size_t HostOctree::update_brick(bool overwrite, uint32_t* brick, const BoundsF& b, uint32_t x, uint32_t y, uint32_t z,
-                                uint32_t size, uint32_t data) const {
+size_t HostOctree::update_brick(bool overwrite, uint32_t handle, const BoundsF& b, uint32_t x, uint32_t y, uint32_t z,
+                                uint32_t size, uint32_t data) {
     size_t mi[3];
     matrix_index(b, x, y, z, dim_, mi);
     const size_t update_size = std::min<size_t>((size_t)dim_ - mi[0], size);
     const bool color_some = (data & 0xFFFFu) < NONE16, data_some = (data >> 16) != NONE16;
+    // written in place: the brick's revision moves, its block map is brought up to date below instead of being dropped
+    brick_rev_[handle] = revision_;
+    uint32_t* brick = voxels_.data() + (size_t)handle * vol_;
+    const size_t hi[3] = {std::min<size_t>(mi[0] + size, dim_), std::min<size_t>(mi[1] + size, dim_), std::min<size_t>(mi[2] + size, dim_)};
     // the same box of voxels as the reference's x / y / z loops (update/mod.rs:637-675), walked in memory order (x fastest)
-    for (size_t iz = mi[2]; iz < std::min<size_t>(mi[2] + size, dim_); ++iz)
-        for (size_t iy = mi[1]; iy < std::min<size_t>(mi[1] + size, dim_); ++iy)
-            for (size_t ix = mi[0]; ix < std::min<size_t>(mi[0] + size, dim_); ++ix) {
+    for (size_t iz = mi[2]; iz < hi[2]; ++iz)
+        for (size_t iy = mi[1]; iy < hi[1]; ++iy)
+            for (size_t ix = mi[0]; ix < hi[0]; ++ix) {
                 uint32_t& v = brick[flat(ix, iy, iz, dim_)];
                 if (overwrite) {
                     v = data;
@@ -509,6 +552,7 @@ size_t HostOctree::update_brick(bool overwrite, uint32_t* brick, const BoundsF& 
                     if (data_some) v = (v & 0x0000FFFFu) | (data & 0xFFFF0000u);
                 }
             }
+    blocks_update(handle, mi, hi);
     return update_size;
 }
 
@@ -521,7 +565,7 @@ size_t HostOctree::leaf_update(bool overwrite, size_t key, const BoundsF& node_b
         BrickRef& b = n.brick[octant];
         if (b.kind == BK_EMPTY) {
             const uint32_t h = brick_alloc(NIL);
-            const size_t us = update_brick(overwrite, brick_mut(h), target_b, x, y, z, size, content);
+            const size_t us = update_brick(overwrite, h, target_b, x, y, z, size, content);
             BrickRef& nb = nodes_[key].brick[octant];
             nb.kind = BK_PARTED;
             nb.value = h;
@@ -531,7 +575,7 @@ size_t HostOctree::leaf_update(bool overwrite, size_t key, const BoundsF& node_b
             const uint32_t voxel = b.value;
             if ((content_empty && !value_is_empty(voxel)) || (!content_empty && voxel != content)) {
                 const uint32_t h = brick_alloc(voxel);
-                const size_t us = update_brick(overwrite, brick_mut(h), target_b, x, y, z, size, content);
+                const size_t us = update_brick(overwrite, h, target_b, x, y, z, size, content);
                 BrickRef& nb = nodes_[key].brick[octant];
                 nb.kind = BK_PARTED;
                 nb.value = h;
@@ -539,14 +583,14 @@ size_t HostOctree::leaf_update(bool overwrite, size_t key, const BoundsF& node_b
             }
             return 0;
         }
-        return update_brick(overwrite, brick_mut(b.value), target_b, x, y, z, size, content);
+        return update_brick(overwrite, b.value, target_b, x, y, z, size, content);
     }
     if (n.kind == NK_UNIFORM) {
         BrickRef& mat = n.brick[0];
         if (mat.kind == BK_EMPTY) {
             if (content_empty) return 0;  // the reference recurses forever here; insert() never reaches it (insert.rs:117)
             const uint32_t h = brick_alloc(NIL);
-            const size_t us = update_brick(overwrite, brick_mut(h), target_b, x, y, z, size, content);
+            const size_t us = update_brick(overwrite, h, target_b, x, y, z, size, content);
             NodeRec& m = nodes_[key];
             clear_content(key);
             m.kind = NK_LEAF;
@@ -576,17 +620,17 @@ size_t HostOctree::leaf_update(bool overwrite, size_t key, const BoundsF& node_b
         const uint32_t cur = brick_data(mat.value)[flat(mi[0], mi[1], mi[2], dim_)];
         if (dim_ > 1 && ((content_empty && value_is_empty(cur)) || (!content_empty && cur == content))) return 0;
         if (node_b.size <= (float)dim_ && dim_ > 1)
-            return update_brick(overwrite, brick_mut(mat.value), node_b, x, y, z, size, content);
+            return update_brick(overwrite, mat.value, node_b, x, y, z, size, content);
         // split the uniform leaf into 8 bricks
         uint32_t parts[8];
         size_t us = 0;
         const uint32_t src_handle = mat.value;
         if (dim_ == 1) {
             for (size_t o = 0; o < 8; ++o) parts[o] = brick_clone(src_handle);
-            us = update_brick(overwrite, brick_mut(parts[octant]), target_b, x, y, z, size, content);
+            us = update_brick(overwrite, parts[octant], target_b, x, y, z, size, content);
         } else {
             dilute(brick_data(src_handle), parts);
-            us = update_brick(overwrite, brick_mut(parts[octant]), target_b, x, y, z, size, content);
+            us = update_brick(overwrite, parts[octant], target_b, x, y, z, size, content);
         }
         clear_content(key);  // releases the source brick
         NodeRec& m = nodes_[key];

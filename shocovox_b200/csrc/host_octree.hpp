@@ -120,8 +120,9 @@ class HostOctree {
     uint32_t brick_alloc(uint32_t fill);
     uint32_t brick_clone(uint32_t handle);
     void brick_release(BrickRef& b);
-    uint32_t* brick_mut(uint32_t handle) {
+    uint32_t* brick_mut(uint32_t handle) {  // any writer: what is known about the brick's 2x2x2 blocks is dropped
         brick_rev_[handle] = revision_;
+        block_count_[handle] = BLOCKS_UNKNOWN;
         return voxels_.data() + (size_t)handle * vol_;
     }
     BrickRef brick_copy(const BrickRef& b);
@@ -136,8 +137,10 @@ class HostOctree {
     uint32_t add_to_palette(const svx_entry& e);
     size_t leaf_update(bool overwrite, size_t key, const BoundsF& node_b, const BoundsF& target_b, size_t octant,
                        uint32_t x, uint32_t y, uint32_t z, uint32_t size, uint32_t content);
-    size_t update_brick(bool overwrite, uint32_t* brick, const BoundsF& b, uint32_t x, uint32_t y, uint32_t z,
-                        uint32_t size, uint32_t data) const;
+    size_t update_brick(bool overwrite, uint32_t handle, const BoundsF& b, uint32_t x, uint32_t y, uint32_t z,
+                        uint32_t size, uint32_t data);
+    void blocks_rebuild(uint32_t handle) const;
+    void blocks_update(uint32_t handle, const size_t lo[3], const size_t hi[3]);
     void subdivide_leaf_to_nodes(size_t key, size_t target_octant);
     void deallocate_children_of(size_t key);
     void store_occupied_bits(size_t key, uint64_t bits);
@@ -167,7 +170,14 @@ class HostOctree {
     std::vector<uint32_t> voxels_;
     std::vector<uint32_t> free_bricks_;
     std::vector<uint64_t> brick_rev_;  // per brick handle: revision_ of the mutation that last wrote it
-    mutable std::vector<uint32_t> witness2_;  // per brick: a 2x2x2 block known to be non-uniform (NIL = none known)
+    // Per brick: which aligned 2x2x2 blocks hold more than one value (one bit per block, index (bz * half + by) * half + bx)
+    // and how many do - what the "8 bricks as one brick of half the resolution" test of simplify asks for after every insert
+    // (brick_blockwise_uniform). Built on the first question, then kept exact by update_brick, the one in-place writer of the
+    // edit path; every other writer goes through brick_mut, which drops the map (BLOCKS_UNKNOWN).
+    static constexpr uint32_t BLOCKS_UNKNOWN = 0xFFFFFFFFu;
+    mutable std::vector<uint64_t> block_bits_;
+    mutable std::vector<uint32_t> block_count_;
+    uint32_t block_words_ = 1;
     mutable std::vector<uint32_t> witness_;  // per brick: a voxel index known to differ from voxel 0 (0 = none known)
     std::vector<svx_albedo> colors_;
     std::vector<uint32_t> datas_;
