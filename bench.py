@@ -231,9 +231,11 @@ def run_reference(args, rank: int):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "strong" if (args.gpus > 1 and args.mode != "poses") else "weak",
+        "scaling": "weak" if args.mode == "poses" else "strong",  # as our arm labels the same launch
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "resolution": list(res), "rays_per_step": rays,
+        # the workload is our arm's: one whole frame per step; this arm times a bounded sample of its rows (cpu_baseline.sample)
+        "config": {"workload": args.workload, "description": desc, "resolution": list(res), "rays_per_step": w * h,
+                   "rays_sampled_per_step": rays,
                    **({"mips": {"strategy": "MIPMapStrategy::default(), enabled", "viewing_distance": vd}} if args.mips is not None else {})},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

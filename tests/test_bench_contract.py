@@ -25,6 +25,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f32"
     assert line["steps"] == 3 and line["warmup"] >= 3 and line["value"] > 0 and line["ms_per_step"] > 0
     assert line["config"]["workload"] == "cpu_render_150" and "model" not in line["config"]
+    # the shared keys carry what our arm prints for the same launch: one whole frame per step, labelled like ours
+    assert line["config"]["rays_per_step"] == 150 * 150 and line["config"]["resolution"] == [150, 150] and line["scaling"] == "strong"
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
